@@ -1,0 +1,195 @@
+/* rz_b200.h — C ABI of the B200-native rusterize burn path (librz_b200.so).
+ *
+ * The reference (ttrotto/rusterize) has no C ABI: its seam is the Rust generic call
+ *     geoms.rasterize::<DenseArray<N> | SparseArray<N>>(RasterizeContext<N>)
+ * (rust/src/rasterize.rs:54-62, implemented by ArrayBuilder::build at :71-116 and :118-157).
+ * The entry points below are what an FFI shim for that seam binds (INTEGRATION.md shows the Rust
+ * `extern "C"` block and the ctypes stub).  Plain pointers and sizes only; no torch types.
+ *
+ * Error convention (rust/src/error.rs:4-14): every fallible call returns RZ_OK, RZ_VALUE_ERROR or
+ * RZ_RUNTIME_ERROR and writes the reference's message string into `err` (NUL-terminated, truncated
+ * to errlen).  There is no CPU fallback: compute entry points return RZ_RUNTIME_ERROR when no CUDA
+ * device is usable.
+ *
+ * Thread-safety: calls are re-entrant; the only shared state is a lazily created per-device
+ * context (stream, scratch arena) guarded by a mutex, so concurrent calls on one device serialise.
+ */
+#ifndef RZ_B200_H
+#define RZ_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RZ_OK 0
+#define RZ_VALUE_ERROR 1   /* RusterizeError::ValueError   */
+#define RZ_RUNTIME_ERROR 2 /* RusterizeError::RuntimeError */
+
+/* Output dtypes, in the order of python/src/rusterize.rs:171-182. */
+typedef enum {
+    RZ_U8 = 0, RZ_U16, RZ_U32, RZ_U64, RZ_I8, RZ_I16, RZ_I32, RZ_I64, RZ_F32, RZ_F64
+} rz_dtype;
+
+/* rust/src/rasterization/pixel_functions.rs:8-16 */
+typedef enum {
+    RZ_SUM = 0, RZ_FIRST, RZ_LAST, RZ_MIN, RZ_MAX, RZ_COUNT, RZ_ANY
+} rz_pixel_fn;
+
+/* rust/src/geo/raster.rs:10-20 (RasterInfo).  epsg < 0 means None. */
+typedef struct rz_raster_info {
+    uint64_t nrows, ncols;
+    double xmin, ymin, xmax, ymax;
+    double xres, yres;
+    int32_t epsg;
+    int32_t _pad;
+} rz_raster_info;
+
+/* python/src/geo/raster.rs:6-14 (RawRasterInfo) / rust/src/geo/raster.rs:36-42 (RasterInfoBuilder). */
+typedef struct rz_raw_raster_info {
+    int32_t has_shape;
+    int32_t has_extent;
+    int32_t has_resolution;
+    int32_t tap;
+    uint64_t nrows, ncols;     /* shape = [nrows, ncols] */
+    double extent[4];          /* xmin, ymin, xmax, ymax */
+    double xres, yres;
+    int32_t epsg;              /* < 0: None */
+    int32_t _pad;
+} rz_raw_raster_info;
+
+/* Opaque geometry set: the host-side flattening of &[geo::Geometry<f64>] into SoA vertex pools
+ * (polygon rings / line strings / points) plus a parts table, in pinned memory, with a cached
+ * device copy.  Replaces the Vec<Geometry<f64>> argument of Rasterize::rasterize. */
+typedef struct rz_geoms rz_geoms;
+
+/* Part kinds of the flattened form (rust/src/rasterization/burn_geometry.rs:24-210). */
+#define RZ_PART_POLYGON 0 /* Polygon / MultiPolygon / Rect / Triangle: all rings pooled (even-odd)   */
+#define RZ_PART_LINE 1    /* LineString / MultiLineString / Line: all segments pooled                 */
+#define RZ_PART_POINT 2   /* Point / MultiPoint                                                       */
+
+/* Zero-parse ingestion for callers that already hold coordinates (the FFI shim walks
+ * geo::Geometry and fills these; bench.py fills them from numpy).
+ *   geometry g  = parts  [geom_part_off[g], geom_part_off[g+1])      (burn order; >1 only for collections)
+ *   part p      = seqs   [part_seq_off[p],  part_seq_off[p+1])       (rings | line strings | one point run)
+ *   sequence s  = coords [seq_coord_off[s], seq_coord_off[s+1])
+ * Polygon rings must already be closed (geo_types::Polygon::new does that). */
+typedef struct rz_geom_soa {
+    uint64_t n_geoms, n_parts, n_seqs, n_coords;
+    const uint64_t* geom_part_off; /* [n_geoms+1] */
+    const uint8_t* part_kind;      /* [n_parts]   */
+    const uint64_t* part_seq_off;  /* [n_parts+1] */
+    const uint64_t* seq_coord_off; /* [n_seqs+1]  */
+    const double* x;               /* [n_coords] world coordinates */
+    const double* y;
+} rz_geom_soa;
+
+/* python/src/geo/parse_geometry.rs:109-121 (parse_sequence_wkb): ISO/EWKB, 2-D used, geometries with
+ * no geo_types equivalent (POINT EMPTY) are dropped.  NULL + err on malformed input. */
+rz_geoms* rz_geoms_from_wkb(const uint8_t* const* bufs, const uint64_t* lens, uint64_t n, char* err, size_t errlen);
+/* python/src/geo/parse_geometry.rs:123-134 (parse_sequence_wkt) */
+rz_geoms* rz_geoms_from_wkt(const char* const* strs, uint64_t n, char* err, size_t errlen);
+rz_geoms* rz_geoms_from_soa(const rz_geom_soa* soa, char* err, size_t errlen);
+uint64_t rz_geoms_len(const rz_geoms* g);     /* geometries kept */
+uint64_t rz_geoms_n_parts(const rz_geoms* g);
+uint64_t rz_geoms_n_coords(const rz_geoms* g);
+/* union of geo::BoundingRect (rust/src/geo/raster.rs:75-86); RZ_RUNTIME_ERROR when empty */
+int rz_geoms_bounds(const rz_geoms* g, double out_xmin_ymin_xmax_ymax[4]);
+/* Copy the flattened pools to `device` now (otherwise done lazily by the first rasterize call). */
+int rz_geoms_upload(rz_geoms* g, int device, char* err, size_t errlen);
+/* Drop cached device copies so the next call pays the host->device transfer again. */
+void rz_geoms_evict(rz_geoms* g);
+void rz_geoms_free(rz_geoms* g);
+
+/* Introspection of the flattened form (tests, FFI debugging). Returned pointers live as long as g. */
+const uint8_t* rz_geoms_part_kind(const rz_geoms* g);
+const uint64_t* rz_geoms_part_geom(const rz_geoms* g);
+uint64_t rz_geoms_pool_len(const rz_geoms* g, int kind);
+const double* rz_geoms_pool_x(const rz_geoms* g, int kind);
+const double* rz_geoms_pool_y(const rz_geoms* g, int kind);
+const uint32_t* rz_geoms_pool_tag(const rz_geoms* g, int kind);
+
+/* rust/src/geo/raster.rs:50-156 (RasterInfoBuilder::build / build_with / finalize), same messages.
+ * `g` may be NULL when raw->has_extent. */
+int rz_raster_info_build(const rz_raw_raster_info* raw, const rz_geoms* g, rz_raster_info* out, char* err,
+                         size_t errlen);
+
+/* rust/src/rasterize.rs:199-205 (group_keys): bands are the distinct keys in byte-lexicographic
+ * order.  Writes band_of_geom[n] and band_first[b] = first geometry index carrying band b's key.
+ * Returns the number of bands. */
+int64_t rz_group_keys(const char* const* keys, uint64_t n, int32_t* band_of_geom, uint64_t* band_first);
+
+/* rust/src/prelude.rs:92-106 (RasterizeContext<N>) + execution controls that only exist here. */
+typedef struct rz_context {
+    rz_raster_info raster_info;
+    int32_t dtype;    /* rz_dtype */
+    int32_t pixel_fn; /* rz_pixel_fn */
+    /* FieldSource (rust/src/rasterize.rs:24-31): one value of dtype, or field_len values */
+    const void* field;
+    int32_t field_is_scalar;
+    int32_t all_touched;
+    uint64_t field_len;
+    const uint8_t* field_valid; /* nullable; 0 = null field => geometry skipped (rasterize.rs:187-192) */
+    /* `by` after rz_group_keys; NULL => single band "band_1" */
+    const int32_t* band_of_geom;
+    uint64_t by_len;
+    int32_t n_bands;
+    int32_t device;         /* CUDA device ordinal */
+    const void* background; /* one value of dtype */
+    /* Row-band shard: only raster rows [row_begin, row_end) of every band are produced and `out`
+     * is [n_bands][row_end-row_begin][ncols].  0,0 = all rows.  (north_star: row-band sharding.) */
+    uint64_t row_begin, row_end;
+    void* stream;           /* cudaStream_t to run on; NULL = the library's own per-device stream */
+    uint32_t flags;
+    uint32_t tile_bytes;    /* bytes of one shared-memory row tile per warp; 0 = default (4096) */
+} rz_context;
+
+#define RZ_FLAG_OUT_ON_DEVICE 1u   /* `out` is device memory (no D2H) */
+#define RZ_FLAG_FORCE_H2D 2u       /* re-upload geometry even if a device copy is cached */
+#define RZ_FLAG_SYNC_STAGES 4u     /* record per-stage CUDA-event timings into rz_stats */
+
+typedef struct rz_stats {
+    uint64_t n_parts, n_poly_vertices, n_line_vertices, n_points;
+    uint64_t n_records;        /* sort keys emitted (polygon crossings incl. tile replicas + line/point pixels) */
+    uint64_t n_crossings;      /* polygon scanline crossings (X) */
+    uint64_t n_tasks;          /* (band,row,column-tile) fill tasks */
+    uint32_t key_bits, sort_passes, tile_width, n_windows;
+    float h2d_ms, count_ms, emit_ms, sort_ms, index_ms, fill_ms, d2h_ms, total_ms;
+    uint64_t h2d_bytes, d2h_bytes;
+    uint64_t out_bytes;        /* B * rows * C * sizeof(dtype) */
+    uint32_t kernel_launches;
+    uint32_t _pad;
+} rz_stats;
+
+/* DenseArray::build (rust/src/rasterize.rs:71-116): out is [n_bands][rows][ncols] of ctx->dtype,
+ * C-contiguous, host memory unless RZ_FLAG_OUT_ON_DEVICE. */
+int rz_rasterize_dense(rz_geoms* g, const rz_context* ctx, void* out, rz_stats* stats, char* err, size_t errlen);
+
+/* SparseArray::build (rust/src/rasterize.rs:118-157): every (row, col, value) write, per band, in
+ * burn order (rust/src/encoding/writers.rs:86-131). */
+typedef struct rz_sparse rz_sparse;
+int rz_rasterize_sparse(rz_geoms* g, const rz_context* ctx, rz_sparse** out, rz_stats* stats, char* err,
+                        size_t errlen);
+uint64_t rz_sparse_len(const rz_sparse* s);
+uint64_t rz_sparse_n_bands(const rz_sparse* s);
+const uint64_t* rz_sparse_rows(const rz_sparse* s);   /* [len] */
+const uint64_t* rz_sparse_cols(const rz_sparse* s);   /* [len] */
+const void* rz_sparse_data(const rz_sparse* s);       /* [len] of dtype */
+const uint64_t* rz_sparse_counts(const rz_sparse* s); /* [n_bands] per-band triplet counts ("offsets") */
+void rz_sparse_free(rz_sparse* s);
+/* SparseArray::build_array (rust/src/encoding/arrays.rs:103-143): replay triplets through the pixel
+ * function on the GPU.  rows/cols/data/counts are host arrays; out as in rz_rasterize_dense. */
+int rz_sparse_build_array(const rz_context* ctx, uint64_t n_bands, const uint64_t* counts, const uint64_t* rows,
+                          const uint64_t* cols, const void* data, void* out, rz_stats* stats, char* err,
+                          size_t errlen);
+
+/* Device plumbing */
+int rz_device_count(void);
+const char* rz_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RZ_B200_H */

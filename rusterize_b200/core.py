@@ -1,0 +1,229 @@
+"""Typed Python layer directly above the C ABI (include/rz_b200.h): geometry handles, grid math,
+band grouping and the dense / sparse burn calls.  Mirrors the reference's core crate surface
+(`Rasterize::rasterize::<DenseArray<N> | SparseArray<N>>(RasterizeContext<N>)`,
+rust/src/rasterize.rs:54-62; `RasterInfoBuilder`, rust/src/geo/raster.rs:36-181)."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import DTYPES, FUNS, Context, GeomSoA, RasterInfo, RawRasterInfo, Stats, errbuf, lib, ptr, raise_for
+
+
+class Geoms:
+    """A parsed + flattened geometry set (the `&[geo::Geometry<f64>]` argument of the reference)."""
+
+    def __init__(self, handle: int):
+        if not handle:
+            raise RuntimeError("null rz_geoms handle")
+        self._h = handle
+
+    # -- constructors --------------------------------------------------------------------------
+    @classmethod
+    def from_wkb(cls, wkbs) -> "Geoms":
+        L = lib()
+        n = len(wkbs)
+        bufs = [bytes(b) for b in wkbs]
+        arr = (C.c_char_p * n)(*bufs)
+        lens = (C.c_uint64 * n)(*[len(b) for b in bufs])
+        err = errbuf()
+        h = L.rz_geoms_from_wkb(arr, lens, n, err, len(err))
+        if not h:
+            msg = err.value.decode()
+            # parse failures are panics in the reference; an all-dropped input is a ValueError
+            raise (ValueError if msg.startswith("Could not parse") else RuntimeError)(msg)
+        return cls(h)
+
+    @classmethod
+    def from_wkt(cls, wkts) -> "Geoms":
+        L = lib()
+        n = len(wkts)
+        arr = (C.c_char_p * n)(*[s.encode() for s in wkts])
+        err = errbuf()
+        h = L.rz_geoms_from_wkt(arr, n, err, len(err))
+        if not h:
+            msg = err.value.decode()
+            raise (ValueError if msg.startswith("Could not parse") else RuntimeError)(msg)
+        return cls(h)
+
+    @classmethod
+    def from_any(cls, geoms) -> "Geoms":
+        """list / ndarray of WKT str or WKB bytes (python/src/geo/parse_geometry.rs:46-63)."""
+        if len(geoms) == 0:
+            raise ValueError("No geometries found.")
+        first = geoms[0]
+        if isinstance(first, (bytes, bytearray, memoryview, np.bytes_)):
+            return cls.from_wkb(geoms)
+        if isinstance(first, str):
+            return cls.from_wkt([str(s) for s in geoms])
+        raise ValueError("Sequence must contain geometries as shapely Geometry, bytes (WKB), or string (WKT).")
+
+    @classmethod
+    def from_soa(cls, geom_part_off, part_kind, part_seq_off, seq_coord_off, x, y) -> "Geoms":
+        a = [np.ascontiguousarray(geom_part_off, np.uint64), np.ascontiguousarray(part_kind, np.uint8),
+             np.ascontiguousarray(part_seq_off, np.uint64), np.ascontiguousarray(seq_coord_off, np.uint64),
+             np.ascontiguousarray(x, np.float64), np.ascontiguousarray(y, np.float64)]
+        soa = GeomSoA(len(a[0]) - 1, len(a[1]), len(a[3]) - 1, len(a[4]), *[v.ctypes.data for v in a])
+        err = errbuf()
+        h = lib().rz_geoms_from_soa(C.byref(soa), err, len(err))
+        if not h:
+            raise RuntimeError(err.value.decode())
+        return cls(h)
+
+    @classmethod
+    def from_polygons(cls, x, y, ring_off) -> "Geoms":
+        """G single-ring polygons: polygon i = coords[ring_off[i]:ring_off[i+1]] (closed if needed)."""
+        ring_off = np.ascontiguousarray(ring_off, np.uint64)
+        g = len(ring_off) - 1
+        idx = np.arange(g + 1, dtype=np.uint64)
+        return cls.from_soa(idx, np.zeros(g, np.uint8), idx, ring_off, x, y)
+
+    # -- accessors -----------------------------------------------------------------------------
+    def __len__(self) -> int:
+        return lib().rz_geoms_len(self._h)
+
+    @property
+    def n_parts(self) -> int:
+        return lib().rz_geoms_n_parts(self._h)
+
+    @property
+    def n_coords(self) -> int:
+        return lib().rz_geoms_n_coords(self._h)
+
+    def bounds(self):
+        b = (C.c_double * 4)()
+        if lib().rz_geoms_bounds(self._h, b) != 0:
+            return None
+        return tuple(b)
+
+    def upload(self, device: int = 0) -> None:
+        err = errbuf()
+        raise_for(lib().rz_geoms_upload(self._h, device, err, len(err)), err)
+
+    def evict(self) -> None:
+        lib().rz_geoms_evict(self._h)
+
+    def parts(self):
+        """(part_kind[u8], part_geom[u64]) of the flattened form."""
+        L, n = lib(), self.n_parts
+        if n == 0:
+            return np.empty(0, np.uint8), np.empty(0, np.uint64)
+        kind = np.ctypeslib.as_array(C.cast(L.rz_geoms_part_kind(self._h), C.POINTER(C.c_uint8)), (n,)).copy()
+        geom = np.ctypeslib.as_array(C.cast(L.rz_geoms_part_geom(self._h), C.POINTER(C.c_uint64)), (n,)).copy()
+        return kind, geom
+
+    def pool(self, kind: int):
+        """(x, y, tag) of one vertex pool (0 polygon rings, 1 line strings, 2 points)."""
+        L = lib()
+        n = L.rz_geoms_pool_len(self._h, kind)
+        if n == 0:
+            return np.empty(0), np.empty(0), np.empty(0, np.uint32)
+        x = np.ctypeslib.as_array(C.cast(L.rz_geoms_pool_x(self._h, kind), C.POINTER(C.c_double)), (n,)).copy()
+        y = np.ctypeslib.as_array(C.cast(L.rz_geoms_pool_y(self._h, kind), C.POINTER(C.c_double)), (n,)).copy()
+        t = np.ctypeslib.as_array(C.cast(L.rz_geoms_pool_tag(self._h, kind), C.POINTER(C.c_uint32)), (n,)).copy()
+        return x, y, t
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h and _lib._lib is not None:
+            _lib._lib.rz_geoms_free(h)
+
+
+def raster_info(geoms: Geoms | None, shape=None, extent=None, resolution=None, tap=False, epsg=None) -> RasterInfo:
+    """RasterInfoBuilder::{build, build_with} (rust/src/geo/raster.rs:50-156)."""
+    raw = RawRasterInfo()
+    raw.has_shape = int(shape is not None)
+    raw.has_extent = int(extent is not None)
+    raw.has_resolution = int(resolution is not None)
+    raw.tap = int(bool(tap))
+    if shape is not None:
+        raw.nrows, raw.ncols = int(shape[0]), int(shape[1])
+    if extent is not None:
+        raw.extent = (C.c_double * 4)(*[float(v) for v in extent])
+    if resolution is not None:
+        raw.xres, raw.yres = float(resolution[0]), float(resolution[1])
+    raw.epsg = -1 if epsg is None else int(epsg)
+    out = RasterInfo()
+    err = errbuf()
+    rc = lib().rz_raster_info_build(C.byref(raw), geoms._h if geoms is not None else None, C.byref(out), err, len(err))
+    raise_for(rc, err)
+    return out
+
+
+def group_keys(keys):
+    """group_keys (rust/src/rasterize.rs:199-205) -> (band_of_geom int32[n], sorted band names)."""
+    n = len(keys)
+    enc = [str(k).encode() for k in keys]
+    arr = (C.c_char_p * n)(*enc)
+    band = np.empty(n, np.int32)
+    first = np.empty(max(n, 1), np.uint64)
+    nb = lib().rz_group_keys(arr, n, band.ctypes.data, first.ctypes.data)
+    return band, [str(keys[int(i)]) for i in first[:nb]]
+
+
+def _context(geoms, ri, fun, dtype, field, field_valid, band_of_geom, n_bands, background, all_touched, device, rows,
+             stream, flags, tile_bytes):
+    dt = np.dtype(dtype)
+    if dt.name not in DTYPES:
+        raise ValueError("Unsupported dtype")
+    if fun not in FUNS:
+        raise ValueError("Unknown pixel function")  # python/src/rusterize.rs:149-151
+    with np.errstate(invalid="ignore", over="ignore"):
+        if np.ndim(field) == 0:
+            f = np.array([field]).astype(dt)
+            scalar, flen = 1, 0
+        else:
+            f = np.ascontiguousarray(np.asarray(field).astype(dt, copy=False))
+            scalar, flen = 0, len(f)
+        bg = np.array([background]).astype(dt)
+    fv = None if field_valid is None else np.ascontiguousarray(field_valid, np.uint8)
+    band = None if band_of_geom is None else np.ascontiguousarray(band_of_geom, np.int32)
+    ctx = Context()
+    ctx.raster_info = ri
+    ctx.dtype = DTYPES.index(dt.name)
+    ctx.pixel_fn = FUNS.index(fun)
+    ctx.field = f.ctypes.data
+    ctx.field_is_scalar = scalar
+    ctx.all_touched = int(bool(all_touched))
+    ctx.field_len = flen
+    ctx.field_valid = ptr(fv)
+    ctx.band_of_geom = ptr(band)
+    ctx.by_len = 0 if band is None else len(band)
+    ctx.n_bands = int(n_bands)
+    ctx.device = int(device)
+    ctx.background = bg.ctypes.data
+    ctx.row_begin, ctx.row_end = (0, 0) if rows is None else (int(rows[0]), int(rows[1]))
+    ctx.stream = stream
+    ctx.flags = int(flags)
+    ctx.tile_bytes = int(tile_bytes)
+    return ctx, dt, (f, bg, fv, band)
+
+
+def rasterize_dense(geoms: Geoms, ri: RasterInfo, fun="last", dtype="float64", field=1, field_valid=None,
+                    band_of_geom=None, n_bands=1, background=0, all_touched=False, out=None, device=0, rows=None,
+                    stream=None, flags=0, tile_bytes=0):
+    """DenseArray::build (rust/src/rasterize.rs:71-116) on the GPU.
+
+    `out`: None (a new numpy array is returned), a C-contiguous numpy array to fill, or an int
+    device pointer (then RZ_FLAG_OUT_ON_DEVICE is implied and nothing is copied back).
+    Returns (array_or_None, stats dict).  Shape [n_bands, rows, ncols]."""
+    ctx, dt, keep = _context(geoms, ri, fun, dtype, field, field_valid, band_of_geom, n_bands, background,
+                             all_touched, device, rows, stream, flags, tile_bytes)
+    nb = n_bands if band_of_geom is not None else 1
+    nrows = ri.nrows if rows is None else rows[1] - rows[0]
+    arr = None
+    if isinstance(out, (int, np.integer)):
+        ctx.flags |= _lib.FLAG_OUT_ON_DEVICE
+        out_ptr = int(out)
+    else:
+        arr = np.empty((nb, nrows, ri.ncols), dt) if out is None else out
+        if arr.dtype != dt or not arr.flags.c_contiguous or arr.size != nb * nrows * ri.ncols:
+            raise ValueError("`out` must be a C-contiguous array of the output dtype and shape")
+        out_ptr = arr.ctypes.data
+    st = Stats()
+    err = errbuf()
+    rc = lib().rz_rasterize_dense(geoms._h, C.byref(ctx), out_ptr, C.byref(st), err, len(err))
+    raise_for(rc, err)
+    return arr, st.as_dict()

@@ -1,0 +1,772 @@
+// rz_engine.cu — device context, pipeline orchestration and the C ABI of librz_b200.so.
+//
+// Replaces the slab  rust/src/rasterize.rs:71-196 (ArrayBuilder::build + process)
+//                  + rust/src/rasterization/*  + rust/src/encoding/writers.rs
+// of the reference with:  host flattening (rz_host.cpp) -> CUDA kernels (rz_kernels.cuh) -> copy-back.
+// There is no CPU fallback: without a usable CUDA device every compute entry point fails.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "rz_host.hpp"
+#include "rz_kernels.cuh"
+
+namespace rz {
+
+// ------------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------------
+struct Error {
+    int code;
+    std::string msg;
+};
+static void set_err(char* err, size_t n, const std::string& m) {
+    if (err && n) {
+        std::strncpy(err, m.c_str(), n - 1);
+        err[n - 1] = 0;
+    }
+}
+#define CUDA_TRY(expr)                                                                                   \
+    do {                                                                                                 \
+        cudaError_t _e = (expr);                                                                         \
+        if (_e != cudaSuccess) {                                                                         \
+            (void)cudaGetLastError();                                                                    \
+            throw Error{RZ_RUNTIME_ERROR, std::string("CUDA error: ") + cudaGetErrorString(_e) + " at " + \
+                                              __FILE__ + ":" + std::to_string(__LINE__)};              \
+        }                                                                                                \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// device memory
+// ------------------------------------------------------------------------------------------------
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    void ensure(size_t bytes) {
+        if (bytes <= cap) return;
+        if (p) CUDA_TRY(cudaFree(p));
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        if (cudaMalloc(&p, want) != cudaSuccess) {
+            (void)cudaGetLastError();
+            want = bytes;
+            CUDA_TRY(cudaMalloc(&p, want));
+        }
+        cap = want;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <typename T> T* as() { return reinterpret_cast<T*>(p); }
+};
+
+struct DeviceGeoms {
+    int dev = 0;
+    double* x[3] = {nullptr, nullptr, nullptr};
+    double* y[3] = {nullptr, nullptr, nullptr};
+    uint32_t* tag[3] = {nullptr, nullptr, nullptr};
+    uint8_t* part_kind = nullptr;
+    uint32_t* part_geom = nullptr;
+    double* part_xlo = nullptr;
+    double* part_xhi = nullptr;
+    size_t bytes = 0;
+    ~DeviceGeoms() {
+        cudaSetDevice(dev);
+        for (int k = 0; k < 3; k++) {
+            cudaFree(x[k]);
+            cudaFree(y[k]);
+            cudaFree(tag[k]);
+        }
+        cudaFree(part_kind);
+        cudaFree(part_geom);
+        cudaFree(part_xlo);
+        cudaFree(part_xhi);
+        (void)cudaGetLastError();
+    }
+};
+
+struct DeviceCtx {
+    int dev = 0;
+    std::mutex mu;
+    cudaStream_t stream = nullptr;
+    int sm_count = 148;
+    DevBuf keys_a, keys_b, hist, digit_total, task_start, part_info, field, valid, band, last_kept, counters, win_out;
+    Counters* h_counters = nullptr;  // pinned
+    cudaEvent_t ev[16];
+};
+
+static std::mutex g_ctx_mu;
+static std::map<int, std::unique_ptr<DeviceCtx>> g_ctx;
+
+static DeviceCtx& device_ctx(int dev) {
+    std::lock_guard<std::mutex> lk(g_ctx_mu);
+    auto it = g_ctx.find(dev);
+    if (it != g_ctx.end()) return *it->second;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+        (void)cudaGetLastError();
+        throw Error{RZ_RUNTIME_ERROR, "No CUDA device available: librz_b200 has no CPU fallback."};
+    }
+    if (dev < 0 || dev >= n) throw Error{RZ_RUNTIME_ERROR, "Invalid CUDA device ordinal."};
+    CUDA_TRY(cudaSetDevice(dev));
+    std::unique_ptr<DeviceCtx> c(new DeviceCtx());
+    c->dev = dev;
+    CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, dev));
+    CUDA_TRY(cudaHostAlloc((void**)&c->h_counters, sizeof(Counters), cudaHostAllocDefault));
+    for (auto& e : c->ev) CUDA_TRY(cudaEventCreate(&e));
+    DeviceCtx& ref = *c;
+    g_ctx[dev] = std::move(c);
+    return ref;
+}
+
+template <typename T> static void upload_vec(T** dst, const std::vector<T>& v, cudaStream_t s, size_t& bytes) {
+    *dst = nullptr;
+    if (v.empty()) return;
+    // one spare element so kernels may read index i+1 of the last vertex unconditionally
+    CUDA_TRY(cudaMalloc((void**)dst, (v.size() + 1) * sizeof(T)));
+    CUDA_TRY(cudaMemcpyAsync(*dst, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, s));
+    bytes += v.size() * sizeof(T);
+}
+
+static void pin_host(rz_geoms* g) {
+    if (g->pinned) return;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+        (void)cudaGetLastError();
+        return;
+    }
+    auto reg = [](const void* p, size_t bytes) {
+        if (bytes >= (1u << 16) && cudaHostRegister(const_cast<void*>(p), bytes, cudaHostRegisterDefault) != cudaSuccess)
+            (void)cudaGetLastError();
+    };
+    for (int k = 0; k < 3; k++) {
+        reg(g->pool[k].x.data(), g->pool[k].x.size() * 8);
+        reg(g->pool[k].y.data(), g->pool[k].y.size() * 8);
+        reg(g->pool[k].tag.data(), g->pool[k].tag.size() * 4);
+    }
+    g->pinned = true;
+}
+
+static void unpin_host(rz_geoms* g) {
+    if (!g->pinned) return;
+    auto unreg = [](const void* p, size_t bytes) {
+        if (bytes >= (1u << 16) && cudaHostUnregister(const_cast<void*>(p)) != cudaSuccess) (void)cudaGetLastError();
+    };
+    for (int k = 0; k < 3; k++) {
+        unreg(g->pool[k].x.data(), g->pool[k].x.size() * 8);
+        unreg(g->pool[k].y.data(), g->pool[k].y.size() * 8);
+        unreg(g->pool[k].tag.data(), g->pool[k].tag.size() * 4);
+    }
+    g->pinned = false;
+}
+
+static DeviceGeoms* geoms_on_device(rz_geoms* g, DeviceCtx& c, cudaStream_t s, bool force, size_t* h2d_bytes) {
+    std::lock_guard<std::mutex> lk(g->mu);
+    auto it = g->dev.find(c.dev);
+    if (it != g->dev.end() && !force) return it->second;
+    if (it != g->dev.end()) {
+        delete it->second;
+        g->dev.erase(it);
+    }
+    for (int k = 0; k < 3; k++)
+        if (g->pool[k].size() >= 0xfffffff0ull) throw Error{RZ_RUNTIME_ERROR, "Too many vertices (limit 2^32 per pool)."};
+    pin_host(g);
+    std::unique_ptr<DeviceGeoms> d(new DeviceGeoms());
+    d->dev = c.dev;
+    size_t bytes = 0;
+    for (int k = 0; k < 3; k++) {
+        upload_vec(&d->x[k], g->pool[k].x, s, bytes);
+        upload_vec(&d->y[k], g->pool[k].y, s, bytes);
+        upload_vec(&d->tag[k], g->pool[k].tag, s, bytes);
+    }
+    upload_vec(&d->part_kind, g->part_kind, s, bytes);
+    std::vector<uint32_t> pg(g->part_geom.begin(), g->part_geom.end());
+    upload_vec(&d->part_geom, pg, s, bytes);
+    upload_vec(&d->part_xlo, g->part_xlo, s, bytes);
+    upload_vec(&d->part_xhi, g->part_xhi, s, bytes);
+    CUDA_TRY(cudaStreamSynchronize(s));  // `pg` is a temporary
+    d->bytes = bytes;
+    if (h2d_bytes) *h2d_bytes += bytes;
+    DeviceGeoms* raw = d.release();
+    g->dev[c.dev] = raw;
+    return raw;
+}
+
+// ------------------------------------------------------------------------------------------------
+// fill dispatch: 10 dtypes x 7 pixel functions
+// ------------------------------------------------------------------------------------------------
+typedef void (*FillLaunch)(dim3, size_t, cudaStream_t, FillParams, const uint64_t*, const uint32_t*, const PartInfo*,
+                           const uint8_t*, uint64_t, void*);
+
+template <typename N, int FN>
+static void fill_launch(dim3 grid, size_t smem, cudaStream_t s, FillParams F, const uint64_t* keys,
+                        const uint32_t* task_start, const PartInfo* info, const uint8_t* kind, uint64_t bg, void* out) {
+    fill_kernel<N, FN><<<grid, FILL_WARPS * 32, smem, s>>>(F, keys, task_start, info, kind, bg, (N*)out);
+}
+
+template <typename N> static FillLaunch fill_for_fn(int fn) {
+    switch (fn) {
+        case RZ_SUM: return fill_launch<N, RZ_SUM>;
+        case RZ_FIRST: return fill_launch<N, RZ_FIRST>;
+        case RZ_LAST: return fill_launch<N, RZ_LAST>;
+        case RZ_MIN: return fill_launch<N, RZ_MIN>;
+        case RZ_MAX: return fill_launch<N, RZ_MAX>;
+        case RZ_COUNT: return fill_launch<N, RZ_COUNT>;
+        case RZ_ANY: return fill_launch<N, RZ_ANY>;
+    }
+    return nullptr;
+}
+
+static FillLaunch fill_for(int dtype, int fn) {
+    switch (dtype) {
+        case RZ_U8: return fill_for_fn<uint8_t>(fn);
+        case RZ_U16: return fill_for_fn<uint16_t>(fn);
+        case RZ_U32: return fill_for_fn<uint32_t>(fn);
+        case RZ_U64: return fill_for_fn<uint64_t>(fn);
+        case RZ_I8: return fill_for_fn<int8_t>(fn);
+        case RZ_I16: return fill_for_fn<int16_t>(fn);
+        case RZ_I32: return fill_for_fn<int32_t>(fn);
+        case RZ_I64: return fill_for_fn<int64_t>(fn);
+        case RZ_F32: return fill_for_fn<float>(fn);
+        case RZ_F64: return fill_for_fn<double>(fn);
+    }
+    return nullptr;
+}
+
+// ------------------------------------------------------------------------------------------------
+// the dense pipeline
+// ------------------------------------------------------------------------------------------------
+static uint32_t bits_for(uint64_t n_values) {  // bits needed to represent values 0 .. n_values-1
+    uint32_t b = 0;
+    while (b < 64 && (1ull << b) < n_values) b++;
+    return b;
+}
+
+struct Window {
+    uint32_t r0, r1;
+};
+
+struct Timer {
+    DeviceCtx& c;
+    cudaStream_t s;
+    int next = 0;
+    Timer(DeviceCtx& c_, cudaStream_t s_) : c(c_), s(s_) {}
+};
+
+static const uint64_t MAX_WINDOW_RECORDS = 1ull << 30;      // 16 GiB of ping-pong key buffers
+static const uint64_t MAX_WINDOW_OUT_BYTES = 12ull << 30;  // staging buffer when `out` is host memory
+
+static void rasterize_dense(rz_geoms* g, const rz_context* ctx, void* out, rz_stats* st) {
+    const rz_raster_info& ri = ctx->raster_info;
+    // rust/src/rasterize.rs:208-229
+    if (!ctx->field_is_scalar && ctx->field_len != g->n_geoms)
+        throw Error{RZ_VALUE_ERROR, "Geometry and field lengths must match"};
+    if (ctx->band_of_geom && ctx->by_len != g->n_geoms)
+        throw Error{RZ_VALUE_ERROR, "Geometry and by lengths must match"};
+    const size_t isz = dtype_size(ctx->dtype);
+    if (!isz) throw Error{RZ_VALUE_ERROR, "Unsupported dtype"};
+    if (ctx->pixel_fn < 0 || ctx->pixel_fn > RZ_ANY) throw Error{RZ_VALUE_ERROR, "Unknown pixel function"};
+    if (ctx->all_touched)
+        throw Error{RZ_RUNTIME_ERROR, "all_touched=True is not implemented on the B200 path yet."};
+    if (ri.nrows == 0 || ri.ncols == 0) return;
+    if (ri.nrows >= (1ull << 31) || ri.ncols >= (1ull << 31))
+        throw Error{RZ_RUNTIME_ERROR, "Raster dimensions above 2^31 are not supported."};
+    const uint32_t n_bands = ctx->band_of_geom ? (uint32_t)std::max(ctx->n_bands, 0) : 1u;
+    if (n_bands == 0) return;
+    uint32_t shard_r0 = (uint32_t)ctx->row_begin, shard_r1 = (uint32_t)ctx->row_end;
+    if (ctx->row_begin == 0 && ctx->row_end == 0) shard_r1 = (uint32_t)ri.nrows;
+    if (shard_r1 > ri.nrows || shard_r0 >= shard_r1) throw Error{RZ_VALUE_ERROR, "Invalid row shard"};
+    const uint32_t shard_rows = shard_r1 - shard_r0;
+    const bool out_dev = (ctx->flags & RZ_FLAG_OUT_ON_DEVICE) != 0;
+
+    DeviceCtx& c = device_ctx(ctx->device);
+    std::lock_guard<std::mutex> lk(c.mu);
+    CUDA_TRY(cudaSetDevice(c.dev));
+    cudaStream_t s = ctx->stream ? (cudaStream_t)ctx->stream : c.stream;
+    rz_stats S;
+    std::memset(&S, 0, sizeof S);
+    enum { EV_START, EV_H2D, EV_A, EV_B, EV_END };
+    CUDA_TRY(cudaEventRecord(c.ev[EV_START], s));
+
+    // ---- inputs to the device ------------------------------------------------------------------
+    size_t h2d = 0;
+    DeviceGeoms* dg = geoms_on_device(g, c, s, (ctx->flags & RZ_FLAG_FORCE_H2D) != 0, &h2d);
+    const uint32_t n_parts = (uint32_t)g->part_kind.size();
+    const size_t n_field = ctx->field_is_scalar ? 1 : (size_t)g->n_geoms;
+    c.field.ensure(std::max<size_t>(n_field * isz, 8));
+    if (n_field) CUDA_TRY(cudaMemcpyAsync(c.field.p, ctx->field, n_field * isz, cudaMemcpyHostToDevice, s));
+    h2d += n_field * isz;
+    const uint8_t* d_valid = nullptr;
+    if (ctx->field_valid && g->n_geoms) {
+        c.valid.ensure(g->n_geoms);
+        CUDA_TRY(cudaMemcpyAsync(c.valid.p, ctx->field_valid, g->n_geoms, cudaMemcpyHostToDevice, s));
+        d_valid = c.valid.as<uint8_t>();
+        h2d += g->n_geoms;
+    }
+    const int32_t* d_band = nullptr;
+    if (ctx->band_of_geom && g->n_geoms) {
+        c.band.ensure(g->n_geoms * 4);
+        CUDA_TRY(cudaMemcpyAsync(c.band.p, ctx->band_of_geom, g->n_geoms * 4, cudaMemcpyHostToDevice, s));
+        d_band = c.band.as<int32_t>();
+        h2d += g->n_geoms * 4;
+    }
+    CUDA_TRY(cudaEventRecord(c.ev[EV_H2D], s));
+    S.h2d_bytes = h2d;
+
+    // ---- tiling and key layout -----------------------------------------------------------------
+    uint32_t tile_bytes = ctx->tile_bytes ? ctx->tile_bytes : 4096u;
+    uint32_t tile_w = 1;
+    while ((uint64_t)tile_w * 2 * isz <= tile_bytes) tile_w *= 2;
+    while (tile_w / 2 >= ri.ncols && tile_w > 1) tile_w /= 2;               // no wider than the raster needs
+    while ((ri.ncols + tile_w - 1) / tile_w > 65535u) tile_w *= 2;          // PartInfo keeps tiles in 16 bits
+    uint32_t tile_shift = bits_for(tile_w);
+    const uint32_t n_tiles = (uint32_t)((ri.ncols + tile_w - 1) / tile_w);
+    if ((size_t)tile_w * isz * FILL_WARPS > 200u * 1024u) throw Error{RZ_RUNTIME_ERROR, "tile_bytes too large"};
+
+    KParams P;
+    std::memset(&P, 0, sizeof P);
+    P.xmin = ri.xmin;
+    P.ymax = ri.ymax;
+    P.xres = ri.xres;
+    P.yres = ri.yres;
+    P.nrows = (uint32_t)ri.nrows;
+    P.ncols = (uint32_t)ri.ncols;
+    P.nrows_f = (double)ri.nrows;
+    P.ncols_f = (double)ri.ncols;
+    P.tile_w = tile_w;
+    P.tile_shift = tile_shift;
+    P.n_tiles = n_tiles;
+    P.col_bits = tile_shift + 1;  // relative columns 0 .. tile_w inclusive
+    P.part_bits = std::max(1u, bits_for(std::max<uint64_t>(n_parts, 1)));
+    P.part_shift = P.col_bits;
+    P.task_shift = P.col_bits + P.part_bits;
+    P.n_bands = n_bands;
+    P.dedup_lines = ri.xres != ri.yres;
+    P.n_parts = n_parts;
+    S.n_parts = n_parts;
+    S.n_poly_vertices = g->pool[0].size();
+    S.n_line_vertices = g->pool[1].size();
+    S.n_points = g->pool[2].size();
+    S.tile_width = tile_w;
+    S.out_bytes = (uint64_t)n_bands * shard_rows * ri.ncols * isz;
+
+    uint64_t bg_bits = 0;
+    std::memcpy(&bg_bits, ctx->background, isz);
+
+    // ---- per-part resolution -------------------------------------------------------------------
+    c.part_info.ensure(std::max<size_t>((size_t)n_parts * sizeof(PartInfo), 16));
+    c.last_kept.ensure(std::max<size_t>((size_t)n_parts * 4, 16));
+    c.counters.ensure(sizeof(Counters));
+    uint32_t launches = 0;
+    if (n_parts) {
+        part_prepare_kernel<<<(n_parts + 255) / 256, 256, 0, s>>>(
+            P, dg->part_kind, dg->part_geom, dg->part_xlo, dg->part_xhi, c.field.as<uint8_t>(), (uint32_t)isz,
+            ctx->field_is_scalar, d_valid, d_band, c.part_info.as<PartInfo>());
+        launches++;
+    }
+    const PartInfo* d_info = c.part_info.as<PartInfo>();
+    Counters* d_ctr = c.counters.as<Counters>();
+
+    // ---- windows ---------------------------------------------------------------------------------
+    // Rows are processed in windows so that (a) the key fits 64 bits, (b) the record buffers and the
+    // staging buffer stay bounded.  Windows that turn out too heavy are halved.
+    auto window_fits = [&](uint32_t rows) {
+        uint64_t tasks = (uint64_t)n_bands * rows * n_tiles;
+        if (tasks >= (1ull << 31)) return false;
+        if (bits_for(tasks) + P.task_shift > 64) return false;
+        if (!out_dev && (uint64_t)n_bands * rows * ri.ncols * isz > MAX_WINDOW_OUT_BYTES && rows > 1) return false;
+        return true;
+    };
+    uint32_t win_rows = shard_rows;
+    while (!window_fits(win_rows)) {
+        if (win_rows == 1) throw Error{RZ_RUNTIME_ERROR, "Problem too large for the 64-bit record key."};
+        win_rows = (win_rows + 1) / 2;
+    }
+    std::vector<Window> todo;
+    for (uint32_t r = shard_r0; r < shard_r1; r += win_rows) todo.push_back(Window{r, std::min(r + win_rows, shard_r1)});
+    std::reverse(todo.begin(), todo.end());  // pop_back walks top to bottom
+
+    FillLaunch fill = fill_for(ctx->dtype, ctx->pixel_fn);
+    float count_ms = 0, emit_ms = 0, sort_ms = 0, index_ms = 0, fill_ms = 0, d2h_ms = 0;
+    const bool timed = (ctx->flags & RZ_FLAG_SYNC_STAGES) != 0;
+    auto lap = [&](float& acc, int ea, int eb) {
+        if (!timed) return;
+        CUDA_TRY(cudaEventSynchronize(c.ev[eb]));
+        float ms = 0;
+        CUDA_TRY(cudaEventElapsedTime(&ms, c.ev[ea], c.ev[eb]));
+        acc += ms;
+    };
+    const uint32_t nv_poly = (uint32_t)g->pool[0].size(), nv_line = (uint32_t)g->pool[1].size(),
+                   nv_pt = (uint32_t)g->pool[2].size();
+    const uint32_t per_block = SETUP_THREADS * SETUP_ITEMS;
+
+    while (!todo.empty()) {
+        Window w = todo.back();
+        todo.pop_back();
+        P.win_r0 = w.r0;
+        P.win_r1 = w.r1;
+        const uint32_t rows = w.r1 - w.r0;
+
+        // ---- count --------------------------------------------------------------------------
+        if (timed) CUDA_TRY(cudaEventRecord(c.ev[EV_A], s));
+        CUDA_TRY(cudaMemsetAsync(d_ctr, 0, sizeof(Counters), s));
+        if (nv_poly) {
+            poly_count_kernel<<<(nv_poly + per_block - 1) / per_block, SETUP_THREADS, 0, s>>>(
+                P, dg->x[0], dg->y[0], dg->tag[0], nv_poly, d_info, d_ctr);
+            launches++;
+        }
+        if (nv_line) {
+            CUDA_TRY(cudaMemsetAsync(c.last_kept.p, 0, (size_t)n_parts * 4, s));
+            line_count_kernel<<<(nv_line + per_block - 1) / per_block, SETUP_THREADS, 0, s>>>(
+                P, dg->x[1], dg->y[1], dg->tag[1], nv_line, d_info, c.last_kept.as<uint32_t>(), d_ctr);
+            line_final_kernel<<<(n_parts + 255) / 256, 256, 0, s>>>(P, dg->x[1], dg->y[1], dg->tag[1], dg->part_kind,
+                                                                     d_info, c.last_kept.as<uint32_t>(), d_ctr,
+                                                                     nullptr, 0);
+            launches += 2;
+        }
+        if (nv_pt) {
+            point_kernel<<<(nv_pt + 255) / 256, 256, 0, s>>>(P, dg->x[2], dg->y[2], dg->tag[2], nv_pt, d_info, d_ctr,
+                                                             nullptr, 0);
+            launches++;
+        }
+        CUDA_TRY(cudaMemcpyAsync(c.h_counters, d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, s));
+        if (timed) CUDA_TRY(cudaEventRecord(c.ev[EV_B], s));
+        CUDA_TRY(cudaStreamSynchronize(s));
+        lap(count_ms, EV_A, EV_B);
+        if (c.h_counters->bad_line)
+            throw Error{RZ_RUNTIME_ERROR,
+                        "A line segment extends more than 2^29 pixels from the raster origin; unsupported."};
+        const uint64_t n_rec = c.h_counters->records;
+        if (n_rec > MAX_WINDOW_RECORDS && rows > 1) {  // too heavy: halve and retry
+            uint32_t mid = w.r0 + rows / 2;
+            todo.push_back(Window{mid, w.r1});
+            todo.push_back(Window{w.r0, mid});
+            continue;
+        }
+        if (n_rec >= (1ull << 32) - 4096) throw Error{RZ_RUNTIME_ERROR, "Too many records in a single raster row."};
+        S.n_records += n_rec;
+        S.n_crossings += c.h_counters->crossings;
+        S.n_windows++;
+        const uint32_t n = (uint32_t)n_rec;
+        const uint32_t n_tasks = n_bands * rows * n_tiles;
+        S.n_tasks += n_tasks;
+        const uint32_t key_bits = P.task_shift + bits_for(n_tasks);
+        S.key_bits = std::max(S.key_bits, key_bits);
+
+        // ---- emit ---------------------------------------------------------------------------
+        if (timed) CUDA_TRY(cudaEventRecord(c.ev[EV_A], s));
+        c.keys_a.ensure(std::max<size_t>((size_t)n * 8, 64));
+        c.keys_b.ensure(std::max<size_t>((size_t)n * 8, 64));
+        uint64_t* ka = c.keys_a.as<uint64_t>();
+        uint64_t* kb = c.keys_b.as<uint64_t>();
+        if (n) {
+            if (nv_poly) {
+                poly_emit_kernel<<<(nv_poly + per_block - 1) / per_block, SETUP_THREADS, 0, s>>>(
+                    P, dg->x[0], dg->y[0], dg->tag[0], nv_poly, d_info, d_ctr, ka);
+                launches++;
+            }
+            if (nv_line) {
+                line_emit_kernel<<<(nv_line + per_block - 1) / per_block, SETUP_THREADS, 0, s>>>(
+                    P, dg->x[1], dg->y[1], dg->tag[1], nv_line, d_info, d_ctr, ka);
+                line_final_kernel<<<(n_parts + 255) / 256, 256, 0, s>>>(P, dg->x[1], dg->y[1], dg->tag[1],
+                                                                         dg->part_kind, d_info,
+                                                                         c.last_kept.as<uint32_t>(), d_ctr, ka, 1);
+                launches += 2;
+            }
+            if (nv_pt) {
+                point_kernel<<<(nv_pt + 255) / 256, 256, 0, s>>>(P, dg->x[2], dg->y[2], dg->tag[2], nv_pt, d_info,
+                                                                 d_ctr, ka, 1);
+                launches++;
+            }
+        }
+        if (timed) CUDA_TRY(cudaEventRecord(c.ev[EV_B], s));
+        lap(emit_ms, EV_A, EV_B);
+
+        // ---- sort ---------------------------------------------------------------------------
+        if (timed) CUDA_TRY(cudaEventRecord(c.ev[EV_A], s));
+        if (n > 1) {
+            const uint32_t n_blocks = (n + RS_TILE - 1) / RS_TILE;
+            c.hist.ensure((size_t)n_blocks * RS_RADIX * 4);
+            c.digit_total.ensure(RS_RADIX * 4);
+            for (uint32_t shift = 0; shift < key_bits; shift += 8) {
+                radix_hist_kernel<<<n_blocks, RS_THREADS, 0, s>>>(ka, n, shift, n_blocks, c.hist.as<uint32_t>());
+                radix_scan_rows_kernel<<<RS_RADIX, 1024, 0, s>>>(c.hist.as<uint32_t>(), n_blocks,
+                                                                c.digit_total.as<uint32_t>());
+                radix_scatter_kernel<<<n_blocks, RS_THREADS, 0, s>>>(ka, kb, n, shift, n_blocks,
+                                                                     c.hist.as<uint32_t>(),
+                                                                     c.digit_total.as<uint32_t>());
+                std::swap(ka, kb);
+                launches += 3;
+                S.sort_passes++;
+            }
+        }
+        if (timed) CUDA_TRY(cudaEventRecord(c.ev[EV_B], s));
+        lap(sort_ms, EV_A, EV_B);
+
+        // ---- task index ---------------------------------------------------------------------
+        if (timed) CUDA_TRY(cudaEventRecord(c.ev[EV_A], s));
+        c.task_start.ensure(((size_t)n_tasks + 1) * 4);
+        task_index_kernel<<<(n_tasks + 1 + 255) / 256, 256, 0, s>>>(ka, n, P.task_shift, n_tasks,
+                                                                    c.task_start.as<uint32_t>());
+        launches++;
+        if (timed) CUDA_TRY(cudaEventRecord(c.ev[EV_B], s));
+        lap(index_ms, EV_A, EV_B);
+
+        // ---- fill ---------------------------------------------------------------------------
+        if (timed) CUDA_TRY(cudaEventRecord(c.ev[EV_A], s));
+        FillParams F;
+        F.n_tasks = n_tasks;
+        F.n_tiles = n_tiles;
+        F.tile_w = tile_w;
+        F.ncols = (uint32_t)ri.ncols;
+        F.win_rows = rows;
+        F.col_bits = P.col_bits;
+        F.part_shift = P.part_shift;
+        F.part_bits = P.part_bits;
+        F.dedup_lines = P.dedup_lines;
+        void* d_out;
+        if (out_dev) {
+            d_out = out;
+            F.out_rows = shard_rows;
+            F.win_row_off = w.r0 - shard_r0;
+        } else {
+            c.win_out.ensure((size_t)n_bands * rows * ri.ncols * isz);
+            d_out = c.win_out.p;
+            F.out_rows = rows;
+            F.win_row_off = 0;
+        }
+        F.vec_ok = ((uintptr_t)d_out % 16 == 0) && ((ri.ncols * isz) % 16 == 0) && (((size_t)tile_w * isz) % 16 == 0);
+        const uint32_t grid = (n_tasks + FILL_WARPS - 1) / FILL_WARPS;
+        fill(dim3(grid), (size_t)FILL_WARPS * tile_w * isz, s, F, ka, c.task_start.as<uint32_t>(), d_info,
+             dg->part_kind, bg_bits, d_out);
+        launches++;
+        CUDA_TRY(cudaGetLastError());
+        if (timed) CUDA_TRY(cudaEventRecord(c.ev[EV_B], s));
+        lap(fill_ms, EV_A, EV_B);
+
+        // ---- copy back ----------------------------------------------------------------------
+        if (!out_dev) {
+            if (timed) CUDA_TRY(cudaEventRecord(c.ev[EV_A], s));
+            const size_t chunk = (size_t)rows * ri.ncols * isz;
+            for (uint32_t b = 0; b < n_bands; b++) {
+                char* dst = (char*)out + ((size_t)b * shard_rows + (w.r0 - shard_r0)) * ri.ncols * isz;
+                CUDA_TRY(cudaMemcpyAsync(dst, (char*)d_out + (size_t)b * chunk, chunk, cudaMemcpyDeviceToHost, s));
+            }
+            S.d2h_bytes += chunk * n_bands;
+            if (timed) CUDA_TRY(cudaEventRecord(c.ev[EV_B], s));
+            CUDA_TRY(cudaStreamSynchronize(s));  // staging buffer is reused by the next window
+            lap(d2h_ms, EV_A, EV_B);
+        }
+    }
+    CUDA_TRY(cudaEventRecord(c.ev[EV_END], s));
+    if (!out_dev || timed) {
+        CUDA_TRY(cudaEventSynchronize(c.ev[EV_END]));
+        CUDA_TRY(cudaEventElapsedTime(&S.total_ms, c.ev[EV_START], c.ev[EV_END]));
+        CUDA_TRY(cudaEventElapsedTime(&S.h2d_ms, c.ev[EV_START], c.ev[EV_H2D]));
+    }
+    S.count_ms = count_ms;
+    S.emit_ms = emit_ms;
+    S.sort_ms = sort_ms;
+    S.index_ms = index_ms;
+    S.fill_ms = fill_ms;
+    S.d2h_ms = d2h_ms;
+    S.kernel_launches = launches;
+    if (st) *st = S;
+}
+
+}  // namespace rz
+
+// ================================================================================================
+// C ABI
+// ================================================================================================
+using rz::Error;
+using rz::set_err;
+
+rz_geoms::~rz_geoms() {
+    for (auto& kv : dev) delete kv.second;
+    dev.clear();
+    rz::unpin_host(this);
+}
+
+template <typename F> static int guarded(char* err, size_t errlen, F f) {
+    try {
+        f();
+        return RZ_OK;
+    } catch (const Error& e) {
+        set_err(err, errlen, e.msg);
+        return e.code;
+    } catch (const std::bad_alloc&) {
+        set_err(err, errlen, "Out of host memory.");
+        return RZ_RUNTIME_ERROR;
+    } catch (const std::exception& e) {
+        set_err(err, errlen, e.what());
+        return RZ_RUNTIME_ERROR;
+    }
+}
+
+extern "C" {
+
+rz_geoms* rz_geoms_from_wkb(const uint8_t* const* bufs, const uint64_t* lens, uint64_t n, char* err, size_t errlen) {
+    std::unique_ptr<rz_geoms> g(new rz_geoms());
+    int rc = guarded(err, errlen, [&]() {
+        rz::Flattener f(g.get());
+        for (uint64_t i = 0; i < n; i++) {
+            bool keep = false;
+            f.begin_geometry();
+            if (!rz::read_wkb(bufs[i], (size_t)lens[i], f, &keep))
+                throw Error{RZ_RUNTIME_ERROR, f.ok() ? "Cannot parse geometry. Check that the WKB bytes are valid."
+                                                     : f.error()};
+            f.end_geometry(keep);
+        }
+        // python/src/geo/parse_geometry.rs:20-28 (bail_if_empty_geoms)
+        if (g->n_geoms == 0)
+            throw Error{RZ_VALUE_ERROR, "Could not parse geometry. Only WKT or WKB formats are supported."};
+        rz::finish_geoms(g.get());
+    });
+    return rc == RZ_OK ? g.release() : nullptr;
+}
+
+rz_geoms* rz_geoms_from_wkt(const char* const* strs, uint64_t n, char* err, size_t errlen) {
+    std::unique_ptr<rz_geoms> g(new rz_geoms());
+    int rc = guarded(err, errlen, [&]() {
+        rz::Flattener f(g.get());
+        for (uint64_t i = 0; i < n; i++) {
+            bool keep = false;
+            f.begin_geometry();
+            if (!rz::read_wkt(strs[i], f, &keep))
+                throw Error{RZ_RUNTIME_ERROR, f.ok() ? "Cannot parse geometry. Check that the WKT is valid." : f.error()};
+            f.end_geometry(keep);
+        }
+        if (g->n_geoms == 0)
+            throw Error{RZ_VALUE_ERROR, "Could not parse geometry. Only WKT or WKB formats are supported."};
+        rz::finish_geoms(g.get());
+    });
+    return rc == RZ_OK ? g.release() : nullptr;
+}
+
+rz_geoms* rz_geoms_from_soa(const rz_geom_soa* soa, char* err, size_t errlen) {
+    std::unique_ptr<rz_geoms> g(new rz_geoms());
+    int rc = guarded(err, errlen, [&]() {
+        rz::Flattener f(g.get());
+        for (int k = 0; k < 3; k++) {  // a good guess: most inputs are single-kind
+            g->pool[k].x.reserve(k == 0 ? soa->n_coords + soa->n_seqs : 0);
+            g->pool[k].y.reserve(k == 0 ? soa->n_coords + soa->n_seqs : 0);
+            g->pool[k].tag.reserve(k == 0 ? soa->n_coords + soa->n_seqs : 0);
+        }
+        for (uint64_t gi = 0; gi < soa->n_geoms; gi++) {
+            f.begin_geometry();
+            for (uint64_t p = soa->geom_part_off[gi]; p < soa->geom_part_off[gi + 1]; p++) {
+                int kind = soa->part_kind[p];
+                if (kind < 0 || kind > 2) throw Error{RZ_VALUE_ERROR, "Invalid part kind"};
+                f.begin_part(kind);
+                uint64_t s0 = soa->part_seq_off[p], s1 = soa->part_seq_off[p + 1];
+                for (uint64_t s = s0; s < s1; s++) {
+                    // geo::BoundingRect looks at exterior rings only; the SoA form has no polygon
+                    // boundaries, so every ring counts (callers needing exactness pass an extent).
+                    f.begin_seq(true);
+                    for (uint64_t k = soa->seq_coord_off[s]; k < soa->seq_coord_off[s + 1]; k++)
+                        f.coord(soa->x[k], soa->y[k]);
+                    f.end_seq();
+                }
+                f.end_part();
+            }
+            f.end_geometry(true);
+            if (!f.ok()) throw Error{RZ_RUNTIME_ERROR, f.error()};
+        }
+        rz::finish_geoms(g.get());
+    });
+    return rc == RZ_OK ? g.release() : nullptr;
+}
+
+uint64_t rz_geoms_len(const rz_geoms* g) { return g->n_geoms; }
+uint64_t rz_geoms_n_parts(const rz_geoms* g) { return g->part_kind.size(); }
+uint64_t rz_geoms_n_coords(const rz_geoms* g) { return g->pool[0].size() + g->pool[1].size() + g->pool[2].size(); }
+
+int rz_geoms_bounds(const rz_geoms* g, double out[4]) {
+    if (!g->has_bounds) return RZ_RUNTIME_ERROR;
+    std::memcpy(out, g->bounds, sizeof g->bounds);
+    return RZ_OK;
+}
+
+int rz_geoms_upload(rz_geoms* g, int device, char* err, size_t errlen) {
+    return guarded(err, errlen, [&]() {
+        rz::DeviceCtx& c = rz::device_ctx(device);
+        std::lock_guard<std::mutex> lk(c.mu);
+        CUDA_TRY(cudaSetDevice(c.dev));
+        rz::geoms_on_device(g, c, c.stream, false, nullptr);
+    });
+}
+
+void rz_geoms_evict(rz_geoms* g) {
+    std::lock_guard<std::mutex> lk(g->mu);
+    for (auto& kv : g->dev) delete kv.second;
+    g->dev.clear();
+}
+
+void rz_geoms_free(rz_geoms* g) { delete g; }
+
+const uint8_t* rz_geoms_part_kind(const rz_geoms* g) { return g->part_kind.data(); }
+const uint64_t* rz_geoms_part_geom(const rz_geoms* g) { return g->part_geom.data(); }
+uint64_t rz_geoms_pool_len(const rz_geoms* g, int kind) { return kind >= 0 && kind < 3 ? g->pool[kind].size() : 0; }
+const double* rz_geoms_pool_x(const rz_geoms* g, int kind) { return g->pool[kind].x.data(); }
+const double* rz_geoms_pool_y(const rz_geoms* g, int kind) { return g->pool[kind].y.data(); }
+const uint32_t* rz_geoms_pool_tag(const rz_geoms* g, int kind) { return g->pool[kind].tag.data(); }
+
+int rz_raster_info_build(const rz_raw_raster_info* raw, const rz_geoms* g, rz_raster_info* out, char* err,
+                         size_t errlen) {
+    std::string msg;
+    int rc = rz::build_raster_info(raw, g, out, msg);
+    if (rc) set_err(err, errlen, msg);
+    return rc;
+}
+
+int64_t rz_group_keys(const char* const* keys, uint64_t n, int32_t* band_of_geom, uint64_t* band_first) {
+    return rz::group_keys(keys, n, band_of_geom, band_first);
+}
+
+int rz_rasterize_dense(rz_geoms* g, const rz_context* ctx, void* out, rz_stats* stats, char* err, size_t errlen) {
+    return guarded(err, errlen, [&]() { rz::rasterize_dense(g, ctx, out, stats); });
+}
+
+// ---- sparse (implemented in rz_sparse.cuh; placeholders until then) ---------------------------
+struct rz_sparse {
+    std::vector<uint64_t> rows, cols, counts;
+    std::vector<uint8_t> data;
+};
+int rz_rasterize_sparse(rz_geoms*, const rz_context*, rz_sparse**, rz_stats*, char* err, size_t errlen) {
+    set_err(err, errlen, "sparse encoding is not implemented on the B200 path yet.");
+    return RZ_RUNTIME_ERROR;
+}
+uint64_t rz_sparse_len(const rz_sparse* s) { return s->rows.size(); }
+uint64_t rz_sparse_n_bands(const rz_sparse* s) { return s->counts.size(); }
+const uint64_t* rz_sparse_rows(const rz_sparse* s) { return s->rows.data(); }
+const uint64_t* rz_sparse_cols(const rz_sparse* s) { return s->cols.data(); }
+const void* rz_sparse_data(const rz_sparse* s) { return s->data.data(); }
+const uint64_t* rz_sparse_counts(const rz_sparse* s) { return s->counts.data(); }
+void rz_sparse_free(rz_sparse* s) { delete s; }
+int rz_sparse_build_array(const rz_context*, uint64_t, const uint64_t*, const uint64_t*, const uint64_t*, const void*,
+                          void*, rz_stats*, char* err, size_t errlen) {
+    set_err(err, errlen, "sparse replay is not implemented on the B200 path yet.");
+    return RZ_RUNTIME_ERROR;
+}
+
+int rz_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+const char* rz_version(void) { return "rz_b200 0.1.0 (sm_100a)"; }
+
+}  // extern "C"

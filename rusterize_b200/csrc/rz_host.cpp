@@ -1,0 +1,614 @@
+// rz_host.cpp — geometry flattening (WKB / WKT / SoA -> pooled SoA + parts table), raster-grid
+// math and band grouping.  Host only.
+//
+// Reference behaviour followed (paths relative to the reference repo):
+//   rust/src/rasterization/burn_geometry.rs:24-210  which geometry types pool into one burn unit
+//   python/src/geo/parse_geometry.rs:77-134          which inputs are dropped / rejected
+//   rust/src/geo/raster.rs:50-156                    extent / shape / resolution rules
+//   rust/src/rasterize.rs:199-205                    band order for `by`
+#include "rz_host.hpp"
+
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <limits>
+
+namespace rz {
+
+// ------------------------------------------------------------------------------------------------
+// Flattener
+// ------------------------------------------------------------------------------------------------
+void Flattener::begin_geometry() {
+    for (int k = 0; k < 3; k++) mark_pool_[k] = g_->pool[k].size();
+    mark_parts_ = g_->part_kind.size();
+    geom_has_bounds_ = false;
+}
+
+void Flattener::end_geometry(bool keep) {
+    if (!keep) {  // roll back whatever the dropped geometry appended
+        for (int k = 0; k < 3; k++) {
+            g_->pool[k].x.resize(mark_pool_[k]);
+            g_->pool[k].y.resize(mark_pool_[k]);
+            g_->pool[k].tag.resize(mark_pool_[k]);
+        }
+        g_->part_kind.resize(mark_parts_);
+        g_->part_geom.resize(mark_parts_);
+        g_->part_xlo.resize(mark_parts_);
+        g_->part_xhi.resize(mark_parts_);
+        return;
+    }
+    if (geom_has_bounds_) {
+        if (!g_->has_bounds) {
+            std::memcpy(g_->bounds, gb_, sizeof gb_);
+            g_->has_bounds = true;
+        } else {
+            // rust/src/geo/raster.rs:81-84: f64::min / f64::max (NaN-ignoring)
+            g_->bounds[0] = std::fmin(g_->bounds[0], gb_[0]);
+            g_->bounds[1] = std::fmin(g_->bounds[1], gb_[1]);
+            g_->bounds[2] = std::fmax(g_->bounds[2], gb_[2]);
+            g_->bounds[3] = std::fmax(g_->bounds[3], gb_[3]);
+        }
+    }
+    g_->n_geoms++;
+}
+
+void Flattener::begin_part(int kind) {
+    kind_ = kind;
+    size_t p = g_->part_kind.size();
+    if (p >= TAG_PART_MASK) {
+        ok_ = false;
+        err_ = "Too many geometry parts (limit 2^30 - 1).";
+        p = 0;
+    }
+    part_ = (uint32_t)p;
+    g_->part_kind.push_back((uint8_t)kind);
+    g_->part_geom.push_back(g_->n_geoms);
+    g_->part_xlo.push_back(std::numeric_limits<double>::infinity());
+    g_->part_xhi.push_back(-std::numeric_limits<double>::infinity());
+}
+
+void Flattener::end_part() { kind_ = -1; }
+
+void Flattener::begin_seq(bool counts_for_bounds) {
+    seq_start_ = g_->pool[kind_].size();
+    seq_bounds_ = counts_for_bounds;
+}
+
+void Flattener::bound(double x, double y) {
+    // geo's bounding-rect fold: plain </> comparisons seeded by the first coordinate
+    if (!geom_has_bounds_) {
+        gb_[0] = gb_[2] = x;
+        gb_[1] = gb_[3] = y;
+        geom_has_bounds_ = true;
+        return;
+    }
+    if (x < gb_[0]) gb_[0] = x;
+    if (x > gb_[2]) gb_[2] = x;
+    if (y < gb_[1]) gb_[1] = y;
+    if (y > gb_[3]) gb_[3] = y;
+}
+
+void Flattener::coord(double x, double y) {
+    Pool& p = g_->pool[kind_];
+    p.x.push_back(x);
+    p.y.push_back(y);
+    p.tag.push_back(part_);
+    if (seq_bounds_) bound(x, y);
+    if (kind_ == RZ_PART_POLYGON) {
+        double& lo = g_->part_xlo[part_];
+        double& hi = g_->part_xhi[part_];
+        lo = std::fmin(lo, x);
+        hi = std::fmax(hi, x);
+    }
+}
+
+void Flattener::end_seq() {
+    Pool& p = g_->pool[kind_];
+    size_t n = p.size() - seq_start_;
+    if (n == 0 || kind_ == RZ_PART_POINT) return;
+    size_t a = seq_start_, b = p.size() - 1;
+    bool closed = p.x[a] == p.x[b] && p.y[a] == p.y[b];
+    if (kind_ == RZ_PART_POLYGON && !closed) {
+        // geo_types::Polygon::new closes every ring
+        double fx = p.x[a], fy = p.y[a];
+        p.x.push_back(fx);
+        p.y.push_back(fy);
+        p.tag.push_back(part_);
+        closed = true;
+    }
+    if (kind_ == RZ_PART_LINE && closed)
+        for (size_t i = seq_start_; i < p.size(); i++) p.tag[i] |= TAG_CLOSED;
+    p.tag.back() |= TAG_SEQ_END;
+}
+
+// ------------------------------------------------------------------------------------------------
+// WKB
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+struct Cursor {
+    const uint8_t* p;
+    const uint8_t* end;
+    bool ok = true;
+    bool need(size_t n) {
+        if ((size_t)(end - p) < n) ok = false;
+        return ok;
+    }
+    uint8_t u8() {
+        if (!need(1)) return 0;
+        return *p++;
+    }
+    uint32_t u32(bool le) {
+        if (!need(4)) return 0;
+        uint32_t v = le ? ((uint32_t)p[0] | (uint32_t)p[1] << 8 | (uint32_t)p[2] << 16 | (uint32_t)p[3] << 24)
+                        : ((uint32_t)p[3] | (uint32_t)p[2] << 8 | (uint32_t)p[1] << 16 | (uint32_t)p[0] << 24);
+        p += 4;
+        return v;
+    }
+    double f64(bool le) {
+        if (!need(8)) return 0;
+        uint64_t v = 0;
+        if (le) std::memcpy(&v, p, 8);
+        else
+            for (int i = 0; i < 8; i++) v = (v << 8) | p[i];
+        p += 8;
+        double d;
+        std::memcpy(&d, &v, 8);
+        return d;
+    }
+};
+
+struct WkbHeader {
+    bool le;
+    uint32_t type;
+    int dims;
+};
+
+bool wkb_header(Cursor& c, WkbHeader& h) {
+    uint8_t bo = c.u8();
+    if (!c.ok || bo > 1) return c.ok = false;
+    h.le = bo == 1;
+    uint32_t t = c.u32(h.le);
+    h.dims = 2;
+    if (t & 0x80000000u) h.dims++;
+    if (t & 0x40000000u) h.dims++;
+    bool srid = (t & 0x20000000u) != 0;
+    t &= 0x0fffffffu;
+    uint32_t iso = t / 1000;
+    if (iso == 1 || iso == 2) h.dims = 3;
+    else if (iso == 3) h.dims = 4;
+    h.type = t % 1000;
+    if (srid) c.u32(h.le);
+    return c.ok;
+}
+
+void wkb_coords(Cursor& c, const WkbHeader& h, Flattener& f) {
+    uint32_t n = c.u32(h.le);
+    if (!c.need((size_t)n * 8 * (size_t)h.dims)) return;
+    for (uint32_t i = 0; i < n; i++) {
+        double x = c.f64(h.le), y = c.f64(h.le);
+        for (int k = 2; k < h.dims; k++) c.f64(h.le);
+        f.coord(x, y);
+    }
+}
+
+void wkb_poly_rings(Cursor& c, const WkbHeader& h, Flattener& f) {
+    uint32_t nr = c.u32(h.le);
+    for (uint32_t r = 0; r < nr && c.ok; r++) {
+        f.begin_seq(r == 0);
+        wkb_coords(c, h, f);
+        f.end_seq();
+    }
+}
+
+// `nested`: >0 while inside a GeometryCollection.  Returns whether the geometry exists in geo_types.
+bool wkb_geom(Cursor& c, Flattener& f, int depth) {
+    if (depth > 64) return c.ok = false;
+    WkbHeader h;
+    if (!wkb_header(c, h)) return false;
+    switch (h.type) {
+        case 1: {  // Point
+            if (!c.need(8 * (size_t)h.dims)) return false;
+            double x = c.f64(h.le), y = c.f64(h.le);
+            for (int k = 2; k < h.dims; k++) c.f64(h.le);
+            if (x != x && y != y) return false;  // POINT EMPTY -> try_to_geometry() == None
+            f.begin_part(RZ_PART_POINT);
+            f.begin_seq(true);
+            f.coord(x, y);
+            f.end_seq();
+            f.end_part();
+            return true;
+        }
+        case 2:  // LineString
+            f.begin_part(RZ_PART_LINE);
+            f.begin_seq(true);
+            wkb_coords(c, h, f);
+            f.end_seq();
+            f.end_part();
+            return c.ok;
+        case 3:  // Polygon
+            f.begin_part(RZ_PART_POLYGON);
+            wkb_poly_rings(c, h, f);
+            f.end_part();
+            return c.ok;
+        case 4: {  // MultiPoint
+            uint32_t n = c.u32(h.le);
+            f.begin_part(RZ_PART_POINT);
+            f.begin_seq(true);
+            for (uint32_t i = 0; i < n && c.ok; i++) {
+                WkbHeader m;
+                if (!wkb_header(c, m) || m.type != 1) return c.ok = false;
+                if (!c.need(8 * (size_t)m.dims)) return false;
+                double x = c.f64(m.le), y = c.f64(m.le);
+                for (int k = 2; k < m.dims; k++) c.f64(m.le);
+                if (!(x != x && y != y)) f.coord(x, y);
+            }
+            f.end_seq();
+            f.end_part();
+            return c.ok;
+        }
+        case 5: {  // MultiLineString
+            uint32_t n = c.u32(h.le);
+            f.begin_part(RZ_PART_LINE);
+            for (uint32_t i = 0; i < n && c.ok; i++) {
+                WkbHeader m;
+                if (!wkb_header(c, m) || m.type != 2) return c.ok = false;
+                f.begin_seq(true);
+                wkb_coords(c, m, f);
+                f.end_seq();
+            }
+            f.end_part();
+            return c.ok;
+        }
+        case 6: {  // MultiPolygon
+            uint32_t n = c.u32(h.le);
+            f.begin_part(RZ_PART_POLYGON);
+            for (uint32_t i = 0; i < n && c.ok; i++) {
+                WkbHeader m;
+                if (!wkb_header(c, m) || m.type != 3) return c.ok = false;
+                wkb_poly_rings(c, m, f);
+            }
+            f.end_part();
+            return c.ok;
+        }
+        case 7: {  // GeometryCollection: members burned one after another (burn_geometry.rs:64-74)
+            uint32_t n = c.u32(h.le);
+            for (uint32_t i = 0; i < n && c.ok; i++) wkb_geom(c, f, depth + 1);
+            return c.ok;
+        }
+        default:
+            return c.ok = false;
+    }
+}
+
+}  // namespace
+
+bool read_wkb(const uint8_t* buf, size_t len, Flattener& f, bool* keep) {
+    Cursor c{buf, buf + len};
+    *keep = wkb_geom(c, f, 0);
+    return c.ok && f.ok();
+}
+
+// ------------------------------------------------------------------------------------------------
+// WKT
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+struct Lex {
+    const char* s;
+    bool ok = true;
+    void ws() {
+        while (*s == ' ' || *s == '\t' || *s == '\n' || *s == '\r') s++;
+    }
+    bool eat(char ch) {
+        ws();
+        if (*s == ch) {
+            s++;
+            return true;
+        }
+        return false;
+    }
+    void expect(char ch) {
+        if (!eat(ch)) ok = false;
+    }
+    // case-insensitive keyword
+    bool word(std::string& out) {
+        ws();
+        out.clear();
+        while ((*s >= 'A' && *s <= 'Z') || (*s >= 'a' && *s <= 'z')) out.push_back((char)(*s++ & ~0x20));
+        return !out.empty();
+    }
+    bool peek_alpha() {
+        ws();
+        return (*s >= 'A' && *s <= 'Z') || (*s >= 'a' && *s <= 'z');
+    }
+    double num() {
+        ws();
+        char* e = nullptr;
+        double v = std::strtod(s, &e);  // correctly rounded, like Rust's f64::from_str
+        if (e == s) ok = false;
+        s = e;
+        return v;
+    }
+};
+
+int wkt_dims(Lex& l, bool* empty) {
+    int dims = 2;
+    *empty = false;
+    for (;;) {
+        const char* save = l.s;
+        std::string w;
+        if (!l.peek_alpha()) break;
+        l.word(w);
+        if (w == "Z" || w == "M") dims = 3;
+        else if (w == "ZM") dims = 4;
+        else if (w == "EMPTY") {
+            *empty = true;
+            break;
+        } else {
+            l.s = save;
+            l.ok = false;
+            break;
+        }
+    }
+    return dims;
+}
+
+void wkt_coord(Lex& l, int dims, double* x, double* y) {
+    *x = l.num();
+    *y = l.num();
+    for (int k = 2; k < dims; k++) l.num();
+}
+
+void wkt_coord_list(Lex& l, int dims, Flattener& f) {  // "(x y, x y, ...)"
+    l.expect('(');
+    do {
+        double x, y;
+        wkt_coord(l, dims, &x, &y);
+        if (!l.ok) return;
+        f.coord(x, y);
+    } while (l.eat(','));
+    l.expect(')');
+}
+
+void wkt_poly_body(Lex& l, int dims, Flattener& f) {  // "((ring),(ring))"
+    l.expect('(');
+    int r = 0;
+    do {
+        f.begin_seq(r++ == 0);
+        wkt_coord_list(l, dims, f);
+        f.end_seq();
+    } while (l.ok && l.eat(','));
+    l.expect(')');
+}
+
+bool wkt_geom(Lex& l, Flattener& f, int depth) {
+    if (depth > 64) return l.ok = false;
+    std::string name;
+    if (!l.word(name)) return l.ok = false;
+    bool empty;
+    int dims = wkt_dims(l, &empty);
+    if (!l.ok) return false;
+    if (name == "POINT") {
+        if (empty) return false;
+        l.expect('(');
+        double x, y;
+        wkt_coord(l, dims, &x, &y);
+        l.expect(')');
+        if (!l.ok) return false;
+        f.begin_part(RZ_PART_POINT);
+        f.begin_seq(true);
+        f.coord(x, y);
+        f.end_seq();
+        f.end_part();
+        return true;
+    }
+    if (name == "LINESTRING") {
+        f.begin_part(RZ_PART_LINE);
+        f.begin_seq(true);
+        if (!empty) wkt_coord_list(l, dims, f);
+        f.end_seq();
+        f.end_part();
+        return l.ok;
+    }
+    if (name == "POLYGON") {
+        f.begin_part(RZ_PART_POLYGON);
+        if (!empty) wkt_poly_body(l, dims, f);
+        f.end_part();
+        return l.ok;
+    }
+    if (name == "MULTIPOINT") {
+        f.begin_part(RZ_PART_POINT);
+        f.begin_seq(true);
+        if (!empty) {
+            l.expect('(');
+            do {
+                double x, y;
+                if (l.eat('(')) {
+                    wkt_coord(l, dims, &x, &y);
+                    l.expect(')');
+                } else {
+                    std::string w;
+                    const char* save = l.s;
+                    if (l.peek_alpha() && l.word(w) && w == "EMPTY") continue;
+                    l.s = save;
+                    wkt_coord(l, dims, &x, &y);
+                }
+                if (!l.ok) break;
+                f.coord(x, y);
+            } while (l.eat(','));
+            l.expect(')');
+        }
+        f.end_seq();
+        f.end_part();
+        return l.ok;
+    }
+    if (name == "MULTILINESTRING") {
+        f.begin_part(RZ_PART_LINE);
+        if (!empty) {
+            l.expect('(');
+            do {
+                f.begin_seq(true);
+                wkt_coord_list(l, dims, f);
+                f.end_seq();
+            } while (l.ok && l.eat(','));
+            l.expect(')');
+        }
+        f.end_part();
+        return l.ok;
+    }
+    if (name == "MULTIPOLYGON") {
+        f.begin_part(RZ_PART_POLYGON);
+        if (!empty) {
+            l.expect('(');
+            do {
+                wkt_poly_body(l, dims, f);
+            } while (l.ok && l.eat(','));
+            l.expect(')');
+        }
+        f.end_part();
+        return l.ok;
+    }
+    if (name == "GEOMETRYCOLLECTION") {
+        if (!empty) {
+            l.expect('(');
+            do {
+                wkt_geom(l, f, depth + 1);
+            } while (l.ok && l.eat(','));
+            l.expect(')');
+        }
+        return l.ok;
+    }
+    return l.ok = false;
+}
+
+}  // namespace
+
+bool read_wkt(const char* s, Flattener& f, bool* keep) {
+    Lex l{s};
+    *keep = wkt_geom(l, f, 0);
+    l.ws();
+    if (*l.s != 0) l.ok = false;
+    return l.ok && f.ok();
+}
+
+void finish_geoms(rz_geoms* g) {
+    for (int k = 0; k < 3; k++) {
+        g->pool[k].x.shrink_to_fit();
+        g->pool[k].y.shrink_to_fit();
+        g->pool[k].tag.shrink_to_fit();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Grid math — rust/src/geo/raster.rs:50-156
+// ------------------------------------------------------------------------------------------------
+namespace {
+// Rust `f64 as usize`: truncate, saturate, NaN -> 0
+uint64_t as_usize(double v) {
+    if (!(v == v) || v <= 0.0) return 0;
+    if (v >= 18446744073709551615.0) return UINT64_MAX;
+    return (uint64_t)v;
+}
+bool is_pos_or_neg_zero_equal_zero(double v) {
+    // total_cmp(&0.0) == Equal: only +0.0 qualifies (raster.rs:53)
+    return v == 0.0 && !std::signbit(v);
+}
+}  // namespace
+
+int build_raster_info(const rz_raw_raster_info* raw, const rz_geoms* g, rz_raster_info* out, std::string& err) {
+    double xmin, ymin, xmax, ymax;
+    bool inferred;
+    if (raw->has_extent) {
+        const double* e = raw->extent;
+        if (is_pos_or_neg_zero_equal_zero(e[0]) && is_pos_or_neg_zero_equal_zero(e[1]) &&
+            is_pos_or_neg_zero_equal_zero(e[2]) && is_pos_or_neg_zero_equal_zero(e[3])) {
+            err = "Unspecified extent (all zeros).";
+            return RZ_VALUE_ERROR;
+        }
+        xmin = e[0];
+        ymin = e[1];
+        xmax = e[2];
+        ymax = e[3];
+        inferred = false;
+    } else {
+        if (!g || !g->has_bounds) {
+            err = "Cannot infer bounding box from geometry.";
+            return RZ_RUNTIME_ERROR;
+        }
+        xmin = g->bounds[0];
+        ymin = g->bounds[1];
+        xmax = g->bounds[2];
+        ymax = g->bounds[3];
+        inferred = true;
+    }
+    bool has_shape = raw->has_shape != 0, has_res = raw->has_resolution != 0, tap = raw->tap != 0;
+    if (!has_shape && !has_res) {
+        err = "Must set at least one of `shape` or `resolution`";
+        return RZ_VALUE_ERROR;
+    }
+    if (has_shape && has_res) {
+        err = "Shape and resolution are mutually exclusive; provide only one";
+        return RZ_VALUE_ERROR;
+    }
+    uint64_t nrows = has_shape ? raw->nrows : 0, ncols = has_shape ? raw->ncols : 0;
+    double xres = has_res ? raw->xres : 0.0, yres = has_res ? raw->yres : 0.0;
+    if (has_shape && (nrows == 0 || ncols == 0)) {
+        err = "Shape values must be > 0.";
+        return RZ_VALUE_ERROR;
+    }
+    if (has_res && (xres <= 0.0 || yres <= 0.0)) {
+        err = "Resolution values must be > 0.";
+        return RZ_VALUE_ERROR;
+    }
+    if (inferred && !tap && has_res) {  // half-pixel buffer
+        xmin -= xres / 2.0;
+        xmax += xres / 2.0;
+        ymin -= yres / 2.0;
+        ymax += yres / 2.0;
+    }
+    if (!has_res) {
+        xres = (xmax - xmin) / (double)ncols;
+        yres = (ymax - ymin) / (double)nrows;
+    } else if (tap) {
+        xmin = std::floor(xmin / xres) * xres;
+        xmax = std::ceil(xmax / xres) * xres;
+        ymin = std::floor(ymin / yres) * yres;
+        ymax = std::ceil(ymax / yres) * yres;
+    }
+    if (!has_shape) {
+        nrows = as_usize(0.5 + (ymax - ymin) / yres);
+        ncols = as_usize(0.5 + (xmax - xmin) / xres);
+    }
+    out->nrows = nrows;
+    out->ncols = ncols;
+    out->xmin = xmin;
+    out->ymin = ymin;
+    out->xmax = xmax;
+    out->ymax = ymax;
+    out->xres = xres;
+    out->yres = yres;
+    out->epsg = raw->epsg;
+    out->_pad = 0;
+    return RZ_OK;
+}
+
+// rust/src/rasterize.rs:199-205 — BTreeMap<&String, Vec<usize>>: byte-lexicographic key order.
+int64_t group_keys(const char* const* keys, uint64_t n, int32_t* band_of_geom, uint64_t* band_first) {
+    std::map<std::string, int32_t> order;
+    for (uint64_t i = 0; i < n; i++) order.emplace(std::string(keys[i]), 0);
+    int32_t b = 0;
+    for (auto& kv : order) kv.second = b++;
+    std::vector<char> seen((size_t)b, 0);
+    for (uint64_t i = 0; i < n; i++) {
+        int32_t k = order[std::string(keys[i])];
+        band_of_geom[i] = k;
+        if (!seen[(size_t)k]) {
+            seen[(size_t)k] = 1;
+            band_first[k] = i;
+        }
+    }
+    return b;
+}
+
+}  // namespace rz

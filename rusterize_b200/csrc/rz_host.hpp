@@ -1,0 +1,105 @@
+// rz_host.hpp — host side of the burn path: flattened geometry pools, WKB/WKT readers, grid math.
+// Pure C++17 (no CUDA) so it is testable on a CPU-only box.
+#pragma once
+
+#include <cstdint>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/rz_b200.h"
+
+namespace rz {
+
+// Tag word stored next to every pooled vertex.
+//   polygon / line pools: bits 0..29 part id, bit 30 = "owning line string is closed" (first coord ==
+//   last coord, rust/src/geo/edges.rs:115), bit 31 = last vertex of its ring / line string (no
+//   segment starts here).
+//   point pool: part id.
+constexpr uint32_t TAG_PART_MASK = 0x3fffffffu;
+constexpr uint32_t TAG_CLOSED = 0x40000000u;
+constexpr uint32_t TAG_SEQ_END = 0x80000000u;
+
+struct Pool {
+    std::vector<double> x, y;
+    std::vector<uint32_t> tag;
+    size_t size() const { return x.size(); }
+};
+
+struct DeviceGeoms;  // rz_engine.cu
+
+}  // namespace rz
+
+// The opaque handle of include/rz_b200.h.
+struct rz_geoms {
+    uint64_t n_geoms = 0;
+    rz::Pool pool[3];                  // indexed by RZ_PART_*
+    std::vector<uint8_t> part_kind;    // [n_parts]
+    std::vector<uint64_t> part_geom;   // [n_parts] owning geometry (index among kept geometries)
+    std::vector<double> part_xlo, part_xhi;  // [n_parts] world-x extent of polygon parts (column-tile range)
+    bool has_bounds = false;
+    double bounds[4] = {0, 0, 0, 0};   // union of geo::BoundingRect, xmin ymin xmax ymax
+    bool pinned = false;
+
+    std::mutex mu;
+    std::map<int, rz::DeviceGeoms*> dev;  // cached device copies, by ordinal
+
+    ~rz_geoms();
+};
+
+namespace rz {
+
+// Streaming builder shared by the WKB reader, the WKT reader and the SoA ingestion.  It applies
+// the pooling rules of rust/src/rasterization/burn_geometry.rs:24-210:
+//   * Polygon / MultiPolygon  -> ONE polygon part holding every ring of every member polygon
+//   * LineString / MultiLineString -> ONE line part holding every member line string
+//   * Point / MultiPoint -> ONE point part
+//   * GeometryCollection -> its members' parts, in order (each burned independently)
+class Flattener {
+  public:
+    explicit Flattener(rz_geoms* g) : g_(g) {}
+    void begin_geometry();
+    void end_geometry(bool keep);
+    void begin_part(int kind);
+    void end_part();
+    // polygons: ring_is_exterior feeds geo::BoundingRect (exterior ring only); rings are closed
+    // like geo_types::Polygon::new does.
+    void begin_seq(bool counts_for_bounds);
+    void coord(double x, double y);
+    void end_seq();
+    bool ok() const { return ok_; }
+    const char* error() const { return err_; }
+
+  private:
+    void bound(double x, double y);
+    rz_geoms* g_;
+    int kind_ = -1;
+    uint32_t part_ = 0;
+    size_t seq_start_ = 0;
+    bool seq_bounds_ = false;
+    bool geom_has_bounds_ = false;
+    double gb_[4];
+    // rollback marks for a dropped top-level geometry
+    size_t mark_pool_[3], mark_parts_;
+    bool ok_ = true;
+    const char* err_ = "";
+};
+
+// ISO WKB / EWKB reader (little or big endian, Z/M dropped).  Returns false on malformed bytes.
+// `*keep` = false when the top-level geometry has no geo_types equivalent (POINT EMPTY).
+bool read_wkb(const uint8_t* buf, size_t len, Flattener& f, bool* keep);
+// WKT reader with strtod-exact coordinates.
+bool read_wkt(const char* s, Flattener& f, bool* keep);
+
+void finish_geoms(rz_geoms* g);
+
+int build_raster_info(const rz_raw_raster_info* raw, const rz_geoms* g, rz_raster_info* out, std::string& err);
+int64_t group_keys(const char* const* keys, uint64_t n, int32_t* band_of_geom, uint64_t* band_first);
+
+inline size_t dtype_size(int dt) {
+    static const size_t s[10] = {1, 2, 4, 8, 1, 2, 4, 8, 4, 8};
+    return (dt >= 0 && dt < 10) ? s[dt] : 0;
+}
+
+}  // namespace rz

@@ -1,0 +1,814 @@
+// rz_kernels.cuh — device code of the burn path (sm_100a).
+//
+// Pipeline (one "window" = a contiguous range of raster rows of every band):
+//   part_prepare      per part: band, value, column-tile range                         (rasterize.rs:162-196)
+//   *_count / *_emit  edge setup: polygon scanline crossings, Bresenham line pixels,
+//                     point cells -> 64-bit records  [task | part | col]                (edges.rs, burners.rs)
+//   radix sort        LSD, 8-bit digits, keys only                                      (burners.rs:276,302)
+//   task_index        record range of every (band,row,column-tile) task
+//   fill              one warp per task: row tile in shared memory, records replayed in
+//                     part order with the reference's pixel-function rules, tile flushed
+//                     once with coalesced stores                                        (pixel_functions.rs)
+//
+// f64 discipline: every geometry operation uses the explicit round-to-nearest intrinsics
+// (__dadd_rn/__dsub_rn/__dmul_rn/__ddiv_rn), which the compiler never contracts into FMA, because
+// the reference computes x0 + (cy - y0) * dxdy with two roundings (edges.rs:50-55).
+#pragma once
+
+#include <cfloat>
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace rz {
+
+struct KParams {
+    double xmin, ymax, xres, yres;  // world -> pixel
+    double nrows_f, ncols_f;
+    uint32_t nrows, ncols;          // full raster
+    uint32_t win_r0, win_r1;        // rows of this window (absolute)
+    uint32_t tile_w, tile_shift;    // column-tile width (power of two) and its log2
+    uint32_t n_tiles;               // ceil(ncols / tile_w)
+    uint32_t col_bits, part_bits;   // key layout: [task | part | col]
+    uint32_t part_shift, task_shift;
+    uint32_t n_bands;
+    uint32_t dedup_lines;           // xres != yres (burn_geometry.rs:179,202)
+    uint32_t n_parts;
+};
+
+// Per-part data resolved once per call.
+struct PartInfo {
+    uint64_t value_bits;  // field value of the owning geometry, in the output dtype
+    int32_t band;         // -1: skipped (null field)
+    uint16_t t_lo, t_hi;  // column tiles a polygon part can touch (t_lo > t_hi: none)
+};
+
+struct Counters {
+    unsigned long long records;     // total records counted (count pass)
+    unsigned long long crossings;   // polygon crossings without tile replication
+    unsigned long long cursor;      // emit allocation cursor
+    unsigned int bad_line;          // a line segment left the supported ±2^29 pixel domain
+    unsigned int pad;
+};
+
+// ---------------------------------------------------------------------------------------------
+// small helpers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double px_x(const KParams& P, double X) { return __ddiv_rn(__dsub_rn(X, P.xmin), P.xres); }
+__device__ __forceinline__ double px_y(const KParams& P, double Y) { return __ddiv_rn(__dsub_rn(P.ymax, Y), P.yres); }
+
+// Rust `f64 as usize` followed by min(., lim): NaN / negatives -> 0, saturating.
+__device__ __forceinline__ uint32_t sat_u32(double v, uint32_t lim) {
+    if (!(v > 0.0)) return 0u;
+    if (v >= (double)lim) return lim;
+    return (uint32_t)v;
+}
+// Rust `f64 as isize` restricted to ±2^40 (callers flag anything beyond ±2^29 as unsupported).
+__device__ __forceinline__ long long sat_i64(double v) {
+    if (!(v == v)) return 0;
+    if (v <= -1099511627776.0) return -1099511627776LL;
+    if (v >= 1099511627776.0) return 1099511627776LL;
+    return (long long)v;
+}
+
+__device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
+
+// ---------------------------------------------------------------------------------------------
+// part_prepare
+// ---------------------------------------------------------------------------------------------
+// One thread per part.  Resolves the burn value (field[i] or the scalar), the band and, for polygon
+// parts, the range of column tiles whose pixels the part can fill.
+__global__ void part_prepare_kernel(KParams P, const uint8_t* __restrict__ part_kind,
+                                    const uint32_t* __restrict__ part_geom, const double* __restrict__ part_xlo,
+                                    const double* __restrict__ part_xhi, const uint8_t* __restrict__ field,
+                                    uint32_t itemsize, int field_is_scalar, const uint8_t* __restrict__ field_valid,
+                                    const int32_t* __restrict__ band_of_geom, PartInfo* __restrict__ info) {
+    uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P.n_parts) return;
+    uint32_t g = part_geom[p];
+    PartInfo pi;
+    pi.band = band_of_geom ? band_of_geom[g] : 0;
+    if (field_valid && !field_valid[g]) pi.band = -1;
+    uint64_t v = 0;
+    const uint8_t* src = field + (field_is_scalar ? 0 : (size_t)g * itemsize);
+    for (uint32_t k = 0; k < itemsize; k++) v |= (uint64_t)src[k] << (8 * k);
+    pi.value_bits = v;
+    pi.t_lo = 1;
+    pi.t_hi = 0;
+    if (part_kind[p] == 0) {
+        // Crossing columns lie within one pixel of the columns of the part's x-extent (x on an edge
+        // is an interpolation between its end points, up to rounding).
+        double fl = floor(__dadd_rn(px_x(P, part_xlo[p]), 0.5)), fh = floor(__dadd_rn(px_x(P, part_xhi[p]), 0.5));
+        uint32_t cl = sat_u32(fl, P.ncols), ch = sat_u32(fh, P.ncols);
+        cl = cl > 0 ? cl - 1 : 0;
+        ch = ch < P.ncols ? ch + 1 : P.ncols;
+        if (ch > cl && cl < P.ncols) {  // fillable pixels [cl, ch)
+            pi.t_lo = (uint16_t)(cl >> P.tile_shift);
+            pi.t_hi = (uint16_t)((ch - 1) >> P.tile_shift);
+        }
+    }
+    info[p] = pi;
+}
+
+// ---------------------------------------------------------------------------------------------
+// polygon edge setup — rust/src/geo/edges.rs:27-55, 90-110; burners.rs:279-315
+// ---------------------------------------------------------------------------------------------
+struct PolyEdgeRec {
+    double x_top, y_top, dxdy;
+    uint32_t row_lo;   // first window row the edge is active on
+    uint32_t n_rows;   // rows in [row_lo, row_lo+n_rows) are active
+    uint32_t part;
+    int32_t band;
+    uint32_t t_lo, n_t;
+};
+
+__device__ __forceinline__ bool poly_edge_setup(const KParams& P, const double* __restrict__ x,
+                                                const double* __restrict__ y, const uint32_t* __restrict__ tag,
+                                                const PartInfo* __restrict__ info, uint32_t i, uint32_t n,
+                                                PolyEdgeRec& e) {
+    e.n_rows = 0;
+    e.n_t = 0;
+    if (i >= n) return false;
+    uint32_t t = tag[i];
+    if (t & 0x80000000u) return false;  // last vertex of its ring
+    e.part = t & 0x3fffffffu;
+    PartInfo pi = info[e.part];
+    if (pi.band < 0 || pi.t_lo > pi.t_hi) return false;
+    e.band = pi.band;
+    e.t_lo = pi.t_lo;
+    e.n_t = (uint32_t)pi.t_hi - pi.t_lo + 1;
+    double x0 = px_x(P, x[i]), y0 = px_y(P, y[i]);
+    double x1 = px_x(P, x[i + 1]), y1 = px_y(P, y[i + 1]);
+    if (!(fabs(__dsub_rn(y0, y1)) >= DBL_EPSILON)) return false;  // skip horizontal (edges.rs:100)
+    double min_y = fmin(y0, y1), max_y = fmax(y0, y1);
+    if (!(min_y < P.nrows_f && max_y >= 0.0)) return false;  // edges.rs:105
+    double x_bot, y_bot;
+    if (y0 < y1) { e.x_top = x0; e.y_top = y0; x_bot = x1; y_bot = y1; }
+    else { e.x_top = x1; e.y_top = y1; x_bot = x0; y_bot = y0; }
+    uint32_t ystart = sat_u32(ceil(__dsub_rn(e.y_top, 0.5)), P.nrows);  // edges.rs:32-33 (+ rows < nrows)
+    uint32_t yend = sat_u32(ceil(__dsub_rn(y_bot, 0.5)), P.nrows);
+    e.dxdy = __ddiv_rn(__dsub_rn(x_bot, e.x_top), __dsub_rn(y_bot, e.y_top));
+    uint32_t lo = max(ystart, P.win_r0), hi = min(yend, P.win_r1);
+    if (hi <= lo) return false;
+    e.row_lo = lo;
+    e.n_rows = hi - lo;
+    return true;
+}
+
+// key of the crossing of edge e with row `row`, replicated into column tile `tile`
+__device__ __forceinline__ uint64_t poly_key(const KParams& P, const PolyEdgeRec& e, uint32_t row, uint32_t tile) {
+    double cy = __dadd_rn((double)row, 0.5);
+    double xi = __dadd_rn(e.x_top, __dmul_rn(__dsub_rn(cy, e.y_top), e.dxdy));  // edges.rs:50-55
+    uint32_t col = sat_u32(floor(__dadd_rn(xi, 0.5)), P.ncols);                 // burners.rs:310-311
+    uint32_t ts = tile << P.tile_shift;
+    uint32_t te = min(ts + P.tile_w, P.ncols);
+    uint32_t rel = min(max(col, ts), te) - ts;
+    uint64_t task = ((uint64_t)e.band * (P.win_r1 - P.win_r0) + (row - P.win_r0)) * P.n_tiles + tile;
+    return (task << P.task_shift) | ((uint64_t)e.part << P.part_shift) | rel;
+}
+
+constexpr int SETUP_THREADS = 256;
+constexpr int SETUP_ITEMS = 4;
+constexpr uint32_t LONG_EDGE = 64;  // records above which a warp cooperates on one edge
+
+// block-wide exclusive scan of one value per thread (256 threads); returns exclusive prefix, total in *total
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* smem_warp, uint32_t* total) {
+    uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
+    uint32_t inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= (uint32_t)o) inc += t;
+    }
+    if (lane == 31) smem_warp[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t w = lane < (blockDim.x >> 5) ? smem_warp[lane] : 0;
+        uint32_t winc = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t t = __shfl_up_sync(0xffffffffu, winc, o);
+            if (lane >= (uint32_t)o) winc += t;
+        }
+        smem_warp[lane] = winc - w;  // exclusive warp offsets
+        if (lane == 31) smem_warp[32] = winc;
+    }
+    __syncthreads();
+    *total = smem_warp[32];
+    return smem_warp[warp] + inc - v;
+}
+
+__global__ void __launch_bounds__(SETUP_THREADS)
+poly_count_kernel(KParams P, const double* __restrict__ x, const double* __restrict__ y,
+                  const uint32_t* __restrict__ tag, uint32_t n, const PartInfo* __restrict__ info,
+                  Counters* __restrict__ ctr) {
+    unsigned long long rec = 0, crs = 0;
+    uint32_t base = blockIdx.x * (SETUP_THREADS * SETUP_ITEMS);
+#pragma unroll
+    for (int r = 0; r < SETUP_ITEMS; r++) {
+        PolyEdgeRec e;
+        if (poly_edge_setup(P, x, y, tag, info, base + r * SETUP_THREADS + threadIdx.x, n, e)) {
+            rec += (unsigned long long)e.n_rows * e.n_t;
+            crs += e.n_rows;
+        }
+    }
+    // block reduce -> one atomic per block
+    __shared__ unsigned long long s_rec[SETUP_THREADS / 32], s_crs[SETUP_THREADS / 32];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        rec += __shfl_down_sync(0xffffffffu, rec, o);
+        crs += __shfl_down_sync(0xffffffffu, crs, o);
+    }
+    if (lane_id() == 0) { s_rec[threadIdx.x >> 5] = rec; s_crs[threadIdx.x >> 5] = crs; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < SETUP_THREADS / 32; w++) { rec += s_rec[w]; crs += s_crs[w]; }
+        if (rec) atomicAdd(&ctr->records, rec);
+        if (crs) atomicAdd(&ctr->crossings, crs);
+    }
+}
+
+// Emit: every block reserves a contiguous range of the record buffer with one atomic (record order
+// before the sort is irrelevant), short edges are written by their own thread, long edges by the
+// whole warp with lanes striding the edge's rows.
+__global__ void __launch_bounds__(SETUP_THREADS)
+poly_emit_kernel(KParams P, const double* __restrict__ x, const double* __restrict__ y,
+                 const uint32_t* __restrict__ tag, uint32_t n, const PartInfo* __restrict__ info,
+                 Counters* __restrict__ ctr, uint64_t* __restrict__ keys) {
+    __shared__ uint32_t s_warp[33];
+    __shared__ unsigned long long s_base;
+    uint32_t base = blockIdx.x * (SETUP_THREADS * SETUP_ITEMS);
+    PolyEdgeRec e[SETUP_ITEMS];
+    uint32_t cnt[SETUP_ITEMS];
+    uint32_t mine = 0;
+#pragma unroll
+    for (int r = 0; r < SETUP_ITEMS; r++) {
+        poly_edge_setup(P, x, y, tag, info, base + r * SETUP_THREADS + threadIdx.x, n, e[r]);
+        cnt[r] = e[r].n_rows * e[r].n_t;
+        mine += cnt[r];
+    }
+    uint32_t total;
+    uint32_t off = block_exclusive_scan(mine, s_warp, &total);
+    if (total == 0) return;
+    if (threadIdx.x == 0) s_base = atomicAdd(&ctr->cursor, (unsigned long long)total);
+    __syncthreads();
+    uint64_t* out = keys + s_base + off;
+    uint32_t lane = lane_id();
+#pragma unroll
+    for (int r = 0; r < SETUP_ITEMS; r++) {
+        bool is_long = cnt[r] > LONG_EDGE;
+        if (!is_long) {
+            uint32_t k = 0;
+            for (uint32_t row = 0; row < e[r].n_rows; row++)
+                for (uint32_t t = 0; t < e[r].n_t; t++) out[k++] = poly_key(P, e[r], e[r].row_lo + row, e[r].t_lo + t);
+        }
+        uint32_t m = __ballot_sync(0xffffffffu, is_long);
+        while (m) {
+            int src = __ffs(m) - 1;
+            m &= m - 1;
+            PolyEdgeRec b;
+            b.x_top = __shfl_sync(0xffffffffu, e[r].x_top, src);
+            b.y_top = __shfl_sync(0xffffffffu, e[r].y_top, src);
+            b.dxdy = __shfl_sync(0xffffffffu, e[r].dxdy, src);
+            b.row_lo = __shfl_sync(0xffffffffu, e[r].row_lo, src);
+            b.n_rows = __shfl_sync(0xffffffffu, e[r].n_rows, src);
+            b.part = __shfl_sync(0xffffffffu, e[r].part, src);
+            b.band = __shfl_sync(0xffffffffu, e[r].band, src);
+            b.t_lo = __shfl_sync(0xffffffffu, e[r].t_lo, src);
+            b.n_t = __shfl_sync(0xffffffffu, e[r].n_t, src);
+            unsigned long long p = (unsigned long long)(uintptr_t)out;
+            uint64_t* bout = (uint64_t*)(uintptr_t)__shfl_sync(0xffffffffu, p, src);
+            uint32_t tot = b.n_rows * b.n_t;
+            for (uint32_t k = lane; k < tot; k += 32) {
+                uint32_t row = k / b.n_t, t = k - row * b.n_t;
+                bout[k] = poly_key(P, b, b.row_lo + row, b.t_lo + t);
+            }
+        }
+        out += cnt[r];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// line segments — rust/src/geo/edges.rs:112-134; burners.rs:35-92
+// ---------------------------------------------------------------------------------------------
+// The reference walks an integer Bresenham loop.  Iteration k (k = 0 .. L-1, L = max(dx,|dy|))
+// visits   major = m0 + s_major*k,   minor = n0 + s_minor * floor((2*d_minor*k + d_major) / (2*d_major))
+// (derived from the error recurrence at burners.rs:60-84; tests/test_bresenham.py checks the closed
+// form against the loop exhaustively).  That lets us clip to the window in O(1) and emit any k.
+struct LineRec {
+    long long ix0, iy0;
+    long long dmaj, dmin;  // |delta| along major / minor axis
+    int sx, sy;
+    int xmajor;
+    uint32_t k_lo, n;      // iterations [k_lo, k_lo+n) are inside the window
+    uint32_t part;
+    int32_t band;
+};
+
+constexpr long long LINE_DOMAIN = 1LL << 29;
+
+__device__ __forceinline__ long long ceil_div(long long a, long long b) {  // b > 0
+    long long q = a / b, r = a % b;
+    return q + ((r != 0) && (r > 0));
+}
+__device__ __forceinline__ long long floor_div(long long a, long long b) {  // b > 0
+    long long q = a / b, r = a % b;
+    return q - ((r != 0) && (r < 0));
+}
+
+// pixel visited by iteration k
+__device__ __forceinline__ void line_pixel(const LineRec& l, long long k, long long& px, long long& py) {
+    long long q = l.dmaj > 0 ? (2 * l.dmin * k + l.dmaj) / (2 * l.dmaj) : 0;
+    if (l.xmajor) { px = l.ix0 + l.sx * k; py = l.iy0 + l.sy * q; }
+    else { py = l.iy0 + l.sy * k; px = l.ix0 + l.sx * q; }
+}
+
+// intersect [klo,khi] with { k : lo <= c0 + s*k < hi }
+__device__ __forceinline__ void clip_linear(long long c0, int s, long long lo, long long hi, long long& klo, long long& khi) {
+    if (s > 0) { klo = max(klo, lo - c0); khi = min(khi, hi - 1 - c0); }
+    else { klo = max(klo, c0 - hi + 1); khi = min(khi, c0 - lo); }
+}
+// intersect [klo,khi] with { k : lo <= c0 + s*q(k) < hi }, q(k) = floor((2*dmin*k + dmaj)/(2*dmaj))
+__device__ __forceinline__ void clip_stepped(long long c0, int s, long long lo, long long hi, long long dmin, long long dmaj,
+                                             long long& klo, long long& khi) {
+    long long qa, qb;  // need qa <= q <= qb
+    if (s > 0) { qa = lo - c0; qb = hi - 1 - c0; }
+    else { qa = c0 - hi + 1; qb = c0 - lo; }
+    if (dmin == 0) {  // q == 0 for every k
+        if (qa > 0 || qb < 0) khi = klo - 1;
+        return;
+    }
+    // q >= qa  <=>  k >= ceil((2*dmaj*qa - dmaj) / (2*dmin));   q <= qb  <=>  k <= ceil((2*dmaj*(qb+1) - dmaj)/(2*dmin)) - 1
+    if (qa > 0) klo = max(klo, ceil_div(2 * dmaj * qa - dmaj, 2 * dmin));
+    if (qb < 0) { khi = klo - 1; return; }
+    if (qb < dmin) khi = min(khi, ceil_div(2 * dmaj * (qb + 1) - dmaj, 2 * dmin) - 1);
+}
+
+__device__ __forceinline__ bool line_setup(const KParams& P, const double* __restrict__ x, const double* __restrict__ y,
+                                           const uint32_t* __restrict__ tag, const PartInfo* __restrict__ info,
+                                           uint32_t i, uint32_t n, LineRec& l, bool* kept, Counters* ctr) {
+    l.n = 0;
+    *kept = false;
+    if (i >= n) return false;
+    uint32_t t = tag[i];
+    if (t & 0x80000000u) return false;
+    l.part = t & 0x3fffffffu;
+    PartInfo pi = info[l.part];
+    if (pi.band < 0) return false;
+    l.band = pi.band;
+    double x0 = px_x(P, x[i]), y0 = px_y(P, y[i]);
+    double x1 = px_x(P, x[i + 1]), y1 = px_y(P, y[i + 1]);
+    double min_x = fmin(x0, x1), max_x = fmax(x0, x1), min_y = fmin(y0, y1), max_y = fmax(y0, y1);
+    if (!(min_x < P.ncols_f && max_x >= 0.0 && min_y < P.nrows_f && max_y >= 0.0)) return false;  // edges.rs:130
+    *kept = true;
+    long long ix0 = sat_i64(floor(x0)), ix1 = sat_i64(floor(x1));
+    long long iy0 = sat_i64(floor(y0)), iy1 = sat_i64(floor(y1));
+    if (llabs(ix0) > LINE_DOMAIN || llabs(ix1) > LINE_DOMAIN || llabs(iy0) > LINE_DOMAIN || llabs(iy1) > LINE_DOMAIN) {
+        atomicOr(&ctr->bad_line, 1u);
+        return false;
+    }
+    long long dx = llabs(ix1 - ix0), dy = llabs(iy1 - iy0);
+    l.ix0 = ix0;
+    l.iy0 = iy0;
+    l.sx = ix0 < ix1 ? 1 : -1;
+    l.sy = iy0 < iy1 ? 1 : -1;
+    l.xmajor = dx >= dy;
+    l.dmaj = l.xmajor ? dx : dy;
+    l.dmin = l.xmajor ? dy : dx;
+    long long klo = 0, khi = l.dmaj - 1;  // the segment's last pixel is not written by the loop
+    if (l.xmajor) {
+        clip_linear(ix0, l.sx, 0, (long long)P.ncols, klo, khi);
+        clip_stepped(iy0, l.sy, (long long)P.win_r0, (long long)P.win_r1, l.dmin, l.dmaj, klo, khi);
+    } else {
+        clip_linear(iy0, l.sy, (long long)P.win_r0, (long long)P.win_r1, klo, khi);
+        clip_stepped(ix0, l.sx, 0, (long long)P.ncols, l.dmin, l.dmaj, klo, khi);
+    }
+    if (khi < klo) return true;
+    l.k_lo = (uint32_t)klo;
+    l.n = (uint32_t)(khi - klo + 1);
+    return true;
+}
+
+__device__ __forceinline__ uint64_t pixel_key(const KParams& P, int32_t band, uint32_t part, uint32_t row, uint32_t col) {
+    uint32_t tile = col >> P.tile_shift;
+    uint64_t task = ((uint64_t)band * (P.win_r1 - P.win_r0) + (row - P.win_r0)) * P.n_tiles + tile;
+    return (task << P.task_shift) | ((uint64_t)part << P.part_shift) | (col - (tile << P.tile_shift));
+}
+
+__device__ __forceinline__ uint64_t line_key(const KParams& P, const LineRec& l, uint32_t k) {
+    long long px, py;
+    line_pixel(l, (long long)k, px, py);
+    return pixel_key(P, l.band, l.part, (uint32_t)py, (uint32_t)px);
+}
+
+// count pass; also records, per line part, the highest kept segment (the one that may write its end pixel)
+__global__ void __launch_bounds__(SETUP_THREADS)
+line_count_kernel(KParams P, const double* __restrict__ x, const double* __restrict__ y,
+                  const uint32_t* __restrict__ tag, uint32_t n, const PartInfo* __restrict__ info,
+                  uint32_t* __restrict__ last_kept, Counters* __restrict__ ctr) {
+    unsigned long long rec = 0;
+    uint32_t base = blockIdx.x * (SETUP_THREADS * SETUP_ITEMS);
+#pragma unroll
+    for (int r = 0; r < SETUP_ITEMS; r++) {
+        LineRec l;
+        bool kept;
+        uint32_t i = base + r * SETUP_THREADS + threadIdx.x;
+        line_setup(P, x, y, tag, info, i, n, l, &kept, ctr);
+        rec += l.n;
+        if (kept) atomicMax(&last_kept[l.part], i + 1);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) rec += __shfl_down_sync(0xffffffffu, rec, o);
+    if (lane_id() == 0 && rec) atomicAdd(&ctr->records, rec);
+}
+
+__global__ void __launch_bounds__(SETUP_THREADS)
+line_emit_kernel(KParams P, const double* __restrict__ x, const double* __restrict__ y,
+                 const uint32_t* __restrict__ tag, uint32_t n, const PartInfo* __restrict__ info,
+                 Counters* __restrict__ ctr, uint64_t* __restrict__ keys) {
+    __shared__ uint32_t s_warp[33];
+    __shared__ unsigned long long s_base;
+    uint32_t base = blockIdx.x * (SETUP_THREADS * SETUP_ITEMS);
+    LineRec l[SETUP_ITEMS];
+    uint32_t mine = 0;
+#pragma unroll
+    for (int r = 0; r < SETUP_ITEMS; r++) {
+        bool kept;
+        line_setup(P, x, y, tag, info, base + r * SETUP_THREADS + threadIdx.x, n, l[r], &kept, ctr);
+        mine += l[r].n;
+    }
+    uint32_t total;
+    uint32_t off = block_exclusive_scan(mine, s_warp, &total);
+    if (total == 0) return;
+    if (threadIdx.x == 0) s_base = atomicAdd(&ctr->cursor, (unsigned long long)total);
+    __syncthreads();
+    uint64_t* out = keys + s_base + off;
+    uint32_t lane = lane_id();
+#pragma unroll
+    for (int r = 0; r < SETUP_ITEMS; r++) {
+        bool is_long = l[r].n > LONG_EDGE;
+        if (!is_long)
+            for (uint32_t k = 0; k < l[r].n; k++) out[k] = line_key(P, l[r], l[r].k_lo + k);
+        uint32_t m = __ballot_sync(0xffffffffu, is_long);
+        while (m) {
+            int src = __ffs(m) - 1;
+            m &= m - 1;
+            LineRec b;
+            b.ix0 = __shfl_sync(0xffffffffu, l[r].ix0, src);
+            b.iy0 = __shfl_sync(0xffffffffu, l[r].iy0, src);
+            b.dmaj = __shfl_sync(0xffffffffu, l[r].dmaj, src);
+            b.dmin = __shfl_sync(0xffffffffu, l[r].dmin, src);
+            b.sx = __shfl_sync(0xffffffffu, l[r].sx, src);
+            b.sy = __shfl_sync(0xffffffffu, l[r].sy, src);
+            b.xmajor = __shfl_sync(0xffffffffu, l[r].xmajor, src);
+            b.k_lo = __shfl_sync(0xffffffffu, l[r].k_lo, src);
+            b.n = __shfl_sync(0xffffffffu, l[r].n, src);
+            b.part = __shfl_sync(0xffffffffu, l[r].part, src);
+            b.band = __shfl_sync(0xffffffffu, l[r].band, src);
+            unsigned long long p = (unsigned long long)(uintptr_t)out;
+            uint64_t* bout = (uint64_t*)(uintptr_t)__shfl_sync(0xffffffffu, p, src);
+            for (uint32_t k = lane; k < b.n; k += 32) bout[k] = line_key(P, b, b.k_lo + k);
+        }
+        out += l[r].n;
+    }
+}
+
+// The end pixel of the last kept segment of a pooled line part is written iff that segment's own
+// line string is not closed (burners.rs:87-89).  One thread per part; mode 0 counts, mode 1 emits.
+__global__ void line_final_kernel(KParams P, const double* __restrict__ x, const double* __restrict__ y,
+                                  const uint32_t* __restrict__ tag, const uint8_t* __restrict__ part_kind,
+                                  const PartInfo* __restrict__ info, const uint32_t* __restrict__ last_kept,
+                                  Counters* __restrict__ ctr, uint64_t* __restrict__ keys, int mode) {
+    uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P.n_parts || part_kind[p] != 1) return;
+    uint32_t lk = last_kept[p];
+    if (lk == 0) return;
+    uint32_t i = lk - 1;
+    if (tag[i] & 0x40000000u) return;  // closed line string
+    PartInfo pi = info[p];
+    if (pi.band < 0) return;
+    long long ix1 = sat_i64(floor(px_x(P, x[i + 1]))), iy1 = sat_i64(floor(px_y(P, y[i + 1])));
+    if (ix1 < 0 || ix1 >= (long long)P.ncols || iy1 < (long long)P.win_r0 || iy1 >= (long long)P.win_r1) return;
+    if (mode == 0) atomicAdd(&ctr->records, 1ull);
+    else keys[atomicAdd(&ctr->cursor, 1ull)] = pixel_key(P, pi.band, p, (uint32_t)iy1, (uint32_t)ix1);
+}
+
+// ---------------------------------------------------------------------------------------------
+// points — rust/src/geo/edges.rs:79-88; burners.rs:250-258
+// ---------------------------------------------------------------------------------------------
+__global__ void point_kernel(KParams P, const double* __restrict__ x, const double* __restrict__ y,
+                             const uint32_t* __restrict__ tag, uint32_t n, const PartInfo* __restrict__ info,
+                             Counters* __restrict__ ctr, uint64_t* __restrict__ keys, int mode) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    bool hit = false;
+    uint64_t key = 0;
+    if (i < n) {
+        uint32_t part = tag[i] & 0x3fffffffu;
+        PartInfo pi = info[part];
+        double px = px_x(P, x[i]), py = px_y(P, y[i]);
+        if (pi.band >= 0 && px >= 0.0 && px < P.ncols_f && py >= 0.0 && py < P.nrows_f) {
+            uint32_t col = (uint32_t)px, row = (uint32_t)py;  // `as usize` of an in-range value truncates
+            if (row >= P.win_r0 && row < P.win_r1) {
+                hit = true;
+                if (mode) key = pixel_key(P, pi.band, part, row, col);
+            }
+        }
+    }
+    uint32_t m = __ballot_sync(0xffffffffu, hit);
+    if (m == 0) return;
+    uint32_t lane = lane_id();
+    unsigned long long base = 0;
+    if (lane == 0) base = atomicAdd(mode ? &ctr->cursor : &ctr->records, (unsigned long long)__popc(m));
+    if (mode) {
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (hit) keys[base + __popc(m & ((1u << lane) - 1))] = key;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// LSD radix sort, 8-bit digits, 64-bit keys (keys only)
+// ---------------------------------------------------------------------------------------------
+constexpr int RS_THREADS = 256;
+constexpr int RS_ITEMS = 16;
+constexpr int RS_TILE = RS_THREADS * RS_ITEMS;  // 4096 keys per block
+constexpr int RS_RADIX = 256;
+
+// per-block digit histogram, stored digit-major: hist[d * n_blocks + b]
+__global__ void __launch_bounds__(RS_THREADS)
+radix_hist_kernel(const uint64_t* __restrict__ keys, uint32_t n, uint32_t shift, uint32_t n_blocks,
+                  uint32_t* __restrict__ hist) {
+    __shared__ uint32_t s[RS_RADIX];
+    s[threadIdx.x] = 0;
+    __syncthreads();
+    uint32_t base = blockIdx.x * RS_TILE;
+#pragma unroll
+    for (int r = 0; r < RS_ITEMS; r++) {
+        uint32_t i = base + r * RS_THREADS + threadIdx.x;
+        if (i < n) atomicAdd(&s[(uint32_t)(keys[i] >> shift) & (RS_RADIX - 1)], 1u);
+    }
+    __syncthreads();
+    hist[threadIdx.x * n_blocks + blockIdx.x] = s[threadIdx.x];
+}
+
+// one block per digit: exclusive scan of its row of block counts (in place) + digit total
+__global__ void __launch_bounds__(1024)
+radix_scan_rows_kernel(uint32_t* __restrict__ hist, uint32_t n_blocks, uint32_t* __restrict__ digit_total) {
+    __shared__ uint32_t s_warp[33];
+    uint32_t* row = hist + (size_t)blockIdx.x * n_blocks;
+    uint32_t carry = 0;
+    uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
+    for (uint32_t b0 = 0; b0 < n_blocks; b0 += 1024) {
+        uint32_t i = b0 + threadIdx.x;
+        uint32_t v = i < n_blocks ? row[i] : 0, inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= (uint32_t)o) inc += t;
+        }
+        if (lane == 31) s_warp[warp] = inc;
+        __syncthreads();
+        if (warp == 0) {
+            uint32_t w = s_warp[lane], winc = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                uint32_t t = __shfl_up_sync(0xffffffffu, winc, o);
+                if (lane >= (uint32_t)o) winc += t;
+            }
+            s_warp[lane] = winc - w;
+            if (lane == 31) s_warp[32] = winc;
+        }
+        __syncthreads();
+        if (i < n_blocks) row[i] = carry + s_warp[warp] + inc - v;
+        carry += s_warp[32];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) digit_total[blockIdx.x] = carry;
+}
+
+// Stable scatter.  Keys are ranked warp by warp, 32 consecutive keys per round, with
+// __match_any_sync; the tile is then staged in shared memory in sorted order so that global stores
+// go out in runs of equal digits.
+__global__ void __launch_bounds__(RS_THREADS)
+radix_scatter_kernel(const uint64_t* __restrict__ keys_in, uint64_t* __restrict__ keys_out, uint32_t n, uint32_t shift,
+                     uint32_t n_blocks, const uint32_t* __restrict__ hist, const uint32_t* __restrict__ digit_total) {
+    __shared__ uint64_t s_keys[RS_TILE];
+    __shared__ uint32_t s_cnt[RS_THREADS / 32][RS_RADIX];
+    __shared__ uint32_t s_dbase[RS_RADIX];   // first block-sorted position of each digit
+    __shared__ uint32_t s_goff[RS_RADIX];    // global offset minus block-sorted position
+    __shared__ uint32_t s_warp[33];
+    const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
+    for (int w = 0; w < RS_THREADS / 32; w++) s_cnt[w][threadIdx.x] = 0;
+    __syncthreads();
+    const uint32_t tile0 = blockIdx.x * RS_TILE;
+    const uint32_t wbase = tile0 + warp * (32 * RS_ITEMS);
+    uint64_t key[RS_ITEMS];
+    uint16_t rank[RS_ITEMS];
+#pragma unroll
+    for (int r = 0; r < RS_ITEMS; r++) {
+        uint32_t i = wbase + r * 32 + lane;
+        key[r] = i < n ? keys_in[i] : ~0ull;  // padding sorts after every real key of the tile
+    }
+#pragma unroll
+    for (int r = 0; r < RS_ITEMS; r++) {
+        uint32_t d = (uint32_t)(key[r] >> shift) & (RS_RADIX - 1);
+        uint32_t peers = __match_any_sync(0xffffffffu, d);
+        int leader = __ffs(peers) - 1;
+        uint32_t c = 0;
+        if ((int)lane == leader) {
+            c = s_cnt[warp][d];
+            s_cnt[warp][d] = c + __popc(peers);
+        }
+        c = __shfl_sync(0xffffffffu, c, leader);
+        rank[r] = (uint16_t)(c + __popc(peers & ((1u << lane) - 1)));
+        __syncwarp();
+    }
+    __syncthreads();
+    // thread d: turn per-warp counts of digit d into exclusive warp bases, get the block count
+    uint32_t d = threadIdx.x, run = 0;
+#pragma unroll
+    for (int w = 0; w < RS_THREADS / 32; w++) {
+        uint32_t t = s_cnt[w][d];
+        s_cnt[w][d] = run;
+        run += t;
+    }
+    uint32_t tot;
+    uint32_t dbase = block_exclusive_scan(run, s_warp, &tot);
+    // global base of digit d for this block = (keys of smaller digits) + (digit d in earlier blocks)
+    uint32_t gd = 0;
+    {
+        // exclusive scan of digit totals (256 values) — reuse the same block scan
+        uint32_t t2;
+        uint32_t dt = digit_total[d];
+        gd = block_exclusive_scan(dt, s_warp, &t2);
+    }
+    s_dbase[d] = dbase;
+    s_goff[d] = gd + hist[d * n_blocks + blockIdx.x] - dbase;
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < RS_ITEMS; r++) {
+        uint32_t dd = (uint32_t)(key[r] >> shift) & (RS_RADIX - 1);
+        s_keys[s_dbase[dd] + s_cnt[warp][dd] + rank[r]] = key[r];
+    }
+    __syncthreads();
+    uint32_t n_valid = min((uint32_t)RS_TILE, n - tile0);
+#pragma unroll
+    for (int r = 0; r < RS_ITEMS; r++) {
+        uint32_t pos = r * RS_THREADS + threadIdx.x;
+        if (pos < n_valid) {
+            uint64_t k = s_keys[pos];
+            uint32_t dd = (uint32_t)(k >> shift) & (RS_RADIX - 1);
+            keys_out[s_goff[dd] + pos] = k;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// task index: first record of every task (lower bound on the sorted keys)
+// ---------------------------------------------------------------------------------------------
+__global__ void task_index_kernel(const uint64_t* __restrict__ keys, uint32_t n, uint32_t task_shift, uint32_t n_tasks,
+                                  uint32_t* __restrict__ task_start) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t > n_tasks) return;
+    uint32_t lo = 0, hi = n;
+    while (lo < hi) {
+        uint32_t mid = lo + ((hi - lo) >> 1);
+        if ((keys[mid] >> task_shift) < (uint64_t)t) lo = mid + 1;
+        else hi = mid;
+    }
+    task_start[t] = lo;
+}
+
+// ---------------------------------------------------------------------------------------------
+// pixel functions — rust/src/rasterization/pixel_functions.rs:56-123
+// ---------------------------------------------------------------------------------------------
+template <typename N> __device__ __forceinline__ bool is_nan_v(N) { return false; }
+template <> __device__ __forceinline__ bool is_nan_v<float>(float v) { return v != v; }
+template <> __device__ __forceinline__ bool is_nan_v<double>(double v) { return v != v; }
+
+template <typename N> struct Wrap { typedef N U; };
+template <> struct Wrap<int8_t> { typedef uint8_t U; };
+template <> struct Wrap<int16_t> { typedef uint16_t U; };
+template <> struct Wrap<int32_t> { typedef uint32_t U; };
+template <> struct Wrap<int64_t> { typedef uint64_t U; };
+// Rust release-mode `+=` (wrapping for integers; one rounding for floats)
+template <typename N> __device__ __forceinline__ N add_v(N a, N b) {
+    typedef typename Wrap<N>::U U;
+    return (N)(U)((U)a + (U)b);
+}
+template <> __device__ __forceinline__ float add_v<float>(float a, float b) { return __fadd_rn(a, b); }
+template <> __device__ __forceinline__ double add_v<double>(double a, double b) { return __dadd_rn(a, b); }
+
+template <typename N, int FN> __device__ __forceinline__ N apply_px(N cur, N v, N bg) {
+    bool untouched = (cur == bg) || is_nan_v(cur);
+    if (FN == RZ_SUM) return (untouched || is_nan_v(v)) ? v : add_v(cur, v);
+    if (FN == RZ_FIRST) return untouched ? v : cur;
+    if (FN == RZ_LAST) return v;
+    if (FN == RZ_MIN) return (untouched || cur > v) ? v : cur;
+    if (FN == RZ_MAX) return (untouched || cur < v) ? v : cur;
+    if (FN == RZ_COUNT) return untouched ? (N)1 : add_v(cur, (N)1);
+    return (N)1;  // any
+}
+
+template <typename N> __device__ __forceinline__ N value_from_bits(uint64_t b) {
+    N v;
+    memcpy(&v, &b, sizeof(N));
+    return v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// fill — one warp per (band, row, column tile)
+// ---------------------------------------------------------------------------------------------
+struct FillParams {
+    uint32_t n_tasks, n_tiles, tile_w, ncols;
+    uint32_t win_rows;         // rows in this window
+    uint32_t win_row_off;      // first window row relative to the output's first row
+    uint32_t out_rows;         // rows per band in `out`
+    uint32_t col_bits, part_shift, part_bits;
+    uint32_t dedup_lines;
+    uint32_t vec_ok;           // rows of `out` are 16-byte aligned
+};
+
+constexpr int FILL_WARPS = 4;
+
+template <typename N, int FN>
+__global__ void __launch_bounds__(FILL_WARPS * 32)
+fill_kernel(FillParams F, const uint64_t* __restrict__ keys, const uint32_t* __restrict__ task_start,
+            const PartInfo* __restrict__ info, const uint8_t* __restrict__ part_kind, uint64_t bg_bits,
+            N* __restrict__ out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
+    N* row = reinterpret_cast<N*>(smem_raw) + (size_t)warp * F.tile_w;
+    const N bg = value_from_bits<N>(bg_bits);
+    const uint32_t col_mask = (1u << F.col_bits) - 1u;
+    const uint64_t part_mask = (1ull << F.part_bits) - 1ull;
+
+    for (uint32_t task = blockIdx.x * FILL_WARPS + warp; task < F.n_tasks; task += gridDim.x * FILL_WARPS) {
+        const uint32_t tile = task % F.n_tiles;
+        const uint32_t br = task / F.n_tiles;  // band * win_rows + row
+        const uint32_t band = br / F.win_rows, r = br - band * F.win_rows;
+        const uint32_t c0 = tile * F.tile_w;
+        const uint32_t w = min(F.tile_w, F.ncols - c0);
+        N* dst = out + ((size_t)band * F.out_rows + F.win_row_off + r) * F.ncols + c0;
+        const uint32_t beg = task_start[task], end = task_start[task + 1];
+
+        for (uint32_t i = lane; i < w; i += 32) row[i] = bg;
+        __syncwarp();
+
+        uint64_t carry_hi = ~0ull;   // (task|part) of the record before this chunk
+        uint64_t carry_key = ~0ull;  // full key of the record before this chunk
+        uint32_t carry_par = 0;      // index parity of this chunk's lane 0 within its part run
+        for (uint32_t base = beg; base < end; base += 32) {
+            const uint32_t i = base + lane;
+            const bool valid = i < end;
+            const uint64_t key = valid ? keys[i] : ~0ull;
+            uint64_t nxt = __shfl_down_sync(0xffffffffu, key, 1);
+            if (lane == 31) nxt = (i + 1 < end) ? keys[i + 1] : ~0ull;
+            const uint64_t hi = key >> F.col_bits;
+            uint64_t prev_hi = __shfl_up_sync(0xffffffffu, hi, 1);
+            uint64_t prev_key = __shfl_up_sync(0xffffffffu, key, 1);
+            if (lane == 0) { prev_hi = carry_hi; prev_key = carry_key; }
+            const bool head = hi != prev_hi;
+            const uint32_t heads = __ballot_sync(0xffffffffu, head);
+            const uint32_t below = heads & (0xffffffffu >> (31 - lane));
+            const uint32_t par = below ? ((lane - (31 - __clz(below))) & 1u) : ((carry_par + lane) & 1u);
+            const uint32_t part = (uint32_t)((key >> F.part_shift) & part_mask);
+            const uint32_t kind = valid ? part_kind[part] : 0;
+            const uint32_t col = (uint32_t)key & col_mask, ncol = (uint32_t)nxt & col_mask;
+            bool start;
+            uint32_t xs = col, xe;
+            if (kind == 0) {  // polygon crossing: even-odd pairs within (task, part); odd tail dropped
+                xe = ncol;
+                start = valid && par == 0 && (nxt >> F.col_bits) == hi && col < ncol;
+            } else {          // line / point pixel
+                xe = col + 1;
+                start = valid && !(kind == 1 && F.dedup_lines && key == prev_key);
+            }
+            N v = start ? value_from_bits<N>(info[part].value_bits) : (N)0;
+            uint32_t m = __ballot_sync(0xffffffffu, start);
+            while (m) {
+                const int src = __ffs(m) - 1;
+                m &= m - 1;
+                const uint32_t bxs = __shfl_sync(0xffffffffu, xs, src);
+                const uint32_t bxe = __shfl_sync(0xffffffffu, xe, src);
+                const N bv = __shfl_sync(0xffffffffu, v, src);
+                for (uint32_t p = bxs + lane; p < bxe; p += 32) row[p] = apply_px<N, FN>(row[p], bv, bg);
+                __syncwarp();
+            }
+            carry_hi = __shfl_sync(0xffffffffu, hi, 31);
+            carry_key = __shfl_sync(0xffffffffu, key, 31);
+            carry_par = (__shfl_sync(0xffffffffu, par, 31) + 1u) & 1u;
+        }
+
+        // flush the tile: every output byte is written exactly once
+        if (F.vec_ok && (w * sizeof(N)) % 16 == 0) {
+            const uint4* s4 = reinterpret_cast<const uint4*>(row);
+            uint4* d4 = reinterpret_cast<uint4*>(dst);
+            const uint32_t n4 = (uint32_t)(w * sizeof(N) / 16);
+            for (uint32_t i = lane; i < n4; i += 32) __stcs(d4 + i, s4[i]);
+        } else {
+            for (uint32_t i = lane; i < w; i += 32) dst[i] = row[i];
+        }
+        __syncwarp();
+    }
+}
+
+}  // namespace rz
