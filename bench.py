@@ -1,0 +1,372 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the B200 burn path.
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (one rank per GPU under torchrun)
+    python bench.py --impl reference --steps K --warmup W    # CPU restatement of the reference (oracle)
+
+Workload (BASELINE.json configs[3], the one `north_star`'s target is quoted on): 1M synthetic star
+polygons (100..300 vertices, seed 4) -> 65536 x 65536 float32 grid, fun=sum, background=NaN.  With
+N GPUs the raster is split into N row bands (no collective; strong scaling: total work is fixed).
+
+One "step" = one full rasterisation.  `value` is device-resident throughput (geometry already in
+HBM, raster left in HBM); `e2e` goes through the public call with pinned HOST buffers: geometry
+host->device and raster device->host inside the timed region.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tests"))
+
+WORKLOADS = {
+    # name: (n_polys, vmin, vmax, rho, rows, cols, dtype, fun, seed)
+    "c4": dict(n=1_000_000, vmin=100, vmax=300, rho=48.0, rows=65536, cols=65536, dtype="float32", fun="sum", seed=4,
+               desc="1M star polygons (100-300 vertices) -> 65536x65536 f32, fun=sum, bg=NaN"),
+    "c1": dict(n=10_000, vmin=64, vmax=64, rho=82.0, rows=4096, cols=4096, dtype="float64", fun="sum", seed=1,
+               desc="10k 64-vertex star polygons -> 4096x4096 f64, fun=sum, bg=NaN"),
+    "tiny": dict(n=2_000, vmin=16, vmax=48, rho=24.0, rows=1024, cols=1024, dtype="float32", fun="sum", seed=7,
+                 desc="2k star polygons -> 1024x1024 f32 (CI smoke size)"),
+}
+
+
+def make_workload(name: str, scale: float = 1.0):
+    import synth
+
+    w = dict(WORKLOADS[name])
+    if scale != 1.0:  # shrink polygons and grid together (keeps density)
+        w["n"] = max(1, int(w["n"] * scale))
+        side = max(64, int(w["rows"] * scale ** 0.5) // 64 * 64)
+        w["rows"] = w["cols"] = side
+    x, y, off = synth.star_polygons(w["seed"], w["n"], w["vmin"], w["vmax"], w["rho"], w["cols"], w["rows"])
+    vals = synth.splitmix_u(w["seed"], w["n"], 9).astype(w["dtype"])
+    return w, x, y, off, vals
+
+
+def band_of(rank: int, world: int, rows: int):
+    r0 = rows * rank // world
+    r1 = rows * (rank + 1) // world
+    return r0, r1
+
+
+def select_band_polygons(x, y, off, vals, rows_total, r0, r1):
+    """Polygons whose y-extent can touch raster rows [r0, r1) (world y = rows_total - pixel y; res 1).
+    Order is preserved, so results equal the unsharded run."""
+    o = off.astype(np.int64)
+    ymin = np.minimum.reduceat(y, o[:-1])
+    ymax = np.maximum.reduceat(y, o[:-1])
+    # pixel rows covered: [rows_total - ymax, rows_total - ymin]; keep a 1-row margin
+    keep = (rows_total - ymax <= r1 + 1) & (rows_total - ymin >= r0 - 1)
+    if keep.all():
+        return x, y, off, vals
+    cnt = (o[1:] - o[:-1])[keep]
+    idx = np.repeat(o[:-1][keep], cnt) + (np.arange(int(cnt.sum())) - np.repeat(np.cumsum(cnt) - cnt, cnt))
+    noff = np.zeros(len(cnt) + 1, np.uint64)
+    noff[1:] = np.cumsum(cnt)
+    return x[idx], y[idx], noff, vals[keep]
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.idx)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            p = [s.strip() for s in ln.split(",")]
+            if len(p) < 9:
+                continue
+            try:
+                sm.append(float(p[1]))
+                mx.append(float(p[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, p[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle (C++ restatement of the reference's CPU algorithm) on a bounded sample
+# ------------------------------------------------------------------------------------------------
+def cpu_sample(w, x, y, off, vals, sample_rows: int):
+    """Rows [0, sample_rows) of the workload's raster with every polygon that can touch them; the
+    oracle burns them onto a sample_rows x cols grid aligned with the full grid."""
+    import oracle
+
+    sx, sy, soff, svals = select_band_polygons(x, y, off, vals, w["rows"], 0, sample_rows)
+    g = oracle.Geoms.from_rings(sx, sy, soff)
+    ri = oracle.raster_info(None, shape=(sample_rows, w["cols"]),
+                            extent=(0.0, float(w["rows"] - sample_rows), float(w["cols"]), float(w["rows"])))
+    return g, ri, svals, len(soff) - 1
+
+
+def time_oracle(w, g, ri, svals, steps: int, warmup: int):
+    import oracle
+
+    bg = np.nan if w["dtype"].startswith("float") else 0
+    ts = []
+    out = None
+    for i in range(warmup + steps):
+        t = time.perf_counter()
+        out, _ = oracle.rasterize_dense(g, ri, w["fun"], w["dtype"], svals, None, None, bg, threads=1)
+        if i >= warmup:
+            ts.append(time.perf_counter() - t)
+    return float(np.mean(ts)), out
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    w, x, y, off, vals = make_workload(args.workload, args.scale)
+    sample_rows = min(w["rows"], args.cpu_sample_rows)
+    g, ri, svals, n_s = cpu_sample(w, x, y, off, vals, sample_rows)
+    sec, _ = time_oracle(w, g, ri, svals, args.steps, args.warmup)
+    mpx = sample_rows * w["cols"] / sec / 1e6
+    sample = (f"rows [0,{sample_rows}) of the {w['rows']}x{w['cols']} grid with the {n_s} polygons touching them; "
+              "C++ restatement of the rusterize CPU algorithm (oracle/rz_oracle.cpp), 1 thread because the "
+              "reference parallelises over `by` bands only and this workload has one band")
+    line = {
+        "impl": "reference", "metric": "output_Mpixels_per_s", "value": mpx, "unit": "Mpixel/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64 geometry / %s values" % w["dtype"],
+        "data": "synthetic", "config": {"workload": f"{args.workload}: {w['desc']}", "scale": args.scale},
+        "polygons_per_s": n_s / sec,
+        "cpu_baseline": {"value": mpx, "unit": "Mpixel/s", "cores": 1, "kind": "port", "sample": sample,
+                         "host_cores_available": os.cpu_count()},
+        "e2e": {"value": mpx, "unit": "Mpixel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    from rusterize_b200 import _lib, core
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the burn path has no CPU fallback (use --impl reference)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    w, x, y, off, vals = make_workload(args.workload, args.scale)
+    rows, cols = w["rows"], w["cols"]
+    r0, r1 = band_of(rank, world, rows)
+    bx, by, boff, bvals = select_band_polygons(x, y, off, vals, rows, r0, r1)
+    geoms = core.Geoms.from_polygons(bx, by, boff)
+    ri = core.raster_info(None, shape=(rows, cols), extent=(0.0, 0.0, float(cols), float(rows)))
+    dt = np.dtype(w["dtype"])
+    bg = np.nan if dt.kind == "f" else 0
+    tdt = {"float32": torch.float32, "float64": torch.float64}[w["dtype"]]
+    d_out = torch.empty((1, r1 - r0, cols), dtype=tdt, device="cuda")
+    stream = torch.cuda.current_stream().cuda_stream
+    geoms.upload(local)
+
+    def step(flags=0, out=None):
+        return core.rasterize_dense(geoms, ri, w["fun"], w["dtype"], bvals, background=bg, device=local,
+                                    rows=(r0, r1), out=d_out.data_ptr() if out is None else out, stream=stream,
+                                    flags=flags, tile_bytes=args.tile_bytes)[1]
+
+    # ---- device-resident throughput --------------------------------------------------------------
+    for _ in range(args.warmup):
+        step()
+    sampler = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    stats = []
+    for _ in range(args.steps):
+        stats.append(step(flags=_lib.FLAG_SYNC_STAGES))
+    ev1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms = ev0.elapsed_time(ev1) / args.steps
+    t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+
+    # ---- end to end through the public call with pinned host buffers -------------------------
+    e2e = None
+    if not args.no_e2e:
+        h_out = torch.empty((1, r1 - r0, cols), dtype=tdt).pin_memory()
+        h_np = h_out.numpy()
+        n_e2e = max(1, min(args.steps, args.e2e_steps))
+        step(flags=_lib.FLAG_FORCE_H2D, out=h_np)  # warm
+        barrier()
+        t0 = time.perf_counter()
+        est = []
+        for _ in range(n_e2e):
+            est.append(step(flags=_lib.FLAG_FORCE_H2D, out=h_np))
+        barrier()
+        e_ms = (time.perf_counter() - t0) * 1e3 / n_e2e
+        t = torch.tensor([e_ms], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e_ms = float(t.item())
+        hb = torch.tensor([est[-1]["h2d_bytes"], est[-1]["d2h_bytes"]], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(hb)
+        e2e = {"value": rows * cols / (e_ms / 1e3) / 1e6, "unit": "Mpixel/s", "ms_per_step": e_ms,
+               "h2d_bytes_per_step": int(hb[0].item()), "d2h_bytes_per_step": int(hb[1].item()), "steps": n_e2e,
+               "checksum": float(np.nansum(h_np[0, :: max(1, (r1 - r0) // 64)], dtype=np.float64))}
+
+    # ---- gather per-rank stage stats -----------------------------------------------------------
+    keys = ["n_records", "n_crossings", "out_bytes", "kernel_launches"]
+    agg = torch.tensor([float(np.mean([s[k] for s in stats])) for k in keys], device="cuda", dtype=torch.float64)
+    stage = torch.tensor([float(np.mean([s[k] for s in stats])) for k in
+                          ["count_ms", "emit_ms", "sort_ms", "index_ms", "fill_ms"]], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(agg)
+        dist.all_reduce(stage, op=dist.ReduceOp.MAX)
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    peak, peak_src = peaks()
+    s0 = stats[-1]
+    fill_ms = float(np.mean([s["fill_ms"] for s in stats]))
+    fill_bytes = 8.0 * s0["n_records"] + s0["out_bytes"]          # rank 0's launch: records read once + raster written once
+    achieved = fill_bytes / (fill_ms / 1e3) / 1e9
+    traffic = None
+    tp = ROOT / "profiles" / "fill_traffic.json"
+    if tp.exists():
+        try:
+            traffic = json.loads(tp.read_text()).get(args.workload)
+        except Exception:
+            pass
+
+    # ---- CPU baseline on a bounded sample (rank 0, N=1 only) ---------------------------------
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        sample_rows = min(rows, args.cpu_sample_rows)
+        og, ori, svals, n_s = cpu_sample(w, x, y, off, vals, sample_rows)
+        sec, o_out = time_oracle(w, og, ori, svals, 1, 0)
+        # the sample doubles as a full-size parity check of the band's first rows
+        got = d_out[0, :sample_rows].cpu().numpy() if r0 == 0 else None
+        parity = None
+        if got is not None:
+            a, b = o_out[0], got
+            both_nan = np.isnan(a) & np.isnan(b)
+            parity = {"bit_exact": bool(np.array_equal(a, b, equal_nan=True)),
+                      "max_rel_err": float(np.max(np.where(both_nan, 0.0, np.abs(a - b) / np.maximum(np.abs(a), 1e-30))))}
+        cpu = {"value": sample_rows * cols / sec / 1e6, "unit": "Mpixel/s", "cores": 1, "kind": "port",
+               "sample": f"rows [0,{sample_rows}) of the grid with the {n_s} polygons touching them, oracle/rz_oracle.cpp, "
+                         "1 thread (the reference parallelises over `by` bands only)",
+               "seconds": sec, "parity_vs_gpu": parity, "host_cores_available": os.cpu_count()}
+
+    line = {
+        "metric": "output_Mpixels_per_s", "value": rows * cols / (ms_max / 1e3) / 1e6, "unit": "Mpixel/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f64 geometry / %s values" % w["dtype"], "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {w['desc']}", "scale": args.scale, "parallelism": f"row-bands x{world}",
+                   "l2": "inputs (vertex pools + record buffers + raster) are far larger than the 126 MB L2",
+                   "tile_bytes": args.tile_bytes or 4096},
+        "polygons_per_s": w["n"] / (ms_max / 1e3),
+        "stage_ms_max_over_ranks": dict(zip(["count", "emit", "sort", "index", "fill"], [float(v) for v in stage])),
+        "records": int(agg[0].item()), "crossings": int(agg[1].item()),
+        "gpu_launches": int(round(agg[3].item())) * args.steps,
+        "roofline": {"bound": "hbm", "kernel": "fill_kernel<float, sum>", "achieved": achieved, "peak": peak,
+                     "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                     "bytes_per_launch": fill_bytes, "ms_per_launch": fill_ms},
+        "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS))
+    ap.add_argument("--scale", type=float, default=1.0, help="shrink polygons and grid area by this factor")
+    ap.add_argument("--cpu-sample-rows", type=int, default=4096)
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--tile-bytes", type=int, default=0)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_b200(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

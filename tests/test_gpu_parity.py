@@ -1,0 +1,178 @@
+"""GPU parity: the CUDA burn path, called through the C ABI (rusterize_b200.core -> librz_b200.so),
+against the CPU oracle on identical inputs.  Bit-exact for every dtype and pixel function —
+including floating-point `sum`, because the fill kernel replays writes in the reference's order."""
+import numpy as np
+import pytest
+from PIL import Image
+
+import oracle
+import synth
+from cases import GEOMS, GEOMS_EXPLODED, R_INFO, VALUES, VALUES_EXPLODED, rmat, sq
+from rusterize_b200 import core
+
+pytestmark = pytest.mark.gpu
+GOLDEN = __import__("os").path.join(__import__("os").path.dirname(__file__), "golden")
+
+
+def both(geoms, fun="last", dtype="float64", burn=1, bg=0, by=None, field_valid=None, rows=None, tile_bytes=0, **kw):
+    og = oracle.Geoms.from_any(geoms)
+    ori = oracle.raster_info(og, **kw)
+    exp, names = oracle.rasterize_dense(og, ori, fun, dtype, burn, field_valid, by, bg)
+    g = core.Geoms.from_any(geoms)
+    ri = core.raster_info(g, **kw)
+    band, nb = None, 1
+    if by is not None:
+        band, bn = core.group_keys(by)
+        nb = len(bn)
+        assert bn == names
+    got, st = core.rasterize_dense(g, ri, fun, dtype, burn, field_valid, band, nb, bg, rows=rows, tile_bytes=tile_bytes)
+    if rows is not None:
+        exp = exp[:, rows[0]:rows[1]]
+    return exp, got, st
+
+
+def assert_same(exp, got):
+    assert exp.shape == got.shape and exp.dtype == got.dtype
+    assert np.array_equal(exp, got, equal_nan=exp.dtype.kind == "f"), f"{np.sum(exp != got)} pixels differ"
+
+
+def test_golden_tifs():
+    exp, got, _ = both(GEOMS, "sum", "uint8", VALUES, 0, resolution=(1, 1))
+    assert_same(exp, got)
+    assert np.array_equal(got[0], np.array(Image.open(f"{GOLDEN}/standard_output_sum.tif")))
+    exp, got, _ = both(GEOMS_EXPLODED, "sum", "uint8", VALUES_EXPLODED, 0, shape=(47, 319))
+    assert_same(exp, got)
+    assert np.array_equal(got[0], np.array(Image.open(f"{GOLDEN}/standard_output_sum_custom_shape.tif")))
+
+
+@pytest.mark.parametrize("fun,vals,expect", [
+    ("sum", [5, 7], 12), ("min", [5, 7], 5), ("max", [5, 7], 7), ("first", [5, 7], 5), ("last", [5, 7], 7),
+    ("count", [1, 1], 2), ("any", [5, 7], 1)])
+def test_r_known_answers(fun, vals, expect):
+    two = [sq(0, 0, 4, 4), sq(0, 0, 4, 4)]
+    exp, got, _ = both(two, fun, "float64", np.array(vals, float), 0.0, shape=(4, 4), extent=(0, 0, 4, 4))
+    assert_same(exp, got)
+    assert np.array_equal(got[0], np.full((4, 4), float(expect)))
+
+
+def test_r_geometry_cases():
+    kw = dict(shape=(4, 4), extent=(0, 0, 4, 4))
+    _, got, _ = both(["LINESTRING (0 0, 4 4)"], burn=9.0, **kw)
+    assert np.array_equal(got[0], rmat([0, 0, 0, 0, 0, 0, 0, 9, 0, 0, 9, 0, 0, 9, 0, 0]))
+    mp = "MULTIPOLYGON (((0 0, 2 0, 2 2, 0 2, 0 0)), ((2 2, 4 2, 4 4, 2 4, 2 2)))"
+    _, got, _ = both([mp], burn=9.0, **kw)
+    assert np.array_equal(got[0], rmat([0, 0, 9, 9, 0, 0, 9, 9, 9, 9, 0, 0, 9, 9, 0, 0]))
+    exp, got, _ = both([sq(0, 0, 2, 4), sq(2, 0, 4, 4)], burn=np.array([10.0, 20.0]), by=["a", "b"], **kw)
+    assert_same(exp, got)
+    assert np.array_equal(got[0], rmat([10] * 8 + [0] * 8)) and np.array_equal(got[1], rmat([0] * 8 + [20] * 8))
+
+
+@pytest.mark.parametrize("dtype", oracle.DTYPES)
+@pytest.mark.parametrize("fun", oracle.FUNS)
+def test_all_dtypes_and_functions_mixed_geometries(dtype, fun):
+    seed = oracle.DTYPES.index(dtype) * 7 + oracle.FUNS.index(fun)
+    geoms = synth.mixed_geometries(seed, 150, 300, 200, rho=20.0)
+    rng = np.random.default_rng(seed)
+    dt = np.dtype(dtype)
+    # values collide with the background and (for floats) include NaN: exercises the sentinel quirks
+    burn = rng.integers(0, 5, len(geoms)).astype(dt)
+    bg = 0
+    if dt.kind == "f":
+        burn[rng.random(len(geoms)) < 0.1] = np.nan
+        bg = np.nan if seed % 2 else 2.0
+    elif seed % 3 == 0:
+        bg = 2
+    exp, got, _ = both(geoms, fun, dtype, burn, bg, shape=(200, 300), extent=(0, 0, 300, 200))
+    assert_same(exp, got)
+
+
+def test_integer_wraparound_and_count_restart():
+    many = [sq(0, 0, 4, 4)] * 300
+    for fun, dtype, bg in [("sum", "uint8", 0), ("sum", "int8", 5), ("count", "uint8", 0), ("count", "uint8", 7),
+                           ("sum", "int16", -3)]:
+        exp, got, _ = both(many, fun, dtype, np.arange(300) % 120, bg, shape=(4, 4), extent=(0, 0, 4, 4))
+        assert_same(exp, got)
+
+
+def test_by_bands_lexicographic_and_null_fields():
+    geoms = synth.mixed_geometries(11, 200, 256, 256)
+    n = len(geoms)
+    by = [str(i % 12) for i in range(n)]
+    valid = (np.arange(n) % 5 != 0).astype(np.uint8)
+    for fun in ("first", "last", "min", "max"):
+        exp, got, _ = both(geoms, fun, "int32", 1 + (np.arange(n) * 2654435761 % 1000), 0, by=by, field_valid=valid,
+                           shape=(256, 256), extent=(0, 0, 256, 256))
+        assert exp.shape[0] == 12
+        assert_same(exp, got)
+
+
+def test_non_square_pixels_line_dedup():
+    rng = np.random.default_rng(5)
+    lines = []
+    for _ in range(60):
+        p = np.cumsum(rng.normal(0, 15, (rng.integers(2, 30), 2)), 0) + rng.random(2) * 200
+        lines.append("LINESTRING (" + ", ".join(f"{a:.3f} {b:.3f}" for a, b in p) + ")")
+    lines.append("MULTILINESTRING ((0 0, 200 200), (200 200, 0 0), (0 0, 200 200))")
+    for shape in [(97, 311), (200, 200)]:
+        for fun in ("sum", "count"):
+            exp, got, _ = both(lines, fun, "int32", 1, 0, shape=shape, extent=(0, 0, 200, 200))
+            assert_same(exp, got)
+
+
+def test_geometry_outside_and_on_boundaries():
+    geoms = [sq(-50, -50, 500, 500), sq(-10, 3, 2, 5), sq(98, 98, 120, 120), sq(0.5, 0.5, 99.5, 99.5),
+             "POLYGON ((10 10, 90 10.0000000000000001, 90 50, 10 50, 10 10))",      # epsilon-horizontal edge
+             "POLYGON ((20.5 20.5, 40.5 20.5, 40.5 40.5, 20.5 40.5, 20.5 20.5))",   # vertices on pixel centres
+             "LINESTRING (-500 50, 500 50)", "LINESTRING (50 -1e6, 50 1e6)", "LINESTRING (-30 -30, 130 140)",
+             "POINT (0 0)", "POINT (100 100)", "POINT (99.999 0.001)", "MULTIPOINT ((5 5), (5 5), (-1 5))",
+             "POLYGON ((30 30, 70 70, 70 30, 30 70, 30 30))"]                        # self-intersecting bow-tie
+    for fun in ("sum", "count", "first"):
+        exp, got, _ = both(geoms, fun, "float32", np.arange(1, len(geoms) + 1, dtype=np.float32), np.nan,
+                           shape=(100, 100), extent=(0, 0, 100, 100))
+        assert_same(exp, got)
+
+
+@pytest.mark.parametrize("tile_bytes", [64, 256, 4096, 32768])
+def test_tile_width_does_not_change_results(tile_bytes):
+    geoms = synth.mixed_geometries(21, 250, 1000, 120, rho=60.0)
+    exp, got, st = both(geoms, "sum", "float32", np.arange(len(geoms), dtype=np.float32), np.nan, tile_bytes=tile_bytes,
+                        shape=(120, 1000), extent=(0, 0, 1000, 120))
+    assert st["tile_width"] == min(1024, tile_bytes // 4)
+    assert_same(exp, got)
+
+
+def test_row_band_shards_equal_full_raster():
+    geoms = synth.mixed_geometries(31, 300, 400, 400, rho=40.0)
+    burn = np.arange(len(geoms)) % 9
+    for fun in ("sum", "last"):
+        for r0, r1 in [(0, 100), (100, 101), (101, 399), (399, 400)]:
+            exp, got, _ = both(geoms, fun, "int32", burn, 0, rows=(r0, r1), shape=(400, 400), extent=(0, 0, 400, 400))
+            assert_same(exp, got)
+
+
+def test_star_polygons_c1_shape_properties():
+    # BASELINE config 1 at full size: parity against the oracle + size-independent properties
+    x, y, off = synth.star_polygons(1, 10000, 64, 64, 82.0, 4096, 4096)
+    vals = 100 * synth.splitmix_u(1, 10000, 9)
+    g = core.Geoms.from_polygons(x, y, off)
+    ri = core.raster_info(None, shape=(4096, 4096), extent=(0, 0, 4096, 4096))
+    got, st = core.rasterize_dense(g, ri, "sum", "float64", vals, background=np.nan)
+    og = oracle.Geoms.from_rings(x, y, off)
+    ori = oracle.raster_info(None, shape=(4096, 4096), extent=(0, 0, 4096, 4096))
+    exp, _ = oracle.rasterize_dense(og, ori, "sum", "float64", vals, background=np.nan)
+    assert_same(exp, got)
+    # linearity in the field for count (field-independent) and idempotence of `any`
+    cnt, _ = core.rasterize_dense(g, ri, "count", "uint32", 1, background=0)
+    anyv, _ = core.rasterize_dense(g, ri, "any", "uint8", 1, background=0)
+    assert np.array_equal(anyv[0] == 1, cnt[0] > 0) and np.array_equal(np.isnan(got[0]), cnt[0] == 0)
+    ones, _ = core.rasterize_dense(g, ri, "sum", "float64", 1.0, background=np.nan)
+    assert np.array_equal(np.nan_to_num(ones[0]).astype(np.uint32), cnt[0])
+
+
+def test_errors_through_the_abi():
+    g = core.Geoms.from_wkt([sq(0, 0, 4, 4)])
+    ri = core.raster_info(g, shape=(4, 4))
+    with pytest.raises(ValueError, match="Geometry and field lengths must match"):
+        core.rasterize_dense(g, ri, field=np.array([1.0, 2.0]))
+    with pytest.raises(ValueError, match="Geometry and by lengths must match"):
+        core.rasterize_dense(g, ri, band_of_geom=np.array([0, 1], np.int32), n_bands=2)

@@ -1,0 +1,135 @@
+"""CPU-only checks of the product's host side: the C ABI loads and exports every declared symbol,
+the WKB / WKT flatteners, grid math and band grouping agree with the oracle, and compute entry
+points fail loudly (no CPU fallback) without a GPU."""
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import oracle
+from cases import GEOMS, GEOMS_EXPLODED, sq
+from oracle.wkt2wkb import wkt_to_wkb
+from rusterize_b200 import _lib, core
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = (ROOT / "include" / "rz_b200.h").read_text()
+    declared = set(re.findall(r"\b(rz_[a-z0-9_]+)\s*\(", hdr))
+    assert declared, "no declarations found"
+    L = _lib.lib()
+    for name in sorted(declared):
+        assert hasattr(L, name), f"librz_b200.so does not export {name}"
+    assert declared == set(_lib.SYMBOLS), (declared ^ set(_lib.SYMBOLS))
+    assert b"sm_100a" in L.rz_version()
+
+
+def test_no_cpu_fallback():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    g = core.Geoms.from_wkt([sq(0, 0, 4, 4)])
+    ri = core.raster_info(g, shape=(4, 4))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        core.rasterize_dense(g, ri)
+
+
+def test_flatten_parts_and_pooling():
+    # burn_geometry.rs:24-210 — one part per Polygon/MultiPolygon/LineString/MultiLineString/
+    # Point/MultiPoint; collections contribute their members' parts in order.
+    g = core.Geoms.from_wkt(GEOMS)
+    kind, geom = g.parts()
+    assert len(g) == 5
+    assert kind.tolist() == [0, 0, 0, 1, 2, 0, 1, 0]
+    assert geom.tolist() == [0, 1, 2, 3, 4, 4, 4, 4]
+    x, y, tag = g.pool(0)
+    # first polygon: exterior 5 + hole 4 vertices, both rings of part 0, ring ends flagged
+    assert (tag[:9] & 0x3FFFFFFF).tolist() == [0] * 9
+    assert [i for i in range(9) if tag[i] & 0x80000000] == [4, 8]
+    lx, ly, ltag = g.pool(1)
+    assert len(lx) == 18 + 2 and sum(1 for t in ltag if t & 0x80000000) == 10
+    assert not any(t & 0x40000000 for t in ltag)  # no closed line string
+    assert g.bounds() == (-180.0, -70.0, 180.0, 60.0)
+
+
+def test_wkt_and_wkb_readers_agree():
+    for geoms in (GEOMS, GEOMS_EXPLODED, ["MULTIPOINT ((1 2), (3 4))", "MULTIPOINT (1 2, 3 4)",
+                                          "POLYGON Z ((0 0 1, 4 0 1, 4 4 1, 0 0 1))", "LINESTRING (0 0, 1 1, 0 0)",
+                                          "POINT (1e-3 -2.5E2)", "GEOMETRYCOLLECTION EMPTY", "POLYGON EMPTY"]):
+        a = core.Geoms.from_wkt(geoms)
+        b = core.Geoms.from_wkb([wkt_to_wkb(s) for s in geoms])
+        assert len(a) == len(b)
+        assert all(np.array_equal(p, q) for p, q in zip(a.parts(), b.parts()))
+        for k in range(3):
+            assert all(np.array_equal(p, q) for p, q in zip(a.pool(k), b.pool(k)))
+
+
+def test_polygon_rings_are_closed_and_line_closed_flag():
+    g = core.Geoms.from_wkt(["POLYGON ((0 0, 4 0, 4 4))", "LINESTRING (0 0, 1 1, 0 0)", "LINESTRING (0 0, 1 1)"])
+    x, y, tag = g.pool(0)
+    assert list(zip(x, y)) == [(0, 0), (4, 0), (4, 4), (0, 0)]  # geo_types::Polygon::new closes rings
+    lx, ly, lt = g.pool(1)
+    assert [bool(t & 0x40000000) for t in lt] == [True, True, True, False, False]
+
+
+def test_big_endian_and_ewkb():
+    import struct
+
+    be = struct.pack(">BI", 0, 2) + struct.pack(">I", 2) + struct.pack(">dddd", 1.0, 2.0, 3.0, 4.0)
+    ewkb = struct.pack("<BI", 1, 0x20000001) + struct.pack("<I", 4326) + struct.pack("<dd", 5.0, 6.0)
+    g = core.Geoms.from_wkb([be, ewkb])
+    assert g.pool(1)[0].tolist() == [1.0, 3.0] and g.pool(2)[0].tolist() == [5.0]
+
+
+def test_dropped_and_invalid_inputs():
+    # python/src/geo/parse_geometry.rs: empty points are dropped, all-dropped input is a ValueError
+    g = core.Geoms.from_wkb([wkt_to_wkb("POINT EMPTY"), wkt_to_wkb("POINT (1 1)")])
+    assert len(g) == 1
+    with pytest.raises(ValueError, match="Could not parse geometry"):
+        core.Geoms.from_wkb([wkt_to_wkb("POINT EMPTY")])
+    with pytest.raises(RuntimeError, match="Cannot parse geometry"):
+        core.Geoms.from_wkb([b"\x01\x03\x00\x00\x00\x05"])
+    with pytest.raises(RuntimeError, match="Cannot parse geometry"):
+        core.Geoms.from_wkt(["POLYGON ((0 0, 1 1"])
+    with pytest.raises(ValueError, match="No geometries found"):
+        core.Geoms.from_any([])
+
+
+@pytest.mark.parametrize("kw", [
+    dict(resolution=(1, 1)), dict(resolution=(0.5, 2.0)), dict(shape=(47, 319)), dict(resolution=(7, 3), tap=True),
+    dict(shape=(10, 20), extent=(-349, -507, 1, 0)), dict(resolution=(1, 1), extent=(-349, -507, 1, 0)),
+    dict(resolution=(0.3, 0.7), extent=(-10.05, -3.3, 17.77, 9.1), tap=True)])
+def test_raster_info_matches_oracle(kw):
+    g = core.Geoms.from_wkt(GEOMS)
+    og = oracle.Geoms.from_any(GEOMS)
+    a = core.raster_info(g, **kw)
+    b = oracle.raster_info(og, **kw)
+    assert (a.nrows, a.ncols, a.xmin, a.ymin, a.xmax, a.ymax, a.xres, a.yres) == b.as_tuple()
+
+
+def test_raster_info_errors():
+    g = core.Geoms.from_wkt([sq(0, 0, 4, 4)])
+    cases = [
+        (dict(), ValueError, "Must set at least one of `shape` or `resolution`"),
+        (dict(shape=(4, 4), resolution=(1, 1)), ValueError, "Shape and resolution are mutually exclusive"),
+        (dict(shape=(0, 4)), ValueError, "Shape values must be > 0."),
+        (dict(resolution=(0.0, 1.0)), ValueError, "Resolution values must be > 0."),
+        (dict(shape=(4, 4), extent=(0, 0, 0, 0)), ValueError, "Unspecified extent"),
+    ]
+    for kw, exc, msg in cases:
+        with pytest.raises(exc, match=msg):
+            core.raster_info(g, **kw)
+    empty = core.Geoms.from_wkt(["GEOMETRYCOLLECTION EMPTY"])
+    with pytest.raises(RuntimeError, match="Cannot infer bounding box from geometry."):
+        core.raster_info(empty, shape=(4, 4))
+
+
+def test_group_keys_matches_oracle():
+    keys = [str(i % 32) for i in range(200)] + ["é", "a", "B", ""]
+    band, names = core.group_keys(keys)
+    oband, onames = oracle.group_keys(keys)
+    assert names == onames and np.array_equal(band, oband)
+    assert names[:4] == ["", "0", "1", "10"]  # byte-lexicographic (rasterize.rs:199-205)
