@@ -97,7 +97,8 @@ struct DeviceCtx {
     std::mutex mu;
     cudaStream_t stream = nullptr;
     int sm_count = 148;
-    DevBuf keys_a, keys_b, hist, digit_total, task_start, part_info, field, valid, band, last_kept, counters, win_out;
+    DevBuf keys_a, keys_b, hist, digit_total, task_start, part_info, field, valid, band, last_kept, counters, win_out,
+        block_total;
     Counters* h_counters = nullptr;  // pinned
     cudaEvent_t ev[16];
 };
@@ -261,7 +262,7 @@ struct Timer {
     Timer(DeviceCtx& c_, cudaStream_t s_) : c(c_), s(s_) {}
 };
 
-static const uint64_t MAX_WINDOW_RECORDS = 1ull << 30;      // 16 GiB of ping-pong key buffers
+static const uint64_t MAX_WINDOW_RECORDS = 1ull << 31;      // 32 GiB of ping-pong key buffers
 static const uint64_t MAX_WINDOW_OUT_BYTES = 12ull << 30;  // staging buffer when `out` is host memory
 
 static void rasterize_dense(rz_geoms* g, const rz_context* ctx, void* out, rz_stats* st) {
@@ -322,14 +323,18 @@ static void rasterize_dense(rz_geoms* g, const rz_context* ctx, void* out, rz_st
     S.h2d_bytes = h2d;
 
     // ---- tiling and key layout -----------------------------------------------------------------
-    uint32_t tile_bytes = ctx->tile_bytes ? ctx->tile_bytes : 4096u;
-    uint32_t tile_w = 1;
-    while ((uint64_t)tile_w * 2 * isz <= tile_bytes) tile_w *= 2;
-    while (tile_w / 2 >= ri.ncols && tile_w > 1) tile_w /= 2;               // no wider than the raster needs
-    while ((ri.ncols + tile_w - 1) / tile_w > 65535u) tile_w *= 2;          // PartInfo keeps tiles in 16 bits
+    // One warp owns a row tile of tile_w pixels; the fill kernel keeps one toggle bit per pixel in a
+    // 32-lane x 32-bit mask, hence tile_w <= 1024.
+    uint32_t tile_w = FILL_MAX_TILE_W;
+    if (ctx->tile_bytes) {
+        tile_w = 1;
+        while ((uint64_t)tile_w * 2 * isz <= ctx->tile_bytes && tile_w * 2 <= FILL_MAX_TILE_W) tile_w *= 2;
+    }
+    while (tile_w / 2 >= ri.ncols && tile_w > 1) tile_w /= 2;  // no wider than the raster needs
+    if ((ri.ncols + tile_w - 1) / tile_w > 65535u)
+        throw Error{RZ_RUNTIME_ERROR, "Raster too wide for the chosen tile width (more than 65535 column tiles)."};
     uint32_t tile_shift = bits_for(tile_w);
     const uint32_t n_tiles = (uint32_t)((ri.ncols + tile_w - 1) / tile_w);
-    if ((size_t)tile_w * isz * FILL_WARPS > 200u * 1024u) throw Error{RZ_RUNTIME_ERROR, "tile_bytes too large"};
 
     KParams P;
     std::memset(&P, 0, sizeof P);
@@ -407,6 +412,7 @@ static void rasterize_dense(rz_geoms* g, const rz_context* ctx, void* out, rz_st
     const uint32_t nv_poly = (uint32_t)g->pool[0].size(), nv_line = (uint32_t)g->pool[1].size(),
                    nv_pt = (uint32_t)g->pool[2].size();
     const uint32_t per_block = SETUP_THREADS * SETUP_ITEMS;
+    const bool all_poly = nv_line == 0 && nv_pt == 0;
 
     while (!todo.empty()) {
         Window w = todo.back();
@@ -418,10 +424,13 @@ static void rasterize_dense(rz_geoms* g, const rz_context* ctx, void* out, rz_st
         // ---- count --------------------------------------------------------------------------
         if (timed) CUDA_TRY(cudaEventRecord(c.ev[EV_A], s));
         CUDA_TRY(cudaMemsetAsync(d_ctr, 0, sizeof(Counters), s));
+        const uint32_t poly_blocks = (nv_poly + SETUP_THREADS - 1) / SETUP_THREADS;
         if (nv_poly) {
-            poly_count_kernel<<<(nv_poly + per_block - 1) / per_block, SETUP_THREADS, 0, s>>>(
-                P, dg->x[0], dg->y[0], dg->tag[0], nv_poly, d_info, d_ctr);
-            launches++;
+            c.block_total.ensure((size_t)poly_blocks * 4);
+            poly_count_kernel<<<poly_blocks, SETUP_THREADS, 0, s>>>(P, dg->x[0], dg->y[0], dg->tag[0], nv_poly, d_info,
+                                                                   c.block_total.as<uint32_t>(), d_ctr);
+            scan_u32_kernel<<<1, 1024, 0, s>>>(c.block_total.as<uint32_t>(), poly_blocks);
+            launches += 2;
         }
         if (nv_line) {
             CUDA_TRY(cudaMemsetAsync(c.last_kept.p, 0, (size_t)n_parts * 4, s));
@@ -469,10 +478,13 @@ static void rasterize_dense(rz_geoms* g, const rz_context* ctx, void* out, rz_st
         uint64_t* kb = c.keys_b.as<uint64_t>();
         if (n) {
             if (nv_poly) {
-                poly_emit_kernel<<<(nv_poly + per_block - 1) / per_block, SETUP_THREADS, 0, s>>>(
-                    P, dg->x[0], dg->y[0], dg->tag[0], nv_poly, d_info, d_ctr, ka);
+                poly_emit_kernel<<<poly_blocks, SETUP_THREADS, 0, s>>>(P, dg->x[0], dg->y[0], dg->tag[0], nv_poly,
+                                                                      d_info, c.block_total.as<uint32_t>(), 0, ka);
                 launches++;
             }
+            // line / point records go behind the polygon records
+            c.h_counters->cursor = c.h_counters->poly_records;
+            CUDA_TRY(cudaMemcpyAsync(&d_ctr->cursor, &c.h_counters->cursor, 8, cudaMemcpyHostToDevice, s));
             if (nv_line) {
                 line_emit_kernel<<<(nv_line + per_block - 1) / per_block, SETUP_THREADS, 0, s>>>(
                     P, dg->x[1], dg->y[1], dg->tag[1], nv_line, d_info, d_ctr, ka);
@@ -496,7 +508,10 @@ static void rasterize_dense(rz_geoms* g, const rz_context* ctx, void* out, rz_st
             const uint32_t n_blocks = (n + RS_TILE - 1) / RS_TILE;
             c.hist.ensure((size_t)n_blocks * RS_RADIX * 4);
             c.digit_total.ensure(RS_RADIX * 4);
-            for (uint32_t shift = 0; shift < key_bits; shift += 8) {
+            // Polygon-only jobs are emitted in part order, so a stable sort on the task bits alone
+            // leaves every task's records grouped by part in burn order; otherwise sort (task, part).
+            // Column bits are never sorted: the fill kernel does not need column order.
+            for (uint32_t shift = all_poly ? P.task_shift : P.part_shift; shift < key_bits; shift += 8) {
                 radix_hist_kernel<<<n_blocks, RS_THREADS, 0, s>>>(ka, n, shift, n_blocks, c.hist.as<uint32_t>());
                 radix_scan_rows_kernel<<<RS_RADIX, 1024, 0, s>>>(c.hist.as<uint32_t>(), n_blocks,
                                                                 c.digit_total.as<uint32_t>());
@@ -532,6 +547,7 @@ static void rasterize_dense(rz_geoms* g, const rz_context* ctx, void* out, rz_st
         F.part_shift = P.part_shift;
         F.part_bits = P.part_bits;
         F.dedup_lines = P.dedup_lines;
+        F.all_poly = all_poly;
         void* d_out;
         if (out_dev) {
             d_out = out;

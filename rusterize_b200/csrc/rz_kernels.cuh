@@ -45,7 +45,8 @@ struct PartInfo {
 struct Counters {
     unsigned long long records;     // total records counted (count pass)
     unsigned long long crossings;   // polygon crossings without tile replication
-    unsigned long long cursor;      // emit allocation cursor
+    unsigned long long cursor;      // emit allocation cursor (line / point records; polygons use scanned block bases)
+    unsigned long long poly_records; // records of polygon parts (they occupy the front of the buffer)
     unsigned int bad_line;          // a line segment left the supported ±2^29 pixel domain
     unsigned int pad;
 };
@@ -167,8 +168,8 @@ __device__ __forceinline__ uint64_t poly_key(const KParams& P, const PolyEdgeRec
 }
 
 constexpr int SETUP_THREADS = 256;
-constexpr int SETUP_ITEMS = 4;
-constexpr uint32_t LONG_EDGE = 64;  // records above which a warp cooperates on one edge
+constexpr int SETUP_ITEMS = 4;      // line kernels: vertices per thread
+constexpr uint32_t LONG_EDGE = 64;  // line kernels: records above which a warp cooperates on one segment
 
 // block-wide exclusive scan of one value per thread (256 threads); returns exclusive prefix, total in *total
 __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* smem_warp, uint32_t* total) {
@@ -197,93 +198,123 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* s
     return smem_warp[warp] + inc - v;
 }
 
+// Count pass: one thread per ring vertex.  Besides the global totals it stores the number of
+// records of every block so that the emit pass can place blocks in vertex order (= part order),
+// which lets a polygon-only job sort on the task bits alone.
 __global__ void __launch_bounds__(SETUP_THREADS)
 poly_count_kernel(KParams P, const double* __restrict__ x, const double* __restrict__ y,
                   const uint32_t* __restrict__ tag, uint32_t n, const PartInfo* __restrict__ info,
-                  Counters* __restrict__ ctr) {
-    unsigned long long rec = 0, crs = 0;
-    uint32_t base = blockIdx.x * (SETUP_THREADS * SETUP_ITEMS);
-#pragma unroll
-    for (int r = 0; r < SETUP_ITEMS; r++) {
-        PolyEdgeRec e;
-        if (poly_edge_setup(P, x, y, tag, info, base + r * SETUP_THREADS + threadIdx.x, n, e)) {
-            rec += (unsigned long long)e.n_rows * e.n_t;
-            crs += e.n_rows;
-        }
+                  uint32_t* __restrict__ block_total, Counters* __restrict__ ctr) {
+    __shared__ uint32_t s_rec[SETUP_THREADS / 32], s_crs[SETUP_THREADS / 32];
+    PolyEdgeRec e;
+    uint32_t rec = 0, crs = 0;
+    if (poly_edge_setup(P, x, y, tag, info, blockIdx.x * SETUP_THREADS + threadIdx.x, n, e)) {
+        rec = e.n_rows * e.n_t;
+        crs = e.n_rows;
     }
-    // block reduce -> one atomic per block
-    __shared__ unsigned long long s_rec[SETUP_THREADS / 32], s_crs[SETUP_THREADS / 32];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        rec += __shfl_down_sync(0xffffffffu, rec, o);
-        crs += __shfl_down_sync(0xffffffffu, crs, o);
-    }
+    rec = __reduce_add_sync(0xffffffffu, rec);
+    crs = __reduce_add_sync(0xffffffffu, crs);
     if (lane_id() == 0) { s_rec[threadIdx.x >> 5] = rec; s_crs[threadIdx.x >> 5] = crs; }
     __syncthreads();
     if (threadIdx.x == 0) {
         for (int w = 1; w < SETUP_THREADS / 32; w++) { rec += s_rec[w]; crs += s_crs[w]; }
-        if (rec) atomicAdd(&ctr->records, rec);
-        if (crs) atomicAdd(&ctr->crossings, crs);
+        block_total[blockIdx.x] = rec;
+        if (rec) {
+            atomicAdd(&ctr->records, (unsigned long long)rec);
+            atomicAdd(&ctr->poly_records, (unsigned long long)rec);
+        }
+        if (crs) atomicAdd(&ctr->crossings, (unsigned long long)crs);
     }
 }
 
-// Emit: every block reserves a contiguous range of the record buffer with one atomic (record order
-// before the sort is irrelevant), short edges are written by their own thread, long edges by the
-// whole warp with lanes striding the edge's rows.
+// In-place exclusive scan of the per-block totals (single block; n is a few hundred thousand).
+__global__ void __launch_bounds__(1024) scan_u32_kernel(uint32_t* __restrict__ v, uint32_t n) {
+    __shared__ uint32_t s_warp[33];
+    uint32_t carry = 0;
+    const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
+    for (uint32_t b0 = 0; b0 < n; b0 += 1024) {
+        uint32_t i = b0 + threadIdx.x;
+        uint32_t val = i < n ? v[i] : 0, inc = val;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= (uint32_t)o) inc += t;
+        }
+        if (lane == 31) s_warp[warp] = inc;
+        __syncthreads();
+        if (warp == 0) {
+            uint32_t w = s_warp[lane], winc = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                uint32_t t = __shfl_up_sync(0xffffffffu, winc, o);
+                if (lane >= (uint32_t)o) winc += t;
+            }
+            s_warp[lane] = winc - w;
+            if (lane == 31) s_warp[32] = winc;
+        }
+        __syncthreads();
+        if (i < n) v[i] = carry + s_warp[warp] + inc - val;
+        carry += s_warp[32];
+        __syncthreads();
+    }
+}
+
+// Emit pass: blocks write at their scanned base, warps flatten the records of their 32 edges so
+// that consecutive lanes store consecutive records (coalesced 256-byte stores).
 __global__ void __launch_bounds__(SETUP_THREADS)
 poly_emit_kernel(KParams P, const double* __restrict__ x, const double* __restrict__ y,
                  const uint32_t* __restrict__ tag, uint32_t n, const PartInfo* __restrict__ info,
-                 Counters* __restrict__ ctr, uint64_t* __restrict__ keys) {
-    __shared__ uint32_t s_warp[33];
-    __shared__ unsigned long long s_base;
-    uint32_t base = blockIdx.x * (SETUP_THREADS * SETUP_ITEMS);
-    PolyEdgeRec e[SETUP_ITEMS];
-    uint32_t cnt[SETUP_ITEMS];
-    uint32_t mine = 0;
+                 const uint32_t* __restrict__ block_base, uint64_t base_offset, uint64_t* __restrict__ keys) {
+    __shared__ uint32_t s_wtot[SETUP_THREADS / 32];
+    __shared__ double s_xtop[SETUP_THREADS], s_ytop[SETUP_THREADS], s_dxdy[SETUP_THREADS];
+    __shared__ uint32_t s_pre[SETUP_THREADS], s_rowlo[SETUP_THREADS], s_part[SETUP_THREADS];
+    __shared__ uint32_t s_tl[SETUP_THREADS];  // t_lo | n_t << 16
+    __shared__ int32_t s_band[SETUP_THREADS];
+    const uint32_t lane = lane_id(), warp = threadIdx.x >> 5, w0 = warp * 32;
+    PolyEdgeRec e;
+    poly_edge_setup(P, x, y, tag, info, blockIdx.x * SETUP_THREADS + threadIdx.x, n, e);
+    const uint32_t cnt = e.n_rows * e.n_t;
+    uint32_t inc = cnt;
 #pragma unroll
-    for (int r = 0; r < SETUP_ITEMS; r++) {
-        poly_edge_setup(P, x, y, tag, info, base + r * SETUP_THREADS + threadIdx.x, n, e[r]);
-        cnt[r] = e[r].n_rows * e[r].n_t;
-        mine += cnt[r];
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= (uint32_t)o) inc += t;
     }
-    uint32_t total;
-    uint32_t off = block_exclusive_scan(mine, s_warp, &total);
-    if (total == 0) return;
-    if (threadIdx.x == 0) s_base = atomicAdd(&ctr->cursor, (unsigned long long)total);
+    const uint32_t wtot = __shfl_sync(0xffffffffu, inc, 31);
+    if (lane == 0) s_wtot[warp] = wtot;
+    s_pre[threadIdx.x] = inc - cnt;
+    s_xtop[threadIdx.x] = e.x_top;
+    s_ytop[threadIdx.x] = e.y_top;
+    s_dxdy[threadIdx.x] = e.dxdy;
+    s_rowlo[threadIdx.x] = e.row_lo;
+    s_part[threadIdx.x] = e.part;
+    s_tl[threadIdx.x] = e.t_lo | (e.n_t << 16);
+    s_band[threadIdx.x] = e.band;
     __syncthreads();
-    uint64_t* out = keys + s_base + off;
-    uint32_t lane = lane_id();
+    uint32_t wbase = 0;
+    for (uint32_t w = 0; w < warp; w++) wbase += s_wtot[w];
+    uint64_t* out = keys + base_offset + block_base[blockIdx.x] + wbase;
+    for (uint32_t t = lane; t < wtot; t += 32) {
+        // last edge of this warp whose first record is <= t
+        uint32_t lo = 0, hi = 32;
 #pragma unroll
-    for (int r = 0; r < SETUP_ITEMS; r++) {
-        bool is_long = cnt[r] > LONG_EDGE;
-        if (!is_long) {
-            uint32_t k = 0;
-            for (uint32_t row = 0; row < e[r].n_rows; row++)
-                for (uint32_t t = 0; t < e[r].n_t; t++) out[k++] = poly_key(P, e[r], e[r].row_lo + row, e[r].t_lo + t);
+        for (int it = 0; it < 5; it++) {
+            uint32_t mid = (lo + hi) >> 1;
+            if (s_pre[w0 + mid] <= t) lo = mid;
+            else hi = mid;
         }
-        uint32_t m = __ballot_sync(0xffffffffu, is_long);
-        while (m) {
-            int src = __ffs(m) - 1;
-            m &= m - 1;
-            PolyEdgeRec b;
-            b.x_top = __shfl_sync(0xffffffffu, e[r].x_top, src);
-            b.y_top = __shfl_sync(0xffffffffu, e[r].y_top, src);
-            b.dxdy = __shfl_sync(0xffffffffu, e[r].dxdy, src);
-            b.row_lo = __shfl_sync(0xffffffffu, e[r].row_lo, src);
-            b.n_rows = __shfl_sync(0xffffffffu, e[r].n_rows, src);
-            b.part = __shfl_sync(0xffffffffu, e[r].part, src);
-            b.band = __shfl_sync(0xffffffffu, e[r].band, src);
-            b.t_lo = __shfl_sync(0xffffffffu, e[r].t_lo, src);
-            b.n_t = __shfl_sync(0xffffffffu, e[r].n_t, src);
-            unsigned long long p = (unsigned long long)(uintptr_t)out;
-            uint64_t* bout = (uint64_t*)(uintptr_t)__shfl_sync(0xffffffffu, p, src);
-            uint32_t tot = b.n_rows * b.n_t;
-            for (uint32_t k = lane; k < tot; k += 32) {
-                uint32_t row = k / b.n_t, t = k - row * b.n_t;
-                bout[k] = poly_key(P, b, b.row_lo + row, b.t_lo + t);
-            }
-        }
-        out += cnt[r];
+        const uint32_t j = w0 + lo;
+        const uint32_t local = t - s_pre[j];
+        const uint32_t tl = s_tl[j], n_t = tl >> 16;
+        uint32_t row_off = local, tt = 0;
+        if (n_t > 1) { row_off = local / n_t; tt = local - row_off * n_t; }
+        PolyEdgeRec b;
+        b.x_top = s_xtop[j];
+        b.y_top = s_ytop[j];
+        b.dxdy = s_dxdy[j];
+        b.part = s_part[j];
+        b.band = s_band[j];
+        out[t] = poly_key(P, b, s_rowlo[j] + row_off, (tl & 0xffffu) + tt);
     }
 }
 
@@ -717,6 +748,15 @@ template <typename N> __device__ __forceinline__ N value_from_bits(uint64_t b) {
 // ---------------------------------------------------------------------------------------------
 // fill — one warp per (band, row, column tile)
 // ---------------------------------------------------------------------------------------------
+// The task's records arrive grouped by part, parts in burn order (stable sort).  A polygon part's
+// records of this row ("run") are its scanline crossings in arbitrary order: the warp XORs one bit
+// per crossing into a 1024-bit toggle mask (one 32-bit word per lane); a prefix-XOR over the mask
+// is the even-odd inside mask — exactly the spans burners.rs:302-315 gets from sorting and pairing,
+// because pairing consecutive sorted crossings == parity of the number of crossings at or left of a
+// pixel.  An unpaired last crossing (odd run) is dropped like chunks_exact(2) does, by removing the
+// largest column.  The part's value is then applied to the masked pixels with the reference's
+// pixel-function rule, 32 consecutive pixels per step, before the next part is looked at: writes
+// hit every pixel in burn order, so even floating-point `sum` is bit-exact.
 struct FillParams {
     uint32_t n_tasks, n_tiles, tile_w, ncols;
     uint32_t win_rows;         // rows in this window
@@ -725,9 +765,43 @@ struct FillParams {
     uint32_t col_bits, part_shift, part_bits;
     uint32_t dedup_lines;
     uint32_t vec_ok;           // rows of `out` are 16-byte aligned
+    uint32_t all_poly;         // no line / point parts: skip the kind lookup
 };
 
 constexpr int FILL_WARPS = 4;
+constexpr uint32_t FILL_MAX_TILE_W = 1024;  // 32 lanes x 32 toggle bits
+
+// Close a polygon run: turn the toggle mask into the inside mask and apply the part's value.
+template <typename N, int FN>
+__device__ __forceinline__ void finish_poly_run(uint32_t* tog, N* row, uint32_t lane, uint32_t lt_mask, uint32_t w,
+                                                uint32_t run_cnt, uint32_t run_max, N v, N bg) {
+    // odd run: the sorted list's last crossing has no partner (burners.rs:305)
+    if ((run_cnt & 1u) && run_max < w && lane == (run_max >> 5)) tog[lane] ^= 1u << (run_max & 31);
+    const uint32_t t = tog[lane];
+    tog[lane] = 0;
+    uint32_t m = t;
+    m ^= m << 1;
+    m ^= m << 2;
+    m ^= m << 4;
+    m ^= m << 8;
+    m ^= m << 16;
+    const uint32_t odd_words = __ballot_sync(0xffffffffu, __popc(t) & 1);
+    if (__popc(odd_words & lt_mask) & 1) m = ~m;
+    const int rem = (int)w - (int)(lane * 32);
+    if (rem <= 0) m = 0;
+    else if (rem < 32) m &= (1u << rem) - 1u;
+    uint32_t nz = __ballot_sync(0xffffffffu, m != 0);
+    while (nz) {
+        const int src = __ffs(nz) - 1;
+        nz &= nz - 1;
+        const uint32_t mw = __shfl_sync(0xffffffffu, m, src);
+        if ((mw >> lane) & 1u) {
+            const uint32_t p = (uint32_t)src * 32 + lane;
+            row[p] = apply_px<N, FN>(row[p], v, bg);
+        }
+    }
+    __syncwarp();
+}
 
 template <typename N, int FN>
 __global__ void __launch_bounds__(FILL_WARPS * 32)
@@ -735,11 +809,15 @@ fill_kernel(FillParams F, const uint64_t* __restrict__ keys, const uint32_t* __r
             const PartInfo* __restrict__ info, const uint8_t* __restrict__ part_kind, uint64_t bg_bits,
             N* __restrict__ out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ uint32_t s_tog[FILL_WARPS][32];
     const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
     N* row = reinterpret_cast<N*>(smem_raw) + (size_t)warp * F.tile_w;
+    uint32_t* tog = s_tog[warp];
     const N bg = value_from_bits<N>(bg_bits);
     const uint32_t col_mask = (1u << F.col_bits) - 1u;
     const uint64_t part_mask = (1ull << F.part_bits) - 1ull;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    tog[lane] = 0;
 
     for (uint32_t task = blockIdx.x * FILL_WARPS + warp; task < F.n_tasks; task += gridDim.x * FILL_WARPS) {
         const uint32_t tile = task % F.n_tiles;
@@ -753,49 +831,89 @@ fill_kernel(FillParams F, const uint64_t* __restrict__ keys, const uint32_t* __r
         for (uint32_t i = lane; i < w; i += 32) row[i] = bg;
         __syncwarp();
 
-        uint64_t carry_hi = ~0ull;   // (task|part) of the record before this chunk
-        uint64_t carry_key = ~0ull;  // full key of the record before this chunk
-        uint32_t carry_par = 0;      // index parity of this chunk's lane 0 within its part run
+        uint64_t carry_hi = ~0ull;  // (task|part) of the record before this chunk
+        uint32_t run_cnt = 0, run_max = 0;
+        uint32_t open_part = 0xffffffffu, open_kind = 0;  // run left open at the end of the previous chunk
         for (uint32_t base = beg; base < end; base += 32) {
             const uint32_t i = base + lane;
-            const bool valid = i < end;
+            const uint32_t nvalid = min(32u, end - base);
+            const bool valid = lane < nvalid;
             const uint64_t key = valid ? keys[i] : ~0ull;
-            uint64_t nxt = __shfl_down_sync(0xffffffffu, key, 1);
-            if (lane == 31) nxt = (i + 1 < end) ? keys[i + 1] : ~0ull;
             const uint64_t hi = key >> F.col_bits;
             uint64_t prev_hi = __shfl_up_sync(0xffffffffu, hi, 1);
-            uint64_t prev_key = __shfl_up_sync(0xffffffffu, key, 1);
-            if (lane == 0) { prev_hi = carry_hi; prev_key = carry_key; }
-            const bool head = hi != prev_hi;
-            const uint32_t heads = __ballot_sync(0xffffffffu, head);
-            const uint32_t below = heads & (0xffffffffu >> (31 - lane));
-            const uint32_t par = below ? ((lane - (31 - __clz(below))) & 1u) : ((carry_par + lane) & 1u);
+            if (lane == 0) prev_hi = carry_hi;
+            const uint32_t heads = __ballot_sync(0xffffffffu, valid && hi != prev_hi);
             const uint32_t part = (uint32_t)((key >> F.part_shift) & part_mask);
-            const uint32_t kind = valid ? part_kind[part] : 0;
-            const uint32_t col = (uint32_t)key & col_mask, ncol = (uint32_t)nxt & col_mask;
-            bool start;
-            uint32_t xs = col, xe;
-            if (kind == 0) {  // polygon crossing: even-odd pairs within (task, part); odd tail dropped
-                xe = ncol;
-                start = valid && par == 0 && (nxt >> F.col_bits) == hi && col < ncol;
-            } else {          // line / point pixel
-                xe = col + 1;
-                start = valid && !(kind == 1 && F.dedup_lines && key == prev_key);
+            const uint32_t col = (uint32_t)key & col_mask;
+            const bool last_chunk = base + 32 >= end;
+
+            if ((heads & 1u) && open_part != 0xffffffffu) {  // the open run ended exactly at the chunk boundary
+                if (open_kind == 0)
+                    finish_poly_run<N, FN>(tog, row, lane, lt_mask, w, run_cnt, run_max,
+                                           value_from_bits<N>(info[open_part].value_bits), bg);
+                else {
+                    tog[lane] = 0;
+                    __syncwarp();
+                }
+                run_cnt = 0;
+                run_max = 0;
             }
-            N v = start ? value_from_bits<N>(info[part].value_bits) : (N)0;
-            uint32_t m = __ballot_sync(0xffffffffu, start);
-            while (m) {
-                const int src = __ffs(m) - 1;
-                m &= m - 1;
-                const uint32_t bxs = __shfl_sync(0xffffffffu, xs, src);
-                const uint32_t bxe = __shfl_sync(0xffffffffu, xe, src);
-                const N bv = __shfl_sync(0xffffffffu, v, src);
-                for (uint32_t p = bxs + lane; p < bxe; p += 32) row[p] = apply_px<N, FN>(row[p], bv, bg);
-                __syncwarp();
+            open_part = 0xffffffffu;
+
+            uint32_t start = 0;
+            while (start < nvalid) {  // one iteration per run present in this chunk (warp-uniform)
+                const uint32_t rest = start < 31 ? (heads & (0xffffffffu << (start + 1))) : 0u;
+                const uint32_t stop = rest ? (uint32_t)(__ffs(rest) - 1) : nvalid;
+                const bool in_run = lane >= start && lane < stop;
+                const bool run_ends = stop < nvalid || last_chunk;
+                const uint32_t run_part = __shfl_sync(0xffffffffu, part, start);
+                const uint32_t kind = F.all_poly ? 0u : (uint32_t)part_kind[run_part];
+                if (kind == 0) {
+                    if (in_run && col < w) atomicXor(&tog[col >> 5], 1u << (col & 31));
+                    run_cnt += stop - start;
+                    run_max = max(run_max, __reduce_max_sync(0xffffffffu, in_run ? col : 0u));
+                    __syncwarp();
+                    if (run_ends) {
+                        finish_poly_run<N, FN>(tog, row, lane, lt_mask, w, run_cnt, run_max,
+                                               value_from_bits<N>(info[run_part].value_bits), bg);
+                        run_cnt = 0;
+                        run_max = 0;
+                    }
+                } else {
+                    // line / point pixels: one write per record (burners.rs:69-89, 250-258)
+                    const N v = value_from_bits<N>(info[run_part].value_bits);
+                    const bool dedup = kind == 1 && F.dedup_lines;  // LineWriter + PixelCache (writers.rs:25-29)
+                    if (dedup) {
+                        if (in_run) {
+                            const uint32_t bit = 1u << (col & 31);
+                            if (!(atomicOr(&tog[col >> 5], bit) & bit)) row[col] = apply_px<N, FN>(row[col], v, bg);
+                        }
+                        __syncwarp();
+                        if (run_ends) {
+                            tog[lane] = 0;
+                            __syncwarp();
+                        }
+                    } else {
+                        // revisits are written again: apply once per record, same-pixel records serially
+                        const uint32_t run_mask = __ballot_sync(0xffffffffu, in_run);
+                        if (in_run) {
+                            const uint32_t peers = __match_any_sync(run_mask, col);
+                            if ((int)lane == __ffs(peers) - 1) {
+                                N cur = row[col];
+                                for (int k = __popc(peers); k > 0; k--) cur = apply_px<N, FN>(cur, v, bg);
+                                row[col] = cur;
+                            }
+                        }
+                        __syncwarp();
+                    }
+                }
+                if (!run_ends) {
+                    open_part = run_part;
+                    open_kind = (kind == 1 && F.dedup_lines) ? 1u : (kind == 0 ? 0u : 2u);
+                }
+                start = stop;
             }
             carry_hi = __shfl_sync(0xffffffffu, hi, 31);
-            carry_key = __shfl_sync(0xffffffffu, key, 31);
-            carry_par = (__shfl_sync(0xffffffffu, par, 31) + 1u) & 1u;
         }
 
         // flush the tile: every output byte is written exactly once
