@@ -227,3 +227,54 @@ def rasterize_dense(geoms: Geoms, ri: RasterInfo, fun="last", dtype="float64", f
     rc = lib().rz_rasterize_dense(geoms._h, C.byref(ctx), out_ptr, C.byref(st), err, len(err))
     raise_for(rc, err)
     return arr, st.as_dict()
+
+
+def rasterize_sparse(geoms: Geoms, ri: RasterInfo, fun="last", dtype="float64", field=1, field_valid=None,
+                     band_of_geom=None, n_bands=1, background=0, all_touched=False, device=0, stream=None, flags=0):
+    """SparseArray::build (rust/src/rasterize.rs:118-157) on the GPU -> dict(rows, cols, data, counts, stats)."""
+    ctx, dt, keep = _context(geoms, ri, fun, dtype, field, field_valid, band_of_geom, n_bands, background,
+                             all_touched, device, None, stream, flags, 0)
+    L = lib()
+    h = C.c_void_p()
+    st = Stats()
+    err = errbuf()
+    rc = L.rz_rasterize_sparse(geoms._h, C.byref(ctx), C.byref(h), C.byref(st), err, len(err))
+    raise_for(rc, err)
+    try:
+        n, nb = L.rz_sparse_len(h), L.rz_sparse_n_bands(h)
+
+        def view(p, count, t):
+            if count == 0:
+                return np.empty(0, t)
+            return np.frombuffer((C.c_char * (count * np.dtype(t).itemsize)).from_address(p), dtype=t).copy()
+
+        return dict(rows=view(L.rz_sparse_rows(h), n, np.uint64), cols=view(L.rz_sparse_cols(h), n, np.uint64),
+                    data=view(L.rz_sparse_data(h), n, dt), counts=view(L.rz_sparse_counts(h), nb, np.uint64),
+                    stats=st.as_dict())
+    finally:
+        L.rz_sparse_free(h)
+
+
+def sparse_build_array(ri: RasterInfo, fun, background, counts, rows, cols, data, device=0):
+    """SparseArray::build_array (rust/src/encoding/arrays.rs:103-143): replay the triplets through the
+    pixel function on the GPU -> array [n_bands, nrows, ncols]."""
+    dt = data.dtype
+    ctx = Context()
+    ctx.raster_info = ri
+    ctx.dtype = DTYPES.index(dt.name)
+    ctx.pixel_fn = FUNS.index(fun)
+    with np.errstate(invalid="ignore", over="ignore"):
+        bg = np.array([background]).astype(dt)
+    ctx.background = bg.ctypes.data
+    ctx.device = int(device)
+    counts = np.ascontiguousarray(counts, np.uint64)
+    rows = np.ascontiguousarray(rows, np.uint64)
+    cols = np.ascontiguousarray(cols, np.uint64)
+    data = np.ascontiguousarray(data)
+    out = np.empty((len(counts), ri.nrows, ri.ncols), dt)
+    st = Stats()
+    err = errbuf()
+    rc = lib().rz_sparse_build_array(C.byref(ctx), len(counts), counts.ctypes.data, rows.ctypes.data, cols.ctypes.data,
+                                     data.ctypes.data, out.ctypes.data, C.byref(st), err, len(err))
+    raise_for(rc, err)
+    return out

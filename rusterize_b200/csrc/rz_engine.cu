@@ -14,6 +14,7 @@
 
 #include "rz_host.hpp"
 #include "rz_kernels.cuh"
+#include "rz_sparse.cuh"
 
 namespace rz {
 
@@ -76,6 +77,8 @@ struct DeviceGeoms {
     uint32_t* part_geom = nullptr;
     double* part_xlo = nullptr;
     double* part_xhi = nullptr;
+    uint32_t* part_vbeg = nullptr;
+    uint32_t* part_vend = nullptr;
     size_t bytes = 0;
     ~DeviceGeoms() {
         cudaSetDevice(dev);
@@ -88,6 +91,8 @@ struct DeviceGeoms {
         cudaFree(part_geom);
         cudaFree(part_xlo);
         cudaFree(part_xhi);
+        cudaFree(part_vbeg);
+        cudaFree(part_vend);
         (void)cudaGetLastError();
     }
 };
@@ -98,7 +103,7 @@ struct DeviceCtx {
     cudaStream_t stream = nullptr;
     int sm_count = 148;
     DevBuf keys_a, keys_b, hist, digit_total, task_start, part_info, field, valid, band, last_kept, counters, win_out,
-        block_total;
+        block_total, sp_a, sp_b, sp_c, sp_d, sp_e, sp_f, sp_g, sp_rows, sp_cols, sp_data, sp_partial;
     Counters* h_counters = nullptr;  // pinned
     cudaEvent_t ev[16];
 };
@@ -193,6 +198,8 @@ static DeviceGeoms* geoms_on_device(rz_geoms* g, DeviceCtx& c, cudaStream_t s, b
     upload_vec(&d->part_geom, pg, s, bytes);
     upload_vec(&d->part_xlo, g->part_xlo, s, bytes);
     upload_vec(&d->part_xhi, g->part_xhi, s, bytes);
+    upload_vec(&d->part_vbeg, g->part_vbeg, s, bytes);
+    upload_vec(&d->part_vend, g->part_vend, s, bytes);
     CUDA_TRY(cudaStreamSynchronize(s));  // `pg` is a temporary
     d->bytes = bytes;
     if (h2d_bytes) *h2d_bytes += bytes;
@@ -210,7 +217,10 @@ typedef void (*FillLaunch)(dim3, size_t, cudaStream_t, FillParams, const uint64_
 template <typename N, int FN>
 static void fill_launch(dim3 grid, size_t smem, cudaStream_t s, FillParams F, const uint64_t* keys,
                         const uint32_t* task_start, const PartInfo* info, const uint8_t* kind, uint64_t bg, void* out) {
-    fill_kernel<N, FN><<<grid, FILL_WARPS * 32, smem, s>>>(F, keys, task_start, info, kind, bg, (N*)out);
+    if (F.all_poly)
+        fill_kernel<N, FN, true><<<grid, FILL_WARPS * 32, smem, s>>>(F, keys, task_start, info, kind, bg, (N*)out);
+    else
+        fill_kernel<N, FN, false><<<grid, FILL_WARPS * 32, smem, s>>>(F, keys, task_start, info, kind, bg, (N*)out);
 }
 
 template <typename N> static FillLaunch fill_for_fn(int fn) {
@@ -561,7 +571,7 @@ static void rasterize_dense(rz_geoms* g, const rz_context* ctx, void* out, rz_st
         }
         F.vec_ok = ((uintptr_t)d_out % 16 == 0) && ((ri.ncols * isz) % 16 == 0) && (((size_t)tile_w * isz) % 16 == 0);
         const uint32_t grid = (n_tasks + FILL_WARPS - 1) / FILL_WARPS;
-        fill(dim3(grid), (size_t)FILL_WARPS * tile_w * isz, s, F, ka, c.task_start.as<uint32_t>(), d_info,
+        fill(dim3(grid), (size_t)FILL_WARPS * FILL_MAX_TILE_W * isz, s, F, ka, c.task_start.as<uint32_t>(), d_info,
              dg->part_kind, bg_bits, d_out);
         launches++;
         CUDA_TRY(cudaGetLastError());
@@ -594,6 +604,293 @@ static void rasterize_dense(rz_geoms* g, const rz_context* ctx, void* out, rz_st
     S.index_ms = index_ms;
     S.fill_ms = fill_ms;
     S.d2h_ms = d2h_ms;
+    S.kernel_launches = launches;
+    if (st) *st = S;
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// the sparse pipeline
+// ------------------------------------------------------------------------------------------------
+}  // namespace rz
+
+struct rz_sparse {
+    std::vector<uint64_t> rows, cols, counts;
+    std::vector<uint8_t> data;
+};
+
+namespace rz {
+
+template <typename Op, typename In, typename Out>
+static void device_scan(In in, uint32_t n, Out out, DevBuf& partial, cudaStream_t s, uint32_t& launches) {
+    const uint32_t nb = (n + SC_TILE - 1) / SC_TILE;
+    partial.ensure(((size_t)nb + 2) * 8);
+    unsigned long long* p = partial.as<unsigned long long>();
+    if (nb == 0) {
+        CUDA_TRY(cudaMemsetAsync(p, 0, 8, s));
+        return;
+    }
+    scan_reduce_kernel<Op, In><<<nb, SC_THREADS, 0, s>>>(in, n, p);
+    scan_partials_kernel<Op><<<1, 1024, 0, s>>>(p, nb);
+    scan_apply_kernel<Op, In, Out><<<nb, SC_THREADS, 0, s>>>(in, n, p, out);
+    launches += 3;
+}
+
+static unsigned long long scan_total(DevBuf& partial, uint32_t n, cudaStream_t s) {
+    const uint32_t nb = (n + SC_TILE - 1) / SC_TILE;
+    unsigned long long t = 0;
+    CUDA_TRY(cudaMemcpyAsync(&t, partial.as<unsigned long long>() + nb, 8, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    return t;
+}
+
+template <typename N>
+static void sparse_expand(cudaStream_t s, const KParams& P, SparseLayout L, DeviceGeoms* dg, DeviceCtx& c, uint32_t n_rec,
+                          const uint64_t* keys, uint32_t nv_line, uint32_t nv_pt, uint32_t& launches) {
+    unsigned long long* rows = c.sp_rows.as<unsigned long long>();
+    unsigned long long* cols = c.sp_cols.as<unsigned long long>();
+    N* data = c.sp_data.as<N>();
+    const PartInfo* info = c.part_info.as<PartInfo>();
+    const unsigned long long* base = c.sp_f.as<unsigned long long>();
+    const unsigned long long* start = c.sp_e.as<unsigned long long>();
+    if (n_rec) {
+        poly_expand_kernel<N><<<(n_rec + 255) / 256, 256, 0, s>>>(keys, c.sp_a.as<uint32_t>(),
+                                                                 c.sp_b.as<unsigned long long>(), n_rec, L, info, base,
+                                                                 start, rows, cols, data);
+        launches++;
+    }
+    if (nv_line) {
+        line_expand_kernel<N><<<(nv_line + 255) / 256, 256, 0, s>>>(
+            P, dg->x[1], dg->y[1], dg->tag[1], nv_line, info, c.last_kept.as<uint32_t>(), c.counters.as<Counters>(),
+            c.sp_c.as<unsigned long long>(), base, start, rows, cols, data);
+        launches++;
+    }
+    if (nv_pt) {
+        point_expand_kernel<N><<<(nv_pt + 255) / 256, 256, 0, s>>>(P, dg->x[2], dg->y[2], dg->tag[2], nv_pt, info,
+                                                                  c.sp_d.as<unsigned long long>(), base, start, rows,
+                                                                  cols, data);
+        launches++;
+    }
+}
+
+static void rasterize_sparse(rz_geoms* g, const rz_context* ctx, rz_sparse* out, rz_stats* st) {
+    const rz_raster_info& ri = ctx->raster_info;
+    if (!ctx->field_is_scalar && ctx->field_len != g->n_geoms)
+        throw Error{RZ_VALUE_ERROR, "Geometry and field lengths must match"};
+    if (ctx->band_of_geom && ctx->by_len != g->n_geoms)
+        throw Error{RZ_VALUE_ERROR, "Geometry and by lengths must match"};
+    const size_t isz = dtype_size(ctx->dtype);
+    if (!isz) throw Error{RZ_VALUE_ERROR, "Unsupported dtype"};
+    if (ctx->pixel_fn < 0 || ctx->pixel_fn > RZ_ANY) throw Error{RZ_VALUE_ERROR, "Unknown pixel function"};
+    if (ctx->all_touched)
+        throw Error{RZ_RUNTIME_ERROR, "all_touched=True is not implemented on the B200 path yet."};
+    const uint32_t n_bands = ctx->band_of_geom ? (uint32_t)std::max(ctx->n_bands, 0) : 1u;
+    out->counts.assign(n_bands, 0);
+    if (ri.nrows == 0 || ri.ncols == 0 || n_bands == 0) return;
+    if (ri.nrows >= (1ull << 31) || ri.ncols >= (1ull << 31))
+        throw Error{RZ_RUNTIME_ERROR, "Raster dimensions above 2^31 are not supported."};
+    const uint32_t nv_poly = (uint32_t)g->pool[0].size(), nv_line = (uint32_t)g->pool[1].size(),
+                   nv_pt = (uint32_t)g->pool[2].size();
+    if (ri.xres != ri.yres && nv_line)
+        throw Error{RZ_RUNTIME_ERROR,
+                    "sparse encoding of line geometries on non-square pixels (per-geometry pixel dedup) is not "
+                    "implemented on the B200 path yet."};
+
+    DeviceCtx& c = device_ctx(ctx->device);
+    std::lock_guard<std::mutex> lk(c.mu);
+    CUDA_TRY(cudaSetDevice(c.dev));
+    cudaStream_t s = ctx->stream ? (cudaStream_t)ctx->stream : c.stream;
+    rz_stats S;
+    std::memset(&S, 0, sizeof S);
+    enum { EV_START, EV_END };
+    CUDA_TRY(cudaEventRecord(c.ev[EV_START], s));
+    size_t h2d = 0;
+    DeviceGeoms* dg = geoms_on_device(g, c, s, (ctx->flags & RZ_FLAG_FORCE_H2D) != 0, &h2d);
+    const uint32_t n_parts = (uint32_t)g->part_kind.size();
+    const size_t n_field = ctx->field_is_scalar ? 1 : (size_t)g->n_geoms;
+    c.field.ensure(std::max<size_t>(n_field * isz, 8));
+    if (n_field) CUDA_TRY(cudaMemcpyAsync(c.field.p, ctx->field, n_field * isz, cudaMemcpyHostToDevice, s));
+    const uint8_t* d_valid = nullptr;
+    if (ctx->field_valid && g->n_geoms) {
+        c.valid.ensure(g->n_geoms);
+        CUDA_TRY(cudaMemcpyAsync(c.valid.p, ctx->field_valid, g->n_geoms, cudaMemcpyHostToDevice, s));
+        d_valid = c.valid.as<uint8_t>();
+    }
+    const int32_t* d_band = nullptr;
+    if (ctx->band_of_geom && g->n_geoms) {
+        c.band.ensure(g->n_geoms * 4);
+        CUDA_TRY(cudaMemcpyAsync(c.band.p, ctx->band_of_geom, g->n_geoms * 4, cudaMemcpyHostToDevice, s));
+        d_band = c.band.as<int32_t>();
+    }
+    S.h2d_bytes = h2d + n_field * isz;
+
+    KParams P;
+    std::memset(&P, 0, sizeof P);
+    P.xmin = ri.xmin;
+    P.ymax = ri.ymax;
+    P.xres = ri.xres;
+    P.yres = ri.yres;
+    P.nrows = (uint32_t)ri.nrows;
+    P.ncols = (uint32_t)ri.ncols;
+    P.nrows_f = (double)ri.nrows;
+    P.ncols_f = (double)ri.ncols;
+    P.tile_w = 1u << 31;  // a single column tile: crossings keep absolute columns
+    P.tile_shift = 31;
+    P.n_tiles = 1;
+    P.win_r0 = 0;
+    P.win_r1 = P.nrows;
+    P.n_bands = n_bands;
+    P.n_parts = n_parts;
+    SparseLayout L;
+    L.col_bits = bits_for(ri.ncols + 1);
+    L.row_bits = std::max(1u, bits_for(ri.nrows));
+    const uint32_t part_bits = std::max(1u, bits_for(std::max<uint64_t>(n_parts, 1)));
+    const uint32_t key_bits = L.col_bits + L.row_bits + part_bits;
+    if (key_bits > 64) throw Error{RZ_RUNTIME_ERROR, "Problem too large for the 64-bit sparse record key."};
+    S.key_bits = key_bits;
+    S.n_parts = n_parts;
+    S.n_poly_vertices = nv_poly;
+    S.n_line_vertices = nv_line;
+    S.n_points = nv_pt;
+    uint32_t launches = 0;
+    if (n_parts == 0) return;
+
+    c.part_info.ensure((size_t)n_parts * sizeof(PartInfo));
+    c.last_kept.ensure((size_t)n_parts * 4);
+    c.counters.ensure(sizeof(Counters));
+    part_prepare_kernel<<<(n_parts + 255) / 256, 256, 0, s>>>(P, dg->part_kind, dg->part_geom, dg->part_xlo,
+                                                              dg->part_xhi, c.field.as<uint8_t>(), (uint32_t)isz,
+                                                              ctx->field_is_scalar, d_valid, d_band,
+                                                              c.part_info.as<PartInfo>());
+    launches++;
+    const PartInfo* d_info = c.part_info.as<PartInfo>();
+    Counters* d_ctr = c.counters.as<Counters>();
+    CUDA_TRY(cudaMemsetAsync(d_ctr, 0, sizeof(Counters), s));
+
+    // ---- polygon crossings: count, emit in part order, sort by (part,row,col) ---------------------
+    uint32_t n_rec = 0;
+    uint64_t* keys = nullptr;
+    if (nv_poly) {
+        const uint32_t poly_blocks = (nv_poly + SETUP_THREADS - 1) / SETUP_THREADS;
+        c.block_total.ensure((size_t)poly_blocks * 4);
+        poly_count_kernel<<<poly_blocks, SETUP_THREADS, 0, s>>>(P, dg->x[0], dg->y[0], dg->tag[0], nv_poly, d_info,
+                                                               c.block_total.as<uint32_t>(), d_ctr);
+        scan_u32_kernel<<<1, 1024, 0, s>>>(c.block_total.as<uint32_t>(), poly_blocks);
+        launches += 2;
+        CUDA_TRY(cudaMemcpyAsync(c.h_counters, d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(cudaStreamSynchronize(s));
+        if (c.h_counters->records >= (1ull << 32) - 4096)
+            throw Error{RZ_RUNTIME_ERROR, "Too many polygon crossings for one sparse call (limit 2^32)."};
+        n_rec = (uint32_t)c.h_counters->records;
+        S.n_crossings = n_rec;
+        S.n_records = n_rec;
+        if (n_rec) {
+            c.keys_a.ensure((size_t)n_rec * 8);
+            c.keys_b.ensure((size_t)n_rec * 8);
+            uint64_t* ka = c.keys_a.as<uint64_t>();
+            uint64_t* kb = c.keys_b.as<uint64_t>();
+            poly_emit_sparse_kernel<<<poly_blocks, SETUP_THREADS, 0, s>>>(P, L, dg->x[0], dg->y[0], dg->tag[0], nv_poly,
+                                                                         d_info, c.block_total.as<uint32_t>(), ka);
+            launches++;
+            if (n_rec > 1) {
+                const uint32_t n_blocks = (n_rec + RS_TILE - 1) / RS_TILE;
+                c.hist.ensure((size_t)n_blocks * RS_RADIX * 4);
+                c.digit_total.ensure(RS_RADIX * 4);
+                // records are emitted in part order: a stable sort on (row, col) would interleave parts, so
+                // all bits are sorted
+                for (uint32_t shift = 0; shift < key_bits; shift += 8) {
+                    radix_hist_kernel<<<n_blocks, RS_THREADS, 0, s>>>(ka, n_rec, shift, n_blocks, c.hist.as<uint32_t>());
+                    radix_scan_rows_kernel<<<RS_RADIX, 1024, 0, s>>>(c.hist.as<uint32_t>(), n_blocks,
+                                                                    c.digit_total.as<uint32_t>());
+                    radix_scatter_kernel<<<n_blocks, RS_THREADS, 0, s>>>(ka, kb, n_rec, shift, n_blocks,
+                                                                         c.hist.as<uint32_t>(),
+                                                                         c.digit_total.as<uint32_t>());
+                    std::swap(ka, kb);
+                    launches += 3;
+                    S.sort_passes++;
+                }
+            }
+            keys = ka;
+        }
+    }
+    // ---- spans: pair the sorted crossings, prefix-sum their lengths ------------------------------
+    unsigned long long poly_total = 0, line_total = 0, pt_total = 0;
+    if (n_rec) {
+        c.sp_a.ensure((size_t)n_rec * 4);  // seg_start
+        c.sp_b.ensure((size_t)n_rec * 8);  // poly_off
+        device_scan<OpMax>(InSegHead{keys, L.col_bits}, n_rec, OutSegStart{c.sp_a.as<uint32_t>()}, c.sp_partial, s,
+                           launches);
+        device_scan<OpAdd>(InSpanLen{keys, c.sp_a.as<uint32_t>(), n_rec, L.col_bits}, n_rec,
+                           OutPrefix64{c.sp_b.as<unsigned long long>()}, c.sp_partial, s, launches);
+        poly_total = scan_total(c.sp_partial, n_rec, s);
+    }
+    if (nv_line) {
+        CUDA_TRY(cudaMemsetAsync(c.last_kept.p, 0, (size_t)n_parts * 4, s));
+        line_last_kept_kernel<<<(nv_line + 255) / 256, 256, 0, s>>>(P, dg->x[1], dg->y[1], dg->tag[1], nv_line, d_info,
+                                                                   c.last_kept.as<uint32_t>(), d_ctr);
+        launches++;
+        c.sp_c.ensure((size_t)nv_line * 8);
+        device_scan<OpAdd>(InLineLen{P, dg->x[1], dg->y[1], dg->tag[1], d_info, c.last_kept.as<uint32_t>(), d_ctr, nv_line},
+                           nv_line, OutPrefix64{c.sp_c.as<unsigned long long>()}, c.sp_partial, s, launches);
+        line_total = scan_total(c.sp_partial, nv_line, s);
+        CUDA_TRY(cudaMemcpyAsync(c.h_counters, d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(cudaStreamSynchronize(s));
+        if (c.h_counters->bad_line)
+            throw Error{RZ_RUNTIME_ERROR,
+                        "A line segment extends more than 2^29 pixels from the raster origin; unsupported."};
+    }
+    if (nv_pt) {
+        c.sp_d.ensure((size_t)nv_pt * 8);
+        device_scan<OpAdd>(InPointHit{P, dg->x[2], dg->y[2], dg->tag[2], d_info}, nv_pt,
+                           OutPrefix64{c.sp_d.as<unsigned long long>()}, c.sp_partial, s, launches);
+        pt_total = scan_total(c.sp_partial, nv_pt, s);
+    }
+    // ---- per-part counts, band-major bases ------------------------------------------------------
+    c.task_start.ensure(((size_t)n_parts + 1) * 4);  // rec_beg
+    part_rec_range_kernel<<<(n_parts + 1 + 255) / 256, 256, 0, s>>>(keys, n_rec, L.col_bits + L.row_bits, n_parts,
+                                                                    c.task_start.as<uint32_t>());
+    c.sp_g.ensure((size_t)n_parts * 8);  // count
+    c.sp_e.ensure((size_t)n_parts * 8);  // start
+    c.sp_f.ensure((size_t)n_parts * 8);  // base
+    part_count_kernel<<<(n_parts + 255) / 256, 256, 0, s>>>(
+        n_parts, dg->part_kind, dg->part_vbeg, dg->part_vend, c.task_start.as<uint32_t>(),
+        c.sp_b.as<unsigned long long>(), n_rec, poly_total, c.sp_c.as<unsigned long long>(), nv_line, line_total,
+        c.sp_d.as<unsigned long long>(), nv_pt, pt_total, c.sp_g.as<unsigned long long>(),
+        c.sp_e.as<unsigned long long>());
+    launches += 2;
+    unsigned long long total = 0;
+    for (uint32_t b = 0; b < n_bands; b++) {  // bands in sorted key order, parts ascending inside a band
+        device_scan<OpAdd>(InBandCount{c.sp_g.as<unsigned long long>(), d_info, (int32_t)b}, n_parts,
+                           OutBandBase{c.sp_f.as<unsigned long long>(), d_info, (int32_t)b, total}, c.sp_partial, s,
+                           launches);
+        const unsigned long long bt = scan_total(c.sp_partial, n_parts, s);
+        out->counts[b] = bt;
+        total += bt;
+    }
+    // ---- expand ------------------------------------------------------------------------------------
+    out->rows.resize(total);
+    out->cols.resize(total);
+    out->data.resize(total * isz);
+    if (total) {
+        c.sp_rows.ensure(total * 8);
+        c.sp_cols.ensure(total * 8);
+        c.sp_data.ensure(total * isz);
+        switch (isz) {  // triplet values are moved bit-wise: dispatch on the item size only
+            case 1: sparse_expand<uint8_t>(s, P, L, dg, c, n_rec, keys, nv_line, nv_pt, launches); break;
+            case 2: sparse_expand<uint16_t>(s, P, L, dg, c, n_rec, keys, nv_line, nv_pt, launches); break;
+            case 4: sparse_expand<uint32_t>(s, P, L, dg, c, n_rec, keys, nv_line, nv_pt, launches); break;
+            default: sparse_expand<uint64_t>(s, P, L, dg, c, n_rec, keys, nv_line, nv_pt, launches); break;
+        }
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaMemcpyAsync(out->rows.data(), c.sp_rows.p, total * 8, cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(cudaMemcpyAsync(out->cols.data(), c.sp_cols.p, total * 8, cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(cudaMemcpyAsync(out->data.data(), c.sp_data.p, total * isz, cudaMemcpyDeviceToHost, s));
+        S.d2h_bytes = total * (16 + isz);
+    }
+    CUDA_TRY(cudaEventRecord(c.ev[EV_END], s));
+    CUDA_TRY(cudaEventSynchronize(c.ev[EV_END]));
+    CUDA_TRY(cudaEventElapsedTime(&S.total_ms, c.ev[EV_START], c.ev[EV_END]));
+    S.out_bytes = total * (16 + isz);
     S.kernel_launches = launches;
     if (st) *st = S;
 }
@@ -752,14 +1049,12 @@ int rz_rasterize_dense(rz_geoms* g, const rz_context* ctx, void* out, rz_stats* 
     return guarded(err, errlen, [&]() { rz::rasterize_dense(g, ctx, out, stats); });
 }
 
-// ---- sparse (implemented in rz_sparse.cuh; placeholders until then) ---------------------------
-struct rz_sparse {
-    std::vector<uint64_t> rows, cols, counts;
-    std::vector<uint8_t> data;
-};
-int rz_rasterize_sparse(rz_geoms*, const rz_context*, rz_sparse**, rz_stats*, char* err, size_t errlen) {
-    set_err(err, errlen, "sparse encoding is not implemented on the B200 path yet.");
-    return RZ_RUNTIME_ERROR;
+int rz_rasterize_sparse(rz_geoms* g, const rz_context* ctx, rz_sparse** out, rz_stats* stats, char* err,
+                        size_t errlen) {
+    std::unique_ptr<rz_sparse> sp(new rz_sparse());
+    int rc = guarded(err, errlen, [&]() { rz::rasterize_sparse(g, ctx, sp.get(), stats); });
+    if (rc == RZ_OK) *out = sp.release();
+    return rc;
 }
 uint64_t rz_sparse_len(const rz_sparse* s) { return s->rows.size(); }
 uint64_t rz_sparse_n_bands(const rz_sparse* s) { return s->counts.size(); }

@@ -35,6 +35,8 @@ void Flattener::end_geometry(bool keep) {
         g_->part_geom.resize(mark_parts_);
         g_->part_xlo.resize(mark_parts_);
         g_->part_xhi.resize(mark_parts_);
+        g_->part_vbeg.resize(mark_parts_);
+        g_->part_vend.resize(mark_parts_);
         return;
     }
     if (geom_has_bounds_) {
@@ -65,9 +67,14 @@ void Flattener::begin_part(int kind) {
     g_->part_geom.push_back(g_->n_geoms);
     g_->part_xlo.push_back(std::numeric_limits<double>::infinity());
     g_->part_xhi.push_back(-std::numeric_limits<double>::infinity());
+    g_->part_vbeg.push_back((uint32_t)g_->pool[kind].size());
+    g_->part_vend.push_back((uint32_t)g_->pool[kind].size());
 }
 
-void Flattener::end_part() { kind_ = -1; }
+void Flattener::end_part() {
+    g_->part_vend[part_] = (uint32_t)g_->pool[kind_].size();
+    kind_ = -1;
+}
 
 void Flattener::begin_seq(bool counts_for_bounds) {
     seq_start_ = g_->pool[kind_].size();

@@ -771,12 +771,38 @@ struct FillParams {
 constexpr int FILL_WARPS = 4;
 constexpr uint32_t FILL_MAX_TILE_W = 1024;  // 32 lanes x 32 toggle bits
 
-// Close a polygon run: turn the toggle mask into the inside mask and apply the part's value.
+// Rare path: a polygon run with an odd number of crossings.  burners.rs:305 pairs the sorted
+// crossings with chunks_exact(2), i.e. the largest column is ignored: cancel one toggle there.
+__device__ __noinline__ void drop_last_crossing(uint32_t* tog, const uint64_t* __restrict__ keys, uint32_t beg,
+                                                uint32_t end, uint32_t col_mask, uint32_t w, uint32_t lane) {
+    uint32_t mx = 0;
+    for (uint32_t i = beg + lane; i < end; i += 32) mx = max(mx, (uint32_t)keys[i] & col_mask);
+    mx = __reduce_max_sync(0xffffffffu, mx);
+    if (mx < w && lane == (mx >> 5)) tog[lane] ^= 1u << (mx & 31);
+    __syncwarp();
+}
+
+// Apply value v to the pixels whose bit is set in the warp's inside mask (word `lane` of m covers
+// pixels lane*32 .. lane*32+31).  One 32-pixel word per step, conflict-free shared-memory access.
 template <typename N, int FN>
-__device__ __forceinline__ void finish_poly_run(uint32_t* tog, N* row, uint32_t lane, uint32_t lt_mask, uint32_t w,
-                                                uint32_t run_cnt, uint32_t run_max, N v, N bg) {
-    // odd run: the sorted list's last crossing has no partner (burners.rs:305)
-    if ((run_cnt & 1u) && run_max < w && lane == (run_max >> 5)) tog[lane] ^= 1u << (run_max & 31);
+__device__ __forceinline__ void apply_mask(N* __restrict__ row_lane, uint32_t m, uint32_t lane, N v, N bg) {
+    uint32_t nz = __ballot_sync(0xffffffffu, m != 0);
+    while (nz) {
+        const int src = __ffs(nz) - 1;
+        nz &= nz - 1;
+        const uint32_t mw = __shfl_sync(0xffffffffu, m, src);
+        N* p = row_lane + src * 32;
+        const N cur = *p;
+        const N nv = apply_px<N, FN>(cur, v, bg);
+        *p = ((mw >> lane) & 1u) ? nv : cur;
+    }
+}
+
+// Close a polygon run: turn the toggle mask into the even-odd inside mask and burn the value.
+// Bits at or beyond the tile's width may end up set; they only touch shared-memory pixels that are
+// never flushed.
+template <typename N, int FN>
+__device__ __forceinline__ void finish_poly_run(uint32_t* tog, N* row_lane, uint32_t lane, uint32_t lt_mask, N v, N bg) {
     const uint32_t t = tog[lane];
     tog[lane] = 0;
     uint32_t m = t;
@@ -787,23 +813,11 @@ __device__ __forceinline__ void finish_poly_run(uint32_t* tog, N* row, uint32_t 
     m ^= m << 16;
     const uint32_t odd_words = __ballot_sync(0xffffffffu, __popc(t) & 1);
     if (__popc(odd_words & lt_mask) & 1) m = ~m;
-    const int rem = (int)w - (int)(lane * 32);
-    if (rem <= 0) m = 0;
-    else if (rem < 32) m &= (1u << rem) - 1u;
-    uint32_t nz = __ballot_sync(0xffffffffu, m != 0);
-    while (nz) {
-        const int src = __ffs(nz) - 1;
-        nz &= nz - 1;
-        const uint32_t mw = __shfl_sync(0xffffffffu, m, src);
-        if ((mw >> lane) & 1u) {
-            const uint32_t p = (uint32_t)src * 32 + lane;
-            row[p] = apply_px<N, FN>(row[p], v, bg);
-        }
-    }
+    apply_mask<N, FN>(row_lane, m, lane, v, bg);
     __syncwarp();
 }
 
-template <typename N, int FN>
+template <typename N, int FN, bool ALL_POLY>
 __global__ void __launch_bounds__(FILL_WARPS * 32)
 fill_kernel(FillParams F, const uint64_t* __restrict__ keys, const uint32_t* __restrict__ task_start,
             const PartInfo* __restrict__ info, const uint8_t* __restrict__ part_kind, uint64_t bg_bits,
@@ -811,7 +825,8 @@ fill_kernel(FillParams F, const uint64_t* __restrict__ keys, const uint32_t* __r
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ uint32_t s_tog[FILL_WARPS][32];
     const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
-    N* row = reinterpret_cast<N*>(smem_raw) + (size_t)warp * F.tile_w;
+    N* row = reinterpret_cast<N*>(smem_raw) + (size_t)warp * FILL_MAX_TILE_W;
+    N* row_lane = row + lane;
     uint32_t* tog = s_tog[warp];
     const N bg = value_from_bits<N>(bg_bits);
     const uint32_t col_mask = (1u << F.col_bits) - 1u;
@@ -827,61 +842,64 @@ fill_kernel(FillParams F, const uint64_t* __restrict__ keys, const uint32_t* __r
         const uint32_t w = min(F.tile_w, F.ncols - c0);
         N* dst = out + ((size_t)band * F.out_rows + F.win_row_off + r) * F.ncols + c0;
         const uint32_t beg = task_start[task], end = task_start[task + 1];
+        uint64_t key_next = beg + lane < end ? keys[beg + lane] : ~0ull;
 
-        for (uint32_t i = lane; i < w; i += 32) row[i] = bg;
+        // every pixel of the warp's tile starts as background (geo/raster.rs:23-28)
+        for (uint32_t i = lane; i < FILL_MAX_TILE_W; i += 32) row[i] = bg;
         __syncwarp();
 
-        uint64_t carry_hi = ~0ull;  // (task|part) of the record before this chunk
-        uint32_t run_cnt = 0, run_max = 0;
-        uint32_t open_part = 0xffffffffu, open_kind = 0;  // run left open at the end of the previous chunk
+        uint64_t carry_hi = ~0ull;   // (task|part) of the record before this chunk
+        uint32_t run_cnt = 0;        // records of the currently open polygon run
+        uint32_t run_beg = beg;      // its first record
+        uint32_t open_kind = 3;      // kind of the run left open by the previous chunk (3 = none)
+        N open_v = bg;
         for (uint32_t base = beg; base < end; base += 32) {
-            const uint32_t i = base + lane;
             const uint32_t nvalid = min(32u, end - base);
             const bool valid = lane < nvalid;
-            const uint64_t key = valid ? keys[i] : ~0ull;
+            const uint64_t key = key_next;
+            key_next = base + 32 + lane < end ? keys[base + 32 + lane] : ~0ull;  // prefetch
             const uint64_t hi = key >> F.col_bits;
             uint64_t prev_hi = __shfl_up_sync(0xffffffffu, hi, 1);
             if (lane == 0) prev_hi = carry_hi;
             const uint32_t heads = __ballot_sync(0xffffffffu, valid && hi != prev_hi);
-            const uint32_t part = (uint32_t)((key >> F.part_shift) & part_mask);
+            const uint32_t part = (uint32_t)(hi & part_mask);
             const uint32_t col = (uint32_t)key & col_mask;
+            const N my_v = valid ? value_from_bits<N>(info[part].value_bits) : bg;
             const bool last_chunk = base + 32 >= end;
 
-            if ((heads & 1u) && open_part != 0xffffffffu) {  // the open run ended exactly at the chunk boundary
-                if (open_kind == 0)
-                    finish_poly_run<N, FN>(tog, row, lane, lt_mask, w, run_cnt, run_max,
-                                           value_from_bits<N>(info[open_part].value_bits), bg);
-                else {
+            if ((heads & 1u) && open_kind != 3) {  // the open run ended exactly at the chunk boundary
+                if (open_kind == 0) {
+                    if (run_cnt & 1u) drop_last_crossing(tog, keys, run_beg, base, col_mask, w, lane);
+                    finish_poly_run<N, FN>(tog, row_lane, lane, lt_mask, open_v, bg);
+                } else if (open_kind == 1) {
                     tog[lane] = 0;
                     __syncwarp();
                 }
                 run_cnt = 0;
-                run_max = 0;
             }
-            open_part = 0xffffffffu;
+            open_kind = 3;
 
             uint32_t start = 0;
             while (start < nvalid) {  // one iteration per run present in this chunk (warp-uniform)
-                const uint32_t rest = start < 31 ? (heads & (0xffffffffu << (start + 1))) : 0u;
+                const uint32_t rest = start < 31 ? (heads & (0xfffffffeu << start)) : 0u;
                 const uint32_t stop = rest ? (uint32_t)(__ffs(rest) - 1) : nvalid;
                 const bool in_run = lane >= start && lane < stop;
                 const bool run_ends = stop < nvalid || last_chunk;
-                const uint32_t run_part = __shfl_sync(0xffffffffu, part, start);
-                const uint32_t kind = F.all_poly ? 0u : (uint32_t)part_kind[run_part];
+                const N v = __shfl_sync(0xffffffffu, my_v, start);
+                uint32_t kind = 0;
+                if (!ALL_POLY) kind = part_kind[__shfl_sync(0xffffffffu, part, start)];
+                if ((heads >> start) & 1u) run_beg = base + start;
                 if (kind == 0) {
                     if (in_run && col < w) atomicXor(&tog[col >> 5], 1u << (col & 31));
                     run_cnt += stop - start;
-                    run_max = max(run_max, __reduce_max_sync(0xffffffffu, in_run ? col : 0u));
                     __syncwarp();
                     if (run_ends) {
-                        finish_poly_run<N, FN>(tog, row, lane, lt_mask, w, run_cnt, run_max,
-                                               value_from_bits<N>(info[run_part].value_bits), bg);
+                        if (run_cnt & 1u) drop_last_crossing(tog, keys, run_beg, base + stop, col_mask, w, lane);
+                        finish_poly_run<N, FN>(tog, row_lane, lane, lt_mask, v, bg);
                         run_cnt = 0;
-                        run_max = 0;
                     }
                 } else {
                     // line / point pixels: one write per record (burners.rs:69-89, 250-258)
-                    const N v = value_from_bits<N>(info[run_part].value_bits);
                     const bool dedup = kind == 1 && F.dedup_lines;  // LineWriter + PixelCache (writers.rs:25-29)
                     if (dedup) {
                         if (in_run) {
@@ -908,8 +926,8 @@ fill_kernel(FillParams F, const uint64_t* __restrict__ keys, const uint32_t* __r
                     }
                 }
                 if (!run_ends) {
-                    open_part = run_part;
-                    open_kind = (kind == 1 && F.dedup_lines) ? 1u : (kind == 0 ? 0u : 2u);
+                    open_kind = kind == 0 ? 0u : ((kind == 1 && F.dedup_lines) ? 1u : 2u);
+                    open_v = v;
                 }
                 start = stop;
             }

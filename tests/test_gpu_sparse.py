@@ -1,0 +1,103 @@
+"""GPU parity of the sparse (COO) encoding: triplets must equal the oracle's, element for element
+and in the same (burn) order — rust/src/encoding/writers.rs:86-131."""
+import numpy as np
+import pytest
+
+import oracle
+import synth
+from cases import GEOMS, VALUES, sq
+from rusterize_b200 import core
+
+pytestmark = pytest.mark.gpu
+
+
+def both(geoms, fun="last", dtype="float64", burn=1, bg=0, by=None, field_valid=None, **kw):
+    og = oracle.Geoms.from_any(geoms)
+    ori = oracle.raster_info(og, **kw)
+    exp = oracle.rasterize_sparse(og, ori, fun, dtype, burn, field_valid, by, bg)
+    g = core.Geoms.from_any(geoms)
+    ri = core.raster_info(g, **kw)
+    band, nb = None, 1
+    if by is not None:
+        band, bn = core.group_keys(by)
+        nb = len(bn)
+    got = core.rasterize_sparse(g, ri, fun, dtype, burn, field_valid, band, nb, bg)
+    return exp, got, ri
+
+
+def assert_same(exp, got):
+    assert np.array_equal(exp["counts"], got["counts"]), (exp["counts"], got["counts"])
+    for k in ("rows", "cols"):
+        assert np.array_equal(exp[k], got[k]), k
+    assert exp["data"].dtype == got["data"].dtype
+    assert np.array_equal(exp["data"], got["data"], equal_nan=exp["data"].dtype.kind == "f")
+
+
+def test_documented_sparse_frame():
+    # python/docs/python.md:106-136
+    exp, got, ri = both(GEOMS, "sum", "float64", VALUES, np.nan, resolution=(1, 1))
+    assert_same(exp, got)
+    assert len(got["rows"]) == 29363
+    assert list(zip(got["rows"][:3].tolist(), got["cols"][:3].tolist())) == [(6, 40), (6, 41), (6, 42)]
+    assert list(zip(got["rows"][-2:].tolist(), got["cols"][-2:].tolist(), got["data"][-2:].tolist())) == \
+        [(39, 289, 5.0), (39, 290, 5.0)]
+
+
+@pytest.mark.parametrize("dtype", ["uint8", "int32", "float32", "float64", "uint64", "int16"])
+def test_mixed_geometries(dtype):
+    seed = 100 + oracle.DTYPES.index(dtype)
+    geoms = synth.mixed_geometries(seed, 200, 300, 300, rho=25.0)
+    burn = (np.arange(len(geoms)) % 11).astype(dtype)
+    exp, got, _ = both(geoms, "sum", dtype, burn, 0, shape=(300, 300), extent=(0, 0, 300, 300))
+    assert_same(exp, got)
+
+
+def test_bands_and_null_fields():
+    geoms = synth.mixed_geometries(7, 250, 256, 256)
+    n = len(geoms)
+    by = [str(i % 7) for i in range(n)]
+    valid = (np.arange(n) % 4 != 1).astype(np.uint8)
+    exp, got, _ = both(geoms, "max", "int32", np.arange(n), 0, by=by, field_valid=valid, shape=(256, 256),
+                       extent=(0, 0, 256, 256))
+    assert len(got["counts"]) == 7
+    assert_same(exp, got)
+
+
+def test_edge_cases():
+    geoms = [sq(-50, -50, 500, 500), sq(98, 98, 120, 120), "POLYGON ((30 30, 70 70, 70 30, 30 70, 30 30))",
+             "LINESTRING (-500 50, 500 50)", "LINESTRING (0 0, 100 100, 0 0)", "POINT (100 100)", "POINT (5 5)",
+             "MULTIPOINT ((5 5), (5 5), (-1 5))", "GEOMETRYCOLLECTION EMPTY", "POLYGON EMPTY"]
+    exp, got, _ = both(geoms, "count", "uint16", np.arange(len(geoms)), 0, shape=(100, 100), extent=(0, 0, 100, 100))
+    assert_same(exp, got)
+    # nothing burned at all
+    exp, got, _ = both(["POINT (1000 1000)"], shape=(10, 10), extent=(0, 0, 10, 10))
+    assert len(got["rows"]) == 0 and got["counts"].tolist() == [0]
+
+
+def test_small_parcels_like_config5():
+    # BASELINE config 5 in miniature: axis-jittered quads, sparse, f32
+    rng = np.random.default_rng(5)
+    n, size = 20000, 2048
+    cx, cy = rng.random(n) * size, rng.random(n) * size
+    w, h = 6 + 8 * rng.random(n), 6 + 8 * rng.random(n)
+    j = rng.random((n, 4, 2)) - 0.5
+    quad = np.stack([np.stack([cx - w / 2, cy - h / 2], 1), np.stack([cx + w / 2, cy - h / 2], 1),
+                     np.stack([cx + w / 2, cy + h / 2], 1), np.stack([cx - w / 2, cy + h / 2], 1)], 1) + j
+    ring = np.concatenate([quad, quad[:, :1]], 1).reshape(-1, 2)
+    off = np.arange(n + 1, dtype=np.uint64) * 5
+    vals = rng.random(n).astype(np.float32)
+    g = core.Geoms.from_polygons(ring[:, 0], ring[:, 1], off)
+    ri = core.raster_info(None, shape=(size, size), extent=(0, 0, size, size))
+    got = core.rasterize_sparse(g, ri, "sum", "float32", vals, background=np.nan)
+    og = oracle.Geoms.from_rings(ring[:, 0], ring[:, 1], off)
+    ori = oracle.raster_info(None, shape=(size, size), extent=(0, 0, size, size))
+    exp = oracle.rasterize_sparse(og, ori, "sum", "float32", vals, None, None, np.nan)
+    assert_same(exp, got)
+    # size-independent property: replaying the triplets gives the dense raster
+    dense, _ = core.rasterize_dense(g, ri, "sum", "float32", vals, background=np.nan)
+    assert np.array_equal(oracle.sparse_replay(ori, got | {"data": got["data"]}, "sum", np.nan), dense, equal_nan=True)
+
+
+def test_unsupported_sparse_line_dedup_is_loud():
+    with pytest.raises(RuntimeError, match="non-square pixels"):
+        both(["LINESTRING (0 0, 4 4)"], shape=(3, 7), extent=(0, 0, 4, 4))
