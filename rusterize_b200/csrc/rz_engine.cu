@@ -895,6 +895,146 @@ static void rasterize_sparse(rz_geoms* g, const rz_context* ctx, rz_sparse* out,
     if (st) *st = S;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// sparse replay (SparseArray::build_array)
+// ------------------------------------------------------------------------------------------------
+typedef void (*ReplayLaunch)(dim3, size_t, cudaStream_t, FillParams, const uint64_t*, const uint32_t*,
+                             const unsigned long long*, const void*, uint32_t, uint64_t, void*);
+template <typename N, int FN>
+static void replay_launch(dim3 grid, size_t smem, cudaStream_t s, FillParams F, const uint64_t* keys,
+                          const uint32_t* task_start, const unsigned long long* cols, const void* data, uint32_t idx_bits,
+                          uint64_t bg, void* out) {
+    replay_fill_kernel<N, FN><<<grid, FILL_WARPS * 32, smem, s>>>(F, keys, task_start, cols, (const N*)data, idx_bits, bg,
+                                                                 (N*)out);
+}
+template <typename N> static ReplayLaunch replay_for_fn(int fn) {
+    switch (fn) {
+        case RZ_SUM: return replay_launch<N, RZ_SUM>;
+        case RZ_FIRST: return replay_launch<N, RZ_FIRST>;
+        case RZ_LAST: return replay_launch<N, RZ_LAST>;
+        case RZ_MIN: return replay_launch<N, RZ_MIN>;
+        case RZ_MAX: return replay_launch<N, RZ_MAX>;
+        case RZ_COUNT: return replay_launch<N, RZ_COUNT>;
+        case RZ_ANY: return replay_launch<N, RZ_ANY>;
+    }
+    return nullptr;
+}
+static ReplayLaunch replay_for(int dtype, int fn) {
+    switch (dtype) {
+        case RZ_U8: return replay_for_fn<uint8_t>(fn);
+        case RZ_U16: return replay_for_fn<uint16_t>(fn);
+        case RZ_U32: return replay_for_fn<uint32_t>(fn);
+        case RZ_U64: return replay_for_fn<uint64_t>(fn);
+        case RZ_I8: return replay_for_fn<int8_t>(fn);
+        case RZ_I16: return replay_for_fn<int16_t>(fn);
+        case RZ_I32: return replay_for_fn<int32_t>(fn);
+        case RZ_I64: return replay_for_fn<int64_t>(fn);
+        case RZ_F32: return replay_for_fn<float>(fn);
+        case RZ_F64: return replay_for_fn<double>(fn);
+    }
+    return nullptr;
+}
+
+static void sparse_build_array(const rz_context* ctx, uint64_t n_bands, const uint64_t* counts, const uint64_t* rows,
+                               const uint64_t* cols, const void* data, void* out, rz_stats* st) {
+    const rz_raster_info& ri = ctx->raster_info;
+    const size_t isz = dtype_size(ctx->dtype);
+    if (!isz) throw Error{RZ_VALUE_ERROR, "Unsupported dtype"};
+    if (ctx->pixel_fn < 0 || ctx->pixel_fn > RZ_ANY) throw Error{RZ_VALUE_ERROR, "Unknown pixel function"};
+    if (ri.nrows == 0 || ri.ncols == 0 || n_bands == 0) return;
+    if (ri.nrows >= (1ull << 31) || ri.ncols >= (1ull << 31))
+        throw Error{RZ_RUNTIME_ERROR, "Raster dimensions above 2^31 are not supported."};
+    std::vector<unsigned long long> band_off(n_bands + 1, 0);
+    for (uint64_t b = 0; b < n_bands; b++) band_off[b + 1] = band_off[b] + counts[b];
+    const uint64_t n64 = band_off[n_bands];
+    if (n64 >= (1ull << 32) - 4096) throw Error{RZ_RUNTIME_ERROR, "Too many triplets for one replay call (limit 2^32)."};
+    const uint32_t n = (uint32_t)n64;
+    const bool out_dev = (ctx->flags & RZ_FLAG_OUT_ON_DEVICE) != 0;
+
+    DeviceCtx& c = device_ctx(ctx->device);
+    std::lock_guard<std::mutex> lk(c.mu);
+    CUDA_TRY(cudaSetDevice(c.dev));
+    cudaStream_t s = ctx->stream ? (cudaStream_t)ctx->stream : c.stream;
+    uint32_t tile_w = FILL_MAX_TILE_W;
+    while (tile_w / 2 >= ri.ncols && tile_w > 1) tile_w /= 2;
+    const uint32_t tile_shift = bits_for(tile_w);
+    const uint32_t n_tiles = (uint32_t)((ri.ncols + tile_w - 1) / tile_w);
+    const uint64_t n_tasks64 = n_bands * ri.nrows * n_tiles;
+    const uint32_t idx_bits = std::max(1u, bits_for(std::max<uint64_t>(n, 1)));
+    if (n_tasks64 >= (1ull << 31) || bits_for(n_tasks64 + 1) + idx_bits > 64)
+        throw Error{RZ_RUNTIME_ERROR, "Raster too large for a single replay call."};
+    const uint32_t n_tasks = (uint32_t)n_tasks64;
+    uint32_t launches = 0;
+    const size_t out_bytes = (size_t)n_tasks64 / n_tiles * ri.ncols * isz;
+    void* d_out = out;
+    if (!out_dev) {
+        c.win_out.ensure(out_bytes);
+        d_out = c.win_out.p;
+    }
+    c.sp_rows.ensure(std::max<size_t>((size_t)n * 8, 8));
+    c.sp_cols.ensure(std::max<size_t>((size_t)n * 8, 8));
+    c.sp_data.ensure(std::max<size_t>((size_t)n * isz, 8));
+    c.sp_g.ensure((n_bands + 1) * 8);
+    c.keys_a.ensure(std::max<size_t>((size_t)n * 8, 64));
+    c.keys_b.ensure(std::max<size_t>((size_t)n * 8, 64));
+    uint64_t* ka = c.keys_a.as<uint64_t>();
+    uint64_t* kb = c.keys_b.as<uint64_t>();
+    if (n) {
+        CUDA_TRY(cudaMemcpyAsync(c.sp_rows.p, rows, (size_t)n * 8, cudaMemcpyHostToDevice, s));
+        CUDA_TRY(cudaMemcpyAsync(c.sp_cols.p, cols, (size_t)n * 8, cudaMemcpyHostToDevice, s));
+        CUDA_TRY(cudaMemcpyAsync(c.sp_data.p, data, (size_t)n * isz, cudaMemcpyHostToDevice, s));
+        CUDA_TRY(cudaMemcpyAsync(c.sp_g.p, band_off.data(), (n_bands + 1) * 8, cudaMemcpyHostToDevice, s));
+        replay_emit_kernel<<<(n + 255) / 256, 256, 0, s>>>(c.sp_rows.as<unsigned long long>(),
+                                                           c.sp_cols.as<unsigned long long>(), n,
+                                                           c.sp_g.as<unsigned long long>(), (uint32_t)n_bands,
+                                                           (uint32_t)ri.nrows, (uint32_t)ri.ncols, n_tiles, tile_shift,
+                                                           idx_bits, n_tasks, ka);
+        launches++;
+        const uint32_t key_bits = idx_bits + bits_for((uint64_t)n_tasks + 1);
+        if (n > 1) {
+            const uint32_t n_blocks = (n + RS_TILE - 1) / RS_TILE;
+            c.hist.ensure((size_t)n_blocks * RS_RADIX * 4);
+            c.digit_total.ensure(RS_RADIX * 4);
+            for (uint32_t shift = idx_bits; shift < key_bits; shift += 8) {  // stable: burn order survives
+                radix_hist_kernel<<<n_blocks, RS_THREADS, 0, s>>>(ka, n, shift, n_blocks, c.hist.as<uint32_t>());
+                radix_scan_rows_kernel<<<RS_RADIX, 1024, 0, s>>>(c.hist.as<uint32_t>(), n_blocks,
+                                                                c.digit_total.as<uint32_t>());
+                radix_scatter_kernel<<<n_blocks, RS_THREADS, 0, s>>>(ka, kb, n, shift, n_blocks, c.hist.as<uint32_t>(),
+                                                                     c.digit_total.as<uint32_t>());
+                std::swap(ka, kb);
+                launches += 3;
+            }
+        }
+    }
+    c.task_start.ensure(((size_t)n_tasks + 1) * 4);
+    task_index_kernel<<<(n_tasks + 1 + 255) / 256, 256, 0, s>>>(ka, n, idx_bits, n_tasks, c.task_start.as<uint32_t>());
+    FillParams F;
+    std::memset(&F, 0, sizeof F);
+    F.n_tasks = n_tasks;
+    F.n_tiles = n_tiles;
+    F.tile_w = tile_w;
+    F.ncols = (uint32_t)ri.ncols;
+    uint64_t bg_bits = 0;
+    std::memcpy(&bg_bits, ctx->background, isz);
+    replay_for(ctx->dtype, ctx->pixel_fn)(dim3((n_tasks + FILL_WARPS - 1) / FILL_WARPS),
+                                          (size_t)FILL_WARPS * FILL_MAX_TILE_W * isz, s, F, ka,
+                                          c.task_start.as<uint32_t>(), c.sp_cols.as<unsigned long long>(), c.sp_data.p,
+                                          idx_bits, bg_bits, d_out);
+    launches += 2;
+    CUDA_TRY(cudaGetLastError());
+    if (!out_dev) CUDA_TRY(cudaMemcpyAsync(out, d_out, out_bytes, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    if (st) {
+        std::memset(st, 0, sizeof *st);
+        st->n_records = n;
+        st->kernel_launches = launches;
+        st->out_bytes = out_bytes;
+        st->h2d_bytes = (uint64_t)n * (16 + isz);
+        st->d2h_bytes = out_dev ? 0 : out_bytes;
+    }
+}
+
 }  // namespace rz
 
 // ================================================================================================
@@ -1063,10 +1203,9 @@ const uint64_t* rz_sparse_cols(const rz_sparse* s) { return s->cols.data(); }
 const void* rz_sparse_data(const rz_sparse* s) { return s->data.data(); }
 const uint64_t* rz_sparse_counts(const rz_sparse* s) { return s->counts.data(); }
 void rz_sparse_free(rz_sparse* s) { delete s; }
-int rz_sparse_build_array(const rz_context*, uint64_t, const uint64_t*, const uint64_t*, const uint64_t*, const void*,
-                          void*, rz_stats*, char* err, size_t errlen) {
-    set_err(err, errlen, "sparse replay is not implemented on the B200 path yet.");
-    return RZ_RUNTIME_ERROR;
+int rz_sparse_build_array(const rz_context* ctx, uint64_t n_bands, const uint64_t* counts, const uint64_t* rows,
+                          const uint64_t* cols, const void* data, void* out, rz_stats* stats, char* err, size_t errlen) {
+    return guarded(err, errlen, [&]() { rz::sparse_build_array(ctx, n_bands, counts, rows, cols, data, out, stats); });
 }
 
 int rz_device_count(void) {

@@ -434,3 +434,71 @@ __global__ void point_expand_kernel(KParams P, const double* __restrict__ x, con
 }
 
 }  // namespace rz
+
+// ---------------------------------------------------------------------------------------------
+// replay: SparseArray::build_array (rust/src/encoding/arrays.rs:103-143)
+// ---------------------------------------------------------------------------------------------
+// Every triplet becomes a record [task | index]; a stable sort on the task bits keeps the triplets of
+// a (band,row,tile) task in their original (burn) order, and one warp replays them through the
+// pixel function on a shared-memory row tile.
+namespace rz {
+
+__global__ void replay_emit_kernel(const unsigned long long* __restrict__ rows, const unsigned long long* __restrict__ cols,
+                                   uint32_t n, const unsigned long long* __restrict__ band_off, uint32_t n_bands,
+                                   uint32_t nrows, uint32_t ncols, uint32_t n_tiles, uint32_t tile_shift,
+                                   uint32_t idx_bits, uint32_t n_tasks, uint64_t* __restrict__ keys) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t band = 0;
+    while (band + 1 < n_bands && (unsigned long long)i >= band_off[band + 1]) band++;
+    const unsigned long long r = rows[i], c = cols[i];
+    // out-of-range triplets (the reference would panic on the index) are parked in a task nobody replays
+    uint64_t task = n_tasks;
+    if (r < nrows && c < ncols) task = ((uint64_t)band * nrows + r) * n_tiles + (uint32_t)(c >> tile_shift);
+    keys[i] = (task << idx_bits) | i;
+}
+
+template <typename N, int FN>
+__global__ void __launch_bounds__(FILL_WARPS * 32)
+replay_fill_kernel(FillParams F, const uint64_t* __restrict__ keys, const uint32_t* __restrict__ task_start,
+                   const unsigned long long* __restrict__ cols, const N* __restrict__ data, uint32_t idx_bits,
+                   uint64_t bg_bits, N* __restrict__ out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
+    N* row = reinterpret_cast<N*>(smem_raw) + (size_t)warp * FILL_MAX_TILE_W;
+    const N bg = value_from_bits<N>(bg_bits);
+    const uint64_t idx_mask = (1ull << idx_bits) - 1ull;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    for (uint32_t task = blockIdx.x * FILL_WARPS + warp; task < F.n_tasks; task += gridDim.x * FILL_WARPS) {
+        const uint32_t tile = task % F.n_tiles;
+        const uint32_t br = task / F.n_tiles;
+        const uint32_t c0 = tile * F.tile_w;
+        const uint32_t w = min(F.tile_w, F.ncols - c0);
+        N* dst = out + (size_t)br * F.ncols + c0;
+        const uint32_t beg = task_start[task], end = task_start[task + 1];
+        for (uint32_t i = lane; i < w; i += 32) row[i] = bg;
+        __syncwarp();
+        for (uint32_t base = beg; base < end; base += 32) {
+            const bool valid = base + lane < end;
+            uint32_t col = 0xffffffffu - lane;  // distinct dummies for idle lanes
+            N v = bg;
+            if (valid) {
+                const uint32_t idx = (uint32_t)(keys[base + lane] & idx_mask);
+                col = (uint32_t)cols[idx] - c0;
+                v = data[idx];
+            }
+            // records hitting the same pixel are applied in record order, one per round
+            const uint32_t peers = __match_any_sync(0xffffffffu, col);
+            const uint32_t rank = __popc(peers & lt_mask);
+            const uint32_t rounds = __reduce_max_sync(0xffffffffu, valid ? rank : 0u);
+            for (uint32_t r = 0; r <= rounds; r++) {
+                if (valid && rank == r) row[col] = apply_px<N, FN>(row[col], v, bg);
+                __syncwarp();
+            }
+        }
+        for (uint32_t i = lane; i < w; i += 32) dst[i] = row[i];
+        __syncwarp();
+    }
+}
+
+}  // namespace rz

@@ -1,0 +1,92 @@
+"""The reference-facing Python surface (`rusterize()` -> `_rusterize()` -> C ABI) on the GPU: cases
+ported from /root/reference/python/test/test_many.py to list-of-WKT / list-of-WKB inputs."""
+import numpy as np
+import pytest
+from PIL import Image
+
+import oracle
+import synth
+from cases import GEOMS, VALUES
+from oracle.wkt2wkb import wkt_to_wkb
+from rusterize_b200 import SparseArray, core, rusterize
+
+pytestmark = pytest.mark.gpu
+GOLDEN = __import__("os").path.join(__import__("os").path.dirname(__file__), "golden")
+
+
+def test_coherence_with_golden_tif():
+    # TestCoherence.test_standard (test_many.py:228-235)
+    r = rusterize(GEOMS, res=(1, 1), dtype="uint8", burn=VALUES, fun="sum", encoding="numpy").squeeze()
+    assert np.array_equal(r, np.array(Image.open(f"{GOLDEN}/standard_output_sum.tif")))
+
+
+def test_input_formats_agree():
+    # TestFormats.test_inputs (test_many.py:167-201), the inputs that exist without geopandas/polars
+    a = rusterize(GEOMS, res=(1, 1), dtype="uint8", fun="sum", encoding="numpy")
+    b = rusterize(np.asarray(GEOMS), res=(1, 1), dtype="uint8", fun="sum", encoding="numpy")
+    wkb = [wkt_to_wkb(s) for s in GEOMS]
+    c = rusterize(wkb, res=(1, 1), dtype="uint8", fun="sum", encoding="numpy")
+    d = rusterize(np.asarray(wkb, dtype=object), res=(1, 1), dtype="uint8", fun="sum", encoding="numpy")
+    assert a.shape == (1, 131, 361)
+    assert np.array_equal(a, b) and np.array_equal(a, c) and np.array_equal(a, d)
+
+
+def test_arguments():
+    # TestArguments (test_many.py:115-163)
+    r = rusterize(GEOMS, res=(1, 1), burn=99, encoding="numpy").squeeze()
+    assert np.nanmax(r) == 99 and np.nanmin(r[r > 0]) == 99 and np.isnan(r[0, 0])
+    r = rusterize(GEOMS, res=(1, 1), burn=1, background=-1, encoding="numpy").squeeze()
+    assert r[0, 0] == -1
+    # background that does not fit the dtype silently becomes 0 (python/src/rusterize.rs:50-53)
+    r = rusterize(GEOMS, res=(1, 1), burn=1, dtype="uint8", encoding="numpy").squeeze()
+    assert r[0, 0] == 0
+    r = rusterize(GEOMS, res=(1, 1), burn=1, dtype="uint8", background=-1, encoding="numpy").squeeze()
+    assert r[0, 0] == 0
+    with pytest.raises(TypeError):
+        rusterize(GEOMS, res=(1, 1), burn=1.5, dtype="uint8", encoding="numpy")
+
+
+def test_outputs_numpy_equals_sparse():
+    # TestFormats.test_outputs (test_many.py:216-224): numpy == sparse.to_numpy
+    r_numpy = rusterize(GEOMS, res=(1, 1), dtype="uint8", burn=VALUES, encoding="numpy")
+    sp = rusterize(GEOMS, res=(1, 1), dtype="uint8", burn=VALUES, encoding="sparse")
+    assert isinstance(sp, SparseArray)
+    assert np.array_equal(r_numpy, sp.to_numpy())
+    assert sp.shape() == (1, 131, 361) and sp.extent() == (-180.5, -70.5, 180.5, 60.5) and sp.resolution() == (1.0, 1.0)
+    assert repr(sp) == ("SparseArray:\n- Shape: (1, 131, 361)\n- Extent: (-180.5, -70.5, 180.5, 60.5)\n"
+                        "- Resolution: (1.0, 1.0)\n- EPSG: None\n- Estimated size: 47.29 KB")
+    sp64 = rusterize(GEOMS, res=(1, 1), burn=VALUES.astype(float), fun="sum", encoding="sparse")
+    assert "378.33 KB" in repr(sp64) and len(sp64.rows) == 29363  # python/docs/python.md:106-136
+
+
+@pytest.mark.parametrize("fun", oracle.FUNS)
+def test_sparse_replay_matches_dense(fun):
+    geoms = synth.mixed_geometries(41, 300, 400, 300, rho=40.0)
+    n = len(geoms)
+    burn = (np.arange(n) % 5).astype(np.float32)
+    burn[::17] = np.nan
+    g = core.Geoms.from_wkb(geoms)
+    ri = core.raster_info(g, shape=(300, 400), extent=(0, 0, 400, 300))
+    band, names = core.group_keys([str(i % 3) for i in range(n)])
+    dense, _ = core.rasterize_dense(g, ri, fun, "float32", burn, None, band, 3, 2.0)
+    sp = core.rasterize_sparse(g, ri, fun, "float32", burn, None, band, 3, 2.0)
+    replay = core.sparse_build_array(ri, fun, 2.0, sp["counts"], sp["rows"], sp["cols"], sp["data"])
+    assert np.array_equal(dense, replay, equal_nan=True)
+    og = oracle.Geoms.from_wkb(geoms)
+    ori = oracle.raster_info(og, shape=(300, 400), extent=(0, 0, 400, 300))
+    assert np.array_equal(oracle.sparse_replay(ori, sp, fun, 2.0), replay, equal_nan=True)
+
+
+def test_replay_duplicate_pixels_in_order():
+    # many writes to few pixels: order-dependent functions must replay strictly in triplet order
+    rng = np.random.default_rng(3)
+    n = 5000
+    rows, cols = rng.integers(0, 3, n).astype(np.uint64), rng.integers(0, 4, n).astype(np.uint64)
+    data = rng.integers(0, 4, n).astype(np.int32)
+    ri = core.raster_info(None, shape=(3, 4), extent=(0, 0, 4, 3))
+    ori = oracle.raster_info(None, shape=(3, 4), extent=(0, 0, 4, 3))
+    counts = np.array([3000, 2000], np.uint64)
+    for fun in oracle.FUNS:
+        got = core.sparse_build_array(ri, fun, 2, counts, rows, cols, data)
+        exp = oracle.sparse_replay(ori, dict(counts=counts, rows=rows, cols=cols, data=data), fun, 2)
+        assert np.array_equal(exp, got), fun
