@@ -1,0 +1,84 @@
+"""Host-side logic of the multi-GPU path on CPU: row-band planning, per-band geometry selection and
+assembly, run as a world-size-2 gloo job.  The compute stand-in is the oracle (this is tests/): the
+CUDA path itself needs a GPU and is covered by test_gpu_parity.py::test_row_band_shards_equal_full_raster."""
+import os
+import subprocess
+import sys
+import textwrap
+
+import numpy as np
+
+import bench
+import oracle
+import synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_band_plan_covers_rows_exactly():
+    for rows in (1, 7, 4096, 65536, 65537):
+        for world in (1, 2, 3, 4, 8):
+            bands = [bench.band_of(r, world, rows) for r in range(world)]
+            assert bands[0][0] == 0 and bands[-1][1] == rows
+            assert all(a[1] == b[0] for a, b in zip(bands, bands[1:]))
+
+
+def test_band_selection_keeps_every_touching_polygon_in_order():
+    w, x, y, off, vals = bench.make_workload("tiny")
+    full = oracle.rasterize_dense(oracle.Geoms.from_rings(x, y, off), oracle.raster_info(
+        None, shape=(w["rows"], w["cols"]), extent=(0, 0, w["cols"], w["rows"])), "sum", "float32", vals,
+        background=np.nan)[0]
+    for r0, r1 in [(0, 100), (100, 612), (612, 1024)]:
+        bx, by, boff, bvals = bench.select_band_polygons(x, y, off, vals, w["rows"], r0, r1)
+        assert len(boff) - 1 < w["n"]
+        ri = oracle.raster_info(None, shape=(r1 - r0, w["cols"]), extent=(0, w["rows"] - r1, w["cols"], w["rows"] - r0))
+        band = oracle.rasterize_dense(oracle.Geoms.from_rings(bx, by, boff), ri, "sum", "float32", bvals,
+                                      background=np.nan)[0]
+        assert np.array_equal(band[0], full[0, r0:r1], equal_nan=True)
+
+
+WORKER = textwrap.dedent("""
+    import os, sys
+    sys.path.insert(0, {root!r}); sys.path.insert(0, os.path.join({root!r}, "tests"))
+    import numpy as np, torch, torch.distributed as dist
+    import bench, oracle
+    dist.init_process_group("gloo")
+    rank, world = dist.get_rank(), dist.get_world_size()
+    w, x, y, off, vals = bench.make_workload("tiny")
+    r0, r1 = bench.band_of(rank, world, w["rows"])
+    bx, by, boff, bvals = bench.select_band_polygons(x, y, off, vals, w["rows"], r0, r1)
+    ri = oracle.raster_info(None, shape=(r1 - r0, w["cols"]), extent=(0, w["rows"] - r1, w["cols"], w["rows"] - r0))
+    band = oracle.rasterize_dense(oracle.Geoms.from_rings(bx, by, boff), ri, "sum", "float32", bvals, background=np.nan)[0]
+    parts = [torch.empty((1, b[1] - b[0], w["cols"])) for b in (bench.band_of(r, world, w["rows"]) for r in range(world))]
+    dist.all_gather(parts, torch.from_numpy(band))
+    if rank == 0:
+        full = oracle.rasterize_dense(oracle.Geoms.from_rings(x, y, off), oracle.raster_info(
+            None, shape=(w["rows"], w["cols"]), extent=(0, 0, w["cols"], w["rows"])), "sum", "float32", vals,
+            background=np.nan)[0]
+        got = torch.cat(parts, 1).numpy()
+        assert np.array_equal(got, full, equal_nan=True)
+        print("SHARDS_OK")
+    dist.destroy_process_group()
+""")
+
+
+def test_world_size_2_gloo(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER.format(root=ROOT))
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29613", str(script)],
+                       capture_output=True, text=True, timeout=300, env=env)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "SHARDS_OK" in r.stdout
+
+
+def test_reference_arm_prints_contract_line():
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "tiny",
+                        "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    import json
+
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["cpu_baseline"]["kind"] == "port" and line["value"] > 0
+    assert line["e2e"]["h2d_bytes_per_step"] == 0
