@@ -285,8 +285,6 @@ static void rasterize_dense(rz_geoms* g, const rz_context* ctx, void* out, rz_st
     const size_t isz = dtype_size(ctx->dtype);
     if (!isz) throw Error{RZ_VALUE_ERROR, "Unsupported dtype"};
     if (ctx->pixel_fn < 0 || ctx->pixel_fn > RZ_ANY) throw Error{RZ_VALUE_ERROR, "Unknown pixel function"};
-    if (ctx->all_touched)
-        throw Error{RZ_RUNTIME_ERROR, "all_touched=True is not implemented on the B200 path yet."};
     if (ri.nrows == 0 || ri.ncols == 0) return;
     if (ri.nrows >= (1ull << 31) || ri.ncols >= (1ull << 31))
         throw Error{RZ_RUNTIME_ERROR, "Raster dimensions above 2^31 are not supported."};
@@ -359,12 +357,15 @@ static void rasterize_dense(rz_geoms* g, const rz_context* ctx, void* out, rz_st
     P.tile_w = tile_w;
     P.tile_shift = tile_shift;
     P.n_tiles = n_tiles;
-    P.col_bits = tile_shift + 1;  // relative columns 0 .. tile_w inclusive
+    P.col_bits = tile_shift + 2;  // relative columns 0 .. tile_w inclusive + the boundary-walk flag bit
     P.part_bits = std::max(1u, bits_for(std::max<uint64_t>(n_parts, 1)));
     P.part_shift = P.col_bits;
     P.task_shift = P.col_bits + P.part_bits;
     P.n_bands = n_bands;
-    P.dedup_lines = ri.xres != ri.yres;
+    const bool touched = ctx->all_touched != 0;
+    // all_touched: every part writes each pixel of its pixel set once (PixelCache for sum/count; for the
+    // other functions repeated writes of the same value are idempotent) - prelude.rs:116-118
+    P.dedup_lines = ri.xres != ri.yres || touched;
     P.n_parts = n_parts;
     S.n_parts = n_parts;
     S.n_poly_vertices = g->pool[0].size();
@@ -422,7 +423,7 @@ static void rasterize_dense(rz_geoms* g, const rz_context* ctx, void* out, rz_st
     const uint32_t nv_poly = (uint32_t)g->pool[0].size(), nv_line = (uint32_t)g->pool[1].size(),
                    nv_pt = (uint32_t)g->pool[2].size();
     const uint32_t per_block = SETUP_THREADS * SETUP_ITEMS;
-    const bool all_poly = nv_line == 0 && nv_pt == 0;
+    const bool all_poly = nv_line == 0 && nv_pt == 0 && !ctx->all_touched;
 
     while (!todo.empty()) {
         Window w = todo.back();
@@ -442,7 +443,13 @@ static void rasterize_dense(rz_geoms* g, const rz_context* ctx, void* out, rz_st
             scan_u32_kernel<<<1, 1024, 0, s>>>(c.block_total.as<uint32_t>(), poly_blocks);
             launches += 2;
         }
-        if (nv_line) {
+        if (touched) {
+            if (nv_poly) touched_walk_kernel<<<(nv_poly + 255) / 256, 256, 0, s>>>(P, dg->x[0], dg->y[0], dg->tag[0], nv_poly,
+                                                                                 d_info, d_ctr, nullptr, 0);
+            if (nv_line) touched_walk_kernel<<<(nv_line + 255) / 256, 256, 0, s>>>(P, dg->x[1], dg->y[1], dg->tag[1], nv_line,
+                                                                                 d_info, d_ctr, nullptr, 0);
+            launches += (nv_poly != 0) + (nv_line != 0);
+        } else if (nv_line) {
             CUDA_TRY(cudaMemsetAsync(c.last_kept.p, 0, (size_t)n_parts * 4, s));
             line_count_kernel<<<(nv_line + per_block - 1) / per_block, SETUP_THREADS, 0, s>>>(
                 P, dg->x[1], dg->y[1], dg->tag[1], nv_line, d_info, c.last_kept.as<uint32_t>(), d_ctr);
@@ -495,7 +502,13 @@ static void rasterize_dense(rz_geoms* g, const rz_context* ctx, void* out, rz_st
             // line / point records go behind the polygon records
             c.h_counters->cursor = c.h_counters->poly_records;
             CUDA_TRY(cudaMemcpyAsync(&d_ctr->cursor, &c.h_counters->cursor, 8, cudaMemcpyHostToDevice, s));
-            if (nv_line) {
+            if (touched) {
+                if (nv_poly) touched_walk_kernel<<<(nv_poly + 255) / 256, 256, 0, s>>>(P, dg->x[0], dg->y[0], dg->tag[0],
+                                                                                     nv_poly, d_info, d_ctr, ka, 1);
+                if (nv_line) touched_walk_kernel<<<(nv_line + 255) / 256, 256, 0, s>>>(P, dg->x[1], dg->y[1], dg->tag[1],
+                                                                                     nv_line, d_info, d_ctr, ka, 1);
+                launches += (nv_poly != 0) + (nv_line != 0);
+            } else if (nv_line) {
                 line_emit_kernel<<<(nv_line + per_block - 1) / per_block, SETUP_THREADS, 0, s>>>(
                     P, dg->x[1], dg->y[1], dg->tag[1], nv_line, d_info, d_ctr, ka);
                 line_final_kernel<<<(n_parts + 255) / 256, 256, 0, s>>>(P, dg->x[1], dg->y[1], dg->tag[1],
@@ -557,7 +570,8 @@ static void rasterize_dense(rz_geoms* g, const rz_context* ctx, void* out, rz_st
         F.part_shift = P.part_shift;
         F.part_bits = P.part_bits;
         F.dedup_lines = P.dedup_lines;
-        F.all_poly = all_poly;
+        F.all_poly = nv_line == 0 && nv_pt == 0;
+        F.all_touched = touched;
         void* d_out;
         if (out_dev) {
             d_out = out;

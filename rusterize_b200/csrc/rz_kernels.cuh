@@ -556,6 +556,111 @@ __global__ void point_kernel(KParams P, const double* __restrict__ x, const doub
 }
 
 // ---------------------------------------------------------------------------------------------
+// all_touched line walk — rust/src/rasterization/burners.rs:94-247 (GDAL-derived)
+// ---------------------------------------------------------------------------------------------
+// A data-dependent f64 walk per segment; one thread walks one segment and calls f(row, col) for every
+// in-raster pixel, in the reference's order.  Used for line parts and, with all_touched, for every
+// polygon ring (burn_geometry.rs:89-106, 225-238).
+template <typename F>
+__device__ __forceinline__ void all_touched_walk(const KParams& P, double x, double y, double xe, double ye, F f) {
+    const double EPS_INTERSECT = 1e-4, TOL = 1e-9;
+    const long long nrows = P.nrows, ncols = P.ncols;
+    if (x > xe) { double t = x; x = xe; xe = t; t = y; y = ye; ye = t; }
+    if (fabs(__dsub_rn(x, xe)) < 0.01) {  // vertical
+        if (ye < y) { double t = y; y = ye; ye = t; }
+        long long ix = sat_i64(floor(xe)), iy = sat_i64(floor(y));
+        long long iy_end = sat_i64(floor(__dsub_rn(ye, EPS_INTERSECT)));
+        if (ix < 0 || ix >= ncols) return;
+        iy = max(iy, 0LL);
+        iy_end = min(iy_end, nrows - 1);
+        for (long long r = iy; r <= iy_end; r++) f((uint32_t)r, (uint32_t)ix);
+        return;
+    }
+    if (fabs(__dsub_rn(y, ye)) < 0.01) {  // horizontal
+        if (xe < x) { double t = x; x = xe; xe = t; }
+        long long ix = sat_i64(floor(x)), iy = sat_i64(floor(y));
+        long long ix_end = sat_i64(floor(__dsub_rn(xe, EPS_INTERSECT)));
+        if (iy < 0 || iy >= nrows) return;
+        ix = max(ix, 0LL);
+        ix_end = min(ix_end, ncols - 1);
+        for (long long c = ix; c <= ix_end; c++) f((uint32_t)iy, (uint32_t)c);
+        return;
+    }
+    const double slope = __ddiv_rn(__dsub_rn(ye, y), __dsub_rn(xe, x));
+    const double inv_slope = __ddiv_rn(1.0, slope);
+    if (x < 0.0) { y = __dadd_rn(y, __dmul_rn(__dsub_rn(0.0, x), slope)); x = 0.0; }
+    if (xe > P.ncols_f) { ye = __dadd_rn(ye, __dmul_rn(__dsub_rn(P.ncols_f, xe), slope)); xe = P.ncols_f; }
+    if (y < 0.0) { x = __dadd_rn(x, __dmul_rn(__dsub_rn(0.0, y), inv_slope)); y = 0.0; }
+    else if (y > P.nrows_f) { x = __dadd_rn(x, __dmul_rn(__dsub_rn(P.nrows_f, y), inv_slope)); y = P.nrows_f; }
+    if (ye < 0.0) xe = __dadd_rn(xe, __dmul_rn(__dsub_rn(0.0, ye), inv_slope));
+    else if (ye > P.nrows_f) xe = __dadd_rn(xe, __dmul_rn(__dsub_rn(P.nrows_f, ye), inv_slope));
+    // f64::clamp keeps NaN
+    x = x < 0.0 ? 0.0 : (x > P.ncols_f ? P.ncols_f : x);
+    xe = xe < 0.0 ? 0.0 : (xe > P.ncols_f ? P.ncols_f : xe);
+    // every iteration advances x by at least TOL/|slope| > 0; the bound only guards against NaN/denormal stalls
+    for (uint32_t guard = 0; x >= 0.0 && x < xe && guard < 0x7fffffffu; guard++) {
+        const long long ix = sat_i64(floor(x)), iy = sat_i64(floor(y));
+        if (ix >= 0 && ix < ncols && iy >= 0 && iy < nrows) f((uint32_t)iy, (uint32_t)ix);
+        double sx = __dsub_rn(floor(__dadd_rn(x, 1.0)), x);
+        double sy = __dmul_rn(sx, slope);
+        if (sat_i64(floor(__dadd_rn(y, sy))) == iy) {
+            x = __dadd_rn(x, sx);
+            y = __dadd_rn(y, sy);
+        } else if (slope < 0.0) {
+            sy = __dsub_rn((double)iy, y);
+            if (sy > -TOL) sy = -TOL;
+            sx = __ddiv_rn(sy, slope);
+            x = __dadd_rn(x, sx);
+            y = __dadd_rn(y, sy);
+        } else {
+            sy = __dsub_rn((double)(iy + 1), y);
+            if (sy < TOL) sy = TOL;
+            sx = __ddiv_rn(sy, slope);
+            x = __dadd_rn(x, sx);
+            y = __dadd_rn(y, sy);
+        }
+    }
+}
+
+// One thread per vertex of a ring / line-string pool.  mode 0 counts the in-window pixels, mode 1
+// emits one record per pixel (flagged as "pixel of the part's boundary walk").
+__global__ void __launch_bounds__(256)
+touched_walk_kernel(KParams P, const double* __restrict__ x, const double* __restrict__ y,
+                    const uint32_t* __restrict__ tag, uint32_t n, const PartInfo* __restrict__ info,
+                    Counters* __restrict__ ctr, uint64_t* __restrict__ keys, int mode) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long cnt = 0;
+    if (i < n && !(tag[i] & 0x80000000u)) {
+        const uint32_t part = tag[i] & 0x3fffffffu;
+        const PartInfo pi = info[part];
+        const double x0 = px_x(P, x[i]), y0 = px_y(P, y[i]), x1 = px_x(P, x[i + 1]), y1 = px_y(P, y[i + 1]);
+        const double min_x = fmin(x0, x1), max_x = fmax(x0, x1), min_y = fmin(y0, y1), max_y = fmax(y0, y1);
+        if (pi.band >= 0 && min_x < P.ncols_f && max_x >= 0.0 && min_y < P.nrows_f && max_y >= 0.0) {  // edges.rs:130
+            const uint64_t flag = 1ull << (P.col_bits - 1);
+            all_touched_walk(P, x0, y0, x1, y1, [&](uint32_t row, uint32_t col) {
+                if (row < P.win_r0 || row >= P.win_r1) return;
+                if (mode == 0) {
+                    cnt++;
+                    return;
+                }
+                // warp-aggregated append
+                const uint32_t active = __activemask();
+                const int leader = __ffs(active) - 1;
+                unsigned long long base = 0;
+                if ((int)lane_id() == leader) base = atomicAdd(&ctr->cursor, (unsigned long long)__popc(active));
+                base = __shfl_sync(active, base, leader);
+                keys[base + __popc(active & ((1u << lane_id()) - 1u))] = pixel_key(P, pi.band, part, row, col) | flag;
+            });
+        }
+    }
+    if (mode == 0) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) cnt += __shfl_down_sync(0xffffffffu, cnt, o);
+        if (lane_id() == 0 && cnt) atomicAdd(&ctr->records, cnt);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // LSD radix sort, 8-bit digits, 64-bit keys (keys only)
 // ---------------------------------------------------------------------------------------------
 constexpr int RS_THREADS = 256;
@@ -766,6 +871,7 @@ struct FillParams {
     uint32_t dedup_lines;
     uint32_t vec_ok;           // rows of `out` are 16-byte aligned
     uint32_t all_poly;         // no line / point parts: skip the kind lookup
+    uint32_t all_touched;      // polygon runs also carry boundary-walk pixels (flagged records)
 };
 
 constexpr int FILL_WARPS = 4;
@@ -774,9 +880,13 @@ constexpr uint32_t FILL_MAX_TILE_W = 1024;  // 32 lanes x 32 toggle bits
 // Rare path: a polygon run with an odd number of crossings.  burners.rs:305 pairs the sorted
 // crossings with chunks_exact(2), i.e. the largest column is ignored: cancel one toggle there.
 __device__ __noinline__ void drop_last_crossing(uint32_t* tog, const uint64_t* __restrict__ keys, uint32_t beg,
-                                                uint32_t end, uint32_t col_mask, uint32_t w, uint32_t lane) {
+                                                uint32_t end, uint32_t col_mask, uint32_t flag_bit, uint32_t w,
+                                                uint32_t lane) {
     uint32_t mx = 0;
-    for (uint32_t i = beg + lane; i < end; i += 32) mx = max(mx, (uint32_t)keys[i] & col_mask);
+    for (uint32_t i = beg + lane; i < end; i += 32) {
+        const uint32_t k = (uint32_t)keys[i];
+        if (!(k & flag_bit)) mx = max(mx, k & col_mask);
+    }
     mx = __reduce_max_sync(0xffffffffu, mx);
     if (mx < w && lane == (mx >> 5)) tog[lane] ^= 1u << (mx & 31);
     __syncwarp();
@@ -802,9 +912,12 @@ __device__ __forceinline__ void apply_mask(N* __restrict__ row_lane, uint32_t m,
 // Bits at or beyond the tile's width may end up set; they only touch shared-memory pixels that are
 // never flushed.
 template <typename N, int FN>
-__device__ __forceinline__ void finish_poly_run(uint32_t* tog, N* row_lane, uint32_t lane, uint32_t lt_mask, N v, N bg) {
+__device__ __forceinline__ void finish_poly_run(uint32_t* tog, uint32_t* orm, N* row_lane, uint32_t lane,
+                                                uint32_t lt_mask, N v, N bg) {
     const uint32_t t = tog[lane];
     tog[lane] = 0;
+    const uint32_t walked = orm[lane];  // all_touched: pixels of the ring walk (burn_geometry.rs:225-238)
+    orm[lane] = 0;
     uint32_t m = t;
     m ^= m << 1;
     m ^= m << 2;
@@ -813,6 +926,7 @@ __device__ __forceinline__ void finish_poly_run(uint32_t* tog, N* row_lane, uint
     m ^= m << 16;
     const uint32_t odd_words = __ballot_sync(0xffffffffu, __popc(t) & 1);
     if (__popc(odd_words & lt_mask) & 1) m = ~m;
+    m |= walked;
     apply_mask<N, FN>(row_lane, m, lane, v, bg);
     __syncwarp();
 }
@@ -823,13 +937,16 @@ fill_kernel(FillParams F, const uint64_t* __restrict__ keys, const uint32_t* __r
             const PartInfo* __restrict__ info, const uint8_t* __restrict__ part_kind, uint64_t bg_bits,
             N* __restrict__ out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ uint32_t s_tog[FILL_WARPS][32];
+    __shared__ uint32_t s_tog[FILL_WARPS][32], s_orm[FILL_WARPS][32];
     const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
     N* row = reinterpret_cast<N*>(smem_raw) + (size_t)warp * FILL_MAX_TILE_W;
     N* row_lane = row + lane;
     uint32_t* tog = s_tog[warp];
+    uint32_t* orm = s_orm[warp];
+    orm[lane] = 0;
     const N bg = value_from_bits<N>(bg_bits);
-    const uint32_t col_mask = (1u << F.col_bits) - 1u;
+    const uint32_t col_mask = (1u << (F.col_bits - 1)) - 1u;  // the top bit of the column field is the walk flag
+    const uint32_t flag_bit = 1u << (F.col_bits - 1);
     const uint64_t part_mask = (1ull << F.part_bits) - 1ull;
     const uint32_t lt_mask = (1u << lane) - 1u;
     tog[lane] = 0;
@@ -864,13 +981,14 @@ fill_kernel(FillParams F, const uint64_t* __restrict__ keys, const uint32_t* __r
             const uint32_t heads = __ballot_sync(0xffffffffu, valid && hi != prev_hi);
             const uint32_t part = (uint32_t)(hi & part_mask);
             const uint32_t col = (uint32_t)key & col_mask;
+            const bool walk_px = ((uint32_t)key & flag_bit) != 0;
             const N my_v = valid ? value_from_bits<N>(info[part].value_bits) : bg;
             const bool last_chunk = base + 32 >= end;
 
             if ((heads & 1u) && open_kind != 3) {  // the open run ended exactly at the chunk boundary
                 if (open_kind == 0) {
-                    if (run_cnt & 1u) drop_last_crossing(tog, keys, run_beg, base, col_mask, w, lane);
-                    finish_poly_run<N, FN>(tog, row_lane, lane, lt_mask, open_v, bg);
+                    if (run_cnt & 1u) drop_last_crossing(tog, keys, run_beg, base, col_mask, flag_bit, w, lane);
+                    finish_poly_run<N, FN>(tog, orm, row_lane, lane, lt_mask, open_v, bg);
                 } else if (open_kind == 1) {
                     tog[lane] = 0;
                     __syncwarp();
@@ -890,12 +1008,20 @@ fill_kernel(FillParams F, const uint64_t* __restrict__ keys, const uint32_t* __r
                 if (!ALL_POLY) kind = part_kind[__shfl_sync(0xffffffffu, part, start)];
                 if ((heads >> start) & 1u) run_beg = base + start;
                 if (kind == 0) {
-                    if (in_run && col < w) atomicXor(&tog[col >> 5], 1u << (col & 31));
-                    run_cnt += stop - start;
+                    if (F.all_touched) {
+                        if (in_run && col < w) {
+                            if (walk_px) atomicOr(&orm[col >> 5], 1u << (col & 31));
+                            else atomicXor(&tog[col >> 5], 1u << (col & 31));
+                        }
+                        run_cnt += __popc(__ballot_sync(0xffffffffu, in_run && !walk_px));
+                    } else {
+                        if (in_run && col < w) atomicXor(&tog[col >> 5], 1u << (col & 31));
+                        run_cnt += stop - start;
+                    }
                     __syncwarp();
                     if (run_ends) {
-                        if (run_cnt & 1u) drop_last_crossing(tog, keys, run_beg, base + stop, col_mask, w, lane);
-                        finish_poly_run<N, FN>(tog, row_lane, lane, lt_mask, v, bg);
+                        if (run_cnt & 1u) drop_last_crossing(tog, keys, run_beg, base + stop, col_mask, flag_bit, w, lane);
+                        finish_poly_run<N, FN>(tog, orm, row_lane, lane, lt_mask, v, bg);
                         run_cnt = 0;
                     }
                 } else {

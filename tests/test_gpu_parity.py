@@ -14,10 +14,11 @@ pytestmark = pytest.mark.gpu
 GOLDEN = __import__("os").path.join(__import__("os").path.dirname(__file__), "golden")
 
 
-def both(geoms, fun="last", dtype="float64", burn=1, bg=0, by=None, field_valid=None, rows=None, tile_bytes=0, **kw):
+def both(geoms, fun="last", dtype="float64", burn=1, bg=0, by=None, field_valid=None, rows=None, tile_bytes=0,
+         all_touched=False, **kw):
     og = oracle.Geoms.from_any(geoms)
     ori = oracle.raster_info(og, **kw)
-    exp, names = oracle.rasterize_dense(og, ori, fun, dtype, burn, field_valid, by, bg)
+    exp, names = oracle.rasterize_dense(og, ori, fun, dtype, burn, field_valid, by, bg, all_touched)
     g = core.Geoms.from_any(geoms)
     ri = core.raster_info(g, **kw)
     band, nb = None, 1
@@ -25,7 +26,8 @@ def both(geoms, fun="last", dtype="float64", burn=1, bg=0, by=None, field_valid=
         band, bn = core.group_keys(by)
         nb = len(bn)
         assert bn == names
-    got, st = core.rasterize_dense(g, ri, fun, dtype, burn, field_valid, band, nb, bg, rows=rows, tile_bytes=tile_bytes)
+    got, st = core.rasterize_dense(g, ri, fun, dtype, burn, field_valid, band, nb, bg, all_touched, rows=rows,
+                                   tile_bytes=tile_bytes)
     if rows is not None:
         exp = exp[:, rows[0]:rows[1]]
     return exp, got, st
@@ -176,3 +178,41 @@ def test_errors_through_the_abi():
         core.rasterize_dense(g, ri, field=np.array([1.0, 2.0]))
     with pytest.raises(ValueError, match="Geometry and by lengths must match"):
         core.rasterize_dense(g, ri, band_of_geom=np.array([0, 1], np.int32), n_bands=2)
+
+
+# ---- all_touched: GDAL-style line walk + 2-pass polygons, burners.rs:94-247 ----------
+@pytest.mark.parametrize("fun", oracle.FUNS)
+@pytest.mark.parametrize("dtype,bg", [("float64", np.nan), ("uint8", 0), ("int32", 2)])
+def test_all_touched_mixed_geometries(fun, dtype, bg):
+    seed = 500 + oracle.FUNS.index(fun)
+    geoms = synth.mixed_geometries(seed, 120, 300, 200, rho=20.0)
+    burn = (np.arange(len(geoms)) % 5).astype(dtype)
+    exp, got, _ = both(geoms, fun, dtype, burn, bg, all_touched=True, shape=(200, 300), extent=(0, 0, 300, 200))
+    assert_same(exp, got)
+
+
+def test_all_touched_reference_cases():
+    # test_many.py:237-262 geometry at res 0.5, and the custom-shape / extent variants (:283-325, :348-372)
+    for kw in [dict(resolution=(0.5, 0.5)), dict(shape=(47, 319)), dict(resolution=(1, 1), extent=(-349, -507, 1, 0)),
+               dict(shape=(47, 319), extent=(-349, -507, 1, 0))]:
+        exp, got, _ = both(GEOMS_EXPLODED, "sum", "uint8", VALUES_EXPLODED, 0, all_touched=True, **kw)
+        assert_same(exp, got)
+    # R test-geometry.R:25-30: all_touched burns a superset of the standard cells
+    kw = dict(shape=(4, 4), extent=(0, 0, 4, 4))
+    _, on, _ = both(["LINESTRING (0 0, 4 4)"], burn=9.0, all_touched=True, **kw)
+    _, off, _ = both(["LINESTRING (0 0, 4 4)"], burn=9.0, **kw)
+    assert (on > 0).sum() > (off > 0).sum() and ((off > 0) <= (on > 0)).all()
+
+
+def test_all_touched_shards_tiles_and_edges():
+    from oracle.wkt2wkb import wkt_to_wkb
+
+    geoms = synth.mixed_geometries(77, 200, 1500, 150, rho=70.0) + [wkt_to_wkb(s) for s in (
+        "LINESTRING (-500 50, 2500 50)", "LINESTRING (750 -1e5, 750.001 1e5)", "LINESTRING (-30 -30, 1600 170)",
+        sq(-50, -50, 5000, 5000))]
+    burn = np.arange(len(geoms)) % 7
+    for fun in ("sum", "last"):
+        for rows in [None, (0, 60), (60, 150)]:
+            exp, got, _ = both(geoms, fun, "int32", burn, 0, all_touched=True, rows=rows, tile_bytes=1024,
+                               shape=(150, 1500), extent=(0, 0, 1500, 150))
+            assert_same(exp, got)

@@ -101,3 +101,9 @@ def test_small_parcels_like_config5():
 def test_unsupported_sparse_line_dedup_is_loud():
     with pytest.raises(RuntimeError, match="non-square pixels"):
         both(["LINESTRING (0 0, 4 4)"], shape=(3, 7), extent=(0, 0, 4, 4))
+
+
+def test_sparse_all_touched_is_loud():
+    with pytest.raises(RuntimeError, match="all_touched"):
+        g = core.Geoms.from_wkt(["LINESTRING (0 0, 4 4)"])
+        core.rasterize_sparse(g, core.raster_info(g, shape=(4, 4)), all_touched=True)
