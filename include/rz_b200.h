@@ -149,6 +149,8 @@ typedef struct rz_context {
 #define RZ_FLAG_OUT_ON_DEVICE 1u   /* `out` is device memory (no D2H) */
 #define RZ_FLAG_FORCE_H2D 2u       /* re-upload geometry even if a device copy is cached */
 #define RZ_FLAG_SYNC_STAGES 4u     /* record per-stage CUDA-event timings into rz_stats */
+#define RZ_FLAG_NO_TILE_ENGINE 8u      /* always use the crossing-record pipeline */
+#define RZ_FLAG_FORCE_TILE_ENGINE 16u  /* use the tile-binned engine whenever the job is polygon-only */
 
 typedef struct rz_stats {
     uint64_t n_parts, n_poly_vertices, n_line_vertices, n_points;
@@ -160,7 +162,7 @@ typedef struct rz_stats {
     uint64_t h2d_bytes, d2h_bytes;
     uint64_t out_bytes;        /* B * rows * C * sizeof(dtype) */
     uint32_t kernel_launches;
-    uint32_t _pad;
+    uint32_t engine;           /* 0 = crossing records + sort + row-tile fill, 1 = tile-binned polygon engine */
 } rz_stats;
 
 /* DenseArray::build (rust/src/rasterize.rs:71-116): out is [n_bands][rows][ncols] of ctx->dtype,

@@ -15,6 +15,7 @@ FUNS = ["sum", "first", "last", "min", "max", "count", "any"]
 
 RZ_OK, RZ_VALUE_ERROR, RZ_RUNTIME_ERROR = 0, 1, 2
 FLAG_OUT_ON_DEVICE, FLAG_FORCE_H2D, FLAG_SYNC_STAGES = 1, 2, 4
+FLAG_NO_TILE_ENGINE, FLAG_FORCE_TILE_ENGINE = 8, 16
 
 
 class RasterInfo(C.Structure):
@@ -70,7 +71,7 @@ class Stats(C.Structure):
         ("h2d_ms", C.c_float), ("count_ms", C.c_float), ("emit_ms", C.c_float), ("sort_ms", C.c_float),
         ("index_ms", C.c_float), ("fill_ms", C.c_float), ("d2h_ms", C.c_float), ("total_ms", C.c_float),
         ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("out_bytes", C.c_uint64),
-        ("kernel_launches", C.c_uint32), ("_pad", C.c_uint32),
+        ("kernel_launches", C.c_uint32), ("engine", C.c_uint32),
     ]
 
     def as_dict(self):

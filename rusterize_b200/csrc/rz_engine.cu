@@ -15,6 +15,7 @@
 #include "rz_host.hpp"
 #include "rz_kernels.cuh"
 #include "rz_sparse.cuh"
+#include "rz_tiles.cuh"
 
 namespace rz {
 
@@ -77,6 +78,8 @@ struct DeviceGeoms {
     uint32_t* part_geom = nullptr;
     double* part_xlo = nullptr;
     double* part_xhi = nullptr;
+    double* part_ylo = nullptr;
+    double* part_yhi = nullptr;
     uint32_t* part_vbeg = nullptr;
     uint32_t* part_vend = nullptr;
     size_t bytes = 0;
@@ -91,6 +94,8 @@ struct DeviceGeoms {
         cudaFree(part_geom);
         cudaFree(part_xlo);
         cudaFree(part_xhi);
+        cudaFree(part_ylo);
+        cudaFree(part_yhi);
         cudaFree(part_vbeg);
         cudaFree(part_vend);
         (void)cudaGetLastError();
@@ -103,7 +108,7 @@ struct DeviceCtx {
     cudaStream_t stream = nullptr;
     int sm_count = 148;
     DevBuf keys_a, keys_b, hist, digit_total, task_start, part_info, field, valid, band, last_kept, counters, win_out,
-        block_total, sp_a, sp_b, sp_c, sp_d, sp_e, sp_f, sp_g, sp_rows, sp_cols, sp_data, sp_partial;
+        block_total, tile_cnt, tile_off, tile_ctr, sp_a, sp_b, sp_c, sp_d, sp_e, sp_f, sp_g, sp_rows, sp_cols, sp_data, sp_partial;
     Counters* h_counters = nullptr;  // pinned
     cudaEvent_t ev[16];
 };
@@ -198,6 +203,8 @@ static DeviceGeoms* geoms_on_device(rz_geoms* g, DeviceCtx& c, cudaStream_t s, b
     upload_vec(&d->part_geom, pg, s, bytes);
     upload_vec(&d->part_xlo, g->part_xlo, s, bytes);
     upload_vec(&d->part_xhi, g->part_xhi, s, bytes);
+    upload_vec(&d->part_ylo, g->part_ylo, s, bytes);
+    upload_vec(&d->part_yhi, g->part_yhi, s, bytes);
     upload_vec(&d->part_vbeg, g->part_vbeg, s, bytes);
     upload_vec(&d->part_vend, g->part_vend, s, bytes);
     CUDA_TRY(cudaStreamSynchronize(s));  // `pg` is a temporary
@@ -248,6 +255,82 @@ static FillLaunch fill_for(int dtype, int fn) {
         case RZ_I64: return fill_for_fn<int64_t>(fn);
         case RZ_F32: return fill_for_fn<float>(fn);
         case RZ_F64: return fill_for_fn<double>(fn);
+    }
+    return nullptr;
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// device-wide scan helper (kernels in rz_sparse.cuh)
+// ------------------------------------------------------------------------------------------------
+template <typename Op, typename In, typename Out>
+static void device_scan(In in, uint32_t n, Out out, DevBuf& partial, cudaStream_t s, uint32_t& launches) {
+    const uint32_t nb = (n + SC_TILE - 1) / SC_TILE;
+    partial.ensure(((size_t)nb + 2) * 8);
+    unsigned long long* p = partial.as<unsigned long long>();
+    if (nb == 0) {
+        CUDA_TRY(cudaMemsetAsync(p, 0, 8, s));
+        return;
+    }
+    scan_reduce_kernel<Op, In><<<nb, SC_THREADS, 0, s>>>(in, n, p);
+    scan_partials_kernel<Op><<<1, 1024, 0, s>>>(p, nb);
+    scan_apply_kernel<Op, In, Out><<<nb, SC_THREADS, 0, s>>>(in, n, p, out);
+    launches += 3;
+}
+
+static unsigned long long scan_total(DevBuf& partial, uint32_t n, cudaStream_t s) {
+    const uint32_t nb = (n + SC_TILE - 1) / SC_TILE;
+    unsigned long long t = 0;
+    CUDA_TRY(cudaMemcpyAsync(&t, partial.as<unsigned long long>() + nb, 8, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    return t;
+}
+
+// ------------------------------------------------------------------------------------------------
+// tile-binned engine dispatch
+// ------------------------------------------------------------------------------------------------
+typedef void (*TileLaunch)(uint32_t, cudaStream_t, KParams, TileParams, const uint64_t*, const uint32_t*,
+                           const PartInfo*, const uint32_t*, const uint32_t*, const double*, const double*,
+                           const uint32_t*, uint64_t, void*);
+
+template <typename N, int FN>
+static void tile_launch(uint32_t grid, cudaStream_t s, KParams P, TileParams T, const uint64_t* recs,
+                        const uint32_t* tile_start, const PartInfo* info, const uint32_t* vbeg, const uint32_t* vend,
+                        const double* x, const double* y, const uint32_t* tag, uint64_t bg, void* out) {
+    constexpr int TR = sizeof(N) <= 4 ? 128 : 64;
+    const size_t smem = (size_t)TR * TILE_C * sizeof(N);
+    static bool configured = false;  // per instantiation
+    if (!configured) {
+        CUDA_TRY(cudaFuncSetAttribute(tile_fill_kernel<N, FN, TR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    tile_fill_kernel<N, FN, TR><<<grid, TILE_THREADS, smem, s>>>(P, T, recs, tile_start, info, vbeg, vend, x, y, tag, bg,
+                                                               (N*)out);
+}
+template <typename N> static TileLaunch tile_for_fn(int fn) {
+    switch (fn) {
+        case RZ_SUM: return tile_launch<N, RZ_SUM>;
+        case RZ_FIRST: return tile_launch<N, RZ_FIRST>;
+        case RZ_LAST: return tile_launch<N, RZ_LAST>;
+        case RZ_MIN: return tile_launch<N, RZ_MIN>;
+        case RZ_MAX: return tile_launch<N, RZ_MAX>;
+        case RZ_COUNT: return tile_launch<N, RZ_COUNT>;
+        case RZ_ANY: return tile_launch<N, RZ_ANY>;
+    }
+    return nullptr;
+}
+static TileLaunch tile_for(int dtype, int fn) {
+    switch (dtype) {
+        case RZ_U8: return tile_for_fn<uint8_t>(fn);
+        case RZ_U16: return tile_for_fn<uint16_t>(fn);
+        case RZ_U32: return tile_for_fn<uint32_t>(fn);
+        case RZ_U64: return tile_for_fn<uint64_t>(fn);
+        case RZ_I8: return tile_for_fn<int8_t>(fn);
+        case RZ_I16: return tile_for_fn<int16_t>(fn);
+        case RZ_I32: return tile_for_fn<int32_t>(fn);
+        case RZ_I64: return tile_for_fn<int64_t>(fn);
+        case RZ_F32: return tile_for_fn<float>(fn);
+        case RZ_F64: return tile_for_fn<double>(fn);
     }
     return nullptr;
 }
@@ -431,6 +514,115 @@ static void rasterize_dense(rz_geoms* g, const rz_context* ctx, void* out, rz_st
         P.win_r0 = w.r0;
         P.win_r1 = w.r1;
         const uint32_t rows = w.r1 - w.r0;
+
+        // ---- tile-binned engine (polygon-only jobs made of small parts) ------------------------
+        if (nv_line == 0 && nv_pt == 0 && !touched && n_parts && !(ctx->flags & RZ_FLAG_NO_TILE_ENGINE)) {
+            TileParams T;
+            std::memset(&T, 0, sizeof T);
+            T.tile_r = isz <= 4 ? 128u : 64u;
+            T.n_tc = (uint32_t)((ri.ncols + TILE_C - 1) / TILE_C);
+            T.n_tr = (rows + T.tile_r - 1) / T.tile_r;
+            const uint64_t n_tiles64 = (uint64_t)n_bands * T.n_tr * T.n_tc;
+            T.part_bits = P.part_bits;
+            if (n_tiles64 < (1ull << 31) && bits_for(n_tiles64) + T.part_bits <= 64) {
+                T.n_tiles = (uint32_t)n_tiles64;
+                if (timed) CUDA_TRY(cudaEventRecord(c.ev[EV_A], s));
+                c.tile_cnt.ensure((size_t)n_parts * 4);
+                c.tile_off.ensure((size_t)n_parts * 8);
+                c.tile_ctr.ensure(sizeof(TileCounters));
+                TileCounters* d_tc = c.tile_ctr.as<TileCounters>();
+                CUDA_TRY(cudaMemsetAsync(d_tc, 0, sizeof(TileCounters), s));
+                tile_bin_kernel<<<(n_parts + 255) / 256, 256, 0, s>>>(P, T, d_info, dg->part_xlo, dg->part_xhi, dg->part_ylo,
+                                                                      dg->part_yhi, dg->part_vbeg, dg->part_vend,
+                                                                      c.tile_cnt.as<uint32_t>(), nullptr, nullptr, d_tc, 0);
+                launches++;
+                TileCounters h_tc;
+                CUDA_TRY(cudaMemcpyAsync(&h_tc, d_tc, sizeof h_tc, cudaMemcpyDeviceToHost, s));
+                CUDA_TRY(cudaStreamSynchronize(s));
+                // cost model: the tile engine touches every ring vertex of a part once per overlapped tile
+                const bool wanted = (ctx->flags & RZ_FLAG_FORCE_TILE_ENGINE) ||
+                                    h_tc.edge_visits <= 6ull * nv_poly + (1ull << 20);
+                if (wanted && h_tc.pairs < (1ull << 31)) {
+                    const uint32_t n_rec = (uint32_t)h_tc.pairs;
+                    device_scan<OpAdd>(InU32{c.tile_cnt.as<uint32_t>()}, n_parts,
+                                       OutPrefix64{c.tile_off.as<unsigned long long>()}, c.sp_partial, s, launches);
+                    c.keys_a.ensure(std::max<size_t>((size_t)n_rec * 8, 64));
+                    c.keys_b.ensure(std::max<size_t>((size_t)n_rec * 8, 64));
+                    uint64_t* ka = c.keys_a.as<uint64_t>();
+                    uint64_t* kb = c.keys_b.as<uint64_t>();
+                    tile_bin_kernel<<<(n_parts + 255) / 256, 256, 0, s>>>(
+                        P, T, d_info, dg->part_xlo, dg->part_xhi, dg->part_ylo, dg->part_yhi, dg->part_vbeg, dg->part_vend,
+                        nullptr, c.tile_off.as<unsigned long long>(), ka, d_tc, 1);
+                    launches++;
+                    if (timed) CUDA_TRY(cudaEventRecord(c.ev[EV_B], s));
+                    lap(emit_ms, EV_A, EV_B);
+                    if (timed) CUDA_TRY(cudaEventRecord(c.ev[EV_A], s));
+                    const uint32_t tkey_bits = T.part_bits + bits_for(n_tiles64);
+                    if (n_rec > 1) {  // records are in part order: a stable sort on the tile bits keeps burn order
+                        const uint32_t n_blocks = (n_rec + RS_TILE - 1) / RS_TILE;
+                        c.hist.ensure((size_t)n_blocks * RS_RADIX * 4);
+                        c.digit_total.ensure(RS_RADIX * 4);
+                        for (uint32_t shift = T.part_bits; shift < tkey_bits; shift += 8) {
+                            radix_hist_kernel<<<n_blocks, RS_THREADS, 0, s>>>(ka, n_rec, shift, n_blocks,
+                                                                              c.hist.as<uint32_t>());
+                            radix_scan_rows_kernel<<<RS_RADIX, 1024, 0, s>>>(c.hist.as<uint32_t>(), n_blocks,
+                                                                            c.digit_total.as<uint32_t>());
+                            radix_scatter_kernel<<<n_blocks, RS_THREADS, 0, s>>>(ka, kb, n_rec, shift, n_blocks,
+                                                                                 c.hist.as<uint32_t>(),
+                                                                                 c.digit_total.as<uint32_t>());
+                            std::swap(ka, kb);
+                            launches += 3;
+                            S.sort_passes++;
+                        }
+                    }
+                    c.task_start.ensure(((size_t)T.n_tiles + 1) * 4);
+                    task_index_kernel<<<(T.n_tiles + 1 + 255) / 256, 256, 0, s>>>(ka, n_rec, T.part_bits, T.n_tiles,
+                                                                                c.task_start.as<uint32_t>());
+                    launches++;
+                    if (timed) CUDA_TRY(cudaEventRecord(c.ev[EV_B], s));
+                    lap(sort_ms, EV_A, EV_B);
+                    if (timed) CUDA_TRY(cudaEventRecord(c.ev[EV_A], s));
+                    void* d_out;
+                    if (out_dev) {
+                        d_out = out;
+                        T.out_rows = shard_rows;
+                        T.win_row_off = w.r0 - shard_r0;
+                    } else {
+                        c.win_out.ensure((size_t)n_bands * rows * ri.ncols * isz);
+                        d_out = c.win_out.p;
+                        T.out_rows = rows;
+                        T.win_row_off = 0;
+                    }
+                    T.vec_ok = ((uintptr_t)d_out % 16 == 0) && ((ri.ncols * isz) % 16 == 0);
+                    tile_for(ctx->dtype, ctx->pixel_fn)(T.n_tiles, s, P, T, ka, c.task_start.as<uint32_t>(), d_info,
+                                                        dg->part_vbeg, dg->part_vend, dg->x[0], dg->y[0], dg->tag[0],
+                                                        bg_bits, d_out);
+                    launches++;
+                    CUDA_TRY(cudaGetLastError());
+                    if (timed) CUDA_TRY(cudaEventRecord(c.ev[EV_B], s));
+                    lap(fill_ms, EV_A, EV_B);
+                    S.engine = 1;
+                    S.n_records += n_rec;
+                    S.n_tasks += T.n_tiles;
+                    S.n_windows++;
+                    S.key_bits = std::max(S.key_bits, tkey_bits);
+                    S.tile_width = TILE_C;
+                    if (!out_dev) {
+                        if (timed) CUDA_TRY(cudaEventRecord(c.ev[EV_A], s));
+                        const size_t chunk = (size_t)rows * ri.ncols * isz;
+                        for (uint32_t b = 0; b < n_bands; b++) {
+                            char* dst = (char*)out + ((size_t)b * shard_rows + (w.r0 - shard_r0)) * ri.ncols * isz;
+                            CUDA_TRY(cudaMemcpyAsync(dst, (char*)d_out + (size_t)b * chunk, chunk, cudaMemcpyDeviceToHost, s));
+                        }
+                        S.d2h_bytes += chunk * n_bands;
+                        if (timed) CUDA_TRY(cudaEventRecord(c.ev[EV_B], s));
+                        CUDA_TRY(cudaStreamSynchronize(s));
+                        lap(d2h_ms, EV_A, EV_B);
+                    }
+                    continue;
+                }
+            }
+        }
 
         // ---- count --------------------------------------------------------------------------
         if (timed) CUDA_TRY(cudaEventRecord(c.ev[EV_A], s));
@@ -634,29 +826,6 @@ struct rz_sparse {
 };
 
 namespace rz {
-
-template <typename Op, typename In, typename Out>
-static void device_scan(In in, uint32_t n, Out out, DevBuf& partial, cudaStream_t s, uint32_t& launches) {
-    const uint32_t nb = (n + SC_TILE - 1) / SC_TILE;
-    partial.ensure(((size_t)nb + 2) * 8);
-    unsigned long long* p = partial.as<unsigned long long>();
-    if (nb == 0) {
-        CUDA_TRY(cudaMemsetAsync(p, 0, 8, s));
-        return;
-    }
-    scan_reduce_kernel<Op, In><<<nb, SC_THREADS, 0, s>>>(in, n, p);
-    scan_partials_kernel<Op><<<1, 1024, 0, s>>>(p, nb);
-    scan_apply_kernel<Op, In, Out><<<nb, SC_THREADS, 0, s>>>(in, n, p, out);
-    launches += 3;
-}
-
-static unsigned long long scan_total(DevBuf& partial, uint32_t n, cudaStream_t s) {
-    const uint32_t nb = (n + SC_TILE - 1) / SC_TILE;
-    unsigned long long t = 0;
-    CUDA_TRY(cudaMemcpyAsync(&t, partial.as<unsigned long long>() + nb, 8, cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(cudaStreamSynchronize(s));
-    return t;
-}
 
 template <typename N>
 static void sparse_expand(cudaStream_t s, const KParams& P, SparseLayout L, DeviceGeoms* dg, DeviceCtx& c, uint32_t n_rec,

@@ -35,6 +35,8 @@ void Flattener::end_geometry(bool keep) {
         g_->part_geom.resize(mark_parts_);
         g_->part_xlo.resize(mark_parts_);
         g_->part_xhi.resize(mark_parts_);
+        g_->part_ylo.resize(mark_parts_);
+        g_->part_yhi.resize(mark_parts_);
         g_->part_vbeg.resize(mark_parts_);
         g_->part_vend.resize(mark_parts_);
         return;
@@ -67,6 +69,8 @@ void Flattener::begin_part(int kind) {
     g_->part_geom.push_back(g_->n_geoms);
     g_->part_xlo.push_back(std::numeric_limits<double>::infinity());
     g_->part_xhi.push_back(-std::numeric_limits<double>::infinity());
+    g_->part_ylo.push_back(std::numeric_limits<double>::infinity());
+    g_->part_yhi.push_back(-std::numeric_limits<double>::infinity());
     g_->part_vbeg.push_back((uint32_t)g_->pool[kind].size());
     g_->part_vend.push_back((uint32_t)g_->pool[kind].size());
 }
@@ -106,6 +110,8 @@ void Flattener::coord(double x, double y) {
         double& hi = g_->part_xhi[part_];
         lo = std::fmin(lo, x);
         hi = std::fmax(hi, x);
+        g_->part_ylo[part_] = std::fmin(g_->part_ylo[part_], y);
+        g_->part_yhi[part_] = std::fmax(g_->part_yhi[part_], y);
     }
 }
 

@@ -38,6 +38,7 @@ struct rz_geoms {
     std::vector<uint8_t> part_kind;    // [n_parts]
     std::vector<uint64_t> part_geom;   // [n_parts] owning geometry (index among kept geometries)
     std::vector<double> part_xlo, part_xhi;  // [n_parts] world-x extent of polygon parts (column-tile range)
+    std::vector<double> part_ylo, part_yhi;  // [n_parts] world-y extent of polygon parts (row-tile range)
     std::vector<uint32_t> part_vbeg, part_vend;  // [n_parts] vertex range of the part inside its pool
     bool has_bounds = false;
     double bounds[4] = {0, 0, 0, 0};   // union of geo::BoundingRect, xmin ymin xmax ymax

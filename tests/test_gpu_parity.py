@@ -15,7 +15,7 @@ GOLDEN = __import__("os").path.join(__import__("os").path.dirname(__file__), "go
 
 
 def both(geoms, fun="last", dtype="float64", burn=1, bg=0, by=None, field_valid=None, rows=None, tile_bytes=0,
-         all_touched=False, **kw):
+         all_touched=False, flags=0, **kw):
     og = oracle.Geoms.from_any(geoms)
     ori = oracle.raster_info(og, **kw)
     exp, names = oracle.rasterize_dense(og, ori, fun, dtype, burn, field_valid, by, bg, all_touched)
@@ -27,7 +27,7 @@ def both(geoms, fun="last", dtype="float64", burn=1, bg=0, by=None, field_valid=
         nb = len(bn)
         assert bn == names
     got, st = core.rasterize_dense(g, ri, fun, dtype, burn, field_valid, band, nb, bg, all_touched, rows=rows,
-                                   tile_bytes=tile_bytes)
+                                   tile_bytes=tile_bytes, flags=flags)
     if rows is not None:
         exp = exp[:, rows[0]:rows[1]]
     return exp, got, st
@@ -216,3 +216,77 @@ def test_all_touched_shards_tiles_and_edges():
             exp, got, _ = both(geoms, fun, "int32", burn, 0, all_touched=True, rows=rows, tile_bytes=1024,
                                shape=(150, 1500), extent=(0, 0, 1500, 150))
             assert_same(exp, got)
+
+
+# ---- the two engines (crossing records vs tile-binned) must agree with the oracle on polygon jobs ----
+def _polygon_job(seed, n, width, height, rho):
+    from oracle import wkt2wkb as W
+
+    rng = np.random.default_rng(seed)
+    out = []
+
+    def star(cx, cy, r, nv):
+        th = 2 * np.pi * (np.arange(nv) + 0.8 * rng.random(nv)) / nv
+        rr = r * (0.5 + 0.5 * rng.random(nv))
+        p = np.stack([cx + rr * np.cos(th), cy + rr * np.sin(th)], 1)
+        if rng.random() < 0.3:
+            p = np.round(p * 2) / 2  # vertices on pixel centres / edges
+        return np.vstack([p, p[:1]])
+
+    for _ in range(n):
+        cx, cy = rng.random() * width * 1.2 - 0.1 * width, rng.random() * height * 1.2 - 0.1 * height
+        r = rho * (0.2 + rng.random() ** 3 * 4)
+        rings = [star(cx, cy, r, rng.integers(3, 60))]
+        if rng.random() < 0.3:
+            rings.append(star(cx, cy, r * 0.4, rng.integers(3, 12)))
+        if rng.random() < 0.2:
+            out.append(W.multipolygon_wkb([rings, [star(cx + r, cy, r * 0.7, 9)]]))
+        else:
+            out.append(W.polygon_wkb(rings))
+    return out
+
+
+@pytest.mark.parametrize("engine_flag", [8, 16], ids=["records", "tiles"])
+@pytest.mark.parametrize("fun,dtype,bg", [("sum", "float32", np.nan), ("sum", "float64", 0.0), ("first", "int32", 0),
+                                          ("last", "uint8", 3), ("min", "int16", 2), ("max", "float32", 2.0),
+                                          ("count", "uint32", 0), ("any", "uint8", 0), ("sum", "int64", 7)])
+def test_engines_polygon_jobs(engine_flag, fun, dtype, bg):
+    seed = 900 + oracle.FUNS.index(fun)
+    geoms = _polygon_job(seed, 400, 700, 500, 30.0)
+    n = len(geoms)
+    burn = (np.arange(n) % 6).astype(dtype)
+    by = [str(i % 4) for i in range(n)] if seed % 2 else None
+    exp, got, st = both(geoms, fun, dtype, burn, bg, by, flags=engine_flag, shape=(500, 700), extent=(0, 0, 700, 500))
+    assert st["engine"] == (1 if engine_flag == 16 else 0)
+    assert_same(exp, got)
+
+
+@pytest.mark.parametrize("engine_flag", [8, 16], ids=["records", "tiles"])
+def test_engines_shards_odd_rows_and_edges(engine_flag):
+    geoms = _polygon_job(77, 300, 900, 400, 50.0)
+    from oracle.wkt2wkb import wkt_to_wkb
+
+    geoms += [wkt_to_wkb(s) for s in (
+        sq(-50, -50, 5000, 5000), sq(127.5, 63.5, 128.5, 64.5), sq(0, 0, 128, 128), sq(128, 128, 256, 256),
+        "POLYGON ((10 10, 890 10.0000000000000001, 890 50, 10 50, 10 10))",       # epsilon-horizontal edge
+        "POLYGON ((0.5 0.5, 300 0.5000000000000001, 300 200.5, 0.5 0.5))",         # odd crossing count on row 0
+        "POLYGON ((30 30, 770 370, 770 30, 30 370, 30 30))")]                      # bow-tie across many tiles
+    burn = np.arange(len(geoms)) % 7 + 1
+    for fun, dtype, bg in (("sum", "float64", np.nan), ("count", "int32", 0)):
+        for rows in (None, (0, 130), (130, 400)):
+            exp, got, st = both(geoms, fun, dtype, burn, bg, rows=rows, flags=engine_flag, shape=(400, 900),
+                                extent=(0, 0, 900, 400))
+            assert_same(exp, got)
+
+
+def test_engine_choice_is_automatic():
+    small = _polygon_job(5, 200, 2000, 2000, 20.0)
+    _, _, st = both(small, shape=(2000, 2000), extent=(0, 0, 2000, 2000))
+    assert st["engine"] == 1
+    from oracle.wkt2wkb import wkt_to_wkb
+
+    huge = [wkt_to_wkb("POLYGON ((" + ", ".join(f"{1000 + 990 * np.cos(a):.3f} {1000 + 990 * np.sin(a):.3f}" for a in
+                                              np.linspace(0, 2 * np.pi, 5000)) + "))")] * 3
+    exp, got, st = both(huge, "count", "uint8", 1, 0, shape=(2000, 2000), extent=(0, 0, 2000, 2000))
+    assert st["engine"] == 0  # 5000-vertex polygon over 256 tiles: the record pipeline is cheaper
+    assert_same(exp, got)
