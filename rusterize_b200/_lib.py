@@ -8,7 +8,7 @@ from pathlib import Path
 import numpy as np
 
 _HERE = Path(__file__).resolve().parent
-SO_PATH = _HERE / "librz_b200.so"
+SO_PATH = Path(__import__("os").environ.get("RZ_B200_SO", _HERE / "librz_b200.so"))
 
 DTYPES = ["uint8", "uint16", "uint32", "uint64", "int8", "int16", "int32", "int64", "float32", "float64"]
 FUNS = ["sum", "first", "last", "min", "max", "count", "any"]

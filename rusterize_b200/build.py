@@ -10,7 +10,7 @@ HERE = Path(__file__).resolve().parent
 CSRC = HERE / "csrc"
 SO = HERE / "librz_b200.so"
 SOURCES = [CSRC / "rz_engine.cu", CSRC / "rz_host.cpp"]
-HEADERS = [CSRC / "rz_kernels.cuh", CSRC / "rz_host.hpp", HERE.parent / "include" / "rz_b200.h"]
+HEADERS = sorted(CSRC.glob("*.cuh")) + sorted(CSRC.glob("*.hpp")) + [HERE.parent / "include" / "rz_b200.h"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -297,7 +297,7 @@ template <typename N, int FN>
 static void tile_launch(uint32_t grid, cudaStream_t s, KParams P, TileParams T, const uint64_t* recs,
                         const uint32_t* tile_start, const PartInfo* info, const uint32_t* vbeg, const uint32_t* vend,
                         const double* x, const double* y, const uint32_t* tag, uint64_t bg, void* out) {
-    constexpr int TR = sizeof(N) <= 4 ? 128 : 64;
+    constexpr int TR = sizeof(N) <= 4 ? 64 : 32;
     const size_t smem = (size_t)TR * TILE_C * sizeof(N);
     static bool configured = false;  // per instantiation
     if (!configured) {
@@ -519,7 +519,7 @@ static void rasterize_dense(rz_geoms* g, const rz_context* ctx, void* out, rz_st
         if (nv_line == 0 && nv_pt == 0 && !touched && n_parts && !(ctx->flags & RZ_FLAG_NO_TILE_ENGINE)) {
             TileParams T;
             std::memset(&T, 0, sizeof T);
-            T.tile_r = isz <= 4 ? 128u : 64u;
+            T.tile_r = isz <= 4 ? 64u : 32u;
             T.n_tc = (uint32_t)((ri.ncols + TILE_C - 1) / TILE_C);
             T.n_tr = (rows + T.tile_r - 1) / T.tile_r;
             const uint64_t n_tiles64 = (uint64_t)n_bands * T.n_tr * T.n_tc;

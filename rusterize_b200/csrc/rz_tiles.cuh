@@ -130,17 +130,41 @@ __device__ __forceinline__ uint32_t tile_edge_col(const KParams& P, const TileEd
     return sat_u32(floor(__dadd_rn(xi, 0.5)), P.ncols);                               // burners.rs:310-311
 }
 
+// A row can only have an odd number of crossings when a non-horizontal edge was skipped for being
+// shorter than f64::EPSILON in y (edges.rs:100) while still straddling a pixel centre.  Pixel-centre
+// ordinates k+0.5 with k >= 1 are spaced >= EPSILON apart, so that can only happen on raster row 0
+// (centre 0.5): only that row's crossing count is tracked.
+//
+// Warp-specialised CTA, no block barrier in the main loop:
+//   producer warps (0..5)  part k of the tile goes to producer k%6, which bins its edges into toggle
+//                          mask slot k%8 (phase 1) and then publishes ready[slot] = k+1;
+//   consumer warps (6..7)  each owns half of the tile's rows and applies parts strictly in
+//                          order (phases 2+3) as their masks become ready, clearing the mask words it
+//                          read; the last consumer of a part frees the slot (consumed++).
+// Producers run up to 8 parts ahead of the consumers, so edge setup (f64 divides, global loads) overlaps
+// the pixel work instead of alternating with it across barriers.
+constexpr int TILE_SLOTS = 8;
+constexpr int TILE_PRODUCERS = 6;
+constexpr int TILE_CONSUMERS = 2;
+
+__device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t* p) { return *reinterpret_cast<const volatile uint32_t*>(p); }
+__device__ __forceinline__ void st_volatile_u32(uint32_t* p, uint32_t v) { *reinterpret_cast<volatile uint32_t*>(p) = v; }
+
 template <typename N, int FN, int TILE_R>
 __global__ void __launch_bounds__(TILE_THREADS)
 tile_fill_kernel(KParams P, TileParams T, const uint64_t* __restrict__ recs, const uint32_t* __restrict__ tile_start,
                  const PartInfo* __restrict__ info, const uint32_t* __restrict__ vbeg, const uint32_t* __restrict__ vend,
                  const double* __restrict__ x, const double* __restrict__ y, const uint32_t* __restrict__ tag,
                  uint64_t bg_bits, N* __restrict__ out) {
+    static_assert(TILE_THREADS == 32 * (TILE_PRODUCERS + TILE_CONSUMERS), "role split");
+    static_assert(TILE_R % (8 * TILE_CONSUMERS) == 0, "each consumer owns whole 8-row groups");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     N* tile = reinterpret_cast<N*>(smem_raw);  // [TILE_R][TILE_C]
-    __shared__ uint32_t s_mask[TILE_R][4];
-    __shared__ uint32_t s_cpar[TILE_R / 32];   // parity of the number of crossings per row (all columns)
-    __shared__ uint32_t s_max;
+    __shared__ uint32_t s_mask[TILE_SLOTS][TILE_R][4];
+    __shared__ unsigned long long s_val[TILE_SLOTS];
+    __shared__ uint32_t s_ready[TILE_SLOTS], s_done[TILE_SLOTS], s_cnt[TILE_SLOTS], s_par0[TILE_SLOTS], s_consumed;
+    __shared__ double s_xt[TILE_PRODUCERS][32], s_yt[TILE_PRODUCERS][32], s_dx[TILE_PRODUCERS][32];
+    __shared__ uint32_t s_pre[TILE_PRODUCERS][32], s_lo[TILE_PRODUCERS][32];
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const N bg = value_from_bits<N>(bg_bits);
     const uint64_t part_mask = (1ull << T.part_bits) - 1ull;
@@ -149,95 +173,172 @@ tile_fill_kernel(KParams P, TileParams T, const uint64_t* __restrict__ recs, con
     const uint32_t tcol = t % T.n_tc, trow = (t / T.n_tc) % T.n_tr, band = t / (T.n_tc * T.n_tr);
     const uint32_t r0 = P.win_r0 + trow * TILE_R, r1 = min(r0 + TILE_R, P.win_r1);
     const uint32_t c0 = tcol * TILE_C, c1 = min(c0 + TILE_C, P.ncols);
+    const uint32_t beg = tile_start[t], n_parts_here = tile_start[t + 1] - beg;
 
     for (uint32_t i = tid; i < TILE_R * TILE_C; i += TILE_THREADS) tile[i] = bg;  // geo/raster.rs:23-28
-    for (uint32_t i = tid; i < TILE_R * 4; i += TILE_THREADS) (&s_mask[0][0])[i] = 0;
-    if (tid < TILE_R / 32) s_cpar[tid] = 0;
+    if (n_parts_here) {
+        for (uint32_t i = tid; i < TILE_SLOTS * TILE_R * 4; i += TILE_THREADS) (&s_mask[0][0][0])[i] = 0;
+        if (tid < TILE_SLOTS) {
+            s_ready[tid] = 0;
+            s_done[tid] = 0;
+            s_cnt[tid] = 0;
+            s_par0[tid] = 0;
+        }
+        if (tid == 0) s_consumed = 0;
+    }
     __syncthreads();
 
-    const uint32_t beg = tile_start[t], end = tile_start[t + 1];
-    for (uint32_t rec = beg; rec < end; rec++) {
-        const uint32_t part = (uint32_t)(recs[rec] & part_mask);
-        const uint32_t vb = vbeg[part], ve = vend[part];
-        const N v = value_from_bits<N>(info[part].value_bits);
-
-        // ---- phase 1: crossings of the part's edges with the tile's rows -> toggle bits ------------
-        for (uint32_t i = vb + tid; i + 1 < ve; i += TILE_THREADS) {
-            if (tag[i] & 0x80000000u) continue;  // last vertex of its ring
-            TileEdge e;
-            if (!tile_edge_setup(P, x, y, i, r0, r1, e)) continue;
-            for (uint32_t row = e.lo; row < e.hi; row++) {
-                const uint32_t col = tile_edge_col(P, e, row);
-                const uint32_t rr = row - r0;
-                atomicXor(&s_cpar[rr >> 5], 1u << (rr & 31));
-                if (col >= c1) continue;                 // right of the tile: no effect on its pixels
-                const uint32_t rel = col <= c0 ? 0u : col - c0;
-                atomicXor(&s_mask[rr][rel >> 5], 1u << (rel & 31));
-            }
-        }
-        __syncthreads();
-
-        // ---- rare: rows with an odd number of crossings drop their largest column (burners.rs:305) ---
-        uint32_t odd = 0;
+    if (n_parts_here && warp < TILE_PRODUCERS) {
+        // ================= producers: phase 1, one 32-edge batch at a time =================
+        // Batches of all parts form one sequence; batch b goes to producer b % TILE_PRODUCERS, so the
+        // edges of one part are binned by several warps at once and parts overlap in a pipeline.
+        // world-y band outside which an edge cannot cross any of this tile's rows (one row of margin)
+        const double cull_hi = __dsub_rn(P.ymax, __dmul_rn(__dsub_rn((double)r0, 1.0), P.yres));
+        const double cull_lo = __dsub_rn(P.ymax, __dmul_rn(__dadd_rn((double)r1, 1.0), P.yres));
+        uint32_t b_first = 0;  // sequence number of the part's first batch
+        for (uint32_t k = 0; k < n_parts_here; k++) {
+            const uint32_t slot = k % TILE_SLOTS;
+            const uint32_t part = (uint32_t)(recs[beg + k] & part_mask);
+            const uint32_t vb = vbeg[part], ve = vend[part];
+            const uint32_t n_edges = ve > vb ? ve - vb - 1 : 0u;
+            const uint32_t nb = max(1u, (n_edges + 31) / 32);
+            uint32_t(*mask)[4] = s_mask[slot];
+            // first batch of this part that belongs to this warp
+            uint32_t j = (warp + TILE_PRODUCERS - b_first % TILE_PRODUCERS) % TILE_PRODUCERS;
+            b_first += nb;
+            if (j >= nb) continue;
+            while (k >= ld_volatile_u32(&s_consumed) + TILE_SLOTS) __nanosleep(64);  // slot still in use
+            __syncwarp();
+            for (; j < nb; j += TILE_PRODUCERS) {
+                const uint32_t i = vb + j * 32 + lane;
+                TileEdge e;
+                uint32_t cnt = 0;
+                if (i + 1 < ve && !(tag[i] & 0x80000000u)) {
+                    const double ya = y[i], yb = y[i + 1];
+                    if (!(fmax(ya, yb) < cull_lo || fmin(ya, yb) > cull_hi) && tile_edge_setup(P, x, y, i, r0, r1, e))
+                        cnt = e.hi - e.lo;
+                }
+                uint32_t inc = cnt;
 #pragma unroll
-        for (int k = 0; k < TILE_R / 32; k++) odd |= s_cpar[k];
-        if (odd) {
-            for (int k = 0; k < TILE_R / 32; k++) {
-                uint32_t bits = s_cpar[k];
-                while (bits) {
-                    const uint32_t rr = k * 32 + (__ffs(bits) - 1);
-                    bits &= bits - 1;
-                    const uint32_t row = r0 + rr;
-                    if (tid == 0) s_max = 0;
-                    __syncthreads();
-                    for (uint32_t i = vb + tid; i + 1 < ve; i += TILE_THREADS) {
-                        if (tag[i] & 0x80000000u) continue;
-                        TileEdge e;
-                        if (!tile_edge_setup(P, x, y, i, row, row + 1, e)) continue;
-                        atomicMax(&s_max, tile_edge_col(P, e, row) + 1u);
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t up = __shfl_up_sync(0xffffffffu, inc, o);
+                    if (lane >= (uint32_t)o) inc += up;
+                }
+                const uint32_t wtot = __shfl_sync(0xffffffffu, inc, 31);
+                uint32_t par0 = 0;  // this lane's share of the row-0 crossing count parity
+                if (wtot) {
+                    s_pre[warp][lane] = inc - cnt;
+                    if (cnt) {
+                        s_xt[warp][lane] = e.x_top;
+                        s_yt[warp][lane] = e.y_top;
+                        s_dx[warp][lane] = e.dxdy;
+                        s_lo[warp][lane] = e.lo;
                     }
-                    __syncthreads();
-                    if (tid == 0 && s_max) {
-                        const uint32_t col = s_max - 1;
-                        if (col < c1) {
+                    __syncwarp();
+                    for (uint32_t q = lane; q < wtot; q += 32) {
+                        uint32_t lo = 0, hi = 32;  // last edge whose first crossing is <= q
+#pragma unroll
+                        for (int it = 0; it < 5; it++) {
+                            const uint32_t mid = (lo + hi) >> 1;
+                            if (s_pre[warp][mid] <= q) lo = mid;
+                            else hi = mid;
+                        }
+                        TileEdge eb;
+                        eb.x_top = s_xt[warp][lo];
+                        eb.y_top = s_yt[warp][lo];
+                        eb.dxdy = s_dx[warp][lo];
+                        const uint32_t row = s_lo[warp][lo] + (q - s_pre[warp][lo]);
+                        const uint32_t col = tile_edge_col(P, eb, row);
+                        par0 ^= (row == 0);
+                        if (col < c1) {  // right of the tile: no effect on its pixels
                             const uint32_t rel = col <= c0 ? 0u : col - c0;
-                            s_mask[rr][rel >> 5] ^= 1u << (rel & 31);
+                            atomicXor(&mask[row - r0][rel >> 5], 1u << (rel & 31));
                         }
                     }
-                    __syncthreads();
+                }
+                const uint32_t odd = __popc(__ballot_sync(0xffffffffu, par0 & 1u)) & 1u;
+                __threadfence_block();
+                uint32_t fin = 0;
+                if (lane == 0) {
+                    if (odd) atomicXor(&s_par0[slot], 1u);
+                    fin = atomicAdd(&s_cnt[slot], 1u) + 1u;
+                }
+                fin = __shfl_sync(0xffffffffu, fin, 0);
+                if (fin == nb) {  // this warp finished the part's last outstanding batch
+                    __threadfence_block();
+                    // rare: an odd row 0 drops its largest column (chunks_exact(2), burners.rs:305)
+                    if (r0 == 0 && ld_volatile_u32(&s_par0[slot])) {
+                        uint32_t mx = 0;
+                        for (uint32_t ii = vb + lane; ii + 1 < ve; ii += 32) {
+                            if (tag[ii] & 0x80000000u) continue;
+                            TileEdge e0;
+                            if (tile_edge_setup(P, x, y, ii, 0, 1, e0)) mx = max(mx, tile_edge_col(P, e0, 0) + 1u);
+                        }
+                        mx = __reduce_max_sync(0xffffffffu, mx);
+                        if (lane == 0 && mx && mx - 1 < c1) {
+                            const uint32_t rel = mx - 1 <= c0 ? 0u : mx - 1 - c0;
+                            atomicXor(&mask[0][rel >> 5], 1u << (rel & 31));
+                        }
+                    }
+                    if (lane == 0) {
+                        s_par0[slot] = 0;
+                        s_cnt[slot] = 0;
+                        s_val[slot] = info[part].value_bits;
+                        __threadfence_block();
+                        st_volatile_u32(&s_ready[slot], k + 1);
+                    }
+                }
+                __syncwarp();
+            }
+        }
+    } else if (n_parts_here) {
+        // ================= consumer: phases 2+3 on its own rows =================
+        const uint32_t cw = warp - TILE_PRODUCERS;
+        constexpr uint32_t GROUPS = TILE_R / 8 / TILE_CONSUMERS;  // 8-row groups per consumer
+        for (uint32_t k = 0; k < n_parts_here; k++) {
+            const uint32_t slot = k % TILE_SLOTS;
+            while (ld_volatile_u32(&s_ready[slot]) != k + 1) __nanosleep(32);
+            __syncwarp();
+            __threadfence_block();
+            const N v = value_from_bits<N>(*reinterpret_cast<volatile unsigned long long*>(&s_val[slot]));
+            uint32_t(*mask)[4] = s_mask[slot];
+#pragma unroll
+            for (uint32_t gg = 0; gg < GROUPS; gg++) {
+                const uint32_t g = cw * GROUPS + gg;
+                const uint32_t rr = g * 8 + (lane >> 2), wd = lane & 3u;
+                const uint32_t tg = *reinterpret_cast<volatile uint32_t*>(&mask[rr][wd]);
+                if (__ballot_sync(0xffffffffu, tg != 0) == 0) continue;  // part does not reach these rows
+                mask[rr][wd] = 0;
+                uint32_t m = tg;
+                m ^= m << 1;
+                m ^= m << 2;
+                m ^= m << 4;
+                m ^= m << 8;
+                m ^= m << 16;
+                const uint32_t odd_words = __ballot_sync(0xffffffffu, __popc(tg) & 1);
+                if (__popc((odd_words >> (lane & ~3u)) & ((1u << wd) - 1u)) & 1) m = ~m;  // carry from the left words
+                uint32_t nz = __ballot_sync(0xffffffffu, m != 0);
+                N* base = tile + g * (8 * TILE_C) + lane;  // word `src` of the group starts at base + src*32
+                while (nz) {
+                    const int src = __ffs(nz) - 1;
+                    nz &= nz - 1;
+                    const uint32_t mw = __shfl_sync(0xffffffffu, m, src);
+                    N* p = base + src * 32;
+                    const N cur = *p;
+                    const N nv = apply_px<N, FN>(cur, v, bg);
+                    *p = ((mw >> lane) & 1u) ? nv : cur;
                 }
             }
-            if (tid < TILE_R / 32) s_cpar[tid] = 0;
-            __syncthreads();
-        }
-
-        // ---- phases 2+3: 8 rows per warp step; lane = (row in group, mask word) --------------------
-        for (uint32_t g = warp; g < TILE_R / 8; g += TILE_THREADS / 32) {
-            const uint32_t rr = g * 8 + (lane >> 2), wd = lane & 3u;
-            const uint32_t tg = s_mask[rr][wd];
-            if (__ballot_sync(0xffffffffu, tg != 0) == 0) continue;  // part does not reach these rows
-            s_mask[rr][wd] = 0;
-            uint32_t m = tg;
-            m ^= m << 1;
-            m ^= m << 2;
-            m ^= m << 4;
-            m ^= m << 8;
-            m ^= m << 16;
-            const uint32_t odd_words = __ballot_sync(0xffffffffu, __popc(tg) & 1);
-            if (__popc((odd_words >> (lane & ~3u)) & ((1u << wd) - 1u)) & 1) m = ~m;  // carry from the words to the left
-            uint32_t nz = __ballot_sync(0xffffffffu, m != 0);
-            while (nz) {
-                const int src = __ffs(nz) - 1;
-                nz &= nz - 1;
-                const uint32_t mw = __shfl_sync(0xffffffffu, m, src);
-                N* p = tile + (g * 8 + (src >> 2)) * TILE_C + (src & 3) * 32 + lane;
-                const N cur = *p;
-                const N nv = apply_px<N, FN>(cur, v, bg);
-                *p = ((mw >> lane) & 1u) ? nv : cur;
+            __syncwarp();
+            __threadfence_block();
+            if (lane == 0 && atomicAdd(&s_done[slot], 1u) == TILE_CONSUMERS - 1) {
+                s_done[slot] = 0;
+                __threadfence_block();
+                atomicAdd(&s_consumed, 1u);  // the slot may be reused by part k + TILE_SLOTS
             }
         }
-        __syncthreads();
     }
+    __syncthreads();
 
     // ---- flush: every output byte is written exactly once ---------------------------------------------
     const uint32_t cols = c1 - c0;
