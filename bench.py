@@ -230,10 +230,12 @@ def run_b200(args):
     stream = torch.cuda.current_stream().cuda_stream
     geoms.upload(local)
 
+    eng_flag = {"auto": 0, "records": _lib.FLAG_NO_TILE_ENGINE, "tiles": _lib.FLAG_FORCE_TILE_ENGINE}[args.engine]
+
     def step(flags=0, out=None):
         return core.rasterize_dense(geoms, ri, w["fun"], w["dtype"], bvals, background=bg, device=local,
                                     rows=(r0, r1), out=d_out.data_ptr() if out is None else out, stream=stream,
-                                    flags=flags, tile_bytes=args.tile_bytes)[1]
+                                    flags=flags | eng_flag, tile_bytes=args.tile_bytes)[1]
 
     # ---- device-resident throughput --------------------------------------------------------------
     for _ in range(args.warmup):
@@ -297,7 +299,15 @@ def run_b200(args):
     peak, peak_src = peaks()
     s0 = stats[-1]
     fill_ms = float(np.mean([s["fill_ms"] for s in stats]))
-    fill_bytes = 8.0 * s0["n_records"] + s0["out_bytes"]          # rank 0's launch: records read once + raster written once
+    if s0["engine"] == 1:
+        # tile engine: the kernel fuses edge setup, crossing binning and fill: every ring vertex of the
+        # band (x, y f64 + u32 tag) read once + (tile,part) records + raster written once
+        kernel = "tile_fill_kernel<%s, %s>" % (w["dtype"], w["fun"])
+        fill_bytes = 20.0 * s0["n_poly_vertices"] + 8.0 * s0["n_records"] + s0["out_bytes"]
+    else:
+        # record pipeline: crossing records read once + raster written once
+        kernel = "fill_kernel<%s, %s>" % (w["dtype"], w["fun"])
+        fill_bytes = 8.0 * s0["n_records"] + s0["out_bytes"]
     achieved = fill_bytes / (fill_ms / 1e3) / 1e9
     traffic = None
     tp = ROOT / "profiles" / "fill_traffic.json"
@@ -333,12 +343,12 @@ def run_b200(args):
         "dtype": "f64 geometry / %s values" % w["dtype"], "data": "synthetic",
         "config": {"workload": f"{args.workload}: {w['desc']}", "scale": args.scale, "parallelism": f"row-bands x{world}",
                    "l2": "inputs (vertex pools + record buffers + raster) are far larger than the 126 MB L2",
-                   "tile_bytes": args.tile_bytes or 4096},
+                   "engine": "tile-binned" if s0["engine"] == 1 else "crossing-records"},
         "polygons_per_s": w["n"] / (ms_max / 1e3),
         "stage_ms_max_over_ranks": dict(zip(["count", "emit", "sort", "index", "fill"], [float(v) for v in stage])),
         "records": int(agg[0].item()), "crossings": int(agg[1].item()),
         "gpu_launches": int(round(agg[3].item())) * args.steps,
-        "roofline": {"bound": "hbm", "kernel": "fill_kernel<float, sum>", "achieved": achieved, "peak": peak,
+        "roofline": {"bound": "hbm", "kernel": kernel, "achieved": achieved, "peak": peak,
                      "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                      "bytes_per_launch": fill_bytes, "ms_per_launch": fill_ms},
         "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
@@ -360,6 +370,7 @@ def main():
     ap.add_argument("--cpu-sample-rows", type=int, default=4096)
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--tile-bytes", type=int, default=0)
+    ap.add_argument("--engine", default="auto", choices=["auto", "records", "tiles"])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

@@ -108,7 +108,7 @@ struct DeviceCtx {
     cudaStream_t stream = nullptr;
     int sm_count = 148;
     DevBuf keys_a, keys_b, hist, digit_total, task_start, part_info, field, valid, band, last_kept, counters, win_out,
-        block_total, tile_cnt, tile_off, tile_ctr, sp_a, sp_b, sp_c, sp_d, sp_e, sp_f, sp_g, sp_rows, sp_cols, sp_data, sp_partial;
+        block_total, tile_cnt, tile_off, tile_ctr, tile_px, tile_py, sp_a, sp_b, sp_c, sp_d, sp_e, sp_f, sp_g, sp_rows, sp_cols, sp_data, sp_partial;
     Counters* h_counters = nullptr;  // pinned
     cudaEvent_t ev[16];
 };
@@ -507,6 +507,7 @@ static void rasterize_dense(rz_geoms* g, const rz_context* ctx, void* out, rz_st
                    nv_pt = (uint32_t)g->pool[2].size();
     const uint32_t per_block = SETUP_THREADS * SETUP_ITEMS;
     const bool all_poly = nv_line == 0 && nv_pt == 0 && !ctx->all_touched;
+    bool tile_vertices_ready = false;
 
     while (!todo.empty()) {
         Window w = todo.back();
@@ -594,9 +595,18 @@ static void rasterize_dense(rz_geoms* g, const rz_context* ctx, void* out, rz_st
                         T.win_row_off = 0;
                     }
                     T.vec_ok = ((uintptr_t)d_out % 16 == 0) && ((ri.ncols * isz) % 16 == 0);
+                    if (!tile_vertices_ready) {  // pixel-space vertices, shared by all windows of this call
+                        c.tile_px.ensure((size_t)(nv_poly + 1) * 8);
+                        c.tile_py.ensure((size_t)(nv_poly + 1) * 8);
+                        vertex_transform_kernel<<<(nv_poly + 255) / 256, 256, 0, s>>>(P, dg->x[0], dg->y[0], nv_poly,
+                                                                                     c.tile_px.as<double>(),
+                                                                                     c.tile_py.as<double>());
+                        launches++;
+                        tile_vertices_ready = true;
+                    }
                     tile_for(ctx->dtype, ctx->pixel_fn)(T.n_tiles, s, P, T, ka, c.task_start.as<uint32_t>(), d_info,
-                                                        dg->part_vbeg, dg->part_vend, dg->x[0], dg->y[0], dg->tag[0],
-                                                        bg_bits, d_out);
+                                                        dg->part_vbeg, dg->part_vend, c.tile_px.as<double>(),
+                                                        c.tile_py.as<double>(), dg->tag[0], bg_bits, d_out);
                     launches++;
                     CUDA_TRY(cudaGetLastError());
                     if (timed) CUDA_TRY(cudaEventRecord(c.ev[EV_B], s));

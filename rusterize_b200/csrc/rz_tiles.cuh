@@ -5,6 +5,7 @@
 // raster, it is far cheaper to bin PARTS to 128-column x TILE_R-row tiles (a few million (tile,part)
 // records, stably sorted by tile so parts stay in burn order) and let one CTA per tile do the whole
 // scanline job in shared memory, part after part:
+//   phase 0  (once per call) every ring vertex is transformed to pixel space (edges.rs:94-97);
 //   phase 1  threads take the part's ring edges (edges.rs:27-46, 90-110), compute the crossings with
 //            the tile's rows (edges.rs:50-55) and XOR one bit per crossing into a TILE_R x 128 bit
 //            toggle mask (columns left of the tile clamp to bit 0, columns right of it are dropped);
@@ -98,15 +99,25 @@ struct InU32 {
     __device__ unsigned long long operator()(uint32_t i) const { return v[i]; }
 };
 
-// One ring edge against the tile's rows: false when it contributes no crossing there.
+// World -> pixel transform of every ring vertex, once per call (edges.rs:94-97): the tile kernel visits
+// a part's edges once per overlapped tile and would otherwise repeat these four divides each time.
+__global__ void vertex_transform_kernel(KParams P, const double* __restrict__ x, const double* __restrict__ y,
+                                        uint32_t n, double* __restrict__ px, double* __restrict__ py) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    px[i] = px_x(P, x[i]);
+    py[i] = px_y(P, y[i]);
+}
+
+// One ring edge (pixel-space vertices) against the tile's rows: false when it contributes no crossing there.
 struct TileEdge {
     double x_top, y_top, dxdy;
     uint32_t lo, hi;  // active rows [lo, hi) inside the tile (absolute)
 };
-__device__ __forceinline__ bool tile_edge_setup(const KParams& P, const double* __restrict__ x,
-                                                const double* __restrict__ y, uint32_t i, uint32_t r0, uint32_t r1,
+__device__ __forceinline__ bool tile_edge_setup(const KParams& P, const double* __restrict__ px,
+                                                const double* __restrict__ py, uint32_t i, uint32_t r0, uint32_t r1,
                                                 TileEdge& e) {
-    const double y0 = px_y(P, y[i]), y1 = px_y(P, y[i + 1]);
+    const double y0 = py[i], y1 = py[i + 1];
     if (!(fabs(__dsub_rn(y0, y1)) >= DBL_EPSILON)) return false;  // edges.rs:100
     const double min_y = fmin(y0, y1), max_y = fmax(y0, y1);
     if (!(min_y < P.nrows_f && max_y >= 0.0)) return false;       // edges.rs:105
@@ -117,7 +128,7 @@ __device__ __forceinline__ bool tile_edge_setup(const KParams& P, const double* 
     e.lo = max(ystart, r0);
     e.hi = min(yend, r1);
     if (e.hi <= e.lo) return false;
-    const double x0 = px_x(P, x[i]), x1 = px_x(P, x[i + 1]);
+    const double x0 = px[i], x1 = px[i + 1];
     const double x_bot = down ? x1 : x0;
     e.x_top = down ? x0 : x1;
     e.y_top = y_top;
@@ -136,14 +147,14 @@ __device__ __forceinline__ uint32_t tile_edge_col(const KParams& P, const TileEd
 // (centre 0.5): only that row's crossing count is tracked.
 //
 // Warp-specialised CTA, no block barrier in the main loop:
-//   producer warps (0..5)  part k of the tile goes to producer k%6, which bins its edges into toggle
+//   producer warps          the 32-edge batches of all parts form one sequence; batch b goes to producer b%P, which bins its edges into toggle
 //                          mask slot k%8 (phase 1) and then publishes ready[slot] = k+1;
-//   consumer warps (6..7)  each owns half of the tile's rows and applies parts strictly in
+//   consumer warps          each owns a fixed subset of the tile's 8-row groups and applies parts strictly in
 //                          order (phases 2+3) as their masks become ready, clearing the mask words it
 //                          read; the last consumer of a part frees the slot (consumed++).
 // Producers run up to 8 parts ahead of the consumers, so edge setup (f64 divides, global loads) overlaps
 // the pixel work instead of alternating with it across barriers.
-constexpr int TILE_SLOTS = 8;
+constexpr int TILE_SLOTS = 4;
 constexpr int TILE_PRODUCERS = 6;
 constexpr int TILE_CONSUMERS = 2;
 
@@ -151,13 +162,12 @@ __device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t* p) { return 
 __device__ __forceinline__ void st_volatile_u32(uint32_t* p, uint32_t v) { *reinterpret_cast<volatile uint32_t*>(p) = v; }
 
 template <typename N, int FN, int TILE_R>
-__global__ void __launch_bounds__(TILE_THREADS)
+__global__ void __launch_bounds__(TILE_THREADS, 5)
 tile_fill_kernel(KParams P, TileParams T, const uint64_t* __restrict__ recs, const uint32_t* __restrict__ tile_start,
                  const PartInfo* __restrict__ info, const uint32_t* __restrict__ vbeg, const uint32_t* __restrict__ vend,
                  const double* __restrict__ x, const double* __restrict__ y, const uint32_t* __restrict__ tag,
                  uint64_t bg_bits, N* __restrict__ out) {
     static_assert(TILE_THREADS == 32 * (TILE_PRODUCERS + TILE_CONSUMERS), "role split");
-    static_assert(TILE_R % (8 * TILE_CONSUMERS) == 0, "each consumer owns whole 8-row groups");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     N* tile = reinterpret_cast<N*>(smem_raw);  // [TILE_R][TILE_C]
     __shared__ uint32_t s_mask[TILE_SLOTS][TILE_R][4];
@@ -192,9 +202,6 @@ tile_fill_kernel(KParams P, TileParams T, const uint64_t* __restrict__ recs, con
         // ================= producers: phase 1, one 32-edge batch at a time =================
         // Batches of all parts form one sequence; batch b goes to producer b % TILE_PRODUCERS, so the
         // edges of one part are binned by several warps at once and parts overlap in a pipeline.
-        // world-y band outside which an edge cannot cross any of this tile's rows (one row of margin)
-        const double cull_hi = __dsub_rn(P.ymax, __dmul_rn(__dsub_rn((double)r0, 1.0), P.yres));
-        const double cull_lo = __dsub_rn(P.ymax, __dmul_rn(__dadd_rn((double)r1, 1.0), P.yres));
         uint32_t b_first = 0;  // sequence number of the part's first batch
         for (uint32_t k = 0; k < n_parts_here; k++) {
             const uint32_t slot = k % TILE_SLOTS;
@@ -213,11 +220,7 @@ tile_fill_kernel(KParams P, TileParams T, const uint64_t* __restrict__ recs, con
                 const uint32_t i = vb + j * 32 + lane;
                 TileEdge e;
                 uint32_t cnt = 0;
-                if (i + 1 < ve && !(tag[i] & 0x80000000u)) {
-                    const double ya = y[i], yb = y[i + 1];
-                    if (!(fmax(ya, yb) < cull_lo || fmin(ya, yb) > cull_hi) && tile_edge_setup(P, x, y, i, r0, r1, e))
-                        cnt = e.hi - e.lo;
-                }
+                if (i + 1 < ve && !(tag[i] & 0x80000000u) && tile_edge_setup(P, x, y, i, r0, r1, e)) cnt = e.hi - e.lo;
                 uint32_t inc = cnt;
 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1) {
@@ -294,7 +297,6 @@ tile_fill_kernel(KParams P, TileParams T, const uint64_t* __restrict__ recs, con
     } else if (n_parts_here) {
         // ================= consumer: phases 2+3 on its own rows =================
         const uint32_t cw = warp - TILE_PRODUCERS;
-        constexpr uint32_t GROUPS = TILE_R / 8 / TILE_CONSUMERS;  // 8-row groups per consumer
         for (uint32_t k = 0; k < n_parts_here; k++) {
             const uint32_t slot = k % TILE_SLOTS;
             while (ld_volatile_u32(&s_ready[slot]) != k + 1) __nanosleep(32);
@@ -302,9 +304,7 @@ tile_fill_kernel(KParams P, TileParams T, const uint64_t* __restrict__ recs, con
             __threadfence_block();
             const N v = value_from_bits<N>(*reinterpret_cast<volatile unsigned long long*>(&s_val[slot]));
             uint32_t(*mask)[4] = s_mask[slot];
-#pragma unroll
-            for (uint32_t gg = 0; gg < GROUPS; gg++) {
-                const uint32_t g = cw * GROUPS + gg;
+            for (uint32_t g = cw; g < TILE_R / 8; g += TILE_CONSUMERS) {  // this consumer's 8-row groups
                 const uint32_t rr = g * 8 + (lane >> 2), wd = lane & 3u;
                 const uint32_t tg = *reinterpret_cast<volatile uint32_t*>(&mask[rr][wd]);
                 if (__ballot_sync(0xffffffffu, tg != 0) == 0) continue;  // part does not reach these rows
@@ -319,14 +319,22 @@ tile_fill_kernel(KParams P, TileParams T, const uint64_t* __restrict__ recs, con
                 if (__popc((odd_words >> (lane & ~3u)) & ((1u << wd) - 1u)) & 1) m = ~m;  // carry from the left words
                 uint32_t nz = __ballot_sync(0xffffffffu, m != 0);
                 N* base = tile + g * (8 * TILE_C) + lane;  // word `src` of the group starts at base + src*32
-                while (nz) {
-                    const int src = __ffs(nz) - 1;
+                while (nz) {  // two mask words per step: their shared-memory round trips overlap
+                    const int src0 = __ffs(nz) - 1;
                     nz &= nz - 1;
-                    const uint32_t mw = __shfl_sync(0xffffffffu, m, src);
-                    N* p = base + src * 32;
-                    const N cur = *p;
-                    const N nv = apply_px<N, FN>(cur, v, bg);
-                    *p = ((mw >> lane) & 1u) ? nv : cur;
+                    const int src1 = nz ? __ffs(nz) - 1 : src0;
+                    const bool two = nz != 0;
+                    nz &= nz - 1;
+                    const uint32_t mw0 = __shfl_sync(0xffffffffu, m, src0);
+                    const uint32_t mw1 = __shfl_sync(0xffffffffu, m, src1);
+                    N* p0 = base + src0 * 32;
+                    N* p1 = base + src1 * 32;
+                    const N cur0 = *p0;
+                    const N cur1 = *p1;
+                    const N nv0 = apply_px<N, FN>(cur0, v, bg);
+                    const N nv1 = apply_px<N, FN>(cur1, v, bg);
+                    *p0 = ((mw0 >> lane) & 1u) ? nv0 : cur0;
+                    if (two) *p1 = ((mw1 >> lane) & 1u) ? nv1 : cur1;
                 }
             }
             __syncwarp();
