@@ -221,7 +221,10 @@ def run_b200(args):
     rows, cols = w["rows"], w["cols"]
     r0, r1 = band_of(rank, world, rows)
     bx, by, boff, bvals = select_band_polygons(x, y, off, vals, rows, r0, r1)
+    if world > 1:
+        del x, y, off, vals  # only rank 0 at N=1 needs the full set again (CPU baseline sample)
     geoms = core.Geoms.from_polygons(bx, by, boff)
+    del bx, by
     ri = core.raster_info(None, shape=(rows, cols), extent=(0.0, 0.0, float(cols), float(rows)))
     dt = np.dtype(w["dtype"])
     bg = np.nan if dt.kind == "f" else 0
