@@ -108,7 +108,7 @@ struct DeviceCtx {
     cudaStream_t stream = nullptr;
     int sm_count = 148;
     DevBuf keys_a, keys_b, hist, digit_total, task_start, part_info, field, valid, band, last_kept, counters, win_out,
-        block_total, tile_cnt, tile_off, tile_ctr, tile_px, tile_py, sp_a, sp_b, sp_c, sp_d, sp_e, sp_f, sp_g, sp_rows, sp_cols, sp_data, sp_partial;
+        block_total, vs_keys, vs_first, sp_raw, tile_cnt, tile_off, tile_ctr, tile_px, tile_py, sp_a, sp_b, sp_c, sp_d, sp_e, sp_f, sp_g, sp_rows, sp_cols, sp_data, sp_partial;
     Counters* h_counters = nullptr;  // pinned
     cudaEvent_t ev[16];
 };
@@ -839,7 +839,8 @@ namespace rz {
 
 template <typename N>
 static void sparse_expand(cudaStream_t s, const KParams& P, SparseLayout L, DeviceGeoms* dg, DeviceCtx& c, uint32_t n_rec,
-                          const uint64_t* keys, uint32_t nv_line, uint32_t nv_pt, uint32_t& launches) {
+                          const uint64_t* keys, uint32_t nv_line, uint32_t nv_pt, VisitSet vs, bool line_dedup,
+                          uint32_t& launches) {
     unsigned long long* rows = c.sp_rows.as<unsigned long long>();
     unsigned long long* cols = c.sp_cols.as<unsigned long long>();
     N* data = c.sp_data.as<N>();
@@ -855,7 +856,8 @@ static void sparse_expand(cudaStream_t s, const KParams& P, SparseLayout L, Devi
     if (nv_line) {
         line_expand_kernel<N><<<(nv_line + 255) / 256, 256, 0, s>>>(
             P, dg->x[1], dg->y[1], dg->tag[1], nv_line, info, c.last_kept.as<uint32_t>(), c.counters.as<Counters>(),
-            c.sp_c.as<unsigned long long>(), base, start, rows, cols, data);
+            c.sp_c.as<unsigned long long>(), c.sp_raw.as<unsigned long long>(), vs, line_dedup ? 1 : 0, base, start, rows, cols,
+            data);
         launches++;
     }
     if (nv_pt) {
@@ -884,10 +886,7 @@ static void rasterize_sparse(rz_geoms* g, const rz_context* ctx, rz_sparse* out,
         throw Error{RZ_RUNTIME_ERROR, "Raster dimensions above 2^31 are not supported."};
     const uint32_t nv_poly = (uint32_t)g->pool[0].size(), nv_line = (uint32_t)g->pool[1].size(),
                    nv_pt = (uint32_t)g->pool[2].size();
-    if (ri.xres != ri.yres && nv_line)
-        throw Error{RZ_RUNTIME_ERROR,
-                    "sparse encoding of line geometries on non-square pixels (per-geometry pixel dedup) is not "
-                    "implemented on the B200 path yet."};
+    const bool line_dedup = ri.xres != ri.yres && nv_line;  // burn_geometry.rs:179, 202
 
     DeviceCtx& c = device_ctx(ctx->device);
     std::lock_guard<std::mutex> lk(c.mu);
@@ -1008,6 +1007,8 @@ static void rasterize_sparse(rz_geoms* g, const rz_context* ctx, rz_sparse* out,
     }
     // ---- spans: pair the sorted crossings, prefix-sum their lengths ------------------------------
     unsigned long long poly_total = 0, line_total = 0, pt_total = 0;
+    VisitSet vs;
+    std::memset(&vs, 0, sizeof vs);
     if (n_rec) {
         c.sp_a.ensure((size_t)n_rec * 4);  // seg_start
         c.sp_b.ensure((size_t)n_rec * 8);  // poly_off
@@ -1023,14 +1024,39 @@ static void rasterize_sparse(rz_geoms* g, const rz_context* ctx, rz_sparse* out,
                                                                    c.last_kept.as<uint32_t>(), d_ctr);
         launches++;
         c.sp_c.ensure((size_t)nv_line * 8);
-        device_scan<OpAdd>(InLineLen{P, dg->x[1], dg->y[1], dg->tag[1], d_info, c.last_kept.as<uint32_t>(), d_ctr, nv_line},
-                           nv_line, OutPrefix64{c.sp_c.as<unsigned long long>()}, c.sp_partial, s, launches);
+        const InLineLen line_len{P, dg->x[1], dg->y[1], dg->tag[1], d_info, c.last_kept.as<uint32_t>(), d_ctr, nv_line};
+        device_scan<OpAdd>(line_len, nv_line, OutPrefix64{c.sp_c.as<unsigned long long>()}, c.sp_partial, s, launches);
         line_total = scan_total(c.sp_partial, nv_line, s);
         CUDA_TRY(cudaMemcpyAsync(c.h_counters, d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, s));
         CUDA_TRY(cudaStreamSynchronize(s));
         if (c.h_counters->bad_line)
             throw Error{RZ_RUNTIME_ERROR,
                         "A line segment extends more than 2^29 pixels from the raster origin; unsupported."};
+        if (line_dedup && line_total) {
+            // non-square pixels: a line part writes a pixel only on its first visit.  Burn indices come
+            // from the raw prefix; a hash set keeps the smallest one per (part,row,col); kept writes are
+            // then re-scanned.
+            unsigned long long cap = 1024;
+            while (cap < 2 * line_total) cap <<= 1;
+            c.vs_keys.ensure(cap * 8);
+            c.vs_first.ensure(cap * 8);
+            CUDA_TRY(cudaMemsetAsync(c.vs_keys.p, 0xff, cap * 8, s));
+            CUDA_TRY(cudaMemsetAsync(c.vs_first.p, 0xff, cap * 8, s));
+            vs.keys = c.vs_keys.as<unsigned long long>();
+            vs.first = c.vs_first.as<unsigned long long>();
+            vs.mask = cap - 1;
+            vs.col_bits = L.col_bits;
+            vs.row_bits = L.row_bits;
+            c.sp_raw.ensure((size_t)nv_line * 8);
+            CUDA_TRY(cudaMemcpyAsync(c.sp_raw.p, c.sp_c.p, (size_t)nv_line * 8, cudaMemcpyDeviceToDevice, s));
+            line_visit_insert_kernel<<<(nv_line + 255) / 256, 256, 0, s>>>(
+                P, dg->x[1], dg->y[1], dg->tag[1], nv_line, d_info, c.last_kept.as<uint32_t>(), d_ctr,
+                c.sp_raw.as<unsigned long long>(), vs);
+            launches++;
+            device_scan<OpAdd>(InLineKept{line_len, c.sp_raw.as<unsigned long long>(), vs}, nv_line,
+                               OutPrefix64{c.sp_c.as<unsigned long long>()}, c.sp_partial, s, launches);
+            line_total = scan_total(c.sp_partial, nv_line, s);
+        }
     }
     if (nv_pt) {
         c.sp_d.ensure((size_t)nv_pt * 8);
@@ -1069,10 +1095,10 @@ static void rasterize_sparse(rz_geoms* g, const rz_context* ctx, rz_sparse* out,
         c.sp_cols.ensure(total * 8);
         c.sp_data.ensure(total * isz);
         switch (isz) {  // triplet values are moved bit-wise: dispatch on the item size only
-            case 1: sparse_expand<uint8_t>(s, P, L, dg, c, n_rec, keys, nv_line, nv_pt, launches); break;
-            case 2: sparse_expand<uint16_t>(s, P, L, dg, c, n_rec, keys, nv_line, nv_pt, launches); break;
-            case 4: sparse_expand<uint32_t>(s, P, L, dg, c, n_rec, keys, nv_line, nv_pt, launches); break;
-            default: sparse_expand<uint64_t>(s, P, L, dg, c, n_rec, keys, nv_line, nv_pt, launches); break;
+            case 1: sparse_expand<uint8_t>(s, P, L, dg, c, n_rec, keys, nv_line, nv_pt, vs, line_dedup && line_total, launches); break;
+            case 2: sparse_expand<uint16_t>(s, P, L, dg, c, n_rec, keys, nv_line, nv_pt, vs, line_dedup && line_total, launches); break;
+            case 4: sparse_expand<uint32_t>(s, P, L, dg, c, n_rec, keys, nv_line, nv_pt, vs, line_dedup && line_total, launches); break;
+            default: sparse_expand<uint64_t>(s, P, L, dg, c, n_rec, keys, nv_line, nv_pt, vs, line_dedup && line_total, launches); break;
         }
         CUDA_TRY(cudaGetLastError());
         CUDA_TRY(cudaMemcpyAsync(out->rows.data(), c.sp_rows.p, total * 8, cudaMemcpyDeviceToHost, s));

@@ -182,6 +182,79 @@ poly_emit_sparse_kernel(KParams P, SparseLayout L, const double* __restrict__ x,
 }
 
 // ---------------------------------------------------------------------------------------------
+// line pixels in burn order + first-visit filter (PixelCache, pixel_cache.rs / writers.rs:15-36)
+// ---------------------------------------------------------------------------------------------
+// Calls f(part, row, col, j) for the j-th pixel write of segment i (clipped Bresenham run, then the
+// end pixel of the part's last kept segment when its line string is open, burners.rs:87-89).
+template <typename F>
+__device__ __forceinline__ void for_each_line_pixel(const KParams& P, const double* __restrict__ x,
+                                                    const double* __restrict__ y, const uint32_t* __restrict__ tag,
+                                                    const PartInfo* __restrict__ info,
+                                                    const uint32_t* __restrict__ last_kept, Counters* ctr, uint32_t i,
+                                                    uint32_t n, F f) {
+    LineRec l;
+    bool kept;
+    line_setup(P, x, y, tag, info, i, n, l, &kept, ctr);
+    if (!kept) return;
+    uint32_t j = 0;
+    for (uint32_t k = 0; k < l.n; k++, j++) {
+        long long px, py;
+        line_pixel(l, (long long)l.k_lo + k, px, py);
+        f(l.part, (uint32_t)py, (uint32_t)px, j);
+    }
+    if (last_kept[l.part] == i + 1 && !(tag[i] & 0x40000000u)) {
+        long long ix1 = sat_i64(floor(px_x(P, x[i + 1]))), iy1 = sat_i64(floor(px_y(P, y[i + 1])));
+        if (ix1 >= 0 && ix1 < (long long)P.ncols && iy1 >= 0 && iy1 < (long long)P.nrows)
+            f(l.part, (uint32_t)iy1, (uint32_t)ix1, j);
+    }
+}
+
+// Open-addressing hash set keyed by (part,row,col) holding the smallest burn index that wrote the
+// pixel: a write is kept iff it is that first visit (LineWriter::write, writers.rs:25-29).
+struct VisitSet {
+    unsigned long long* keys;  // ~0 = empty
+    unsigned long long* first; // smallest burn index
+    unsigned long long mask;   // capacity - 1 (power of two)
+    uint32_t col_bits, row_bits;
+    __device__ __forceinline__ unsigned long long key_of(uint32_t part, uint32_t row, uint32_t col) const {
+        return ((((unsigned long long)part << row_bits) | row) << col_bits) | col;
+    }
+    __device__ __forceinline__ unsigned long long slot_of(unsigned long long k) const {
+        k ^= k >> 33;
+        k *= 0xff51afd7ed558ccdull;
+        k ^= k >> 33;
+        k *= 0xc4ceb9fe1a85ec53ull;
+        k ^= k >> 33;
+        return k & mask;
+    }
+    __device__ __forceinline__ void insert(unsigned long long k, unsigned long long burn) const {
+        for (unsigned long long h = slot_of(k);; h = (h + 1) & mask) {
+            const unsigned long long old = atomicCAS(&keys[h], ~0ull, k);
+            if (old == ~0ull || old == k) {
+                atomicMin(&first[h], burn);
+                return;
+            }
+        }
+    }
+    __device__ __forceinline__ bool is_first(unsigned long long k, unsigned long long burn) const {
+        for (unsigned long long h = slot_of(k);; h = (h + 1) & mask)
+            if (keys[h] == k) return first[h] == burn;
+    }
+};
+
+__global__ void line_visit_insert_kernel(KParams P, const double* __restrict__ x, const double* __restrict__ y,
+                                         const uint32_t* __restrict__ tag, uint32_t n, const PartInfo* __restrict__ info,
+                                         const uint32_t* __restrict__ last_kept, Counters* __restrict__ ctr,
+                                         const unsigned long long* __restrict__ raw_off, VisitSet vs) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned long long b0 = raw_off[i];
+    for_each_line_pixel(P, x, y, tag, info, last_kept, ctr, i, n, [&](uint32_t part, uint32_t row, uint32_t col, uint32_t j) {
+        vs.insert(vs.key_of(part, row, col), b0 + j);
+    });
+}
+
+// ---------------------------------------------------------------------------------------------
 // functors for the scans
 // ---------------------------------------------------------------------------------------------
 // head position of the (part,row) segment a sorted crossing belongs to -> max-scan gives seg start
@@ -218,8 +291,7 @@ struct OutPrefix64 {
     unsigned long long* off;
     __device__ void operator()(uint32_t i, unsigned long long exclusive, unsigned long long) const { off[i] = exclusive; }
 };
-// pixel writes of line segment i (clipped Bresenham run + the end pixel of the part's last kept
-// segment when its line string is open, burners.rs:87-89)
+// pixel writes of line segment i
 struct InLineLen {
     KParams P;
     const double* x;
@@ -230,14 +302,23 @@ struct InLineLen {
     Counters* ctr;
     uint32_t n;
     __device__ unsigned long long operator()(uint32_t i) const {
-        LineRec l;
-        bool kept;
-        line_setup(P, x, y, tag, info, i, n, l, &kept, ctr);
-        unsigned long long c = l.n;
-        if (kept && last_kept[l.part] == i + 1 && !(tag[i] & 0x40000000u)) {
-            long long ix1 = sat_i64(floor(px_x(P, x[i + 1]))), iy1 = sat_i64(floor(px_y(P, y[i + 1])));
-            if (ix1 >= 0 && ix1 < (long long)P.ncols && iy1 >= 0 && iy1 < (long long)P.nrows) c++;
-        }
+        unsigned long long c = 0;
+        for_each_line_pixel(P, x, y, tag, info, last_kept, ctr, i, n, [&](uint32_t, uint32_t, uint32_t, uint32_t) { c++; });
+        return c;
+    }
+};
+// ... of which first visits of their pixel inside the part (non-square pixels)
+struct InLineKept {
+    InLineLen base;
+    const unsigned long long* raw_off;
+    VisitSet vs;
+    __device__ unsigned long long operator()(uint32_t i) const {
+        unsigned long long c = 0;
+        const unsigned long long b0 = raw_off[i];
+        for_each_line_pixel(base.P, base.x, base.y, base.tag, base.info, base.last_kept, base.ctr, i, base.n,
+                            [&](uint32_t part, uint32_t row, uint32_t col, uint32_t j) {
+                                c += vs.is_first(vs.key_of(part, row, col), b0 + j);
+                            });
         return c;
     }
 };
@@ -384,32 +465,26 @@ __global__ void __launch_bounds__(256)
 line_expand_kernel(KParams P, const double* __restrict__ x, const double* __restrict__ y,
                    const uint32_t* __restrict__ tag, uint32_t n, const PartInfo* __restrict__ info,
                    const uint32_t* __restrict__ last_kept, Counters* __restrict__ ctr,
-                   const unsigned long long* __restrict__ line_off, const unsigned long long* __restrict__ part_base,
+                   const unsigned long long* __restrict__ line_off, const unsigned long long* __restrict__ raw_off,
+                   VisitSet vs, int dedup, const unsigned long long* __restrict__ part_base,
                    const unsigned long long* __restrict__ part_start, unsigned long long* __restrict__ rows,
                    unsigned long long* __restrict__ cols, N* __restrict__ data) {
     const uint32_t i = blockIdx.x * 256 + threadIdx.x;
-    LineRec l;
-    bool kept;
-    line_setup(P, x, y, tag, info, i, n, l, &kept, ctr);
-    if (!kept) return;
-    unsigned long long d = part_base[l.part] + (line_off[i] - part_start[l.part]);
-    const N v = value_from_bits<N>(info[l.part].value_bits);
-    for (uint32_t k = 0; k < l.n; k++) {
-        long long px, py;
-        line_pixel(l, (long long)l.k_lo + k, px, py);
-        rows[d] = (unsigned long long)py;
-        cols[d] = (unsigned long long)px;
-        data[d] = v;
-        d++;
-    }
-    if (last_kept[l.part] == i + 1 && !(tag[i] & 0x40000000u)) {
-        long long ix1 = sat_i64(floor(px_x(P, x[i + 1]))), iy1 = sat_i64(floor(px_y(P, y[i + 1])));
-        if (ix1 >= 0 && ix1 < (long long)P.ncols && iy1 >= 0 && iy1 < (long long)P.nrows) {
-            rows[d] = (unsigned long long)iy1;
-            cols[d] = (unsigned long long)ix1;
-            data[d] = v;
+    if (i >= n) return;
+    unsigned long long d = 0;
+    bool have_d = false;
+    const unsigned long long b0 = dedup ? raw_off[i] : 0ull;
+    for_each_line_pixel(P, x, y, tag, info, last_kept, ctr, i, n, [&](uint32_t part, uint32_t row, uint32_t col, uint32_t j) {
+        if (!have_d) {
+            d = part_base[part] + (line_off[i] - part_start[part]);
+            have_d = true;
         }
-    }
+        if (dedup && !vs.is_first(vs.key_of(part, row, col), b0 + j)) return;
+        rows[d] = row;
+        cols[d] = col;
+        data[d] = value_from_bits<N>(info[part].value_bits);
+        d++;
+    });
 }
 
 template <typename N>

@@ -98,9 +98,22 @@ def test_small_parcels_like_config5():
     assert np.array_equal(oracle.sparse_replay(ori, got | {"data": got["data"]}, "sum", np.nan), dense, equal_nan=True)
 
 
-def test_unsupported_sparse_line_dedup_is_loud():
-    with pytest.raises(RuntimeError, match="non-square pixels"):
-        both(["LINESTRING (0 0, 4 4)"], shape=(3, 7), extent=(0, 0, 4, 4))
+def test_non_square_pixels_line_dedup_first_visits_in_burn_order():
+    # PixelCache (pixel_cache.rs, writers.rs:15-36): on non-square pixels a line part writes a pixel only
+    # the first time it visits it
+    rng = np.random.default_rng(9)
+    lines = []
+    for _ in range(80):
+        p = np.cumsum(rng.normal(0, 12, (rng.integers(2, 40), 2)), 0) + rng.random(2) * 200
+        lines.append("LINESTRING (" + ", ".join(f"{a:.3f} {b:.3f}" for a, b in p) + ")")
+    lines += ["MULTILINESTRING ((0 0, 200 200), (200 200, 0 0), (0 0, 200 200))", "LINESTRING (-500 50, 500 50, -500 50)",
+              "POLYGON ((20 20, 120 20, 120 90, 20 20))", "POINT (5 5)", "LINESTRING (10 10, 10 10)"]
+    for shape in [(97, 311), (311, 97)]:
+        exp, got, _ = both(lines, "sum", "int32", np.arange(len(lines)), 0, shape=shape, extent=(0, 0, 200, 200))
+        assert_same(exp, got)
+    exp, got, _ = both(lines, "count", "float32", 1, np.nan, by=[str(i % 3) for i in range(len(lines))],
+                       shape=(60, 250), extent=(0, 0, 200, 200))
+    assert_same(exp, got)
 
 
 def test_sparse_all_touched_is_loud():
