@@ -108,7 +108,8 @@ struct DeviceCtx {
     cudaStream_t stream = nullptr;
     int sm_count = 148;
     DevBuf keys_a, keys_b, hist, digit_total, task_start, part_info, field, valid, band, last_kept, counters, win_out,
-        block_total, vs_keys, vs_first, sp_raw, tile_cnt, tile_off, tile_ctr, tile_px, tile_py, sp_a, sp_b, sp_c, sp_d, sp_e, sp_f, sp_g, sp_rows, sp_cols, sp_data, sp_partial;
+        block_total, vs_keys, vs_first, sp_raw, tile_cnt, tile_cnt2, tile_off, tile_off2, tile_ctr, tile_px, tile_py,
+        tile_pt, tile_pairs, tile_masks, sp_a, sp_b, sp_c, sp_d, sp_e, sp_f, sp_g, sp_rows, sp_cols, sp_data, sp_partial;
     Counters* h_counters = nullptr;  // pinned
     cudaEvent_t ev[16];
 };
@@ -290,22 +291,15 @@ static unsigned long long scan_total(DevBuf& partial, uint32_t n, cudaStream_t s
 // tile-binned engine dispatch
 // ------------------------------------------------------------------------------------------------
 typedef void (*TileLaunch)(uint32_t, cudaStream_t, KParams, TileParams, const uint64_t*, const uint32_t*,
-                           const PartInfo*, const uint32_t*, const uint32_t*, const double*, const double*,
-                           const uint32_t*, uint64_t, void*);
+                           const PartInfo*, const PartTile*, const uint32_t*, uint64_t, void*);
 
 template <typename N, int FN>
 static void tile_launch(uint32_t grid, cudaStream_t s, KParams P, TileParams T, const uint64_t* recs,
-                        const uint32_t* tile_start, const PartInfo* info, const uint32_t* vbeg, const uint32_t* vend,
-                        const double* x, const double* y, const uint32_t* tag, uint64_t bg, void* out) {
+                        const uint32_t* tile_start, const PartInfo* info, const PartTile* pt, const uint32_t* masks,
+                        uint64_t bg, void* out) {
     constexpr int TR = sizeof(N) <= 4 ? 64 : 32;
     const size_t smem = (size_t)TR * TILE_C * sizeof(N);
-    static bool configured = false;  // per instantiation
-    if (!configured) {
-        CUDA_TRY(cudaFuncSetAttribute(tile_fill_kernel<N, FN, TR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
-    tile_fill_kernel<N, FN, TR><<<grid, TILE_THREADS, smem, s>>>(P, T, recs, tile_start, info, vbeg, vend, x, y, tag, bg,
-                                                               (N*)out);
+    tile_apply_kernel<N, FN, TR><<<grid, TR * 4, smem, s>>>(P, T, recs, tile_start, info, pt, masks, bg, (N*)out);
 }
 template <typename N> static TileLaunch tile_for_fn(int fn) {
     switch (fn) {
@@ -529,31 +523,42 @@ static void rasterize_dense(rz_geoms* g, const rz_context* ctx, void* out, rz_st
                 T.n_tiles = (uint32_t)n_tiles64;
                 if (timed) CUDA_TRY(cudaEventRecord(c.ev[EV_A], s));
                 c.tile_cnt.ensure((size_t)n_parts * 4);
+                c.tile_cnt2.ensure((size_t)n_parts * 4);
                 c.tile_off.ensure((size_t)n_parts * 8);
+                c.tile_off2.ensure((size_t)n_parts * 8);
+                c.tile_pt.ensure((size_t)n_parts * sizeof(PartTile));
                 c.tile_ctr.ensure(sizeof(TileCounters));
                 TileCounters* d_tc = c.tile_ctr.as<TileCounters>();
                 CUDA_TRY(cudaMemsetAsync(d_tc, 0, sizeof(TileCounters), s));
-                tile_bin_kernel<<<(n_parts + 255) / 256, 256, 0, s>>>(P, T, d_info, dg->part_xlo, dg->part_xhi, dg->part_ylo,
-                                                                      dg->part_yhi, dg->part_vbeg, dg->part_vend,
-                                                                      c.tile_cnt.as<uint32_t>(), nullptr, nullptr, d_tc, 0);
+                tile_bin_kernel<<<(n_parts + 255) / 256, 256, 0, s>>>(
+                    P, T, d_info, dg->part_xlo, dg->part_xhi, dg->part_ylo, dg->part_yhi, dg->part_vbeg, dg->part_vend,
+                    c.tile_cnt.as<uint32_t>(), c.tile_cnt2.as<uint32_t>(), nullptr, nullptr, nullptr, nullptr, nullptr,
+                    d_tc, 0);
                 launches++;
                 TileCounters h_tc;
                 CUDA_TRY(cudaMemcpyAsync(&h_tc, d_tc, sizeof h_tc, cudaMemcpyDeviceToHost, s));
                 CUDA_TRY(cudaStreamSynchronize(s));
-                // cost model: the tile engine touches every ring vertex of a part once per overlapped tile
+                // cost model: tile_mask touches every ring vertex of a part once per overlapped tile-row
+                // (and per 384-column chunk); the inside masks take 16 bytes per tile row and (part,tile) pair
+                const uint64_t mask_bytes = h_tc.pairs * T.tile_r * 16ull;
                 const bool wanted = (ctx->flags & RZ_FLAG_FORCE_TILE_ENGINE) ||
                                     h_tc.edge_visits <= 6ull * nv_poly + (1ull << 20);
-                if (wanted && h_tc.pairs < (1ull << 31)) {
-                    const uint32_t n_rec = (uint32_t)h_tc.pairs;
+                if (wanted && h_tc.pairs < (1ull << 31) && h_tc.row_pairs < (1ull << 31) && mask_bytes <= (24ull << 30)) {
+                    const uint32_t n_rec = (uint32_t)h_tc.pairs, n_rows = (uint32_t)h_tc.row_pairs;
                     device_scan<OpAdd>(InU32{c.tile_cnt.as<uint32_t>()}, n_parts,
                                        OutPrefix64{c.tile_off.as<unsigned long long>()}, c.sp_partial, s, launches);
+                    device_scan<OpAdd>(InU32{c.tile_cnt2.as<uint32_t>()}, n_parts,
+                                       OutPrefix64{c.tile_off2.as<unsigned long long>()}, c.sp_partial, s, launches);
                     c.keys_a.ensure(std::max<size_t>((size_t)n_rec * 8, 64));
                     c.keys_b.ensure(std::max<size_t>((size_t)n_rec * 8, 64));
+                    c.tile_pairs.ensure(std::max<size_t>((size_t)n_rows * 8, 64));
+                    c.tile_masks.ensure(std::max<size_t>(mask_bytes, 64));
                     uint64_t* ka = c.keys_a.as<uint64_t>();
                     uint64_t* kb = c.keys_b.as<uint64_t>();
                     tile_bin_kernel<<<(n_parts + 255) / 256, 256, 0, s>>>(
                         P, T, d_info, dg->part_xlo, dg->part_xhi, dg->part_ylo, dg->part_yhi, dg->part_vbeg, dg->part_vend,
-                        nullptr, c.tile_off.as<unsigned long long>(), ka, d_tc, 1);
+                        nullptr, nullptr, c.tile_off.as<unsigned long long>(), c.tile_off2.as<unsigned long long>(),
+                        c.tile_pt.as<PartTile>(), c.tile_pairs.as<uint64_t>(), ka, d_tc, 1);
                     launches++;
                     if (timed) CUDA_TRY(cudaEventRecord(c.ev[EV_B], s));
                     lap(emit_ms, EV_A, EV_B);
@@ -582,6 +587,34 @@ static void rasterize_dense(rz_geoms* g, const rz_context* ctx, void* out, rz_st
                     launches++;
                     if (timed) CUDA_TRY(cudaEventRecord(c.ev[EV_B], s));
                     lap(sort_ms, EV_A, EV_B);
+                    // ---- inside masks of every (part, tile) pair ----------------------------------
+                    if (timed) CUDA_TRY(cudaEventRecord(c.ev[EV_A], s));
+                    if (!tile_vertices_ready) {  // pixel-space vertices, shared by all windows of this call
+                        c.tile_px.ensure((size_t)(nv_poly + 1) * 8);
+                        c.tile_py.ensure((size_t)(nv_poly + 1) * 8);
+                        vertex_transform_kernel<<<(nv_poly + 255) / 256, 256, 0, s>>>(P, dg->x[0], dg->y[0], nv_poly,
+                                                                                     c.tile_px.as<double>(),
+                                                                                     c.tile_py.as<double>());
+                        launches++;
+                        tile_vertices_ready = true;
+                    }
+                    if (n_rows) {
+                        const uint32_t grid = (n_rows + MASK_WARPS - 1) / MASK_WARPS;
+                        if (T.tile_r == 64)
+                            tile_mask_kernel<64><<<grid, MASK_WARPS * 32, 0, s>>>(
+                                P, T, c.tile_pairs.as<uint64_t>(), n_rows, c.tile_pt.as<PartTile>(), dg->part_vbeg,
+                                dg->part_vend, c.tile_px.as<double>(), c.tile_py.as<double>(), dg->tag[0],
+                                c.tile_masks.as<uint32_t>());
+                        else
+                            tile_mask_kernel<32><<<grid, MASK_WARPS * 32, 0, s>>>(
+                                P, T, c.tile_pairs.as<uint64_t>(), n_rows, c.tile_pt.as<PartTile>(), dg->part_vbeg,
+                                dg->part_vend, c.tile_px.as<double>(), c.tile_py.as<double>(), dg->tag[0],
+                                c.tile_masks.as<uint32_t>());
+                        launches++;
+                    }
+                    if (timed) CUDA_TRY(cudaEventRecord(c.ev[EV_B], s));
+                    lap(count_ms, EV_A, EV_B);  // reported as the "count" stage slot: mask build
+                    // ---- apply ------------------------------------------------------------------------
                     if (timed) CUDA_TRY(cudaEventRecord(c.ev[EV_A], s));
                     void* d_out;
                     if (out_dev) {
@@ -595,18 +628,9 @@ static void rasterize_dense(rz_geoms* g, const rz_context* ctx, void* out, rz_st
                         T.win_row_off = 0;
                     }
                     T.vec_ok = ((uintptr_t)d_out % 16 == 0) && ((ri.ncols * isz) % 16 == 0);
-                    if (!tile_vertices_ready) {  // pixel-space vertices, shared by all windows of this call
-                        c.tile_px.ensure((size_t)(nv_poly + 1) * 8);
-                        c.tile_py.ensure((size_t)(nv_poly + 1) * 8);
-                        vertex_transform_kernel<<<(nv_poly + 255) / 256, 256, 0, s>>>(P, dg->x[0], dg->y[0], nv_poly,
-                                                                                     c.tile_px.as<double>(),
-                                                                                     c.tile_py.as<double>());
-                        launches++;
-                        tile_vertices_ready = true;
-                    }
                     tile_for(ctx->dtype, ctx->pixel_fn)(T.n_tiles, s, P, T, ka, c.task_start.as<uint32_t>(), d_info,
-                                                        dg->part_vbeg, dg->part_vend, c.tile_px.as<double>(),
-                                                        c.tile_py.as<double>(), dg->tag[0], bg_bits, d_out);
+                                                        c.tile_pt.as<PartTile>(), c.tile_masks.as<uint32_t>(), bg_bits,
+                                                        d_out);
                     launches++;
                     CUDA_TRY(cudaGetLastError());
                     if (timed) CUDA_TRY(cudaEventRecord(c.ev[EV_B], s));

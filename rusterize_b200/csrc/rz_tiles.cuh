@@ -2,30 +2,41 @@
 //
 // The crossing-record pipeline (rz_kernels.cuh) materialises one 8-byte record per scanline crossing
 // and sorts them: ~11 passes over 9 GB at BASELINE config 4.  When parts are small compared with the
-// raster, it is far cheaper to bin PARTS to 128-column x TILE_R-row tiles (a few million (tile,part)
-// records, stably sorted by tile so parts stay in burn order) and let one CTA per tile do the whole
-// scanline job in shared memory, part after part:
-//   phase 0  (once per call) every ring vertex is transformed to pixel space (edges.rs:94-97);
-//   phase 1  threads take the part's ring edges (edges.rs:27-46, 90-110), compute the crossings with
-//            the tile's rows (edges.rs:50-55) and XOR one bit per crossing into a TILE_R x 128 bit
-//            toggle mask (columns left of the tile clamp to bit 0, columns right of it are dropped);
-//   phase 2  prefix-XOR along each mask row = even-odd inside mask (== sorting + pairing the
-//            crossings, burners.rs:302-315; an odd row drops its largest column like chunks_exact);
-//   phase 3  the part's value is applied to the masked pixels with the reference's pixel-function rule
-//            (pixel_functions.rs:56-123), 32 consecutive pixels per warp step.
-// Parts are applied strictly in burn order, so every pixel function stays bit-exact, and every output
-// byte is written to HBM once.
+// raster it is far cheaper never to materialise crossings.  Parts are binned to tiles of 128 columns x
+// TILE_R rows and the scanline job is split into two embarrassingly parallel kernels:
+//
+//   vertex_transform   every ring vertex to pixel space, once per call (edges.rs:94-97).
+//   tile_bin (x2)      per part: the tile rows / tile columns its bounding box overlaps; emits the list
+//                      of (part, tile-row) pairs and the (tile, part) records (stably sorted by tile, so
+//                      every tile sees its parts in burn order).
+//   tile_mask          one WARP per (part, tile-row): takes the part's ring edges 32 at a time
+//                      (edges.rs:27-46, 90-110), computes their crossings with the tile-row's rows
+//                      (edges.rs:50-55, warp-flattened so all lanes stay busy) and XORs one bit per
+//                      crossing into a shared-memory toggle mask spanning the part's tile columns; a
+//                      prefix-XOR along each row turns it into the even-odd INSIDE mask (== sorting and
+//                      pairing the crossings, burners.rs:302-315), written to global memory as one
+//                      TILE_R x 128-bit block per (part, tile).
+//   tile_apply         one CTA per tile, tile pixels in shared memory (initialised to the background,
+//                      flushed once).  Each warp owns 8 rows and, with NO synchronisation with the other
+//                      warps, walks the tile's parts in burn order: one coalesced 128-byte load fetches
+//                      its 8 rows x 4 words of the part's inside mask, and the part's value is applied to
+//                      the masked pixels with the reference's pixel-function rule
+//                      (pixel_functions.rs:56-123), 32 consecutive pixels per step.
+//
+// Parts are applied strictly in burn order per pixel, so every pixel function stays bit-exact, and every
+// output byte is written to HBM once.
 #pragma once
 
 #include "rz_kernels.cuh"
 
 namespace rz {
 
-constexpr uint32_t TILE_C = 128;  // columns per tile = 4 mask words per row
-constexpr int TILE_THREADS = 256;
+constexpr uint32_t TILE_C = 128;        // columns per tile = 4 mask words per row
+constexpr uint32_t MASK_MAX_WORDS = 12; // tile_mask: widest toggle-mask chunk kept in shared memory (384 columns)
+constexpr int MASK_WARPS = 4;
 
 struct TileParams {
-    uint32_t tile_r;           // rows per tile
+    uint32_t tile_r;           // rows per tile (64, or 32 for 8-byte dtypes)
     uint32_t n_tc, n_tr;       // tile grid of one band in this window
     uint32_t n_tiles;          // n_bands * n_tr * n_tc
     uint32_t part_bits;
@@ -34,8 +45,16 @@ struct TileParams {
 };
 
 struct TileCounters {
-    unsigned long long pairs;        // sum over parts of tiles overlapped
-    unsigned long long edge_visits;  // sum over parts of tiles * ring vertices
+    unsigned long long pairs;        // (part, tile) pairs
+    unsigned long long row_pairs;    // (part, tile-row) pairs
+    unsigned long long edge_visits;  // sum over parts of tile-rows x column chunks x ring vertices
+};
+
+// where a part's inside-mask blocks live: block(tr, tc) = first_block + (tr - tr0) * ntc + (tc - tc0)
+struct PartTile {
+    unsigned long long first_block;
+    uint32_t tr0, tc0;
+    uint32_t ntr, ntc;
 };
 
 // pixel rows / columns a polygon part can fill, from its world extent (one pixel of margin)
@@ -53,42 +72,63 @@ __device__ __forceinline__ bool part_pixel_box(const KParams& P, double xlo, dou
     return r_hi > r_lo && c_hi > c_lo && c_lo < P.ncols;
 }
 
-// mode 0: cnt[p] = tiles overlapped by part p (+ totals); mode 1: write its records at off[p]
+// mode 0: per part the number of (part,tile) pairs and of (part,tile-row) pairs (+ totals);
+// mode 1: with the scanned offsets, fill PartTile and emit the row-pair list and the tile records.
 __global__ void tile_bin_kernel(KParams P, TileParams T, const PartInfo* __restrict__ info,
                                 const double* __restrict__ xlo, const double* __restrict__ xhi,
                                 const double* __restrict__ ylo, const double* __restrict__ yhi,
                                 const uint32_t* __restrict__ vbeg, const uint32_t* __restrict__ vend,
-                                uint32_t* __restrict__ cnt, const unsigned long long* __restrict__ off,
-                                uint64_t* __restrict__ recs, TileCounters* __restrict__ tc, int mode) {
+                                uint32_t* __restrict__ cnt_tiles, uint32_t* __restrict__ cnt_rows,
+                                const unsigned long long* __restrict__ off_tiles,
+                                const unsigned long long* __restrict__ off_rows, PartTile* __restrict__ pt,
+                                uint64_t* __restrict__ row_pairs, uint64_t* __restrict__ recs,
+                                TileCounters* __restrict__ tc, int mode) {
     const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
-    uint32_t n = 0, r_lo = 0, r_hi = 0, c_lo = 0, c_hi = 0;
-    int32_t band = -1;
+    uint32_t ntr = 0, ntc = 0, r_lo = 0, r_hi = 0, c_lo = 0, c_hi = 0;
     if (p < P.n_parts) {
-        band = info[p].band;
-        if (band >= 0 && part_pixel_box(P, xlo[p], xhi[p], ylo[p], yhi[p], r_lo, r_hi, c_lo, c_hi)) {
+        const int32_t band = info[p].band;
+        if (band >= 0 && vend[p] > vbeg[p] + 1 &&
+            part_pixel_box(P, xlo[p], xhi[p], ylo[p], yhi[p], r_lo, r_hi, c_lo, c_hi)) {
             const uint32_t tr0 = (r_lo - P.win_r0) / T.tile_r, tr1 = (r_hi - 1 - P.win_r0) / T.tile_r;
             const uint32_t tc0 = c_lo / TILE_C, tc1 = (c_hi - 1) / TILE_C;
-            n = (tr1 - tr0 + 1) * (tc1 - tc0 + 1);
+            ntr = tr1 - tr0 + 1;
+            ntc = tc1 - tc0 + 1;
             if (mode == 1) {
-                unsigned long long o = off[p];
-                for (uint32_t tr = tr0; tr <= tr1; tr++)
+                PartTile q;
+                q.first_block = off_tiles[p];
+                q.tr0 = tr0;
+                q.tc0 = tc0;
+                q.ntr = ntr;
+                q.ntc = ntc;
+                pt[p] = q;
+                unsigned long long o = off_tiles[p], orow = off_rows[p];
+                for (uint32_t tr = tr0; tr <= tr1; tr++) {
+                    row_pairs[orow++] = ((uint64_t)tr << 32) | p;
                     for (uint32_t tcol = tc0; tcol <= tc1; tcol++) {
                         const uint64_t tile = ((uint64_t)band * T.n_tr + tr) * T.n_tc + tcol;
                         recs[o++] = (tile << T.part_bits) | p;
                     }
+                }
             }
         }
     }
     if (mode == 0) {
-        if (p < P.n_parts) cnt[p] = n;
-        unsigned long long pairs = n, visits = (unsigned long long)n * (p < P.n_parts ? vend[p] - vbeg[p] : 0u);
+        if (p < P.n_parts) {
+            cnt_tiles[p] = ntr * ntc;
+            cnt_rows[p] = ntr;
+        }
+        const uint32_t chunks = (ntc * 4 + MASK_MAX_WORDS - 1) / MASK_MAX_WORDS;
+        unsigned long long pairs = (unsigned long long)ntr * ntc, rows = ntr,
+                           visits = (unsigned long long)ntr * chunks * (p < P.n_parts ? vend[p] - vbeg[p] : 0u);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             pairs += __shfl_down_sync(0xffffffffu, pairs, o);
+            rows += __shfl_down_sync(0xffffffffu, rows, o);
             visits += __shfl_down_sync(0xffffffffu, visits, o);
         }
         if (lane_id() == 0 && pairs) {
             atomicAdd(&tc->pairs, pairs);
+            atomicAdd(&tc->row_pairs, rows);
             atomicAdd(&tc->edge_visits, visits);
         }
     }
@@ -99,8 +139,8 @@ struct InU32 {
     __device__ unsigned long long operator()(uint32_t i) const { return v[i]; }
 };
 
-// World -> pixel transform of every ring vertex, once per call (edges.rs:94-97): the tile kernel visits
-// a part's edges once per overlapped tile and would otherwise repeat these four divides each time.
+// World -> pixel transform of every ring vertex, once per call (edges.rs:94-97): tile_mask visits a part's
+// edges once per tile-row and would otherwise repeat these four divides each time.
 __global__ void vertex_transform_kernel(KParams P, const double* __restrict__ x, const double* __restrict__ y,
                                         uint32_t n, double* __restrict__ px, double* __restrict__ py) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -109,10 +149,10 @@ __global__ void vertex_transform_kernel(KParams P, const double* __restrict__ x,
     py[i] = px_y(P, y[i]);
 }
 
-// One ring edge (pixel-space vertices) against the tile's rows: false when it contributes no crossing there.
+// One ring edge (pixel-space vertices) against rows [r0, r1): false when it has no crossing there.
 struct TileEdge {
     double x_top, y_top, dxdy;
-    uint32_t lo, hi;  // active rows [lo, hi) inside the tile (absolute)
+    uint32_t lo, hi;  // active rows [lo, hi) (absolute)
 };
 __device__ __forceinline__ bool tile_edge_setup(const KParams& P, const double* __restrict__ px,
                                                 const double* __restrict__ py, uint32_t i, uint32_t r0, uint32_t r1,
@@ -141,218 +181,184 @@ __device__ __forceinline__ uint32_t tile_edge_col(const KParams& P, const TileEd
     return sat_u32(floor(__dadd_rn(xi, 0.5)), P.ncols);                               // burners.rs:310-311
 }
 
+// ---------------------------------------------------------------------------------------------
+// tile_mask: one warp per (part, tile-row)
+// ---------------------------------------------------------------------------------------------
 // A row can only have an odd number of crossings when a non-horizontal edge was skipped for being
 // shorter than f64::EPSILON in y (edges.rs:100) while still straddling a pixel centre.  Pixel-centre
 // ordinates k+0.5 with k >= 1 are spaced >= EPSILON apart, so that can only happen on raster row 0
-// (centre 0.5): only that row's crossing count is tracked.
-//
-// Warp-specialised CTA, no block barrier in the main loop:
-//   producer warps          the 32-edge batches of all parts form one sequence; batch b goes to producer b%P, which bins its edges into toggle
-//                          mask slot k%8 (phase 1) and then publishes ready[slot] = k+1;
-//   consumer warps          each owns a fixed subset of the tile's 8-row groups and applies parts strictly in
-//                          order (phases 2+3) as their masks become ready, clearing the mask words it
-//                          read; the last consumer of a part frees the slot (consumed++).
-// Producers run up to 8 parts ahead of the consumers, so edge setup (f64 divides, global loads) overlaps
-// the pixel work instead of alternating with it across barriers.
-constexpr int TILE_SLOTS = 4;
-constexpr int TILE_PRODUCERS = 6;
-constexpr int TILE_CONSUMERS = 2;
+// (centre 0.5): only that row's crossing count is tracked, and an odd row 0 drops its largest column like
+// chunks_exact(2) drops the unpaired tail (burners.rs:305).
+template <int TILE_R>
+__global__ void __launch_bounds__(MASK_WARPS * 32)
+tile_mask_kernel(KParams P, TileParams T, const uint64_t* __restrict__ row_pairs, uint32_t n_row_pairs,
+                 const PartTile* __restrict__ pt, const uint32_t* __restrict__ vbeg, const uint32_t* __restrict__ vend,
+                 const double* __restrict__ px, const double* __restrict__ py, const uint32_t* __restrict__ tag,
+                 uint32_t* __restrict__ masks) {
+    __shared__ uint32_t s_mask[MASK_WARPS][TILE_R][MASK_MAX_WORDS];
+    __shared__ double s_xt[MASK_WARPS][32], s_yt[MASK_WARPS][32], s_dx[MASK_WARPS][32];
+    __shared__ uint32_t s_pre[MASK_WARPS][32], s_lo[MASK_WARPS][32];
+    const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
+    const uint32_t pair = blockIdx.x * MASK_WARPS + warp;
+    if (pair >= n_row_pairs) return;
+    const uint64_t rp = row_pairs[pair];
+    const uint32_t part = (uint32_t)rp, tr = (uint32_t)(rp >> 32);
+    const PartTile q = pt[part];
+    const uint32_t vb = vbeg[part], ve = vend[part];
+    const uint32_t r0 = P.win_r0 + tr * TILE_R, r1 = min(r0 + TILE_R, P.win_r1);
+    uint32_t(*mask)[MASK_MAX_WORDS] = s_mask[warp];
+    const uint32_t words_total = q.ntc * 4;
 
-__device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t* p) { return *reinterpret_cast<const volatile uint32_t*>(p); }
-__device__ __forceinline__ void st_volatile_u32(uint32_t* p, uint32_t v) { *reinterpret_cast<volatile uint32_t*>(p) = v; }
-
-template <typename N, int FN, int TILE_R>
-__global__ void __launch_bounds__(TILE_THREADS, 5)
-tile_fill_kernel(KParams P, TileParams T, const uint64_t* __restrict__ recs, const uint32_t* __restrict__ tile_start,
-                 const PartInfo* __restrict__ info, const uint32_t* __restrict__ vbeg, const uint32_t* __restrict__ vend,
-                 const double* __restrict__ x, const double* __restrict__ y, const uint32_t* __restrict__ tag,
-                 uint64_t bg_bits, N* __restrict__ out) {
-    static_assert(TILE_THREADS == 32 * (TILE_PRODUCERS + TILE_CONSUMERS), "role split");
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    N* tile = reinterpret_cast<N*>(smem_raw);  // [TILE_R][TILE_C]
-    __shared__ uint32_t s_mask[TILE_SLOTS][TILE_R][4];
-    __shared__ unsigned long long s_val[TILE_SLOTS];
-    __shared__ uint32_t s_ready[TILE_SLOTS], s_done[TILE_SLOTS], s_cnt[TILE_SLOTS], s_par0[TILE_SLOTS], s_consumed;
-    __shared__ double s_xt[TILE_PRODUCERS][32], s_yt[TILE_PRODUCERS][32], s_dx[TILE_PRODUCERS][32];
-    __shared__ uint32_t s_pre[TILE_PRODUCERS][32], s_lo[TILE_PRODUCERS][32];
-    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-    const N bg = value_from_bits<N>(bg_bits);
-    const uint64_t part_mask = (1ull << T.part_bits) - 1ull;
-
-    const uint32_t t = blockIdx.x;
-    const uint32_t tcol = t % T.n_tc, trow = (t / T.n_tc) % T.n_tr, band = t / (T.n_tc * T.n_tr);
-    const uint32_t r0 = P.win_r0 + trow * TILE_R, r1 = min(r0 + TILE_R, P.win_r1);
-    const uint32_t c0 = tcol * TILE_C, c1 = min(c0 + TILE_C, P.ncols);
-    const uint32_t beg = tile_start[t], n_parts_here = tile_start[t + 1] - beg;
-
-    for (uint32_t i = tid; i < TILE_R * TILE_C; i += TILE_THREADS) tile[i] = bg;  // geo/raster.rs:23-28
-    if (n_parts_here) {
-        for (uint32_t i = tid; i < TILE_SLOTS * TILE_R * 4; i += TILE_THREADS) (&s_mask[0][0][0])[i] = 0;
-        if (tid < TILE_SLOTS) {
-            s_ready[tid] = 0;
-            s_done[tid] = 0;
-            s_cnt[tid] = 0;
-            s_par0[tid] = 0;
-        }
-        if (tid == 0) s_consumed = 0;
-    }
-    __syncthreads();
-
-    if (n_parts_here && warp < TILE_PRODUCERS) {
-        // ================= producers: phase 1, one 32-edge batch at a time =================
-        // Batches of all parts form one sequence; batch b goes to producer b % TILE_PRODUCERS, so the
-        // edges of one part are binned by several warps at once and parts overlap in a pipeline.
-        uint32_t b_first = 0;  // sequence number of the part's first batch
-        for (uint32_t k = 0; k < n_parts_here; k++) {
-            const uint32_t slot = k % TILE_SLOTS;
-            const uint32_t part = (uint32_t)(recs[beg + k] & part_mask);
-            const uint32_t vb = vbeg[part], ve = vend[part];
-            const uint32_t n_edges = ve > vb ? ve - vb - 1 : 0u;
-            const uint32_t nb = max(1u, (n_edges + 31) / 32);
-            uint32_t(*mask)[4] = s_mask[slot];
-            // first batch of this part that belongs to this warp
-            uint32_t j = (warp + TILE_PRODUCERS - b_first % TILE_PRODUCERS) % TILE_PRODUCERS;
-            b_first += nb;
-            if (j >= nb) continue;
-            while (k >= ld_volatile_u32(&s_consumed) + TILE_SLOTS) __nanosleep(64);  // slot still in use
+    for (uint32_t w0 = 0; w0 < words_total; w0 += MASK_MAX_WORDS) {  // one pass per 384-column chunk
+        const uint32_t nw = min(MASK_MAX_WORDS, words_total - w0);
+        const uint32_t c0 = q.tc0 * TILE_C + w0 * 32;                 // first pixel column of the chunk
+        const uint32_t c1 = min(c0 + nw * 32, P.ncols);
+        for (uint32_t i = lane; i < TILE_R * MASK_MAX_WORDS; i += 32) (&mask[0][0])[i] = 0;
+        __syncwarp();
+        uint32_t par0 = 0;  // this lane's share of the row-0 crossing count parity
+        for (uint32_t i0 = vb; i0 + 1 < ve; i0 += 32) {
+            const uint32_t i = i0 + lane;
+            TileEdge e;
+            uint32_t cnt = 0;
+            if (i + 1 < ve && !(tag[i] & 0x80000000u) && tile_edge_setup(P, px, py, i, r0, r1, e)) cnt = e.hi - e.lo;
+            uint32_t inc = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t up = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= (uint32_t)o) inc += up;
+            }
+            const uint32_t wtot = __shfl_sync(0xffffffffu, inc, 31);
+            if (wtot == 0) continue;
+            s_pre[warp][lane] = inc - cnt;
+            if (cnt) {
+                s_xt[warp][lane] = e.x_top;
+                s_yt[warp][lane] = e.y_top;
+                s_dx[warp][lane] = e.dxdy;
+                s_lo[warp][lane] = e.lo;
+            }
             __syncwarp();
-            for (; j < nb; j += TILE_PRODUCERS) {
-                const uint32_t i = vb + j * 32 + lane;
+            for (uint32_t k = lane; k < wtot; k += 32) {  // all lanes share the 32 edges' crossings evenly
+                uint32_t lo = 0, hi = 32;                 // last edge whose first crossing is <= k
+#pragma unroll
+                for (int it = 0; it < 5; it++) {
+                    const uint32_t mid = (lo + hi) >> 1;
+                    if (s_pre[warp][mid] <= k) lo = mid;
+                    else hi = mid;
+                }
+                TileEdge b;
+                b.x_top = s_xt[warp][lo];
+                b.y_top = s_yt[warp][lo];
+                b.dxdy = s_dx[warp][lo];
+                const uint32_t row = s_lo[warp][lo] + (k - s_pre[warp][lo]);
+                const uint32_t col = tile_edge_col(P, b, row);
+                par0 ^= (row == 0);
+                if (col < c1) {  // a crossing right of the chunk has no effect on its pixels
+                    const uint32_t rel = col <= c0 ? 0u : col - c0;  // left of it: parity carry-in at bit 0
+                    atomicXor(&mask[row - r0][rel >> 5], 1u << (rel & 31));
+                }
+            }
+            __syncwarp();
+        }
+        if (r0 == 0 && (__popc(__ballot_sync(0xffffffffu, par0 & 1u)) & 1)) {  // rare: odd row 0
+            uint32_t mx = 0;
+            for (uint32_t i = vb + lane; i + 1 < ve; i += 32) {
+                if (tag[i] & 0x80000000u) continue;
                 TileEdge e;
-                uint32_t cnt = 0;
-                if (i + 1 < ve && !(tag[i] & 0x80000000u) && tile_edge_setup(P, x, y, i, r0, r1, e)) cnt = e.hi - e.lo;
-                uint32_t inc = cnt;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const uint32_t up = __shfl_up_sync(0xffffffffu, inc, o);
-                    if (lane >= (uint32_t)o) inc += up;
-                }
-                const uint32_t wtot = __shfl_sync(0xffffffffu, inc, 31);
-                uint32_t par0 = 0;  // this lane's share of the row-0 crossing count parity
-                if (wtot) {
-                    s_pre[warp][lane] = inc - cnt;
-                    if (cnt) {
-                        s_xt[warp][lane] = e.x_top;
-                        s_yt[warp][lane] = e.y_top;
-                        s_dx[warp][lane] = e.dxdy;
-                        s_lo[warp][lane] = e.lo;
-                    }
-                    __syncwarp();
-                    for (uint32_t q = lane; q < wtot; q += 32) {
-                        uint32_t lo = 0, hi = 32;  // last edge whose first crossing is <= q
-#pragma unroll
-                        for (int it = 0; it < 5; it++) {
-                            const uint32_t mid = (lo + hi) >> 1;
-                            if (s_pre[warp][mid] <= q) lo = mid;
-                            else hi = mid;
-                        }
-                        TileEdge eb;
-                        eb.x_top = s_xt[warp][lo];
-                        eb.y_top = s_yt[warp][lo];
-                        eb.dxdy = s_dx[warp][lo];
-                        const uint32_t row = s_lo[warp][lo] + (q - s_pre[warp][lo]);
-                        const uint32_t col = tile_edge_col(P, eb, row);
-                        par0 ^= (row == 0);
-                        if (col < c1) {  // right of the tile: no effect on its pixels
-                            const uint32_t rel = col <= c0 ? 0u : col - c0;
-                            atomicXor(&mask[row - r0][rel >> 5], 1u << (rel & 31));
-                        }
-                    }
-                }
-                const uint32_t odd = __popc(__ballot_sync(0xffffffffu, par0 & 1u)) & 1u;
-                __threadfence_block();
-                uint32_t fin = 0;
-                if (lane == 0) {
-                    if (odd) atomicXor(&s_par0[slot], 1u);
-                    fin = atomicAdd(&s_cnt[slot], 1u) + 1u;
-                }
-                fin = __shfl_sync(0xffffffffu, fin, 0);
-                if (fin == nb) {  // this warp finished the part's last outstanding batch
-                    __threadfence_block();
-                    // rare: an odd row 0 drops its largest column (chunks_exact(2), burners.rs:305)
-                    if (r0 == 0 && ld_volatile_u32(&s_par0[slot])) {
-                        uint32_t mx = 0;
-                        for (uint32_t ii = vb + lane; ii + 1 < ve; ii += 32) {
-                            if (tag[ii] & 0x80000000u) continue;
-                            TileEdge e0;
-                            if (tile_edge_setup(P, x, y, ii, 0, 1, e0)) mx = max(mx, tile_edge_col(P, e0, 0) + 1u);
-                        }
-                        mx = __reduce_max_sync(0xffffffffu, mx);
-                        if (lane == 0 && mx && mx - 1 < c1) {
-                            const uint32_t rel = mx - 1 <= c0 ? 0u : mx - 1 - c0;
-                            atomicXor(&mask[0][rel >> 5], 1u << (rel & 31));
-                        }
-                    }
-                    if (lane == 0) {
-                        s_par0[slot] = 0;
-                        s_cnt[slot] = 0;
-                        s_val[slot] = info[part].value_bits;
-                        __threadfence_block();
-                        st_volatile_u32(&s_ready[slot], k + 1);
-                    }
-                }
-                __syncwarp();
+                if (tile_edge_setup(P, px, py, i, 0, 1, e)) mx = max(mx, tile_edge_col(P, e, 0) + 1u);
+            }
+            mx = __reduce_max_sync(0xffffffffu, mx);
+            if (lane == 0 && mx && mx - 1 < c1) {
+                const uint32_t rel = mx - 1 <= c0 ? 0u : mx - 1 - c0;
+                mask[0][rel >> 5] ^= 1u << (rel & 31);
             }
         }
-    } else if (n_parts_here) {
-        // ================= consumer: phases 2+3 on its own rows =================
-        const uint32_t cw = warp - TILE_PRODUCERS;
-        for (uint32_t k = 0; k < n_parts_here; k++) {
-            const uint32_t slot = k % TILE_SLOTS;
-            while (ld_volatile_u32(&s_ready[slot]) != k + 1) __nanosleep(32);
-            __syncwarp();
-            __threadfence_block();
-            const N v = value_from_bits<N>(*reinterpret_cast<volatile unsigned long long*>(&s_val[slot]));
-            uint32_t(*mask)[4] = s_mask[slot];
-            for (uint32_t g = cw; g < TILE_R / 8; g += TILE_CONSUMERS) {  // this consumer's 8-row groups
-                const uint32_t rr = g * 8 + (lane >> 2), wd = lane & 3u;
-                const uint32_t tg = *reinterpret_cast<volatile uint32_t*>(&mask[rr][wd]);
-                if (__ballot_sync(0xffffffffu, tg != 0) == 0) continue;  // part does not reach these rows
-                mask[rr][wd] = 0;
-                uint32_t m = tg;
+        __syncwarp();
+        // toggle mask -> inside mask, row by row (one lane per row), in place
+        for (uint32_t rr = lane; rr < TILE_R; rr += 32) {
+            uint32_t carry = 0;
+            for (uint32_t wd = 0; wd < nw; wd++) {
+                uint32_t m = mask[rr][wd];
                 m ^= m << 1;
                 m ^= m << 2;
                 m ^= m << 4;
                 m ^= m << 8;
                 m ^= m << 16;
-                const uint32_t odd_words = __ballot_sync(0xffffffffu, __popc(tg) & 1);
-                if (__popc((odd_words >> (lane & ~3u)) & ((1u << wd) - 1u)) & 1) m = ~m;  // carry from the left words
-                uint32_t nz = __ballot_sync(0xffffffffu, m != 0);
-                N* base = tile + g * (8 * TILE_C) + lane;  // word `src` of the group starts at base + src*32
-                while (nz) {  // two mask words per step: their shared-memory round trips overlap
-                    const int src0 = __ffs(nz) - 1;
-                    nz &= nz - 1;
-                    const int src1 = nz ? __ffs(nz) - 1 : src0;
-                    const bool two = nz != 0;
-                    nz &= nz - 1;
-                    const uint32_t mw0 = __shfl_sync(0xffffffffu, m, src0);
-                    const uint32_t mw1 = __shfl_sync(0xffffffffu, m, src1);
-                    N* p0 = base + src0 * 32;
-                    N* p1 = base + src1 * 32;
-                    const N cur0 = *p0;
-                    const N cur1 = *p1;
-                    const N nv0 = apply_px<N, FN>(cur0, v, bg);
-                    const N nv1 = apply_px<N, FN>(cur1, v, bg);
-                    *p0 = ((mw0 >> lane) & 1u) ? nv0 : cur0;
-                    if (two) *p1 = ((mw1 >> lane) & 1u) ? nv1 : cur1;
-                }
-            }
-            __syncwarp();
-            __threadfence_block();
-            if (lane == 0 && atomicAdd(&s_done[slot], 1u) == TILE_CONSUMERS - 1) {
-                s_done[slot] = 0;
-                __threadfence_block();
-                atomicAdd(&s_consumed, 1u);  // the slot may be reused by part k + TILE_SLOTS
+                m ^= carry;
+                carry = (m >> 31) ? 0xffffffffu : 0u;
+                mask[rr][wd] = m;
             }
         }
+        __syncwarp();
+        // one TILE_R x 4-word block per (part, tile): consecutive lanes write consecutive words
+        const unsigned long long row_base = q.first_block + (unsigned long long)(tr - q.tr0) * q.ntc;
+        for (uint32_t tcl = 0; tcl * 4 < nw; tcl++) {
+            uint32_t* dst = masks + (row_base + w0 / 4 + tcl) * (TILE_R * 4);
+            for (uint32_t i = lane; i < TILE_R * 4; i += 32) dst[i] = mask[i >> 2][tcl * 4 + (i & 3)];
+        }
+        __syncwarp();
     }
-    __syncthreads();
+}
+
+// ---------------------------------------------------------------------------------------------
+// tile_apply: one CTA per tile, each warp owns 8 rows, no synchronisation between warps
+// ---------------------------------------------------------------------------------------------
+template <typename N, int FN, int TILE_R>
+__global__ void __launch_bounds__(TILE_R * 4)
+tile_apply_kernel(KParams P, TileParams T, const uint64_t* __restrict__ recs, const uint32_t* __restrict__ tile_start,
+                  const PartInfo* __restrict__ info, const PartTile* __restrict__ pt,
+                  const uint32_t* __restrict__ masks, uint64_t bg_bits, N* __restrict__ out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
+    N* rows8 = reinterpret_cast<N*>(smem_raw) + (size_t)warp * 8 * TILE_C;  // this warp's 8 rows x 128 columns
+    const N bg = value_from_bits<N>(bg_bits);
+    const uint64_t part_mask = (1ull << T.part_bits) - 1ull;
+
+    const uint32_t t = blockIdx.x;
+    const uint32_t tcol = t % T.n_tc, trow = (t / T.n_tc) % T.n_tr, band = t / (T.n_tc * T.n_tr);
+    const uint32_t r0 = P.win_r0 + trow * TILE_R + warp * 8;
+    if (r0 >= P.win_r1) return;
+    const uint32_t r1 = min(r0 + 8, P.win_r1);
+    const uint32_t c0 = tcol * TILE_C, c1 = min(c0 + TILE_C, P.ncols);
+
+    for (uint32_t i = lane; i < 8 * TILE_C; i += 32) rows8[i] = bg;  // geo/raster.rs:23-28
+    __syncwarp();
+
+    const uint32_t beg = tile_start[t], end = tile_start[t + 1];
+    N* base = rows8 + lane;
+    for (uint32_t rec = beg; rec < end; rec++) {
+        const uint32_t part = (uint32_t)(recs[rec] & part_mask);
+        const PartTile q = pt[part];
+        const unsigned long long blk = q.first_block + (unsigned long long)(trow - q.tr0) * q.ntc + (tcol - q.tc0);
+        // lane = (row in this warp's group, mask word): one coalesced 128-byte load
+        const uint32_t m = masks[blk * (TILE_R * 4) + warp * 32 + lane];
+        uint32_t nz = __ballot_sync(0xffffffffu, m != 0);
+        if (nz == 0) continue;  // the part does not reach these 8 rows
+        const N v = value_from_bits<N>(info[part].value_bits);
+        while (nz) {  // two mask words per step: their shared-memory round trips overlap
+            const int src0 = __ffs(nz) - 1;
+            nz &= nz - 1;
+            const int src1 = nz ? __ffs(nz) - 1 : src0;
+            const bool two = nz != 0;
+            nz &= nz - 1;
+            const uint32_t mw0 = __shfl_sync(0xffffffffu, m, src0);
+            const uint32_t mw1 = __shfl_sync(0xffffffffu, m, src1);
+            N* p0 = base + src0 * 32;  // word `src` of the group covers rows8[src*32 .. src*32+31]
+            N* p1 = base + src1 * 32;
+            const N cur0 = *p0;
+            const N cur1 = *p1;
+            const N nv0 = apply_px<N, FN>(cur0, v, bg);
+            const N nv1 = apply_px<N, FN>(cur1, v, bg);
+            *p0 = ((mw0 >> lane) & 1u) ? nv0 : cur0;
+            if (two) *p1 = ((mw1 >> lane) & 1u) ? nv1 : cur1;
+        }
+        __syncwarp();
+    }
 
     // ---- flush: every output byte is written exactly once ---------------------------------------------
     const uint32_t cols = c1 - c0;
-    for (uint32_t rr = warp; rr < r1 - r0; rr += TILE_THREADS / 32) {
+    for (uint32_t rr = 0; rr < r1 - r0; rr++) {
         N* dst = out + ((size_t)band * T.out_rows + T.win_row_off + (r0 - P.win_r0) + rr) * P.ncols + c0;
-        const N* src = tile + rr * TILE_C;
+        const N* src = rows8 + rr * TILE_C;
         if (T.vec_ok && cols == TILE_C) {
             const uint4* s4 = reinterpret_cast<const uint4*>(src);
             uint4* d4 = reinterpret_cast<uint4*>(dst);
