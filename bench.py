@@ -302,11 +302,19 @@ def run_b200(args):
     peak, peak_src = peaks()
     s0 = stats[-1]
     fill_ms = float(np.mean([s["fill_ms"] for s in stats]))
+    other = None
     if s0["engine"] == 1:
-        # tile engine: the kernel fuses edge setup, crossing binning and fill: every ring vertex of the
-        # band (x, y f64 + u32 tag) read once + (tile,part) records + raster written once
-        kernel = "tile_fill_kernel<%s, %s>" % (w["dtype"], w["fun"])
-        fill_bytes = 20.0 * s0["n_poly_vertices"] + 8.0 * s0["n_records"] + s0["out_bytes"]
+        # tile engine, span-fill kernel = tile_apply: inside-mask blocks (tile_r rows x 16 B) + record + value
+        # per (part,tile) pair read once, raster written once
+        tile_r = 64 if dt.itemsize <= 4 else 32
+        kernel = "tile_apply_kernel<%s, %s, %d>" % (w["dtype"], w["fun"], tile_r)
+        fill_bytes = s0["n_records"] * (tile_r * 16.0 + 16.0) + s0["out_bytes"]
+        mask_ms = float(np.mean([s["count_ms"] for s in stats]))
+        # tile_mask: pixel-space vertices (16 B) + tags (4 B) read once, mask blocks written once
+        mask_bytes = 20.0 * s0["n_poly_vertices"] + s0["n_records"] * tile_r * 16.0
+        other = {"kernel": "tile_mask_kernel<%d> (+ vertex_transform)" % tile_r, "ms_per_launch": mask_ms,
+                 "bytes_per_launch": mask_bytes, "achieved": mask_bytes / (mask_ms / 1e3) / 1e9,
+                 "frac": mask_bytes / (mask_ms / 1e3) / 1e9 / peak, "note": "instruction-issue bound (f64 edge math)"}
     else:
         # record pipeline: crossing records read once + raster written once
         kernel = "fill_kernel<%s, %s>" % (w["dtype"], w["fun"])
@@ -348,12 +356,13 @@ def run_b200(args):
                    "l2": "inputs (vertex pools + record buffers + raster) are far larger than the 126 MB L2",
                    "engine": "tile-binned" if s0["engine"] == 1 else "crossing-records"},
         "polygons_per_s": w["n"] / (ms_max / 1e3),
-        "stage_ms_max_over_ranks": dict(zip(["count", "emit", "sort", "index", "fill"], [float(v) for v in stage])),
+        "stage_ms_max_over_ranks": dict(zip(["mask_build" if s0["engine"] == 1 else "count", "emit", "sort", "index", "fill"],
+                                            [float(v) for v in stage])),
         "records": int(agg[0].item()), "crossings": int(agg[1].item()),
         "gpu_launches": int(round(agg[3].item())) * args.steps,
         "roofline": {"bound": "hbm", "kernel": kernel, "achieved": achieved, "peak": peak,
                      "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                     "bytes_per_launch": fill_bytes, "ms_per_launch": fill_ms},
+                     "bytes_per_launch": fill_bytes, "ms_per_launch": fill_ms, "second_kernel": other},
         "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
     }
     print(json.dumps(line))

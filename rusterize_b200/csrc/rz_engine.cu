@@ -109,7 +109,7 @@ struct DeviceCtx {
     int sm_count = 148;
     DevBuf keys_a, keys_b, hist, digit_total, task_start, part_info, field, valid, band, last_kept, counters, win_out,
         block_total, vs_keys, vs_first, sp_raw, tile_cnt, tile_cnt2, tile_off, tile_off2, tile_ctr, tile_px, tile_py,
-        tile_pt, tile_pairs, tile_masks, sp_a, sp_b, sp_c, sp_d, sp_e, sp_f, sp_g, sp_rows, sp_cols, sp_data, sp_partial;
+        tile_pt, tile_pairs, tile_masks, tile_val, sp_a, sp_b, sp_c, sp_d, sp_e, sp_f, sp_g, sp_rows, sp_cols, sp_data, sp_partial;
     Counters* h_counters = nullptr;  // pinned
     cudaEvent_t ev[16];
 };
@@ -291,15 +291,16 @@ static unsigned long long scan_total(DevBuf& partial, uint32_t n, cudaStream_t s
 // tile-binned engine dispatch
 // ------------------------------------------------------------------------------------------------
 typedef void (*TileLaunch)(uint32_t, cudaStream_t, KParams, TileParams, const uint64_t*, const uint32_t*,
-                           const PartInfo*, const PartTile*, const uint32_t*, uint64_t, void*);
+                           const unsigned long long*, uint32_t, const uint32_t*, uint64_t, void*);
 
 template <typename N, int FN>
 static void tile_launch(uint32_t grid, cudaStream_t s, KParams P, TileParams T, const uint64_t* recs,
-                        const uint32_t* tile_start, const PartInfo* info, const PartTile* pt, const uint32_t* masks,
-                        uint64_t bg, void* out) {
+                        const uint32_t* tile_start, const unsigned long long* block_value, uint32_t block_bits,
+                        const uint32_t* masks, uint64_t bg, void* out) {
     constexpr int TR = sizeof(N) <= 4 ? 64 : 32;
     const size_t smem = (size_t)TR * TILE_C * sizeof(N);
-    tile_apply_kernel<N, FN, TR><<<grid, TR * 4, smem, s>>>(P, T, recs, tile_start, info, pt, masks, bg, (N*)out);
+    tile_apply_kernel<N, FN, TR><<<grid, TR * 4, smem, s>>>(P, T, recs, tile_start, block_value, block_bits, masks, bg,
+                                                            (N*)out);
 }
 template <typename N> static TileLaunch tile_for_fn(int fn) {
     switch (fn) {
@@ -519,7 +520,7 @@ static void rasterize_dense(rz_geoms* g, const rz_context* ctx, void* out, rz_st
             T.n_tr = (rows + T.tile_r - 1) / T.tile_r;
             const uint64_t n_tiles64 = (uint64_t)n_bands * T.n_tr * T.n_tc;
             T.part_bits = P.part_bits;
-            if (n_tiles64 < (1ull << 31) && bits_for(n_tiles64) + T.part_bits <= 64) {
+            if (n_tiles64 < (1ull << 31)) {  // record = [tile | block], both below 2^31
                 T.n_tiles = (uint32_t)n_tiles64;
                 if (timed) CUDA_TRY(cudaEventRecord(c.ev[EV_A], s));
                 c.tile_cnt.ensure((size_t)n_parts * 4);
@@ -533,7 +534,7 @@ static void rasterize_dense(rz_geoms* g, const rz_context* ctx, void* out, rz_st
                 tile_bin_kernel<<<(n_parts + 255) / 256, 256, 0, s>>>(
                     P, T, d_info, dg->part_xlo, dg->part_xhi, dg->part_ylo, dg->part_yhi, dg->part_vbeg, dg->part_vend,
                     c.tile_cnt.as<uint32_t>(), c.tile_cnt2.as<uint32_t>(), nullptr, nullptr, nullptr, nullptr, nullptr,
-                    d_tc, 0);
+                    nullptr, 0, d_tc, 0);
                 launches++;
                 TileCounters h_tc;
                 CUDA_TRY(cudaMemcpyAsync(&h_tc, d_tc, sizeof h_tc, cudaMemcpyDeviceToHost, s));
@@ -553,22 +554,25 @@ static void rasterize_dense(rz_geoms* g, const rz_context* ctx, void* out, rz_st
                     c.keys_b.ensure(std::max<size_t>((size_t)n_rec * 8, 64));
                     c.tile_pairs.ensure(std::max<size_t>((size_t)n_rows * 8, 64));
                     c.tile_masks.ensure(std::max<size_t>(mask_bytes, 64));
+                    c.tile_val.ensure(std::max<size_t>((size_t)n_rec * 8, 64));
+                    const uint32_t block_bits = std::max(1u, bits_for(std::max<uint64_t>(n_rec, 1)));
                     uint64_t* ka = c.keys_a.as<uint64_t>();
                     uint64_t* kb = c.keys_b.as<uint64_t>();
                     tile_bin_kernel<<<(n_parts + 255) / 256, 256, 0, s>>>(
                         P, T, d_info, dg->part_xlo, dg->part_xhi, dg->part_ylo, dg->part_yhi, dg->part_vbeg, dg->part_vend,
                         nullptr, nullptr, c.tile_off.as<unsigned long long>(), c.tile_off2.as<unsigned long long>(),
-                        c.tile_pt.as<PartTile>(), c.tile_pairs.as<uint64_t>(), ka, d_tc, 1);
+                        c.tile_pt.as<PartTile>(), c.tile_pairs.as<uint64_t>(), ka, c.tile_val.as<unsigned long long>(),
+                        block_bits, d_tc, 1);
                     launches++;
                     if (timed) CUDA_TRY(cudaEventRecord(c.ev[EV_B], s));
                     lap(emit_ms, EV_A, EV_B);
                     if (timed) CUDA_TRY(cudaEventRecord(c.ev[EV_A], s));
-                    const uint32_t tkey_bits = T.part_bits + bits_for(n_tiles64);
+                    const uint32_t tkey_bits = block_bits + bits_for(n_tiles64);
                     if (n_rec > 1) {  // records are in part order: a stable sort on the tile bits keeps burn order
                         const uint32_t n_blocks = (n_rec + RS_TILE - 1) / RS_TILE;
                         c.hist.ensure((size_t)n_blocks * RS_RADIX * 4);
                         c.digit_total.ensure(RS_RADIX * 4);
-                        for (uint32_t shift = T.part_bits; shift < tkey_bits; shift += 8) {
+                        for (uint32_t shift = block_bits; shift < tkey_bits; shift += 8) {
                             radix_hist_kernel<<<n_blocks, RS_THREADS, 0, s>>>(ka, n_rec, shift, n_blocks,
                                                                               c.hist.as<uint32_t>());
                             radix_scan_rows_kernel<<<RS_RADIX, 1024, 0, s>>>(c.hist.as<uint32_t>(), n_blocks,
@@ -582,7 +586,7 @@ static void rasterize_dense(rz_geoms* g, const rz_context* ctx, void* out, rz_st
                         }
                     }
                     c.task_start.ensure(((size_t)T.n_tiles + 1) * 4);
-                    task_index_kernel<<<(T.n_tiles + 1 + 255) / 256, 256, 0, s>>>(ka, n_rec, T.part_bits, T.n_tiles,
+                    task_index_kernel<<<(T.n_tiles + 1 + 255) / 256, 256, 0, s>>>(ka, n_rec, block_bits, T.n_tiles,
                                                                                 c.task_start.as<uint32_t>());
                     launches++;
                     if (timed) CUDA_TRY(cudaEventRecord(c.ev[EV_B], s));
@@ -628,9 +632,9 @@ static void rasterize_dense(rz_geoms* g, const rz_context* ctx, void* out, rz_st
                         T.win_row_off = 0;
                     }
                     T.vec_ok = ((uintptr_t)d_out % 16 == 0) && ((ri.ncols * isz) % 16 == 0);
-                    tile_for(ctx->dtype, ctx->pixel_fn)(T.n_tiles, s, P, T, ka, c.task_start.as<uint32_t>(), d_info,
-                                                        c.tile_pt.as<PartTile>(), c.tile_masks.as<uint32_t>(), bg_bits,
-                                                        d_out);
+                    tile_for(ctx->dtype, ctx->pixel_fn)(T.n_tiles, s, P, T, ka, c.task_start.as<uint32_t>(),
+                                                        c.tile_val.as<unsigned long long>(), block_bits,
+                                                        c.tile_masks.as<uint32_t>(), bg_bits, d_out);
                     launches++;
                     CUDA_TRY(cudaGetLastError());
                     if (timed) CUDA_TRY(cudaEventRecord(c.ev[EV_B], s));

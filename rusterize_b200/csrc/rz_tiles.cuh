@@ -73,7 +73,8 @@ __device__ __forceinline__ bool part_pixel_box(const KParams& P, double xlo, dou
 }
 
 // mode 0: per part the number of (part,tile) pairs and of (part,tile-row) pairs (+ totals);
-// mode 1: with the scanned offsets, fill PartTile and emit the row-pair list and the tile records.
+// mode 1: with the scanned offsets, fill PartTile and emit the row-pair list and the tile records
+// [tile | block], block = index of the (part,tile) pair's inside-mask block.
 __global__ void tile_bin_kernel(KParams P, TileParams T, const PartInfo* __restrict__ info,
                                 const double* __restrict__ xlo, const double* __restrict__ xhi,
                                 const double* __restrict__ ylo, const double* __restrict__ yhi,
@@ -82,6 +83,7 @@ __global__ void tile_bin_kernel(KParams P, TileParams T, const PartInfo* __restr
                                 const unsigned long long* __restrict__ off_tiles,
                                 const unsigned long long* __restrict__ off_rows, PartTile* __restrict__ pt,
                                 uint64_t* __restrict__ row_pairs, uint64_t* __restrict__ recs,
+                                unsigned long long* __restrict__ block_value, uint32_t block_bits,
                                 TileCounters* __restrict__ tc, int mode) {
     const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t ntr = 0, ntc = 0, r_lo = 0, r_hi = 0, c_lo = 0, c_hi = 0;
@@ -106,7 +108,9 @@ __global__ void tile_bin_kernel(KParams P, TileParams T, const PartInfo* __restr
                     row_pairs[orow++] = ((uint64_t)tr << 32) | p;
                     for (uint32_t tcol = tc0; tcol <= tc1; tcol++) {
                         const uint64_t tile = ((uint64_t)band * T.n_tr + tr) * T.n_tc + tcol;
-                        recs[o++] = (tile << T.part_bits) | p;
+                        block_value[o] = info[p].value_bits;  // tile_apply reads the value by block, not by part
+                        recs[o] = (tile << block_bits) | o;   // block index ascends with the part id: burn order
+                        o++;
                     }
                 }
             }
@@ -154,25 +158,33 @@ struct TileEdge {
     double x_top, y_top, dxdy;
     uint32_t lo, hi;  // active rows [lo, hi) (absolute)
 };
-__device__ __forceinline__ bool tile_edge_setup(const KParams& P, const double* __restrict__ px,
-                                                const double* __restrict__ py, uint32_t i, uint32_t r0, uint32_t r1,
-                                                TileEdge& e) {
-    const double y0 = py[i], y1 = py[i + 1];
+// y part of the edge test on already loaded pixel-space ordinates; *down = edge runs top to bottom
+__device__ __forceinline__ bool tile_edge_rows(const KParams& P, double y0, double y1, uint32_t r0, uint32_t r1,
+                                               TileEdge& e, bool* down, double* y_bot) {
     if (!(fabs(__dsub_rn(y0, y1)) >= DBL_EPSILON)) return false;  // edges.rs:100
     const double min_y = fmin(y0, y1), max_y = fmax(y0, y1);
     if (!(min_y < P.nrows_f && max_y >= 0.0)) return false;       // edges.rs:105
-    const bool down = y0 < y1;                                    // edges.rs:29
-    const double y_top = down ? y0 : y1, y_bot = down ? y1 : y0;
-    const uint32_t ystart = sat_u32(ceil(__dsub_rn(y_top, 0.5)), P.nrows);
-    const uint32_t yend = sat_u32(ceil(__dsub_rn(y_bot, 0.5)), P.nrows);
+    *down = y0 < y1;                                              // edges.rs:29
+    e.y_top = *down ? y0 : y1;
+    *y_bot = *down ? y1 : y0;
+    const uint32_t ystart = sat_u32(ceil(__dsub_rn(e.y_top, 0.5)), P.nrows);
+    const uint32_t yend = sat_u32(ceil(__dsub_rn(*y_bot, 0.5)), P.nrows);
     e.lo = max(ystart, r0);
     e.hi = min(yend, r1);
-    if (e.hi <= e.lo) return false;
-    const double x0 = px[i], x1 = px[i + 1];
+    return e.hi > e.lo;
+}
+__device__ __forceinline__ void tile_edge_slope(double x0, double x1, bool down, double y_bot, TileEdge& e) {
     const double x_bot = down ? x1 : x0;
     e.x_top = down ? x0 : x1;
-    e.y_top = y_top;
-    e.dxdy = __ddiv_rn(__dsub_rn(x_bot, e.x_top), __dsub_rn(y_bot, y_top));
+    e.dxdy = __ddiv_rn(__dsub_rn(x_bot, e.x_top), __dsub_rn(y_bot, e.y_top));  // edges.rs:36
+}
+__device__ __forceinline__ bool tile_edge_setup(const KParams& P, const double* __restrict__ px,
+                                                const double* __restrict__ py, uint32_t i, uint32_t r0, uint32_t r1,
+                                                TileEdge& e) {
+    bool down;
+    double y_bot;
+    if (!tile_edge_rows(P, py[i], py[i + 1], r0, r1, e, &down, &y_bot)) return false;
+    tile_edge_slope(px[i], px[i + 1], down, y_bot, e);
     return true;
 }
 __device__ __forceinline__ uint32_t tile_edge_col(const KParams& P, const TileEdge& e, uint32_t row) {
@@ -190,7 +202,7 @@ __device__ __forceinline__ uint32_t tile_edge_col(const KParams& P, const TileEd
 // (centre 0.5): only that row's crossing count is tracked, and an odd row 0 drops its largest column like
 // chunks_exact(2) drops the unpaired tail (burners.rs:305).
 template <int TILE_R>
-__global__ void __launch_bounds__(MASK_WARPS * 32)
+__global__ void __launch_bounds__(MASK_WARPS * 32, 10)
 tile_mask_kernel(KParams P, TileParams T, const uint64_t* __restrict__ row_pairs, uint32_t n_row_pairs,
                  const PartTile* __restrict__ pt, const uint32_t* __restrict__ vbeg, const uint32_t* __restrict__ vend,
                  const double* __restrict__ px, const double* __restrict__ py, const uint32_t* __restrict__ tag,
@@ -216,11 +228,32 @@ tile_mask_kernel(KParams P, TileParams T, const uint64_t* __restrict__ row_pairs
         for (uint32_t i = lane; i < TILE_R * MASK_MAX_WORDS; i += 32) (&mask[0][0])[i] = 0;
         __syncwarp();
         uint32_t par0 = 0;  // this lane's share of the row-0 crossing count parity
+        // software pipeline: the next batch's tag / ordinates are in flight while this one is processed
+        uint32_t tg_n = 0x80000000u;
+        double y0_n = 0.0, y1_n = 0.0;
+        if (vb + lane + 1 < ve) {
+            tg_n = tag[vb + lane];
+            y0_n = py[vb + lane];
+            y1_n = py[vb + lane + 1];
+        }
         for (uint32_t i0 = vb; i0 + 1 < ve; i0 += 32) {
             const uint32_t i = i0 + lane;
+            const uint32_t tg = tg_n;
+            const double y0 = y0_n, y1 = y1_n;
+            tg_n = 0x80000000u;
+            if (i + 33 < ve) {
+                tg_n = tag[i + 32];
+                y0_n = py[i + 32];
+                y1_n = py[i + 33];
+            }
             TileEdge e;
             uint32_t cnt = 0;
-            if (i + 1 < ve && !(tag[i] & 0x80000000u) && tile_edge_setup(P, px, py, i, r0, r1, e)) cnt = e.hi - e.lo;
+            bool down;
+            double y_bot;
+            if (!(tg & 0x80000000u) && tile_edge_rows(P, y0, y1, r0, r1, e, &down, &y_bot)) {
+                tile_edge_slope(px[i], px[i + 1], down, y_bot, e);
+                cnt = e.hi - e.lo;
+            }
             uint32_t inc = cnt;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
@@ -302,16 +335,38 @@ tile_mask_kernel(KParams P, TileParams T, const uint64_t* __restrict__ row_pairs
 // ---------------------------------------------------------------------------------------------
 // tile_apply: one CTA per tile, each warp owns 8 rows, no synchronisation between warps
 // ---------------------------------------------------------------------------------------------
+template <typename N, int FN>
+__device__ __forceinline__ void apply_group_mask(N* __restrict__ base, uint32_t m, uint32_t lane, N v, N bg) {
+    uint32_t nz = __ballot_sync(0xffffffffu, m != 0);
+    while (nz) {  // two mask words per step: their shared-memory round trips overlap
+        const int src0 = __ffs(nz) - 1;
+        nz &= nz - 1;
+        const int src1 = nz ? __ffs(nz) - 1 : src0;
+        const bool two = nz != 0;
+        nz &= nz - 1;
+        const uint32_t mw0 = __shfl_sync(0xffffffffu, m, src0);
+        const uint32_t mw1 = __shfl_sync(0xffffffffu, m, src1);
+        N* p0 = base + src0 * 32;  // word `src` of the group covers pixels src*32 .. src*32+31 of the 8 rows
+        N* p1 = base + src1 * 32;
+        const N cur0 = *p0;
+        const N cur1 = *p1;
+        const N nv0 = apply_px<N, FN>(cur0, v, bg);
+        const N nv1 = apply_px<N, FN>(cur1, v, bg);
+        *p0 = ((mw0 >> lane) & 1u) ? nv0 : cur0;
+        if (two) *p1 = ((mw1 >> lane) & 1u) ? nv1 : cur1;
+    }
+}
+
 template <typename N, int FN, int TILE_R>
 __global__ void __launch_bounds__(TILE_R * 4)
 tile_apply_kernel(KParams P, TileParams T, const uint64_t* __restrict__ recs, const uint32_t* __restrict__ tile_start,
-                  const PartInfo* __restrict__ info, const PartTile* __restrict__ pt,
+                  const unsigned long long* __restrict__ block_value, uint32_t block_bits,
                   const uint32_t* __restrict__ masks, uint64_t bg_bits, N* __restrict__ out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
     N* rows8 = reinterpret_cast<N*>(smem_raw) + (size_t)warp * 8 * TILE_C;  // this warp's 8 rows x 128 columns
     const N bg = value_from_bits<N>(bg_bits);
-    const uint64_t part_mask = (1ull << T.part_bits) - 1ull;
+    const uint64_t block_mask = (1ull << block_bits) - 1ull;
 
     const uint32_t t = blockIdx.x;
     const uint32_t tcol = t % T.n_tc, trow = (t / T.n_tc) % T.n_tr, band = t / (T.n_tc * T.n_tr);
@@ -325,33 +380,27 @@ tile_apply_kernel(KParams P, TileParams T, const uint64_t* __restrict__ recs, co
 
     const uint32_t beg = tile_start[t], end = tile_start[t + 1];
     N* base = rows8 + lane;
-    for (uint32_t rec = beg; rec < end; rec++) {
-        const uint32_t part = (uint32_t)(recs[rec] & part_mask);
-        const PartTile q = pt[part];
-        const unsigned long long blk = q.first_block + (unsigned long long)(trow - q.tr0) * q.ntc + (tcol - q.tc0);
-        // lane = (row in this warp's group, mask word): one coalesced 128-byte load
-        const uint32_t m = masks[blk * (TILE_R * 4) + warp * 32 + lane];
-        uint32_t nz = __ballot_sync(0xffffffffu, m != 0);
-        if (nz == 0) continue;  // the part does not reach these 8 rows
-        const N v = value_from_bits<N>(info[part].value_bits);
-        while (nz) {  // two mask words per step: their shared-memory round trips overlap
-            const int src0 = __ffs(nz) - 1;
-            nz &= nz - 1;
-            const int src1 = nz ? __ffs(nz) - 1 : src0;
-            const bool two = nz != 0;
-            nz &= nz - 1;
-            const uint32_t mw0 = __shfl_sync(0xffffffffu, m, src0);
-            const uint32_t mw1 = __shfl_sync(0xffffffffu, m, src1);
-            N* p0 = base + src0 * 32;  // word `src` of the group covers rows8[src*32 .. src*32+31]
-            N* p1 = base + src1 * 32;
-            const N cur0 = *p0;
-            const N cur1 = *p1;
-            const N nv0 = apply_px<N, FN>(cur0, v, bg);
-            const N nv1 = apply_px<N, FN>(cur1, v, bg);
-            *p0 = ((mw0 >> lane) & 1u) ? nv0 : cur0;
-            if (two) *p1 = ((mw1 >> lane) & 1u) ? nv1 : cur1;
+    const uint32_t* my_masks = masks + warp * 32 + lane;  // lane = (row in this warp's group, mask word)
+    for (uint32_t chunk = beg; chunk < end; chunk += 32) {
+        // 32 records with one coalesced load; their mask words are fetched four parts ahead of the apply
+        const uint32_t n = min(32u, end - chunk);
+        const unsigned long long my_blk = lane < n ? (recs[chunk + lane] & block_mask) : 0ull;
+        for (uint32_t j0 = 0; j0 < n; j0 += 4) {
+            unsigned long long blk[4];
+            uint32_t m[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                blk[u] = __shfl_sync(0xffffffffu, my_blk, (j0 + u) & 31);
+                m[u] = j0 + u < n ? my_masks[blk[u] * (TILE_R * 4)] : 0u;  // one coalesced 128-byte load
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                if (__ballot_sync(0xffffffffu, m[u] != 0) == 0) continue;  // the part does not reach these 8 rows
+                const N v = value_from_bits<N>(block_value[blk[u]]);
+                apply_group_mask<N, FN>(base, m[u], lane, v, bg);
+                __syncwarp();
+            }
         }
-        __syncwarp();
     }
 
     // ---- flush: every output byte is written exactly once ---------------------------------------------
