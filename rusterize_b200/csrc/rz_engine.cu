@@ -293,14 +293,33 @@ static unsigned long long scan_total(DevBuf& partial, uint32_t n, cudaStream_t s
 typedef void (*TileLaunch)(uint32_t, cudaStream_t, KParams, TileParams, const uint64_t*, const uint32_t*,
                            const unsigned long long*, uint32_t, const uint32_t*, uint64_t, void*);
 
+template <typename N> struct NanBackground {
+    static constexpr bool possible = false;
+    static bool is(N) { return false; }
+};
+template <> struct NanBackground<float> {
+    static constexpr bool possible = true;
+    static bool is(float v) { return v != v; }
+};
+template <> struct NanBackground<double> {
+    static constexpr bool possible = true;
+    static bool is(double v) { return v != v; }
+};
+
 template <typename N, int FN>
 static void tile_launch(uint32_t grid, cudaStream_t s, KParams P, TileParams T, const uint64_t* recs,
                         const uint32_t* tile_start, const unsigned long long* block_value, uint32_t block_bits,
                         const uint32_t* masks, uint64_t bg, void* out) {
     constexpr int TR = sizeof(N) <= 4 ? 64 : 32;
     const size_t smem = (size_t)TR * TILE_C * sizeof(N);
-    tile_apply_kernel<N, FN, TR><<<grid, TR * 4, smem, s>>>(P, T, recs, tile_start, block_value, block_bits, masks, bg,
-                                                            (N*)out);
+    N bgv;
+    std::memcpy(&bgv, &bg, sizeof(N));
+    if (NanBackground<N>::is(bgv))  // float dtypes with a NaN background: one comparison less per pixel
+        tile_apply_kernel<N, FN, TR, NanBackground<N>::possible><<<grid, TR * 4, smem, s>>>(
+            P, T, recs, tile_start, block_value, block_bits, masks, bg, (N*)out);
+    else
+        tile_apply_kernel<N, FN, TR, false><<<grid, TR * 4, smem, s>>>(P, T, recs, tile_start, block_value, block_bits,
+                                                                       masks, bg, (N*)out);
 }
 template <typename N> static TileLaunch tile_for_fn(int fn) {
     switch (fn) {

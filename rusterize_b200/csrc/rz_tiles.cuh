@@ -335,7 +335,7 @@ tile_mask_kernel(KParams P, TileParams T, const uint64_t* __restrict__ row_pairs
 // ---------------------------------------------------------------------------------------------
 // tile_apply: one CTA per tile, each warp owns 8 rows, no synchronisation between warps
 // ---------------------------------------------------------------------------------------------
-template <typename N, int FN>
+template <typename N, int FN, bool BGNAN>
 __device__ __forceinline__ void apply_group_mask(N* __restrict__ base, uint32_t m, uint32_t lane, N v, N bg) {
     uint32_t nz = __ballot_sync(0xffffffffu, m != 0);
     while (nz) {  // two mask words per step: their shared-memory round trips overlap
@@ -350,14 +350,14 @@ __device__ __forceinline__ void apply_group_mask(N* __restrict__ base, uint32_t 
         N* p1 = base + src1 * 32;
         const N cur0 = *p0;
         const N cur1 = *p1;
-        const N nv0 = apply_px<N, FN>(cur0, v, bg);
-        const N nv1 = apply_px<N, FN>(cur1, v, bg);
+        const N nv0 = apply_px<N, FN, BGNAN>(cur0, v, bg);
+        const N nv1 = apply_px<N, FN, BGNAN>(cur1, v, bg);
         *p0 = ((mw0 >> lane) & 1u) ? nv0 : cur0;
         if (two) *p1 = ((mw1 >> lane) & 1u) ? nv1 : cur1;
     }
 }
 
-template <typename N, int FN, int TILE_R>
+template <typename N, int FN, int TILE_R, bool BGNAN>
 __global__ void __launch_bounds__(TILE_R * 4)
 tile_apply_kernel(KParams P, TileParams T, const uint64_t* __restrict__ recs, const uint32_t* __restrict__ tile_start,
                   const unsigned long long* __restrict__ block_value, uint32_t block_bits,
@@ -386,18 +386,19 @@ tile_apply_kernel(KParams P, TileParams T, const uint64_t* __restrict__ recs, co
         const uint32_t n = min(32u, end - chunk);
         const unsigned long long my_blk = lane < n ? (recs[chunk + lane] & block_mask) : 0ull;
         for (uint32_t j0 = 0; j0 < n; j0 += 4) {
-            unsigned long long blk[4];
             uint32_t m[4];
+            unsigned long long vbits[4];
 #pragma unroll
             for (int u = 0; u < 4; u++) {
-                blk[u] = __shfl_sync(0xffffffffu, my_blk, (j0 + u) & 31);
-                m[u] = j0 + u < n ? my_masks[blk[u] * (TILE_R * 4)] : 0u;  // one coalesced 128-byte load
+                const unsigned long long blk = __shfl_sync(0xffffffffu, my_blk, (j0 + u) & 31);
+                const bool live = j0 + u < n;
+                m[u] = live ? my_masks[blk * (TILE_R * 4)] : 0u;  // one coalesced 128-byte load
+                vbits[u] = live ? block_value[blk] : 0ull;        // broadcast load, in flight with the mask
             }
 #pragma unroll
             for (int u = 0; u < 4; u++) {
                 if (__ballot_sync(0xffffffffu, m[u] != 0) == 0) continue;  // the part does not reach these 8 rows
-                const N v = value_from_bits<N>(block_value[blk[u]]);
-                apply_group_mask<N, FN>(base, m[u], lane, v, bg);
+                apply_group_mask<N, FN, BGNAN>(base, m[u], lane, value_from_bits<N>(vbits[u]), bg);
                 __syncwarp();
             }
         }
