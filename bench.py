@@ -267,12 +267,12 @@ def run_b200(args):
         h_out = torch.empty((1, r1 - r0, cols), dtype=tdt).pin_memory()
         h_np = h_out.numpy()
         n_e2e = max(1, min(args.steps, args.e2e_steps))
-        step(flags=_lib.FLAG_FORCE_H2D, out=h_np)  # warm
+        step(flags=_lib.FLAG_FORCE_H2D | _lib.FLAG_SYNC_STAGES, out=h_np)  # warm
         barrier()
         t0 = time.perf_counter()
         est = []
         for _ in range(n_e2e):
-            est.append(step(flags=_lib.FLAG_FORCE_H2D, out=h_np))
+            est.append(step(flags=_lib.FLAG_FORCE_H2D | _lib.FLAG_SYNC_STAGES, out=h_np))
         barrier()
         e_ms = (time.perf_counter() - t0) * 1e3 / n_e2e
         t = torch.tensor([e_ms], device="cuda", dtype=torch.float64)
@@ -282,9 +282,14 @@ def run_b200(args):
         hb = torch.tensor([est[-1]["h2d_bytes"], est[-1]["d2h_bytes"]], device="cuda", dtype=torch.float64)
         if world > 1:
             dist.all_reduce(hb)
+        # the host raster must equal the device-resident one (same rows sampled on both sides)
+        stride = max(1, (r1 - r0) // 64)
+        same = bool(np.array_equal(h_np[0, ::stride], d_out[0, ::stride].cpu().numpy(), equal_nan=True))
         e2e = {"value": rows * cols / (e_ms / 1e3) / 1e6, "unit": "Mpixel/s", "ms_per_step": e_ms,
                "h2d_bytes_per_step": int(hb[0].item()), "d2h_bytes_per_step": int(hb[1].item()), "steps": n_e2e,
-               "checksum": float(np.nansum(h_np[0, :: max(1, (r1 - r0) // 64)], dtype=np.float64))}
+               "rank0_h2d_ms": est[-1]["h2d_ms"], "rank0_d2h_ms": est[-1]["d2h_ms"],
+               "host_equals_device_raster": same,
+               "checksum": float(np.nansum(h_np[0, ::stride], dtype=np.float64))}
 
     # ---- gather per-rank stage stats -----------------------------------------------------------
     keys = ["n_records", "n_crossings", "out_bytes", "kernel_launches"]
