@@ -139,11 +139,12 @@ static DeviceCtx& device_ctx(int dev) {
     return ref;
 }
 
+// (re)upload a host vector; the device buffer is allocated on first use and reused afterwards (a
+// geometry set is immutable, so a forced re-upload only pays the copy)
 template <typename T> static void upload_vec(T** dst, const std::vector<T>& v, cudaStream_t s, size_t& bytes) {
-    *dst = nullptr;
     if (v.empty()) return;
     // one spare element so kernels may read index i+1 of the last vertex unconditionally
-    CUDA_TRY(cudaMalloc((void**)dst, (v.size() + 1) * sizeof(T)));
+    if (*dst == nullptr) CUDA_TRY(cudaMalloc((void**)dst, (v.size() + 1) * sizeof(T)));
     CUDA_TRY(cudaMemcpyAsync(*dst, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, s));
     bytes += v.size() * sizeof(T);
 }
@@ -184,14 +185,15 @@ static DeviceGeoms* geoms_on_device(rz_geoms* g, DeviceCtx& c, cudaStream_t s, b
     std::lock_guard<std::mutex> lk(g->mu);
     auto it = g->dev.find(c.dev);
     if (it != g->dev.end() && !force) return it->second;
-    if (it != g->dev.end()) {
-        delete it->second;
-        g->dev.erase(it);
-    }
     for (int k = 0; k < 3; k++)
         if (g->pool[k].size() >= 0xfffffff0ull) throw Error{RZ_RUNTIME_ERROR, "Too many vertices (limit 2^32 per pool)."};
     pin_host(g);
-    std::unique_ptr<DeviceGeoms> d(new DeviceGeoms());
+    std::unique_ptr<DeviceGeoms> fresh;
+    DeviceGeoms* d = it != g->dev.end() ? it->second : nullptr;
+    if (!d) {
+        fresh.reset(new DeviceGeoms());
+        d = fresh.get();
+    }
     d->dev = c.dev;
     size_t bytes = 0;
     for (int k = 0; k < 3; k++) {
@@ -211,9 +213,8 @@ static DeviceGeoms* geoms_on_device(rz_geoms* g, DeviceCtx& c, cudaStream_t s, b
     CUDA_TRY(cudaStreamSynchronize(s));  // `pg` is a temporary
     d->bytes = bytes;
     if (h2d_bytes) *h2d_bytes += bytes;
-    DeviceGeoms* raw = d.release();
-    g->dev[c.dev] = raw;
-    return raw;
+    if (fresh) g->dev[c.dev] = fresh.release();
+    return d;
 }
 
 // ------------------------------------------------------------------------------------------------
