@@ -77,32 +77,79 @@ def select_band_polygons(x, y, off, vals, rows_total, r0, r1):
 
 
 class ClockSampler:
-    """nvidia-smi clocks/throttle reasons during the timed region (B200_PROFILING.md)."""
+    """SM clock and throttle reasons sampled DURING the timed region (B200_PROFILING.md's clocks line).
+    NVML is polled in-process every few ms (a timed region of a handful of ~10 ms steps is over before
+    `nvidia-smi -lms` prints its first line); nvidia-smi is the fallback when pynvml is missing."""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, gpu_index: int):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            try:
+                gpu_index = int(vis.split(",")[gpu_index])
+            except (ValueError, IndexError):
+                pass
         self.idx = gpu_index
-        self.lines = []
-        self.proc = None
+        self.lines, self.sm, self.mx, self.reasons = [], [], [], set()
+        self.proc = self.thread = self.nvml = None
+        self.stop_flag = threading.Event()
 
     def start(self):
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(self.idx)
+            self.nvml = pynvml
+            self.mx.append(float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)))
+            self._poll_once()
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.idx)],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
-            self.t.start()
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
         except Exception:
             self.proc = None
+
+    def _poll_once(self):
+        n = self.nvml
+        self.sm.append(float(n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM)))
+        try:
+            r = n.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+        except Exception:
+            r = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+        for nm, bit in zip(self.NAMES, (0x8, 0x40, 0x20, 0x4)):  # nvml.h: HwSlowdown, HwThermal, SwThermal, SwPowerCap
+            if r & bit:
+                self.reasons.add(nm)
+
+    def _poll(self):
+        while not self.stop_flag.is_set():
+            try:
+                self._poll_once()
+            except Exception:
+                break
+            time.sleep(0.004)
 
     def _read(self):
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
     def stop(self):
+        if self.nvml:
+            self.stop_flag.set()
+            self.thread.join(timeout=2)
+            return {"sm_mhz": float(np.median(self.sm)), "sm_max_mhz": max(self.mx), "reasons": sorted(self.reasons),
+                    "samples": len(self.sm), "source": "nvml"}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -111,22 +158,20 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for ln in self.lines:
             p = [s.strip() for s in ln.split(",")]
             if len(p) < 9:
                 continue
             try:
-                sm.append(float(p[1]))
-                mx.append(float(p[2]))
+                self.sm.append(float(p[1]))
+                self.mx.append(float(p[2]))
             except ValueError:
                 continue
-            for nm, v in zip(names, p[5:9]):
+            for nm, v in zip(self.NAMES, p[5:9]):
                 if v.lower().startswith("active"):
-                    reasons.add(nm)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                    self.reasons.add(nm)
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": max(self.mx) if self.mx else None,
+                "reasons": sorted(self.reasons), "samples": len(self.sm), "source": "nvidia-smi"}
 
 
 def peaks():
@@ -230,7 +275,12 @@ def run_b200(args):
     bg = np.nan if dt.kind == "f" else 0
     tdt = {"float32": torch.float32, "float64": torch.float64}[w["dtype"]]
     d_out = torch.empty((1, r1 - r0, cols), dtype=tdt, device="cuda")
-    stream = torch.cuda.current_stream().cuda_stream
+    # A dedicated (non-default) stream: the library launches on the stream handle it is given - handle 0
+    # would mean "use the library's own stream" - and the timing events below are recorded on the same stream.
+    tstream = torch.cuda.Stream()
+    torch.cuda.set_stream(tstream)
+    stream = tstream.cuda_stream
+    assert stream != 0
     geoms.upload(local)
 
     eng_flag = {"auto": 0, "records": _lib.FLAG_NO_TILE_ENGINE, "tiles": _lib.FLAG_FORCE_TILE_ENGINE}[args.engine]
@@ -248,14 +298,22 @@ def run_b200(args):
     if rank == 0:
         sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_wall = time.perf_counter()
     ev0.record()
-    stats = []
+    marks = []
     for _ in range(args.steps):
-        stats.append(step(flags=_lib.FLAG_SYNC_STAGES))
+        step()
+        marks.append(torch.cuda.Event(enable_timing=True))
+        marks[-1].record()
     ev1.record()
     barrier()
+    wall_ms = (time.perf_counter() - t_wall) * 1e3 / args.steps  # cross-check of the CUDA-event time
+    each_ms = [a.elapsed_time(b) for a, b in zip([ev0] + marks[:-1], marks)]
     clocks = sampler.stop() if rank == 0 else None
     ms = ev0.elapsed_time(ev1) / args.steps
+    # per-stage CUDA-event timings come from a separate pass: the event synchronisations they need would
+    # otherwise sit inside the timed region
+    stats = [step(flags=_lib.FLAG_SYNC_STAGES) for _ in range(min(args.steps, 3))]
     t = torch.tensor([ms], device="cuda", dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -355,6 +413,8 @@ def run_b200(args):
     line = {
         "metric": "output_Mpixels_per_s", "value": rows * cols / (ms_max / 1e3) / 1e6, "unit": "Mpixel/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max,
+        "wall_ms_per_step_rank0": wall_ms, "ms_each_step_rank0": [round(v, 3) for v in each_ms],
+        "lib_total_ms_staged_pass": float(np.mean([s["total_ms"] for s in stats])),
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64 geometry / %s values" % w["dtype"], "data": "synthetic",
         "config": {"workload": f"{args.workload}: {w['desc']}", "scale": args.scale, "parallelism": f"row-bands x{world}",

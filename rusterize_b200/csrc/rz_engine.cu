@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <string>
@@ -109,9 +110,12 @@ struct DeviceCtx {
     int sm_count = 148;
     DevBuf keys_a, keys_b, hist, digit_total, task_start, part_info, field, valid, band, last_kept, counters, win_out,
         block_total, vs_keys, vs_first, sp_raw, tile_cnt, tile_cnt2, tile_off, tile_off2, tile_ctr, tile_px, tile_py,
-        tile_pt, tile_pairs, tile_masks, tile_val, sp_a, sp_b, sp_c, sp_d, sp_e, sp_f, sp_g, sp_rows, sp_cols, sp_data, sp_partial;
+        tile_pt, tile_pairs, tile_masks, tile_val, tile_vrow, tile_pos, tile_val2, sp_a, sp_b, sp_c, sp_d, sp_e, sp_f, sp_g, sp_rows, sp_cols, sp_data, sp_partial, sp_w, sp_wraw, sp_ws;
     Counters* h_counters = nullptr;  // pinned
     cudaEvent_t ev[16];
+    cudaStream_t copy_stream = nullptr;  // device->host copies of finished row windows overlap the next window
+    cudaEvent_t ev_filled[2], ev_copied[2], ev_d2h[2];
+    DevBuf win_out2;
 };
 
 static std::mutex g_ctx_mu;
@@ -134,19 +138,79 @@ static DeviceCtx& device_ctx(int dev) {
     CUDA_TRY(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, dev));
     CUDA_TRY(cudaHostAlloc((void**)&c->h_counters, sizeof(Counters), cudaHostAllocDefault));
     for (auto& e : c->ev) CUDA_TRY(cudaEventCreate(&e));
+    CUDA_TRY(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    for (int k = 0; k < 2; k++) {
+        CUDA_TRY(cudaEventCreateWithFlags(&c->ev_filled[k], cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&c->ev_copied[k], cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreate(&c->ev_d2h[k]));
+    }
     DeviceCtx& ref = *c;
     g_ctx[dev] = std::move(c);
     return ref;
 }
 
+// Host -> device copy of [src, src+bytes) that never spans two host registrations (CUDA rejects such a copy):
+// the range is cut at the borders of the page-locked ranges; cuts outside any of them go as pageable copies.
+static void copy_h2d_split(void* dst, const void* src, size_t bytes, const std::vector<std::pair<void*, size_t>>& pinned,
+                           cudaStream_t s) {
+    uintptr_t a = (uintptr_t)src;
+    const uintptr_t end = a + bytes;
+    while (a < end) {
+        uintptr_t b = end;
+        for (const auto& r : pinned) {
+            const uintptr_t r0 = (uintptr_t)r.first, r1 = r0 + r.second;
+            if (a >= r0 && a < r1) { b = std::min(end, r1); break; }  // inside a registration: up to its end
+            if (r0 > a && r0 < b) b = r0;                             // outside: up to the next one
+        }
+        CUDA_TRY(cudaMemcpyAsync((char*)dst + (a - (uintptr_t)src), (const void*)a, b - a, cudaMemcpyHostToDevice, s));
+        a = b;
+    }
+}
+
 // (re)upload a host vector; the device buffer is allocated on first use and reused afterwards (a
 // geometry set is immutable, so a forced re-upload only pays the copy)
-template <typename T> static void upload_vec(T** dst, const std::vector<T>& v, cudaStream_t s, size_t& bytes) {
+template <typename T>
+static void upload_vec(T** dst, const std::vector<T>& v, cudaStream_t s, size_t& bytes,
+                       const std::vector<std::pair<void*, size_t>>& pinned) {
     if (v.empty()) return;
     // one spare element so kernels may read index i+1 of the last vertex unconditionally
     if (*dst == nullptr) CUDA_TRY(cudaMalloc((void**)dst, (v.size() + 1) * sizeof(T)));
-    CUDA_TRY(cudaMemcpyAsync(*dst, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, s));
+    copy_h2d_split(*dst, v.data(), v.size() * sizeof(T), pinned, s);
     bytes += v.size() * sizeof(T);
+}
+
+// Page-lock the vertex pools where they lie so uploads run at PCIe speed.  cudaHostRegister was seen to
+// refuse one 1.6 GB vector out of three ("OS call failed"), which silently left that pool pageable (2.5x
+// slower upload); a refused vector is therefore moved to freshly allocated storage and tried again, and as a
+// last resort registered in page-aligned 256 MiB pieces so that only the refused pieces stay pageable.
+// RZ_VERBOSE=1 reports what was refused.
+template <typename T> static void pin_vec(rz_geoms* g, std::vector<T>& v, bool verbose) {
+    const size_t bytes = v.size() * sizeof(T);
+    if (bytes < (1u << 16)) return;
+    auto try_reg = [&](void* p, size_t n) {
+        const cudaError_t e = cudaHostRegister(p, n, cudaHostRegisterDefault);
+        if (e == cudaSuccess) {
+            g->pinned_ranges.emplace_back(p, n);
+            return true;
+        }
+        (void)cudaGetLastError();
+        if (verbose) std::fprintf(stderr, "librz_b200: cudaHostRegister(%zu bytes) refused: %s\n", n, cudaGetErrorString(e));
+        return false;
+    };
+    if (try_reg(v.data(), bytes)) return;
+    {
+        std::vector<T> fresh(v);
+        v.swap(fresh);
+    }
+    if (try_reg(v.data(), bytes)) return;
+    const uintptr_t piece = (uintptr_t)256 << 20, page = 4096;
+    uintptr_t a = ((uintptr_t)v.data() + page - 1) & ~(page - 1);
+    const uintptr_t end = ((uintptr_t)v.data() + bytes) & ~(page - 1);
+    while (a < end) {
+        const uintptr_t b = std::min(end, a + piece);
+        try_reg((void*)a, b - a);
+        a = b;
+    }
 }
 
 static void pin_host(rz_geoms* g) {
@@ -156,28 +220,27 @@ static void pin_host(rz_geoms* g) {
         (void)cudaGetLastError();
         return;
     }
-    auto reg = [](const void* p, size_t bytes) {
-        if (bytes >= (1u << 16) && cudaHostRegister(const_cast<void*>(p), bytes, cudaHostRegisterDefault) != cudaSuccess)
-            (void)cudaGetLastError();
-    };
+    const bool verbose = std::getenv("RZ_VERBOSE") != nullptr;
     for (int k = 0; k < 3; k++) {
-        reg(g->pool[k].x.data(), g->pool[k].x.size() * 8);
-        reg(g->pool[k].y.data(), g->pool[k].y.size() * 8);
-        reg(g->pool[k].tag.data(), g->pool[k].tag.size() * 4);
+        pin_vec(g, g->pool[k].x, verbose);
+        pin_vec(g, g->pool[k].y, verbose);
+        pin_vec(g, g->pool[k].tag, verbose);
     }
+    pin_vec(g, g->part_xlo, verbose);  // the parts table (45 B/part) is uploaded with the pools
+    pin_vec(g, g->part_xhi, verbose);
+    pin_vec(g, g->part_ylo, verbose);
+    pin_vec(g, g->part_yhi, verbose);
+    pin_vec(g, g->part_vbeg, verbose);
+    pin_vec(g, g->part_vend, verbose);
+    pin_vec(g, g->part_kind, verbose);
     g->pinned = true;
 }
 
 static void unpin_host(rz_geoms* g) {
     if (!g->pinned) return;
-    auto unreg = [](const void* p, size_t bytes) {
-        if (bytes >= (1u << 16) && cudaHostUnregister(const_cast<void*>(p)) != cudaSuccess) (void)cudaGetLastError();
-    };
-    for (int k = 0; k < 3; k++) {
-        unreg(g->pool[k].x.data(), g->pool[k].x.size() * 8);
-        unreg(g->pool[k].y.data(), g->pool[k].y.size() * 8);
-        unreg(g->pool[k].tag.data(), g->pool[k].tag.size() * 4);
-    }
+    for (auto& r : g->pinned_ranges)
+        if (cudaHostUnregister(r.first) != cudaSuccess) (void)cudaGetLastError();
+    g->pinned_ranges.clear();
     g->pinned = false;
 }
 
@@ -197,19 +260,19 @@ static DeviceGeoms* geoms_on_device(rz_geoms* g, DeviceCtx& c, cudaStream_t s, b
     d->dev = c.dev;
     size_t bytes = 0;
     for (int k = 0; k < 3; k++) {
-        upload_vec(&d->x[k], g->pool[k].x, s, bytes);
-        upload_vec(&d->y[k], g->pool[k].y, s, bytes);
-        upload_vec(&d->tag[k], g->pool[k].tag, s, bytes);
+        upload_vec(&d->x[k], g->pool[k].x, s, bytes, g->pinned_ranges);
+        upload_vec(&d->y[k], g->pool[k].y, s, bytes, g->pinned_ranges);
+        upload_vec(&d->tag[k], g->pool[k].tag, s, bytes, g->pinned_ranges);
     }
-    upload_vec(&d->part_kind, g->part_kind, s, bytes);
+    upload_vec(&d->part_kind, g->part_kind, s, bytes, g->pinned_ranges);
     std::vector<uint32_t> pg(g->part_geom.begin(), g->part_geom.end());
-    upload_vec(&d->part_geom, pg, s, bytes);
-    upload_vec(&d->part_xlo, g->part_xlo, s, bytes);
-    upload_vec(&d->part_xhi, g->part_xhi, s, bytes);
-    upload_vec(&d->part_ylo, g->part_ylo, s, bytes);
-    upload_vec(&d->part_yhi, g->part_yhi, s, bytes);
-    upload_vec(&d->part_vbeg, g->part_vbeg, s, bytes);
-    upload_vec(&d->part_vend, g->part_vend, s, bytes);
+    upload_vec(&d->part_geom, pg, s, bytes, g->pinned_ranges);
+    upload_vec(&d->part_xlo, g->part_xlo, s, bytes, g->pinned_ranges);
+    upload_vec(&d->part_xhi, g->part_xhi, s, bytes, g->pinned_ranges);
+    upload_vec(&d->part_ylo, g->part_ylo, s, bytes, g->pinned_ranges);
+    upload_vec(&d->part_yhi, g->part_yhi, s, bytes, g->pinned_ranges);
+    upload_vec(&d->part_vbeg, g->part_vbeg, s, bytes, g->pinned_ranges);
+    upload_vec(&d->part_vend, g->part_vend, s, bytes, g->pinned_ranges);
     CUDA_TRY(cudaStreamSynchronize(s));  // `pg` is a temporary
     d->bytes = bytes;
     if (h2d_bytes) *h2d_bytes += bytes;
@@ -291,8 +354,8 @@ static unsigned long long scan_total(DevBuf& partial, uint32_t n, cudaStream_t s
 // ------------------------------------------------------------------------------------------------
 // tile-binned engine dispatch
 // ------------------------------------------------------------------------------------------------
-typedef void (*TileLaunch)(uint32_t, cudaStream_t, KParams, TileParams, const uint64_t*, const uint32_t*,
-                           const unsigned long long*, uint32_t, const uint32_t*, uint64_t, void*);
+typedef void (*TileLaunch)(uint32_t, cudaStream_t, KParams, TileParams, const uint32_t*, const unsigned long long*,
+                           const uint32_t*, uint64_t, void*);
 
 template <typename N> struct NanBackground {
     static constexpr bool possible = false;
@@ -308,19 +371,20 @@ template <> struct NanBackground<double> {
 };
 
 template <typename N, int FN>
-static void tile_launch(uint32_t grid, cudaStream_t s, KParams P, TileParams T, const uint64_t* recs,
-                        const uint32_t* tile_start, const unsigned long long* block_value, uint32_t block_bits,
-                        const uint32_t* masks, uint64_t bg, void* out) {
+static void tile_launch(uint32_t, cudaStream_t s, KParams P, TileParams T, const uint32_t* tile_start,
+                        const unsigned long long* value_sorted, const uint32_t* masks, uint64_t bg, void* out) {
     constexpr int TR = sizeof(N) <= 4 ? 64 : 32;
-    const size_t smem = (size_t)TR * TILE_C * sizeof(N);
+    // one CTA per tile: (tile columns, tile rows x bands) when that fits the grid limits, else flattened
+    const uint64_t gy = (uint64_t)T.n_tr * P.n_bands;
+    const dim3 grid = gy <= 65535 ? dim3(T.n_tc, (unsigned)gy) : dim3(T.n_tiles);
+    const size_t smem = sizeof(N) >= 4 ? 0 : (size_t)TR * TILE_C * sizeof(N);  // flush staging of 1/2-byte dtypes only
     N bgv;
     std::memcpy(&bgv, &bg, sizeof(N));
     if (NanBackground<N>::is(bgv))  // float dtypes with a NaN background: one comparison less per pixel
-        tile_apply_kernel<N, FN, TR, NanBackground<N>::possible><<<grid, TR * 4, smem, s>>>(
-            P, T, recs, tile_start, block_value, block_bits, masks, bg, (N*)out);
+        tile_apply_kernel<N, FN, TR, NanBackground<N>::possible><<<grid, TR * 4, smem, s>>>(P, T, tile_start, value_sorted,
+                                                                                         masks, bg, (N*)out);
     else
-        tile_apply_kernel<N, FN, TR, false><<<grid, TR * 4, smem, s>>>(P, T, recs, tile_start, block_value, block_bits,
-                                                                       masks, bg, (N*)out);
+        tile_apply_kernel<N, FN, TR, false><<<grid, TR * 4, smem, s>>>(P, T, tile_start, value_sorted, masks, bg, (N*)out);
 }
 template <typename N> static TileLaunch tile_for_fn(int fn) {
     switch (fn) {
@@ -371,7 +435,7 @@ struct Timer {
 };
 
 static const uint64_t MAX_WINDOW_RECORDS = 1ull << 31;      // 32 GiB of ping-pong key buffers
-static const uint64_t MAX_WINDOW_OUT_BYTES = 12ull << 30;  // staging buffer when `out` is host memory
+static const uint64_t MAX_WINDOW_OUT_BYTES = 2ull << 30;   // one of the two staging buffers when `out` is host memory
 
 static void rasterize_dense(rz_geoms* g, const rz_context* ctx, void* out, rz_stats* st) {
     const rz_raster_info& ri = ctx->raster_info;
@@ -400,7 +464,7 @@ static void rasterize_dense(rz_geoms* g, const rz_context* ctx, void* out, rz_st
     cudaStream_t s = ctx->stream ? (cudaStream_t)ctx->stream : c.stream;
     rz_stats S;
     std::memset(&S, 0, sizeof S);
-    enum { EV_START, EV_H2D, EV_A, EV_B, EV_END };
+    enum { EV_START, EV_H2D, EV_END, EV_A0 };  // EV_A0..: one event pair per stage of a window (6 pairs)
     CUDA_TRY(cudaEventRecord(c.ev[EV_START], s));
 
     // ---- inputs to the device ------------------------------------------------------------------
@@ -511,12 +575,47 @@ static void rasterize_dense(rz_geoms* g, const rz_context* ctx, void* out, rz_st
     FillLaunch fill = fill_for(ctx->dtype, ctx->pixel_fn);
     float count_ms = 0, emit_ms = 0, sort_ms = 0, index_ms = 0, fill_ms = 0, d2h_ms = 0;
     const bool timed = (ctx->flags & RZ_FLAG_SYNC_STAGES) != 0;
-    auto lap = [&](float& acc, int ea, int eb) {
-        if (!timed) return;
-        CUDA_TRY(cudaEventSynchronize(c.ev[eb]));
-        float ms = 0;
-        CUDA_TRY(cudaEventElapsedTime(&ms, c.ev[ea], c.ev[eb]));
-        acc += ms;
+    // Stage timings: every stage records its own event pair and the pairs are read once per window, after
+    // the window's last kernel: no host synchronisation sits between the stages being timed.
+    float* lap_acc[6];
+    int n_laps = 0;
+    auto lap = [&](float& acc, int, int) {
+        if (timed) lap_acc[n_laps++] = &acc;
+    };
+    auto flush_laps = [&]() {
+        if (!timed || !n_laps) return;
+        CUDA_TRY(cudaEventSynchronize(c.ev[EV_A0 + 2 * n_laps - 1]));
+        for (int i = 0; i < n_laps; i++) {
+            float ms = 0;
+            CUDA_TRY(cudaEventElapsedTime(&ms, c.ev[EV_A0 + 2 * i], c.ev[EV_A0 + 2 * i + 1]));
+            *lap_acc[i] += ms;
+        }
+        n_laps = 0;
+    };
+#define EV_A (EV_A0 + 2 * n_laps)
+#define EV_B (EV_A0 + 2 * n_laps + 1)
+    // Host output: windows are rendered into two staging buffers in turn; the copy of a finished window runs
+    // on the copy stream while the next window is computed (PCIe D2H is the longest phase of an end-to-end call).
+    uint32_t n_staged = 0;
+    auto stage_begin = [&](uint32_t rows) -> void* {  // staging buffer the window's kernels may write now
+        DevBuf& b = (n_staged & 1) ? c.win_out2 : c.win_out;
+        if (n_staged >= 2) CUDA_TRY(cudaStreamWaitEvent(s, c.ev_copied[n_staged & 1], 0));
+        else b.ensure((size_t)n_bands * std::max(rows, std::min(win_rows, shard_rows)) * ri.ncols * isz);  // largest window
+        return b.p;
+    };
+    auto stage_copy = [&](const Window& w, void* d_out) {  // window finished on `s`: copy it back asynchronously
+        const uint32_t k = n_staged & 1, rows = w.r1 - w.r0;
+        CUDA_TRY(cudaEventRecord(c.ev_filled[k], s));
+        CUDA_TRY(cudaStreamWaitEvent(c.copy_stream, c.ev_filled[k], 0));
+        if (n_staged == 0) CUDA_TRY(cudaEventRecord(c.ev_d2h[0], c.copy_stream));
+        const size_t chunk = (size_t)rows * ri.ncols * isz;
+        for (uint32_t b = 0; b < n_bands; b++) {
+            char* dst = (char*)out + ((size_t)b * shard_rows + (w.r0 - shard_r0)) * ri.ncols * isz;
+            CUDA_TRY(cudaMemcpyAsync(dst, (char*)d_out + (size_t)b * chunk, chunk, cudaMemcpyDeviceToHost, c.copy_stream));
+        }
+        CUDA_TRY(cudaEventRecord(c.ev_copied[k], c.copy_stream));
+        S.d2h_bytes += chunk * n_bands;
+        n_staged++;
     };
     const uint32_t nv_poly = (uint32_t)g->pool[0].size(), nv_line = (uint32_t)g->pool[1].size(),
                    nv_pt = (uint32_t)g->pool[2].size();
@@ -608,7 +707,13 @@ static void rasterize_dense(rz_geoms* g, const rz_context* ctx, void* out, rz_st
                     c.task_start.ensure(((size_t)T.n_tiles + 1) * 4);
                     task_index_kernel<<<(T.n_tiles + 1 + 255) / 256, 256, 0, s>>>(ka, n_rec, block_bits, T.n_tiles,
                                                                                 c.task_start.as<uint32_t>());
-                    launches++;
+                    c.tile_pos.ensure(std::max<size_t>((size_t)n_rec * 4, 64));
+                    c.tile_val2.ensure(std::max<size_t>((size_t)n_rec * 8, 64));
+                    if (n_rec)
+                        block_pos_kernel<<<(n_rec + 255) / 256, 256, 0, s>>>(
+                            ka, n_rec, block_bits, c.tile_val.as<unsigned long long>(), c.tile_pos.as<uint32_t>(),
+                            c.tile_val2.as<unsigned long long>());
+                    launches += 2;
                     if (timed) CUDA_TRY(cudaEventRecord(c.ev[EV_B], s));
                     lap(sort_ms, EV_A, EV_B);
                     // ---- inside masks of every (part, tile) pair ----------------------------------
@@ -616,9 +721,10 @@ static void rasterize_dense(rz_geoms* g, const rz_context* ctx, void* out, rz_st
                     if (!tile_vertices_ready) {  // pixel-space vertices, shared by all windows of this call
                         c.tile_px.ensure((size_t)(nv_poly + 1) * 8);
                         c.tile_py.ensure((size_t)(nv_poly + 1) * 8);
-                        vertex_transform_kernel<<<(nv_poly + 255) / 256, 256, 0, s>>>(P, dg->x[0], dg->y[0], nv_poly,
-                                                                                     c.tile_px.as<double>(),
-                                                                                     c.tile_py.as<double>());
+                        c.tile_vrow.ensure((size_t)(nv_poly + 1) * 4);
+                        vertex_transform_kernel<<<(nv_poly + 255) / 256, 256, 0, s>>>(
+                            P, dg->x[0], dg->y[0], dg->tag[0], nv_poly, c.tile_px.as<double>(), c.tile_py.as<double>(),
+                            c.tile_vrow.as<uint32_t>());
                         launches++;
                         tile_vertices_ready = true;
                     }
@@ -627,13 +733,13 @@ static void rasterize_dense(rz_geoms* g, const rz_context* ctx, void* out, rz_st
                         if (T.tile_r == 64)
                             tile_mask_kernel<64><<<grid, MASK_WARPS * 32, 0, s>>>(
                                 P, T, c.tile_pairs.as<uint64_t>(), n_rows, c.tile_pt.as<PartTile>(), dg->part_vbeg,
-                                dg->part_vend, c.tile_px.as<double>(), c.tile_py.as<double>(), dg->tag[0],
-                                c.tile_masks.as<uint32_t>());
+                                dg->part_vend, c.tile_px.as<double>(), c.tile_py.as<double>(),
+                                c.tile_vrow.as<uint32_t>(), c.tile_pos.as<uint32_t>(), c.tile_masks.as<uint32_t>());
                         else
                             tile_mask_kernel<32><<<grid, MASK_WARPS * 32, 0, s>>>(
                                 P, T, c.tile_pairs.as<uint64_t>(), n_rows, c.tile_pt.as<PartTile>(), dg->part_vbeg,
-                                dg->part_vend, c.tile_px.as<double>(), c.tile_py.as<double>(), dg->tag[0],
-                                c.tile_masks.as<uint32_t>());
+                                dg->part_vend, c.tile_px.as<double>(), c.tile_py.as<double>(),
+                                c.tile_vrow.as<uint32_t>(), c.tile_pos.as<uint32_t>(), c.tile_masks.as<uint32_t>());
                         launches++;
                     }
                     if (timed) CUDA_TRY(cudaEventRecord(c.ev[EV_B], s));
@@ -646,14 +752,13 @@ static void rasterize_dense(rz_geoms* g, const rz_context* ctx, void* out, rz_st
                         T.out_rows = shard_rows;
                         T.win_row_off = w.r0 - shard_r0;
                     } else {
-                        c.win_out.ensure((size_t)n_bands * rows * ri.ncols * isz);
-                        d_out = c.win_out.p;
+                        d_out = stage_begin(rows);
                         T.out_rows = rows;
                         T.win_row_off = 0;
                     }
                     T.vec_ok = ((uintptr_t)d_out % 16 == 0) && ((ri.ncols * isz) % 16 == 0);
-                    tile_for(ctx->dtype, ctx->pixel_fn)(T.n_tiles, s, P, T, ka, c.task_start.as<uint32_t>(),
-                                                        c.tile_val.as<unsigned long long>(), block_bits,
+                    tile_for(ctx->dtype, ctx->pixel_fn)(T.n_tiles, s, P, T, c.task_start.as<uint32_t>(),
+                                                        c.tile_val2.as<unsigned long long>(),
                                                         c.tile_masks.as<uint32_t>(), bg_bits, d_out);
                     launches++;
                     CUDA_TRY(cudaGetLastError());
@@ -665,18 +770,8 @@ static void rasterize_dense(rz_geoms* g, const rz_context* ctx, void* out, rz_st
                     S.n_windows++;
                     S.key_bits = std::max(S.key_bits, tkey_bits);
                     S.tile_width = TILE_C;
-                    if (!out_dev) {
-                        if (timed) CUDA_TRY(cudaEventRecord(c.ev[EV_A], s));
-                        const size_t chunk = (size_t)rows * ri.ncols * isz;
-                        for (uint32_t b = 0; b < n_bands; b++) {
-                            char* dst = (char*)out + ((size_t)b * shard_rows + (w.r0 - shard_r0)) * ri.ncols * isz;
-                            CUDA_TRY(cudaMemcpyAsync(dst, (char*)d_out + (size_t)b * chunk, chunk, cudaMemcpyDeviceToHost, s));
-                        }
-                        S.d2h_bytes += chunk * n_bands;
-                        if (timed) CUDA_TRY(cudaEventRecord(c.ev[EV_B], s));
-                        CUDA_TRY(cudaStreamSynchronize(s));
-                        lap(d2h_ms, EV_A, EV_B);
-                    }
+                    if (!out_dev) stage_copy(w, d_out);
+                    flush_laps();
                     continue;
                 }
             }
@@ -725,6 +820,7 @@ static void rasterize_dense(rz_geoms* g, const rz_context* ctx, void* out, rz_st
             uint32_t mid = w.r0 + rows / 2;
             todo.push_back(Window{mid, w.r1});
             todo.push_back(Window{w.r0, mid});
+            flush_laps();
             continue;
         }
         if (n_rec >= (1ull << 32) - 4096) throw Error{RZ_RUNTIME_ERROR, "Too many records in a single raster row."};
@@ -828,8 +924,7 @@ static void rasterize_dense(rz_geoms* g, const rz_context* ctx, void* out, rz_st
             F.out_rows = shard_rows;
             F.win_row_off = w.r0 - shard_r0;
         } else {
-            c.win_out.ensure((size_t)n_bands * rows * ri.ncols * isz);
-            d_out = c.win_out.p;
+            d_out = stage_begin(rows);
             F.out_rows = rows;
             F.win_row_off = 0;
         }
@@ -843,22 +938,17 @@ static void rasterize_dense(rz_geoms* g, const rz_context* ctx, void* out, rz_st
         lap(fill_ms, EV_A, EV_B);
 
         // ---- copy back ----------------------------------------------------------------------
-        if (!out_dev) {
-            if (timed) CUDA_TRY(cudaEventRecord(c.ev[EV_A], s));
-            const size_t chunk = (size_t)rows * ri.ncols * isz;
-            for (uint32_t b = 0; b < n_bands; b++) {
-                char* dst = (char*)out + ((size_t)b * shard_rows + (w.r0 - shard_r0)) * ri.ncols * isz;
-                CUDA_TRY(cudaMemcpyAsync(dst, (char*)d_out + (size_t)b * chunk, chunk, cudaMemcpyDeviceToHost, s));
-            }
-            S.d2h_bytes += chunk * n_bands;
-            if (timed) CUDA_TRY(cudaEventRecord(c.ev[EV_B], s));
-            CUDA_TRY(cudaStreamSynchronize(s));  // staging buffer is reused by the next window
-            lap(d2h_ms, EV_A, EV_B);
-        }
+        if (!out_dev) stage_copy(w, d_out);
+        flush_laps();
+    }
+    if (!out_dev && n_staged) {  // the call returns when the last window has landed in host memory
+        CUDA_TRY(cudaEventRecord(c.ev_d2h[1], c.copy_stream));
+        CUDA_TRY(cudaStreamWaitEvent(s, c.ev_d2h[1], 0));
     }
     CUDA_TRY(cudaEventRecord(c.ev[EV_END], s));
     if (!out_dev || timed) {
         CUDA_TRY(cudaEventSynchronize(c.ev[EV_END]));
+        if (!out_dev && n_staged) CUDA_TRY(cudaEventElapsedTime(&d2h_ms, c.ev_d2h[0], c.ev_d2h[1]));
         CUDA_TRY(cudaEventElapsedTime(&S.total_ms, c.ev[EV_START], c.ev[EV_END]));
         CUDA_TRY(cudaEventElapsedTime(&S.h2d_ms, c.ev[EV_START], c.ev[EV_H2D]));
     }
@@ -870,6 +960,8 @@ static void rasterize_dense(rz_geoms* g, const rz_context* ctx, void* out, rz_st
     S.d2h_ms = d2h_ms;
     S.kernel_launches = launches;
     if (st) *st = S;
+#undef EV_A
+#undef EV_B
 }
 
 
@@ -885,33 +977,52 @@ struct rz_sparse {
 
 namespace rz {
 
+struct SparseJob {
+    uint32_t n_rec, nv_poly, nv_line, nv_pt;
+    const uint64_t* keys;
+    VisitSet vs;
+    bool touched, line_dedup, poly_dedup;
+};
+
 template <typename N>
-static void sparse_expand(cudaStream_t s, const KParams& P, SparseLayout L, DeviceGeoms* dg, DeviceCtx& c, uint32_t n_rec,
-                          const uint64_t* keys, uint32_t nv_line, uint32_t nv_pt, VisitSet vs, bool line_dedup,
-                          uint32_t& launches) {
+static void sparse_expand(cudaStream_t s, const KParams& P, SparseLayout L, DeviceGeoms* dg, DeviceCtx& c,
+                          const SparseJob& J, uint32_t& launches) {
     unsigned long long* rows = c.sp_rows.as<unsigned long long>();
     unsigned long long* cols = c.sp_cols.as<unsigned long long>();
     N* data = c.sp_data.as<N>();
     const PartInfo* info = c.part_info.as<PartInfo>();
     const unsigned long long* base = c.sp_f.as<unsigned long long>();
     const unsigned long long* start = c.sp_e.as<unsigned long long>();
-    if (n_rec) {
-        poly_expand_kernel<N><<<(n_rec + 255) / 256, 256, 0, s>>>(keys, c.sp_a.as<uint32_t>(),
-                                                                 c.sp_b.as<unsigned long long>(), n_rec, L, info, base,
-                                                                 start, rows, cols, data);
+    if (J.n_rec) {
+        if (J.poly_dedup)
+            poly_expand_dedup_kernel<N><<<(J.n_rec + 255) / 256, 256, 0, s>>>(
+                J.keys, c.sp_a.as<uint32_t>(), c.sp_b.as<unsigned long long>(), J.n_rec, L, J.vs, info, base, start, rows,
+                cols, data);
+        else
+            poly_expand_kernel<N><<<(J.n_rec + 255) / 256, 256, 0, s>>>(J.keys, c.sp_a.as<uint32_t>(),
+                                                                       c.sp_b.as<unsigned long long>(), J.n_rec, L, info,
+                                                                       base, start, rows, cols, data);
         launches++;
     }
-    if (nv_line) {
-        line_expand_kernel<N><<<(nv_line + 255) / 256, 256, 0, s>>>(
-            P, dg->x[1], dg->y[1], dg->tag[1], nv_line, info, c.last_kept.as<uint32_t>(), c.counters.as<Counters>(),
-            c.sp_c.as<unsigned long long>(), c.sp_raw.as<unsigned long long>(), vs, line_dedup ? 1 : 0, base, start, rows, cols,
-            data);
+    if (J.touched && J.nv_poly) {  // pass 1 of every polygon part: its rings' boundary walk
+        line_expand_kernel<N, true><<<(J.nv_poly + 255) / 256, 256, 0, s>>>(
+            P, dg->x[0], dg->y[0], dg->tag[0], J.nv_poly, info, c.last_kept.as<uint32_t>(), c.counters.as<Counters>(),
+            c.sp_w.as<unsigned long long>(), c.sp_wraw.as<unsigned long long>(), J.vs, J.poly_dedup ? 1 : 0, base,
+            c.sp_ws.as<unsigned long long>(), rows, cols, data);
         launches++;
     }
-    if (nv_pt) {
-        point_expand_kernel<N><<<(nv_pt + 255) / 256, 256, 0, s>>>(P, dg->x[2], dg->y[2], dg->tag[2], nv_pt, info,
-                                                                  c.sp_d.as<unsigned long long>(), base, start, rows,
-                                                                  cols, data);
+    if (J.nv_line) {
+        auto k = J.touched ? line_expand_kernel<N, true> : line_expand_kernel<N, false>;
+        k<<<(J.nv_line + 255) / 256, 256, 0, s>>>(P, dg->x[1], dg->y[1], dg->tag[1], J.nv_line, info,
+                                                  c.last_kept.as<uint32_t>(), c.counters.as<Counters>(),
+                                                  c.sp_c.as<unsigned long long>(), c.sp_raw.as<unsigned long long>(), J.vs,
+                                                  J.line_dedup ? 1 : 0, base, start, rows, cols, data);
+        launches++;
+    }
+    if (J.nv_pt) {
+        point_expand_kernel<N><<<(J.nv_pt + 255) / 256, 256, 0, s>>>(P, dg->x[2], dg->y[2], dg->tag[2], J.nv_pt, info,
+                                                                    c.sp_d.as<unsigned long long>(), base, start, rows,
+                                                                    cols, data);
         launches++;
     }
 }
@@ -925,8 +1036,6 @@ static void rasterize_sparse(rz_geoms* g, const rz_context* ctx, rz_sparse* out,
     const size_t isz = dtype_size(ctx->dtype);
     if (!isz) throw Error{RZ_VALUE_ERROR, "Unsupported dtype"};
     if (ctx->pixel_fn < 0 || ctx->pixel_fn > RZ_ANY) throw Error{RZ_VALUE_ERROR, "Unknown pixel function"};
-    if (ctx->all_touched)
-        throw Error{RZ_RUNTIME_ERROR, "all_touched=True is not implemented on the B200 path yet."};
     const uint32_t n_bands = ctx->band_of_geom ? (uint32_t)std::max(ctx->n_bands, 0) : 1u;
     out->counts.assign(n_bands, 0);
     if (ri.nrows == 0 || ri.ncols == 0 || n_bands == 0) return;
@@ -934,7 +1043,12 @@ static void rasterize_sparse(rz_geoms* g, const rz_context* ctx, rz_sparse* out,
         throw Error{RZ_RUNTIME_ERROR, "Raster dimensions above 2^31 are not supported."};
     const uint32_t nv_poly = (uint32_t)g->pool[0].size(), nv_line = (uint32_t)g->pool[1].size(),
                    nv_pt = (uint32_t)g->pool[2].size();
-    const bool line_dedup = ri.xres != ri.yres && nv_line;  // burn_geometry.rs:179, 202
+    // all_touched (burners.rs:94-247): line parts and, as pass 1, polygon rings are walked GDAL-style; with
+    // sum / count (S::REQUIRES_DEDUP, prelude.rs:116-118) every part writes a pixel once (PixelCache)
+    const bool touched = ctx->all_touched != 0;
+    const bool fn_dedup = touched && (ctx->pixel_fn == RZ_SUM || ctx->pixel_fn == RZ_COUNT);
+    const bool line_dedup = (ri.xres != ri.yres || fn_dedup) && nv_line;  // burn_geometry.rs:179, 202
+    const bool poly_dedup = fn_dedup && nv_poly;                          // burn_geometry.rs:99-103
 
     DeviceCtx& c = device_ctx(ctx->device);
     std::lock_guard<std::mutex> lk(c.mu);
@@ -1053,58 +1167,95 @@ static void rasterize_sparse(rz_geoms* g, const rz_context* ctx, rz_sparse* out,
             keys = ka;
         }
     }
-    // ---- spans: pair the sorted crossings, prefix-sum their lengths ------------------------------
-    unsigned long long poly_total = 0, line_total = 0, pt_total = 0;
+    // ---- write counts of every unit -------------------------------------------------------------------
+    unsigned long long poly_total = 0, line_total = 0, pt_total = 0, walk_total = 0;
     VisitSet vs;
     std::memset(&vs, 0, sizeof vs);
-    if (n_rec) {
+    if (n_rec) {  // (part,row) segments of the sorted crossings
         c.sp_a.ensure((size_t)n_rec * 4);  // seg_start
         c.sp_b.ensure((size_t)n_rec * 8);  // poly_off
         device_scan<OpMax>(InSegHead{keys, L.col_bits}, n_rec, OutSegStart{c.sp_a.as<uint32_t>()}, c.sp_partial, s,
                            launches);
-        device_scan<OpAdd>(InSpanLen{keys, c.sp_a.as<uint32_t>(), n_rec, L.col_bits}, n_rec,
-                           OutPrefix64{c.sp_b.as<unsigned long long>()}, c.sp_partial, s, launches);
-        poly_total = scan_total(c.sp_partial, n_rec, s);
     }
+    // raw write counts of the line parts and of the polygon boundary walks
+    const InLineLen<false> line_len{P, dg->x[1], dg->y[1], dg->tag[1], d_info, c.last_kept.as<uint32_t>(), d_ctr, nv_line};
+    const InLineLen<true> line_walk{P, dg->x[1], dg->y[1], dg->tag[1], d_info, c.last_kept.as<uint32_t>(), d_ctr, nv_line};
+    const InLineLen<true> poly_walk{P, dg->x[0], dg->y[0], dg->tag[0], d_info, c.last_kept.as<uint32_t>(), d_ctr, nv_poly};
     if (nv_line) {
-        CUDA_TRY(cudaMemsetAsync(c.last_kept.p, 0, (size_t)n_parts * 4, s));
-        line_last_kept_kernel<<<(nv_line + 255) / 256, 256, 0, s>>>(P, dg->x[1], dg->y[1], dg->tag[1], nv_line, d_info,
-                                                                   c.last_kept.as<uint32_t>(), d_ctr);
-        launches++;
         c.sp_c.ensure((size_t)nv_line * 8);
-        const InLineLen line_len{P, dg->x[1], dg->y[1], dg->tag[1], d_info, c.last_kept.as<uint32_t>(), d_ctr, nv_line};
-        device_scan<OpAdd>(line_len, nv_line, OutPrefix64{c.sp_c.as<unsigned long long>()}, c.sp_partial, s, launches);
+        if (touched) {
+            device_scan<OpAdd>(line_walk, nv_line, OutPrefix64{c.sp_c.as<unsigned long long>()}, c.sp_partial, s, launches);
+        } else {
+            CUDA_TRY(cudaMemsetAsync(c.last_kept.p, 0, (size_t)n_parts * 4, s));
+            line_last_kept_kernel<<<(nv_line + 255) / 256, 256, 0, s>>>(P, dg->x[1], dg->y[1], dg->tag[1], nv_line,
+                                                                       d_info, c.last_kept.as<uint32_t>(), d_ctr);
+            launches++;
+            device_scan<OpAdd>(line_len, nv_line, OutPrefix64{c.sp_c.as<unsigned long long>()}, c.sp_partial, s, launches);
+        }
         line_total = scan_total(c.sp_partial, nv_line, s);
         CUDA_TRY(cudaMemcpyAsync(c.h_counters, d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, s));
         CUDA_TRY(cudaStreamSynchronize(s));
         if (c.h_counters->bad_line)
             throw Error{RZ_RUNTIME_ERROR,
                         "A line segment extends more than 2^29 pixels from the raster origin; unsupported."};
-        if (line_dedup && line_total) {
-            // non-square pixels: a line part writes a pixel only on its first visit.  Burn indices come
-            // from the raw prefix; a hash set keeps the smallest one per (part,row,col); kept writes are
-            // then re-scanned.
-            unsigned long long cap = 1024;
-            while (cap < 2 * line_total) cap <<= 1;
-            c.vs_keys.ensure(cap * 8);
-            c.vs_first.ensure(cap * 8);
-            CUDA_TRY(cudaMemsetAsync(c.vs_keys.p, 0xff, cap * 8, s));
-            CUDA_TRY(cudaMemsetAsync(c.vs_first.p, 0xff, cap * 8, s));
-            vs.keys = c.vs_keys.as<unsigned long long>();
-            vs.first = c.vs_first.as<unsigned long long>();
-            vs.mask = cap - 1;
-            vs.col_bits = L.col_bits;
-            vs.row_bits = L.row_bits;
-            c.sp_raw.ensure((size_t)nv_line * 8);
-            CUDA_TRY(cudaMemcpyAsync(c.sp_raw.p, c.sp_c.p, (size_t)nv_line * 8, cudaMemcpyDeviceToDevice, s));
-            line_visit_insert_kernel<<<(nv_line + 255) / 256, 256, 0, s>>>(
-                P, dg->x[1], dg->y[1], dg->tag[1], nv_line, d_info, c.last_kept.as<uint32_t>(), d_ctr,
-                c.sp_raw.as<unsigned long long>(), vs);
-            launches++;
-            device_scan<OpAdd>(InLineKept{line_len, c.sp_raw.as<unsigned long long>(), vs}, nv_line,
+    }
+    if (touched && nv_poly) {
+        c.sp_w.ensure((size_t)nv_poly * 8);   // walk_off
+        c.sp_ws.ensure((size_t)n_parts * 8);  // walk_start
+        device_scan<OpAdd>(poly_walk, nv_poly, OutPrefix64{c.sp_w.as<unsigned long long>()}, c.sp_partial, s, launches);
+        walk_total = scan_total(c.sp_partial, nv_poly, s);
+    }
+    // First-visit filter (PixelCache): burn indices come from the raw prefixes; a hash set keeps the smallest
+    // one per (part,row,col); kept writes are then re-scanned.
+    const bool ld = line_dedup && line_total, pd = poly_dedup && walk_total;
+    if (ld || pd) {
+        const unsigned long long entries = (ld ? line_total : 0) + (pd ? walk_total : 0);
+        unsigned long long cap = 1024;
+        while (cap < 2 * entries) cap <<= 1;
+        c.vs_keys.ensure(cap * 8);
+        c.vs_first.ensure(cap * 8);
+        CUDA_TRY(cudaMemsetAsync(c.vs_keys.p, 0xff, cap * 8, s));
+        CUDA_TRY(cudaMemsetAsync(c.vs_first.p, 0xff, cap * 8, s));
+        vs.keys = c.vs_keys.as<unsigned long long>();
+        vs.first = c.vs_first.as<unsigned long long>();
+        vs.mask = cap - 1;
+        vs.col_bits = L.col_bits;
+        vs.row_bits = L.row_bits;
+    }
+    if (ld) {
+        c.sp_raw.ensure((size_t)nv_line * 8);
+        CUDA_TRY(cudaMemcpyAsync(c.sp_raw.p, c.sp_c.p, (size_t)nv_line * 8, cudaMemcpyDeviceToDevice, s));
+        auto ins = touched ? line_visit_insert_kernel<true> : line_visit_insert_kernel<false>;
+        ins<<<(nv_line + 255) / 256, 256, 0, s>>>(P, dg->x[1], dg->y[1], dg->tag[1], nv_line, d_info,
+                                                  c.last_kept.as<uint32_t>(), d_ctr, c.sp_raw.as<unsigned long long>(), vs);
+        launches++;
+        if (touched)
+            device_scan<OpAdd>(InLineKept<true>{line_walk, c.sp_raw.as<unsigned long long>(), vs}, nv_line,
                                OutPrefix64{c.sp_c.as<unsigned long long>()}, c.sp_partial, s, launches);
-            line_total = scan_total(c.sp_partial, nv_line, s);
-        }
+        else
+            device_scan<OpAdd>(InLineKept<false>{line_len, c.sp_raw.as<unsigned long long>(), vs}, nv_line,
+                               OutPrefix64{c.sp_c.as<unsigned long long>()}, c.sp_partial, s, launches);
+        line_total = scan_total(c.sp_partial, nv_line, s);
+    }
+    if (pd) {
+        c.sp_wraw.ensure((size_t)nv_poly * 8);
+        CUDA_TRY(cudaMemcpyAsync(c.sp_wraw.p, c.sp_w.p, (size_t)nv_poly * 8, cudaMemcpyDeviceToDevice, s));
+        line_visit_insert_kernel<true><<<(nv_poly + 255) / 256, 256, 0, s>>>(
+            P, dg->x[0], dg->y[0], dg->tag[0], nv_poly, d_info, c.last_kept.as<uint32_t>(), d_ctr,
+            c.sp_wraw.as<unsigned long long>(), vs);
+        launches++;
+        device_scan<OpAdd>(InLineKept<true>{poly_walk, c.sp_wraw.as<unsigned long long>(), vs}, nv_poly,
+                           OutPrefix64{c.sp_w.as<unsigned long long>()}, c.sp_partial, s, launches);
+        walk_total = scan_total(c.sp_partial, nv_poly, s);
+    }
+    if (n_rec) {  // spans: pair the sorted crossings, prefix-sum their (kept) lengths
+        const InSpanLen span_len{keys, c.sp_a.as<uint32_t>(), n_rec, L.col_bits};
+        if (pd)
+            device_scan<OpAdd>(InSpanKept{span_len, vs, L.row_bits}, n_rec, OutPrefix64{c.sp_b.as<unsigned long long>()},
+                               c.sp_partial, s, launches);
+        else
+            device_scan<OpAdd>(span_len, n_rec, OutPrefix64{c.sp_b.as<unsigned long long>()}, c.sp_partial, s, launches);
+        poly_total = scan_total(c.sp_partial, n_rec, s);
     }
     if (nv_pt) {
         c.sp_d.ensure((size_t)nv_pt * 8);
@@ -1122,8 +1273,9 @@ static void rasterize_sparse(rz_geoms* g, const rz_context* ctx, rz_sparse* out,
     part_count_kernel<<<(n_parts + 255) / 256, 256, 0, s>>>(
         n_parts, dg->part_kind, dg->part_vbeg, dg->part_vend, c.task_start.as<uint32_t>(),
         c.sp_b.as<unsigned long long>(), n_rec, poly_total, c.sp_c.as<unsigned long long>(), nv_line, line_total,
-        c.sp_d.as<unsigned long long>(), nv_pt, pt_total, c.sp_g.as<unsigned long long>(),
-        c.sp_e.as<unsigned long long>());
+        c.sp_d.as<unsigned long long>(), nv_pt, pt_total,
+        (touched && nv_poly) ? c.sp_w.as<unsigned long long>() : nullptr, nv_poly, walk_total,
+        c.sp_g.as<unsigned long long>(), c.sp_e.as<unsigned long long>(), c.sp_ws.as<unsigned long long>());
     launches += 2;
     unsigned long long total = 0;
     for (uint32_t b = 0; b < n_bands; b++) {  // bands in sorted key order, parts ascending inside a band
@@ -1142,11 +1294,21 @@ static void rasterize_sparse(rz_geoms* g, const rz_context* ctx, rz_sparse* out,
         c.sp_rows.ensure(total * 8);
         c.sp_cols.ensure(total * 8);
         c.sp_data.ensure(total * isz);
+        SparseJob J;
+        J.n_rec = n_rec;
+        J.nv_poly = nv_poly;
+        J.nv_line = nv_line;
+        J.nv_pt = nv_pt;
+        J.keys = keys;
+        J.vs = vs;
+        J.touched = touched;
+        J.line_dedup = ld;
+        J.poly_dedup = pd;
         switch (isz) {  // triplet values are moved bit-wise: dispatch on the item size only
-            case 1: sparse_expand<uint8_t>(s, P, L, dg, c, n_rec, keys, nv_line, nv_pt, vs, line_dedup && line_total, launches); break;
-            case 2: sparse_expand<uint16_t>(s, P, L, dg, c, n_rec, keys, nv_line, nv_pt, vs, line_dedup && line_total, launches); break;
-            case 4: sparse_expand<uint32_t>(s, P, L, dg, c, n_rec, keys, nv_line, nv_pt, vs, line_dedup && line_total, launches); break;
-            default: sparse_expand<uint64_t>(s, P, L, dg, c, n_rec, keys, nv_line, nv_pt, vs, line_dedup && line_total, launches); break;
+            case 1: sparse_expand<uint8_t>(s, P, L, dg, c, J, launches); break;
+            case 2: sparse_expand<uint16_t>(s, P, L, dg, c, J, launches); break;
+            case 4: sparse_expand<uint32_t>(s, P, L, dg, c, J, launches); break;
+            default: sparse_expand<uint64_t>(s, P, L, dg, c, J, launches); break;
         }
         CUDA_TRY(cudaGetLastError());
         CUDA_TRY(cudaMemcpyAsync(out->rows.data(), c.sp_rows.p, total * 8, cudaMemcpyDeviceToHost, s));

@@ -6,6 +6,7 @@
 #include <map>
 #include <mutex>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/rz_b200.h"
@@ -43,6 +44,7 @@ struct rz_geoms {
     bool has_bounds = false;
     double bounds[4] = {0, 0, 0, 0};   // union of geo::BoundingRect, xmin ymin xmax ymax
     bool pinned = false;
+    std::vector<std::pair<void*, size_t>> pinned_ranges;  // what cudaHostRegister accepted
 
     std::mutex mu;
     std::map<int, rz::DeviceGeoms*> dev;  // cached device copies, by ordinal

@@ -834,9 +834,11 @@ template <> __device__ __forceinline__ float add_v<float>(float a, float b) { re
 template <> __device__ __forceinline__ double add_v<double>(double a, double b) { return __dadd_rn(a, b); }
 
 // BGNAN: the background is NaN, so `cur == bg` can never hold and the test reduces to is_nan(cur)
-template <typename N, int FN, bool BGNAN = false> __device__ __forceinline__ N apply_px(N cur, N v, N bg) {
+// VOK: the caller has checked that v is not NaN (sum's `isnan(v)` test is then dropped)
+template <typename N, int FN, bool BGNAN = false, bool VOK = false>
+__device__ __forceinline__ N apply_px(N cur, N v, N bg) {
     bool untouched = BGNAN ? is_nan_v(cur) : ((cur == bg) || is_nan_v(cur));
-    if (FN == RZ_SUM) return (untouched || is_nan_v(v)) ? v : add_v(cur, v);
+    if (FN == RZ_SUM) return (untouched || (!VOK && is_nan_v(v))) ? v : add_v(cur, v);
     if (FN == RZ_FIRST) return untouched ? v : cur;
     if (FN == RZ_LAST) return v;
     if (FN == RZ_MIN) return (untouched || cur > v) ? v : cur;

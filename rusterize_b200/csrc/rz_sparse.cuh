@@ -186,12 +186,25 @@ poly_emit_sparse_kernel(KParams P, SparseLayout L, const double* __restrict__ x,
 // ---------------------------------------------------------------------------------------------
 // Calls f(part, row, col, j) for the j-th pixel write of segment i (clipped Bresenham run, then the
 // end pixel of the part's last kept segment when its line string is open, burners.rs:87-89).
-template <typename F>
+// TOUCHED: the pixels of the all_touched walk of segment i instead (burners.rs:94-247); the pool may then be
+// the polygon rings (pass 1 of burn_geometry.rs:225-238) as well as the line strings.
+template <bool TOUCHED, typename F>
 __device__ __forceinline__ void for_each_line_pixel(const KParams& P, const double* __restrict__ x,
                                                     const double* __restrict__ y, const uint32_t* __restrict__ tag,
                                                     const PartInfo* __restrict__ info,
                                                     const uint32_t* __restrict__ last_kept, Counters* ctr, uint32_t i,
                                                     uint32_t n, F f) {
+    if (TOUCHED) {
+        if (i >= n || (tag[i] & 0x80000000u)) return;
+        const uint32_t part = tag[i] & 0x3fffffffu;
+        if (info[part].band < 0) return;
+        const double x0 = px_x(P, x[i]), y0 = px_y(P, y[i]), x1 = px_x(P, x[i + 1]), y1 = px_y(P, y[i + 1]);
+        const double min_x = fmin(x0, x1), max_x = fmax(x0, x1), min_y = fmin(y0, y1), max_y = fmax(y0, y1);
+        if (!(min_x < P.ncols_f && max_x >= 0.0 && min_y < P.nrows_f && max_y >= 0.0)) return;  // edges.rs:130
+        uint32_t j = 0;
+        all_touched_walk(P, x0, y0, x1, y1, [&](uint32_t row, uint32_t col) { f(part, row, col, j++); });
+        return;
+    }
     LineRec l;
     bool kept;
     line_setup(P, x, y, tag, info, i, n, l, &kept, ctr);
@@ -236,12 +249,20 @@ struct VisitSet {
             }
         }
     }
+    __device__ __forceinline__ bool contains(unsigned long long k) const {
+        for (unsigned long long h = slot_of(k);; h = (h + 1) & mask) {
+            const unsigned long long cur = keys[h];
+            if (cur == k) return true;
+            if (cur == ~0ull) return false;
+        }
+    }
     __device__ __forceinline__ bool is_first(unsigned long long k, unsigned long long burn) const {
         for (unsigned long long h = slot_of(k);; h = (h + 1) & mask)
             if (keys[h] == k) return first[h] == burn;
     }
 };
 
+template <bool TOUCHED>
 __global__ void line_visit_insert_kernel(KParams P, const double* __restrict__ x, const double* __restrict__ y,
                                          const uint32_t* __restrict__ tag, uint32_t n, const PartInfo* __restrict__ info,
                                          const uint32_t* __restrict__ last_kept, Counters* __restrict__ ctr,
@@ -249,9 +270,10 @@ __global__ void line_visit_insert_kernel(KParams P, const double* __restrict__ x
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const unsigned long long b0 = raw_off[i];
-    for_each_line_pixel(P, x, y, tag, info, last_kept, ctr, i, n, [&](uint32_t part, uint32_t row, uint32_t col, uint32_t j) {
-        vs.insert(vs.key_of(part, row, col), b0 + j);
-    });
+    for_each_line_pixel<TOUCHED>(P, x, y, tag, info, last_kept, ctr, i, n,
+                                 [&](uint32_t part, uint32_t row, uint32_t col, uint32_t j) {
+                                     vs.insert(vs.key_of(part, row, col), b0 + j);
+                                 });
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -291,7 +313,22 @@ struct OutPrefix64 {
     unsigned long long* off;
     __device__ void operator()(uint32_t i, unsigned long long exclusive, unsigned long long) const { off[i] = exclusive; }
 };
+// ... minus the pixels the part's boundary walk already wrote (FillWriter, writers.rs:39-60)
+struct InSpanKept {
+    InSpanLen base;
+    VisitSet vs;
+    uint32_t row_bits;
+    __device__ unsigned long long operator()(uint32_t i) const {
+        const uint32_t len = (uint32_t)base(i);
+        if (!len) return 0ull;
+        const uint64_t k = base.keys[i];  // [part | row | col]: the pixel keys of the span are k, k+1, ...
+        unsigned long long c = 0;
+        for (uint32_t j = 0; j < len; j++) c += !vs.contains(k + j);
+        return c;
+    }
+};
 // pixel writes of line segment i
+template <bool TOUCHED>
 struct InLineLen {
     KParams P;
     const double* x;
@@ -303,22 +340,24 @@ struct InLineLen {
     uint32_t n;
     __device__ unsigned long long operator()(uint32_t i) const {
         unsigned long long c = 0;
-        for_each_line_pixel(P, x, y, tag, info, last_kept, ctr, i, n, [&](uint32_t, uint32_t, uint32_t, uint32_t) { c++; });
+        for_each_line_pixel<TOUCHED>(P, x, y, tag, info, last_kept, ctr, i, n,
+                                     [&](uint32_t, uint32_t, uint32_t, uint32_t) { c++; });
         return c;
     }
 };
 // ... of which first visits of their pixel inside the part (non-square pixels)
+template <bool TOUCHED>
 struct InLineKept {
-    InLineLen base;
+    InLineLen<TOUCHED> base;
     const unsigned long long* raw_off;
     VisitSet vs;
     __device__ unsigned long long operator()(uint32_t i) const {
         unsigned long long c = 0;
         const unsigned long long b0 = raw_off[i];
-        for_each_line_pixel(base.P, base.x, base.y, base.tag, base.info, base.last_kept, base.ctr, i, base.n,
-                            [&](uint32_t part, uint32_t row, uint32_t col, uint32_t j) {
-                                c += vs.is_first(vs.key_of(part, row, col), b0 + j);
-                            });
+        for_each_line_pixel<TOUCHED>(base.P, base.x, base.y, base.tag, base.info, base.last_kept, base.ctr, i, base.n,
+                                     [&](uint32_t part, uint32_t row, uint32_t col, uint32_t j) {
+                                         c += vs.is_first(vs.key_of(part, row, col), b0 + j);
+                                     });
         return c;
     }
 };
@@ -370,8 +409,10 @@ __global__ void part_count_kernel(uint32_t n_parts, const uint8_t* __restrict__ 
                                   uint32_t n_rec, unsigned long long poly_total,
                                   const unsigned long long* __restrict__ line_off, uint32_t n_line,
                                   unsigned long long line_total, const unsigned long long* __restrict__ pt_off,
-                                  uint32_t n_pt, unsigned long long pt_total, unsigned long long* __restrict__ count,
-                                  unsigned long long* __restrict__ start) {
+                                  uint32_t n_pt, unsigned long long pt_total,
+                                  const unsigned long long* __restrict__ walk_off, uint32_t n_poly_v,
+                                  unsigned long long walk_total, unsigned long long* __restrict__ count,
+                                  unsigned long long* __restrict__ start, unsigned long long* __restrict__ walk_start) {
     uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n_parts) return;
     unsigned long long a = 0, b = 0;
@@ -380,6 +421,14 @@ __global__ void part_count_kernel(uint32_t n_parts, const uint8_t* __restrict__ 
         const uint32_t i0 = rec_beg[p], i1 = rec_beg[p + 1];
         a = i0 < n_rec ? poly_off[i0] : poly_total;
         b = i1 < n_rec ? poly_off[i1] : poly_total;
+        if (walk_off) {  // all_touched: the part's boundary walk is written before its fill
+            const unsigned long long wa = vbeg[p] < n_poly_v ? walk_off[vbeg[p]] : walk_total;
+            const unsigned long long wb = vend[p] < n_poly_v ? walk_off[vend[p]] : walk_total;
+            walk_start[p] = wa;
+            count[p] = (b - a) + (wb - wa);
+            start[p] = a - (wb - wa);  // modulo 2^64: fill offset inside the part = walk count + (prefix - a)
+            return;
+        }
     } else if (k == 1) {
         a = vbeg[p] < n_line ? line_off[vbeg[p]] : line_total;
         b = vend[p] < n_line ? line_off[vend[p]] : line_total;
@@ -460,7 +509,36 @@ poly_expand_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict
     }
 }
 
+// all_touched with sum / count: a fill pixel is written unless the part's boundary walk visited it; one
+// thread per span writes the kept pixels one after another
 template <typename N>
+__global__ void __launch_bounds__(256)
+poly_expand_dedup_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ seg_start,
+                         const unsigned long long* __restrict__ poly_off, uint32_t n, SparseLayout L, VisitSet vs,
+                         const PartInfo* __restrict__ info, const unsigned long long* __restrict__ part_base,
+                         const unsigned long long* __restrict__ part_start, unsigned long long* __restrict__ rows,
+                         unsigned long long* __restrict__ cols, N* __restrict__ data) {
+    const uint32_t i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    InSpanLen f{keys, seg_start, n, L.col_bits};
+    const uint32_t len = (uint32_t)f(i);
+    if (!len) return;
+    const uint64_t k = keys[i];
+    const uint32_t part = (uint32_t)(k >> (L.col_bits + L.row_bits));
+    const uint32_t row = (uint32_t)(k >> L.col_bits) & ((1u << L.row_bits) - 1u);
+    const uint32_t col = (uint32_t)k & ((1u << L.col_bits) - 1u);
+    const N v = value_from_bits<N>(info[part].value_bits);
+    unsigned long long d = part_base[part] + (poly_off[i] - part_start[part]);
+    for (uint32_t j = 0; j < len; j++) {
+        if (vs.contains(k + j)) continue;
+        rows[d] = row;
+        cols[d] = col + j;
+        data[d] = v;
+        d++;
+    }
+}
+
+template <typename N, bool TOUCHED>
 __global__ void __launch_bounds__(256)
 line_expand_kernel(KParams P, const double* __restrict__ x, const double* __restrict__ y,
                    const uint32_t* __restrict__ tag, uint32_t n, const PartInfo* __restrict__ info,
@@ -474,7 +552,7 @@ line_expand_kernel(KParams P, const double* __restrict__ x, const double* __rest
     unsigned long long d = 0;
     bool have_d = false;
     const unsigned long long b0 = dedup ? raw_off[i] : 0ull;
-    for_each_line_pixel(P, x, y, tag, info, last_kept, ctr, i, n, [&](uint32_t part, uint32_t row, uint32_t col, uint32_t j) {
+    for_each_line_pixel<TOUCHED>(P, x, y, tag, info, last_kept, ctr, i, n, [&](uint32_t part, uint32_t row, uint32_t col, uint32_t j) {
         if (!have_d) {
             d = part_base[part] + (line_off[i] - part_start[part]);
             have_d = true;
