@@ -109,8 +109,8 @@ struct DeviceCtx {
     cudaStream_t stream = nullptr;
     int sm_count = 148;
     DevBuf keys_a, keys_b, hist, digit_total, task_start, part_info, field, valid, band, last_kept, counters, win_out,
-        block_total, vs_keys, vs_first, sp_raw, tile_cnt, tile_cnt2, tile_off, tile_off2, tile_ctr, tile_px, tile_py,
-        tile_pt, tile_pairs, tile_masks, tile_val, tile_vrow, tile_pos, tile_val2, sp_a, sp_b, sp_c, sp_d, sp_e, sp_f, sp_g, sp_rows, sp_cols, sp_data, sp_partial, sp_w, sp_wraw, sp_ws;
+        block_total, vs_keys, vs_first, sp_raw, tile_cnt, tile_cnt2, tile_off, tile_off2, tile_ctr,
+        tile_pt, tile_pairs, tile_masks, tile_val, tile_pos, tile_val2, sp_a, sp_b, sp_c, sp_d, sp_e, sp_f, sp_g, sp_rows, sp_cols, sp_data, sp_partial, sp_w, sp_wraw, sp_ws;
     Counters* h_counters = nullptr;  // pinned
     cudaEvent_t ev[16];
     cudaStream_t copy_stream = nullptr;  // device->host copies of finished row windows overlap the next window
@@ -621,7 +621,6 @@ static void rasterize_dense(rz_geoms* g, const rz_context* ctx, void* out, rz_st
                    nv_pt = (uint32_t)g->pool[2].size();
     const uint32_t per_block = SETUP_THREADS * SETUP_ITEMS;
     const bool all_poly = nv_line == 0 && nv_pt == 0 && !ctx->all_touched;
-    bool tile_vertices_ready = false;
 
     while (!todo.empty()) {
         Window w = todo.back();
@@ -718,28 +717,18 @@ static void rasterize_dense(rz_geoms* g, const rz_context* ctx, void* out, rz_st
                     lap(sort_ms, EV_A, EV_B);
                     // ---- inside masks of every (part, tile) pair ----------------------------------
                     if (timed) CUDA_TRY(cudaEventRecord(c.ev[EV_A], s));
-                    if (!tile_vertices_ready) {  // pixel-space vertices, shared by all windows of this call
-                        c.tile_px.ensure((size_t)(nv_poly + 1) * 8);
-                        c.tile_py.ensure((size_t)(nv_poly + 1) * 8);
-                        c.tile_vrow.ensure((size_t)(nv_poly + 1) * 4);
-                        vertex_transform_kernel<<<(nv_poly + 255) / 256, 256, 0, s>>>(
-                            P, dg->x[0], dg->y[0], dg->tag[0], nv_poly, c.tile_px.as<double>(), c.tile_py.as<double>(),
-                            c.tile_vrow.as<uint32_t>());
-                        launches++;
-                        tile_vertices_ready = true;
-                    }
                     if (n_rows) {
                         const uint32_t grid = (n_rows + MASK_WARPS - 1) / MASK_WARPS;
                         if (T.tile_r == 64)
                             tile_mask_kernel<64><<<grid, MASK_WARPS * 32, 0, s>>>(
                                 P, T, c.tile_pairs.as<uint64_t>(), n_rows, c.tile_pt.as<PartTile>(), dg->part_vbeg,
-                                dg->part_vend, c.tile_px.as<double>(), c.tile_py.as<double>(),
-                                c.tile_vrow.as<uint32_t>(), c.tile_pos.as<uint32_t>(), c.tile_masks.as<uint32_t>());
+                                dg->part_vend, dg->x[0], dg->y[0], dg->tag[0], c.tile_pos.as<uint32_t>(),
+                                c.tile_masks.as<uint32_t>());
                         else
                             tile_mask_kernel<32><<<grid, MASK_WARPS * 32, 0, s>>>(
                                 P, T, c.tile_pairs.as<uint64_t>(), n_rows, c.tile_pt.as<PartTile>(), dg->part_vbeg,
-                                dg->part_vend, c.tile_px.as<double>(), c.tile_py.as<double>(),
-                                c.tile_vrow.as<uint32_t>(), c.tile_pos.as<uint32_t>(), c.tile_masks.as<uint32_t>());
+                                dg->part_vend, dg->x[0], dg->y[0], dg->tag[0], c.tile_pos.as<uint32_t>(),
+                                c.tile_masks.as<uint32_t>());
                         launches++;
                     }
                     if (timed) CUDA_TRY(cudaEventRecord(c.ev[EV_B], s));

@@ -35,7 +35,7 @@ constexpr uint32_t TILE_C = 128;           // columns per tile = 4 mask words pe
 constexpr uint32_t MASK_MAX_WORDS = 16;    // tile_mask: widest toggle-mask chunk kept in shared memory (512 columns)
 constexpr uint32_t MASK_SMEM_WORDS = 1280; // tile_mask: toggle-mask words per warp (rows x (chunk words + 1 pad))
 constexpr int MASK_WARPS = 4;
-constexpr uint32_t VROW_RING_END = 0x80000000u;  // vrow[]: "last vertex of its ring" flag of the vertex tag
+constexpr uint32_t VROW_RING_END = 0x80000000u;  // vertex tag: "last vertex of its ring"
 
 struct TileParams {
     uint32_t tile_r;           // rows per tile (64, or 32 for 8-byte dtypes)
@@ -183,23 +183,6 @@ struct InU32 {
     __device__ unsigned long long operator()(uint32_t i) const { return v[i]; }
 };
 
-// World -> pixel transform of every ring vertex, once per call (edges.rs:94-97), plus its row index
-// vrow = ceil(py - 0.5) clamped to [0, nrows] (edges.rs:32-33) with the vertex tag's ring-end flag in bit 31.
-// An edge (i, i+1) is active on rows [min(vrow_i, vrow_i+1), max(..)): tile_mask finds the edges that cross
-// its rows with integer compares on 4-byte loads and touches the f64 ordinates of those edges only.  The
-// reference's culling test (min_y < nrows && max_y >= 0, edges.rs:105) is implied: such edges clamp to an
-// empty row range.
-__global__ void vertex_transform_kernel(KParams P, const double* __restrict__ x, const double* __restrict__ y,
-                                        const uint32_t* __restrict__ tag, uint32_t n, double* __restrict__ px,
-                                        double* __restrict__ py, uint32_t* __restrict__ vrow) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const double yy = px_y(P, y[i]);
-    px[i] = px_x(P, x[i]);
-    py[i] = yy;
-    vrow[i] = vertex_row(P, yy) | (tag[i] & VROW_RING_END);
-}
-
 // One ring edge (pixel-space vertices): its crossing with a row's centre line.
 struct TileEdge {
     double x_top, y_top, dxdy;
@@ -242,10 +225,10 @@ __global__ void block_pos_kernel(const uint64_t* __restrict__ recs, uint32_t n, 
 // (centre 0.5): only that row's crossing count is tracked, and an odd row 0 drops its largest column like
 // chunks_exact(2) drops the unpaired tail (burners.rs:305).
 template <int TILE_R>
-__global__ void __launch_bounds__(MASK_WARPS * 32, 7)
+__global__ void __launch_bounds__(MASK_WARPS * 32, 6)
 tile_mask_kernel(KParams P, TileParams T, const uint64_t* __restrict__ units, uint32_t n_units,
                  const PartTile* __restrict__ pt, const uint32_t* __restrict__ vbeg, const uint32_t* __restrict__ vend,
-                 const double* __restrict__ px, const double* __restrict__ py, const uint32_t* __restrict__ vrow,
+                 const double* __restrict__ wx, const double* __restrict__ wy, const uint32_t* __restrict__ tag,
                  const uint32_t* __restrict__ pos, uint32_t* __restrict__ masks) {
     __shared__ uint32_t s_mask[MASK_WARPS][MASK_SMEM_WORDS];
     __shared__ double s_xt[MASK_WARPS][32], s_yt[MASK_WARPS][32], s_dx[MASK_WARPS][32];
@@ -272,46 +255,38 @@ tile_mask_kernel(KParams P, TileParams T, const uint64_t* __restrict__ units, ui
         for (uint32_t i = lane; i < n_rows * stride; i += 32) mask[i] = 0;
         __syncwarp();
         uint32_t par0 = 0;  // this lane's share of the row-0 crossing count parity
-        // Software pipeline, two batches deep: the vertex rows of batch b+2 and the f64 ordinates of the
-        // edges of batch b+1 that cross this unit's rows are in flight while batch b is processed.
-        auto edge_rows = [&](uint32_t va, uint32_t vn, uint32_t& lo) -> uint32_t {  // rows [lo, lo+cnt) crossed
-            vn &= ~VROW_RING_END;
-            lo = max(min(va, vn), row_start);
-            const uint32_t hi = min(max(va, vn), row_end);
-            return (!(va & VROW_RING_END) && hi > lo) ? hi - lo : 0u;
-        };
-        uint32_t va_n = VROW_RING_END, vb_n = 0, lo_n = 0, cnt_n = 0;
-        double x0_n = 0.0, y0_n = 0.0, x1_n = 0.0, y1_n = 0.0;
-        if (vb + lane + 1 < ve) cnt_n = edge_rows(vrow[vb + lane], vrow[vb + lane + 1], lo_n);
-        if (cnt_n) {
-            x0_n = px[vb + lane];
-            y0_n = py[vb + lane];
-            x1_n = px[vb + lane + 1];
-            y1_n = py[vb + lane + 1];
+        // Batches of 31 edges: lane l holds ring vertex i0 + l (world coordinates + tag, prefetched one batch
+        // ahead) and, for l < 31, edge (i0 + l, i0 + l + 1) whose second vertex comes from lane l + 1.  The
+        // vertex goes to pixel space here (edges.rs:94-97) and its row index ceil(py - 0.5), clamped to
+        // [0, nrows] (edges.rs:32-33), decides with integer compares which edges cross this unit's rows: an
+        // edge is active on rows [min(row_i, row_i+1), max(..)), which also implies the reference's culling
+        // test (edges.rs:105).  Only those edges pay for the x divides and the slope.
+        double xw_n = 0.0, yw_n = 0.0;
+        uint32_t tg_n = VROW_RING_END;
+        if (vb + lane < ve) {
+            xw_n = wx[vb + lane];
+            yw_n = wy[vb + lane];
+            tg_n = tag[vb + lane];
         }
-        if (vb + lane + 33 < ve) {
-            va_n = vrow[vb + lane + 32];
-            vb_n = vrow[vb + lane + 33];
-        }
-        for (uint32_t i0 = vb; i0 + 1 < ve; i0 += 32) {
-            const uint32_t i = i0 + lane;
-            uint32_t cnt = cnt_n;
-            const uint32_t lo = lo_n;
-            const double x0 = x0_n, y0 = y0_n, x1 = x1_n, y1 = y1_n;
-            cnt_n = edge_rows(va_n, vb_n, lo_n);  // batch b+1 (va_n is RING_END beyond the part's last edge)
-            if (cnt_n) {
-                x0_n = px[i + 32];
-                y0_n = py[i + 32];
-                x1_n = px[i + 33];
-                y1_n = py[i + 33];
+        for (uint32_t i0 = vb; i0 + 1 < ve; i0 += 31) {
+            const double xw = xw_n, yw = yw_n;
+            const uint32_t tg = tg_n;
+            tg_n = VROW_RING_END;
+            if (i0 + 31 + lane < ve) {
+                xw_n = wx[i0 + 31 + lane];
+                yw_n = wy[i0 + 31 + lane];
+                tg_n = tag[i0 + 31 + lane];
             }
-            va_n = VROW_RING_END;
-            if (i + 65 < ve) {
-                va_n = vrow[i + 64];
-                vb_n = vrow[i + 65];
-            }
+            const double y0 = px_y(P, yw);
+            const uint32_t row0 = vertex_row(P, y0);
+            const double y1 = __shfl_down_sync(0xffffffffu, y0, 1);
+            const uint32_t row1 = __shfl_down_sync(0xffffffffu, row0, 1);
+            const double xw1 = __shfl_down_sync(0xffffffffu, xw, 1);
+            const uint32_t lo = max(min(row0, row1), row_start), hi = min(max(row0, row1), row_end);
+            uint32_t cnt = (lane < 31 && i0 + lane + 1 < ve && !(tg & VROW_RING_END) && hi > lo) ? hi - lo : 0u;
             TileEdge e;
-            if (cnt && !tile_edge_slope(x0, y0, x1, y1, e)) cnt = 0;
+            if (cnt && !tile_edge_slope(px_x(P, xw), y0, px_x(P, xw1), y1, e)) cnt = 0;
+            par0 ^= (cnt != 0 && lo == 0);  // a kept edge starting at row 0 has exactly one crossing on it
             const uint32_t act = __ballot_sync(0xffffffffu, cnt != 0);
             if (act == 0) continue;
             uint32_t inc = cnt;
@@ -347,7 +322,6 @@ tile_mask_kernel(KParams P, TileParams T, const uint64_t* __restrict__ units, ui
                     b.dxdy = s_dx[warp][slot];
                     const uint32_t row = lp.x + (kk - lp.y);
                     const uint32_t col = tile_edge_col(P, b, row);
-                    par0 ^= (row == 0);
                     if (col < c1) {  // a crossing right of the chunk has no effect on its pixels
                         const uint32_t rel = col <= c0 ? 0u : col - c0;  // left of it: parity carry-in at bit 0
                         atomicXor(&mask[(row - row_start) * stride + (rel >> 5)], 1u << (rel & 31));
@@ -359,10 +333,12 @@ tile_mask_kernel(KParams P, TileParams T, const uint64_t* __restrict__ units, ui
         if (row_start == 0 && (__popc(__ballot_sync(0xffffffffu, par0 & 1u)) & 1)) {  // rare: odd row 0
             uint32_t mx = 0;
             for (uint32_t i = vb + lane; i + 1 < ve; i += 32) {
-                const uint32_t va = vrow[i], vn = vrow[i + 1] & ~VROW_RING_END;
-                if ((va & VROW_RING_END) || !(min(va, vn) == 0 && max(va, vn) > 0)) continue;
+                if (tag[i] & VROW_RING_END) continue;
+                const double y0 = px_y(P, wy[i]), y1 = px_y(P, wy[i + 1]);
+                const uint32_t va = vertex_row(P, y0), vn = vertex_row(P, y1);
+                if (!(min(va, vn) == 0 && max(va, vn) > 0)) continue;
                 TileEdge e;
-                if (tile_edge_slope(px[i], py[i], px[i + 1], py[i + 1], e)) mx = max(mx, tile_edge_col(P, e, 0) + 1u);
+                if (tile_edge_slope(px_x(P, wx[i]), y0, px_x(P, wx[i + 1]), y1, e)) mx = max(mx, tile_edge_col(P, e, 0) + 1u);
             }
             mx = __reduce_max_sync(0xffffffffu, mx);
             if (lane == 0 && mx && mx - 1 < c1) {
@@ -503,13 +479,23 @@ tile_apply_kernel(KParams P, TileParams T, const uint32_t* __restrict__ tile_sta
 
     // ---- flush: every output byte is written exactly once ---------------------------------------------
     if (sizeof(N) >= 4) {
+        N* dst = out + ((size_t)band * T.out_rows + T.win_row_off + (r0 - P.win_r0)) * P.ncols + c0 + lane;
+        if (r1 - r0 == 8 && c1 - c0 == TILE_C) {  // interior tile (warp-uniform): no bounds tests
 #pragma unroll
-        for (int r = 0; r < 8; r++) {
-            if (r0 + r < r1) {
-                N* dst = out + ((size_t)band * T.out_rows + T.win_row_off + (r0 - P.win_r0) + r) * P.ncols + c0 + lane;
+            for (int r = 0; r < 8; r++) {
 #pragma unroll
-                for (int w = 0; w < 4; w++)
-                    if (c0 + w * 32 + lane < c1) __stcs(dst + w * 32, px[r][w]);
+                for (int w = 0; w < 4; w++) __stcs(dst + w * 32, px[r][w]);
+                dst += P.ncols;
+            }
+        } else {
+#pragma unroll
+            for (int r = 0; r < 8; r++) {
+                if (r0 + r < r1) {
+#pragma unroll
+                    for (int w = 0; w < 4; w++)
+                        if (c0 + w * 32 + lane < c1) __stcs(dst + w * 32, px[r][w]);
+                }
+                dst += P.ncols;
             }
         }
     } else {  // narrow dtypes: stage the rows in shared memory so the stores stay 16 bytes wide

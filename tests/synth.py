@@ -111,3 +111,19 @@ def mixed_geometries(seed, n, width, height, rho=24.0):
             out.append(W.collection_wkb([W.point_wkb(*pts()[0]), W.polygon_wkb(poly()), W.linestring_wkb(line()),
                                          W.collection_wkb([W.polygon_wkb(poly())])]))
     return out
+
+
+def parcels(seed, n, width, height, smin=6.0, smax=14.0):
+    """BASELINE config 5's geometry: n axis-jittered quads ("small parcels"), side ~U[smin, smax] px, closed rings
+    of 5 vertices -> (x, y, ring_off) like star_polygons."""
+    u = lambda s: splitmix_u(seed, n, s)  # noqa: E731
+    cx, cy = u(0) * width, u(1) * height
+    hw, hh = 0.5 * (smin + (smax - smin) * u(2)), 0.5 * (smin + (smax - smin) * u(3))
+    x = np.empty((n, 5))
+    y = np.empty((n, 5))
+    for k, (sx, sy) in enumerate([(-1, -1), (1, -1), (1, 1), (-1, 1)]):
+        x[:, k] = cx + sx * hw + (u(4 + 2 * k) - 0.5) * 2.0  # every corner jittered by up to a pixel
+        y[:, k] = cy + sy * hh + (u(5 + 2 * k) - 0.5) * 2.0
+    x[:, 4], y[:, 4] = x[:, 0], y[:, 0]
+    off = (np.arange(n + 1, dtype=np.uint64) * 5)
+    return np.ascontiguousarray(x.reshape(-1)), np.ascontiguousarray(y.reshape(-1)), off

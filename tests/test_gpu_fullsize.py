@@ -82,3 +82,40 @@ def test_config3_32_layers_first_last_min_max():
     burned = res["last"] != 0
     assert (res["min"][burned] <= res["max"][burned]).all()
     assert np.isin(res["first"][burned][:100000], field).all()
+
+
+def test_config5_sparse_parcels_and_geometry_range_shards():
+    """BASELINE config 5 (sparse encoding of small parcels) at 1/25 of its size: 400k jittered quads over
+    26214 x 26214 (same density as 10M over 131072 x 131072).  The triplet stream must equal the oracle's, and
+    shards made of contiguous geometry ranges (sparse output is ordered band -> geometry -> burn
+    order, so ranges concatenate) must reproduce it exactly."""
+    n, size = 400_000, 26214
+    x, y, off = synth.parcels(5, n, size, size)
+    vals = synth.splitmix_u(5, n, 20).astype(np.float32)
+    g = core.Geoms.from_polygons(x, y, off)
+    ri = core.raster_info(None, shape=(size, size), extent=(0, 0, size, size))
+    got = core.rasterize_sparse(g, ri, "sum", "float32", vals, background=np.nan)
+    og = oracle.Geoms.from_rings(x, y, off)
+    ori = oracle.raster_info(None, shape=(size, size), extent=(0, 0, size, size))
+    exp = oracle.rasterize_sparse(og, ori, "sum", "float32", vals, None, None, np.nan)
+    assert len(exp["rows"]) > 30 * n
+    for k in ("counts", "rows", "cols", "data"):
+        assert np.array_equal(exp[k], got[k]), k
+    # 4 shards of contiguous geometry ranges
+    parts = []
+    for d in range(4):
+        a, b = n * d // 4, n * (d + 1) // 4
+        o = off[a:b + 1]
+        gs = core.Geoms.from_polygons(x[int(o[0]):int(o[-1])], y[int(o[0]):int(o[-1])], o - o[0])
+        parts.append(core.rasterize_sparse(gs, ri, "sum", "float32", vals[a:b], background=np.nan))
+    for k in ("rows", "cols", "data"):
+        assert np.array_equal(np.concatenate([p[k] for p in parts]), got[k]), k
+    assert sum(int(p["counts"][0]) for p in parts) == int(got["counts"][0])
+    # replaying the stream gives the dense raster of the same job (python/test/test_many.py:216-224)
+    rows = (4096, 4096 + 512)
+    dense, _ = core.rasterize_dense(g, ri, "sum", "float32", vals, background=np.nan, rows=rows)
+    sel = (got["rows"] >= rows[0]) & (got["rows"] < rows[1])
+    ri_band = core.raster_info(None, shape=(rows[1] - rows[0], size), extent=(0, size - rows[1], size, size - rows[0]))
+    rep = core.sparse_build_array(ri_band, "sum", np.nan, np.array([int(sel.sum())], np.uint64),
+                                  got["rows"][sel] - np.uint64(rows[0]), got["cols"][sel], got["data"][sel])
+    assert np.array_equal(rep, dense, equal_nan=True)

@@ -82,3 +82,22 @@ def test_reference_arm_prints_contract_line():
     line = json.loads(r.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["cpu_baseline"]["kind"] == "port" and line["value"] > 0
     assert line["e2e"]["h2d_bytes_per_step"] == 0
+
+
+def test_sparse_geometry_range_shards_concatenate():
+    """Sparse output is ordered band -> geometry -> burn order (writers.rs:101-131), so the multi-GPU plan for
+    sparse jobs is contiguous geometry ranges whose streams concatenate.  Host logic checked with
+    the oracle standing in for the device."""
+    n, size = 3000, 1024
+    x, y, off = synth.parcels(11, n, size, size)
+    vals = synth.splitmix_u(11, n, 20).astype(np.float32)
+    ri = oracle.raster_info(None, shape=(size, size), extent=(0, 0, size, size))
+    full = oracle.rasterize_sparse(oracle.Geoms.from_rings(x, y, off), ri, "sum", "float32", vals, None, None, np.nan)
+    parts = []
+    for d in range(3):
+        a, b = n * d // 3, n * (d + 1) // 3
+        o = off[a:b + 1]
+        g = oracle.Geoms.from_rings(x[int(o[0]):int(o[-1])], y[int(o[0]):int(o[-1])], o - o[0])
+        parts.append(oracle.rasterize_sparse(g, ri, "sum", "float32", vals[a:b], None, None, np.nan))
+    for k in ("rows", "cols", "data"):
+        assert np.array_equal(np.concatenate([p[k] for p in parts]), full[k]), k
