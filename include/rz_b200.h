@@ -151,6 +151,9 @@ typedef struct rz_context {
 #define RZ_FLAG_SYNC_STAGES 4u     /* record per-stage CUDA-event timings into rz_stats */
 #define RZ_FLAG_NO_TILE_ENGINE 8u      /* always use the crossing-record pipeline */
 #define RZ_FLAG_FORCE_TILE_ENGINE 16u  /* use the tile-binned engine whenever the job is polygon-only */
+#define RZ_FLAG_STREAMED_H2D 64u        /* host rasters of polygon-only jobs: pull the polygon pool from page-locked
+                                          host memory window by window, under the raster's D2H, instead of uploading
+                                          it up front (opt-in: see rz_engine.cu for the measurement) */
 
 typedef struct rz_stats {
     uint64_t n_parts, n_poly_vertices, n_line_vertices, n_points;

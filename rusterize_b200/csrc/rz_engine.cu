@@ -84,6 +84,7 @@ struct DeviceGeoms {
     uint32_t* part_vbeg = nullptr;
     uint32_t* part_vend = nullptr;
     size_t bytes = 0;
+    bool pending0 = false;  // the polygon pool is still being pulled window by window (streamed upload)
     ~DeviceGeoms() {
         cudaSetDevice(dev);
         for (int k = 0; k < 3; k++) {
@@ -108,9 +109,10 @@ struct DeviceCtx {
     std::mutex mu;
     cudaStream_t stream = nullptr;
     int sm_count = 148;
+    int host_ptr_ok = 0;  // kernels may dereference cudaHostRegister'ed host pointers
     DevBuf keys_a, keys_b, hist, digit_total, task_start, part_info, field, valid, band, last_kept, counters, win_out,
         block_total, vs_keys, vs_first, sp_raw, tile_cnt, tile_cnt2, tile_off, tile_off2, tile_ctr,
-        tile_pt, tile_pairs, tile_masks, tile_val, tile_pos, tile_val2, sp_a, sp_b, sp_c, sp_d, sp_e, sp_f, sp_g, sp_rows, sp_cols, sp_data, sp_partial, sp_w, sp_wraw, sp_ws;
+        tile_pt, tile_pairs, tile_masks, tile_val, tile_pos, tile_val2, sp_a, sp_b, sp_c, sp_d, sp_e, sp_f, sp_g, sp_rows, sp_cols, sp_data, sp_partial, sp_w, sp_wraw, sp_ws, pull_bucket, pull_cnt, pull_order;
     Counters* h_counters = nullptr;  // pinned
     cudaEvent_t ev[16];
     cudaStream_t copy_stream = nullptr;  // device->host copies of finished row windows overlap the next window
@@ -136,6 +138,10 @@ static DeviceCtx& device_ctx(int dev) {
     c->dev = dev;
     CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, dev));
+    if (cudaDeviceGetAttribute(&c->host_ptr_ok, cudaDevAttrCanUseHostPointerForRegisteredMem, dev) != cudaSuccess) {
+        (void)cudaGetLastError();
+        c->host_ptr_ok = 0;
+    }
     CUDA_TRY(cudaHostAlloc((void**)&c->h_counters, sizeof(Counters), cudaHostAllocDefault));
     for (auto& e : c->ev) CUDA_TRY(cudaEventCreate(&e));
     CUDA_TRY(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
@@ -184,11 +190,11 @@ static void upload_vec(T** dst, const std::vector<T>& v, cudaStream_t s, size_t&
 // slower upload); a refused vector is therefore moved to freshly allocated storage and tried again, and as a
 // last resort registered in page-aligned 256 MiB pieces so that only the refused pieces stay pageable.
 // RZ_VERBOSE=1 reports what was refused.
-template <typename T> static void pin_vec(rz_geoms* g, std::vector<T>& v, bool verbose) {
+template <typename T> static bool pin_vec(rz_geoms* g, std::vector<T>& v, bool verbose) {  // true: fully page-locked
     const size_t bytes = v.size() * sizeof(T);
-    if (bytes < (1u << 16)) return;
+    if (bytes < (1u << 16)) return false;
     auto try_reg = [&](void* p, size_t n) {
-        const cudaError_t e = cudaHostRegister(p, n, cudaHostRegisterDefault);
+        const cudaError_t e = cudaHostRegister(p, n, cudaHostRegisterMapped | cudaHostRegisterPortable);
         if (e == cudaSuccess) {
             g->pinned_ranges.emplace_back(p, n);
             return true;
@@ -197,20 +203,24 @@ template <typename T> static void pin_vec(rz_geoms* g, std::vector<T>& v, bool v
         if (verbose) std::fprintf(stderr, "librz_b200: cudaHostRegister(%zu bytes) refused: %s\n", n, cudaGetErrorString(e));
         return false;
     };
-    if (try_reg(v.data(), bytes)) return;
+    if (try_reg(v.data(), bytes)) return true;
     {
         std::vector<T> fresh(v);
         v.swap(fresh);
     }
-    if (try_reg(v.data(), bytes)) return;
+    if (try_reg(v.data(), bytes)) return true;
+    // pieces that share no page: the first starts at the vector's first byte, the last ends at its last one
     const uintptr_t piece = (uintptr_t)256 << 20, page = 4096;
-    uintptr_t a = ((uintptr_t)v.data() + page - 1) & ~(page - 1);
-    const uintptr_t end = ((uintptr_t)v.data() + bytes) & ~(page - 1);
+    uintptr_t a = (uintptr_t)v.data();
+    const uintptr_t end = a + bytes;
+    bool all = true;
     while (a < end) {
-        const uintptr_t b = std::min(end, a + piece);
-        try_reg((void*)a, b - a);
+        uintptr_t b = (a + piece) & ~(page - 1);
+        if (b > end || b <= a) b = end;
+        all = try_reg((void*)a, b - a) && all;
         a = b;
     }
+    return all;
 }
 
 static void pin_host(rz_geoms* g) {
@@ -222,9 +232,10 @@ static void pin_host(rz_geoms* g) {
     }
     const bool verbose = std::getenv("RZ_VERBOSE") != nullptr;
     for (int k = 0; k < 3; k++) {
-        pin_vec(g, g->pool[k].x, verbose);
-        pin_vec(g, g->pool[k].y, verbose);
-        pin_vec(g, g->pool[k].tag, verbose);
+        const bool a = pin_vec(g, g->pool[k].x, verbose);
+        const bool b = pin_vec(g, g->pool[k].y, verbose);
+        const bool t = pin_vec(g, g->pool[k].tag, verbose);
+        if (k == 0) g->pool0_mapped = a && b && t;
     }
     pin_vec(g, g->part_xlo, verbose);  // the parts table (45 B/part) is uploaded with the pools
     pin_vec(g, g->part_xhi, verbose);
@@ -242,15 +253,20 @@ static void unpin_host(rz_geoms* g) {
         if (cudaHostUnregister(r.first) != cudaSuccess) (void)cudaGetLastError();
     g->pinned_ranges.clear();
     g->pinned = false;
+    g->pool0_mapped = false;
 }
 
-static DeviceGeoms* geoms_on_device(rz_geoms* g, DeviceCtx& c, cudaStream_t s, bool force, size_t* h2d_bytes) {
+// defer_pool0: allocate the polygon pool on the device but leave it for the caller to pull window by window
+// (rasterize_dense, streamed upload); the copy is then marked pending until the caller completes it.
+static DeviceGeoms* geoms_on_device(rz_geoms* g, DeviceCtx& c, cudaStream_t s, bool force, size_t* h2d_bytes,
+                                    bool defer_pool0 = false) {
     std::lock_guard<std::mutex> lk(g->mu);
     auto it = g->dev.find(c.dev);
-    if (it != g->dev.end() && !force) return it->second;
+    if (it != g->dev.end() && !force && !it->second->pending0) return it->second;
     for (int k = 0; k < 3; k++)
         if (g->pool[k].size() >= 0xfffffff0ull) throw Error{RZ_RUNTIME_ERROR, "Too many vertices (limit 2^32 per pool)."};
     pin_host(g);
+    defer_pool0 = defer_pool0 && g->pool0_mapped && c.host_ptr_ok;
     std::unique_ptr<DeviceGeoms> fresh;
     DeviceGeoms* d = it != g->dev.end() ? it->second : nullptr;
     if (!d) {
@@ -260,6 +276,13 @@ static DeviceGeoms* geoms_on_device(rz_geoms* g, DeviceCtx& c, cudaStream_t s, b
     d->dev = c.dev;
     size_t bytes = 0;
     for (int k = 0; k < 3; k++) {
+        if (k == 0 && defer_pool0) {
+            const size_t n = g->pool[0].size() + 1;
+            if (!d->x[0]) CUDA_TRY(cudaMalloc((void**)&d->x[0], n * 8));
+            if (!d->y[0]) CUDA_TRY(cudaMalloc((void**)&d->y[0], n * 8));
+            if (!d->tag[0]) CUDA_TRY(cudaMalloc((void**)&d->tag[0], n * 4));
+            continue;
+        }
         upload_vec(&d->x[k], g->pool[k].x, s, bytes, g->pinned_ranges);
         upload_vec(&d->y[k], g->pool[k].y, s, bytes, g->pinned_ranges);
         upload_vec(&d->tag[k], g->pool[k].tag, s, bytes, g->pinned_ranges);
@@ -274,7 +297,8 @@ static DeviceGeoms* geoms_on_device(rz_geoms* g, DeviceCtx& c, cudaStream_t s, b
     upload_vec(&d->part_vbeg, g->part_vbeg, s, bytes, g->pinned_ranges);
     upload_vec(&d->part_vend, g->part_vend, s, bytes, g->pinned_ranges);
     CUDA_TRY(cudaStreamSynchronize(s));  // `pg` is a temporary
-    d->bytes = bytes;
+    d->pending0 = defer_pool0;
+    d->bytes = bytes + (defer_pool0 ? g->pool[0].size() * 20 : 0);
     if (h2d_bytes) *h2d_bytes += bytes;
     if (fresh) g->dev[c.dev] = fresh.release();
     return d;
@@ -435,7 +459,14 @@ struct Timer {
 };
 
 static const uint64_t MAX_WINDOW_RECORDS = 1ull << 31;      // 32 GiB of ping-pong key buffers
-static const uint64_t MAX_WINDOW_OUT_BYTES = 2ull << 30;   // one of the two staging buffers when `out` is host memory
+// one of the two staging buffers when `out` is host memory (RZ_WINDOW_BYTES overrides it: tests use small windows)
+static uint64_t max_window_out_bytes() {
+    if (const char* e = std::getenv("RZ_WINDOW_BYTES")) {
+        const unsigned long long v = std::strtoull(e, nullptr, 10);
+        if (v) return v;
+    }
+    return 2ull << 30;
+}
 
 static void rasterize_dense(rz_geoms* g, const rz_context* ctx, void* out, rz_stats* st) {
     const rz_raster_info& ri = ctx->raster_info;
@@ -469,7 +500,16 @@ static void rasterize_dense(rz_geoms* g, const rz_context* ctx, void* out, rz_st
 
     // ---- inputs to the device ------------------------------------------------------------------
     size_t h2d = 0;
-    DeviceGeoms* dg = geoms_on_device(g, c, s, (ctx->flags & RZ_FLAG_FORCE_H2D) != 0, &h2d);
+    // Streamed upload (rz_tiles.cuh), opt-in: polygon-only jobs that can take the tile engine (which only reads
+    // the parts binned to a window) and whose raster goes back to the host in several windows.  Measured on
+    // config 4 it does overlap the 4 GB upload with the raster's D2H, but the kernel's PCIe read requests
+    // compete with the D2H writes for the upstream direction and the D2H phase stretches by as much as the
+    // upload shrank (417 ms against 395 ms end to end), so it is not the default.
+    const uint64_t MAX_WINDOW_OUT_BYTES = max_window_out_bytes();
+    const bool stream_geoms = (ctx->flags & RZ_FLAG_STREAMED_H2D) && !out_dev && !ctx->all_touched &&
+                              g->pool[1].size() == 0 && g->pool[2].size() == 0 && !(ctx->flags & RZ_FLAG_NO_TILE_ENGINE) &&
+                              (uint64_t)n_bands * shard_rows * ri.ncols * isz >= 2 * MAX_WINDOW_OUT_BYTES;
+    DeviceGeoms* dg = geoms_on_device(g, c, s, (ctx->flags & RZ_FLAG_FORCE_H2D) != 0, &h2d, stream_geoms);
     const uint32_t n_parts = (uint32_t)g->part_kind.size();
     const size_t n_field = ctx->field_is_scalar ? 1 : (size_t)g->n_geoms;
     c.field.ensure(std::max<size_t>(n_field * isz, 8));
@@ -490,7 +530,6 @@ static void rasterize_dense(rz_geoms* g, const rz_context* ctx, void* out, rz_st
         h2d += g->n_geoms * 4;
     }
     CUDA_TRY(cudaEventRecord(c.ev[EV_H2D], s));
-    S.h2d_bytes = h2d;
 
     // ---- tiling and key layout -----------------------------------------------------------------
     // One warp owns a row tile of tile_w pixels; the fill kernel keeps one toggle bit per pixel in a
@@ -543,13 +582,10 @@ static void rasterize_dense(rz_geoms* g, const rz_context* ctx, void* out, rz_st
     c.part_info.ensure(std::max<size_t>((size_t)n_parts * sizeof(PartInfo), 16));
     c.last_kept.ensure(std::max<size_t>((size_t)n_parts * 4, 16));
     c.counters.ensure(sizeof(Counters));
-    uint32_t launches = 0;
-    if (n_parts) {
+    if (n_parts)
         part_prepare_kernel<<<(n_parts + 255) / 256, 256, 0, s>>>(
             P, dg->part_kind, dg->part_geom, dg->part_xlo, dg->part_xhi, c.field.as<uint8_t>(), (uint32_t)isz,
             ctx->field_is_scalar, d_valid, d_band, c.part_info.as<PartInfo>());
-        launches++;
-    }
     const PartInfo* d_info = c.part_info.as<PartInfo>();
     Counters* d_ctr = c.counters.as<Counters>();
 
@@ -571,6 +607,49 @@ static void rasterize_dense(rz_geoms* g, const rz_context* ctx, void* out, rz_st
     std::vector<Window> todo;
     for (uint32_t r = shard_r0; r < shard_r1; r += win_rows) todo.push_back(Window{r, std::min(r + win_rows, shard_r1)});
     std::reverse(todo.begin(), todo.end());  // pop_back walks top to bottom
+
+    // ---- streamed upload of the polygon pool: parts bucketed by the first window they touch -------------
+    uint32_t launches = 0;
+    const uint32_t n_buckets = (shard_rows + win_rows - 1) / win_rows;
+    uint32_t pulled = 0;  // buckets [0, pulled) are on the device; bucket n_buckets = parts touching no window
+    std::vector<unsigned int> bucket_off;
+    float pull_ms = 0;
+    if (dg->pending0) {
+        P.win_r0 = shard_r0;
+        P.win_r1 = shard_r1;
+        c.pull_bucket.ensure((size_t)n_parts * 4);
+        c.pull_order.ensure((size_t)n_parts * 4);
+        c.pull_cnt.ensure((size_t)(2 * n_buckets + 4) * 4);
+        unsigned int* d_cnt = c.pull_cnt.as<unsigned int>();
+        unsigned int* d_off = d_cnt + n_buckets + 1;
+        CUDA_TRY(cudaMemsetAsync(d_cnt, 0, (size_t)(n_buckets + 1) * 4, s));
+        part_bucket_kernel<<<(n_parts + 255) / 256, 256, 0, s>>>(P, dg->part_kind, dg->part_ylo, dg->part_yhi, shard_r0,
+                                                                 shard_r1, win_rows, n_buckets,
+                                                                 c.pull_bucket.as<uint32_t>(), d_cnt);
+        bucket_scan_kernel<<<1, 1, 0, s>>>(d_cnt, d_off, n_buckets + 1);
+        bucket_scatter_kernel<<<(n_parts + 255) / 256, 256, 0, s>>>(n_parts, c.pull_bucket.as<uint32_t>(), d_off, d_cnt,
+                                                                    c.pull_order.as<uint32_t>());
+        launches += 3;
+        bucket_off.resize(n_buckets + 2);
+        CUDA_TRY(cudaMemcpyAsync(bucket_off.data(), d_off, (size_t)(n_buckets + 2) * 4, cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(cudaStreamSynchronize(s));
+    }
+    if (n_parts) launches++;  // part_prepare
+    auto pull_upto = [&](uint32_t b_end) {  // make buckets [0, b_end) resident
+        if (!dg->pending0 || b_end <= pulled) return;
+        const uint32_t i0 = bucket_off[pulled], i1 = bucket_off[b_end];
+        if (i1 > i0) {
+            pull_parts_kernel<<<i1 - i0, 128, 0, s>>>(c.pull_order.as<uint32_t>() + i0, i1 - i0, dg->part_vbeg,
+                                                      dg->part_vend, g->pool[0].x.data(), g->pool[0].y.data(),
+                                                      g->pool[0].tag.data(), dg->x[0], dg->y[0], dg->tag[0]);
+            launches++;
+        }
+        pulled = b_end;
+        if (pulled == n_buckets + 1) {
+            dg->pending0 = false;
+            h2d += g->pool[0].size() * 20;
+        }
+    };
 
     FillLaunch fill = fill_for(ctx->dtype, ctx->pixel_fn);
     float count_ms = 0, emit_ms = 0, sort_ms = 0, index_ms = 0, fill_ms = 0, d2h_ms = 0;
@@ -715,6 +794,13 @@ static void rasterize_dense(rz_geoms* g, const rz_context* ctx, void* out, rz_st
                     launches += 2;
                     if (timed) CUDA_TRY(cudaEventRecord(c.ev[EV_B], s));
                     lap(sort_ms, EV_A, EV_B);
+                    // ---- streamed upload: the parts this window is the first to need ------------------
+                    if (dg->pending0) {
+                        if (timed) CUDA_TRY(cudaEventRecord(c.ev[EV_A], s));
+                        pull_upto(std::min((w.r0 - shard_r0) / win_rows, n_buckets - 1) + 1);
+                        if (timed) CUDA_TRY(cudaEventRecord(c.ev[EV_B], s));
+                        lap(pull_ms, EV_A, EV_B);
+                    }
                     // ---- inside masks of every (part, tile) pair ----------------------------------
                     if (timed) CUDA_TRY(cudaEventRecord(c.ev[EV_A], s));
                     if (n_rows) {
@@ -767,6 +853,7 @@ static void rasterize_dense(rz_geoms* g, const rz_context* ctx, void* out, rz_st
         }
 
         // ---- count --------------------------------------------------------------------------
+        pull_upto(n_buckets + 1);  // the record pipeline reads every ring vertex: finish a streamed upload first
         if (timed) CUDA_TRY(cudaEventRecord(c.ev[EV_A], s));
         CUDA_TRY(cudaMemsetAsync(d_ctr, 0, sizeof(Counters), s));
         const uint32_t poly_blocks = (nv_poly + SETUP_THREADS - 1) / SETUP_THREADS;
@@ -930,6 +1017,7 @@ static void rasterize_dense(rz_geoms* g, const rz_context* ctx, void* out, rz_st
         if (!out_dev) stage_copy(w, d_out);
         flush_laps();
     }
+    pull_upto(n_buckets + 1);  // parts no window needed: the device copy of the geometry is complete again
     if (!out_dev && n_staged) {  // the call returns when the last window has landed in host memory
         CUDA_TRY(cudaEventRecord(c.ev_d2h[1], c.copy_stream));
         CUDA_TRY(cudaStreamWaitEvent(s, c.ev_d2h[1], 0));
@@ -941,6 +1029,8 @@ static void rasterize_dense(rz_geoms* g, const rz_context* ctx, void* out, rz_st
         CUDA_TRY(cudaEventElapsedTime(&S.total_ms, c.ev[EV_START], c.ev[EV_END]));
         CUDA_TRY(cudaEventElapsedTime(&S.h2d_ms, c.ev[EV_START], c.ev[EV_H2D]));
     }
+    S.h2d_bytes = h2d;
+    S.h2d_ms += pull_ms;
     S.count_ms = count_ms;
     S.emit_ms = emit_ms;
     S.sort_ms = sort_ms;

@@ -45,6 +45,7 @@ struct rz_geoms {
     double bounds[4] = {0, 0, 0, 0};   // union of geo::BoundingRect, xmin ymin xmax ymax
     bool pinned = false;
     std::vector<std::pair<void*, size_t>> pinned_ranges;  // what cudaHostRegister accepted
+    bool pool0_mapped = false;  // every byte of the polygon pool is page-locked and mapped: kernels may read it in place
 
     std::mutex mu;
     std::map<int, rz::DeviceGeoms*> dev;  // cached device copies, by ordinal

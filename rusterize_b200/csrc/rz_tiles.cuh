@@ -203,6 +203,80 @@ __device__ __forceinline__ uint32_t tile_edge_col(const KParams& P, const TileEd
     return floor_sat_u32(__dadd_rn(xi, 0.5), P.ncols);                                // burners.rs:310-311
 }
 
+// ---------------------------------------------------------------------------------------------
+// streamed upload: the polygon pool is pulled from page-locked host memory window by window
+// ---------------------------------------------------------------------------------------------
+// An end-to-end call is bound by PCIe: geometry host->device, then the raster device->host.  The two
+// directions are independent, so instead of uploading the whole pool first, every polygon part is assigned
+// to the first row window of the call that its rows touch ("bucket"; parts touching none go to a last one),
+// and the parts of bucket b are copied by a kernel that reads the mapped host arrays directly, right before
+// window b is computed - while the copy stream is still sending window b-1 to the host.
+__global__ void part_bucket_kernel(KParams P, const uint8_t* __restrict__ part_kind, const double* __restrict__ ylo,
+                                   const double* __restrict__ yhi, uint32_t shard_r0, uint32_t shard_r1,
+                                   uint32_t win_rows, uint32_t n_buckets, uint32_t* __restrict__ bucket_of,
+                                   unsigned int* __restrict__ cnt) {
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P.n_parts) return;
+    uint32_t b = 0xffffffffu;  // not a polygon part
+    if (part_kind[p] == 0) {
+        const uint32_t lo = max(vertex_row(P, px_y(P, yhi[p])), shard_r0);
+        const uint32_t hi = min(vertex_row(P, px_y(P, ylo[p])), shard_r1);
+        b = hi > lo ? min((lo - shard_r0) / win_rows, n_buckets - 1) : n_buckets;
+        atomicAdd(&cnt[b], 1u);
+    }
+    bucket_of[p] = b;
+}
+// cnt[0 .. n_buckets] -> off[0 .. n_buckets + 1] (exclusive), cursors reset; a handful of buckets: one thread
+__global__ void bucket_scan_kernel(unsigned int* __restrict__ cnt, unsigned int* __restrict__ off, uint32_t n) {
+    unsigned int run = 0;
+    for (uint32_t i = 0; i < n; i++) {
+        off[i] = run;
+        run += cnt[i];
+        cnt[i] = 0;
+    }
+    off[n] = run;
+}
+__global__ void bucket_scatter_kernel(uint32_t n_parts, const uint32_t* __restrict__ bucket_of,
+                                      const unsigned int* __restrict__ off, unsigned int* __restrict__ cursor,
+                                      uint32_t* __restrict__ order) {
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_parts) return;
+    const uint32_t b = bucket_of[p];
+    if (b != 0xffffffffu) order[off[b] + atomicAdd(&cursor[b], 1u)] = p;
+}
+// one CTA per part: its vertex range from the mapped host arrays (PCIe reads) to the device pool
+__global__ void __launch_bounds__(128)
+pull_parts_kernel(const uint32_t* __restrict__ order, uint32_t n, const uint32_t* __restrict__ vbeg,
+                  const uint32_t* __restrict__ vend, const double* __restrict__ hx, const double* __restrict__ hy,
+                  const uint32_t* __restrict__ htag, double* __restrict__ dx, double* __restrict__ dy,
+                  uint32_t* __restrict__ dtag) {
+    if (blockIdx.x >= n) return;
+    const uint32_t p = order[blockIdx.x];
+    const uint32_t e = vend[p];
+    for (uint32_t i = vbeg[p] + threadIdx.x; i < e; i += 4 * 128) {  // four independent loads per array in flight
+        double a[4], b[4];
+        uint32_t t[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const uint32_t j = i + k * 128;
+            if (j < e) {
+                a[k] = __ldcs(hx + j);
+                b[k] = __ldcs(hy + j);
+                t[k] = __ldcs(htag + j);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const uint32_t j = i + k * 128;
+            if (j < e) {
+                dx[j] = a[k];
+                dy[j] = b[k];
+                dtag[j] = t[k];
+            }
+        }
+    }
+}
+
 // After the stable sort of the [tile | block] records: where every inside-mask block lives.  tile_mask writes
 // block b at position pos[b] of the mask array, i.e. in tile order, and the value of its part goes to the
 // same position, so that tile_apply streams a tile's blocks from consecutive memory with no indirection.

@@ -290,3 +290,39 @@ def test_engine_choice_is_automatic():
     exp, got, st = both(huge, "count", "uint8", 1, 0, shape=(2000, 2000), extent=(0, 0, 2000, 2000))
     assert st["engine"] == 0  # 5000-vertex polygon over 256 tiles: the record pipeline is cheaper
     assert_same(exp, got)
+
+
+def test_windowed_host_output_and_streamed_upload(monkeypatch):
+    """Host rasters come back in row windows through two staging buffers (copy of window k overlaps window k+1),
+    and with RZ_FLAG_STREAMED_H2D the polygon pool is pulled from page-locked host memory window by window
+    instead of uploaded up front (rz_tiles.cuh: part_bucket / pull_parts).  Small windows exercise both on a
+    small job; every variant must equal the oracle and the plain path."""
+    from rusterize_b200 import _lib
+
+    x, y, off = synth.star_polygons(12, 6000, 16, 64, 60.0, 2048, 1536)
+    vals = (100 * synth.splitmix_u(12, 6000, 9)).astype(np.float32)
+    # parts far outside the raster and parts that only touch later windows stay in the pool
+    x[:500] += 5000.0
+    ri_kw = dict(shape=(1536, 2048), extent=(0, 0, 2048, 1536))
+    og = oracle.Geoms.from_rings(x, y, off)
+    exp, _ = oracle.rasterize_dense(og, oracle.raster_info(None, **ri_kw), "sum", "float32", vals, background=np.nan)
+    ri = core.raster_info(None, **ri_kw)
+    plain, st0 = core.rasterize_dense(core.Geoms.from_polygons(x, y, off), ri, "sum", "float32", vals, background=np.nan)
+    assert st0["n_windows"] == 1 and np.array_equal(exp, plain, equal_nan=True)
+    monkeypatch.setenv("RZ_WINDOW_BYTES", str(2048 * 4 * 100))  # 100-row windows -> 16 windows
+    for flags in (0, _lib.FLAG_STREAMED_H2D, _lib.FLAG_STREAMED_H2D | _lib.FLAG_FORCE_TILE_ENGINE):
+        g = core.Geoms.from_polygons(x, y, off)  # fresh handle: nothing cached on the device
+        got, st = core.rasterize_dense(g, ri, "sum", "float32", vals, background=np.nan, flags=flags)
+        assert st["n_windows"] == 16 and st["h2d_bytes"] >= g.n_coords * 20
+        assert np.array_equal(exp, got, equal_nan=True), flags
+        again, st2 = core.rasterize_dense(g, ri, "sum", "float32", vals, background=np.nan, flags=flags)  # cached copy
+        assert st2["h2d_bytes"] < g.n_coords * 20 and np.array_equal(exp, again, equal_nan=True)
+        shard, _ = core.rasterize_dense(g, ri, "last", "float32", vals, background=np.nan, rows=(250, 1111),
+                                        flags=flags | _lib.FLAG_FORCE_H2D)
+        e2, _ = oracle.rasterize_dense(og, oracle.raster_info(None, shape=(861, 2048), extent=(0, 1536 - 1111, 2048, 1536 - 250)),
+                                       "last", "float32", vals, background=np.nan)
+        assert np.array_equal(e2, shard, equal_nan=True)
+    # mixed jobs take the record pipeline: the flag is ignored (and windows still work)
+    geoms = synth.mixed_geometries(3, 300, 2048, 1536, rho=60.0)
+    e3, g3, _ = both(geoms, "count", "uint16", 1, 0, flags=_lib.FLAG_STREAMED_H2D, **ri_kw)
+    assert_same(e3, g3)
