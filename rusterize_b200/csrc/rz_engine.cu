@@ -112,7 +112,7 @@ struct DeviceCtx {
     int host_ptr_ok = 0;  // kernels may dereference cudaHostRegister'ed host pointers
     DevBuf keys_a, keys_b, hist, digit_total, task_start, part_info, field, valid, band, last_kept, counters, win_out,
         block_total, vs_keys, vs_first, sp_raw, tile_cnt, tile_cnt2, tile_off, tile_off2, tile_ctr,
-        tile_pt, tile_pairs, tile_masks, tile_val, tile_pos, tile_val2, sp_a, sp_b, sp_c, sp_d, sp_e, sp_f, sp_g, sp_rows, sp_cols, sp_data, sp_partial, sp_w, sp_wraw, sp_ws, pull_bucket, pull_cnt, pull_order;
+        tile_pt, tile_pairs, tile_masks, tile_val, tile_pos, tile_val2, sp_a, sp_b, sp_c, sp_d, sp_e, sp_f, sp_g, sp_rows, sp_cols, sp_data, sp_partial, sp_w, sp_wraw, sp_ws, pull_bucket, pull_cnt, pull_order, cache_acc, cache_box;
     Counters* h_counters = nullptr;  // pinned
     cudaEvent_t ev[16];
     cudaStream_t copy_stream = nullptr;  // device->host copies of finished row windows overlap the next window
@@ -175,8 +175,8 @@ static void copy_h2d_split(void* dst, const void* src, size_t bytes, const std::
 
 // (re)upload a host vector; the device buffer is allocated on first use and reused afterwards (a
 // geometry set is immutable, so a forced re-upload only pays the copy)
-template <typename T>
-static void upload_vec(T** dst, const std::vector<T>& v, cudaStream_t s, size_t& bytes,
+template <typename T, typename A>
+static void upload_vec(T** dst, const std::vector<T, A>& v, cudaStream_t s, size_t& bytes,
                        const std::vector<std::pair<void*, size_t>>& pinned) {
     if (v.empty()) return;
     // one spare element so kernels may read index i+1 of the last vertex unconditionally
@@ -190,7 +190,8 @@ static void upload_vec(T** dst, const std::vector<T>& v, cudaStream_t s, size_t&
 // slower upload); a refused vector is therefore moved to freshly allocated storage and tried again, and as a
 // last resort registered in page-aligned 256 MiB pieces so that only the refused pieces stay pageable.
 // RZ_VERBOSE=1 reports what was refused.
-template <typename T> static bool pin_vec(rz_geoms* g, std::vector<T>& v, bool verbose) {  // true: fully page-locked
+template <typename T, typename A>
+static bool pin_vec(rz_geoms* g, std::vector<T, A>& v, bool verbose) {  // true: fully page-locked
     const size_t bytes = v.size() * sizeof(T);
     if (bytes < (1u << 16)) return false;
     auto try_reg = [&](void* p, size_t n) {
@@ -205,7 +206,7 @@ template <typename T> static bool pin_vec(rz_geoms* g, std::vector<T>& v, bool v
     };
     if (try_reg(v.data(), bytes)) return true;
     {
-        std::vector<T> fresh(v);
+        std::vector<T, A> fresh(v);
         v.swap(fresh);
     }
     if (try_reg(v.data(), bytes)) return true;
@@ -308,15 +309,16 @@ static DeviceGeoms* geoms_on_device(rz_geoms* g, DeviceCtx& c, cudaStream_t s, b
 // fill dispatch: 10 dtypes x 7 pixel functions
 // ------------------------------------------------------------------------------------------------
 typedef void (*FillLaunch)(dim3, size_t, cudaStream_t, FillParams, const uint64_t*, const uint32_t*, const PartInfo*,
-                           const uint8_t*, uint64_t, void*);
+                           const uint8_t*, uint64_t, void*, AliasCtx);
 
 template <typename N, int FN>
 static void fill_launch(dim3 grid, size_t smem, cudaStream_t s, FillParams F, const uint64_t* keys,
-                        const uint32_t* task_start, const PartInfo* info, const uint8_t* kind, uint64_t bg, void* out) {
+                        const uint32_t* task_start, const PartInfo* info, const uint8_t* kind, uint64_t bg, void* out,
+                        AliasCtx A) {
     if (F.all_poly)
-        fill_kernel<N, FN, true><<<grid, FILL_WARPS * 32, smem, s>>>(F, keys, task_start, info, kind, bg, (N*)out);
+        fill_kernel<N, FN, true><<<grid, FILL_WARPS * 32, smem, s>>>(F, keys, task_start, info, kind, bg, (N*)out, A);
     else
-        fill_kernel<N, FN, false><<<grid, FILL_WARPS * 32, smem, s>>>(F, keys, task_start, info, kind, bg, (N*)out);
+        fill_kernel<N, FN, false><<<grid, FILL_WARPS * 32, smem, s>>>(F, keys, task_start, info, kind, bg, (N*)out, A);
 }
 
 template <typename N> static FillLaunch fill_for_fn(int fn) {
@@ -466,6 +468,20 @@ static uint64_t max_window_out_bytes() {
         if (v) return v;
     }
     return 2ull << 30;
+}
+
+// PixelCache boxes of every polygon part (all_touched with sum / count): c.cache_box / c.cache_acc
+static void build_cache_boxes(DeviceCtx& c, cudaStream_t s, const KParams& P, DeviceGeoms* dg, uint32_t nv_poly,
+                              uint32_t n_parts, uint32_t& launches) {
+    c.cache_acc.ensure(std::max<size_t>((size_t)n_parts * sizeof(CacheAcc), 64));
+    c.cache_box.ensure(std::max<size_t>((size_t)n_parts * sizeof(CacheBox), 64));
+    cache_box_init_kernel<<<(n_parts + 255) / 256, 256, 0, s>>>(n_parts, c.cache_acc.as<CacheAcc>());
+    if (nv_poly)
+        cache_box_kernel<<<(nv_poly + 255) / 256, 256, 0, s>>>(P, dg->x[0], dg->y[0], dg->tag[0], nv_poly,
+                                                              c.cache_acc.as<CacheAcc>());
+    cache_box_finish_kernel<<<(n_parts + 255) / 256, 256, 0, s>>>(n_parts, c.cache_acc.as<CacheAcc>(),
+                                                                 c.cache_box.as<CacheBox>());
+    launches += 3;
 }
 
 static void rasterize_dense(rz_geoms* g, const rz_context* ctx, void* out, rz_stats* st) {
@@ -700,6 +716,42 @@ static void rasterize_dense(rz_geoms* g, const rz_context* ctx, void* out, rz_st
                    nv_pt = (uint32_t)g->pool[2].size();
     const uint32_t per_block = SETUP_THREADS * SETUP_ITEMS;
     const bool all_poly = nv_line == 0 && nv_pt == 0 && !ctx->all_touched;
+
+    // all_touched with sum / count (S::REQUIRES_DEDUP): the parts whose PixelCache box does not cover their fill
+    AliasCtx alias;
+    std::memset(&alias, 0, sizeof alias);
+    if (touched && (ctx->pixel_fn == RZ_SUM || ctx->pixel_fn == RZ_COUNT) && nv_poly) {
+        P.win_r0 = shard_r0;
+        P.win_r1 = shard_r1;
+        build_cache_boxes(c, s, P, dg, nv_poly, n_parts, launches);
+        CUDA_TRY(cudaMemsetAsync(d_ctr, 0, sizeof(Counters), s));
+        touched_walk_kernel<<<(nv_poly + 255) / 256, 256, 0, s>>>(P, dg->x[0], dg->y[0], dg->tag[0], nv_poly, d_info, d_ctr,
+                                                                 nullptr, 2, c.cache_acc.as<CacheAcc>());
+        launches++;
+        CUDA_TRY(cudaMemcpyAsync(c.h_counters, d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(cudaStreamSynchronize(s));
+        const unsigned long long walked = c.h_counters->cursor;
+        if (walked) {  // some part has a dropped ring segment: remember its walked pixels
+            unsigned long long cap = 1024;
+            while (cap < 2 * walked) cap <<= 1;
+            c.vs_keys.ensure(cap * 8);
+            c.vs_first.ensure(cap * 8);
+            CUDA_TRY(cudaMemsetAsync(c.vs_keys.p, 0xff, cap * 8, s));
+            CUDA_TRY(cudaMemsetAsync(c.vs_first.p, 0xff, cap * 8, s));
+            alias.vs.keys = c.vs_keys.as<unsigned long long>();
+            alias.vs.first = c.vs_first.as<unsigned long long>();
+            alias.vs.mask = cap - 1;
+            alias.vs.col_bits = bits_for(ri.ncols + 1);
+            alias.vs.row_bits = std::max(1u, bits_for(ri.nrows));
+            if (alias.vs.col_bits + alias.vs.row_bits + P.part_bits > 64)
+                throw Error{RZ_RUNTIME_ERROR, "Problem too large for the 64-bit pixel-cache key."};
+            touched_walk_kernel<<<(nv_poly + 255) / 256, 256, 0, s>>>(P, dg->x[0], dg->y[0], dg->tag[0], nv_poly, d_info,
+                                                                     d_ctr, nullptr, 3, c.cache_acc.as<CacheAcc>(), alias.vs);
+            launches++;
+            alias.acc = c.cache_acc.as<CacheAcc>();
+            alias.box = c.cache_box.as<CacheBox>();
+        }
+    }
 
     while (!todo.empty()) {
         Window w = todo.back();
@@ -994,6 +1046,8 @@ static void rasterize_dense(rz_geoms* g, const rz_context* ctx, void* out, rz_st
         F.dedup_lines = P.dedup_lines;
         F.all_poly = nv_line == 0 && nv_pt == 0;
         F.all_touched = touched;
+        F.nrows = (uint32_t)ri.nrows;
+        F.win_r0 = w.r0;
         void* d_out;
         if (out_dev) {
             d_out = out;
@@ -1007,7 +1061,7 @@ static void rasterize_dense(rz_geoms* g, const rz_context* ctx, void* out, rz_st
         F.vec_ok = ((uintptr_t)d_out % 16 == 0) && ((ri.ncols * isz) % 16 == 0) && (((size_t)tile_w * isz) % 16 == 0);
         const uint32_t grid = (n_tasks + FILL_WARPS - 1) / FILL_WARPS;
         fill(dim3(grid), (size_t)FILL_WARPS * FILL_MAX_TILE_W * isz, s, F, ka, c.task_start.as<uint32_t>(), d_info,
-             dg->part_kind, bg_bits, d_out);
+             dg->part_kind, bg_bits, d_out, alias);
         launches++;
         CUDA_TRY(cudaGetLastError());
         if (timed) CUDA_TRY(cudaEventRecord(c.ev[EV_B], s));
@@ -1075,8 +1129,8 @@ static void sparse_expand(cudaStream_t s, const KParams& P, SparseLayout L, Devi
     if (J.n_rec) {
         if (J.poly_dedup)
             poly_expand_dedup_kernel<N><<<(J.n_rec + 255) / 256, 256, 0, s>>>(
-                J.keys, c.sp_a.as<uint32_t>(), c.sp_b.as<unsigned long long>(), J.n_rec, L, J.vs, info, base, start, rows,
-                cols, data);
+                P, J.keys, c.sp_a.as<uint32_t>(), c.sp_b.as<unsigned long long>(), J.n_rec, L, J.vs,
+                c.cache_box.as<CacheBox>(), info, base, start, rows, cols, data);
         else
             poly_expand_kernel<N><<<(J.n_rec + 255) / 256, 256, 0, s>>>(J.keys, c.sp_a.as<uint32_t>(),
                                                                        c.sp_b.as<unsigned long long>(), J.n_rec, L, info,
@@ -1329,9 +1383,11 @@ static void rasterize_sparse(rz_geoms* g, const rz_context* ctx, rz_sparse* out,
     }
     if (n_rec) {  // spans: pair the sorted crossings, prefix-sum their (kept) lengths
         const InSpanLen span_len{keys, c.sp_a.as<uint32_t>(), n_rec, L.col_bits};
-        if (pd)
-            device_scan<OpAdd>(InSpanKept{span_len, vs, L.row_bits}, n_rec, OutPrefix64{c.sp_b.as<unsigned long long>()},
-                               c.sp_partial, s, launches);
+        if (pd) {
+            build_cache_boxes(c, s, P, dg, nv_poly, n_parts, launches);
+            device_scan<OpAdd>(InSpanKept{span_len, vs, P, c.cache_box.as<CacheBox>(), L.row_bits}, n_rec,
+                               OutPrefix64{c.sp_b.as<unsigned long long>()}, c.sp_partial, s, launches);
+        }
         else
             device_scan<OpAdd>(span_len, n_rec, OutPrefix64{c.sp_b.as<unsigned long long>()}, c.sp_partial, s, launches);
         poly_total = scan_total(c.sp_partial, n_rec, s);
@@ -1579,6 +1635,21 @@ rz_geoms* rz_geoms_from_wkb(const uint8_t* const* bufs, const uint64_t* lens, ui
     std::unique_ptr<rz_geoms> g(new rz_geoms());
     int rc = guarded(err, errlen, [&]() {
         rz::Flattener f(g.get());
+        // A vertex takes at least 16 WKB bytes: reserve the pool of the first geometry's kind once instead of
+        // growing it by doubling (untouched reserve costs address space only).
+        if (n && lens[0] >= 5) {
+            uint32_t t = 0;
+            for (int k = 0; k < 4; k++) t |= (uint32_t)bufs[0][1 + (bufs[0][0] ? k : 3 - k)] << (8 * k);
+            t = (t & 0x0fffffffu) % 1000;
+            const int kind = (t == 3 || t == 6) ? RZ_PART_POLYGON : (t == 2 || t == 5) ? RZ_PART_LINE : (t == 1 || t == 4) ? RZ_PART_POINT : -1;
+            uint64_t total = 0;
+            for (uint64_t i = 0; i < n; i++) total += lens[i];
+            if (kind >= 0 && total / 16 < 0xfffffff0ull) {
+                g->pool[kind].x.reserve(total / 16 + 16);
+                g->pool[kind].y.reserve(total / 16 + 16);
+                g->pool[kind].tag.reserve(total / 16 + 16);
+            }
+        }
         for (uint64_t i = 0; i < n; i++) {
             bool keep = false;
             f.begin_geometry();
@@ -1633,8 +1704,8 @@ rz_geoms* rz_geoms_from_soa(const rz_geom_soa* soa, char* err, size_t errlen) {
                     // geo::BoundingRect looks at exterior rings only; the SoA form has no polygon
                     // boundaries, so every ring counts (callers needing exactness pass an extent).
                     f.begin_seq(true);
-                    for (uint64_t k = soa->seq_coord_off[s]; k < soa->seq_coord_off[s + 1]; k++)
-                        f.coord(soa->x[k], soa->y[k]);
+                    const uint64_t k0 = soa->seq_coord_off[s], k1 = soa->seq_coord_off[s + 1];
+                    if (k1 > k0) f.coords(soa->x + k0, soa->y + k0, (size_t)(k1 - k0));
                     f.end_seq();
                 }
                 f.end_part();

@@ -115,6 +115,65 @@ void Flattener::coord(double x, double y) {
     }
 }
 
+// Bounds / part extents of the n coordinates just appended at [first, first + n).  Equivalent to calling
+// bound() and the fmin/fmax folds of coord() one coordinate at a time: every fold is "replace when strictly
+// smaller / larger", which ignores NaN operands exactly like f64::min / f64::max do, so folding a run's own
+// minimum (seeded with +-inf) into the running value gives the same result in any grouping.
+void Flattener::extents(size_t first, size_t n) {
+    if (n == 0) return;
+    const Pool& p = g_->pool[kind_];
+    const double* xs = p.x.data() + first;
+    const double* ys = p.y.data() + first;
+    if (seq_bounds_ && !geom_has_bounds_) bound(xs[0], ys[0]);  // geo's fold is seeded by the first coordinate (even a NaN one)
+    const double inf = std::numeric_limits<double>::infinity();
+    double xlo = inf, xhi = -inf, ylo = inf, yhi = -inf;
+    for (size_t i = 0; i < n; i++) {
+        const double x = xs[i], y = ys[i];
+        xlo = x < xlo ? x : xlo;
+        xhi = x > xhi ? x : xhi;
+        ylo = y < ylo ? y : ylo;
+        yhi = y > yhi ? y : yhi;
+    }
+    if (seq_bounds_) {  // (folding the seed coordinate in again changes nothing)
+        if (xlo < gb_[0]) gb_[0] = xlo;
+        if (xhi > gb_[2]) gb_[2] = xhi;
+        if (ylo < gb_[1]) gb_[1] = ylo;
+        if (yhi > gb_[3]) gb_[3] = yhi;
+    }
+    if (kind_ == RZ_PART_POLYGON) {
+        g_->part_xlo[part_] = std::fmin(g_->part_xlo[part_], xlo);
+        g_->part_xhi[part_] = std::fmax(g_->part_xhi[part_], xhi);
+        g_->part_ylo[part_] = std::fmin(g_->part_ylo[part_], ylo);
+        g_->part_yhi[part_] = std::fmax(g_->part_yhi[part_], yhi);
+    }
+}
+
+void Flattener::coords(const double* xs, const double* ys, size_t n) {
+    if (n == 0) return;
+    Pool& p = g_->pool[kind_];
+    const size_t first = p.x.size();
+    p.x.insert(p.x.end(), xs, xs + n);
+    p.y.insert(p.y.end(), ys, ys + n);
+    p.tag.insert(p.tag.end(), n, part_);
+    extents(first, n);
+}
+
+void Flattener::coords_le(const uint8_t* rec, size_t stride, size_t n) {
+    if (n == 0) return;
+    Pool& p = g_->pool[kind_];
+    const size_t first = p.x.size();
+    p.x.resize(first + n);
+    p.y.resize(first + n);
+    p.tag.insert(p.tag.end(), n, part_);
+    double* xd = p.x.data() + first;
+    double* yd = p.y.data() + first;
+    for (size_t i = 0; i < n; i++, rec += stride) {
+        std::memcpy(xd + i, rec, 8);
+        std::memcpy(yd + i, rec + 8, 8);
+    }
+    extents(first, n);
+}
+
 void Flattener::end_seq() {
     Pool& p = g_->pool[kind_];
     size_t n = p.size() - seq_start_;
@@ -198,6 +257,11 @@ bool wkb_header(Cursor& c, WkbHeader& h) {
 void wkb_coords(Cursor& c, const WkbHeader& h, Flattener& f) {
     uint32_t n = c.u32(h.le);
     if (!c.need((size_t)n * 8 * (size_t)h.dims)) return;
+    if (h.le) {  // the common case: one pass over the run
+        f.coords_le(c.p, 8 * (size_t)h.dims, n);
+        c.p += (size_t)n * 8 * (size_t)h.dims;
+        return;
+    }
     for (uint32_t i = 0; i < n; i++) {
         double x = c.f64(h.le), y = c.f64(h.le);
         for (int k = 2; k < h.dims; k++) c.f64(h.le);
@@ -506,10 +570,15 @@ bool read_wkt(const char* s, Flattener& f, bool* keep) {
 }
 
 void finish_geoms(rz_geoms* g) {
+    // give back over-allocation only when it is large: shrinking copies the whole vector, and reserved but
+    // untouched memory is address space, not resident pages
+    auto fit = [](auto& v) {
+        if (v.capacity() > 2 * v.size() + 4096) v.shrink_to_fit();
+    };
     for (int k = 0; k < 3; k++) {
-        g->pool[k].x.shrink_to_fit();
-        g->pool[k].y.shrink_to_fit();
-        g->pool[k].tag.shrink_to_fit();
+        fit(g->pool[k].x);
+        fit(g->pool[k].y);
+        fit(g->pool[k].tag);
     }
 }
 

@@ -6,6 +6,9 @@
 #include <map>
 #include <mutex>
 #include <string>
+#include <cstdlib>
+#include <new>
+#include <sys/mman.h>
 #include <utility>
 #include <vector>
 
@@ -22,9 +25,35 @@ constexpr uint32_t TAG_PART_MASK = 0x3fffffffu;
 constexpr uint32_t TAG_CLOSED = 0x40000000u;
 constexpr uint32_t TAG_SEQ_END = 0x80000000u;
 
+// Allocator of the vertex pools: large blocks are 2 MiB-aligned and advised to use transparent huge pages.
+// Filling a fresh 4 GB pool through 4 KiB pages spends most of its time in page faults (measured: 0.79 s
+// against 0.23 s for 20M vertices); with huge pages the faults are 512 times fewer.
+template <typename T> struct HugeAlloc {
+    using value_type = T;
+    HugeAlloc() = default;
+    template <class U> HugeAlloc(const HugeAlloc<U>&) {}
+    T* allocate(size_t n) {
+        const size_t bytes = n * sizeof(T);
+        void* p = nullptr;
+        if (bytes >= ((size_t)4 << 20)) {
+            const size_t huge = (size_t)2 << 20, rounded = (bytes + huge - 1) & ~(huge - 1);
+            if (posix_memalign(&p, huge, rounded) != 0) throw std::bad_alloc();
+            madvise(p, rounded, MADV_HUGEPAGE);  // advisory: failure only means ordinary pages
+        } else {
+            p = std::malloc(bytes ? bytes : 1);
+            if (!p) throw std::bad_alloc();
+        }
+        return static_cast<T*>(p);
+    }
+    void deallocate(T* p, size_t) { std::free(p); }
+    template <class U> bool operator==(const HugeAlloc<U>&) const { return true; }
+    template <class U> bool operator!=(const HugeAlloc<U>&) const { return false; }
+};
+template <typename T> using HVec = std::vector<T, HugeAlloc<T>>;
+
 struct Pool {
-    std::vector<double> x, y;
-    std::vector<uint32_t> tag;
+    HVec<double> x, y;
+    HVec<uint32_t> tag;
     size_t size() const { return x.size(); }
 };
 
@@ -72,12 +101,17 @@ class Flattener {
     // like geo_types::Polygon::new does.
     void begin_seq(bool counts_for_bounds);
     void coord(double x, double y);
+    // n coordinates at once (same result as n coord() calls): separate x / y arrays, or interleaved
+    // little-endian records of `stride` bytes starting with x, y (a WKB coordinate run)
+    void coords(const double* xs, const double* ys, size_t n);
+    void coords_le(const uint8_t* rec, size_t stride, size_t n);
     void end_seq();
     bool ok() const { return ok_; }
     const char* error() const { return err_; }
 
   private:
     void bound(double x, double y);
+    void extents(size_t first, size_t n);
     rz_geoms* g_;
     int kind_ = -1;
     uint32_t part_ = 0;

@@ -622,14 +622,164 @@ __device__ __forceinline__ void all_touched_walk(const KParams& P, double x, dou
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// PixelCache — rust/src/rasterization/pixel_cache.rs, writers.rs:15-60
+// ---------------------------------------------------------------------------------------------
+// Open-addressing hash set keyed by (part,row,col) holding the smallest burn index that wrote the
+// pixel: a write is kept iff it is that first visit (LineWriter::write, writers.rs:25-29).
+struct VisitSet {
+    unsigned long long* keys;  // ~0 = empty
+    unsigned long long* first; // smallest burn index
+    unsigned long long mask;   // capacity - 1 (power of two)
+    uint32_t col_bits, row_bits;
+    __device__ __forceinline__ unsigned long long key_of(uint32_t part, uint32_t row, uint32_t col) const {
+        return ((((unsigned long long)part << row_bits) | row) << col_bits) | col;
+    }
+    __device__ __forceinline__ unsigned long long slot_of(unsigned long long k) const {
+        k ^= k >> 33;
+        k *= 0xff51afd7ed558ccdull;
+        k ^= k >> 33;
+        k *= 0xc4ceb9fe1a85ec53ull;
+        k ^= k >> 33;
+        return k & mask;
+    }
+    __device__ __forceinline__ void insert(unsigned long long k, unsigned long long burn) const {
+        for (unsigned long long h = slot_of(k);; h = (h + 1) & mask) {
+            const unsigned long long old = atomicCAS(&keys[h], ~0ull, k);
+            if (old == ~0ull || old == k) {
+                atomicMin(&first[h], burn);
+                return;
+            }
+        }
+    }
+    __device__ __forceinline__ bool contains(unsigned long long k) const {
+        for (unsigned long long h = slot_of(k);; h = (h + 1) & mask) {
+            const unsigned long long cur = keys[h];
+            if (cur == k) return true;
+            if (cur == ~0ull) return false;
+        }
+    }
+    __device__ __forceinline__ bool is_first(unsigned long long k, unsigned long long burn) const {
+        for (unsigned long long h = slot_of(k);; h = (h + 1) & mask)
+            if (keys[h] == k) return first[h] == burn;
+    }
+};
+
+// The reference's PixelCache is a bitset over the bounding box of the line segments extract_line kept
+// (pixel_cache.rs:15-37).  CacheBox is that box per polygon part; cache_contains() is PixelCache::contains
+// INCLUDING its behaviour for pixels outside the box, which FillWriter does ask about when a ring segment lies
+// entirely outside the raster and was dropped (edges.rs:124-132): unravel_index (pixel_cache.rs:39-44)
+// wraps, so such a pixel aliases onto another cell of the box - or falls off the bitset, which reads false.
+struct CacheBox {
+    long long xmin, ymin;             // (x_lo as isize, y_lo as isize): truncation, not floor
+    unsigned long long width, length; // floor(hi) - floor(lo) + 1
+};
+struct CacheAcc {  // per part: order-preserving u64 encodings of the kept segments' min / max ordinates
+    unsigned long long xlo, ylo, xhi, yhi;
+    unsigned int dropped, pad;  // a ring segment failed extract_line's test
+};
+__device__ __forceinline__ unsigned long long f64_ordered(double d) {
+    const unsigned long long u = (unsigned long long)__double_as_longlong(d);
+    return (u >> 63) ? ~u : (u | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double f64_from_ordered(unsigned long long u) {
+    u = (u >> 63) ? (u & 0x7fffffffffffffffull) : ~u;
+    return __longlong_as_double((long long)u);
+}
+__device__ __forceinline__ bool cache_contains(uint32_t nrows, uint32_t ncols, const CacheBox& b, const VisitSet& vs,
+                                               uint32_t part, uint32_t row, uint32_t col) {
+    const unsigned long long lx = (unsigned long long)((long long)col - b.xmin);
+    const unsigned long long ly = (unsigned long long)((long long)row - b.ymin);
+    const unsigned long long idx = ly * b.width + lx;  // wrapping, like the release build
+    if (idx >= b.width * b.length) return false;        // FixedBitSet::contains past the end
+    const unsigned long long cy = idx / b.width, cx = idx - cy * b.width;
+    const long long ax = (long long)cx + b.xmin, ay = (long long)cy + b.ymin;
+    if (ax < 0 || ay < 0 || ax >= (long long)ncols || ay >= (long long)nrows) return false;  // never walked
+    return vs.contains(vs.key_of(part, (uint32_t)ay, (uint32_t)ax));
+}
+
+// one thread per ring vertex: the segment (i, i+1) either extends its part's box or marks the part
+__global__ void cache_box_kernel(KParams P, const double* __restrict__ x, const double* __restrict__ y,
+                                 const uint32_t* __restrict__ tag, uint32_t n, CacheAcc* __restrict__ acc) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || (tag[i] & 0x80000000u)) return;
+    const uint32_t part = tag[i] & 0x3fffffffu;
+    const double x0 = px_x(P, x[i]), y0 = px_y(P, y[i]), x1 = px_x(P, x[i + 1]), y1 = px_y(P, y[i + 1]);
+    const double min_x = fmin(x0, x1), max_x = fmax(x0, x1), min_y = fmin(y0, y1), max_y = fmax(y0, y1);
+    if (!(min_x < P.ncols_f && max_x >= 0.0 && min_y < P.nrows_f && max_y >= 0.0)) {  // edges.rs:130
+        atomicOr(&acc[part].dropped, 1u);
+        return;
+    }
+    atomicMin(&acc[part].xlo, f64_ordered(min_x));
+    atomicMin(&acc[part].ylo, f64_ordered(min_y));
+    atomicMax(&acc[part].xhi, f64_ordered(max_x));
+    atomicMax(&acc[part].yhi, f64_ordered(max_y));
+}
+__global__ void cache_box_init_kernel(uint32_t n_parts, CacheAcc* __restrict__ acc) {
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_parts) return;
+    CacheAcc a;
+    a.xlo = a.ylo = f64_ordered(DBL_MAX);  // PixelCache::new's fold seeds (pixel_cache.rs:16-17)
+    a.xhi = a.yhi = f64_ordered(-DBL_MAX);
+    a.dropped = a.pad = 0;
+    acc[p] = a;
+}
+__global__ void cache_box_finish_kernel(uint32_t n_parts, const CacheAcc* __restrict__ acc, CacheBox* __restrict__ box) {
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_parts) return;
+    const double xlo = f64_from_ordered(acc[p].xlo), ylo = f64_from_ordered(acc[p].ylo);
+    const double xhi = f64_from_ordered(acc[p].xhi), yhi = f64_from_ordered(acc[p].yhi);
+    auto as_usize = [](double v) -> unsigned long long {  // Rust `f64 as usize`
+        if (!(v > 0.0)) return 0ull;
+        if (v >= 18446744073709551615.0) return ~0ull;
+        return (unsigned long long)v;
+    };
+    auto as_isize = [](double v) -> long long {  // Rust `f64 as isize`
+        if (!(v == v)) return 0;
+        if (v <= -9223372036854775808.0) return (long long)0x8000000000000000ull;
+        if (v >= 9223372036854775807.0) return 0x7fffffffffffffffll;
+        return (long long)v;
+    };
+    CacheBox b;
+    b.width = as_usize(__dsub_rn(floor(xhi), floor(xlo))) + 1ull;
+    b.length = as_usize(__dsub_rn(floor(yhi), floor(ylo))) + 1ull;
+    b.xmin = as_isize(xlo);
+    b.ymin = as_isize(ylo);
+    box[p] = b;
+}
+
 // One thread per vertex of a ring / line-string pool.  mode 0 counts the in-window pixels, mode 1
 // emits one record per pixel (flagged as "pixel of the part's boundary walk").
 __global__ void __launch_bounds__(256)
 touched_walk_kernel(KParams P, const double* __restrict__ x, const double* __restrict__ y,
                     const uint32_t* __restrict__ tag, uint32_t n, const PartInfo* __restrict__ info,
-                    Counters* __restrict__ ctr, uint64_t* __restrict__ keys, int mode) {
+                    Counters* __restrict__ ctr, uint64_t* __restrict__ keys, int mode,
+                    const CacheAcc* __restrict__ acc = nullptr, VisitSet vs = VisitSet{}) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     unsigned long long cnt = 0;
+    if (mode >= 2) {
+        // modes 2 / 3 (sum / count only): count / remember every walked pixel - over the whole raster, not the
+        // window - of the polygon parts that had a ring segment dropped; their fill may ask the PixelCache
+        // about pixels outside its box, which alias onto these cells (cache_contains)
+        if (i < n && !(tag[i] & 0x80000000u)) {
+            const uint32_t part = tag[i] & 0x3fffffffu;
+            if (info[part].band >= 0 && acc[part].dropped) {
+                const double x0 = px_x(P, x[i]), y0 = px_y(P, y[i]), x1 = px_x(P, x[i + 1]), y1 = px_y(P, y[i + 1]);
+                const double min_x = fmin(x0, x1), max_x = fmax(x0, x1), min_y = fmin(y0, y1), max_y = fmax(y0, y1);
+                if (min_x < P.ncols_f && max_x >= 0.0 && min_y < P.nrows_f && max_y >= 0.0)
+                    all_touched_walk(P, x0, y0, x1, y1, [&](uint32_t row, uint32_t col) {
+                        if (mode == 2) cnt++;
+                        else vs.insert(vs.key_of(part, row, col), 0ull);
+                    });
+            }
+        }
+        if (mode == 2) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) cnt += __shfl_down_sync(0xffffffffu, cnt, o);
+            if (lane_id() == 0 && cnt) atomicAdd(&ctr->cursor, cnt);
+        }
+        return;
+    }
     if (i < n && !(tag[i] & 0x80000000u)) {
         const uint32_t part = tag[i] & 0x3fffffffu;
         const PartInfo pi = info[part];
@@ -875,6 +1025,15 @@ struct FillParams {
     uint32_t vec_ok;           // rows of `out` are 16-byte aligned
     uint32_t all_poly;         // no line / point parts: skip the kind lookup
     uint32_t all_touched;      // polygon runs also carry boundary-walk pixels (flagged records)
+    uint32_t nrows;            // raster rows (full raster)
+    uint32_t win_r0;           // first raster row of this window
+};
+
+// all_touched with sum / count: what FillWriter needs for parts whose PixelCache box does not cover their fill
+struct AliasCtx {
+    const CacheAcc* acc;  // nullptr: not in that mode
+    const CacheBox* box;
+    VisitSet vs;
 };
 
 constexpr int FILL_WARPS = 4;
@@ -914,9 +1073,25 @@ __device__ __forceinline__ void apply_mask(N* __restrict__ row_lane, uint32_t m,
 // Close a polygon run: turn the toggle mask into the even-odd inside mask and burn the value.
 // Bits at or beyond the tile's width may end up set; they only touch shared-memory pixels that are
 // never flushed.
+// FillWriter for a part with a dropped ring segment: remove from the inside mask every pixel the reference's
+// PixelCache claims to contain (cache_contains: aliased cells for pixels outside the cache's box)
+__device__ __noinline__ uint32_t drop_cached_fill(uint32_t m, uint32_t walked, const FillParams& F, const AliasCtx& A,
+                                                  uint32_t part, uint32_t row, uint32_t c0, uint32_t w, uint32_t lane) {
+    const CacheBox b = A.box[part];
+    uint32_t cand = m & ~walked;
+    while (cand) {
+        const uint32_t bit = (uint32_t)__ffs(cand) - 1u;
+        cand &= cand - 1;
+        const uint32_t rel = lane * 32 + bit;
+        if (rel < w && cache_contains(F.nrows, F.ncols, b, A.vs, part, row, c0 + rel)) m &= ~(1u << bit);
+    }
+    return m;
+}
+
 template <typename N, int FN>
 __device__ __forceinline__ void finish_poly_run(uint32_t* tog, uint32_t* orm, N* row_lane, uint32_t lane,
-                                                uint32_t lt_mask, N v, N bg) {
+                                                uint32_t lt_mask, N v, N bg, const FillParams& F, const AliasCtx& A,
+                                                uint32_t part, uint32_t row, uint32_t c0, uint32_t w) {
     const uint32_t t = tog[lane];
     tog[lane] = 0;
     const uint32_t walked = orm[lane];  // all_touched: pixels of the ring walk (burn_geometry.rs:225-238)
@@ -929,6 +1104,7 @@ __device__ __forceinline__ void finish_poly_run(uint32_t* tog, uint32_t* orm, N*
     m ^= m << 16;
     const uint32_t odd_words = __ballot_sync(0xffffffffu, __popc(t) & 1);
     if (__popc(odd_words & lt_mask) & 1) m = ~m;
+    if (A.acc && A.acc[part].dropped) m = drop_cached_fill(m, walked, F, A, part, row, c0, w, lane);
     m |= walked;
     apply_mask<N, FN>(row_lane, m, lane, v, bg);
     __syncwarp();
@@ -938,7 +1114,7 @@ template <typename N, int FN, bool ALL_POLY>
 __global__ void __launch_bounds__(FILL_WARPS * 32)
 fill_kernel(FillParams F, const uint64_t* __restrict__ keys, const uint32_t* __restrict__ task_start,
             const PartInfo* __restrict__ info, const uint8_t* __restrict__ part_kind, uint64_t bg_bits,
-            N* __restrict__ out) {
+            N* __restrict__ out, AliasCtx A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ uint32_t s_tog[FILL_WARPS][32], s_orm[FILL_WARPS][32];
     const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
@@ -972,7 +1148,9 @@ fill_kernel(FillParams F, const uint64_t* __restrict__ keys, const uint32_t* __r
         uint32_t run_cnt = 0;        // records of the currently open polygon run
         uint32_t run_beg = beg;      // its first record
         uint32_t open_kind = 3;      // kind of the run left open by the previous chunk (3 = none)
+        uint32_t open_part = 0;
         N open_v = bg;
+        const uint32_t abs_row = F.win_r0 + r;
         for (uint32_t base = beg; base < end; base += 32) {
             const uint32_t nvalid = min(32u, end - base);
             const bool valid = lane < nvalid;
@@ -991,7 +1169,7 @@ fill_kernel(FillParams F, const uint64_t* __restrict__ keys, const uint32_t* __r
             if ((heads & 1u) && open_kind != 3) {  // the open run ended exactly at the chunk boundary
                 if (open_kind == 0) {
                     if (run_cnt & 1u) drop_last_crossing(tog, keys, run_beg, base, col_mask, flag_bit, w, lane);
-                    finish_poly_run<N, FN>(tog, orm, row_lane, lane, lt_mask, open_v, bg);
+                    finish_poly_run<N, FN>(tog, orm, row_lane, lane, lt_mask, open_v, bg, F, A, open_part, abs_row, c0, w);
                 } else if (open_kind == 1) {
                     tog[lane] = 0;
                     __syncwarp();
@@ -1008,7 +1186,8 @@ fill_kernel(FillParams F, const uint64_t* __restrict__ keys, const uint32_t* __r
                 const bool run_ends = stop < nvalid || last_chunk;
                 const N v = __shfl_sync(0xffffffffu, my_v, start);
                 uint32_t kind = 0;
-                if (!ALL_POLY) kind = part_kind[__shfl_sync(0xffffffffu, part, start)];
+                const uint32_t run_part = __shfl_sync(0xffffffffu, part, start);
+                if (!ALL_POLY) kind = part_kind[run_part];
                 if ((heads >> start) & 1u) run_beg = base + start;
                 if (kind == 0) {
                     if (F.all_touched) {
@@ -1024,7 +1203,7 @@ fill_kernel(FillParams F, const uint64_t* __restrict__ keys, const uint32_t* __r
                     __syncwarp();
                     if (run_ends) {
                         if (run_cnt & 1u) drop_last_crossing(tog, keys, run_beg, base + stop, col_mask, flag_bit, w, lane);
-                        finish_poly_run<N, FN>(tog, orm, row_lane, lane, lt_mask, v, bg);
+                        finish_poly_run<N, FN>(tog, orm, row_lane, lane, lt_mask, v, bg, F, A, run_part, abs_row, c0, w);
                         run_cnt = 0;
                     }
                 } else {
@@ -1057,6 +1236,7 @@ fill_kernel(FillParams F, const uint64_t* __restrict__ keys, const uint32_t* __r
                 if (!run_ends) {
                     open_kind = kind == 0 ? 0u : ((kind == 1 && F.dedup_lines) ? 1u : 2u);
                     open_v = v;
+                    open_part = run_part;
                 }
                 start = stop;
             }

@@ -222,46 +222,6 @@ __device__ __forceinline__ void for_each_line_pixel(const KParams& P, const doub
     }
 }
 
-// Open-addressing hash set keyed by (part,row,col) holding the smallest burn index that wrote the
-// pixel: a write is kept iff it is that first visit (LineWriter::write, writers.rs:25-29).
-struct VisitSet {
-    unsigned long long* keys;  // ~0 = empty
-    unsigned long long* first; // smallest burn index
-    unsigned long long mask;   // capacity - 1 (power of two)
-    uint32_t col_bits, row_bits;
-    __device__ __forceinline__ unsigned long long key_of(uint32_t part, uint32_t row, uint32_t col) const {
-        return ((((unsigned long long)part << row_bits) | row) << col_bits) | col;
-    }
-    __device__ __forceinline__ unsigned long long slot_of(unsigned long long k) const {
-        k ^= k >> 33;
-        k *= 0xff51afd7ed558ccdull;
-        k ^= k >> 33;
-        k *= 0xc4ceb9fe1a85ec53ull;
-        k ^= k >> 33;
-        return k & mask;
-    }
-    __device__ __forceinline__ void insert(unsigned long long k, unsigned long long burn) const {
-        for (unsigned long long h = slot_of(k);; h = (h + 1) & mask) {
-            const unsigned long long old = atomicCAS(&keys[h], ~0ull, k);
-            if (old == ~0ull || old == k) {
-                atomicMin(&first[h], burn);
-                return;
-            }
-        }
-    }
-    __device__ __forceinline__ bool contains(unsigned long long k) const {
-        for (unsigned long long h = slot_of(k);; h = (h + 1) & mask) {
-            const unsigned long long cur = keys[h];
-            if (cur == k) return true;
-            if (cur == ~0ull) return false;
-        }
-    }
-    __device__ __forceinline__ bool is_first(unsigned long long k, unsigned long long burn) const {
-        for (unsigned long long h = slot_of(k);; h = (h + 1) & mask)
-            if (keys[h] == k) return first[h] == burn;
-    }
-};
-
 template <bool TOUCHED>
 __global__ void line_visit_insert_kernel(KParams P, const double* __restrict__ x, const double* __restrict__ y,
                                          const uint32_t* __restrict__ tag, uint32_t n, const PartInfo* __restrict__ info,
@@ -317,13 +277,19 @@ struct OutPrefix64 {
 struct InSpanKept {
     InSpanLen base;
     VisitSet vs;
+    KParams P;
+    const CacheBox* box;
     uint32_t row_bits;
     __device__ unsigned long long operator()(uint32_t i) const {
         const uint32_t len = (uint32_t)base(i);
         if (!len) return 0ull;
-        const uint64_t k = base.keys[i];  // [part | row | col]: the pixel keys of the span are k, k+1, ...
+        const uint64_t k = base.keys[i];  // [part | row | col]
+        const uint32_t part = (uint32_t)(k >> (base.col_bits + row_bits));
+        const uint32_t row = (uint32_t)(k >> base.col_bits) & ((1u << row_bits) - 1u);
+        const uint32_t col = (uint32_t)k & ((1u << base.col_bits) - 1u);
+        const CacheBox b = box[part];
         unsigned long long c = 0;
-        for (uint32_t j = 0; j < len; j++) c += !vs.contains(k + j);
+        for (uint32_t j = 0; j < len; j++) c += !cache_contains(P.nrows, P.ncols, b, vs, part, row, col + j);
         return c;
     }
 };
@@ -513,9 +479,9 @@ poly_expand_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict
 // thread per span writes the kept pixels one after another
 template <typename N>
 __global__ void __launch_bounds__(256)
-poly_expand_dedup_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ seg_start,
+poly_expand_dedup_kernel(KParams P, const uint64_t* __restrict__ keys, const uint32_t* __restrict__ seg_start,
                          const unsigned long long* __restrict__ poly_off, uint32_t n, SparseLayout L, VisitSet vs,
-                         const PartInfo* __restrict__ info, const unsigned long long* __restrict__ part_base,
+                         const CacheBox* __restrict__ box, const PartInfo* __restrict__ info, const unsigned long long* __restrict__ part_base,
                          const unsigned long long* __restrict__ part_start, unsigned long long* __restrict__ rows,
                          unsigned long long* __restrict__ cols, N* __restrict__ data) {
     const uint32_t i = blockIdx.x * 256 + threadIdx.x;
@@ -529,8 +495,9 @@ poly_expand_dedup_kernel(const uint64_t* __restrict__ keys, const uint32_t* __re
     const uint32_t col = (uint32_t)k & ((1u << L.col_bits) - 1u);
     const N v = value_from_bits<N>(info[part].value_bits);
     unsigned long long d = part_base[part] + (poly_off[i] - part_start[part]);
+    const CacheBox b = box[part];
     for (uint32_t j = 0; j < len; j++) {
-        if (vs.contains(k + j)) continue;
+        if (cache_contains(P.nrows, P.ncols, b, vs, part, row, col + j)) continue;  // FillWriter (writers.rs:49-54)
         rows[d] = row;
         cols[d] = col + j;
         data[d] = v;

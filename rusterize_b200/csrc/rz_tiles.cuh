@@ -299,7 +299,7 @@ __global__ void block_pos_kernel(const uint64_t* __restrict__ recs, uint32_t n, 
 // (centre 0.5): only that row's crossing count is tracked, and an odd row 0 drops its largest column like
 // chunks_exact(2) drops the unpaired tail (burners.rs:305).
 template <int TILE_R>
-__global__ void __launch_bounds__(MASK_WARPS * 32, 6)
+__global__ void __launch_bounds__(MASK_WARPS * 32, 8)
 tile_mask_kernel(KParams P, TileParams T, const uint64_t* __restrict__ units, uint32_t n_units,
                  const PartTile* __restrict__ pt, const uint32_t* __restrict__ vbeg, const uint32_t* __restrict__ vend,
                  const double* __restrict__ wx, const double* __restrict__ wy, const uint32_t* __restrict__ tag,

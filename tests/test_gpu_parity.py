@@ -326,3 +326,30 @@ def test_windowed_host_output_and_streamed_upload(monkeypatch):
     geoms = synth.mixed_geometries(3, 300, 2048, 1536, rho=60.0)
     e3, g3, _ = both(geoms, "count", "uint16", 1, 0, flags=_lib.FLAG_STREAMED_H2D, **ri_kw)
     assert_same(e3, g3)
+
+
+def test_all_touched_pixel_cache_box_aliasing():
+    """all_touched with sum / count: the reference's FillWriter asks its PixelCache about fill pixels outside the
+    cache's bounding box when ring segments lie entirely outside the raster (edges.rs:124-132 drops them from the
+    box); the wrapped index (pixel_cache.rs:39-58) aliases onto other cells and the pixel is dropped if that cell
+    was walked.  Both engines' dense path must reproduce it, shards and tiles included."""
+    big = ["POLYGON ((-50 -50, 300 -50, 300 300, -50 300, -50 -50), (100 100, 150 100, 150 150, 100 150, 100 100))",
+           "POLYGON ((-30 -40, 140 -10, 150 120, 60 90, -30 -40))", "POLYGON ((200 -100, 400 128, 200 400, 128 128, 200 -100))",
+           "MULTIPOLYGON (((-10 -10, 270 -10, 270 270, -10 270, -10 -10), (20 20, 60 25, 40 70, 20 20)), "
+           "((500 500, 600 500, 600 600, 500 500)))", "POLYGON ((10 10, 200 30, 120 220, 10 10))"]
+    burn = [1, 2, 4, 8, 16]
+    for fun in ("sum", "count"):
+        for shape in [(256, 256), (64, 200), (200, 64)]:
+            exp, got, _ = both(big, fun, "int32", burn, 0, all_touched=True, shape=shape, extent=(0, 0, 256, 256))
+            assert_same(exp, got)
+        for rows in [(0, 40), (40, 41), (41, 200)]:
+            exp, got, _ = both(big, fun, "float64", burn, np.nan, all_touched=True, rows=rows, tile_bytes=256,
+                               shape=(200, 300), extent=(0, 0, 256, 256))
+            assert_same(exp, got)
+    # the sparse stream of the same job replays to the same raster
+    g = core.Geoms.from_wkt(big)
+    ri = core.raster_info(g, shape=(200, 300), extent=(0, 0, 256, 256))
+    sp = core.rasterize_sparse(g, ri, "sum", "int32", np.array(burn, np.int32), None, None, 1, 0, True)
+    dense, _ = core.rasterize_dense(g, ri, "sum", "int32", np.array(burn, np.int32), None, None, 1, 0, True)
+    rep = core.sparse_build_array(ri, "sum", 0, sp["counts"], sp["rows"], sp["cols"], sp["data"])
+    assert np.array_equal(rep, dense)

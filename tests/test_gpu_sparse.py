@@ -136,18 +136,13 @@ def test_all_touched_reference_geometries_bands_and_non_square_pixels():
                            shape=(47, 319))
         assert_same(exp, got)
     # A ring segment lying entirely outside the raster is dropped by extract_line (edges.rs:124-132).  With
-    # sum / count the reference then tests fill pixels outside its PixelCache's bounding box through a wrapped
-    # index (pixel_cache.rs:39-58) that aliases onto unrelated cells: DESIGN.md "known divergences" - not
-    # reproduced, so such polygons are compared for the functions without a cache only.
+    # sum / count the reference then asks its PixelCache about fill pixels outside the cache's bounding box,
+    # through a wrapped index (pixel_cache.rs:39-58) that aliases onto other cells: reproduced (cache_contains).
     big = ["POLYGON ((-50 -50, 300 -50, 300 300, -50 300, -50 -50), (100 100, 150 100, 150 150, 100 150, 100 100))",
-           "MULTILINESTRING ((0 0, 256 256), (256 256, 0 0))", "POLYGON ((10 10, 200 30, 120 220, 10 10))"]
-    for fun, shape in [("min", (64, 200)), ("last", (200, 64)), ("first", (256, 256))]:
-        exp, got, _ = both(big, fun, "float32", [1.5, 2.5, 4.0], np.nan, all_touched=True, shape=shape,
-                           extent=(0, 0, 256, 256))
-        assert_same(exp, got)
-    for fun, shape in [("count", (64, 200)), ("sum", (200, 64)), ("sum", (256, 256))]:  # every segment touches the raster
-        exp, got, _ = both(["POLYGON ((-20 40, 120 -30, 280 100, 200 250, 30 240, -20 40), (100 100, 150 100, 150 150, 100 100))"]
-                           + big[1:], fun, "float32", [1.5, 2.5, 4.0], np.nan, all_touched=True, shape=shape,
+           "MULTILINESTRING ((0 0, 256 256), (256 256, 0 0))", "POLYGON ((10 10, 200 30, 120 220, 10 10))",
+           "POLYGON ((-30 -40, 140 -10, 150 120, 60 90, -30 -40))", "POLYGON ((200 -100, 400 128, 200 400, 128 128, 200 -100))"]
+    for fun, shape in [("count", (64, 200)), ("sum", (200, 64)), ("sum", (256, 256)), ("last", (200, 64)), ("min", (64, 200))]:
+        exp, got, _ = both(big, fun, "float32", [1.5, 2.5, 4.0, 8.0, 16.0], np.nan, all_touched=True, shape=shape,
                            extent=(0, 0, 256, 256))
         assert_same(exp, got)
     geoms = synth.mixed_geometries(5, 150, 256, 256)
