@@ -187,6 +187,11 @@ struct InU32 {
 struct TileEdge {
     double x_top, y_top, dxdy;
 };
+// ... as tile_mask keeps it in shared memory: plus its first row in the unit and the index of its first crossing
+struct alignas(16) MaskEdge {
+    double x_top, y_top, dxdy;
+    uint32_t lo, pre;
+};
 // false when the reference skips the edge as horizontal (edges.rs:100)
 __device__ __forceinline__ bool tile_edge_slope(double x0, double y0, double x1, double y1, TileEdge& e) {
     if (!(fabs(__dsub_rn(y0, y1)) >= DBL_EPSILON)) return false;
@@ -305,8 +310,7 @@ tile_mask_kernel(KParams P, TileParams T, const uint64_t* __restrict__ units, ui
                  const double* __restrict__ wx, const double* __restrict__ wy, const uint32_t* __restrict__ tag,
                  const uint32_t* __restrict__ pos, uint32_t* __restrict__ masks) {
     __shared__ uint32_t s_mask[MASK_WARPS][MASK_SMEM_WORDS];
-    __shared__ double s_xt[MASK_WARPS][32], s_yt[MASK_WARPS][32], s_dx[MASK_WARPS][32];
-    __shared__ uint2 s_lp[MASK_WARPS][32];  // (first row, index of the first crossing) of the batch's active edges
+    __shared__ MaskEdge s_edge[MASK_WARPS][32];  // the batch's active edges, compacted
     const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
     const uint32_t unit = blockIdx.x * MASK_WARPS + warp;
     if (unit >= n_units) return;
@@ -373,10 +377,13 @@ tile_mask_kernel(KParams P, TileParams T, const uint64_t* __restrict__ units, ui
             const uint32_t pre = inc - cnt;
             if (cnt) {  // active edges are compacted: slot = rank among the batch's active edges
                 const uint32_t slot = __popc(act & lt_mask);
-                s_xt[warp][slot] = e.x_top;
-                s_yt[warp][slot] = e.y_top;
-                s_dx[warp][slot] = e.dxdy;
-                s_lp[warp][slot] = make_uint2(lo, pre);
+                MaskEdge me;
+                me.x_top = e.x_top;
+                me.y_top = e.y_top;
+                me.dxdy = e.dxdy;
+                me.lo = lo;
+                me.pre = pre;
+                s_edge[warp][slot] = me;
             }
             __syncwarp();
             // all lanes share the batch's crossings evenly: crossing kk belongs to the last active edge whose
@@ -389,12 +396,12 @@ tile_mask_kernel(KParams P, TileParams T, const uint64_t* __restrict__ units, ui
                 cum += __popc(starts);
                 const uint32_t kk = k0 + lane;
                 if (kk < wtot) {
-                    const uint2 lp = s_lp[warp][slot];
+                    const MaskEdge me = s_edge[warp][slot];  // two 16-byte shared-memory loads
                     TileEdge b;
-                    b.x_top = s_xt[warp][slot];
-                    b.y_top = s_yt[warp][slot];
-                    b.dxdy = s_dx[warp][slot];
-                    const uint32_t row = lp.x + (kk - lp.y);
+                    b.x_top = me.x_top;
+                    b.y_top = me.y_top;
+                    b.dxdy = me.dxdy;
+                    const uint32_t row = me.lo + (kk - me.pre);
                     const uint32_t col = tile_edge_col(P, b, row);
                     if (col < c1) {  // a crossing right of the chunk has no effect on its pixels
                         const uint32_t rel = col <= c0 ? 0u : col - c0;  // left of it: parity carry-in at bit 0
