@@ -174,6 +174,32 @@ class ClockSampler:
                 "reasons": sorted(self.reasons), "samples": len(self.sm), "source": "nvidia-smi"}
 
 
+def bind_to_gpu_numa_node(gpu_index: int):
+    """Pin this rank to the CPUs NVML reports as local to its GPU, so that the pinned host buffers of the
+    end-to-end path (geometry pools, output raster) are first-touched on the NUMA node the GPU's PCIe link
+    hangs off.  With 8 ranks streaming 17 GB of raster to the host at once, cross-socket traffic is what
+    limits the copies.  Best effort: returns the CPU list or None."""
+    try:
+        import pynvml
+
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            gpu_index = int(vis.split(",")[gpu_index])
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = [64 * w + b for w, m in enumerate(mask) for b in range(64) if (m >> b) & 1]
+        allowed = os.sched_getaffinity(0)
+        cpus = [c for c in cpus if c in allowed]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return cpus
+    except Exception:
+        pass
+    return None
+
+
 def peaks():
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
@@ -254,6 +280,7 @@ def run_b200(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the burn path has no CPU fallback (use --impl reference)")
     torch.cuda.set_device(local)
+    numa = bind_to_gpu_numa_node(local)  # before any large host allocation: first touch decides the NUMA node
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
@@ -429,6 +456,7 @@ def run_b200(args):
                      "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                      "bytes_per_launch": fill_bytes, "ms_per_launch": fill_ms, "second_kernel": other},
         "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
+        "rank0_cpu_affinity": (f"{len(numa)} CPUs local to the GPU (NVML)" if numa else "unchanged"),
     }
     print(json.dumps(line))
     if world > 1:

@@ -11,6 +11,7 @@
 #include <cstring>
 #include <memory>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include "rz_host.hpp"
@@ -381,7 +382,7 @@ static unsigned long long scan_total(DevBuf& partial, uint32_t n, cudaStream_t s
 // tile-binned engine dispatch
 // ------------------------------------------------------------------------------------------------
 typedef void (*TileLaunch)(uint32_t, cudaStream_t, KParams, TileParams, const uint32_t*, const unsigned long long*,
-                           const uint32_t*, uint64_t, void*);
+                           const uint32_t*, uint64_t, void*, bool);
 
 template <typename N> struct NanBackground {
     static constexpr bool possible = false;
@@ -398,19 +399,29 @@ template <> struct NanBackground<double> {
 
 template <typename N, int FN>
 static void tile_launch(uint32_t, cudaStream_t s, KParams P, TileParams T, const uint32_t* tile_start,
-                        const unsigned long long* value_sorted, const uint32_t* masks, uint64_t bg, void* out) {
+                        const unsigned long long* value_sorted, const uint32_t* masks, uint64_t bg, void* out,
+                        bool values_finite) {
     constexpr int TR = sizeof(N) <= 4 ? 64 : 32;
+    constexpr bool is_float = std::is_floating_point<N>::value;
+    constexpr bool additive = FN == RZ_SUM || FN == RZ_COUNT;
     // one CTA per tile: (tile columns, tile rows x bands) when that fits the grid limits, else flattened
     const uint64_t gy = (uint64_t)T.n_tr * P.n_bands;
     const dim3 grid = gy <= 65535 ? dim3(T.n_tc, (unsigned)gy) : dim3(T.n_tiles);
-    const size_t smem = sizeof(N) >= 4 ? 0 : (size_t)TR * TILE_C * sizeof(N);  // flush staging of 1/2-byte dtypes only
+    const size_t smem = (size_t)(TR / 8) * 8 * 4 * (32 * sizeof(N) + 16);  // flush staging: 8 padded rows per warp
     N bgv;
     std::memcpy(&bgv, &bg, sizeof(N));
-    if (NanBackground<N>::is(bgv))  // float dtypes with a NaN background: one comparison less per pixel
-        tile_apply_kernel<N, FN, TR, NanBackground<N>::possible><<<grid, TR * 4, smem, s>>>(P, T, tile_start, value_sorted,
-                                                                                         masks, bg, (N*)out);
+    const bool bg_nan = NanBackground<N>::is(bgv);
+    if (additive && is_float && bg_nan && values_finite)  // MODE 1: masked add + touched mask (see rz_tiles.cuh)
+        tile_apply_kernel<N, additive ? FN : RZ_SUM, TR, is_float ? 1 : 0, true><<<grid, TR * 4, smem, s>>>(
+            P, T, tile_start, value_sorted, masks, bg, (N*)out);
+    else if (additive && !is_float && bg == 0)            // MODE 2: plain masked add
+        tile_apply_kernel<N, additive ? FN : RZ_SUM, TR, is_float ? 0 : 2, false><<<grid, TR * 4, smem, s>>>(
+            P, T, tile_start, value_sorted, masks, bg, (N*)out);
+    else if (bg_nan)  // float dtypes with a NaN background: one comparison less per pixel
+        tile_apply_kernel<N, FN, TR, 0, NanBackground<N>::possible><<<grid, TR * 4, smem, s>>>(P, T, tile_start, value_sorted,
+                                                                                            masks, bg, (N*)out);
     else
-        tile_apply_kernel<N, FN, TR, false><<<grid, TR * 4, smem, s>>>(P, T, tile_start, value_sorted, masks, bg, (N*)out);
+        tile_apply_kernel<N, FN, TR, 0, false><<<grid, TR * 4, smem, s>>>(P, T, tile_start, value_sorted, masks, bg, (N*)out);
 }
 template <typename N> static TileLaunch tile_for_fn(int fn) {
     switch (fn) {
@@ -783,7 +794,7 @@ static void rasterize_dense(rz_geoms* g, const rz_context* ctx, void* out, rz_st
                 tile_bin_kernel<<<(n_parts + 255) / 256, 256, 0, s>>>(
                     P, T, d_info, dg->part_xlo, dg->part_xhi, dg->part_ylo, dg->part_yhi, dg->part_vbeg, dg->part_vend,
                     c.tile_cnt.as<uint32_t>(), c.tile_cnt2.as<uint32_t>(), nullptr, nullptr, nullptr, nullptr, nullptr,
-                    nullptr, 0, d_tc, 0);
+                    nullptr, 0, d_tc, 0, ctx->dtype == RZ_F32 ? 4 : (ctx->dtype == RZ_F64 ? 8 : 0));
                 launches++;
                 TileCounters h_tc;
                 CUDA_TRY(cudaMemcpyAsync(&h_tc, d_tc, sizeof h_tc, cudaMemcpyDeviceToHost, s));
@@ -811,7 +822,7 @@ static void rasterize_dense(rz_geoms* g, const rz_context* ctx, void* out, rz_st
                         P, T, d_info, dg->part_xlo, dg->part_xhi, dg->part_ylo, dg->part_yhi, dg->part_vbeg, dg->part_vend,
                         nullptr, nullptr, c.tile_off.as<unsigned long long>(), c.tile_off2.as<unsigned long long>(),
                         c.tile_pt.as<PartTile>(), c.tile_pairs.as<uint64_t>(), ka, c.tile_val.as<unsigned long long>(),
-                        block_bits, d_tc, 1);
+                        block_bits, d_tc, 1, 0);
                     launches++;
                     if (timed) CUDA_TRY(cudaEventRecord(c.ev[EV_B], s));
                     lap(emit_ms, EV_A, EV_B);
@@ -886,7 +897,7 @@ static void rasterize_dense(rz_geoms* g, const rz_context* ctx, void* out, rz_st
                     T.vec_ok = ((uintptr_t)d_out % 16 == 0) && ((ri.ncols * isz) % 16 == 0);
                     tile_for(ctx->dtype, ctx->pixel_fn)(T.n_tiles, s, P, T, c.task_start.as<uint32_t>(),
                                                         c.tile_val2.as<unsigned long long>(),
-                                                        c.tile_masks.as<uint32_t>(), bg_bits, d_out);
+                                                        c.tile_masks.as<uint32_t>(), bg_bits, d_out, !h_tc.nonfinite);
                     launches++;
                     CUDA_TRY(cudaGetLastError());
                     if (timed) CUDA_TRY(cudaEventRecord(c.ev[EV_B], s));

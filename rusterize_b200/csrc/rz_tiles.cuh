@@ -50,6 +50,7 @@ struct TileCounters {
     unsigned long long pairs;        // (part, tile) pairs
     unsigned long long row_pairs;    // mask units: (part, run of tile rows) handled by one tile_mask warp
     unsigned long long edge_visits;  // sum over parts of units x column chunks x ring vertices
+    unsigned int nonfinite, pad;     // some part burns a NaN / infinite value (float dtypes)
 };
 
 // where a part's inside-mask blocks live: block(tr, tc) = first_block + (tr - tr0) * ntc + (tc - tc0)
@@ -118,7 +119,7 @@ __global__ void tile_bin_kernel(KParams P, TileParams T, const PartInfo* __restr
                                 const unsigned long long* __restrict__ off_rows, PartTile* __restrict__ pt,
                                 uint64_t* __restrict__ row_pairs, uint64_t* __restrict__ recs,
                                 unsigned long long* __restrict__ block_value, uint32_t block_bits,
-                                TileCounters* __restrict__ tc, int mode) {
+                                TileCounters* __restrict__ tc, int mode, int float_bytes) {
     const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t ntr = 0, ntc = 0, n_units = 0, r_lo = 0, r_hi = 0, c_lo = 0, c_hi = 0;
     if (p < P.n_parts) {
@@ -160,6 +161,11 @@ __global__ void tile_bin_kernel(KParams P, TileParams T, const PartInfo* __restr
         if (p < P.n_parts) {
             cnt_tiles[p] = ntr * ntc;
             cnt_rows[p] = n_units;
+            if (float_bytes) {  // exponent all ones: NaN or infinity (tile_apply's additive mode needs finite values)
+                const unsigned long long vb = info[p].value_bits;
+                const bool bad = float_bytes == 4 ? ((vb >> 23) & 0xffu) == 0xffu : ((vb >> 52) & 0x7ffu) == 0x7ffu;
+                if (bad && info[p].band >= 0) atomicOr(&tc->nonfinite, 1u);
+            }
         }
         const uint32_t chunks = (ntc * 4 + MASK_MAX_WORDS - 1) / MASK_MAX_WORDS;
         unsigned long long pairs = (unsigned long long)ntr * ntc, rows = n_units,
@@ -465,37 +471,41 @@ tile_mask_kernel(KParams P, TileParams T, const uint64_t* __restrict__ units, ui
 // ---------------------------------------------------------------------------------------------
 // tile_apply: one CTA per tile, each warp owns 8 rows held in REGISTERS, no synchronisation between warps
 // ---------------------------------------------------------------------------------------------
-// Lane l of a warp keeps pixel (row r, column 32w + l) of its 8 x 128 pixels in register px[r][w]
-// (initialised to the background: geo/raster.rs:23-28).  A part's inside mask arrives as one coalesced
-// 128-byte load, lane 4r + w holding the 32-bit word of (row r, columns 32w ..): for every row the part
-// reaches, its four words are broadcast and each lane applies the part's value to its pixel if its bit is
-// set - the reference's pixel-function rule (pixel_functions.rs:56-123), parts in burn order.  No
-// shared-memory round trip per pixel; the registers are flushed once with coalesced streaming stores.
-// (Measured alternatives on config 4: pixels in shared memory 6.65 ms; registers with 4 consecutive pixels
-// per lane and 16-byte stores 6.09 ms; this layout 5.58 ms.)
-
-// the rows of one part (nz: bit 4r + w = mask word w of row r is not empty) applied to this lane's 8 x 4 pixels
-template <typename N, int FN, bool BGNAN, bool VOK>
-__device__ __forceinline__ void apply_part_rows(N (&px)[8][4], uint32_t m, uint32_t nz, uint32_t lane_bit, N v, N bg) {
+// A part's inside mask arrives as one coalesced 128-byte load per warp: lane 4r + w holds the 32-bit word of
+// (row r, columns 32w .. 32w+31) of the warp's 8 x 128 pixels - and that lane OWNS those 32 pixels, in
+// registers px[0..31] (initialised to the background: geo/raster.rs:23-28).  Applying a part is therefore
+// lane-local: no shuffle, no shared memory; bit b of the lane's own mask word decides whether pixel b takes the
+// part's value through the reference's pixel-function rule (pixel_functions.rs:56-123), parts in burn order.
+//
+// MODE selects how the rule is evaluated (all bit-exact with the reference):
+//   0  generic: apply_px on every pixel slot, selected by the mask bit.
+//   1  additive with a touched mask - `sum` / `count` on a float dtype with a NaN background when every burn value
+//      is finite (checked on the device, TileCounters::nonfinite).  The running value can then never become NaN,
+//      so "untouched" is just "never written": pixels start at -0.0 (the additive identity: -0.0 + v == v for
+//      every v, signed zeros included), a masked add is ONE predicated instruction, the lane ORs the mask word
+//      into its touched word, and untouched pixels become the background at the flush.
+//   2  additive, plain - `sum` / `count` on an integer dtype with background 0: `cur == bg ? v : cur + v` is
+//      `cur + v` for every cur (wrapping), no touched mask needed.
+// (Measured alternatives on config 4: pixels in shared memory 6.65 ms; registers with one column per lane and
+// shuffled mask words 5.30 ms; four consecutive pixels per lane 6.09 ms.)
+template <typename N, int FN, int MODE, bool BGNAN>
+__device__ __forceinline__ void apply_part_word(N (&px)[32], uint32_t mw, N v, N bg) {
 #pragma unroll
-    for (int r = 0; r < 8; r++) {
-        if (nz & (0xfu << (4 * r))) {  // warp-uniform: the part has pixels in row r
-#pragma unroll
-            for (int w = 0; w < 4; w++) {
-                const uint32_t mw = __shfl_sync(0xffffffffu, m, 4 * r + w);
-                const N nv = apply_px<N, FN, BGNAN, VOK>(px[r][w], v, bg);
-                if (mw & lane_bit) px[r][w] = nv;
-            }
+    for (int b = 0; b < 32; b++) {
+        if (MODE == 0) {
+            const N nv = apply_px<N, FN, BGNAN, true>(px[b], v, bg);
+            if (mw & (1u << b)) px[b] = nv;
+        } else {
+            if (mw & (1u << b)) px[b] = add_v(px[b], FN == RZ_COUNT ? (N)1 : v);
         }
     }
 }
 
-template <typename N, int FN, int TILE_R, bool BGNAN>
+template <typename N, int FN, int TILE_R, int MODE, bool BGNAN>
 __global__ void __launch_bounds__(TILE_R * 4, 4)
 tile_apply_kernel(KParams P, TileParams T, const uint32_t* __restrict__ tile_start,
                   const unsigned long long* __restrict__ value_sorted, const uint32_t* __restrict__ masks,
                   uint64_t bg_bits, N* __restrict__ out) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];  // only used to stage the flush of 1/2-byte dtypes
     const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
     const N bg = value_from_bits<N>(bg_bits);
 
@@ -518,18 +528,22 @@ tile_apply_kernel(KParams P, TileParams T, const uint32_t* __restrict__ tile_sta
     const uint32_t t = (band * T.n_tr + trow) * T.n_tc + tcol;
     const uint32_t r0 = P.win_r0 + trow * TILE_R + warp * 8;
     if (r0 >= P.win_r1) return;
-    const uint32_t r1 = min(r0 + 8, P.win_r1);
-    const uint32_t c0 = tcol * TILE_C, c1 = min(c0 + TILE_C, P.ncols);
+    const uint32_t c0 = tcol * TILE_C;
 
-    N px[8][4];
+    N px[32];  // pixel b = (row r0 + (lane >> 2), column c0 + 32 * (lane & 3) + b)
+    uint32_t touched = 0;
+    N ident;
+    if (MODE == 1) {  // -0.0: the additive identity of IEEE addition
+        const uint64_t neg0 = sizeof(N) == 8 ? 0x8000000000000000ull : 0x80000000ull;
+        ident = value_from_bits<N>(neg0);
+    } else {
+        ident = bg;   // MODE 2: bg == 0
+    }
 #pragma unroll
-    for (int r = 0; r < 8; r++)
-#pragma unroll
-        for (int w = 0; w < 4; w++) px[r][w] = bg;
+    for (int b = 0; b < 32; b++) px[b] = ident;
 
     // The tile's blocks [beg, end) are consecutive in memory, parts in burn order.  A ring of APPLY_DEPTH
-    // blocks is kept in flight: one coalesced 128-byte load (lane = (row of this warp's group, mask word))
-    // plus one broadcast load of the part's value per block.
+    // blocks is kept in flight: one coalesced 128-byte load plus one broadcast load of the part's value per block.
     constexpr int APPLY_DEPTH = 4;
     const uint32_t beg = tile_start[t], end = tile_start[t + 1];
     const uint32_t* my_masks = masks + warp * 32 + lane;
@@ -550,53 +564,62 @@ tile_apply_kernel(KParams P, TileParams T, const uint32_t* __restrict__ tile_sta
             const bool live = nxt < end;
             m[u] = live ? my_masks[(size_t)nxt * (TILE_R * 4)] : 0u;
             val[u] = live ? *reinterpret_cast<const N*>(value_sorted + nxt) : bg;
-            const uint32_t nz = __ballot_sync(0xffffffffu, mu != 0);
-            if (nz == 0) continue;  // the part does not reach these 8 rows (or the slot is past the end)
-            // sum: a NaN value replaces the pixel (pixel_functions.rs:56-65), i.e. behaves like `last`
-            if (FN == RZ_SUM && is_nan_v(v)) apply_part_rows<N, RZ_LAST, BGNAN, true>(px, mu, nz, 1u << lane, v, bg);
-            else apply_part_rows<N, FN, BGNAN, true>(px, mu, nz, 1u << lane, v, bg);
+            if (__ballot_sync(0xffffffffu, mu != 0) == 0) continue;  // the part does not reach these 8 rows
+            if (MODE != 0) {
+                apply_part_word<N, FN, MODE, BGNAN>(px, mu, v, bg);
+                touched |= mu;
+            } else if (FN == RZ_SUM && is_nan_v(v)) {
+                // sum: a NaN value replaces the pixel (pixel_functions.rs:56-65), i.e. behaves like `last`
+                apply_part_word<N, RZ_LAST, 0, BGNAN>(px, mu, v, bg);
+            } else {
+                apply_part_word<N, FN, 0, BGNAN>(px, mu, v, bg);
+            }
         }
+    }
+    if (MODE == 1) {
+#pragma unroll
+        for (int b = 0; b < 32; b++)
+            if (!(touched & (1u << b))) px[b] = bg;
     }
 
     // ---- flush: every output byte is written exactly once ---------------------------------------------
-    if (sizeof(N) >= 4) {
-        N* dst = out + ((size_t)band * T.out_rows + T.win_row_off + (r0 - P.win_r0)) * P.ncols + c0 + lane;
-        if (r1 - r0 == 8 && c1 - c0 == TILE_C) {  // interior tile (warp-uniform): no bounds tests
+    // A lane's 32 pixels are contiguous in one output row; storing them directly would make every store
+    // instruction touch 32 different 128-byte lines.  The warp transposes through shared memory instead (16-byte
+    // chunks, segments padded by 16 bytes so that both directions are bank-conflict free) and writes whole rows
+    // with 16-byte streaming stores, 512 contiguous bytes per instruction.
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr uint32_t SEGB = 32 * sizeof(N) + 16, ROWB = 4 * SEGB;  // bytes of one 32-pixel segment / one row
+    constexpr int K16 = 2 * sizeof(N);                                // 16-byte chunks per segment
+    const uint32_t rows_here = min(8u, P.win_r1 - r0);
+    N* gbase = out + ((size_t)band * T.out_rows + T.win_row_off + (r0 - P.win_r0)) * P.ncols + c0;
+    if (T.vec_ok && c0 + TILE_C <= P.ncols) {
+        unsigned char* stage = smem_raw + (size_t)warp * 8 * ROWB;
+        unsigned char* mine = stage + (lane >> 2) * ROWB + (lane & 3u) * SEGB;
 #pragma unroll
-            for (int r = 0; r < 8; r++) {
+        for (int k = 0; k < K16; k++) {
+            alignas(16) N q[16 / sizeof(N)];
 #pragma unroll
-                for (int w = 0; w < 4; w++) __stcs(dst + w * 32, px[r][w]);
-                dst += P.ncols;
-            }
-        } else {
+            for (int j = 0; j < (int)(16 / sizeof(N)); j++) q[j] = px[k * (16 / sizeof(N)) + j];
+            *reinterpret_cast<uint4*>(mine + 16 * k) = *reinterpret_cast<const uint4*>(q);
+        }
+        __syncwarp();
+        constexpr int CH = 4 * K16;  // 16-byte chunks per 128-pixel row
+        for (uint32_t rr = 0; rr < rows_here; rr++) {
+            uint4* drow = reinterpret_cast<uint4*>(gbase + (size_t)rr * P.ncols);
 #pragma unroll
-            for (int r = 0; r < 8; r++) {
-                if (r0 + r < r1) {
-#pragma unroll
-                    for (int w = 0; w < 4; w++)
-                        if (c0 + w * 32 + lane < c1) __stcs(dst + w * 32, px[r][w]);
-                }
-                dst += P.ncols;
+            for (int j0 = 0; j0 < CH; j0 += 32) {
+                const int j = j0 + (int)lane;
+                if (CH >= 32 || j < CH)
+                    __stcs(drow + j, *reinterpret_cast<const uint4*>(stage + rr * ROWB + (j / K16) * SEGB + 16 * (j % K16)));
             }
         }
-    } else {  // narrow dtypes: stage the rows in shared memory so the stores stay 16 bytes wide
-        N* rows8 = reinterpret_cast<N*>(smem_raw) + (size_t)warp * 8 * TILE_C;
+    } else {
+        const uint32_t row = r0 + (lane >> 2), col = c0 + (lane & 3u) * 32u;
+        if (row < P.win_r1) {
+            N* dst = gbase + (size_t)(lane >> 2) * P.ncols + (lane & 3u) * 32u;
 #pragma unroll
-        for (int r = 0; r < 8; r++)
-#pragma unroll
-            for (int w = 0; w < 4; w++) rows8[r * TILE_C + w * 32 + lane] = px[r][w];
-        __syncwarp();
-        const uint32_t cols = c1 - c0;
-        for (uint32_t rr = 0; rr < r1 - r0; rr++) {
-            N* dst = out + ((size_t)band * T.out_rows + T.win_row_off + (r0 - P.win_r0) + rr) * P.ncols + c0;
-            const N* src = rows8 + rr * TILE_C;
-            if (T.vec_ok && cols == TILE_C) {
-                const uint4* s4 = reinterpret_cast<const uint4*>(src);
-                uint4* d4 = reinterpret_cast<uint4*>(dst);
-                for (uint32_t i = lane; i < TILE_C * sizeof(N) / 16; i += 32) __stcs(d4 + i, s4[i]);
-            } else {
-                for (uint32_t i = lane; i < cols; i += 32) dst[i] = src[i];
-            }
+            for (int b = 0; b < 32; b++)
+                if (col + b < P.ncols) dst[b] = px[b];
         }
     }
 }
