@@ -404,9 +404,11 @@ static void tile_launch(uint32_t, cudaStream_t s, KParams P, TileParams T, const
     constexpr int TR = sizeof(N) <= 4 ? 64 : 32;
     constexpr bool is_float = std::is_floating_point<N>::value;
     constexpr bool additive = FN == RZ_SUM || FN == RZ_COUNT;
-    // one CTA per tile: (tile columns, tile rows x bands) when that fits the grid limits, else flattened
+    // one CTA per APPLY_TILES tiles of a tile row: (column groups, tile rows x bands) when that fits the grid
+    // limits, else flattened
     const uint64_t gy = (uint64_t)T.n_tr * P.n_bands;
-    const dim3 grid = gy <= 65535 ? dim3(T.n_tc, (unsigned)gy) : dim3(T.n_tiles);
+    const uint32_t groups = (T.n_tc + APPLY_TILES - 1) / APPLY_TILES;
+    const dim3 grid = gy <= 65535 ? dim3(groups, (unsigned)gy) : dim3((unsigned)(groups * gy));
     const size_t smem = (size_t)(TR / 8) * 8 * 4 * (32 * sizeof(N) + 16);  // flush staging: 8 padded rows per warp
     N bgv;
     std::memcpy(&bgv, &bg, sizeof(N));

@@ -394,26 +394,35 @@ tile_mask_kernel(KParams P, TileParams T, const uint64_t* __restrict__ units, ui
             __syncwarp();
             // all lanes share the batch's crossings evenly: crossing kk belongs to the last active edge whose
             // first crossing is <= kk, found from the bit pattern of the first-crossing positions
+            // Two chunks of 32 crossings per iteration, evaluated without branches up to the atomic, so that the
+            // two dependent f64 chains (shared-memory load -> 5 double ops -> convert) overlap.
             uint32_t cum = 0;
-            for (uint32_t k0 = 0; k0 < wtot; k0 += 32) {
-                const uint32_t d = pre - k0;
-                const uint32_t starts = __reduce_or_sync(0xffffffffu, (cnt && d < 32u) ? 1u << d : 0u);
-                const uint32_t slot = cum + __popc(starts & le_mask) - 1u;
-                cum += __popc(starts);
-                const uint32_t kk = k0 + lane;
-                if (kk < wtot) {
-                    const MaskEdge me = s_edge[warp][slot];  // two 16-byte shared-memory loads
-                    TileEdge b;
-                    b.x_top = me.x_top;
-                    b.y_top = me.y_top;
-                    b.dxdy = me.dxdy;
-                    const uint32_t row = me.lo + (kk - me.pre);
-                    const uint32_t col = tile_edge_col(P, b, row);
-                    if (col < c1) {  // a crossing right of the chunk has no effect on its pixels
-                        const uint32_t rel = col <= c0 ? 0u : col - c0;  // left of it: parity carry-in at bit 0
-                        atomicXor(&mask[(row - row_start) * stride + (rel >> 5)], 1u << (rel & 31));
-                    }
-                }
+            auto crossing = [&](uint32_t slot, uint32_t kk, uint32_t& word, uint32_t& bit) -> bool {
+                const MaskEdge me = s_edge[warp][min(slot, 31u)];  // two 16-byte shared-memory loads
+                TileEdge b;
+                b.x_top = me.x_top;
+                b.y_top = me.y_top;
+                b.dxdy = me.dxdy;
+                const uint32_t row = me.lo + (kk - me.pre);
+                const uint32_t col = tile_edge_col(P, b, row);
+                const uint32_t rel = col <= c0 ? 0u : col - c0;  // left of the chunk: parity carry-in at bit 0
+                word = (row - row_start) * stride + (rel >> 5);
+                bit = 1u << (rel & 31);
+                return kk < wtot && col < c1;  // a crossing right of the chunk has no effect on its pixels
+            };
+            for (uint32_t k0 = 0; k0 < wtot; k0 += 64) {
+                const uint32_t da = pre - k0, db = da - 32u;
+                const uint32_t sa = __reduce_or_sync(0xffffffffu, (cnt && da < 32u) ? 1u << da : 0u);
+                const uint32_t sb = __reduce_or_sync(0xffffffffu, (cnt && db < 32u) ? 1u << db : 0u);
+                const uint32_t slot_a = cum + __popc(sa & le_mask) - 1u;
+                cum += __popc(sa);
+                const uint32_t slot_b = cum + __popc(sb & le_mask) - 1u;
+                cum += __popc(sb);
+                uint32_t wa, ba, wb, bb;
+                const bool oka = crossing(slot_a, k0 + lane, wa, ba);
+                const bool okb = crossing(slot_b, k0 + 32 + lane, wb, bb);
+                if (oka) atomicXor(&mask[wa], ba);
+                if (okb) atomicXor(&mask[wb], bb);
             }
             __syncwarp();
         }
@@ -501,6 +510,8 @@ __device__ __forceinline__ void apply_part_word(N (&px)[32], uint32_t mw, N v, N
     }
 }
 
+constexpr int APPLY_TILES = 4;  // consecutive tiles of one tile row handled by one CTA
+
 template <typename N, int FN, int TILE_R, int MODE, bool BGNAN>
 __global__ void __launch_bounds__(TILE_R * 4, 4)
 tile_apply_kernel(KParams P, TileParams T, const uint32_t* __restrict__ tile_start,
@@ -509,10 +520,11 @@ tile_apply_kernel(KParams P, TileParams T, const uint32_t* __restrict__ tile_sta
     const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
     const N bg = value_from_bits<N>(bg_bits);
 
-    // grid = (tile columns, tile rows x bands), or 1-D when that does not fit the grid limits
-    uint32_t tcol, trow, band;
+    // grid = (groups of APPLY_TILES tile columns, tile rows x bands), or 1-D when that does not fit the grid limits
+    const uint32_t groups = (T.n_tc + APPLY_TILES - 1) / APPLY_TILES;
+    uint32_t tgrp, trow, band;
     if (gridDim.y > 1 || T.n_tr * P.n_bands == 1) {
-        tcol = blockIdx.x;
+        tgrp = blockIdx.x;
         trow = blockIdx.y;
         band = 0;
         if (P.n_bands > 1) {
@@ -521,40 +533,47 @@ tile_apply_kernel(KParams P, TileParams T, const uint32_t* __restrict__ tile_sta
         }
     } else {
         const uint32_t tt = blockIdx.x;
-        tcol = tt % T.n_tc;
-        trow = (tt / T.n_tc) % T.n_tr;
-        band = tt / (T.n_tc * T.n_tr);
+        tgrp = tt % groups;
+        trow = (tt / groups) % T.n_tr;
+        band = tt / (groups * T.n_tr);
     }
-    const uint32_t t = (band * T.n_tr + trow) * T.n_tc + tcol;
+    const uint32_t tcol0 = tgrp * APPLY_TILES, n_here = min((uint32_t)APPLY_TILES, T.n_tc - tcol0);
+    const uint32_t t0 = (band * T.n_tr + trow) * T.n_tc + tcol0;
     const uint32_t r0 = P.win_r0 + trow * TILE_R + warp * 8;
     if (r0 >= P.win_r1) return;
-    const uint32_t c0 = tcol * TILE_C;
 
-    N px[32];  // pixel b = (row r0 + (lane >> 2), column c0 + 32 * (lane & 3) + b)
-    uint32_t touched = 0;
     N ident;
     if (MODE == 1) {  // -0.0: the additive identity of IEEE addition
         const uint64_t neg0 = sizeof(N) == 8 ? 0x8000000000000000ull : 0x80000000ull;
         ident = value_from_bits<N>(neg0);
     } else {
-        ident = bg;   // MODE 2: bg == 0
+        ident = bg;  // MODE 0: the background; MODE 2: bg == 0
     }
-#pragma unroll
-    for (int b = 0; b < 32; b++) px[b] = ident;
 
-    // The tile's blocks [beg, end) are consecutive in memory, parts in burn order.  A ring of APPLY_DEPTH
-    // blocks is kept in flight: one coalesced 128-byte load plus one broadcast load of the part's value per block.
+    // A tile's blocks [beg, end) are consecutive in memory, parts in burn order, and so are the tiles of a tile
+    // row.  A ring of APPLY_DEPTH blocks is kept in flight (one coalesced 128-byte load plus one broadcast load of
+    // the part's value per block); when a tile's blocks are used up the ring is primed with the NEXT tile's
+    // first blocks before this tile is flushed, so only the first tile of a CTA waits for its first loads.
     constexpr int APPLY_DEPTH = 4;
-    const uint32_t beg = tile_start[t], end = tile_start[t + 1];
     const uint32_t* my_masks = masks + warp * 32 + lane;
     uint32_t m[APPLY_DEPTH];
     N val[APPLY_DEPTH];  // the value occupies the low bytes of its 8-byte slot
+    uint32_t beg = tile_start[t0], end = tile_start[t0 + 1];
 #pragma unroll
     for (int u = 0; u < APPLY_DEPTH; u++) {
         const bool live = beg + u < end;
         m[u] = live ? my_masks[(size_t)(beg + u) * (TILE_R * 4)] : 0u;
         val[u] = live ? *reinterpret_cast<const N*>(value_sorted + beg + u) : bg;
     }
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    for (uint32_t ti = 0; ti < n_here; ti++) {
+    const uint32_t end_next = ti + 1 < n_here ? tile_start[t0 + ti + 2] : end;  // needed after this tile's blocks
+    const uint32_t c0 = (tcol0 + ti) * TILE_C;
+    N px[32];  // pixel b = (row r0 + (lane >> 2), column c0 + 32 * (lane & 3) + b)
+    uint32_t touched = 0;
+#pragma unroll
+    for (int b = 0; b < 32; b++) px[b] = ident;
+
     for (uint32_t j0 = beg; j0 < end; j0 += APPLY_DEPTH) {
 #pragma unroll
         for (int u = 0; u < APPLY_DEPTH; u++) {
@@ -576,6 +595,13 @@ tile_apply_kernel(KParams P, TileParams T, const uint32_t* __restrict__ tile_sta
             }
         }
     }
+    // the ring is drained: prime it with the next tile's first blocks, in flight during the flush below
+#pragma unroll
+    for (int u = 0; u < APPLY_DEPTH; u++) {
+        const bool live = end + u < end_next;
+        m[u] = live ? my_masks[(size_t)(end + u) * (TILE_R * 4)] : 0u;
+        val[u] = live ? *reinterpret_cast<const N*>(value_sorted + end + u) : bg;
+    }
     if (MODE == 1) {
 #pragma unroll
         for (int b = 0; b < 32; b++)
@@ -587,7 +613,6 @@ tile_apply_kernel(KParams P, TileParams T, const uint32_t* __restrict__ tile_sta
     // instruction touch 32 different 128-byte lines.  The warp transposes through shared memory instead (16-byte
     // chunks, segments padded by 16 bytes so that both directions are bank-conflict free) and writes whole rows
     // with 16-byte streaming stores, 512 contiguous bytes per instruction.
-    extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr uint32_t SEGB = 32 * sizeof(N) + 16, ROWB = 4 * SEGB;  // bytes of one 32-pixel segment / one row
     constexpr int K16 = 2 * sizeof(N);                                // 16-byte chunks per segment
     const uint32_t rows_here = min(8u, P.win_r1 - r0);
@@ -622,6 +647,10 @@ tile_apply_kernel(KParams P, TileParams T, const uint32_t* __restrict__ tile_sta
                 if (col + b < P.ncols) dst[b] = px[b];
         }
     }
+    __syncwarp();  // the staging rows are reused by the next tile
+    beg = end;
+    end = end_next;
+    }  // tiles of this CTA
 }
 
 }  // namespace rz
