@@ -869,7 +869,7 @@ static void rasterize_dense(rz_geoms* g, const rz_context* ctx, void* out, rz_st
                     // ---- inside masks of every (part, tile) pair ----------------------------------
                     if (timed) CUDA_TRY(cudaEventRecord(c.ev[EV_A], s));
                     if (n_rows) {
-                        const uint32_t grid = (n_rows + MASK_WARPS - 1) / MASK_WARPS;
+                        const uint32_t grid = (n_rows + MASK_WARPS * MASK_UNITS - 1) / (MASK_WARPS * MASK_UNITS);
                         if (T.tile_r == 64)
                             tile_mask_kernel<64><<<grid, MASK_WARPS * 32, 0, s>>>(
                                 P, T, c.tile_pairs.as<uint64_t>(), n_rows, c.tile_pt.as<PartTile>(), dg->part_vbeg,

@@ -35,6 +35,7 @@ constexpr uint32_t TILE_C = 128;           // columns per tile = 4 mask words pe
 constexpr uint32_t MASK_MAX_WORDS = 16;    // tile_mask: widest toggle-mask chunk kept in shared memory (512 columns)
 constexpr uint32_t MASK_SMEM_WORDS = 1280; // tile_mask: toggle-mask words per warp (rows x (chunk words + 1 pad))
 constexpr int MASK_WARPS = 4;
+constexpr uint32_t MASK_UNITS = 4;  // consecutive mask units built by one warp
 constexpr uint32_t VROW_RING_END = 0x80000000u;  // vertex tag: "last vertex of its ring"
 
 struct TileParams {
@@ -318,12 +319,25 @@ tile_mask_kernel(KParams P, TileParams T, const uint64_t* __restrict__ units, ui
     __shared__ uint32_t s_mask[MASK_WARPS][MASK_SMEM_WORDS];
     __shared__ MaskEdge s_edge[MASK_WARPS][32];  // the batch's active edges, compacted
     const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
-    const uint32_t unit = blockIdx.x * MASK_WARPS + warp;
-    if (unit >= n_units) return;
+    // A warp builds MASK_UNITS consecutive units (units are in part order, so are their vertices).  While it works
+    // on one it asks the L2 for the next one's part record and vertex range: a unit lives for ~20 us and would
+    // otherwise start with three dependent global loads.
+    const uint32_t unit0 = (blockIdx.x * MASK_WARPS + warp) * MASK_UNITS;
+    for (uint32_t unit = unit0; unit < min(unit0 + MASK_UNITS, n_units); unit++) {
     const uint64_t un = units[unit];
     const uint32_t part = (uint32_t)un, k_tr = (uint32_t)(un >> 32) & 63u, tr = (uint32_t)(un >> 38);
+    if (unit + 1 < n_units && lane < 3) {
+        const uint32_t pn = (uint32_t)units[unit + 1];
+        const void* a = lane == 0 ? (const void*)(pt + pn) : lane == 1 ? (const void*)(vbeg + pn) : (const void*)(vend + pn);
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
+    }
     const PartTile q = pt[part];
     const uint32_t vb = vbeg[part], ve = vend[part];
+    if (lane < 12) {  // the vertices after this part's are (most often) the next unit's first batch
+        const uint32_t k = lane >> 2;  // 0: x, 1: y, 2: tag; four 128-byte lines each (tags: two)
+        const char* base = k == 0 ? (const char*)(wx + ve) : k == 1 ? (const char*)(wy + ve) : (const char*)(tag + ve);
+        if (k < 2 || (lane & 3u) < 2) asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (lane & 3u) * 128));
+    }
     const uint32_t t0 = P.win_r0 + tr * TILE_R;  // first row of the unit's tile rows
     const uint32_t row_start = max(q.r_lo, t0), row_end = min(q.r_hi, t0 + k_tr * TILE_R);
     const uint32_t n_rows = row_end - row_start;
@@ -475,6 +489,7 @@ tile_mask_kernel(KParams P, TileParams T, const uint64_t* __restrict__ units, ui
         }
         __syncwarp();
     }
+    }  // units of this warp
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -510,7 +525,7 @@ __device__ __forceinline__ void apply_part_word(N (&px)[32], uint32_t mw, N v, N
     }
 }
 
-constexpr int APPLY_TILES = 4;  // consecutive tiles of one tile row handled by one CTA
+constexpr int APPLY_TILES = 8;  // consecutive tiles of one tile row handled by one CTA
 
 template <typename N, int FN, int TILE_R, int MODE, bool BGNAN>
 __global__ void __launch_bounds__(TILE_R * 4, 4)
