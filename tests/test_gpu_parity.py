@@ -353,3 +353,47 @@ def test_all_touched_pixel_cache_box_aliasing():
     dense, _ = core.rasterize_dense(g, ri, "sum", "int32", np.array(burn, np.int32), None, None, 1, 0, True)
     rep = core.sparse_build_array(ri, "sum", 0, sp["counts"], sp["rows"], sp["cols"], sp["data"])
     assert np.array_equal(rep, dense)
+
+
+def _same_bits(exp, got):
+    """Bit-for-bit, signed zeros included; NaNs must coincide (the payload of a GENERATED NaN, inf - inf, is
+    platform defined: x86 and the GPU differ there)."""
+    assert exp.shape == got.shape and exp.dtype == got.dtype
+    if exp.dtype.kind != "f":
+        return bool(np.array_equal(exp, got))
+    u = {4: np.uint32, 8: np.uint64}[exp.dtype.itemsize]
+    nan_e, nan_g = np.isnan(exp), np.isnan(got)
+    return bool(np.array_equal(nan_e, nan_g) and np.array_equal(exp.view(u)[~nan_e], got.view(u)[~nan_g]))
+
+
+def test_tile_engine_apply_modes():
+    """tile_apply evaluates `sum` / `count` additively when that is provably the reference's rule (float dtype,
+    NaN background, all values finite; integer dtype, background 0) and falls back to the generic rule otherwise.
+    Overlapping polygons, values chosen to hit every branch: signed zeros, sums that cancel to 0, NaN and
+    infinite values (inf + -inf makes a NaN that the NEXT write must treat as untouched), integer wrap-around."""
+    from rusterize_b200 import _lib
+
+    x, y, off = synth.star_polygons(21, 1500, 8, 40, 70.0, 700, 500)
+    n = len(off) - 1
+    rng = np.random.default_rng(5)
+    og = oracle.Geoms.from_rings(x, y, off)
+    kw = dict(shape=(500, 700), extent=(0, 0, 700, 500))
+    ori, ri = oracle.raster_info(None, **kw), core.raster_info(None, **kw)
+    g = core.Geoms.from_polygons(x, y, off)
+    finite = rng.choice(np.array([-0.0, 0.0, 1.5, -1.5, 3.25, 1e30, -1e30, 2.0**-140], np.float64), n)
+    wild = finite.copy()
+    wild[rng.random(n) < 0.08] = np.nan
+    wild[rng.random(n) < 0.08] = np.inf
+    wild[rng.random(n) < 0.08] = -np.inf
+    cases = [("sum", "float32", finite, np.nan), ("sum", "float64", finite, np.nan), ("count", "float32", finite, np.nan),
+             ("sum", "float32", wild, np.nan), ("sum", "float64", wild, np.nan), ("count", "float64", wild, np.nan),
+             ("sum", "float32", finite, 0.0), ("sum", "float32", finite, 1.5), ("count", "float32", finite, 1.0),
+             ("sum", "int32", rng.integers(-3, 4, n), 0), ("sum", "uint8", rng.integers(0, 256, n), 0),
+             ("count", "uint8", 1, 0), ("sum", "int16", rng.integers(-3, 4, n), 2), ("count", "int64", 1, 3),
+             ("sum", "int64", rng.integers(-2**62, 2**62, n), 0)]
+    for fun, dtype, vals, bg in cases:
+        v = np.asarray(vals).astype(dtype) if np.ndim(vals) else vals
+        exp, _ = oracle.rasterize_dense(og, ori, fun, dtype, v, background=bg)
+        got, st = core.rasterize_dense(g, ri, fun, dtype, v, background=bg, flags=_lib.FLAG_FORCE_TILE_ENGINE)
+        assert st["engine"] == 1
+        assert _same_bits(exp, got), (fun, dtype, bg)
