@@ -46,6 +46,12 @@ template <typename T> struct HugeAlloc {
         return static_cast<T*>(p);
     }
     void deallocate(T* p, size_t) { std::free(p); }
+    // resize() default-initialises (no zero fill): the pools are always written right after they grow, and a
+    // serial zero fill of gigabytes is exactly the first-touch cost the parallel ingestion avoids
+    template <class U> void construct(U* p) noexcept { ::new (static_cast<void*>(p)) U; }
+    template <class U, class... Args> void construct(U* p, Args&&... args) {
+        ::new (static_cast<void*>(p)) U(std::forward<Args>(args)...);
+    }
     template <class U> bool operator==(const HugeAlloc<U>&) const { return true; }
     template <class U> bool operator!=(const HugeAlloc<U>&) const { return false; }
 };

@@ -23,6 +23,7 @@ namespace rz {
 
 struct KParams {
     double xmin, ymax, xres, yres;  // world -> pixel
+    double inv_xres, inv_yres;      // 1/res when res is a power of two (then d * inv == d / res bit for bit), else 0
     double nrows_f, ncols_f;
     uint32_t nrows, ncols;          // full raster
     uint32_t win_r0, win_r1;        // rows of this window (absolute)
@@ -54,8 +55,17 @@ struct Counters {
 // ---------------------------------------------------------------------------------------------
 // small helpers
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ double px_x(const KParams& P, double X) { return __ddiv_rn(__dsub_rn(X, P.xmin), P.xres); }
-__device__ __forceinline__ double px_y(const KParams& P, double Y) { return __ddiv_rn(__dsub_rn(P.ymax, Y), P.yres); }
+// (X - xmin) / xres, (ymax - Y) / yres (edges.rs:81-82, 94-97).  Dividing by a power of two is an exact scaling,
+// so is multiplying by its reciprocal: both give the correctly rounded value of the same real number, and the
+// 14-instruction f64 divide becomes one multiply for resolutions such as 1, 0.5 or 0.25 (warp-uniform branch).
+__device__ __forceinline__ double px_x(const KParams& P, double X) {
+    const double d = __dsub_rn(X, P.xmin);
+    return P.inv_xres != 0.0 ? __dmul_rn(d, P.inv_xres) : __ddiv_rn(d, P.xres);
+}
+__device__ __forceinline__ double px_y(const KParams& P, double Y) {
+    const double d = __dsub_rn(P.ymax, Y);
+    return P.inv_yres != 0.0 ? __dmul_rn(d, P.inv_yres) : __ddiv_rn(d, P.yres);
+}
 
 // Rust `f64 as usize` followed by min(., lim): NaN / negatives -> 0, saturating.
 __device__ __forceinline__ uint32_t sat_u32(double v, uint32_t lim) {

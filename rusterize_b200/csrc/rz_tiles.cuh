@@ -375,15 +375,15 @@ tile_mask_kernel(KParams P, TileParams T, const uint64_t* __restrict__ units, ui
                 yw_n = wy[i0 + 31 + lane];
                 tg_n = tag[i0 + 31 + lane];
             }
-            const double y0 = px_y(P, yw);
+            const double y0 = px_y(P, yw), x0 = px_x(P, xw);  // one transform per vertex, shared by its two edges
             const uint32_t row0 = vertex_row(P, y0);
             const double y1 = __shfl_down_sync(0xffffffffu, y0, 1);
             const uint32_t row1 = __shfl_down_sync(0xffffffffu, row0, 1);
-            const double xw1 = __shfl_down_sync(0xffffffffu, xw, 1);
+            const double x1 = __shfl_down_sync(0xffffffffu, x0, 1);
             const uint32_t lo = max(min(row0, row1), row_start), hi = min(max(row0, row1), row_end);
             uint32_t cnt = (lane < 31 && i0 + lane + 1 < ve && !(tg & VROW_RING_END) && hi > lo) ? hi - lo : 0u;
             TileEdge e;
-            if (cnt && !tile_edge_slope(px_x(P, xw), y0, px_x(P, xw1), y1, e)) cnt = 0;
+            if (cnt && !tile_edge_slope(x0, y0, x1, y1, e)) cnt = 0;
             par0 ^= (cnt != 0 && lo == 0);  // a kept edge starting at row 0 has exactly one crossing on it
             const uint32_t act = __ballot_sync(0xffffffffu, cnt != 0);
             if (act == 0) continue;

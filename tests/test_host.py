@@ -133,3 +133,30 @@ def test_group_keys_matches_oracle():
     oband, onames = oracle.group_keys(keys)
     assert names == onames and np.array_equal(band, oband)
     assert names[:4] == ["", "0", "1", "10"]  # byte-lexicographic (rasterize.rs:199-205)
+
+
+def test_threaded_wkb_ingestion_equals_serial(monkeypatch):
+    """rz_geoms_from_wkb parses large inputs with several threads (contiguous ranges, appended in order): the
+    flattened form - pools, tags, parts table, bounds - must be identical to the serial walk, dropped geometries
+    (POINT EMPTY) and collections included."""
+    import synth
+    from oracle import wkt2wkb as W
+
+    geoms = synth.mixed_geometries(17, 900, 512, 512)
+    geoms[5] = W.wkt_to_wkb("POINT EMPTY")
+    geoms[450] = W.wkt_to_wkb("GEOMETRYCOLLECTION (POINT (1 2), LINESTRING (0 0, 3 3), POLYGON ((0 0, 4 0, 4 4, 0 0)))")
+    geoms[899] = W.wkt_to_wkb("POINT EMPTY")
+    forms = []
+    for threads in ("1", "2", "7"):
+        monkeypatch.setenv("RZ_PARSE_THREADS", threads)
+        g = core.Geoms.from_wkb(geoms)
+        kind, pg = g.parts()
+        forms.append((len(g), g.bounds(), kind, pg, [g.pool(k) for k in range(3)]))
+    for f in forms[1:]:
+        assert f[0] == forms[0][0] == 898 and f[1] == forms[0][1]
+        assert np.array_equal(f[2], forms[0][2]) and np.array_equal(f[3], forms[0][3])
+        for a, b in zip(f[4], forms[0][4]):
+            assert all(np.array_equal(u, v) for u, v in zip(a, b))
+    monkeypatch.setenv("RZ_PARSE_THREADS", "3")
+    with pytest.raises(RuntimeError, match="Cannot parse geometry"):
+        core.Geoms.from_wkb(geoms[:600] + [b"\x01\x03\x00\x00\x00\x01"] + geoms[600:])
