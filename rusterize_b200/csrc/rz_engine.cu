@@ -409,7 +409,8 @@ static void tile_launch(uint32_t, cudaStream_t s, KParams P, TileParams T, const
     // limits, else flattened
     const uint64_t gy = (uint64_t)T.n_tr * P.n_bands;
     const uint32_t groups = (T.n_tc + APPLY_TILES - 1) / APPLY_TILES;
-    const dim3 grid = gy <= 65535 ? dim3(groups, (unsigned)gy) : dim3((unsigned)(groups * gy));
+    static const bool force_1d = std::getenv("RZ_APPLY_1D") != nullptr;  // tests: exercise the flattened grid
+    const dim3 grid = (gy <= 65535 && !force_1d) ? dim3(groups, (unsigned)gy) : dim3((unsigned)(groups * gy));
     const size_t smem = (size_t)(TR / 8) * 8 * 4 * (32 * sizeof(N) + 16);  // flush staging: 8 padded rows per warp
     N bgv;
     std::memcpy(&bgv, &bg, sizeof(N));

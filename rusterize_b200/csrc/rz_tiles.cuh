@@ -5,23 +5,23 @@
 // raster it is far cheaper never to materialise crossings.  Parts are binned to tiles of 128 columns x
 // TILE_R rows and the scanline job is split into two embarrassingly parallel kernels:
 //
-//   vertex_transform   every ring vertex to pixel space, once per call (edges.rs:94-97).
-//   tile_bin (x2)      per part: the tile rows / tile columns its bounding box overlaps; emits the list
-//                      of (part, tile-row) pairs and the (tile, part) records (stably sorted by tile, so
-//                      every tile sees its parts in burn order).
-//   tile_mask          one WARP per (part, tile-row): takes the part's ring edges 32 at a time
-//                      (edges.rs:27-46, 90-110), computes their crossings with the tile-row's rows
-//                      (edges.rs:50-55, warp-flattened so all lanes stay busy) and XORs one bit per
-//                      crossing into a shared-memory toggle mask spanning the part's tile columns; a
-//                      prefix-XOR along each row turns it into the even-odd INSIDE mask (== sorting and
-//                      pairing the crossings, burners.rs:302-315), written to global memory as one
-//                      TILE_R x 128-bit block per (part, tile).
-//   tile_apply         one CTA per tile, tile pixels in shared memory (initialised to the background,
-//                      flushed once).  Each warp owns 8 rows and, with NO synchronisation with the other
-//                      warps, walks the tile's parts in burn order: one coalesced 128-byte load fetches
-//                      its 8 rows x 4 words of the part's inside mask, and the part's value is applied to
-//                      the masked pixels with the reference's pixel-function rule
-//                      (pixel_functions.rs:56-123), 32 consecutive pixels per step.
+//   tile_bin (x2)      per part: the tiles its bounding box overlaps; emits the mask units - (part, run of
+//                      tile rows) handled by one warp - and the (tile, block) records, stably sorted by tile so
+//                      every tile sees its parts in burn order; block_pos then gives every (part, tile) block
+//                      its position in tile order.
+//   tile_mask          one WARP per mask unit: reads the part's ring vertices from the world-coordinate pool,
+//                      31 edges at a time, transforms them (edges.rs:94-97), finds with integer row compares
+//                      the edges that cross the unit's rows (edges.rs:27-46, 90-110), computes their crossings
+//                      (edges.rs:50-55, warp-flattened so all lanes stay busy) and XORs one bit per crossing
+//                      into a shared-memory toggle mask spanning the part's tile columns; a prefix-XOR along
+//                      each row turns it into the even-odd INSIDE mask (== sorting and pairing the crossings,
+//                      burners.rs:302-315), written as one TILE_R x 128-bit block per (part, tile).
+//   tile_apply         one CTA per 8 tiles of a tile row, pixels in REGISTERS (initialised to the background,
+//                      flushed once).  Each warp owns 8 rows and, with no synchronisation with the other
+//                      warps, walks the tile's parts in burn order: one coalesced 128-byte load brings the
+//                      part's inside mask, lane = (row, 32-column word), and the lane applies the part's value
+//                      to its own 32 pixels with the reference's pixel-function rule
+//                      (pixel_functions.rs:56-123).
 //
 // Parts are applied strictly in burn order per pixel, so every pixel function stays bit-exact, and every
 // output byte is written to HBM once.

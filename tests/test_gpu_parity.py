@@ -397,3 +397,27 @@ def test_tile_engine_apply_modes():
         got, st = core.rasterize_dense(g, ri, fun, dtype, v, background=bg, flags=_lib.FLAG_FORCE_TILE_ENGINE)
         assert st["engine"] == 1
         assert _same_bits(exp, got), (fun, dtype, bg)
+
+
+def test_windowed_host_output_with_bands():
+    """Row windows x `by` bands: every window copies one slab per band out of the staging buffer."""
+    import os
+
+    x, y, off = synth.star_polygons(13, 3000, 8, 32, 50.0, 1024, 900)
+    n = len(off) - 1
+    by = [str(i % 5) for i in range(n)]
+    band, names = core.group_keys(by)
+    vals = (np.arange(n) % 97 + 1).astype(np.int32)
+    kw = dict(shape=(900, 1024), extent=(0, 0, 1024, 900))
+    og = oracle.Geoms.from_rings(x, y, off)
+    exp, _ = oracle.rasterize_dense(og, oracle.raster_info(None, **kw), "max", "int32", vals, None, by, 0, threads=4)
+    g = core.Geoms.from_polygons(x, y, off)
+    ri = core.raster_info(None, **kw)
+    os.environ["RZ_WINDOW_BYTES"] = str(5 * 1024 * 4 * 64)  # windows of at most 64 rows x 5 bands
+    try:
+        for flags in (0, 8):  # tile engine / record pipeline
+            got, st = core.rasterize_dense(g, ri, "max", "int32", vals, None, band, len(names), 0, flags=flags)
+            assert st["n_windows"] >= 15, st["n_windows"]
+            assert np.array_equal(exp, got), flags
+    finally:
+        del os.environ["RZ_WINDOW_BYTES"]
