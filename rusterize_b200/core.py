@@ -127,7 +127,7 @@ class Geoms:
 
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None
-        if h and _lib._lib is not None:
+        if h and _lib is not None and _lib._lib is not None:  # (module globals are gone at interpreter exit)
             _lib._lib.rz_geoms_free(h)
 
 

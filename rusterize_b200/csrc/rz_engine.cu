@@ -812,11 +812,17 @@ static void rasterize_dense(rz_geoms* g, const rz_context* ctx, void* out, rz_st
                 TileCounters h_tc;
                 CUDA_TRY(cudaMemcpyAsync(&h_tc, d_tc, sizeof h_tc, cudaMemcpyDeviceToHost, s));
                 CUDA_TRY(cudaStreamSynchronize(s));
-                // cost model: tile_mask touches every ring vertex of a part once per overlapped tile-row
-                // (and per 384-column chunk); the inside masks take 16 bytes per tile row and (part,tile) pair
+                // Cost model.  tile_mask visits every ring vertex of a part once per mask unit and 512-column chunk
+                // (a few instructions per visit) and then pays per crossing; the record pipeline pays ~10 passes
+                // over HBM per crossing, several times more.  The tile engine therefore wins unless the vertex
+                // visits dwarf the crossings: accepted when the visits are a small multiple of the vertex count
+                // (small parts: config 4) or of the crossings' lower bound, two per part row (few vertices but
+                // large extents: config 3 runs 4-5x faster here than through records).  A huge, vertex-rich part
+                // cut into hundreds of units fails both tests and goes to the record pipeline.
                 const uint64_t mask_bytes = h_tc.pairs * T.tile_r * 16ull;
                 const bool wanted = (ctx->flags & RZ_FLAG_FORCE_TILE_ENGINE) ||
-                                    h_tc.edge_visits <= 6ull * nv_poly + (1ull << 20);
+                                    h_tc.edge_visits <= 6ull * nv_poly + (1ull << 20) ||
+                                    h_tc.edge_visits <= 6ull * h_tc.cross_lb;
                 if (wanted && h_tc.pairs < (1ull << 31) && h_tc.row_pairs < (1ull << 31) && mask_bytes <= (24ull << 30)) {
                     const uint32_t n_rec = (uint32_t)h_tc.pairs, n_rows = (uint32_t)h_tc.row_pairs;
                     device_scan<OpAdd>(InU32{c.tile_cnt.as<uint32_t>()}, n_parts,

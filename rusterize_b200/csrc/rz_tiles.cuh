@@ -51,6 +51,8 @@ struct TileCounters {
     unsigned long long pairs;        // (part, tile) pairs
     unsigned long long row_pairs;    // mask units: (part, run of tile rows) handled by one tile_mask warp
     unsigned long long edge_visits;  // sum over parts of units x column chunks x ring vertices
+    unsigned long long cross_lb;     // lower bound of the crossing count: 2 per part row (a closed ring crosses a
+                                     // row's centre line an even number of times, at least twice)
     unsigned int nonfinite, pad;     // some part burns a NaN / infinite value (float dtypes)
 };
 
@@ -170,17 +172,20 @@ __global__ void tile_bin_kernel(KParams P, TileParams T, const PartInfo* __restr
         }
         const uint32_t chunks = (ntc * 4 + MASK_MAX_WORDS - 1) / MASK_MAX_WORDS;
         unsigned long long pairs = (unsigned long long)ntr * ntc, rows = n_units,
-                           visits = (unsigned long long)n_units * chunks * (p < P.n_parts ? vend[p] - vbeg[p] : 0u);
+                           visits = (unsigned long long)n_units * chunks * (p < P.n_parts ? vend[p] - vbeg[p] : 0u),
+                           cross = ntr ? 2ull * (r_hi - r_lo) : 0ull;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             pairs += __shfl_down_sync(0xffffffffu, pairs, o);
             rows += __shfl_down_sync(0xffffffffu, rows, o);
             visits += __shfl_down_sync(0xffffffffu, visits, o);
+            cross += __shfl_down_sync(0xffffffffu, cross, o);
         }
         if (lane_id() == 0 && pairs) {
             atomicAdd(&tc->pairs, pairs);
             atomicAdd(&tc->row_pairs, rows);
             atomicAdd(&tc->edge_visits, visits);
+            atomicAdd(&tc->cross_lb, cross);
         }
     }
 }
