@@ -240,19 +240,32 @@ def rasterize_sparse(geoms: Geoms, ri: RasterInfo, fun="last", dtype="float64", 
     err = errbuf()
     rc = L.rz_rasterize_sparse(geoms._h, C.byref(ctx), C.byref(h), C.byref(st), err, len(err))
     raise_for(rc, err)
-    try:
-        n, nb = L.rz_sparse_len(h), L.rz_sparse_n_bands(h)
+    owner = _SparseOwner(h)  # the arrays below are views of the library's buffers: freed with the last of them
+    n, nb = L.rz_sparse_len(h), L.rz_sparse_n_bands(h)
 
-        def view(p, count, t):
-            if count == 0:
-                return np.empty(0, t)
-            return np.frombuffer((C.c_char * (count * np.dtype(t).itemsize)).from_address(p), dtype=t).copy()
+    def view(p, count, t):
+        if count == 0:
+            return np.empty(0, t)
+        buf = (C.c_char * (count * np.dtype(t).itemsize)).from_address(p)
+        buf._owner = owner
+        return np.frombuffer(buf, dtype=t)
 
-        return dict(rows=view(L.rz_sparse_rows(h), n, np.uint64), cols=view(L.rz_sparse_cols(h), n, np.uint64),
-                    data=view(L.rz_sparse_data(h), n, dt), counts=view(L.rz_sparse_counts(h), nb, np.uint64),
-                    stats=st.as_dict())
-    finally:
-        L.rz_sparse_free(h)
+    return dict(rows=view(L.rz_sparse_rows(h), n, np.uint64), cols=view(L.rz_sparse_cols(h), n, np.uint64),
+                data=view(L.rz_sparse_data(h), n, dt),
+                counts=view(L.rz_sparse_counts(h), nb, np.uint64).copy(), stats=st.as_dict())
+
+
+class _SparseOwner:
+    """Keeps an rz_sparse handle alive for the numpy views of its buffers (zero-copy hand-over, like the
+    reference's into_pyarray, python/src/encoding/pyarray.rs:27-28)."""
+
+    def __init__(self, handle):
+        self._h = handle
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h and _lib is not None and _lib._lib is not None:
+            _lib._lib.rz_sparse_free(h)
 
 
 def sparse_build_array(ri: RasterInfo, fun, background, counts, rows, cols, data, device=0):

@@ -11,6 +11,7 @@
 #include <cstring>
 #include <memory>
 #include <string>
+#include <sys/mman.h>
 #include <thread>
 #include <type_traits>
 #include <vector>
@@ -1133,9 +1134,102 @@ static void rasterize_dense(rz_geoms* g, const rz_context* ctx, void* out, rz_st
 // ------------------------------------------------------------------------------------------------
 }  // namespace rz
 
+// Host memory for sparse results.  Handing out gigabytes of FRESH memory per call costs far more than the whole
+// device pipeline (measured for 125 M triplets = 2.5 GB: 3.8 ms of kernels against 700 ms to fault the pages in
+// and page-lock them for the copy).  Blocks are therefore huge-page backed, faulted in by several threads,
+// page-locked once, and recycled through a pool when an rz_sparse is freed: steady-state calls copy straight
+// into resident, pinned memory at the PCIe rate.  RZ_HOST_POOL_BYTES caps what the pool keeps (default 8 GiB).
+namespace rz {
+struct HostBlock {
+    void* p = nullptr;
+    size_t cap = 0;
+    bool pinned = false;
+};
+class HostPool {
+  public:
+    HostBlock get(size_t bytes) {
+        if (bytes == 0) return HostBlock{};
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            size_t best = free_.size();
+            for (size_t i = 0; i < free_.size(); i++)
+                if (free_[i].cap >= bytes && free_[i].cap <= 2 * bytes + (1u << 20) &&
+                    (best == free_.size() || free_[i].cap < free_[best].cap))
+                    best = i;
+            if (best != free_.size()) {
+                HostBlock b = free_[best];
+                free_.erase(free_.begin() + best);
+                pooled_ -= b.cap;
+                return b;
+            }
+        }
+        HostBlock b;
+        const size_t huge = (size_t)2 << 20;
+        b.cap = bytes >= huge ? (bytes + huge - 1) & ~(huge - 1) : bytes;
+        if (bytes >= huge) {
+            if (posix_memalign(&b.p, huge, b.cap) != 0) throw std::bad_alloc();
+            madvise(b.p, b.cap, MADV_HUGEPAGE);
+            // first touch in parallel: the kernel clears the pages on the faulting thread
+            const unsigned nt = std::min<unsigned>({std::max(1u, std::thread::hardware_concurrency()), 8u,
+                                                   (unsigned)(b.cap >> 26) + 1u});
+            std::vector<std::thread> th;
+            for (unsigned t = 0; t < nt; t++)
+                th.emplace_back([&, t]() {
+                    char* q = (char*)b.p;
+                    const size_t lo = b.cap / nt * t, hi = t + 1 == nt ? b.cap : b.cap / nt * (t + 1);
+                    for (size_t o = lo; o < hi; o += 4096) q[o] = 0;
+                });
+            for (auto& x : th) x.join();
+            if (cudaHostRegister(b.p, b.cap, cudaHostRegisterDefault) == cudaSuccess) b.pinned = true;
+            else (void)cudaGetLastError();
+        } else {
+            b.p = std::malloc(b.cap);
+            if (!b.p) throw std::bad_alloc();
+        }
+        return b;
+    }
+    void put(HostBlock b) {
+        if (!b.p) return;
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            if (b.cap >= ((size_t)2 << 20) && pooled_ + b.cap <= limit()) {
+                free_.push_back(b);
+                pooled_ += b.cap;
+                return;
+            }
+        }
+        release(b);
+    }
+    ~HostPool() {
+        for (auto& b : free_) release(b);
+    }
+
+  private:
+    static void release(HostBlock& b) {
+        if (b.pinned && cudaHostUnregister(b.p) != cudaSuccess) (void)cudaGetLastError();
+        std::free(b.p);
+        b.p = nullptr;
+    }
+    static size_t limit() {
+        if (const char* e = std::getenv("RZ_HOST_POOL_BYTES")) return (size_t)std::strtoull(e, nullptr, 10);
+        return (size_t)8 << 30;
+    }
+    std::mutex mu_;
+    std::vector<HostBlock> free_;
+    size_t pooled_ = 0;
+};
+static HostPool g_host_pool;
+}  // namespace rz
+
 struct rz_sparse {
-    std::vector<uint64_t> rows, cols, counts;
-    std::vector<uint8_t> data;
+    rz::HostBlock rows, cols, data;  // u64[len], u64[len], dtype[len]
+    uint64_t len = 0;
+    std::vector<uint64_t> counts;
+    ~rz_sparse() {
+        rz::g_host_pool.put(rows);
+        rz::g_host_pool.put(cols);
+        rz::g_host_pool.put(data);
+    }
 };
 
 namespace rz {
@@ -1219,7 +1313,7 @@ static void rasterize_sparse(rz_geoms* g, const rz_context* ctx, rz_sparse* out,
     cudaStream_t s = ctx->stream ? (cudaStream_t)ctx->stream : c.stream;
     rz_stats S;
     std::memset(&S, 0, sizeof S);
-    enum { EV_START, EV_END };
+    enum { EV_START, EV_END, EV_SORTED, EV_COUNTED, EV_EXPANDED };  // stage marks (rz_stats: emit+sort, index, fill, d2h)
     CUDA_TRY(cudaEventRecord(c.ev[EV_START], s));
     size_t h2d = 0;
     DeviceGeoms* dg = geoms_on_device(g, c, s, (ctx->flags & RZ_FLAG_FORCE_H2D) != 0, &h2d);
@@ -1332,6 +1426,7 @@ static void rasterize_sparse(rz_geoms* g, const rz_context* ctx, rz_sparse* out,
             keys = ka;
         }
     }
+    CUDA_TRY(cudaEventRecord(c.ev[EV_SORTED], s));
     // ---- write counts of every unit -------------------------------------------------------------------
     unsigned long long poly_total = 0, line_total = 0, pt_total = 0, walk_total = 0;
     VisitSet vs;
@@ -1453,10 +1548,12 @@ static void rasterize_sparse(rz_geoms* g, const rz_context* ctx, rz_sparse* out,
         out->counts[b] = bt;
         total += bt;
     }
+    CUDA_TRY(cudaEventRecord(c.ev[EV_COUNTED], s));
     // ---- expand ------------------------------------------------------------------------------------
-    out->rows.resize(total);
-    out->cols.resize(total);
-    out->data.resize(total * isz);
+    out->len = total;
+    out->rows = g_host_pool.get(total * 8);
+    out->cols = g_host_pool.get(total * 8);
+    out->data = g_host_pool.get(total * isz);
     if (total) {
         c.sp_rows.ensure(total * 8);
         c.sp_cols.ensure(total * 8);
@@ -1478,14 +1575,21 @@ static void rasterize_sparse(rz_geoms* g, const rz_context* ctx, rz_sparse* out,
             default: sparse_expand<uint64_t>(s, P, L, dg, c, J, launches); break;
         }
         CUDA_TRY(cudaGetLastError());
-        CUDA_TRY(cudaMemcpyAsync(out->rows.data(), c.sp_rows.p, total * 8, cudaMemcpyDeviceToHost, s));
-        CUDA_TRY(cudaMemcpyAsync(out->cols.data(), c.sp_cols.p, total * 8, cudaMemcpyDeviceToHost, s));
-        CUDA_TRY(cudaMemcpyAsync(out->data.data(), c.sp_data.p, total * isz, cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(cudaEventRecord(c.ev[EV_EXPANDED], s));
+        CUDA_TRY(cudaMemcpyAsync(out->rows.p, c.sp_rows.p, total * 8, cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(cudaMemcpyAsync(out->cols.p, c.sp_cols.p, total * 8, cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(cudaMemcpyAsync(out->data.p, c.sp_data.p, total * isz, cudaMemcpyDeviceToHost, s));
         S.d2h_bytes = total * (16 + isz);
     }
     CUDA_TRY(cudaEventRecord(c.ev[EV_END], s));
     CUDA_TRY(cudaEventSynchronize(c.ev[EV_END]));
     CUDA_TRY(cudaEventElapsedTime(&S.total_ms, c.ev[EV_START], c.ev[EV_END]));
+    CUDA_TRY(cudaEventElapsedTime(&S.sort_ms, c.ev[EV_START], c.ev[EV_SORTED]));    // upload + crossings + sort
+    CUDA_TRY(cudaEventElapsedTime(&S.index_ms, c.ev[EV_SORTED], c.ev[EV_COUNTED])); // unit scans, bases
+    if (total) {
+        CUDA_TRY(cudaEventElapsedTime(&S.fill_ms, c.ev[EV_COUNTED], c.ev[EV_EXPANDED]));  // expand kernels
+        CUDA_TRY(cudaEventElapsedTime(&S.d2h_ms, c.ev[EV_EXPANDED], c.ev[EV_END]));       // pin + copy back
+    }
     S.out_bytes = total * (16 + isz);
     S.kernel_launches = launches;
     if (st) *st = S;
@@ -1921,11 +2025,11 @@ int rz_rasterize_sparse(rz_geoms* g, const rz_context* ctx, rz_sparse** out, rz_
     if (rc == RZ_OK) *out = sp.release();
     return rc;
 }
-uint64_t rz_sparse_len(const rz_sparse* s) { return s->rows.size(); }
+uint64_t rz_sparse_len(const rz_sparse* s) { return s->len; }
 uint64_t rz_sparse_n_bands(const rz_sparse* s) { return s->counts.size(); }
-const uint64_t* rz_sparse_rows(const rz_sparse* s) { return s->rows.data(); }
-const uint64_t* rz_sparse_cols(const rz_sparse* s) { return s->cols.data(); }
-const void* rz_sparse_data(const rz_sparse* s) { return s->data.data(); }
+const uint64_t* rz_sparse_rows(const rz_sparse* s) { return (const uint64_t*)s->rows.p; }
+const uint64_t* rz_sparse_cols(const rz_sparse* s) { return (const uint64_t*)s->cols.p; }
+const void* rz_sparse_data(const rz_sparse* s) { return s->data.p; }
 const uint64_t* rz_sparse_counts(const rz_sparse* s) { return s->counts.data(); }
 void rz_sparse_free(rz_sparse* s) { delete s; }
 int rz_sparse_build_array(const rz_context* ctx, uint64_t n_bands, const uint64_t* counts, const uint64_t* rows,

@@ -45,3 +45,21 @@ for extra in (0, _lib.FLAG_FORCE_TILE_ENGINE):
                                                     flags=_lib.FLAG_SYNC_STAGES | extra)[1], reps=3)
         print(f"c3 {fun}/int32 x32 bands: {ms:.2f} ms  engine={st['engine']} records={st['n_records']} "
               f"mask/count={st['count_ms']:.2f} sort={st['sort_ms']:.2f} fill={st['fill_ms']:.2f}")
+
+# config 5, one GPU's share of the 8-GPU plan: 1.25M of the 10M parcels (a contiguous geometry range) over the
+# full 131072 x 131072 extent, sparse encoding (triplets copied back to the host inside the call)
+size, n = 131072, 1_250_000
+x, y, off = synth.parcels(5, n, size, size)
+vals = synth.splitmix_u(5, n, 20).astype(np.float32)
+g5 = core.Geoms.from_polygons(x, y, off)
+g5.upload(0)
+ri5 = core.raster_info(None, shape=(size, size), extent=(0, 0, size, size))
+for rep in range(3):  # results are dropped between calls: from the second call on their host blocks are recycled
+    t = time.perf_counter()
+    sp = core.rasterize_sparse(g5, ri5, "sum", "float32", vals, background=np.nan)
+    dt = time.perf_counter() - t
+    st, ntrip = sp["stats"], len(sp["rows"])
+    del sp
+    print(f"c5 share, call {rep}: {n} parcels -> {ntrip} triplets in {1e3*dt:.1f} ms "
+          f"(device+D2H total_ms={st['total_ms']:.1f}: crossings+sort {st['sort_ms']:.1f}, scans {st['index_ms']:.1f}, "
+          f"expand {st['fill_ms']:.1f}, alloc+D2H {st['d2h_ms']:.1f}; d2h bytes={st['d2h_bytes']/1e9:.2f} GB, launches={st['kernel_launches']})")
