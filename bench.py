@@ -410,9 +410,9 @@ def run_b200(args):
         kernel = "fill_kernel<%s, %s>" % (w["dtype"], w["fun"])
         fill_bytes = 8.0 * s0["n_records"] + s0["out_bytes"]
     achieved = fill_bytes / (fill_ms / 1e3) / 1e9
-    traffic = None
+    traffic = None  # measured DRAM bytes of one launch (ncu): captured for the 1-GPU launch only
     tp = ROOT / "profiles" / "fill_traffic.json"
-    if tp.exists():
+    if tp.exists() and world == 1 and args.scale == 1.0:
         try:
             traffic = json.loads(tp.read_text()).get(args.workload)
         except Exception:

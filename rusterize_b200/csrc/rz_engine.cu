@@ -289,7 +289,7 @@ static DeviceGeoms* geoms_on_device(rz_geoms* g, DeviceCtx& c, cudaStream_t s, b
         }
         upload_vec(&d->x[k], g->pool[k].x, s, bytes, g->pinned_ranges);
         upload_vec(&d->y[k], g->pool[k].y, s, bytes, g->pinned_ranges);
-        upload_vec(&d->tag[k], g->pool[k].tag, s, bytes, g->pinned_ranges);
+        if (g->pool[k].size() && !d->tag[k]) CUDA_TRY(cudaMalloc((void**)&d->tag[k], (g->pool[k].size() + 1) * 4));
     }
     upload_vec(&d->part_kind, g->part_kind, s, bytes, g->pinned_ranges);
     std::vector<uint32_t> pg(g->part_geom.begin(), g->part_geom.end());
@@ -300,9 +300,32 @@ static DeviceGeoms* geoms_on_device(rz_geoms* g, DeviceCtx& c, cudaStream_t s, b
     upload_vec(&d->part_yhi, g->part_yhi, s, bytes, g->pinned_ranges);
     upload_vec(&d->part_vbeg, g->part_vbeg, s, bytes, g->pinned_ranges);
     upload_vec(&d->part_vend, g->part_vend, s, bytes, g->pinned_ranges);
-    CUDA_TRY(cudaStreamSynchronize(s));  // `pg` is a temporary
+    // tag[] is not sent (4 bytes per vertex, a fifth of the upload): it is rebuilt from the parts table and the
+    // sequence lists - tag = part id | TAG_SEQ_END on a sequence's last vertex | TAG_CLOSED on closed line strings
+    std::vector<void*> scratch;
+    if (const uint32_t n_parts = (uint32_t)g->part_kind.size()) {
+        for (int k = 0; k < 3; k++) {
+            if (!g->pool[k].size() || (k == 0 && defer_pool0)) continue;
+            tag_parts_kernel<<<(n_parts + 7) / 8, 256, 0, s>>>(n_parts, (uint8_t)k, d->part_kind, d->part_vbeg, d->part_vend,
+                                                             d->tag[k]);
+            const uint32_t n_seq = (uint32_t)g->pool[k].seq_end.size();
+            if (!n_seq) continue;
+            uint32_t* d_end = nullptr;
+            uint8_t* d_closed = nullptr;
+            CUDA_TRY(cudaMalloc((void**)&d_end, (size_t)n_seq * 4));
+            scratch.push_back(d_end);
+            CUDA_TRY(cudaMalloc((void**)&d_closed, n_seq));
+            scratch.push_back(d_closed);
+            CUDA_TRY(cudaMemcpyAsync(d_end, g->pool[k].seq_end.data(), (size_t)n_seq * 4, cudaMemcpyHostToDevice, s));
+            CUDA_TRY(cudaMemcpyAsync(d_closed, g->pool[k].seq_closed.data(), n_seq, cudaMemcpyHostToDevice, s));
+            bytes += (size_t)n_seq * 5;
+            tag_seqs_kernel<<<(n_seq + 255) / 256, 256, 0, s>>>(n_seq, d_end, d_closed, d->tag[k]);
+        }
+    }
+    CUDA_TRY(cudaStreamSynchronize(s));  // `pg`, the sequence lists on the device are temporaries
+    for (void* q : scratch) cudaFree(q);
     d->pending0 = defer_pool0;
-    d->bytes = bytes + (defer_pool0 ? g->pool[0].size() * 20 : 0);
+    d->bytes = bytes + (defer_pool0 ? g->pool[0].size() * 20 : 0);  // (a streamed upload copies the host tags)
     if (h2d_bytes) *h2d_bytes += bytes;
     if (fresh) g->dev[c.dev] = fresh.release();
     return d;
@@ -1816,8 +1839,12 @@ static void place_pools(rz_geoms* g, rz_geoms* c, const ChunkPlace& at) {
         rz::Pool().tag.swap(s.tag);
     }
 }
-// ... and its parts table / bounds (serial, in chunk order)
+// ... and its sequence lists, parts table and bounds (serial, in chunk order)
 static void place_parts(rz_geoms* g, rz_geoms* c, const ChunkPlace& at) {
+    for (int k = 0; k < 3; k++) {
+        for (uint32_t e : c->pool[k].seq_end) g->pool[k].seq_end.push_back((uint32_t)(e + at.pool_off[k]));
+        g->pool[k].seq_closed.insert(g->pool[k].seq_closed.end(), c->pool[k].seq_closed.begin(), c->pool[k].seq_closed.end());
+    }
     for (size_t p = 0; p < c->part_kind.size(); p++) {
         const int k = c->part_kind[p];
         g->part_kind.push_back(c->part_kind[p]);

@@ -19,7 +19,10 @@ namespace rz {
 // Flattener
 // ------------------------------------------------------------------------------------------------
 void Flattener::begin_geometry() {
-    for (int k = 0; k < 3; k++) mark_pool_[k] = g_->pool[k].size();
+    for (int k = 0; k < 3; k++) {
+        mark_pool_[k] = g_->pool[k].size();
+        mark_seq_[k] = g_->pool[k].seq_end.size();
+    }
     mark_parts_ = g_->part_kind.size();
     geom_has_bounds_ = false;
 }
@@ -30,6 +33,8 @@ void Flattener::end_geometry(bool keep) {
             g_->pool[k].x.resize(mark_pool_[k]);
             g_->pool[k].y.resize(mark_pool_[k]);
             g_->pool[k].tag.resize(mark_pool_[k]);
+            g_->pool[k].seq_end.resize(mark_seq_[k]);
+            g_->pool[k].seq_closed.resize(mark_seq_[k]);
         }
         g_->part_kind.resize(mark_parts_);
         g_->part_geom.resize(mark_parts_);
@@ -188,9 +193,12 @@ void Flattener::end_seq() {
         p.tag.push_back(part_);
         closed = true;
     }
-    if (kind_ == RZ_PART_LINE && closed)
+    const bool flag_closed = kind_ == RZ_PART_LINE && closed;
+    if (flag_closed)
         for (size_t i = seq_start_; i < p.size(); i++) p.tag[i] |= TAG_CLOSED;
     p.tag.back() |= TAG_SEQ_END;
+    p.seq_end.push_back((uint32_t)(p.size() - 1));
+    p.seq_closed.push_back(flag_closed ? 1 : 0);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -60,6 +60,11 @@ template <typename T> using HVec = std::vector<T, HugeAlloc<T>>;
 struct Pool {
     HVec<double> x, y;
     HVec<uint32_t> tag;
+    // the sequences (rings / line strings) of the pool in order: index of the last vertex, "line string is
+    // closed".  Together with the parts table they determine every tag, so the device rebuilds tag[] from them
+    // (5 bytes per sequence on the wire instead of 4 bytes per vertex).
+    std::vector<uint32_t> seq_end;
+    std::vector<uint8_t> seq_closed;
     size_t size() const { return x.size(); }
 };
 
@@ -126,7 +131,7 @@ class Flattener {
     bool geom_has_bounds_ = false;
     double gb_[4];
     // rollback marks for a dropped top-level geometry
-    size_t mark_pool_[3], mark_parts_;
+    size_t mark_pool_[3], mark_seq_[3], mark_parts_;
     bool ok_ = true;
     const char* err_ = "";
 };

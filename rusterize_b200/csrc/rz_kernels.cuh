@@ -121,6 +121,29 @@ __global__ void part_prepare_kernel(KParams P, const uint8_t* __restrict__ part_
 }
 
 // ---------------------------------------------------------------------------------------------
+// vertex tags rebuilt on the device (the host's tag[] is not uploaded)
+// ---------------------------------------------------------------------------------------------
+// tag = part id | 0x80000000 on the last vertex of a ring / line string | 0x40000000 on every vertex of a closed
+// line string (rz::Flattener::end_seq).  One warp per part writes the part id over the part's vertex range...
+__global__ void tag_parts_kernel(uint32_t n_parts, uint8_t kind, const uint8_t* __restrict__ part_kind,
+                                 const uint32_t* __restrict__ vbeg, const uint32_t* __restrict__ vend,
+                                 uint32_t* __restrict__ tag) {
+    const uint32_t p = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (p >= n_parts || part_kind[p] != kind) return;
+    for (uint32_t i = vbeg[p] + lane_id(); i < vend[p]; i += 32) tag[i] = p;
+}
+// ... then one thread per sequence sets the flags (sequences are contiguous in their pool, in order)
+__global__ void tag_seqs_kernel(uint32_t n_seq, const uint32_t* __restrict__ seq_end, const uint8_t* __restrict__ closed,
+                                uint32_t* __restrict__ tag) {
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_seq) return;
+    const uint32_t e = seq_end[s];
+    if (closed[s])
+        for (uint32_t i = s ? seq_end[s - 1] + 1 : 0u; i <= e; i++) tag[i] |= 0x40000000u;
+    tag[e] |= 0x80000000u;
+}
+
+// ---------------------------------------------------------------------------------------------
 // polygon edge setup — rust/src/geo/edges.rs:27-55, 90-110; burners.rs:279-315
 // ---------------------------------------------------------------------------------------------
 struct PolyEdgeRec {
