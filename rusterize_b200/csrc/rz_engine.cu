@@ -116,11 +116,12 @@ struct DeviceCtx {
     DevBuf keys_a, keys_b, hist, digit_total, task_start, part_info, field, valid, band, last_kept, counters, win_out,
         block_total, vs_keys, vs_first, sp_raw, tile_cnt, tile_cnt2, tile_off, tile_off2, tile_ctr,
         tile_pt, tile_pairs, tile_masks, tile_val, tile_pos, tile_val2, sp_a, sp_b, sp_c, sp_d, sp_e, sp_f, sp_g, sp_rows, sp_cols, sp_data, sp_partial, sp_w, sp_wraw, sp_ws, pull_bucket, pull_cnt, pull_order, cache_acc, cache_box;
-    Counters* h_counters = nullptr;  // pinned
+    Counters* h_counters = nullptr;  // pinned + mapped: written by readback_kernel
+    void* h_tile_ctr = nullptr;      // same, for TileCounters
     cudaEvent_t ev[16];
     cudaStream_t copy_stream = nullptr;  // device->host copies of finished row windows overlap the next window
     cudaStream_t copy_stream2 = nullptr; // second half of every window copy (two copy engines in flight)
-    cudaEvent_t ev_half = nullptr;
+    cudaEvent_t ev_half = nullptr, ev_first_fill = nullptr;
     cudaEvent_t ev_filled[2], ev_copied[2], ev_d2h[2];
     DevBuf win_out2;
 };
@@ -147,11 +148,13 @@ static DeviceCtx& device_ctx(int dev) {
         (void)cudaGetLastError();
         c->host_ptr_ok = 0;
     }
-    CUDA_TRY(cudaHostAlloc((void**)&c->h_counters, sizeof(Counters), cudaHostAllocDefault));
+    CUDA_TRY(cudaHostAlloc((void**)&c->h_counters, sizeof(Counters), cudaHostAllocMapped));
+    CUDA_TRY(cudaHostAlloc(&c->h_tile_ctr, 256, cudaHostAllocMapped));
     for (auto& e : c->ev) CUDA_TRY(cudaEventCreate(&e));
     CUDA_TRY(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaStreamCreateWithFlags(&c->copy_stream2, cudaStreamNonBlocking));
     CUDA_TRY(cudaEventCreateWithFlags(&c->ev_half, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreate(&c->ev_first_fill));
     for (int k = 0; k < 2; k++) {
         CUDA_TRY(cudaEventCreateWithFlags(&c->ev_filled[k], cudaEventDisableTiming));
         CUDA_TRY(cudaEventCreateWithFlags(&c->ev_copied[k], cudaEventDisableTiming));
@@ -753,6 +756,7 @@ static void rasterize_dense(rz_geoms* g, const rz_context* ctx, void* out, rz_st
     };
     auto stage_copy = [&](const Window& w, void* d_out) {  // window finished on `s`: copy it back asynchronously
         const uint32_t k = n_staged & 1, rows = w.r1 - w.r0;
+        if (n_staged == 0) CUDA_TRY(cudaEventRecord(c.ev_first_fill, s));
         CUDA_TRY(cudaEventRecord(c.ev_filled[k], s));
         CUDA_TRY(cudaStreamWaitEvent(c.copy_stream, c.ev_filled[k], 0));
         if (n_staged == 0) CUDA_TRY(cudaEventRecord(c.ev_d2h[0], c.copy_stream));
@@ -791,7 +795,8 @@ static void rasterize_dense(rz_geoms* g, const rz_context* ctx, void* out, rz_st
         touched_walk_kernel<<<(nv_poly + 255) / 256, 256, 0, s>>>(P, dg->x[0], dg->y[0], dg->tag[0], nv_poly, d_info, d_ctr,
                                                                  nullptr, 2, c.cache_acc.as<CacheAcc>());
         launches++;
-        CUDA_TRY(cudaMemcpyAsync(c.h_counters, d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, s));
+        readback_kernel<<<1, 32, 0, s>>>((const unsigned long long*)d_ctr, (volatile unsigned long long*)c.h_counters,
+                                         (uint32_t)(sizeof(Counters) / 8));
         CUDA_TRY(cudaStreamSynchronize(s));
         const unsigned long long walked = c.h_counters->cursor;
         if (walked) {  // some part has a dropped ring segment: remember its walked pixels
@@ -848,9 +853,12 @@ static void rasterize_dense(rz_geoms* g, const rz_context* ctx, void* out, rz_st
                     c.tile_cnt.as<uint32_t>(), c.tile_cnt2.as<uint32_t>(), nullptr, nullptr, nullptr, nullptr, nullptr,
                     nullptr, 0, d_tc, 0, ctx->dtype == RZ_F32 ? 4 : (ctx->dtype == RZ_F64 ? 8 : 0));
                 launches++;
-                TileCounters h_tc;
-                CUDA_TRY(cudaMemcpyAsync(&h_tc, d_tc, sizeof h_tc, cudaMemcpyDeviceToHost, s));
+                static_assert(sizeof(TileCounters) % 8 == 0 && sizeof(TileCounters) <= 256, "readback layout");
+                readback_kernel<<<1, 32, 0, s>>>((const unsigned long long*)d_tc, (volatile unsigned long long*)c.h_tile_ctr,
+                                                 (uint32_t)(sizeof(TileCounters) / 8));
                 CUDA_TRY(cudaStreamSynchronize(s));
+                TileCounters h_tc;
+                std::memcpy(&h_tc, c.h_tile_ctr, sizeof h_tc);
                 // Cost model.  tile_mask visits every ring vertex of a part once per mask unit and 512-column chunk
                 // (a few instructions per visit) and then pays per crossing; the record pipeline pays ~10 passes
                 // over HBM per crossing, several times more.  The tile engine therefore wins unless the vertex
@@ -1005,7 +1013,8 @@ static void rasterize_dense(rz_geoms* g, const rz_context* ctx, void* out, rz_st
                                                              nullptr, 0);
             launches++;
         }
-        CUDA_TRY(cudaMemcpyAsync(c.h_counters, d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, s));
+        readback_kernel<<<1, 32, 0, s>>>((const unsigned long long*)d_ctr, (volatile unsigned long long*)c.h_counters,
+                                         (uint32_t)(sizeof(Counters) / 8));
         if (timed) CUDA_TRY(cudaEventRecord(c.ev[EV_B], s));
         CUDA_TRY(cudaStreamSynchronize(s));
         lap(count_ms, EV_A, EV_B);
@@ -1148,7 +1157,17 @@ static void rasterize_dense(rz_geoms* g, const rz_context* ctx, void* out, rz_st
     CUDA_TRY(cudaEventRecord(c.ev[EV_END], s));
     if (!out_dev || timed) {
         CUDA_TRY(cudaEventSynchronize(c.ev[EV_END]));
-        if (!out_dev && n_staged) CUDA_TRY(cudaEventElapsedTime(&d2h_ms, c.ev_d2h[0], c.ev_d2h[1]));
+        if (!out_dev && n_staged) {
+            CUDA_TRY(cudaEventElapsedTime(&d2h_ms, c.ev_d2h[0], c.ev_d2h[1]));
+            if (std::getenv("RZ_VERBOSE")) {
+                float t0 = 0, t1 = 0, tf = 0;
+                CUDA_TRY(cudaEventElapsedTime(&tf, c.ev[EV_START], c.ev_first_fill));
+                std::fprintf(stderr, "librz_b200: first window rendered at %.2f ms\n", tf);
+                CUDA_TRY(cudaEventElapsedTime(&t0, c.ev[EV_START], c.ev_d2h[0]));
+                CUDA_TRY(cudaEventElapsedTime(&t1, c.ev_d2h[1], c.ev[EV_END]));
+                std::fprintf(stderr, "librz_b200: first window copy starts at %.2f ms, copies span %.2f ms, %.2f ms after the last\n", t0, d2h_ms, t1);
+            }
+        }
         CUDA_TRY(cudaEventElapsedTime(&S.total_ms, c.ev[EV_START], c.ev[EV_END]));
         CUDA_TRY(cudaEventElapsedTime(&S.h2d_ms, c.ev[EV_START], c.ev[EV_H2D]));
     }
@@ -1428,7 +1447,8 @@ static void rasterize_sparse(rz_geoms* g, const rz_context* ctx, rz_sparse* out,
                                                                c.block_total.as<uint32_t>(), d_ctr);
         scan_u32_kernel<<<1, 1024, 0, s>>>(c.block_total.as<uint32_t>(), poly_blocks);
         launches += 2;
-        CUDA_TRY(cudaMemcpyAsync(c.h_counters, d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, s));
+        readback_kernel<<<1, 32, 0, s>>>((const unsigned long long*)d_ctr, (volatile unsigned long long*)c.h_counters,
+                                         (uint32_t)(sizeof(Counters) / 8));
         CUDA_TRY(cudaStreamSynchronize(s));
         if (c.h_counters->records >= (1ull << 32) - 4096)
             throw Error{RZ_RUNTIME_ERROR, "Too many polygon crossings for one sparse call (limit 2^32)."};
@@ -1491,7 +1511,8 @@ static void rasterize_sparse(rz_geoms* g, const rz_context* ctx, rz_sparse* out,
             device_scan<OpAdd>(line_len, nv_line, OutPrefix64{c.sp_c.as<unsigned long long>()}, c.sp_partial, s, launches);
         }
         line_total = scan_total(c.sp_partial, nv_line, s);
-        CUDA_TRY(cudaMemcpyAsync(c.h_counters, d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, s));
+        readback_kernel<<<1, 32, 0, s>>>((const unsigned long long*)d_ctr, (volatile unsigned long long*)c.h_counters,
+                                         (uint32_t)(sizeof(Counters) / 8));
         CUDA_TRY(cudaStreamSynchronize(s));
         if (c.h_counters->bad_line)
             throw Error{RZ_RUNTIME_ERROR,

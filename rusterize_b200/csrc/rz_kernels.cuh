@@ -121,6 +121,17 @@ __global__ void part_prepare_kernel(KParams P, const uint8_t* __restrict__ part_
 }
 
 // ---------------------------------------------------------------------------------------------
+// small device -> host readbacks without a copy engine
+// ---------------------------------------------------------------------------------------------
+// Counters the host needs in the middle of a call (record counts, cost-model sums) are stored by this kernel
+// straight into page-locked, mapped host memory.  A cudaMemcpy of a few bytes would queue on the copy engine
+// behind the 2 GiB raster window that is on its way to the host, and stall the next window for its duration.
+__global__ void readback_kernel(const unsigned long long* __restrict__ src, volatile unsigned long long* dst, uint32_t n) {
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
+    __threadfence_system();
+}
+
+// ---------------------------------------------------------------------------------------------
 // vertex tags rebuilt on the device (the host's tag[] is not uploaded)
 // ---------------------------------------------------------------------------------------------
 // tag = part id | 0x80000000 on the last vertex of a ring / line string | 0x40000000 on every vertex of a closed
