@@ -138,7 +138,7 @@ class ClockSampler:
                 self._poll_once()
             except Exception:
                 break
-            time.sleep(0.004)
+            time.sleep(0.02)  # (a faster poll competes with the timed loop for the GIL)
 
     def _read(self):
         for line in self.proc.stdout:
@@ -355,9 +355,11 @@ def run_b200(args):
         step(flags=_lib.FLAG_FORCE_H2D | _lib.FLAG_SYNC_STAGES, out=h_np)  # warm
         barrier()
         t0 = time.perf_counter()
-        est = []
+        est, e_each = [], []
         for _ in range(n_e2e):
+            t_s = time.perf_counter()
             est.append(step(flags=_lib.FLAG_FORCE_H2D | _lib.FLAG_SYNC_STAGES, out=h_np))
+            e_each.append((time.perf_counter() - t_s) * 1e3)
         barrier()
         e_ms = (time.perf_counter() - t0) * 1e3 / n_e2e
         t = torch.tensor([e_ms], device="cuda", dtype=torch.float64)
@@ -373,6 +375,8 @@ def run_b200(args):
         e2e = {"value": rows * cols / (e_ms / 1e3) / 1e6, "unit": "Mpixel/s", "ms_per_step": e_ms,
                "h2d_bytes_per_step": int(hb[0].item()), "d2h_bytes_per_step": int(hb[1].item()), "steps": n_e2e,
                "rank0_h2d_ms": est[-1]["h2d_ms"], "rank0_d2h_ms": est[-1]["d2h_ms"],
+               "rank0_ms_each_step": [round(v, 1) for v in e_each],
+               "rank0_lib_ms_each_step": [[round(s_["h2d_ms"], 1), round(s_["d2h_ms"], 1), round(s_["total_ms"], 1)] for s_ in est],
                "host_equals_device_raster": same,
                "checksum": float(np.nansum(h_np[0, ::stride], dtype=np.float64))}
 

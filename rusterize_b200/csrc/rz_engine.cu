@@ -747,7 +747,7 @@ static void rasterize_dense(rz_geoms* g, const rz_context* ctx, void* out, rz_st
     // Host output: windows are rendered into two staging buffers in turn; the copy of a finished window runs
     // on the copy stream while the next window is computed (PCIe D2H is the longest phase of an end-to-end call).
     uint32_t n_staged = 0;
-    const int copy_streams = std::getenv("RZ_COPY_STREAMS") ? std::atoi(std::getenv("RZ_COPY_STREAMS")) : 2;  // measured on config 4: 365.5 vs 370.5 ms end to end
+    const int copy_streams = std::getenv("RZ_COPY_STREAMS") ? std::atoi(std::getenv("RZ_COPY_STREAMS")) : 1;  // 2: ~2 % faster when it works, but the NEXT call's upload then often runs at half speed (measured)
     auto stage_begin = [&](uint32_t rows) -> void* {  // staging buffer the window's kernels may write now
         DevBuf& b = (n_staged & 1) ? c.win_out2 : c.win_out;
         if (n_staged >= 2) CUDA_TRY(cudaStreamWaitEvent(s, c.ev_copied[n_staged & 1], 0));
