@@ -423,7 +423,9 @@ tile_mask_kernel(KParams P, TileParams T, const uint64_t* __restrict__ units, ui
                 b.y_top = me.y_top;
                 b.dxdy = me.dxdy;
                 const uint32_t row = me.lo + (kk - me.pre);
-                const uint32_t col = tile_edge_col(P, b, row);
+                // floor(x + 0.5) as usize (burners.rs:310-311); the clamp to ncols is implied by `col < c1` below
+                const double cy = __dadd_rn((double)row, 0.5);
+                const uint32_t col = __double2uint_rd(__dadd_rn(__dadd_rn(b.x_top, __dmul_rn(__dsub_rn(cy, b.y_top), b.dxdy)), 0.5));
                 const uint32_t rel = col <= c0 ? 0u : col - c0;  // left of the chunk: parity carry-in at bit 0
                 word = (row - row_start) * stride + (rel >> 5);
                 bit = 1u << (rel & 31);
