@@ -414,7 +414,7 @@ static unsigned long long scan_total(DevBuf& partial, uint32_t n, cudaStream_t s
 // tile-binned engine dispatch
 // ------------------------------------------------------------------------------------------------
 typedef void (*TileLaunch)(uint32_t, cudaStream_t, KParams, TileParams, const uint32_t*, const unsigned long long*,
-                           const uint32_t*, uint64_t, void*, bool);
+                           const uint32_t*, uint64_t, void*, bool, bool);
 
 template <typename N> struct NanBackground {
     static constexpr bool possible = false;
@@ -432,10 +432,11 @@ template <> struct NanBackground<double> {
 template <typename N, int FN>
 static void tile_launch(uint32_t, cudaStream_t s, KParams P, TileParams T, const uint32_t* tile_start,
                         const unsigned long long* value_sorted, const uint32_t* masks, uint64_t bg, void* out,
-                        bool values_finite) {
+                        bool values_finite, bool no_value_is_bg) {
     constexpr int TR = sizeof(N) <= 4 ? 64 : 32;
     constexpr bool is_float = std::is_floating_point<N>::value;
     constexpr bool additive = FN == RZ_SUM || FN == RZ_COUNT;
+    constexpr bool ordered = FN == RZ_FIRST || FN == RZ_MIN || FN == RZ_MAX;
     // one CTA per APPLY_TILES tiles of a tile row: (column groups, tile rows x bands) when that fits the grid
     // limits, else flattened
     const uint64_t gy = (uint64_t)T.n_tr * P.n_bands;
@@ -451,6 +452,9 @@ static void tile_launch(uint32_t, cudaStream_t s, KParams P, TileParams T, const
             P, T, tile_start, value_sorted, masks, bg, (N*)out);
     else if (additive && !is_float && bg == 0)            // MODE 2: plain masked add
         tile_apply_kernel<N, additive ? FN : RZ_SUM, TR, is_float ? 0 : 2, false><<<grid, TR * 4, smem, s>>>(
+            P, T, tile_start, value_sorted, masks, bg, (N*)out);
+    else if (ordered && ((is_float && bg_nan && values_finite) || (!is_float && no_value_is_bg)))  // MODE 3
+        tile_apply_kernel<N, ordered ? FN : RZ_FIRST, TR, 3, NanBackground<N>::possible><<<grid, TR * 4, smem, s>>>(
             P, T, tile_start, value_sorted, masks, bg, (N*)out);
     else if (bg_nan)  // float dtypes with a NaN background: one comparison less per pixel
         tile_apply_kernel<N, FN, TR, 0, NanBackground<N>::possible><<<grid, TR * 4, smem, s>>>(P, T, tile_start, value_sorted,
@@ -851,7 +855,8 @@ static void rasterize_dense(rz_geoms* g, const rz_context* ctx, void* out, rz_st
                 tile_bin_kernel<<<(n_parts + 255) / 256, 256, 0, s>>>(
                     P, T, d_info, dg->part_xlo, dg->part_xhi, dg->part_ylo, dg->part_yhi, dg->part_vbeg, dg->part_vend,
                     c.tile_cnt.as<uint32_t>(), c.tile_cnt2.as<uint32_t>(), nullptr, nullptr, nullptr, nullptr, nullptr,
-                    nullptr, 0, d_tc, 0, ctx->dtype == RZ_F32 ? 4 : (ctx->dtype == RZ_F64 ? 8 : 0));
+                    nullptr, 0, d_tc, 0, ctx->dtype == RZ_F32 ? 4 : (ctx->dtype == RZ_F64 ? 8 : 0), bg_bits,
+                    isz >= 8 ? ~0ull : ((1ull << (8 * isz)) - 1ull));
                 launches++;
                 static_assert(sizeof(TileCounters) % 8 == 0 && sizeof(TileCounters) <= 256, "readback layout");
                 readback_kernel<<<1, 32, 0, s>>>((const unsigned long long*)d_tc, (volatile unsigned long long*)c.h_tile_ctr,
@@ -888,7 +893,7 @@ static void rasterize_dense(rz_geoms* g, const rz_context* ctx, void* out, rz_st
                         P, T, d_info, dg->part_xlo, dg->part_xhi, dg->part_ylo, dg->part_yhi, dg->part_vbeg, dg->part_vend,
                         nullptr, nullptr, c.tile_off.as<unsigned long long>(), c.tile_off2.as<unsigned long long>(),
                         c.tile_pt.as<PartTile>(), c.tile_pairs.as<uint64_t>(), ka, c.tile_val.as<unsigned long long>(),
-                        block_bits, d_tc, 1, 0);
+                        block_bits, d_tc, 1, 0, 0ull, 0ull);
                     launches++;
                     if (timed) CUDA_TRY(cudaEventRecord(c.ev[EV_B], s));
                     lap(emit_ms, EV_A, EV_B);
@@ -963,7 +968,7 @@ static void rasterize_dense(rz_geoms* g, const rz_context* ctx, void* out, rz_st
                     T.vec_ok = ((uintptr_t)d_out % 16 == 0) && ((ri.ncols * isz) % 16 == 0);
                     tile_for(ctx->dtype, ctx->pixel_fn)(T.n_tiles, s, P, T, c.task_start.as<uint32_t>(),
                                                         c.tile_val2.as<unsigned long long>(),
-                                                        c.tile_masks.as<uint32_t>(), bg_bits, d_out, !h_tc.nonfinite);
+                                                        c.tile_masks.as<uint32_t>(), bg_bits, d_out, !h_tc.nonfinite, !h_tc.eq_bg);
                     launches++;
                     CUDA_TRY(cudaGetLastError());
                     if (timed) CUDA_TRY(cudaEventRecord(c.ev[EV_B], s));

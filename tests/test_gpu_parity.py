@@ -390,7 +390,15 @@ def test_tile_engine_apply_modes():
              ("sum", "float32", finite, 0.0), ("sum", "float32", finite, 1.5), ("count", "float32", finite, 1.0),
              ("sum", "int32", rng.integers(-3, 4, n), 0), ("sum", "uint8", rng.integers(0, 256, n), 0),
              ("count", "uint8", 1, 0), ("sum", "int16", rng.integers(-3, 4, n), 2), ("count", "int64", 1, 3),
-             ("sum", "int64", rng.integers(-2**62, 2**62, n), 0)]
+             ("sum", "int64", rng.integers(-2**62, 2**62, n), 0),
+             # first / min / max: touched-mask mode when no value can equal the background, generic rule otherwise
+             ("min", "int32", rng.integers(1, 50, n), 0), ("max", "int32", rng.integers(-50, 0, n), 0),
+             ("first", "int16", rng.integers(1, 50, n), 0), ("min", "uint8", rng.integers(0, 5, n), 0),
+             ("max", "int64", rng.integers(-3, 4, n), 2), ("first", "uint32", rng.integers(0, 3, n), 1),
+             ("min", "float32", finite, np.nan), ("max", "float64", finite, np.nan), ("first", "float32", finite, np.nan),
+             ("min", "float32", wild, np.nan), ("max", "float32", wild, np.nan), ("first", "float64", wild, np.nan),
+             ("min", "float64", finite, 1.5), ("max", "float32", finite, 0.0), ("first", "float32", finite, -0.0),
+             ("last", "float32", wild, np.nan), ("any", "uint8", 1, 0)]
     for fun, dtype, vals, bg in cases:
         v = np.asarray(vals).astype(dtype) if np.ndim(vals) else vals
         exp, _ = oracle.rasterize_dense(og, ori, fun, dtype, v, background=bg)
