@@ -19,6 +19,8 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 
+#include "../../include/rz_b200.h"
+
 namespace rz {
 
 struct KParams {
@@ -88,7 +90,7 @@ __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
 // ---------------------------------------------------------------------------------------------
 // One thread per part.  Resolves the burn value (field[i] or the scalar), the band and, for polygon
 // parts, the range of column tiles whose pixels the part can fill.
-__global__ void part_prepare_kernel(KParams P, const uint8_t* __restrict__ part_kind,
+static __global__ void part_prepare_kernel(KParams P, const uint8_t* __restrict__ part_kind,
                                     const uint32_t* __restrict__ part_geom, const double* __restrict__ part_xlo,
                                     const double* __restrict__ part_xhi, const uint8_t* __restrict__ field,
                                     uint32_t itemsize, int field_is_scalar, const uint8_t* __restrict__ field_valid,
@@ -126,7 +128,7 @@ __global__ void part_prepare_kernel(KParams P, const uint8_t* __restrict__ part_
 // Counters the host needs in the middle of a call (record counts, cost-model sums) are stored by this kernel
 // straight into page-locked, mapped host memory.  A cudaMemcpy of a few bytes would queue on the copy engine
 // behind the 2 GiB raster window that is on its way to the host, and stall the next window for its duration.
-__global__ void readback_kernel(const unsigned long long* __restrict__ src, volatile unsigned long long* dst, uint32_t n) {
+static __global__ void readback_kernel(const unsigned long long* __restrict__ src, volatile unsigned long long* dst, uint32_t n) {
     for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
     __threadfence_system();
 }
@@ -136,7 +138,7 @@ __global__ void readback_kernel(const unsigned long long* __restrict__ src, vola
 // ---------------------------------------------------------------------------------------------
 // tag = part id | 0x80000000 on the last vertex of a ring / line string | 0x40000000 on every vertex of a closed
 // line string (rz::Flattener::end_seq).  One warp per part writes the part id over the part's vertex range...
-__global__ void tag_parts_kernel(uint32_t n_parts, uint8_t kind, const uint8_t* __restrict__ part_kind,
+static __global__ void tag_parts_kernel(uint32_t n_parts, uint8_t kind, const uint8_t* __restrict__ part_kind,
                                  const uint32_t* __restrict__ vbeg, const uint32_t* __restrict__ vend,
                                  uint32_t* __restrict__ tag) {
     const uint32_t p = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -144,7 +146,7 @@ __global__ void tag_parts_kernel(uint32_t n_parts, uint8_t kind, const uint8_t* 
     for (uint32_t i = vbeg[p] + lane_id(); i < vend[p]; i += 32) tag[i] = p;
 }
 // ... then one thread per sequence sets the flags (sequences are contiguous in their pool, in order)
-__global__ void tag_seqs_kernel(uint32_t n_seq, const uint32_t* __restrict__ seq_end, const uint8_t* __restrict__ closed,
+static __global__ void tag_seqs_kernel(uint32_t n_seq, const uint32_t* __restrict__ seq_end, const uint8_t* __restrict__ closed,
                                 uint32_t* __restrict__ tag) {
     const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n_seq) return;
@@ -245,7 +247,7 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* s
 // Count pass: one thread per ring vertex.  Besides the global totals it stores the number of
 // records of every block so that the emit pass can place blocks in vertex order (= part order),
 // which lets a polygon-only job sort on the task bits alone.
-__global__ void __launch_bounds__(SETUP_THREADS)
+static __global__ void __launch_bounds__(SETUP_THREADS)
 poly_count_kernel(KParams P, const double* __restrict__ x, const double* __restrict__ y,
                   const uint32_t* __restrict__ tag, uint32_t n, const PartInfo* __restrict__ info,
                   uint32_t* __restrict__ block_total, Counters* __restrict__ ctr) {
@@ -272,7 +274,7 @@ poly_count_kernel(KParams P, const double* __restrict__ x, const double* __restr
 }
 
 // In-place exclusive scan of the per-block totals (single block; n is a few hundred thousand).
-__global__ void __launch_bounds__(1024) scan_u32_kernel(uint32_t* __restrict__ v, uint32_t n) {
+static __global__ void __launch_bounds__(1024) scan_u32_kernel(uint32_t* __restrict__ v, uint32_t n) {
     __shared__ uint32_t s_warp[33];
     uint32_t carry = 0;
     const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
@@ -305,7 +307,7 @@ __global__ void __launch_bounds__(1024) scan_u32_kernel(uint32_t* __restrict__ v
 
 // Emit pass: blocks write at their scanned base, warps flatten the records of their 32 edges so
 // that consecutive lanes store consecutive records (coalesced 256-byte stores).
-__global__ void __launch_bounds__(SETUP_THREADS)
+static __global__ void __launch_bounds__(SETUP_THREADS)
 poly_emit_kernel(KParams P, const double* __restrict__ x, const double* __restrict__ y,
                  const uint32_t* __restrict__ tag, uint32_t n, const PartInfo* __restrict__ info,
                  const uint32_t* __restrict__ block_base, uint64_t base_offset, uint64_t* __restrict__ keys) {
@@ -476,7 +478,7 @@ __device__ __forceinline__ uint64_t line_key(const KParams& P, const LineRec& l,
 }
 
 // count pass; also records, per line part, the highest kept segment (the one that may write its end pixel)
-__global__ void __launch_bounds__(SETUP_THREADS)
+static __global__ void __launch_bounds__(SETUP_THREADS)
 line_count_kernel(KParams P, const double* __restrict__ x, const double* __restrict__ y,
                   const uint32_t* __restrict__ tag, uint32_t n, const PartInfo* __restrict__ info,
                   uint32_t* __restrict__ last_kept, Counters* __restrict__ ctr) {
@@ -496,7 +498,7 @@ line_count_kernel(KParams P, const double* __restrict__ x, const double* __restr
     if (lane_id() == 0 && rec) atomicAdd(&ctr->records, rec);
 }
 
-__global__ void __launch_bounds__(SETUP_THREADS)
+static __global__ void __launch_bounds__(SETUP_THREADS)
 line_emit_kernel(KParams P, const double* __restrict__ x, const double* __restrict__ y,
                  const uint32_t* __restrict__ tag, uint32_t n, const PartInfo* __restrict__ info,
                  Counters* __restrict__ ctr, uint64_t* __restrict__ keys) {
@@ -549,7 +551,7 @@ line_emit_kernel(KParams P, const double* __restrict__ x, const double* __restri
 
 // The end pixel of the last kept segment of a pooled line part is written iff that segment's own
 // line string is not closed (burners.rs:87-89).  One thread per part; mode 0 counts, mode 1 emits.
-__global__ void line_final_kernel(KParams P, const double* __restrict__ x, const double* __restrict__ y,
+static __global__ void line_final_kernel(KParams P, const double* __restrict__ x, const double* __restrict__ y,
                                   const uint32_t* __restrict__ tag, const uint8_t* __restrict__ part_kind,
                                   const PartInfo* __restrict__ info, const uint32_t* __restrict__ last_kept,
                                   Counters* __restrict__ ctr, uint64_t* __restrict__ keys, int mode) {
@@ -570,7 +572,7 @@ __global__ void line_final_kernel(KParams P, const double* __restrict__ x, const
 // ---------------------------------------------------------------------------------------------
 // points — rust/src/geo/edges.rs:79-88; burners.rs:250-258
 // ---------------------------------------------------------------------------------------------
-__global__ void point_kernel(KParams P, const double* __restrict__ x, const double* __restrict__ y,
+static __global__ void point_kernel(KParams P, const double* __restrict__ x, const double* __restrict__ y,
                              const uint32_t* __restrict__ tag, uint32_t n, const PartInfo* __restrict__ info,
                              Counters* __restrict__ ctr, uint64_t* __restrict__ keys, int mode) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -743,7 +745,7 @@ __device__ __forceinline__ bool cache_contains(uint32_t nrows, uint32_t ncols, c
 }
 
 // one thread per ring vertex: the segment (i, i+1) either extends its part's box or marks the part
-__global__ void cache_box_kernel(KParams P, const double* __restrict__ x, const double* __restrict__ y,
+static __global__ void cache_box_kernel(KParams P, const double* __restrict__ x, const double* __restrict__ y,
                                  const uint32_t* __restrict__ tag, uint32_t n, CacheAcc* __restrict__ acc) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n || (tag[i] & 0x80000000u)) return;
@@ -759,7 +761,7 @@ __global__ void cache_box_kernel(KParams P, const double* __restrict__ x, const 
     atomicMax(&acc[part].xhi, f64_ordered(max_x));
     atomicMax(&acc[part].yhi, f64_ordered(max_y));
 }
-__global__ void cache_box_init_kernel(uint32_t n_parts, CacheAcc* __restrict__ acc) {
+static __global__ void cache_box_init_kernel(uint32_t n_parts, CacheAcc* __restrict__ acc) {
     const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n_parts) return;
     CacheAcc a;
@@ -768,7 +770,7 @@ __global__ void cache_box_init_kernel(uint32_t n_parts, CacheAcc* __restrict__ a
     a.dropped = a.pad = 0;
     acc[p] = a;
 }
-__global__ void cache_box_finish_kernel(uint32_t n_parts, const CacheAcc* __restrict__ acc, CacheBox* __restrict__ box) {
+static __global__ void cache_box_finish_kernel(uint32_t n_parts, const CacheAcc* __restrict__ acc, CacheBox* __restrict__ box) {
     const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n_parts) return;
     const double xlo = f64_from_ordered(acc[p].xlo), ylo = f64_from_ordered(acc[p].ylo);
@@ -794,7 +796,7 @@ __global__ void cache_box_finish_kernel(uint32_t n_parts, const CacheAcc* __rest
 
 // One thread per vertex of a ring / line-string pool.  mode 0 counts the in-window pixels, mode 1
 // emits one record per pixel (flagged as "pixel of the part's boundary walk").
-__global__ void __launch_bounds__(256)
+static __global__ void __launch_bounds__(256)
 touched_walk_kernel(KParams P, const double* __restrict__ x, const double* __restrict__ y,
                     const uint32_t* __restrict__ tag, uint32_t n, const PartInfo* __restrict__ info,
                     Counters* __restrict__ ctr, uint64_t* __restrict__ keys, int mode,
@@ -863,7 +865,7 @@ constexpr int RS_TILE = RS_THREADS * RS_ITEMS;  // 4096 keys per block
 constexpr int RS_RADIX = 256;
 
 // per-block digit histogram, stored digit-major: hist[d * n_blocks + b]
-__global__ void __launch_bounds__(RS_THREADS)
+static __global__ void __launch_bounds__(RS_THREADS)
 radix_hist_kernel(const uint64_t* __restrict__ keys, uint32_t n, uint32_t shift, uint32_t n_blocks,
                   uint32_t* __restrict__ hist) {
     __shared__ uint32_t s[RS_RADIX];
@@ -880,7 +882,7 @@ radix_hist_kernel(const uint64_t* __restrict__ keys, uint32_t n, uint32_t shift,
 }
 
 // one block per digit: exclusive scan of its row of block counts (in place) + digit total
-__global__ void __launch_bounds__(1024)
+static __global__ void __launch_bounds__(1024)
 radix_scan_rows_kernel(uint32_t* __restrict__ hist, uint32_t n_blocks, uint32_t* __restrict__ digit_total) {
     __shared__ uint32_t s_warp[33];
     uint32_t* row = hist + (size_t)blockIdx.x * n_blocks;
@@ -917,7 +919,7 @@ radix_scan_rows_kernel(uint32_t* __restrict__ hist, uint32_t n_blocks, uint32_t*
 // Stable scatter.  Keys are ranked warp by warp, 32 consecutive keys per round, with
 // __match_any_sync; the tile is then staged in shared memory in sorted order so that global stores
 // go out in runs of equal digits.
-__global__ void __launch_bounds__(RS_THREADS)
+static __global__ void __launch_bounds__(RS_THREADS)
 radix_scatter_kernel(const uint64_t* __restrict__ keys_in, uint64_t* __restrict__ keys_out, uint32_t n, uint32_t shift,
                      uint32_t n_blocks, const uint32_t* __restrict__ hist, const uint32_t* __restrict__ digit_total) {
     __shared__ uint64_t s_keys[RS_TILE];
@@ -994,7 +996,7 @@ radix_scatter_kernel(const uint64_t* __restrict__ keys_in, uint64_t* __restrict_
 // ---------------------------------------------------------------------------------------------
 // task index: first record of every task (lower bound on the sorted keys)
 // ---------------------------------------------------------------------------------------------
-__global__ void task_index_kernel(const uint64_t* __restrict__ keys, uint32_t n, uint32_t task_shift, uint32_t n_tasks,
+static __global__ void task_index_kernel(const uint64_t* __restrict__ keys, uint32_t n, uint32_t task_shift, uint32_t n_tasks,
                                   uint32_t* __restrict__ task_start) {
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t > n_tasks) return;
@@ -1085,7 +1087,7 @@ constexpr uint32_t FILL_MAX_TILE_W = 1024;  // 32 lanes x 32 toggle bits
 
 // Rare path: a polygon run with an odd number of crossings.  burners.rs:305 pairs the sorted
 // crossings with chunks_exact(2), i.e. the largest column is ignored: cancel one toggle there.
-__device__ __noinline__ void drop_last_crossing(uint32_t* tog, const uint64_t* __restrict__ keys, uint32_t beg,
+static __device__ __noinline__ void drop_last_crossing(uint32_t* tog, const uint64_t* __restrict__ keys, uint32_t beg,
                                                 uint32_t end, uint32_t col_mask, uint32_t flag_bit, uint32_t w,
                                                 uint32_t lane) {
     uint32_t mx = 0;
@@ -1119,7 +1121,7 @@ __device__ __forceinline__ void apply_mask(N* __restrict__ row_lane, uint32_t m,
 // never flushed.
 // FillWriter for a part with a dropped ring segment: remove from the inside mask every pixel the reference's
 // PixelCache claims to contain (cache_contains: aliased cells for pixels outside the cache's box)
-__device__ __noinline__ uint32_t drop_cached_fill(uint32_t m, uint32_t walked, const FillParams& F, const AliasCtx& A,
+static __device__ __noinline__ uint32_t drop_cached_fill(uint32_t m, uint32_t walked, const FillParams& F, const AliasCtx& A,
                                                   uint32_t part, uint32_t row, uint32_t c0, uint32_t w, uint32_t lane) {
     const CacheBox b = A.box[part];
     uint32_t cand = m & ~walked;
@@ -1155,7 +1157,7 @@ __device__ __forceinline__ void finish_poly_run(uint32_t* tog, uint32_t* orm, N*
 }
 
 template <typename N, int FN, bool ALL_POLY>
-__global__ void __launch_bounds__(FILL_WARPS * 32)
+static __global__ void __launch_bounds__(FILL_WARPS * 32)
 fill_kernel(FillParams F, const uint64_t* __restrict__ keys, const uint32_t* __restrict__ task_start,
             const PartInfo* __restrict__ info, const uint8_t* __restrict__ part_kind, uint64_t bg_bits,
             N* __restrict__ out, AliasCtx A) {

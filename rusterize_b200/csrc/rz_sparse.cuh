@@ -60,7 +60,7 @@ __device__ __forceinline__ unsigned long long block_inclusive_scan64(unsigned lo
 }
 
 template <typename Op, typename In>
-__global__ void __launch_bounds__(SC_THREADS) scan_reduce_kernel(In in, uint32_t n, unsigned long long* __restrict__ partial) {
+static __global__ void __launch_bounds__(SC_THREADS) scan_reduce_kernel(In in, uint32_t n, unsigned long long* __restrict__ partial) {
     __shared__ unsigned long long s_warp[32];
     unsigned long long acc = Op::identity();
     const uint32_t base = blockIdx.x * SC_TILE + threadIdx.x * SC_ITEMS;
@@ -74,7 +74,7 @@ __global__ void __launch_bounds__(SC_THREADS) scan_reduce_kernel(In in, uint32_t
 
 // single block: exclusive scan of the block aggregates in place; partial[nb] = grand total
 template <typename Op>
-__global__ void __launch_bounds__(1024) scan_partials_kernel(unsigned long long* __restrict__ partial, uint32_t nb) {
+static __global__ void __launch_bounds__(1024) scan_partials_kernel(unsigned long long* __restrict__ partial, uint32_t nb) {
     __shared__ unsigned long long s_warp[32];
     unsigned long long carry = Op::identity();
     for (uint32_t b0 = 0; b0 < nb; b0 += 1024) {
@@ -93,7 +93,7 @@ __global__ void __launch_bounds__(1024) scan_partials_kernel(unsigned long long*
 }
 
 template <typename Op, typename In, typename Out>
-__global__ void __launch_bounds__(SC_THREADS)
+static __global__ void __launch_bounds__(SC_THREADS)
 scan_apply_kernel(In in, uint32_t n, const unsigned long long* __restrict__ partial, Out out) {
     __shared__ unsigned long long s_warp[32];
     unsigned long long v[SC_ITEMS];
@@ -134,7 +134,7 @@ __device__ __forceinline__ uint64_t sparse_poly_key(const KParams& P, const Spar
 }
 
 // same structure as poly_emit_kernel, one record per (edge, row), sparse key
-__global__ void __launch_bounds__(SETUP_THREADS)
+static __global__ void __launch_bounds__(SETUP_THREADS)
 poly_emit_sparse_kernel(KParams P, SparseLayout L, const double* __restrict__ x, const double* __restrict__ y,
                         const uint32_t* __restrict__ tag, uint32_t n, const PartInfo* __restrict__ info,
                         const uint32_t* __restrict__ block_base, uint64_t* __restrict__ keys) {
@@ -223,7 +223,7 @@ __device__ __forceinline__ void for_each_line_pixel(const KParams& P, const doub
 }
 
 template <bool TOUCHED>
-__global__ void line_visit_insert_kernel(KParams P, const double* __restrict__ x, const double* __restrict__ y,
+static __global__ void line_visit_insert_kernel(KParams P, const double* __restrict__ x, const double* __restrict__ y,
                                          const uint32_t* __restrict__ tag, uint32_t n, const PartInfo* __restrict__ info,
                                          const uint32_t* __restrict__ last_kept, Counters* __restrict__ ctr,
                                          const unsigned long long* __restrict__ raw_off, VisitSet vs) {
@@ -340,7 +340,7 @@ struct InPointHit {
     }
 };
 
-__global__ void line_last_kept_kernel(KParams P, const double* __restrict__ x, const double* __restrict__ y,
+static __global__ void line_last_kept_kernel(KParams P, const double* __restrict__ x, const double* __restrict__ y,
                                       const uint32_t* __restrict__ tag, uint32_t n, const PartInfo* __restrict__ info,
                                       uint32_t* __restrict__ last_kept, Counters* __restrict__ ctr) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -354,7 +354,7 @@ __global__ void line_last_kept_kernel(KParams P, const double* __restrict__ x, c
 // per-part write counts and bases
 // ---------------------------------------------------------------------------------------------
 // rec_beg[p] = first sorted crossing of polygon part p (lower bound on the part field); p in 0..n_parts
-__global__ void part_rec_range_kernel(const uint64_t* __restrict__ keys, uint32_t n, uint32_t part_shift,
+static __global__ void part_rec_range_kernel(const uint64_t* __restrict__ keys, uint32_t n, uint32_t part_shift,
                                       uint32_t n_parts, uint32_t* __restrict__ rec_beg) {
     uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p > n_parts) return;
@@ -369,7 +369,7 @@ __global__ void part_rec_range_kernel(const uint64_t* __restrict__ keys, uint32_
 
 // count[p] = number of triplets part p writes; start[p] = value of its stream's prefix at the part's
 // first unit (so that unit offset inside the part = prefix - start[p])
-__global__ void part_count_kernel(uint32_t n_parts, const uint8_t* __restrict__ part_kind,
+static __global__ void part_count_kernel(uint32_t n_parts, const uint8_t* __restrict__ part_kind,
                                   const uint32_t* __restrict__ vbeg, const uint32_t* __restrict__ vend,
                                   const uint32_t* __restrict__ rec_beg, const unsigned long long* __restrict__ poly_off,
                                   uint32_t n_rec, unsigned long long poly_total,
@@ -427,7 +427,7 @@ struct OutBandBase {
 // expand: write the triplets at their final positions
 // ---------------------------------------------------------------------------------------------
 template <typename N>
-__global__ void __launch_bounds__(256)
+static __global__ void __launch_bounds__(256)
 poly_expand_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ seg_start,
                    const unsigned long long* __restrict__ poly_off, uint32_t n, SparseLayout L,
                    const PartInfo* __restrict__ info, const unsigned long long* __restrict__ part_base,
@@ -478,7 +478,7 @@ poly_expand_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict
 // all_touched with sum / count: a fill pixel is written unless the part's boundary walk visited it; one
 // thread per span writes the kept pixels one after another
 template <typename N>
-__global__ void __launch_bounds__(256)
+static __global__ void __launch_bounds__(256)
 poly_expand_dedup_kernel(KParams P, const uint64_t* __restrict__ keys, const uint32_t* __restrict__ seg_start,
                          const unsigned long long* __restrict__ poly_off, uint32_t n, SparseLayout L, VisitSet vs,
                          const CacheBox* __restrict__ box, const PartInfo* __restrict__ info, const unsigned long long* __restrict__ part_base,
@@ -506,7 +506,7 @@ poly_expand_dedup_kernel(KParams P, const uint64_t* __restrict__ keys, const uin
 }
 
 template <typename N, bool TOUCHED>
-__global__ void __launch_bounds__(256)
+static __global__ void __launch_bounds__(256)
 line_expand_kernel(KParams P, const double* __restrict__ x, const double* __restrict__ y,
                    const uint32_t* __restrict__ tag, uint32_t n, const PartInfo* __restrict__ info,
                    const uint32_t* __restrict__ last_kept, Counters* __restrict__ ctr,
@@ -533,7 +533,7 @@ line_expand_kernel(KParams P, const double* __restrict__ x, const double* __rest
 }
 
 template <typename N>
-__global__ void point_expand_kernel(KParams P, const double* __restrict__ x, const double* __restrict__ y,
+static __global__ void point_expand_kernel(KParams P, const double* __restrict__ x, const double* __restrict__ y,
                                     const uint32_t* __restrict__ tag, uint32_t n, const PartInfo* __restrict__ info,
                                     const unsigned long long* __restrict__ pt_off,
                                     const unsigned long long* __restrict__ part_base,
@@ -563,7 +563,7 @@ __global__ void point_expand_kernel(KParams P, const double* __restrict__ x, con
 // pixel function on a shared-memory row tile.
 namespace rz {
 
-__global__ void replay_emit_kernel(const unsigned long long* __restrict__ rows, const unsigned long long* __restrict__ cols,
+static __global__ void replay_emit_kernel(const unsigned long long* __restrict__ rows, const unsigned long long* __restrict__ cols,
                                    uint32_t n, const unsigned long long* __restrict__ band_off, uint32_t n_bands,
                                    uint32_t nrows, uint32_t ncols, uint32_t n_tiles, uint32_t tile_shift,
                                    uint32_t idx_bits, uint32_t n_tasks, uint64_t* __restrict__ keys) {
@@ -579,7 +579,7 @@ __global__ void replay_emit_kernel(const unsigned long long* __restrict__ rows, 
 }
 
 template <typename N, int FN>
-__global__ void __launch_bounds__(FILL_WARPS * 32)
+static __global__ void __launch_bounds__(FILL_WARPS * 32)
 replay_fill_kernel(FillParams F, const uint64_t* __restrict__ keys, const uint32_t* __restrict__ task_start,
                    const unsigned long long* __restrict__ cols, const N* __restrict__ data, uint32_t idx_bits,
                    uint64_t bg_bits, N* __restrict__ out) {

@@ -116,7 +116,7 @@ __device__ __forceinline__ bool part_pixel_box(const KParams& P, double xlo, dou
 // mode 0: per part the number of (part,tile) pairs and of (part,tile-row) pairs (+ totals);
 // mode 1: with the scanned offsets, fill PartTile and emit the row-pair list and the tile records
 // [tile | block], block = index of the (part,tile) pair's inside-mask block.
-__global__ void tile_bin_kernel(KParams P, TileParams T, const PartInfo* __restrict__ info,
+static __global__ void tile_bin_kernel(KParams P, TileParams T, const PartInfo* __restrict__ info,
                                 const double* __restrict__ xlo, const double* __restrict__ xhi,
                                 const double* __restrict__ ylo, const double* __restrict__ yhi,
                                 const uint32_t* __restrict__ vbeg, const uint32_t* __restrict__ vend,
@@ -233,7 +233,7 @@ __device__ __forceinline__ uint32_t tile_edge_col(const KParams& P, const TileEd
 // to the first row window of the call that its rows touch ("bucket"; parts touching none go to a last one),
 // and the parts of bucket b are copied by a kernel that reads the mapped host arrays directly, right before
 // window b is computed - while the copy stream is still sending window b-1 to the host.
-__global__ void part_bucket_kernel(KParams P, const uint8_t* __restrict__ part_kind, const double* __restrict__ ylo,
+static __global__ void part_bucket_kernel(KParams P, const uint8_t* __restrict__ part_kind, const double* __restrict__ ylo,
                                    const double* __restrict__ yhi, uint32_t shard_r0, uint32_t shard_r1,
                                    uint32_t win_rows, uint32_t n_buckets, uint32_t* __restrict__ bucket_of,
                                    unsigned int* __restrict__ cnt) {
@@ -249,7 +249,7 @@ __global__ void part_bucket_kernel(KParams P, const uint8_t* __restrict__ part_k
     bucket_of[p] = b;
 }
 // cnt[0 .. n_buckets] -> off[0 .. n_buckets + 1] (exclusive), cursors reset; a handful of buckets: one thread
-__global__ void bucket_scan_kernel(unsigned int* __restrict__ cnt, unsigned int* __restrict__ off, uint32_t n) {
+static __global__ void bucket_scan_kernel(unsigned int* __restrict__ cnt, unsigned int* __restrict__ off, uint32_t n) {
     unsigned int run = 0;
     for (uint32_t i = 0; i < n; i++) {
         off[i] = run;
@@ -258,7 +258,7 @@ __global__ void bucket_scan_kernel(unsigned int* __restrict__ cnt, unsigned int*
     }
     off[n] = run;
 }
-__global__ void bucket_scatter_kernel(uint32_t n_parts, const uint32_t* __restrict__ bucket_of,
+static __global__ void bucket_scatter_kernel(uint32_t n_parts, const uint32_t* __restrict__ bucket_of,
                                       const unsigned int* __restrict__ off, unsigned int* __restrict__ cursor,
                                       uint32_t* __restrict__ order) {
     const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
@@ -267,7 +267,7 @@ __global__ void bucket_scatter_kernel(uint32_t n_parts, const uint32_t* __restri
     if (b != 0xffffffffu) order[off[b] + atomicAdd(&cursor[b], 1u)] = p;
 }
 // one CTA per part: its vertex range from the mapped host arrays (PCIe reads) to the device pool
-__global__ void __launch_bounds__(128)
+static __global__ void __launch_bounds__(128)
 pull_parts_kernel(const uint32_t* __restrict__ order, uint32_t n, const uint32_t* __restrict__ vbeg,
                   const uint32_t* __restrict__ vend, const double* __restrict__ hx, const double* __restrict__ hy,
                   const uint32_t* __restrict__ htag, double* __restrict__ dx, double* __restrict__ dy,
@@ -302,7 +302,7 @@ pull_parts_kernel(const uint32_t* __restrict__ order, uint32_t n, const uint32_t
 // After the stable sort of the [tile | block] records: where every inside-mask block lives.  tile_mask writes
 // block b at position pos[b] of the mask array, i.e. in tile order, and the value of its part goes to the
 // same position, so that tile_apply streams a tile's blocks from consecutive memory with no indirection.
-__global__ void block_pos_kernel(const uint64_t* __restrict__ recs, uint32_t n, uint32_t block_bits,
+static __global__ void block_pos_kernel(const uint64_t* __restrict__ recs, uint32_t n, uint32_t block_bits,
                                  const unsigned long long* __restrict__ block_value, uint32_t* __restrict__ pos,
                                  unsigned long long* __restrict__ value_sorted) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -321,7 +321,7 @@ __global__ void block_pos_kernel(const uint64_t* __restrict__ recs, uint32_t n, 
 // (centre 0.5): only that row's crossing count is tracked, and an odd row 0 drops its largest column like
 // chunks_exact(2) drops the unpaired tail (burners.rs:305).
 template <int TILE_R>
-__global__ void __launch_bounds__(MASK_WARPS * 32, 8)
+static __global__ void __launch_bounds__(MASK_WARPS * 32, 8)
 tile_mask_kernel(KParams P, TileParams T, const uint64_t* __restrict__ units, uint32_t n_units,
                  const PartTile* __restrict__ pt, const uint32_t* __restrict__ vbeg, const uint32_t* __restrict__ vend,
                  const double* __restrict__ wx, const double* __restrict__ wy, const uint32_t* __restrict__ tag,
@@ -557,7 +557,7 @@ __device__ __forceinline__ void apply_part_word(N (&px)[32], uint32_t mw, N v, N
 constexpr int APPLY_TILES = 8;  // consecutive tiles of one tile row handled by one CTA
 
 template <typename N, int FN, int TILE_R, int MODE, bool BGNAN>
-__global__ void __launch_bounds__(TILE_R * 4, 4)
+static __global__ void __launch_bounds__(TILE_R * 4, 4)
 tile_apply_kernel(KParams P, TileParams T, const uint32_t* __restrict__ tile_start,
                   const unsigned long long* __restrict__ value_sorted, const uint32_t* __restrict__ masks,
                   uint64_t bg_bits, N* __restrict__ out) {
