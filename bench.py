@@ -398,14 +398,14 @@ def run_b200(args):
     fill_ms = float(np.mean([s["fill_ms"] for s in stats]))
     other = None
     if s0["engine"] == 1:
-        # tile engine, span-fill kernel = tile_apply: inside-mask blocks (tile_r rows x 16 B) + the part's value
-        # (8 B) per (part,tile) pair read once, raster written once
+        # tile engine, span-fill kernel = tile_apply: compact inside-mask blocks (4 B / word) + one 16-byte block
+        # descriptor per (part,tile) pair read once, raster written once
         tile_r = 64 if dt.itemsize <= 4 else 32
         kernel = "tile_apply_kernel<%s, %s, %d>" % (w["dtype"], w["fun"], tile_r)
-        fill_bytes = s0["n_records"] * (tile_r * 16.0 + 8.0) + s0["out_bytes"]
+        fill_bytes = s0["n_mask_words"] * 4.0 + s0["n_records"] * 16.0 + s0["out_bytes"]
         mask_ms = float(np.mean([s["count_ms"] for s in stats]))
-        # tile_mask: world vertices (16 B) + tags (4 B) read once per mask unit, mask blocks written once
-        mask_bytes = 20.0 * s0["n_poly_vertices"] + s0["n_records"] * tile_r * 16.0
+        # tile_mask: world vertices (16 B) + tags (4 B) read once per mask unit, compact mask blocks written once
+        mask_bytes = 20.0 * s0["n_poly_vertices"] + s0["n_mask_words"] * 4.0
         other = {"kernel": "tile_mask_kernel<%d>" % tile_r, "ms_per_launch": mask_ms,
                  "bytes_per_launch": mask_bytes, "achieved": mask_bytes / (mask_ms / 1e3) / 1e9,
                  "frac": mask_bytes / (mask_ms / 1e3) / 1e9 / peak, "note": "instruction-issue bound (f64 edge math, one crossing per lane)"}

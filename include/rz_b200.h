@@ -151,9 +151,8 @@ typedef struct rz_context {
 #define RZ_FLAG_SYNC_STAGES 4u     /* record per-stage CUDA-event timings into rz_stats */
 #define RZ_FLAG_NO_TILE_ENGINE 8u      /* always use the crossing-record pipeline */
 #define RZ_FLAG_FORCE_TILE_ENGINE 16u  /* use the tile-binned engine whenever the job is polygon-only */
-#define RZ_FLAG_STREAMED_H2D 64u        /* host rasters of polygon-only jobs: pull the polygon pool from page-locked
-                                          host memory window by window, under the raster's D2H, instead of uploading
-                                          it up front (opt-in: see rz_engine.cu for the measurement) */
+#define RZ_FLAG_STREAMED_H2D 64u        /* accepted and ignored (round 1 experiment: pulling the polygon pool from mapped
+                                          host memory under the raster's D2H did not pay) */
 
 typedef struct rz_stats {
     uint64_t n_parts, n_poly_vertices, n_line_vertices, n_points;
@@ -166,6 +165,10 @@ typedef struct rz_stats {
     uint64_t out_bytes;        /* B * rows * C * sizeof(dtype) */
     uint32_t kernel_launches;
     uint32_t engine;           /* 0 = crossing records + sort + row-tile fill, 1 = tile-binned polygon engine */
+    uint64_t n_mask_words;     /* tile engine: 32-bit words of the compact inside-mask blocks (upper bound) */
+    uint32_t host_syncs;       /* times the host waited for the device inside the call (0 for a steady-state
+                                  tile-engine call with device output) */
+    uint32_t plan_cached;      /* tile engine: buffer bounds came from the geometry handle's cache */
 } rz_stats;
 
 /* DenseArray::build (rust/src/rasterize.rs:71-116): out is [n_bands][rows][ncols] of ctx->dtype,

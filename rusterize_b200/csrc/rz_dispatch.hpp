@@ -11,8 +11,8 @@ namespace rz {
 
 typedef void (*FillLaunch)(dim3, size_t, cudaStream_t, FillParams, const uint64_t*, const uint32_t*, const PartInfo*,
                            const uint8_t*, uint64_t, void*, AliasCtx);
-typedef void (*TileLaunch)(uint32_t, cudaStream_t, KParams, TileParams, const uint32_t*, const unsigned long long*,
-                           const uint32_t*, uint64_t, void*, bool, bool);
+typedef void (*TileLaunch)(cudaStream_t, KParams, TileParams, const uint32_t*, const BlockDesc*, const uint32_t*,
+                           const TileCounters*, uint64_t, void*);
 typedef void (*ReplayLaunch)(dim3, size_t, cudaStream_t, FillParams, const uint64_t*, const uint32_t*,
                              const unsigned long long*, const void*, uint32_t, uint64_t, void*);
 

@@ -88,8 +88,9 @@ struct DeviceGeoms {
     uint32_t* part_vbeg = nullptr;
     uint32_t* part_vend = nullptr;
     size_t bytes = 0;
-    bool pending0 = false;  // the polygon pool is still being pulled window by window (streamed upload)
     ~DeviceGeoms() {
+        int prev = -1;
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
         cudaSetDevice(dev);
         for (int k = 0; k < 3; k++) {
             cudaFree(x[k]);
@@ -104,6 +105,7 @@ struct DeviceGeoms {
         cudaFree(part_yhi);
         cudaFree(part_vbeg);
         cudaFree(part_vend);
+        if (prev >= 0) cudaSetDevice(prev);
         (void)cudaGetLastError();
     }
 };
@@ -116,13 +118,16 @@ struct DeviceCtx {
     int host_ptr_ok = 0;  // kernels may dereference cudaHostRegister'ed host pointers
     DevBuf keys_a, keys_b, hist, digit_total, task_start, part_info, field, valid, band, last_kept, counters, win_out,
         block_total, vs_keys, vs_first, sp_raw, tile_cnt, tile_cnt2, tile_off, tile_off2, tile_ctr,
-        tile_pt, tile_pairs, tile_masks, tile_val, tile_pos, tile_val2, sp_a, sp_b, sp_c, sp_d, sp_e, sp_f, sp_g, sp_rows, sp_cols, sp_data, sp_partial, sp_w, sp_wraw, sp_ws, pull_bucket, pull_cnt, pull_order, cache_acc, cache_box;
+        tile_pt, tile_units, tile_masks, tile_desc, tile_desc2, lb_status, sp_a, sp_b, sp_c, sp_d, sp_e, sp_f, sp_g, sp_rows, sp_cols, sp_data, sp_partial, sp_w, sp_wraw, sp_ws, cache_acc, cache_box;
     Counters* h_counters = nullptr;  // pinned + mapped: written by readback_kernel
     void* h_tile_ctr = nullptr;      // same, for TileCounters
     cudaEvent_t ev[16];
     cudaStream_t copy_stream = nullptr;  // device->host copies of finished row windows overlap the next window
     cudaStream_t copy_stream2 = nullptr; // second half of every window copy (two copy engines in flight)
     cudaEvent_t ev_half = nullptr, ev_first_fill = nullptr;
+    cudaEvent_t ev_last = nullptr;  // end of the previous call on this device (scratch buffers are shared by all streams)
+    bool ev_last_valid = false;
+    cudaStream_t last_stream = nullptr;
     cudaEvent_t ev_filled[2], ev_copied[2], ev_d2h[2];
     DevBuf win_out2;
 };
@@ -156,6 +161,7 @@ static DeviceCtx& device_ctx(int dev) {
     CUDA_TRY(cudaStreamCreateWithFlags(&c->copy_stream2, cudaStreamNonBlocking));
     CUDA_TRY(cudaEventCreateWithFlags(&c->ev_half, cudaEventDisableTiming));
     CUDA_TRY(cudaEventCreate(&c->ev_first_fill));
+    CUDA_TRY(cudaEventCreateWithFlags(&c->ev_last, cudaEventDisableTiming));
     for (int k = 0; k < 2; k++) {
         CUDA_TRY(cudaEventCreateWithFlags(&c->ev_filled[k], cudaEventDisableTiming));
         CUDA_TRY(cudaEventCreateWithFlags(&c->ev_copied[k], cudaEventDisableTiming));
@@ -268,17 +274,13 @@ static void unpin_host(rz_geoms* g) {
     g->pool0_mapped = false;
 }
 
-// defer_pool0: allocate the polygon pool on the device but leave it for the caller to pull window by window
-// (rasterize_dense, streamed upload); the copy is then marked pending until the caller completes it.
-static DeviceGeoms* geoms_on_device(rz_geoms* g, DeviceCtx& c, cudaStream_t s, bool force, size_t* h2d_bytes,
-                                    bool defer_pool0 = false) {
+static DeviceGeoms* geoms_on_device(rz_geoms* g, DeviceCtx& c, cudaStream_t s, bool force, size_t* h2d_bytes) {
     std::lock_guard<std::mutex> lk(g->mu);
     auto it = g->dev.find(c.dev);
-    if (it != g->dev.end() && !force && !it->second->pending0) return it->second;
+    if (it != g->dev.end() && !force) return it->second;
     for (int k = 0; k < 3; k++)
         if (g->pool[k].size() >= 0xfffffff0ull) throw Error{RZ_RUNTIME_ERROR, "Too many vertices (limit 2^32 per pool)."};
     pin_host(g);
-    defer_pool0 = defer_pool0 && g->pool0_mapped && c.host_ptr_ok;
     std::unique_ptr<DeviceGeoms> fresh;
     DeviceGeoms* d = it != g->dev.end() ? it->second : nullptr;
     if (!d) {
@@ -288,13 +290,6 @@ static DeviceGeoms* geoms_on_device(rz_geoms* g, DeviceCtx& c, cudaStream_t s, b
     d->dev = c.dev;
     size_t bytes = 0;
     for (int k = 0; k < 3; k++) {
-        if (k == 0 && defer_pool0) {
-            const size_t n = g->pool[0].size() + 1;
-            if (!d->x[0]) CUDA_TRY(cudaMalloc((void**)&d->x[0], n * 8));
-            if (!d->y[0]) CUDA_TRY(cudaMalloc((void**)&d->y[0], n * 8));
-            if (!d->tag[0]) CUDA_TRY(cudaMalloc((void**)&d->tag[0], n * 4));
-            continue;
-        }
         upload_vec(&d->x[k], g->pool[k].x, s, bytes, g->pinned_ranges);
         upload_vec(&d->y[k], g->pool[k].y, s, bytes, g->pinned_ranges);
         if (g->pool[k].size() && !d->tag[k]) CUDA_TRY(cudaMalloc((void**)&d->tag[k], (g->pool[k].size() + 1) * 4));
@@ -313,7 +308,7 @@ static DeviceGeoms* geoms_on_device(rz_geoms* g, DeviceCtx& c, cudaStream_t s, b
     std::vector<void*> scratch;
     if (const uint32_t n_parts = (uint32_t)g->part_kind.size()) {
         for (int k = 0; k < 3; k++) {
-            if (!g->pool[k].size() || (k == 0 && defer_pool0)) continue;
+            if (!g->pool[k].size()) continue;
             tag_parts_kernel<<<(n_parts + 7) / 8, 256, 0, s>>>(n_parts, (uint8_t)k, d->part_kind, d->part_vbeg, d->part_vend,
                                                              d->tag[k]);
             const uint32_t n_seq = (uint32_t)g->pool[k].seq_end.size();
@@ -332,16 +327,12 @@ static DeviceGeoms* geoms_on_device(rz_geoms* g, DeviceCtx& c, cudaStream_t s, b
     }
     CUDA_TRY(cudaStreamSynchronize(s));  // `pg`, the sequence lists on the device are temporaries
     for (void* q : scratch) cudaFree(q);
-    d->pending0 = defer_pool0;
-    d->bytes = bytes + (defer_pool0 ? g->pool[0].size() * 20 : 0);  // (a streamed upload copies the host tags)
+    d->bytes = bytes;
     if (h2d_bytes) *h2d_bytes += bytes;
     if (fresh) g->dev[c.dev] = fresh.release();
     return d;
 }
 
-// ------------------------------------------------------------------------------------------------
-// fill dispatch: 10 dtypes x 7 pixel functions
-// ------------------------------------------------------------------------------------------------
 // ------------------------------------------------------------------------------------------------
 // device-wide scan helper (kernels in rz_sparse.cuh)
 // ------------------------------------------------------------------------------------------------
@@ -422,13 +413,48 @@ static void build_cache_boxes(DeviceCtx& c, cudaStream_t s, const KParams& P, De
     launches += 3;
 }
 
-static void rasterize_dense(rz_geoms* g, const rz_context* ctx, void* out, rz_stats* st) {
-    const rz_raster_info& ri = ctx->raster_info;
-    // rust/src/rasterize.rs:208-229
+// restores the caller's current device when an entry point returns (multi-GPU host processes)
+struct DeviceGuard {
+    int prev = -1;
+    DeviceGuard() {
+        if (cudaGetDevice(&prev) != cudaSuccess) {
+            (void)cudaGetLastError();
+            prev = -1;
+        }
+    }
+    ~DeviceGuard() {
+        if (prev >= 0 && cudaSetDevice(prev) != cudaSuccess) (void)cudaGetLastError();
+    }
+};
+
+// The per-device scratch (DeviceCtx) is shared by all calls on a device, whatever stream they run on: a call
+// first waits for the previous call's last kernel (an event), so that two streams never use the scratch at once.
+static void order_after_previous_call(DeviceCtx& c, cudaStream_t s) {
+    if (c.ev_last_valid && c.last_stream != s) CUDA_TRY(cudaStreamWaitEvent(s, c.ev_last, 0));
+}
+static void mark_call_end(DeviceCtx& c, cudaStream_t s) {
+    CUDA_TRY(cudaEventRecord(c.ev_last, s));
+    c.ev_last_valid = true;
+    c.last_stream = s;
+}
+
+// rust/src/rasterize.rs:208-229 + the band ids of rz_group_keys
+static void validate_lengths(const rz_geoms* g, const rz_context* ctx) {
     if (!ctx->field_is_scalar && ctx->field_len != g->n_geoms)
         throw Error{RZ_VALUE_ERROR, "Geometry and field lengths must match"};
     if (ctx->band_of_geom && ctx->by_len != g->n_geoms)
         throw Error{RZ_VALUE_ERROR, "Geometry and by lengths must match"};
+    if (ctx->band_of_geom) {  // negative = skipped; anything else must name a band
+        const int32_t nb = std::max(ctx->n_bands, 0);
+        bool bad = false;
+        for (uint64_t i = 0; i < g->n_geoms; i++) bad |= ctx->band_of_geom[i] >= nb;
+        if (bad) throw Error{RZ_VALUE_ERROR, "band_of_geom holds a band index >= n_bands"};
+    }
+}
+
+static void rasterize_dense(rz_geoms* g, const rz_context* ctx, void* out, rz_stats* st) {
+    const rz_raster_info& ri = ctx->raster_info;
+    validate_lengths(g, ctx);
     const size_t isz = dtype_size(ctx->dtype);
     if (!isz) throw Error{RZ_VALUE_ERROR, "Unsupported dtype"};
     if (ctx->pixel_fn < 0 || ctx->pixel_fn > RZ_ANY) throw Error{RZ_VALUE_ERROR, "Unknown pixel function"};
@@ -443,10 +469,12 @@ static void rasterize_dense(rz_geoms* g, const rz_context* ctx, void* out, rz_st
     const uint32_t shard_rows = shard_r1 - shard_r0;
     const bool out_dev = (ctx->flags & RZ_FLAG_OUT_ON_DEVICE) != 0;
 
+    DeviceGuard guard;
     DeviceCtx& c = device_ctx(ctx->device);
     std::lock_guard<std::mutex> lk(c.mu);
     CUDA_TRY(cudaSetDevice(c.dev));
     cudaStream_t s = ctx->stream ? (cudaStream_t)ctx->stream : c.stream;
+    order_after_previous_call(c, s);
     rz_stats S;
     std::memset(&S, 0, sizeof S);
     enum { EV_START, EV_H2D, EV_END, EV_A0 };  // EV_A0..: one event pair per stage of a window (6 pairs)
@@ -454,16 +482,8 @@ static void rasterize_dense(rz_geoms* g, const rz_context* ctx, void* out, rz_st
 
     // ---- inputs to the device ------------------------------------------------------------------
     size_t h2d = 0;
-    // Streamed upload (rz_tiles.cuh), opt-in: polygon-only jobs that can take the tile engine (which only reads
-    // the parts binned to a window) and whose raster goes back to the host in several windows.  Measured on
-    // config 4 it does overlap the 4 GB upload with the raster's D2H, but the kernel's PCIe read requests
-    // compete with the D2H writes for the upstream direction and the D2H phase stretches by as much as the
-    // upload shrank (417 ms against 395 ms end to end), so it is not the default.
     const uint64_t MAX_WINDOW_OUT_BYTES = max_window_out_bytes();
-    const bool stream_geoms = (ctx->flags & RZ_FLAG_STREAMED_H2D) && !out_dev && !ctx->all_touched &&
-                              g->pool[1].size() == 0 && g->pool[2].size() == 0 && !(ctx->flags & RZ_FLAG_NO_TILE_ENGINE) &&
-                              (uint64_t)n_bands * shard_rows * ri.ncols * isz >= 2 * MAX_WINDOW_OUT_BYTES;
-    DeviceGeoms* dg = geoms_on_device(g, c, s, (ctx->flags & RZ_FLAG_FORCE_H2D) != 0, &h2d, stream_geoms);
+    DeviceGeoms* dg = geoms_on_device(g, c, s, (ctx->flags & RZ_FLAG_FORCE_H2D) != 0, &h2d);
     const uint32_t n_parts = (uint32_t)g->part_kind.size();
     const size_t n_field = ctx->field_is_scalar ? 1 : (size_t)g->n_geoms;
     c.field.ensure(std::max<size_t>(n_field * isz, 8));
@@ -564,49 +584,7 @@ static void rasterize_dense(rz_geoms* g, const rz_context* ctx, void* out, rz_st
     for (uint32_t r = shard_r0; r < shard_r1; r += win_rows) todo.push_back(Window{r, std::min(r + win_rows, shard_r1)});
     std::reverse(todo.begin(), todo.end());  // pop_back walks top to bottom
 
-    // ---- streamed upload of the polygon pool: parts bucketed by the first window they touch -------------
-    uint32_t launches = 0;
-    const uint32_t n_buckets = (shard_rows + win_rows - 1) / win_rows;
-    uint32_t pulled = 0;  // buckets [0, pulled) are on the device; bucket n_buckets = parts touching no window
-    std::vector<unsigned int> bucket_off;
-    float pull_ms = 0;
-    if (dg->pending0) {
-        P.win_r0 = shard_r0;
-        P.win_r1 = shard_r1;
-        c.pull_bucket.ensure((size_t)n_parts * 4);
-        c.pull_order.ensure((size_t)n_parts * 4);
-        c.pull_cnt.ensure((size_t)(2 * n_buckets + 4) * 4);
-        unsigned int* d_cnt = c.pull_cnt.as<unsigned int>();
-        unsigned int* d_off = d_cnt + n_buckets + 1;
-        CUDA_TRY(cudaMemsetAsync(d_cnt, 0, (size_t)(n_buckets + 1) * 4, s));
-        part_bucket_kernel<<<(n_parts + 255) / 256, 256, 0, s>>>(P, dg->part_kind, dg->part_ylo, dg->part_yhi, shard_r0,
-                                                                 shard_r1, win_rows, n_buckets,
-                                                                 c.pull_bucket.as<uint32_t>(), d_cnt);
-        bucket_scan_kernel<<<1, 1, 0, s>>>(d_cnt, d_off, n_buckets + 1);
-        bucket_scatter_kernel<<<(n_parts + 255) / 256, 256, 0, s>>>(n_parts, c.pull_bucket.as<uint32_t>(), d_off, d_cnt,
-                                                                    c.pull_order.as<uint32_t>());
-        launches += 3;
-        bucket_off.resize(n_buckets + 2);
-        CUDA_TRY(cudaMemcpyAsync(bucket_off.data(), d_off, (size_t)(n_buckets + 2) * 4, cudaMemcpyDeviceToHost, s));
-        CUDA_TRY(cudaStreamSynchronize(s));
-    }
-    if (n_parts) launches++;  // part_prepare
-    auto pull_upto = [&](uint32_t b_end) {  // make buckets [0, b_end) resident
-        if (!dg->pending0 || b_end <= pulled) return;
-        const uint32_t i0 = bucket_off[pulled], i1 = bucket_off[b_end];
-        if (i1 > i0) {
-            pull_parts_kernel<<<i1 - i0, 128, 0, s>>>(c.pull_order.as<uint32_t>() + i0, i1 - i0, dg->part_vbeg,
-                                                      dg->part_vend, g->pool[0].x.data(), g->pool[0].y.data(),
-                                                      g->pool[0].tag.data(), dg->x[0], dg->y[0], dg->tag[0]);
-            launches++;
-        }
-        pulled = b_end;
-        if (pulled == n_buckets + 1) {
-            dg->pending0 = false;
-            h2d += g->pool[0].size() * 20;
-        }
-    };
-
+    uint32_t launches = n_parts ? 1u : 0u;  // part_prepare
     FillLaunch fill = fill_for(ctx->dtype, ctx->pixel_fn);
     float count_ms = 0, emit_ms = 0, sort_ms = 0, index_ms = 0, fill_ms = 0, d2h_ms = 0;
     const bool timed = (ctx->flags & RZ_FLAG_SYNC_STAGES) != 0;
@@ -683,6 +661,7 @@ static void rasterize_dense(rz_geoms* g, const rz_context* ctx, void* out, rz_st
         readback_kernel<<<1, 32, 0, s>>>((const unsigned long long*)d_ctr, (volatile unsigned long long*)c.h_counters,
                                          (uint32_t)(sizeof(Counters) / 8));
         CUDA_TRY(cudaStreamSynchronize(s));
+        S.host_syncs++;
         const unsigned long long walked = c.h_counters->cursor;
         if (walked) {  // some part has a dropped ring segment: remember its walked pixels
             unsigned long long cap = 1024;
@@ -706,6 +685,12 @@ static void rasterize_dense(rz_geoms* g, const rz_context* ctx, void* out, rz_st
         }
     }
 
+    // The tile-binned engine takes polygon-only jobs without all_touched whose coordinates are all finite (its
+    // odd-crossing rule relies on that; see tile_mask_kernel).
+    const bool tile_candidate = nv_line == 0 && nv_pt == 0 && !touched && n_parts && !g->nonfinite &&
+                                !(ctx->flags & RZ_FLAG_NO_TILE_ENGINE);
+    bool tile_stats_pending = false;
+
     while (!todo.empty()) {
         Window w = todo.back();
         todo.pop_back();
@@ -713,38 +698,68 @@ static void rasterize_dense(rz_geoms* g, const rz_context* ctx, void* out, rz_st
         P.win_r1 = w.r1;
         const uint32_t rows = w.r1 - w.r0;
 
-        // ---- tile-binned engine (polygon-only jobs made of small parts) ------------------------
-        if (nv_line == 0 && nv_pt == 0 && !touched && n_parts && !(ctx->flags & RZ_FLAG_NO_TILE_ENGINE)) {
+        // ---- tile-binned engine ---------------------------------------------------------------------
+        if (tile_candidate) {
             TileParams T;
             std::memset(&T, 0, sizeof T);
             T.tile_r = isz <= 4 ? 64u : 32u;
             T.n_tc = (uint32_t)((ri.ncols + TILE_C - 1) / TILE_C);
             T.n_tr = (rows + T.tile_r - 1) / T.tile_r;
             const uint64_t n_tiles64 = (uint64_t)n_bands * T.n_tr * T.n_tc;
-            T.part_bits = P.part_bits;
             if (n_tiles64 < (1ull << 31)) {  // record = [tile | block], both below 2^31
                 T.n_tiles = (uint32_t)n_tiles64;
-                if (timed) CUDA_TRY(cudaEventRecord(c.ev[EV_A], s));
-                c.tile_cnt.ensure((size_t)n_parts * 4);
-                c.tile_cnt2.ensure((size_t)n_parts * 4);
-                c.tile_off.ensure((size_t)n_parts * 8);
-                c.tile_off2.ensure((size_t)n_parts * 8);
-                c.tile_pt.ensure((size_t)n_parts * sizeof(PartTile));
+                c.tile_cnt.ensure((size_t)n_parts * 12);
+                c.tile_off.ensure((size_t)n_parts * 12);
                 c.tile_ctr.ensure(sizeof(TileCounters));
                 TileCounters* d_tc = c.tile_ctr.as<TileCounters>();
-                CUDA_TRY(cudaMemsetAsync(d_tc, 0, sizeof(TileCounters), s));
-                tile_bin_kernel<<<(n_parts + 255) / 256, 256, 0, s>>>(
-                    P, T, d_info, dg->part_xlo, dg->part_xhi, dg->part_ylo, dg->part_yhi, dg->part_vbeg, dg->part_vend,
-                    c.tile_cnt.as<uint32_t>(), c.tile_cnt2.as<uint32_t>(), nullptr, nullptr, nullptr, nullptr, nullptr,
-                    nullptr, 0, d_tc, 0, ctx->dtype == RZ_F32 ? 4 : (ctx->dtype == RZ_F64 ? 8 : 0), bg_bits,
-                    isz >= 8 ? ~0ull : ((1ull << (8 * isz)) - 1ull));
-                launches++;
-                static_assert(sizeof(TileCounters) % 8 == 0 && sizeof(TileCounters) <= 256, "readback layout");
-                readback_kernel<<<1, 32, 0, s>>>((const unsigned long long*)d_tc, (volatile unsigned long long*)c.h_tile_ctr,
-                                                 (uint32_t)(sizeof(TileCounters) / 8));
-                CUDA_TRY(cudaStreamSynchronize(s));
-                TileCounters h_tc;
-                std::memcpy(&h_tc, c.h_tile_ctr, sizeof h_tc);
+                const int float_bytes = ctx->dtype == RZ_F32 ? 4 : (ctx->dtype == RZ_F64 ? 8 : 0);
+                const unsigned long long value_mask = isz >= 8 ? ~0ull : ((1ull << (8 * isz)) - 1ull);
+                auto bin = [&](int mode, int ignore_band) {
+                    tile_bin_kernel<<<(n_parts + 255) / 256, 256, 0, s>>>(
+                        P, T, d_info, dg->part_kind, dg->part_xlo, dg->part_xhi, dg->part_ylo, dg->part_yhi, dg->part_vbeg,
+                        dg->part_vend, c.tile_cnt.as<uint32_t>(), c.tile_off.as<uint32_t>(), c.tile_pt.as<PartTile>(),
+                        c.tile_units.as<uint64_t>(), c.keys_a.as<uint64_t>(), c.tile_desc.as<BlockDesc>(), d_tc, mode,
+                        ignore_band, float_bytes, bg_bits, value_mask);
+                    launches++;
+                };
+                // Upper bounds of this (geometry set, grid, window): cached in the geometry handle.  The first call
+                // counts on the device with every polygon part active and reads the totals back (the one host
+                // synchronisation of the engine); later calls size their buffers from the cache and never wait.
+                const TilePlanKey key{ri.nrows, ri.ncols, ri.xmin, ri.ymax, ri.xres, ri.yres, w.r0, w.r1, T.tile_r};
+                TilePlan plan;
+                bool have_plan = false;
+                {
+                    std::lock_guard<std::mutex> gl(g->mu);
+                    auto it = g->tile_plans.find(key);
+                    if (it != g->tile_plans.end()) {
+                        plan = it->second;
+                        have_plan = true;
+                    }
+                }
+                if (!have_plan) {
+                    if (timed) CUDA_TRY(cudaEventRecord(c.ev[EV_A], s));
+                    CUDA_TRY(cudaMemsetAsync(d_tc, 0, sizeof(TileCounters), s));
+                    bin(0, 1);
+                    static_assert(sizeof(TileCounters) % 8 == 0 && sizeof(TileCounters) <= 256, "readback layout");
+                    readback_kernel<<<1, 32, 0, s>>>((const unsigned long long*)d_tc, (volatile unsigned long long*)c.h_tile_ctr,
+                                                     (uint32_t)(sizeof(TileCounters) / 8));
+                    if (timed) CUDA_TRY(cudaEventRecord(c.ev[EV_B], s));
+                    lap(emit_ms, EV_A, EV_B);
+                    CUDA_TRY(cudaStreamSynchronize(s));
+                    S.host_syncs++;
+                    TileCounters h_tc;
+                    std::memcpy(&h_tc, c.h_tile_ctr, sizeof h_tc);
+                    plan.pairs = h_tc.pairs;
+                    plan.units = h_tc.units;
+                    plan.words = h_tc.words;
+                    plan.edge_visits = h_tc.edge_visits;
+                    plan.cross_lb = h_tc.cross_lb;
+                    std::lock_guard<std::mutex> gl(g->mu);
+                    if (g->tile_plans.size() >= 256) g->tile_plans.clear();
+                    g->tile_plans[key] = plan;
+                } else {
+                    S.plan_cached = 1;
+                }
                 // Cost model.  tile_mask visits every ring vertex of a part once per mask unit and 512-column chunk
                 // (a few instructions per visit) and then pays per crossing; the record pipeline pays ~10 passes
                 // over HBM per crossing, several times more.  The tile engine therefore wins unless the vertex
@@ -752,39 +767,46 @@ static void rasterize_dense(rz_geoms* g, const rz_context* ctx, void* out, rz_st
                 // (small parts: config 4) or of the crossings' lower bound, two per part row (few vertices but
                 // large extents: config 3 runs 4-5x faster here than through records).  A huge, vertex-rich part
                 // cut into hundreds of units fails both tests and goes to the record pipeline.
-                const uint64_t mask_bytes = h_tc.pairs * T.tile_r * 16ull;
                 const bool wanted = (ctx->flags & RZ_FLAG_FORCE_TILE_ENGINE) ||
-                                    h_tc.edge_visits <= 6ull * nv_poly + (1ull << 20) ||
-                                    h_tc.edge_visits <= 6ull * h_tc.cross_lb;
-                if (wanted && h_tc.pairs < (1ull << 31) && h_tc.row_pairs < (1ull << 31) && mask_bytes <= (24ull << 30)) {
-                    const uint32_t n_rec = (uint32_t)h_tc.pairs, n_rows = (uint32_t)h_tc.row_pairs;
-                    device_scan<OpAdd>(InU32{c.tile_cnt.as<uint32_t>()}, n_parts,
-                                       OutPrefix64{c.tile_off.as<unsigned long long>()}, c.sp_partial, s, launches);
-                    device_scan<OpAdd>(InU32{c.tile_cnt2.as<uint32_t>()}, n_parts,
-                                       OutPrefix64{c.tile_off2.as<unsigned long long>()}, c.sp_partial, s, launches);
-                    c.keys_a.ensure(std::max<size_t>((size_t)n_rec * 8, 64));
-                    c.keys_b.ensure(std::max<size_t>((size_t)n_rec * 8, 64));
-                    c.tile_pairs.ensure(std::max<size_t>((size_t)n_rows * 8, 64));
-                    c.tile_masks.ensure(std::max<size_t>(mask_bytes, 64));
-                    c.tile_val.ensure(std::max<size_t>((size_t)n_rec * 8, 64));
-                    const uint32_t block_bits = std::max(1u, bits_for(std::max<uint64_t>(n_rec, 1)));
+                                    plan.edge_visits <= 6ull * nv_poly + (1ull << 20) ||
+                                    plan.edge_visits <= 6ull * plan.cross_lb;
+                if (wanted && plan.pairs < (1ull << 31) && plan.units < (1ull << 31) && plan.words < (1ull << 32) - 64) {
+                    T.cap_pairs = (uint32_t)std::max<uint64_t>(plan.pairs, 1);
+                    T.cap_units = (uint32_t)std::max<uint64_t>(plan.units, 1);
+                    T.block_bits = std::max(1u, bits_for(T.cap_pairs));
+                    const uint32_t n_rec = T.cap_pairs;
+                    const uint32_t n_lb = (n_parts + LB_TILE - 1) / LB_TILE;
+                    c.keys_a.ensure((size_t)n_rec * 8);
+                    c.keys_b.ensure((size_t)n_rec * 8);
+                    c.tile_pt.ensure((size_t)n_parts * sizeof(PartTile));
+                    c.tile_units.ensure((size_t)T.cap_units * 8);
+                    c.tile_desc.ensure((size_t)n_rec * sizeof(BlockDesc));
+                    c.tile_desc2.ensure((size_t)n_rec * sizeof(BlockDesc));
+                    c.tile_masks.ensure(std::max<size_t>((size_t)plan.words * 4, 64));
+                    c.lb_status.ensure((size_t)n_lb * 3 * 8);
                     uint64_t* ka = c.keys_a.as<uint64_t>();
                     uint64_t* kb = c.keys_b.as<uint64_t>();
-                    tile_bin_kernel<<<(n_parts + 255) / 256, 256, 0, s>>>(
-                        P, T, d_info, dg->part_xlo, dg->part_xhi, dg->part_ylo, dg->part_yhi, dg->part_vbeg, dg->part_vend,
-                        nullptr, nullptr, c.tile_off.as<unsigned long long>(), c.tile_off2.as<unsigned long long>(),
-                        c.tile_pt.as<PartTile>(), c.tile_pairs.as<uint64_t>(), ka, c.tile_val.as<unsigned long long>(),
-                        block_bits, d_tc, 1, 0, 0ull, 0ull);
+                    // ---- binning: counts -> offsets -> units, block descriptors, tile records ---------------
+                    if (timed) CUDA_TRY(cudaEventRecord(c.ev[EV_A], s));
+                    CUDA_TRY(cudaMemsetAsync(d_tc, 0, sizeof(TileCounters), s));
+                    CUDA_TRY(cudaMemsetAsync(c.lb_status.p, 0, (size_t)n_lb * 3 * 8, s));
+                    CUDA_TRY(cudaMemsetAsync(ka, 0xff, (size_t)n_rec * 8, s));  // fillers beyond the actual count sort last
+                    bin(0, 0);
+                    scan_lookback_kernel<3><<<n_lb, LB_THREADS, 0, s>>>(c.tile_cnt.as<uint32_t>(), c.tile_off.as<uint32_t>(),
+                                                                        n_parts, c.lb_status.as<unsigned long long>(),
+                                                                        &d_tc->scan_ticket);
                     launches++;
+                    bin(1, 0);
                     if (timed) CUDA_TRY(cudaEventRecord(c.ev[EV_B], s));
                     lap(emit_ms, EV_A, EV_B);
+                    // ---- records are in part order: a stable sort on the tile bits keeps burn order ----------
                     if (timed) CUDA_TRY(cudaEventRecord(c.ev[EV_A], s));
-                    const uint32_t tkey_bits = block_bits + bits_for(n_tiles64);
-                    if (n_rec > 1) {  // records are in part order: a stable sort on the tile bits keeps burn order
+                    const uint32_t tkey_bits = T.block_bits + bits_for(n_tiles64 + 1);
+                    if (n_rec > 1) {
                         const uint32_t n_blocks = (n_rec + RS_TILE - 1) / RS_TILE;
                         c.hist.ensure((size_t)n_blocks * RS_RADIX * 4);
                         c.digit_total.ensure(RS_RADIX * 4);
-                        for (uint32_t shift = block_bits; shift < tkey_bits; shift += 8) {
+                        for (uint32_t shift = T.block_bits; shift < tkey_bits; shift += 8) {
                             radix_hist_kernel<<<n_blocks, RS_THREADS, 0, s>>>(ka, n_rec, shift, n_blocks,
                                                                               c.hist.as<uint32_t>());
                             radix_scan_rows_kernel<<<RS_RADIX, 1024, 0, s>>>(c.hist.as<uint32_t>(), n_blocks,
@@ -798,37 +820,26 @@ static void rasterize_dense(rz_geoms* g, const rz_context* ctx, void* out, rz_st
                         }
                     }
                     c.task_start.ensure(((size_t)T.n_tiles + 1) * 4);
-                    task_index_kernel<<<(T.n_tiles + 1 + 255) / 256, 256, 0, s>>>(ka, n_rec, block_bits, T.n_tiles,
+                    task_index_kernel<<<(T.n_tiles + 1 + 255) / 256, 256, 0, s>>>(ka, n_rec, T.block_bits, T.n_tiles,
                                                                                 c.task_start.as<uint32_t>());
-                    c.tile_pos.ensure(std::max<size_t>((size_t)n_rec * 4, 64));
-                    c.tile_val2.ensure(std::max<size_t>((size_t)n_rec * 8, 64));
-                    if (n_rec)
-                        block_pos_kernel<<<(n_rec + 255) / 256, 256, 0, s>>>(
-                            ka, n_rec, block_bits, c.tile_val.as<unsigned long long>(), c.tile_pos.as<uint32_t>(),
-                            c.tile_val2.as<unsigned long long>());
+                    block_pos_kernel<<<(n_rec + 255) / 256, 256, 0, s>>>(ka, d_tc, T.block_bits, c.tile_desc.as<BlockDesc>(),
+                                                                        c.tile_desc2.as<BlockDesc>());
                     launches += 2;
                     if (timed) CUDA_TRY(cudaEventRecord(c.ev[EV_B], s));
                     lap(sort_ms, EV_A, EV_B);
-                    // ---- streamed upload: the parts this window is the first to need ------------------
-                    if (dg->pending0) {
-                        if (timed) CUDA_TRY(cudaEventRecord(c.ev[EV_A], s));
-                        pull_upto(std::min((w.r0 - shard_r0) / win_rows, n_buckets - 1) + 1);
-                        if (timed) CUDA_TRY(cudaEventRecord(c.ev[EV_B], s));
-                        lap(pull_ms, EV_A, EV_B);
-                    }
-                    // ---- inside masks of every (part, tile) pair ----------------------------------
+                    // ---- inside masks of every (part, tile) block ---------------------------------
                     if (timed) CUDA_TRY(cudaEventRecord(c.ev[EV_A], s));
-                    if (n_rows) {
-                        const uint32_t grid = (n_rows + MASK_WARPS * MASK_UNITS - 1) / (MASK_WARPS * MASK_UNITS);
+                    {
+                        const uint32_t grid = (T.cap_units + MASK_WARPS * MASK_UNITS - 1) / (MASK_WARPS * MASK_UNITS);
                         if (T.tile_r == 64)
                             tile_mask_kernel<64><<<grid, MASK_WARPS * 32, 0, s>>>(
-                                P, T, c.tile_pairs.as<uint64_t>(), n_rows, c.tile_pt.as<PartTile>(), dg->part_vbeg,
-                                dg->part_vend, dg->x[0], dg->y[0], dg->tag[0], c.tile_pos.as<uint32_t>(),
+                                P, T, c.tile_units.as<uint64_t>(), d_tc, c.tile_pt.as<PartTile>(), dg->part_vbeg,
+                                dg->part_vend, dg->x[0], dg->y[0], dg->tag[0], c.tile_desc.as<BlockDesc>(),
                                 c.tile_masks.as<uint32_t>());
                         else
                             tile_mask_kernel<32><<<grid, MASK_WARPS * 32, 0, s>>>(
-                                P, T, c.tile_pairs.as<uint64_t>(), n_rows, c.tile_pt.as<PartTile>(), dg->part_vbeg,
-                                dg->part_vend, dg->x[0], dg->y[0], dg->tag[0], c.tile_pos.as<uint32_t>(),
+                                P, T, c.tile_units.as<uint64_t>(), d_tc, c.tile_pt.as<PartTile>(), dg->part_vbeg,
+                                dg->part_vend, dg->x[0], dg->y[0], dg->tag[0], c.tile_desc.as<BlockDesc>(),
                                 c.tile_masks.as<uint32_t>());
                         launches++;
                     }
@@ -847,19 +858,20 @@ static void rasterize_dense(rz_geoms* g, const rz_context* ctx, void* out, rz_st
                         T.win_row_off = 0;
                     }
                     T.vec_ok = ((uintptr_t)d_out % 16 == 0) && ((ri.ncols * isz) % 16 == 0);
-                    tile_for(ctx->dtype, ctx->pixel_fn)(T.n_tiles, s, P, T, c.task_start.as<uint32_t>(),
-                                                        c.tile_val2.as<unsigned long long>(),
-                                                        c.tile_masks.as<uint32_t>(), bg_bits, d_out, !h_tc.nonfinite, !h_tc.eq_bg);
+                    tile_for(ctx->dtype, ctx->pixel_fn)(s, P, T, c.task_start.as<uint32_t>(), c.tile_desc2.as<BlockDesc>(),
+                                                        c.tile_masks.as<uint32_t>(), d_tc, bg_bits, d_out);
                     launches++;
                     CUDA_TRY(cudaGetLastError());
                     if (timed) CUDA_TRY(cudaEventRecord(c.ev[EV_B], s));
                     lap(fill_ms, EV_A, EV_B);
                     S.engine = 1;
-                    S.n_records += n_rec;
+                    S.n_records += plan.pairs;
+                    S.n_mask_words += plan.words;
                     S.n_tasks += T.n_tiles;
                     S.n_windows++;
                     S.key_bits = std::max(S.key_bits, tkey_bits);
                     S.tile_width = TILE_C;
+                    tile_stats_pending = true;
                     if (!out_dev) stage_copy(w, d_out);
                     flush_laps();
                     continue;
@@ -868,7 +880,6 @@ static void rasterize_dense(rz_geoms* g, const rz_context* ctx, void* out, rz_st
         }
 
         // ---- count --------------------------------------------------------------------------
-        pull_upto(n_buckets + 1);  // the record pipeline reads every ring vertex: finish a streamed upload first
         if (timed) CUDA_TRY(cudaEventRecord(c.ev[EV_A], s));
         CUDA_TRY(cudaMemsetAsync(d_ctr, 0, sizeof(Counters), s));
         const uint32_t poly_blocks = (nv_poly + SETUP_THREADS - 1) / SETUP_THREADS;
@@ -903,6 +914,7 @@ static void rasterize_dense(rz_geoms* g, const rz_context* ctx, void* out, rz_st
                                          (uint32_t)(sizeof(Counters) / 8));
         if (timed) CUDA_TRY(cudaEventRecord(c.ev[EV_B], s));
         CUDA_TRY(cudaStreamSynchronize(s));
+        S.host_syncs++;
         lap(count_ms, EV_A, EV_B);
         if (c.h_counters->bad_line)
             throw Error{RZ_RUNTIME_ERROR,
@@ -1035,14 +1047,28 @@ static void rasterize_dense(rz_geoms* g, const rz_context* ctx, void* out, rz_st
         if (!out_dev) stage_copy(w, d_out);
         flush_laps();
     }
-    pull_upto(n_buckets + 1);  // parts no window needed: the device copy of the geometry is complete again
     if (!out_dev && n_staged) {  // the call returns when the last window has landed in host memory
         CUDA_TRY(cudaEventRecord(c.ev_d2h[1], c.copy_stream));
         CUDA_TRY(cudaStreamWaitEvent(s, c.ev_d2h[1], 0));
     }
+    const bool sync_end = !out_dev || timed;
+    if (tile_stats_pending && sync_end)  // the host waits anyway: bring the last window's counters along
+        readback_kernel<<<1, 32, 0, s>>>((const unsigned long long*)c.tile_ctr.p, (volatile unsigned long long*)c.h_tile_ctr,
+                                         (uint32_t)(sizeof(TileCounters) / 8));
     CUDA_TRY(cudaEventRecord(c.ev[EV_END], s));
-    if (!out_dev || timed) {
+    mark_call_end(c, s);
+    if (sync_end) {
         CUDA_TRY(cudaEventSynchronize(c.ev[EV_END]));
+        S.host_syncs++;
+        if (tile_stats_pending) {
+            TileCounters h_tc;
+            std::memcpy(&h_tc, c.h_tile_ctr, sizeof h_tc);
+            if (h_tc.overflow) {  // cannot happen: the cached bounds count every polygon part
+                std::lock_guard<std::mutex> gl(g->mu);
+                g->tile_plans.clear();
+                throw Error{RZ_RUNTIME_ERROR, "Internal error: tile plan overflow."};
+            }
+        }
         if (!out_dev && n_staged) {
             CUDA_TRY(cudaEventElapsedTime(&d2h_ms, c.ev_d2h[0], c.ev_d2h[1]));
             if (std::getenv("RZ_VERBOSE")) {
@@ -1058,7 +1084,6 @@ static void rasterize_dense(rz_geoms* g, const rz_context* ctx, void* out, rz_st
         CUDA_TRY(cudaEventElapsedTime(&S.h2d_ms, c.ev[EV_START], c.ev[EV_H2D]));
     }
     S.h2d_bytes = h2d;
-    S.h2d_ms += pull_ms;
     S.count_ms = count_ms;
     S.emit_ms = emit_ms;
     S.sort_ms = sort_ms;
@@ -1229,10 +1254,7 @@ static void sparse_expand(cudaStream_t s, const KParams& P, SparseLayout L, Devi
 
 static void rasterize_sparse(rz_geoms* g, const rz_context* ctx, rz_sparse* out, rz_stats* st) {
     const rz_raster_info& ri = ctx->raster_info;
-    if (!ctx->field_is_scalar && ctx->field_len != g->n_geoms)
-        throw Error{RZ_VALUE_ERROR, "Geometry and field lengths must match"};
-    if (ctx->band_of_geom && ctx->by_len != g->n_geoms)
-        throw Error{RZ_VALUE_ERROR, "Geometry and by lengths must match"};
+    validate_lengths(g, ctx);
     const size_t isz = dtype_size(ctx->dtype);
     if (!isz) throw Error{RZ_VALUE_ERROR, "Unsupported dtype"};
     if (ctx->pixel_fn < 0 || ctx->pixel_fn > RZ_ANY) throw Error{RZ_VALUE_ERROR, "Unknown pixel function"};
@@ -1250,10 +1272,12 @@ static void rasterize_sparse(rz_geoms* g, const rz_context* ctx, rz_sparse* out,
     const bool line_dedup = (ri.xres != ri.yres || fn_dedup) && nv_line;  // burn_geometry.rs:179, 202
     const bool poly_dedup = fn_dedup && nv_poly;                          // burn_geometry.rs:99-103
 
+    DeviceGuard guard;
     DeviceCtx& c = device_ctx(ctx->device);
     std::lock_guard<std::mutex> lk(c.mu);
     CUDA_TRY(cudaSetDevice(c.dev));
     cudaStream_t s = ctx->stream ? (cudaStream_t)ctx->stream : c.stream;
+    order_after_previous_call(c, s);
     rz_stats S;
     std::memset(&S, 0, sizeof S);
     enum { EV_START, EV_END, EV_SORTED, EV_COUNTED, EV_EXPANDED };  // stage marks (rz_stats: emit+sort, index, fill, d2h)
@@ -1527,6 +1551,7 @@ static void rasterize_sparse(rz_geoms* g, const rz_context* ctx, rz_sparse* out,
         S.d2h_bytes = total * (16 + isz);
     }
     CUDA_TRY(cudaEventRecord(c.ev[EV_END], s));
+    mark_call_end(c, s);
     CUDA_TRY(cudaEventSynchronize(c.ev[EV_END]));
     CUDA_TRY(cudaEventElapsedTime(&S.total_ms, c.ev[EV_START], c.ev[EV_END]));
     CUDA_TRY(cudaEventElapsedTime(&S.sort_ms, c.ev[EV_START], c.ev[EV_SORTED]));    // upload + crossings + sort
@@ -1560,10 +1585,12 @@ static void sparse_build_array(const rz_context* ctx, uint64_t n_bands, const ui
     const uint32_t n = (uint32_t)n64;
     const bool out_dev = (ctx->flags & RZ_FLAG_OUT_ON_DEVICE) != 0;
 
+    DeviceGuard guard;
     DeviceCtx& c = device_ctx(ctx->device);
     std::lock_guard<std::mutex> lk(c.mu);
     CUDA_TRY(cudaSetDevice(c.dev));
     cudaStream_t s = ctx->stream ? (cudaStream_t)ctx->stream : c.stream;
+    order_after_previous_call(c, s);
     uint32_t tile_w = FILL_MAX_TILE_W;
     while (tile_w / 2 >= ri.ncols && tile_w > 1) tile_w /= 2;
     const uint32_t tile_shift = bits_for(tile_w);
@@ -1632,6 +1659,7 @@ static void sparse_build_array(const rz_context* ctx, uint64_t n_bands, const ui
     launches += 2;
     CUDA_TRY(cudaGetLastError());
     if (!out_dev) CUDA_TRY(cudaMemcpyAsync(out, d_out, out_bytes, cudaMemcpyDeviceToHost, s));
+    mark_call_end(c, s);
     CUDA_TRY(cudaStreamSynchronize(s));
     if (st) {
         std::memset(st, 0, sizeof *st);
@@ -1892,6 +1920,7 @@ int rz_geoms_bounds(const rz_geoms* g, double out[4]) {
 
 int rz_geoms_upload(rz_geoms* g, int device, char* err, size_t errlen) {
     return guarded(err, errlen, [&]() {
+        rz::DeviceGuard guard;
         rz::DeviceCtx& c = rz::device_ctx(device);
         std::lock_guard<std::mutex> lk(c.mu);
         CUDA_TRY(cudaSetDevice(c.dev));
@@ -1900,9 +1929,29 @@ int rz_geoms_upload(rz_geoms* g, int device, char* err, size_t errlen) {
 }
 
 void rz_geoms_evict(rz_geoms* g) {
-    std::lock_guard<std::mutex> lk(g->mu);
-    for (auto& kv : g->dev) delete kv.second;
-    g->dev.clear();
+    // a call in flight on a device holds that device's context mutex while it uses the cached copy: take it
+    // before deleting the copy
+    rz::DeviceGuard guard;
+    std::vector<int> devs;
+    {
+        std::lock_guard<std::mutex> lk(g->mu);
+        for (auto& kv : g->dev) devs.push_back(kv.first);
+    }
+    for (int d : devs) {
+        rz::DeviceCtx* c = nullptr;
+        try {
+            c = &rz::device_ctx(d);
+        } catch (const Error&) {
+            continue;
+        }
+        std::lock_guard<std::mutex> lc(c->mu);
+        std::lock_guard<std::mutex> lk(g->mu);
+        auto it = g->dev.find(d);
+        if (it != g->dev.end()) {
+            delete it->second;
+            g->dev.erase(it);
+        }
+    }
 }
 
 void rz_geoms_free(rz_geoms* g) { delete g; }

@@ -110,6 +110,7 @@ void Flattener::coord(double x, double y) {
     p.y.push_back(y);
     p.tag.push_back(part_);
     if (seq_bounds_) bound(x, y);
+    if (!(x - x == 0.0) || !(y - y == 0.0)) g_->nonfinite = true;
     if (kind_ == RZ_PART_POLYGON) {
         double& lo = g_->part_xlo[part_];
         double& hi = g_->part_xhi[part_];
@@ -131,14 +132,16 @@ void Flattener::extents(size_t first, size_t n) {
     const double* ys = p.y.data() + first;
     if (seq_bounds_ && !geom_has_bounds_) bound(xs[0], ys[0]);  // geo's fold is seeded by the first coordinate (even a NaN one)
     const double inf = std::numeric_limits<double>::infinity();
-    double xlo = inf, xhi = -inf, ylo = inf, yhi = -inf;
+    double xlo = inf, xhi = -inf, ylo = inf, yhi = -inf, zero = 0.0;
     for (size_t i = 0; i < n; i++) {
         const double x = xs[i], y = ys[i];
         xlo = x < xlo ? x : xlo;
         xhi = x > xhi ? x : xhi;
         ylo = y < ylo ? y : ylo;
         yhi = y > yhi ? y : yhi;
+        zero += x * 0.0 + y * 0.0;  // NaN as soon as one coordinate is NaN or infinite
     }
+    if (zero != zero) g_->nonfinite = true;
     if (seq_bounds_) {  // (folding the seed coordinate in again changes nothing)
         if (xlo < gb_[0]) gb_[0] = xlo;
         if (xhi > gb_[2]) gb_[2] = xhi;

@@ -7,6 +7,7 @@
 #include <mutex>
 #include <string>
 #include <cstdlib>
+#include <cstring>
 #include <new>
 #include <sys/mman.h>
 #include <utility>
@@ -70,6 +71,30 @@ struct Pool {
 
 struct DeviceGeoms;  // rz_engine.cu
 
+// Upper bounds of the tile-binned engine's buffers for one (grid, row window, tile height): counted on the device
+// with every polygon part active the first time a geometry set meets the grid, then reused so that later calls
+// never wait for a count (rz_engine.cu).
+struct TilePlanKey {
+    uint64_t nrows, ncols;
+    double xmin, ymax, xres, yres;
+    uint32_t r0, r1, tile_r;
+    bool operator<(const TilePlanKey& o) const {
+        auto bits = [](double d) {
+            uint64_t u;
+            std::memcpy(&u, &d, 8);
+            return u;
+        };
+        const uint64_t a[9] = {nrows, ncols, bits(xmin), bits(ymax), bits(xres), bits(yres), r0, r1, tile_r};
+        const uint64_t b[9] = {o.nrows, o.ncols, bits(o.xmin), bits(o.ymax), bits(o.xres), bits(o.yres), o.r0, o.r1, o.tile_r};
+        for (int i = 0; i < 9; i++)
+            if (a[i] != b[i]) return a[i] < b[i];
+        return false;
+    }
+};
+struct TilePlan {
+    uint64_t pairs = 0, units = 0, words = 0, edge_visits = 0, cross_lb = 0;
+};
+
 }  // namespace rz
 
 // The opaque handle of include/rz_b200.h.
@@ -87,8 +112,11 @@ struct rz_geoms {
     std::vector<std::pair<void*, size_t>> pinned_ranges;  // what cudaHostRegister accepted
     bool pool0_mapped = false;  // every byte of the polygon pool is page-locked and mapped: kernels may read it in place
 
+    bool nonfinite = false;     // some coordinate is NaN or infinite (such sets never take the tile engine)
+
     std::mutex mu;
     std::map<int, rz::DeviceGeoms*> dev;  // cached device copies, by ordinal
+    std::map<rz::TilePlanKey, rz::TilePlan> tile_plans;  // guarded by mu
 
     ~rz_geoms();
 };

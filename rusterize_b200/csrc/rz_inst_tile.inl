@@ -20,10 +20,12 @@ template <> struct NanBackground<double> {
     static bool is(double v) { return v != v; }
 };
 
+// Which evaluation of the pixel-function rule a job gets (rz_tiles.cuh, MODE).  What depends on the burn VALUES
+// (all finite / none equal to the background) is decided on the device: modes 1 and 3 fall back to the generic
+// body inside the kernel.
 template <typename N, int FN>
-static void tile_launch(uint32_t, cudaStream_t s, KParams P, TileParams T, const uint32_t* tile_start,
-                        const unsigned long long* value_sorted, const uint32_t* masks, uint64_t bg, void* out,
-                        bool values_finite, bool no_value_is_bg) {
+static void tile_launch(cudaStream_t s, KParams P, TileParams T, const uint32_t* tile_start, const BlockDesc* desc,
+                        const uint32_t* masks, const TileCounters* tcnt, uint64_t bg, void* out) {
     constexpr int TR = sizeof(N) <= 4 ? 64 : 32;
     constexpr bool is_float = std::is_floating_point<N>::value;
     constexpr bool additive = FN == RZ_SUM || FN == RZ_COUNT;
@@ -38,20 +40,20 @@ static void tile_launch(uint32_t, cudaStream_t s, KParams P, TileParams T, const
     N bgv;
     std::memcpy(&bgv, &bg, sizeof(N));
     const bool bg_nan = NanBackground<N>::is(bgv);
-    if (additive && is_float && bg_nan && values_finite)  // MODE 1: masked add + touched mask (see rz_tiles.cuh)
+    if (additive && is_float && bg_nan)  // MODE 1 (when every value is finite): masked add + touched mask
         tile_apply_kernel<N, additive ? FN : RZ_SUM, TR, is_float ? 1 : 0, true><<<grid, TR * 4, smem, s>>>(
-            P, T, tile_start, value_sorted, masks, bg, (N*)out);
-    else if (additive && !is_float && bg == 0)            // MODE 2: plain masked add
+            P, T, tile_start, desc, masks, tcnt, bg, (N*)out);
+    else if (additive && !is_float && bg == 0)  // MODE 2: plain masked add
         tile_apply_kernel<N, additive ? FN : RZ_SUM, TR, is_float ? 0 : 2, false><<<grid, TR * 4, smem, s>>>(
-            P, T, tile_start, value_sorted, masks, bg, (N*)out);
-    else if (ordered && ((is_float && bg_nan && values_finite) || (!is_float && no_value_is_bg)))  // MODE 3
+            P, T, tile_start, desc, masks, tcnt, bg, (N*)out);
+    else if (ordered && (is_float ? bg_nan : true))  // MODE 3 (when no value can look like the background)
         tile_apply_kernel<N, ordered ? FN : RZ_FIRST, TR, 3, NanBackground<N>::possible><<<grid, TR * 4, smem, s>>>(
-            P, T, tile_start, value_sorted, masks, bg, (N*)out);
+            P, T, tile_start, desc, masks, tcnt, bg, (N*)out);
     else if (bg_nan)  // float dtypes with a NaN background: one comparison less per pixel
-        tile_apply_kernel<N, FN, TR, 0, NanBackground<N>::possible><<<grid, TR * 4, smem, s>>>(P, T, tile_start, value_sorted,
-                                                                                            masks, bg, (N*)out);
+        tile_apply_kernel<N, FN, TR, 0, NanBackground<N>::possible><<<grid, TR * 4, smem, s>>>(P, T, tile_start, desc, masks,
+                                                                                            tcnt, bg, (N*)out);
     else
-        tile_apply_kernel<N, FN, TR, 0, false><<<grid, TR * 4, smem, s>>>(P, T, tile_start, value_sorted, masks, bg, (N*)out);
+        tile_apply_kernel<N, FN, TR, 0, false><<<grid, TR * 4, smem, s>>>(P, T, tile_start, desc, masks, tcnt, bg, (N*)out);
 }
 template <typename N> static TileLaunch tile_for_fn(int fn) {
     switch (fn) {

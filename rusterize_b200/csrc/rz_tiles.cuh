@@ -1,30 +1,37 @@
-// rz_tiles.cuh — tile-binned polygon engine (dense output, jobs made of small polygon parts).
+// rz_tiles.cuh — tile-binned polygon engine (dense output, jobs made of polygon parts).
 //
 // The crossing-record pipeline (rz_kernels.cuh) materialises one 8-byte record per scanline crossing
 // and sorts them: ~11 passes over 9 GB at BASELINE config 4.  When parts are small compared with the
 // raster it is far cheaper never to materialise crossings.  Parts are binned to tiles of 128 columns x
 // TILE_R rows and the scanline job is split into two embarrassingly parallel kernels:
 //
-//   tile_bin (x2)      per part: the tiles its bounding box overlaps; emits the mask units - (part, run of
-//                      tile rows) handled by one warp - and the (tile, block) records, stably sorted by tile so
-//                      every tile sees its parts in burn order; block_pos then gives every (part, tile) block
-//                      its position in tile order.
+//   tile_bin (x2)      per part: the tiles its bounding box overlaps.  Pass 0 counts (part,tile) pairs, mask
+//                      units and mask words per part; one look-back scan turns the three counts into offsets;
+//                      pass 1 emits the mask units - (part, run of tile rows) handled by one warp - one
+//                      descriptor per (part,tile) BLOCK and the [tile | block] records, which are then stably
+//                      sorted by tile so that every tile sees its parts in burn order.
 //   tile_mask          one WARP per mask unit: reads the part's ring vertices from the world-coordinate pool,
 //                      31 edges at a time, transforms them (edges.rs:94-97), finds with integer row compares
 //                      the edges that cross the unit's rows (edges.rs:27-46, 90-110), computes their crossings
 //                      (edges.rs:50-55, warp-flattened so all lanes stay busy) and XORs one bit per crossing
-//                      into a shared-memory toggle mask spanning the part's tile columns; a prefix-XOR along
-//                      each row turns it into the even-odd INSIDE mask (== sorting and pairing the crossings,
-//                      burners.rs:302-315), written as one TILE_R x 128-bit block per (part, tile).
+//                      into a shared-memory toggle mask spanning the part's 32-column words; a prefix-XOR
+//                      along each row turns it into the even-odd INSIDE mask (== sorting and pairing the
+//                      crossings, burners.rs:302-315).  The mask is stored COMPACT: a block holds only the
+//                      rows and the 32-column words of its tile that the part's box covers, and the blocks of
+//                      a part are consecutive in memory (config 4: ~1 GB instead of 4.3 GB of full
+//                      64 x 128-bit blocks).
 //   tile_apply         one CTA per 8 tiles of a tile row, pixels in REGISTERS (initialised to the background,
 //                      flushed once).  Each warp owns 8 rows and, with no synchronisation with the other
-//                      warps, walks the tile's parts in burn order: one coalesced 128-byte load brings the
-//                      part's inside mask, lane = (row, 32-column word), and the lane applies the part's value
-//                      to its own 32 pixels with the reference's pixel-function rule
+//                      warps, walks the tile's block descriptors in burn order: lane = (row, 32-column word)
+//                      fetches its word of the part's inside mask (if the block covers it) and applies the
+//                      part's value to its own 32 pixels with the reference's pixel-function rule
 //                      (pixel_functions.rs:56-123).
 //
 // Parts are applied strictly in burn order per pixel, so every pixel function stays bit-exact, and every
-// output byte is written to HBM once.
+// output byte is written to HBM once.  Every count the host would need in the middle of a call (pairs, units,
+// mask words, "some value is NaN") stays on the device: buffers are sized from an upper bound cached per
+// (geometry set, grid) and the kernels read the actual counts from TileCounters, so a steady-state call has
+// no host synchronisation between its first and its last kernel.
 #pragma once
 
 #include <type_traits>
@@ -35,7 +42,7 @@ namespace rz {
 
 constexpr uint32_t TILE_C = 128;           // columns per tile = 4 mask words per row
 constexpr uint32_t MASK_MAX_WORDS = 16;    // tile_mask: widest toggle-mask chunk kept in shared memory (512 columns)
-constexpr uint32_t MASK_SMEM_WORDS = 1280; // tile_mask: toggle-mask words per warp (rows x (chunk words + 1 pad))
+constexpr uint32_t MASK_SMEM_WORDS = 1280; // tile_mask: toggle-mask words per warp (rows x chunk stride)
 constexpr int MASK_WARPS = 4;
 constexpr uint32_t MASK_UNITS = 4;  // consecutive mask units built by one warp
 constexpr uint32_t VROW_RING_END = 0x80000000u;  // vertex tag: "last vertex of its ring"
@@ -44,38 +51,57 @@ struct TileParams {
     uint32_t tile_r;           // rows per tile (64, or 32 for 8-byte dtypes)
     uint32_t n_tc, n_tr;       // tile grid of one band in this window
     uint32_t n_tiles;          // n_bands * n_tr * n_tc
-    uint32_t part_bits;
+    uint32_t block_bits;       // record = [tile | block index]
     uint32_t win_row_off, out_rows;
     uint32_t vec_ok;
+    uint32_t cap_pairs, cap_units;  // capacity of the record / unit arrays (upper bounds cached on the host)
 };
 
 struct TileCounters {
-    unsigned long long pairs;        // (part, tile) pairs
-    unsigned long long row_pairs;    // mask units: (part, run of tile rows) handled by one tile_mask warp
+    unsigned long long pairs;        // (part, tile) pairs = mask blocks
+    unsigned long long units;        // mask units: (part, run of tile rows) handled by one tile_mask warp
+    unsigned long long words;        // 32-bit words of all compact mask blocks (each block padded to 8 words)
     unsigned long long edge_visits;  // sum over parts of units x column chunks x ring vertices
     unsigned long long cross_lb;     // lower bound of the crossing count: 2 per part row (a closed ring crosses a
                                      // row's centre line an even number of times, at least twice)
     unsigned int nonfinite;          // some part burns a NaN / infinite value (float dtypes)
     unsigned int eq_bg;              // some part burns a value whose bits equal the background's
+    unsigned int overflow;           // a count exceeded its cached upper bound (never expected; checked by the host
+                                     // whenever it synchronises anyway)
+    unsigned int scan_ticket;        // block ticket of the look-back scan
 };
 
-// where a part's inside-mask blocks live: block(tr, tc) = first_block + (tr - tr0) * ntc + (tc - tc0)
-struct PartTile {
-    unsigned long long first_block;
+// One (part, tile) block of the inside mask: rows [row_off, row_off + nrows) x words [w_off, w_off + nw) of the
+// tile, row-major, at word offset `woff` of the mask array; plus the value its part burns.
+struct alignas(16) BlockDesc {
+    unsigned long long value_bits;
+    uint32_t woff;
+    uint32_t geom;  // row_off | nrows << 8 | w_off << 16 | nw << 20
+};
+__device__ __forceinline__ uint32_t pack_geom(uint32_t row_off, uint32_t nrows, uint32_t w_off, uint32_t nw) {
+    return row_off | (nrows << 8) | (w_off << 16) | (nw << 20);
+}
+
+// where a part's blocks live: block(tr, tc) = first_block + (tr - tr0) * ntc + (tc - tc0)
+struct alignas(8) PartTile {
+    uint32_t first_block;
     uint32_t tr0, tc0;
     uint32_t ntr, ntc;
     uint32_t r_lo, r_hi;  // rows the part can fill (absolute, clamped to the window)
+    uint32_t w_lo, w_hi;  // 32-column words the part can fill (absolute)
+    uint32_t pad;
 };
 
 // A mask unit = the tile rows [tr, tr + k) of one part, built by one tile_mask warp: as many tile rows as
 // the part's rows in them fit the warp's shared-memory toggle mask.  Packed [tr:26 | k:6 | part:32].
-__device__ __forceinline__ uint32_t mask_row_capacity(uint32_t ntc) {
-    return MASK_SMEM_WORDS / (min(ntc * 4u, MASK_MAX_WORDS) + 1u);
+__host__ __device__ __forceinline__ uint32_t mask_stride(uint32_t nw) { return nw | 1u; }  // odd: rows spread over banks
+__device__ __forceinline__ uint32_t mask_row_capacity(uint32_t n_words) {
+    return MASK_SMEM_WORDS / mask_stride(min(n_words, MASK_MAX_WORDS));
 }
 template <typename F>
 __device__ __forceinline__ uint32_t for_each_mask_unit(const KParams& P, uint32_t tile_r, uint32_t tr0, uint32_t ntr,
-                                                       uint32_t ntc, uint32_t r_lo, uint32_t r_hi, F&& emit) {
-    const uint32_t cap = mask_row_capacity(ntc);
+                                                       uint32_t n_words, uint32_t r_lo, uint32_t r_hi, F&& emit) {
+    const uint32_t cap = mask_row_capacity(n_words);
     uint32_t n = 0, tr = tr0;
     const uint32_t tr_end = tr0 + ntr;
     while (tr < tr_end) {
@@ -87,6 +113,12 @@ __device__ __forceinline__ uint32_t for_each_mask_unit(const KParams& P, uint32_
         n++;
     }
     return n;
+}
+// Column chunks of a part's word range [w_lo, w_hi): the first starts at w_lo, the following ones at multiples
+// of 16 words from w_lo's tile, so that a tile column (4 words) never straddles two chunks.
+__device__ __forceinline__ uint32_t next_chunk(uint32_t a) { return (a & ~3u) + MASK_MAX_WORDS; }
+__device__ __forceinline__ uint32_t n_chunks(uint32_t w_lo, uint32_t w_hi) {
+    return w_hi > w_lo ? (w_hi - (w_lo & ~3u) + MASK_MAX_WORDS - 1) / MASK_MAX_WORDS : 0u;
 }
 
 // Rust `f64 as usize` after floor / ceil, then min(., lim): cvt.rmi / cvt.rpi saturate (negatives and NaN
@@ -113,52 +145,93 @@ __device__ __forceinline__ bool part_pixel_box(const KParams& P, double xlo, dou
     return r_hi > r_lo && c_hi > c_lo && c_lo < P.ncols;
 }
 
-// mode 0: per part the number of (part,tile) pairs and of (part,tile-row) pairs (+ totals);
-// mode 1: with the scanned offsets, fill PartTile and emit the row-pair list and the tile records
-// [tile | block], block = index of the (part,tile) pair's inside-mask block.
+// rows / words of tile (tr, tc) covered by a part's box; returns the block's size in words, padded to 8
+__device__ __forceinline__ uint32_t block_geom(const KParams& P, uint32_t tile_r, uint32_t tr, uint32_t tc, uint32_t r_lo,
+                                               uint32_t r_hi, uint32_t w_lo, uint32_t w_hi, uint32_t& geom) {
+    const uint32_t t0 = P.win_r0 + tr * tile_r;
+    const uint32_t ra = max(r_lo, t0), rb = min(r_hi, t0 + tile_r);
+    const uint32_t wa = max(w_lo, tc * 4u), wb = min(w_hi, tc * 4u + 4u);
+    geom = pack_geom(ra - t0, rb - ra, wa - tc * 4u, wb - wa);
+    return ((rb - ra) * (wb - wa) + 7u) & ~7u;
+}
+
+// mode 0: per part the number of blocks, of mask units and of mask words (+ totals into TileCounters);
+//         with ignore_band every polygon part counts (upper bounds for the host's plan cache);
+// mode 1: with the scanned offsets, fill PartTile and emit the unit list, the block descriptors (part order)
+//         and the tile records [tile | block].
 static __global__ void tile_bin_kernel(KParams P, TileParams T, const PartInfo* __restrict__ info,
+                                const uint8_t* __restrict__ part_kind,
                                 const double* __restrict__ xlo, const double* __restrict__ xhi,
                                 const double* __restrict__ ylo, const double* __restrict__ yhi,
                                 const uint32_t* __restrict__ vbeg, const uint32_t* __restrict__ vend,
-                                uint32_t* __restrict__ cnt_tiles, uint32_t* __restrict__ cnt_rows,
-                                const unsigned long long* __restrict__ off_tiles,
-                                const unsigned long long* __restrict__ off_rows, PartTile* __restrict__ pt,
-                                uint64_t* __restrict__ row_pairs, uint64_t* __restrict__ recs,
-                                unsigned long long* __restrict__ block_value, uint32_t block_bits,
-                                TileCounters* __restrict__ tc, int mode, int float_bytes, unsigned long long bg_bits,
-                                unsigned long long value_mask) {
+                                uint32_t* __restrict__ cnt, /* [3][n_parts]: blocks, units, words */
+                                const uint32_t* __restrict__ off, /* [3][n_parts] exclusive prefixes */
+                                PartTile* __restrict__ pt, uint64_t* __restrict__ units, uint64_t* __restrict__ recs,
+                                BlockDesc* __restrict__ desc, TileCounters* __restrict__ tc, int mode, int ignore_band,
+                                int float_bytes, unsigned long long bg_bits, unsigned long long value_mask) {
     const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
-    uint32_t ntr = 0, ntc = 0, n_units = 0, r_lo = 0, r_hi = 0, c_lo = 0, c_hi = 0;
+    uint32_t ntr = 0, ntc = 0, n_units = 0, n_words = 0, r_lo = 0, r_hi = 0, c_lo = 0, c_hi = 0, w_lo = 0, w_hi = 0;
     if (p < P.n_parts) {
-        const int32_t band = info[p].band;
-        if (band >= 0 && vend[p] > vbeg[p] + 1 &&
+        const int32_t band = ignore_band ? 0 : info[p].band;
+        if (band >= 0 && part_kind[p] == 0 && vend[p] > vbeg[p] + 1 &&
             part_pixel_box(P, xlo[p], xhi[p], ylo[p], yhi[p], r_lo, r_hi, c_lo, c_hi)) {
             const uint32_t tr0 = (r_lo - P.win_r0) / T.tile_r, tr1 = (r_hi - 1 - P.win_r0) / T.tile_r;
-            const uint32_t tc0 = c_lo / TILE_C, tc1 = (c_hi - 1) / TILE_C;
+            w_lo = c_lo >> 5;
+            w_hi = ((c_hi - 1) >> 5) + 1;
+            const uint32_t tc0 = w_lo >> 2, tc1 = (w_hi - 1) >> 2;
             ntr = tr1 - tr0 + 1;
             ntc = tc1 - tc0 + 1;
             if (mode == 0) {
-                n_units = for_each_mask_unit(P, T.tile_r, tr0, ntr, ntc, r_lo, r_hi, [](uint32_t, uint32_t) {});
-            } else {
-                PartTile q;
-                q.first_block = off_tiles[p];
-                q.tr0 = tr0;
-                q.tc0 = tc0;
-                q.ntr = ntr;
-                q.ntc = ntc;
-                q.r_lo = r_lo;
-                q.r_hi = r_hi;
-                pt[p] = q;
-                unsigned long long o = off_tiles[p], orow = off_rows[p];
-                for_each_mask_unit(P, T.tile_r, tr0, ntr, ntc, r_lo, r_hi, [&](uint32_t tr, uint32_t k) {
-                    row_pairs[orow++] = ((uint64_t)tr << 38) | ((uint64_t)k << 32) | p;
-                });
+                n_units = for_each_mask_unit(P, T.tile_r, tr0, ntr, w_hi - w_lo, r_lo, r_hi, [](uint32_t, uint32_t) {});
+                // words: a tile row's blocks hold rows(tr) x words(tc), each padded to 8 words
                 for (uint32_t tr = tr0; tr <= tr1; tr++) {
-                    for (uint32_t tcol = tc0; tcol <= tc1; tcol++) {
-                        const uint64_t tile = ((uint64_t)band * T.n_tr + tr) * T.n_tc + tcol;
-                        block_value[o] = info[p].value_bits;  // tile_apply reads the value by block, not by part
-                        recs[o] = (tile << block_bits) | o;   // block index ascends with the part id: burn order
-                        o++;
+                    const uint32_t t0 = P.win_r0 + tr * T.tile_r;
+                    const uint32_t rows = min(r_hi, t0 + T.tile_r) - max(r_lo, t0);
+                    if (ntc == 1) {
+                        n_words += (rows * (w_hi - w_lo) + 7u) & ~7u;
+                    } else {
+                        n_words += (rows * ((tc0 + 1) * 4u - w_lo) + 7u) & ~7u;
+                        n_words += (rows * (w_hi - tc1 * 4u) + 7u) & ~7u;
+                        n_words += (ntc - 2) * ((rows * 4u + 7u) & ~7u);
+                    }
+                }
+            } else {
+                const uint32_t o_blk = off[p], o_unit = off[P.n_parts + p];
+                uint32_t woff = off[2 * (size_t)P.n_parts + p];
+                if ((unsigned long long)o_blk + (unsigned long long)ntr * ntc > T.cap_pairs) {
+                    atomicOr(&tc->overflow, 1u);
+                } else {
+                    PartTile q;
+                    q.first_block = o_blk;
+                    q.tr0 = tr0;
+                    q.tc0 = tc0;
+                    q.ntr = ntr;
+                    q.ntc = ntc;
+                    q.r_lo = r_lo;
+                    q.r_hi = r_hi;
+                    q.w_lo = w_lo;
+                    q.w_hi = w_hi;
+                    q.pad = 0;
+                    pt[p] = q;
+                    uint32_t ou = o_unit;
+                    for_each_mask_unit(P, T.tile_r, tr0, ntr, w_hi - w_lo, r_lo, r_hi, [&](uint32_t tr, uint32_t k) {
+                        if (ou < T.cap_units) units[ou] = ((uint64_t)tr << 38) | ((uint64_t)k << 32) | p;
+                        else atomicOr(&tc->overflow, 1u);
+                        ou++;
+                    });
+                    const unsigned long long vb = info[p].value_bits;
+                    uint32_t o = o_blk;
+                    for (uint32_t tr = tr0; tr <= tr1; tr++) {
+                        for (uint32_t tcol = tc0; tcol <= tc1; tcol++) {
+                            const uint64_t tile = ((uint64_t)band * T.n_tr + tr) * T.n_tc + tcol;
+                            BlockDesc d;
+                            d.value_bits = vb;  // tile_apply reads the value with the block, not by part
+                            d.woff = woff;
+                            woff += block_geom(P, T.tile_r, tr, tcol, r_lo, r_hi, w_lo, w_hi, d.geom);
+                            desc[o] = d;
+                            recs[o] = (tile << T.block_bits) | o;  // block index ascends with the part id: burn order
+                            o++;
+                        }
                     }
                 }
             }
@@ -166,48 +239,154 @@ static __global__ void tile_bin_kernel(KParams P, TileParams T, const PartInfo* 
     }
     if (mode == 0) {
         if (p < P.n_parts) {
-            cnt_tiles[p] = ntr * ntc;
-            cnt_rows[p] = n_units;
-            if (float_bytes) {  // exponent all ones: NaN or infinity (tile_apply's additive mode needs finite values)
+            cnt[p] = ntr * ntc;
+            cnt[P.n_parts + p] = n_units;
+            cnt[2 * (size_t)P.n_parts + p] = n_words;
+            if (!ignore_band && ntr) {
                 const unsigned long long vb = info[p].value_bits;
-                const bool bad = float_bytes == 4 ? ((vb >> 23) & 0xffu) == 0xffu : ((vb >> 52) & 0x7ffu) == 0x7ffu;
-                if (bad && info[p].band >= 0) atomicOr(&tc->nonfinite, 1u);
+                if (float_bytes) {  // exponent all ones: NaN or infinity (tile_apply's additive mode needs finite values)
+                    const bool bad = float_bytes == 4 ? ((vb >> 23) & 0xffu) == 0xffu : ((vb >> 52) & 0x7ffu) == 0x7ffu;
+                    if (bad) atomicOr(&tc->nonfinite, 1u);
+                }
+                if (((vb ^ bg_bits) & value_mask) == 0) atomicOr(&tc->eq_bg, 1u);
             }
-            if (info[p].band >= 0 && ((info[p].value_bits ^ bg_bits) & value_mask) == 0) atomicOr(&tc->eq_bg, 1u);
         }
-        const uint32_t chunks = (ntc * 4 + MASK_MAX_WORDS - 1) / MASK_MAX_WORDS;
-        unsigned long long pairs = (unsigned long long)ntr * ntc, rows = n_units,
-                           visits = (unsigned long long)n_units * chunks * (p < P.n_parts ? vend[p] - vbeg[p] : 0u),
+        unsigned long long pairs = (unsigned long long)ntr * ntc, un = n_units, words = n_words,
+                           visits = (unsigned long long)n_units * n_chunks(w_lo, w_hi) * (ntr ? vend[p] - vbeg[p] : 0u),
                            cross = ntr ? 2ull * (r_hi - r_lo) : 0ull;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             pairs += __shfl_down_sync(0xffffffffu, pairs, o);
-            rows += __shfl_down_sync(0xffffffffu, rows, o);
+            un += __shfl_down_sync(0xffffffffu, un, o);
+            words += __shfl_down_sync(0xffffffffu, words, o);
             visits += __shfl_down_sync(0xffffffffu, visits, o);
             cross += __shfl_down_sync(0xffffffffu, cross, o);
         }
         if (lane_id() == 0 && pairs) {
             atomicAdd(&tc->pairs, pairs);
-            atomicAdd(&tc->row_pairs, rows);
+            atomicAdd(&tc->units, un);
+            atomicAdd(&tc->words, words);
             atomicAdd(&tc->edge_visits, visits);
             atomicAdd(&tc->cross_lb, cross);
         }
     }
 }
 
-struct InU32 {
-    const uint32_t* v;
-    __device__ unsigned long long operator()(uint32_t i) const { return v[i]; }
-};
+// ---------------------------------------------------------------------------------------------
+// single-launch exclusive scan of K u32 arrays (decoupled look-back)
+// ---------------------------------------------------------------------------------------------
+// in / out are [K][n]; status holds K 64-bit words per block: flag (2 top bits: 1 = block aggregate, 2 = inclusive
+// prefix) | value, zeroed before the launch together with the ticket.  Blocks take their index from a ticket so
+// that a block only ever waits for blocks that already run.  Totals must stay below 2^32 (checked by the host
+// against its cached upper bounds).
+constexpr int LB_THREADS = 256;
+constexpr int LB_ITEMS = 8;
+constexpr int LB_TILE = LB_THREADS * LB_ITEMS;
+constexpr unsigned long long LB_FLAG_A = 1ull << 62, LB_FLAG_P = 2ull << 62, LB_VALUE = (1ull << 62) - 1ull;
+
+template <int K>
+static __global__ void __launch_bounds__(LB_THREADS)
+scan_lookback_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, uint32_t n,
+                     unsigned long long* __restrict__ status, unsigned int* __restrict__ ticket) {
+    __shared__ uint32_t s_bid;
+    __shared__ uint32_t s_warp[K][LB_THREADS / 32];
+    __shared__ uint32_t s_base[K];
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    if (tid == 0) s_bid = atomicAdd(ticket, 1u);
+    __syncthreads();
+    const uint32_t bid = s_bid;
+    const uint32_t i0 = bid * LB_TILE + tid * LB_ITEMS;
+    uint32_t v[K][LB_ITEMS], tsum[K];
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+        tsum[k] = 0;
+#pragma unroll
+        for (int j = 0; j < LB_ITEMS; j++) {
+            v[k][j] = i0 + j < n ? in[(size_t)k * n + i0 + j] : 0u;
+            tsum[k] += v[k][j];
+        }
+    }
+    // exclusive scan of the thread sums inside the block
+    uint32_t texc[K];
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+        uint32_t inc = tsum[k];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t up = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= (uint32_t)o) inc += up;
+        }
+        if (lane == 31) s_warp[k][warp] = inc;
+        texc[k] = inc - tsum[k];
+    }
+    __syncthreads();
+    if (warp < K) {  // warp k: block aggregate of array k, then the look-back
+        const int k = warp;
+        const uint32_t wv = lane < LB_THREADS / 32 ? s_warp[k][lane] : 0u;
+        uint32_t inc = wv;
+#pragma unroll
+        for (int o = 1; o < LB_THREADS / 32; o <<= 1) {
+            const uint32_t up = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= (uint32_t)o) inc += up;
+        }
+        __syncwarp();
+        if (lane < LB_THREADS / 32) s_warp[k][lane] = inc - wv;  // exclusive warp bases
+        const uint32_t agg = __shfl_sync(0xffffffffu, inc, LB_THREADS / 32 - 1);
+        volatile unsigned long long* st = status + k;
+        if (lane == 0) {
+            st[(size_t)bid * K] = (bid == 0 ? LB_FLAG_P : LB_FLAG_A) | agg;
+            __threadfence();
+        }
+        unsigned long long prefix = 0;
+        if (bid > 0) {
+            long long j = (long long)bid - 1 - (long long)lane;  // this lane's predecessor in the current window of 32
+            while (true) {
+                unsigned long long s = LB_FLAG_P;  // before block 0: an empty inclusive prefix
+                if (j >= 0) {
+                    do {
+                        s = st[(size_t)j * K];
+                    } while ((s >> 62) == 0);
+                }
+                const uint32_t is_p = __ballot_sync(0xffffffffu, (s >> 62) == 2);
+                // sum the values of the lanes up to and including the nearest inclusive prefix
+                const uint32_t first_p = is_p ? (uint32_t)__ffs(is_p) - 1u : 31u;
+                unsigned long long val = lane <= first_p ? (s & LB_VALUE) : 0ull;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) val += __shfl_down_sync(0xffffffffu, val, o);
+                prefix += __shfl_sync(0xffffffffu, val, 0);
+                if (is_p) break;
+                j -= 32;
+            }
+            if (lane == 0) {
+                st[(size_t)bid * K] = LB_FLAG_P | ((prefix + agg) & LB_VALUE);
+                __threadfence();
+            }
+        }
+        if (lane == 0) s_base[k] = (uint32_t)prefix;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+        uint32_t run = s_base[k] + s_warp[k][warp] + texc[k];
+#pragma unroll
+        for (int j = 0; j < LB_ITEMS; j++) {
+            if (i0 + j < n) out[(size_t)k * n + i0 + j] = run;
+            run += v[k][j];
+        }
+    }
+}
 
 // One ring edge (pixel-space vertices): its crossing with a row's centre line.
 struct TileEdge {
     double x_top, y_top, dxdy;
 };
-// ... as tile_mask keeps it in shared memory: plus its first row in the unit and the index of its first crossing
+// ... as tile_mask keeps it in shared memory.  Crossing kk of the batch belongs to this edge when
+// pre <= kk < pre + cnt; it lies on row (lo + kk - pre), whose centre ordinate row + 0.5 is cyb + kk (exact: small
+// integers and halves) and whose index relative to the unit's first row is ib + kk.
 struct alignas(16) MaskEdge {
-    double x_top, y_top, dxdy;
-    uint32_t lo, pre;
+    double x_top, y_top, dxdy, cyb;
+    int32_t ib;
+    uint32_t pad[3];
 };
 // false when the reference skips the edge as horizontal (edges.rs:100)
 __device__ __forceinline__ bool tile_edge_slope(double x0, double y0, double x1, double y1, TileEdge& e) {
@@ -225,91 +404,16 @@ __device__ __forceinline__ uint32_t tile_edge_col(const KParams& P, const TileEd
     return floor_sat_u32(__dadd_rn(xi, 0.5), P.ncols);                                // burners.rs:310-311
 }
 
-// ---------------------------------------------------------------------------------------------
-// streamed upload: the polygon pool is pulled from page-locked host memory window by window
-// ---------------------------------------------------------------------------------------------
-// An end-to-end call is bound by PCIe: geometry host->device, then the raster device->host.  The two
-// directions are independent, so instead of uploading the whole pool first, every polygon part is assigned
-// to the first row window of the call that its rows touch ("bucket"; parts touching none go to a last one),
-// and the parts of bucket b are copied by a kernel that reads the mapped host arrays directly, right before
-// window b is computed - while the copy stream is still sending window b-1 to the host.
-static __global__ void part_bucket_kernel(KParams P, const uint8_t* __restrict__ part_kind, const double* __restrict__ ylo,
-                                   const double* __restrict__ yhi, uint32_t shard_r0, uint32_t shard_r1,
-                                   uint32_t win_rows, uint32_t n_buckets, uint32_t* __restrict__ bucket_of,
-                                   unsigned int* __restrict__ cnt) {
-    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= P.n_parts) return;
-    uint32_t b = 0xffffffffu;  // not a polygon part
-    if (part_kind[p] == 0) {
-        const uint32_t lo = max(vertex_row(P, px_y(P, yhi[p])), shard_r0);
-        const uint32_t hi = min(vertex_row(P, px_y(P, ylo[p])), shard_r1);
-        b = hi > lo ? min((lo - shard_r0) / win_rows, n_buckets - 1) : n_buckets;
-        atomicAdd(&cnt[b], 1u);
-    }
-    bucket_of[p] = b;
-}
-// cnt[0 .. n_buckets] -> off[0 .. n_buckets + 1] (exclusive), cursors reset; a handful of buckets: one thread
-static __global__ void bucket_scan_kernel(unsigned int* __restrict__ cnt, unsigned int* __restrict__ off, uint32_t n) {
-    unsigned int run = 0;
-    for (uint32_t i = 0; i < n; i++) {
-        off[i] = run;
-        run += cnt[i];
-        cnt[i] = 0;
-    }
-    off[n] = run;
-}
-static __global__ void bucket_scatter_kernel(uint32_t n_parts, const uint32_t* __restrict__ bucket_of,
-                                      const unsigned int* __restrict__ off, unsigned int* __restrict__ cursor,
-                                      uint32_t* __restrict__ order) {
-    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= n_parts) return;
-    const uint32_t b = bucket_of[p];
-    if (b != 0xffffffffu) order[off[b] + atomicAdd(&cursor[b], 1u)] = p;
-}
-// one CTA per part: its vertex range from the mapped host arrays (PCIe reads) to the device pool
-static __global__ void __launch_bounds__(128)
-pull_parts_kernel(const uint32_t* __restrict__ order, uint32_t n, const uint32_t* __restrict__ vbeg,
-                  const uint32_t* __restrict__ vend, const double* __restrict__ hx, const double* __restrict__ hy,
-                  const uint32_t* __restrict__ htag, double* __restrict__ dx, double* __restrict__ dy,
-                  uint32_t* __restrict__ dtag) {
-    if (blockIdx.x >= n) return;
-    const uint32_t p = order[blockIdx.x];
-    const uint32_t e = vend[p];
-    for (uint32_t i = vbeg[p] + threadIdx.x; i < e; i += 4 * 128) {  // four independent loads per array in flight
-        double a[4], b[4];
-        uint32_t t[4];
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            const uint32_t j = i + k * 128;
-            if (j < e) {
-                a[k] = __ldcs(hx + j);
-                b[k] = __ldcs(hy + j);
-                t[k] = __ldcs(htag + j);
-            }
-        }
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            const uint32_t j = i + k * 128;
-            if (j < e) {
-                dx[j] = a[k];
-                dy[j] = b[k];
-                dtag[j] = t[k];
-            }
-        }
-    }
-}
-
-// After the stable sort of the [tile | block] records: where every inside-mask block lives.  tile_mask writes
-// block b at position pos[b] of the mask array, i.e. in tile order, and the value of its part goes to the
-// same position, so that tile_apply streams a tile's blocks from consecutive memory with no indirection.
-static __global__ void block_pos_kernel(const uint64_t* __restrict__ recs, uint32_t n, uint32_t block_bits,
-                                 const unsigned long long* __restrict__ block_value, uint32_t* __restrict__ pos,
-                                 unsigned long long* __restrict__ value_sorted) {
+// After the stable sort of the [tile | block] records: the block descriptors in tile order, so that tile_apply
+// streams a tile's descriptors from consecutive memory.  Records beyond the actual count are 0xff.. fillers.
+static __global__ void block_pos_kernel(const uint64_t* __restrict__ recs, const TileCounters* __restrict__ tc,
+                                 uint32_t block_bits, const BlockDesc* __restrict__ desc,
+                                 BlockDesc* __restrict__ desc_sorted) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+    if (i >= (uint32_t)tc->pairs) return;
     const uint32_t blk = (uint32_t)(recs[i] & ((1ull << block_bits) - 1ull));
-    pos[blk] = i;
-    value_sorted[i] = block_value[blk];
+    const uint4 d = *reinterpret_cast<const uint4*>(desc + blk);
+    *reinterpret_cast<uint4*>(desc_sorted + i) = d;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -319,16 +423,18 @@ static __global__ void block_pos_kernel(const uint64_t* __restrict__ recs, uint3
 // shorter than f64::EPSILON in y (edges.rs:100) while still straddling a pixel centre.  Pixel-centre
 // ordinates k+0.5 with k >= 1 are spaced >= EPSILON apart, so that can only happen on raster row 0
 // (centre 0.5): only that row's crossing count is tracked, and an odd row 0 drops its largest column like
-// chunks_exact(2) drops the unpaired tail (burners.rs:305).
+// chunks_exact(2) drops the unpaired tail (burners.rs:305).  (Non-finite coordinates would break this argument:
+// geometry sets holding any are never given to this engine.)
 template <int TILE_R>
 static __global__ void __launch_bounds__(MASK_WARPS * 32, 8)
-tile_mask_kernel(KParams P, TileParams T, const uint64_t* __restrict__ units, uint32_t n_units,
+tile_mask_kernel(KParams P, TileParams T, const uint64_t* __restrict__ units, const TileCounters* __restrict__ tcnt,
                  const PartTile* __restrict__ pt, const uint32_t* __restrict__ vbeg, const uint32_t* __restrict__ vend,
                  const double* __restrict__ wx, const double* __restrict__ wy, const uint32_t* __restrict__ tag,
-                 const uint32_t* __restrict__ pos, uint32_t* __restrict__ masks) {
+                 const BlockDesc* __restrict__ desc, uint32_t* __restrict__ masks) {
     __shared__ uint32_t s_mask[MASK_WARPS][MASK_SMEM_WORDS];
     __shared__ MaskEdge s_edge[MASK_WARPS][32];  // the batch's active edges, compacted
     const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
+    const uint32_t n_units = min((uint32_t)tcnt->units, T.cap_units);
     // A warp builds MASK_UNITS consecutive units (units are in part order, so are their vertices).  While it works
     // on one it asks the L2 for the next one's part record and vertex range: a unit lives for ~20 us and would
     // otherwise start with three dependent global loads.
@@ -352,13 +458,12 @@ tile_mask_kernel(KParams P, TileParams T, const uint64_t* __restrict__ units, ui
     const uint32_t row_start = max(q.r_lo, t0), row_end = min(q.r_hi, t0 + k_tr * TILE_R);
     const uint32_t n_rows = row_end - row_start;
     uint32_t* mask = s_mask[warp];
-    const uint32_t words_total = q.ntc * 4;
     const uint32_t lt_mask = (1u << lane) - 1u, le_mask = lt_mask | (1u << lane);
 
-    for (uint32_t w0 = 0; w0 < words_total; w0 += MASK_MAX_WORDS) {  // one pass per 512-column chunk
-        const uint32_t nw = min(MASK_MAX_WORDS, words_total - w0);
-        const uint32_t stride = nw + 1;                               // odd or padded: rows spread over banks
-        const uint32_t c0 = q.tc0 * TILE_C + w0 * 32;                 // first pixel column of the chunk
+    for (uint32_t wa = q.w_lo; wa < q.w_hi; wa = next_chunk(wa)) {  // one pass per chunk of <= 512 columns
+        const uint32_t nw = min(next_chunk(wa), q.w_hi) - wa;
+        const uint32_t stride = mask_stride(nw);
+        const uint32_t c0 = wa * 32;  // first pixel column of the chunk
         const uint32_t c1 = min(c0 + nw * 32, P.ncols);
         for (uint32_t i = lane; i < n_rows * stride; i += 32) mask[i] = 0;
         __syncwarp();
@@ -406,14 +511,12 @@ tile_mask_kernel(KParams P, TileParams T, const uint64_t* __restrict__ units, ui
             const uint32_t wtot = __shfl_sync(0xffffffffu, inc, 31);
             const uint32_t pre = inc - cnt;
             if (cnt) {  // active edges are compacted: slot = rank among the batch's active edges
-                const uint32_t slot = __popc(act & lt_mask);
-                MaskEdge me;
-                me.x_top = e.x_top;
-                me.y_top = e.y_top;
-                me.dxdy = e.dxdy;
-                me.lo = lo;
-                me.pre = pre;
-                s_edge[warp][slot] = me;
+                MaskEdge* me = &s_edge[warp][__popc(act & lt_mask)];
+                // row + 0.5 of crossing kk is (lo + 0.5 - pre) + kk: all terms are small integers or halves, exact
+                const double cyb = __dsub_rn(__dadd_rn((double)lo, 0.5), (double)pre);
+                *reinterpret_cast<double2*>(&me->x_top) = make_double2(e.x_top, e.y_top);
+                *reinterpret_cast<double2*>(&me->dxdy) = make_double2(e.dxdy, cyb);
+                me->ib = (int32_t)(lo - row_start) - (int32_t)pre;
             }
             __syncwarp();
             // all lanes share the batch's crossings evenly: crossing kk belongs to the last active edge whose
@@ -421,18 +524,17 @@ tile_mask_kernel(KParams P, TileParams T, const uint64_t* __restrict__ units, ui
             // Two chunks of 32 crossings per iteration, evaluated without branches up to the atomic, so that the
             // two dependent f64 chains (shared-memory load -> 5 double ops -> convert) overlap.
             uint32_t cum = 0;
-            auto crossing = [&](uint32_t slot, uint32_t kk, uint32_t& word, uint32_t& bit) -> bool {
-                const MaskEdge me = s_edge[warp][min(slot, 31u)];  // two 16-byte shared-memory loads
-                TileEdge b;
-                b.x_top = me.x_top;
-                b.y_top = me.y_top;
-                b.dxdy = me.dxdy;
-                const uint32_t row = me.lo + (kk - me.pre);
+            double kd = (double)lane;  // crossing index of the lane's first chunk as a double (no conversion per crossing)
+            auto crossing = [&](uint32_t slot, uint32_t kk, double kkd, uint32_t& word, uint32_t& bit) -> bool {
+                const MaskEdge* me = &s_edge[warp][min(slot, 31u)];
+                const double2 a = *reinterpret_cast<const double2*>(&me->x_top);  // x_top, y_top
+                const double2 b = *reinterpret_cast<const double2*>(&me->dxdy);   // dxdy, cyb
+                const uint32_t rrow = (uint32_t)(me->ib + (int32_t)kk);           // row - row_start
+                const double cy = __dadd_rn(b.y, kkd);                            // row + 0.5
                 // floor(x + 0.5) as usize (burners.rs:310-311); the clamp to ncols is implied by `col < c1` below
-                const double cy = __dadd_rn((double)row, 0.5);
-                const uint32_t col = __double2uint_rd(__dadd_rn(__dadd_rn(b.x_top, __dmul_rn(__dsub_rn(cy, b.y_top), b.dxdy)), 0.5));
+                const uint32_t col = __double2uint_rd(__dadd_rn(__dadd_rn(a.x, __dmul_rn(__dsub_rn(cy, a.y), b.x)), 0.5));
                 const uint32_t rel = col <= c0 ? 0u : col - c0;  // left of the chunk: parity carry-in at bit 0
-                word = (row - row_start) * stride + (rel >> 5);
+                word = rrow * stride + (rel >> 5);
                 bit = 1u << (rel & 31);
                 return kk < wtot && col < c1;  // a crossing right of the chunk has no effect on its pixels
             };
@@ -444,11 +546,12 @@ tile_mask_kernel(KParams P, TileParams T, const uint64_t* __restrict__ units, ui
                 cum += __popc(sa);
                 const uint32_t slot_b = cum + __popc(sb & le_mask) - 1u;
                 cum += __popc(sb);
-                uint32_t wa, ba, wb, bb;
-                const bool oka = crossing(slot_a, k0 + lane, wa, ba);
-                const bool okb = crossing(slot_b, k0 + 32 + lane, wb, bb);
-                if (oka) atomicXor(&mask[wa], ba);
-                if (okb) atomicXor(&mask[wb], bb);
+                uint32_t wd_a, bt_a, wd_b, bt_b;
+                const bool oka = crossing(slot_a, k0 + lane, kd, wd_a, bt_a);
+                const bool okb = crossing(slot_b, k0 + 32 + lane, __dadd_rn(kd, 32.0), wd_b, bt_b);
+                kd = __dadd_rn(kd, 64.0);
+                if (oka) atomicXor(&mask[wd_a], bt_a);
+                if (okb) atomicXor(&mask[wd_b], bt_b);
             }
             __syncwarp();
         }
@@ -486,16 +589,22 @@ tile_mask_kernel(KParams P, TileParams T, const uint64_t* __restrict__ units, ui
             }
         }
         __syncwarp();
-        // one TILE_R x 4-word block per (part, tile): consecutive lanes write consecutive words; rows of the
-        // tile outside the part's rows are empty
+        // compact blocks: rows x words of every (tile row of the unit, tile column of the chunk); consecutive lanes
+        // write consecutive words
+        const uint32_t tca = wa >> 2, tcb = (wa + nw - 1) >> 2;
         for (uint32_t j = 0; j < k_tr; j++) {
-            const unsigned long long row_base = q.first_block + (unsigned long long)(tr + j - q.tr0) * q.ntc + w0 / 4;
             const uint32_t tj = t0 + j * TILE_R;
-            for (uint32_t tcl = 0; tcl * 4 < nw; tcl++) {
-                uint32_t* dst = masks + (size_t)pos[row_base + tcl] * (TILE_R * 4);  // tile order
-                for (uint32_t i = lane; i < TILE_R * 4; i += 32) {
-                    const uint32_t rel = tj + (i >> 2) - row_start;  // wraps above n_rows for rows before row_start
-                    dst[i] = rel < n_rows ? mask[rel * stride + tcl * 4 + (i & 3)] : 0u;
+            const uint32_t blk_row = q.first_block + (tr + j - q.tr0) * q.ntc - q.tc0;
+            for (uint32_t tcl = tca; tcl <= tcb; tcl++) {
+                const uint2 wg = *reinterpret_cast<const uint2*>(&desc[blk_row + tcl].woff);
+                const uint32_t geom = wg.y;
+                const uint32_t b_row = geom & 0xffu, b_nr = (geom >> 8) & 0xffu, b_w = (geom >> 16) & 0xfu, b_nw = geom >> 20;
+                const uint32_t inv = b_nw == 1 ? 65536u : b_nw == 2 ? 32768u : b_nw == 3 ? 21846u : 16384u;
+                const uint32_t src0 = (tj + b_row - row_start) * stride + (tcl * 4u + b_w - wa);
+                uint32_t* dst = masks + wg.x;
+                for (uint32_t i = lane; i < b_nr * b_nw; i += 32) {
+                    const uint32_t r = (i * inv) >> 16, w = i - r * b_nw;
+                    dst[i] = mask[src0 + r * stride + w];
                 }
             }
         }
@@ -505,13 +614,15 @@ tile_mask_kernel(KParams P, TileParams T, const uint64_t* __restrict__ units, ui
 }
 
 // ---------------------------------------------------------------------------------------------
-// tile_apply: one CTA per tile, each warp owns 8 rows held in REGISTERS, no synchronisation between warps
+// tile_apply: one CTA per 8 tiles of a tile row, each warp owns 8 rows held in REGISTERS, no synchronisation
+// between warps
 // ---------------------------------------------------------------------------------------------
-// A part's inside mask arrives as one coalesced 128-byte load per warp: lane 4r + w holds the 32-bit word of
-// (row r, columns 32w .. 32w+31) of the warp's 8 x 128 pixels - and that lane OWNS those 32 pixels, in
-// registers px[0..31] (initialised to the background: geo/raster.rs:23-28).  Applying a part is therefore
-// lane-local: no shuffle, no shared memory; bit b of the lane's own mask word decides whether pixel b takes the
-// part's value through the reference's pixel-function rule (pixel_functions.rs:56-123), parts in burn order.
+// Lane 4r + w of a warp OWNS the 32 pixels of (row r of the warp's 8, columns 32w .. 32w+31) of the tile, in
+// registers px[0..31] (initialised to the background: geo/raster.rs:23-28).  For every block of the tile, in burn
+// order, the lane fetches its own word of the part's inside mask - if the block's rows and words cover it - and
+// applies the part's value to its pixels: no shuffle, no shared memory; bit b of the word decides whether pixel b
+// takes the value through the reference's pixel-function rule (pixel_functions.rs:56-123).  Warps whose rows the
+// block does not reach skip it without a load.
 //
 // MODE selects how the rule is evaluated (all bit-exact with the reference):
 //   0  generic: apply_px on every pixel slot, selected by the mask bit.
@@ -526,6 +637,8 @@ tile_mask_kernel(KParams P, TileParams T, const uint64_t* __restrict__ units, ui
 //      burn value equals the background (integer dtypes; TileCounters::eq_bg) or, for a NaN background, no value
 //      is NaN.  `min` / `max` then start from the type's largest / smallest value and are one compare-select,
 //      `first` writes where the mask bit is set and the touched bit is not.
+// Modes 1 and 3 depend on a property of the burn values that only the device knows (TileCounters): the kernel
+// holds both the fast body and the generic one and picks at run time (one uniform branch per CTA).
 // (Measured alternatives on config 4: pixels in shared memory 6.65 ms; registers with one column per lane and
 // shuffled mask words 5.30 ms; four consecutive pixels per lane 6.09 ms.)
 // the largest (+inf) / smallest (-inf) value of a dtype, from its bit pattern
@@ -555,12 +668,12 @@ __device__ __forceinline__ void apply_part_word(N (&px)[32], uint32_t mw, N v, N
 }
 
 constexpr int APPLY_TILES = 8;  // consecutive tiles of one tile row handled by one CTA
+constexpr int APPLY_DEPTH = 4;  // blocks in flight per warp (power of two)
 
 template <typename N, int FN, int TILE_R, int MODE, bool BGNAN>
-static __global__ void __launch_bounds__(TILE_R * 4, 4)
-tile_apply_kernel(KParams P, TileParams T, const uint32_t* __restrict__ tile_start,
-                  const unsigned long long* __restrict__ value_sorted, const uint32_t* __restrict__ masks,
-                  uint64_t bg_bits, N* __restrict__ out) {
+__device__ __forceinline__ void tile_apply_body(const KParams& P, const TileParams& T, const uint32_t* __restrict__ tile_start,
+                                                const BlockDesc* __restrict__ desc, const uint32_t* __restrict__ masks,
+                                                uint64_t bg_bits, N* __restrict__ out, unsigned char* smem_raw) {
     const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
     const N bg = value_from_bits<N>(bg_bits);
 
@@ -583,7 +696,8 @@ tile_apply_kernel(KParams P, TileParams T, const uint32_t* __restrict__ tile_sta
     }
     const uint32_t tcol0 = tgrp * APPLY_TILES, n_here = min((uint32_t)APPLY_TILES, T.n_tc - tcol0);
     const uint32_t t0 = (band * T.n_tr + trow) * T.n_tc + tcol0;
-    const uint32_t r0 = P.win_r0 + trow * TILE_R + warp * 8;
+    const uint32_t wr0 = warp * 8;  // first of this warp's rows inside the tile
+    const uint32_t r0 = P.win_r0 + trow * TILE_R + wr0;
     if (r0 >= P.win_r1) return;
 
     N ident;
@@ -598,22 +712,47 @@ tile_apply_kernel(KParams P, TileParams T, const uint32_t* __restrict__ tile_sta
         ident = bg;  // MODE 0: the background; MODE 2: bg == 0; MODE 3 first: never read before written
     }
 
-    // A tile's blocks [beg, end) are consecutive in memory, parts in burn order, and so are the tiles of a tile
-    // row.  A ring of APPLY_DEPTH blocks is kept in flight (one coalesced 128-byte load plus one broadcast load of
-    // the part's value per block); when a tile's blocks are used up the ring is primed with the NEXT tile's
-    // first blocks before this tile is flushed, so only the first tile of a CTA waits for its first loads.
-    constexpr int APPLY_DEPTH = 4;
-    const uint32_t* my_masks = masks + warp * 32 + lane;
-    uint32_t m[APPLY_DEPTH];
+    // The descriptors of a CTA's tiles are consecutive in memory, tile after tile, parts in burn order inside a
+    // tile.  Two rings indexed by (block index mod APPLY_DEPTH) run over all of them without restarting at tile
+    // borders: slot u holds this lane's mask word and the value of the next block j = u (mod DEPTH) to consume,
+    // and the descriptor (where / which rows and words) of block j + DEPTH; consuming block j loads block
+    // j + DEPTH's word and block j + 2 DEPTH's descriptor.  Only the first tile of a CTA waits for its loads.
+    const uint32_t my_r = wr0 + (lane >> 2), my_w = lane & 3u;
+    auto fetch_word = [&](uint32_t woff, uint32_t geom) -> uint32_t {  // this lane's word of a block, 0 if not covered
+        const uint32_t rr = my_r - (geom & 0xffu), ww = my_w - ((geom >> 16) & 0xfu), nw = geom >> 20;
+        const bool in = rr < ((geom >> 8) & 0xffu) && ww < nw;
+        return in ? __ldg(masks + woff + rr * nw + ww) : 0u;
+    };
+    auto reaches = [&](uint32_t geom) -> bool {  // does the block hold any of this warp's 8 rows?  (warp-uniform)
+        const uint32_t b_row = geom & 0xffu, b_nr = (geom >> 8) & 0xffu;
+        return b_row < wr0 + 8u && b_row + b_nr > wr0;
+    };
+    uint32_t m[APPLY_DEPTH], g_woff[APPLY_DEPTH], g_geom[APPLY_DEPTH];
     N val[APPLY_DEPTH];  // the value occupies the low bytes of its 8-byte slot
+    bool hit[APPLY_DEPTH];
+    const uint32_t cta_end = tile_start[t0 + n_here];  // one past the last block of this CTA's tiles
     uint32_t beg = tile_start[t0], end = tile_start[t0 + 1];
 #pragma unroll
     for (int u = 0; u < APPLY_DEPTH; u++) {
-        const bool live = beg + u < end;
-        m[u] = live ? my_masks[(size_t)(beg + u) * (TILE_R * 4)] : 0u;
-        val[u] = live ? *reinterpret_cast<const N*>(value_sorted + beg + u) : bg;
+        uint32_t j = (beg & ~(uint32_t)(APPLY_DEPTH - 1)) + u;
+        if (j < beg) j += APPLY_DEPTH;
+        uint32_t woff = 0, geom = 0;
+        if (j < cta_end) {
+            const uint2 wg = *reinterpret_cast<const uint2*>(&desc[j].woff);
+            woff = wg.x;
+            geom = wg.y;
+        }
+        hit[u] = j < cta_end && reaches(geom);
+        m[u] = hit[u] ? fetch_word(woff, geom) : 0u;
+        val[u] = hit[u] ? *reinterpret_cast<const N*>(&desc[j].value_bits) : bg;
+        g_woff[u] = 0;
+        g_geom[u] = 0;
+        if (j + APPLY_DEPTH < cta_end) {
+            const uint2 wg = *reinterpret_cast<const uint2*>(&desc[j + APPLY_DEPTH].woff);
+            g_woff[u] = wg.x;
+            g_geom[u] = wg.y;
+        }
     }
-    extern __shared__ __align__(16) unsigned char smem_raw[];
     for (uint32_t ti = 0; ti < n_here; ti++) {
     const uint32_t end_next = ti + 1 < n_here ? tile_start[t0 + ti + 2] : end;  // needed after this tile's blocks
     const uint32_t c0 = (tcol0 + ti) * TILE_C;
@@ -622,16 +761,25 @@ tile_apply_kernel(KParams P, TileParams T, const uint32_t* __restrict__ tile_sta
 #pragma unroll
     for (int b = 0; b < 32; b++) px[b] = ident;
 
-    for (uint32_t j0 = beg; j0 < end; j0 += APPLY_DEPTH) {
+    for (uint32_t j0 = beg & ~(uint32_t)(APPLY_DEPTH - 1); j0 < end; j0 += APPLY_DEPTH) {
 #pragma unroll
         for (int u = 0; u < APPLY_DEPTH; u++) {
+            const uint32_t j = j0 + u;
+            if (j < beg || j >= end) continue;  // another tile's block: its slot stays as it is
             const uint32_t mu = m[u];
             const N v = val[u];
-            const uint32_t nxt = j0 + u + APPLY_DEPTH;  // refill this slot of the ring
-            const bool live = nxt < end;
-            m[u] = live ? my_masks[(size_t)nxt * (TILE_R * 4)] : 0u;
-            val[u] = live ? *reinterpret_cast<const N*>(value_sorted + nxt) : bg;
-            if (__ballot_sync(0xffffffffu, mu != 0) == 0) continue;  // the part does not reach these 8 rows
+            const bool was_hit = hit[u];
+            // refill the slot: word and value of block j + DEPTH (descriptor at hand), descriptor of j + 2 DEPTH
+            const uint32_t nxt = j + APPLY_DEPTH;
+            hit[u] = nxt < cta_end && reaches(g_geom[u]);
+            m[u] = hit[u] ? fetch_word(g_woff[u], g_geom[u]) : 0u;
+            val[u] = hit[u] ? *reinterpret_cast<const N*>(&desc[nxt].value_bits) : bg;
+            if (nxt + APPLY_DEPTH < cta_end) {
+                const uint2 wg = *reinterpret_cast<const uint2*>(&desc[nxt + APPLY_DEPTH].woff);
+                g_woff[u] = wg.x;
+                g_geom[u] = wg.y;
+            }
+            if (!was_hit) continue;  // the block does not reach these 8 rows
             if (MODE == 3) {
                 apply_part_word<N, FN, 3, BGNAN>(px, FN == RZ_FIRST ? (mu & ~touched) : mu, v, bg);
                 touched |= mu;
@@ -645,13 +793,6 @@ tile_apply_kernel(KParams P, TileParams T, const uint32_t* __restrict__ tile_sta
                 apply_part_word<N, FN, 0, BGNAN>(px, mu, v, bg);
             }
         }
-    }
-    // the ring is drained: prime it with the next tile's first blocks, in flight during the flush below
-#pragma unroll
-    for (int u = 0; u < APPLY_DEPTH; u++) {
-        const bool live = end + u < end_next;
-        m[u] = live ? my_masks[(size_t)(end + u) * (TILE_R * 4)] : 0u;
-        val[u] = live ? *reinterpret_cast<const N*>(value_sorted + end + u) : bg;
     }
     if (MODE == 1 || MODE == 3) {
 #pragma unroll
@@ -702,6 +843,23 @@ tile_apply_kernel(KParams P, TileParams T, const uint32_t* __restrict__ tile_sta
     beg = end;
     end = end_next;
     }  // tiles of this CTA
+}
+
+// FAST_MODE runs when the burn values allow it (see MODE above), else the generic MODE 0 body.
+template <typename N, int FN, int TILE_R, int FAST_MODE, bool BGNAN>
+static __global__ void __launch_bounds__(TILE_R * 4, 4)
+tile_apply_kernel(KParams P, TileParams T, const uint32_t* __restrict__ tile_start, const BlockDesc* __restrict__ desc,
+                  const uint32_t* __restrict__ masks, const TileCounters* __restrict__ tcnt, uint64_t bg_bits,
+                  N* __restrict__ out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    if (FAST_MODE == 1 || FAST_MODE == 3) {
+        const bool slow = std::is_floating_point<N>::value ? tcnt->nonfinite != 0 : tcnt->eq_bg != 0;
+        if (slow) {
+            tile_apply_body<N, FN, TILE_R, 0, BGNAN>(P, T, tile_start, desc, masks, bg_bits, out, smem_raw);
+            return;
+        }
+    }
+    tile_apply_body<N, FN, TILE_R, FAST_MODE, BGNAN>(P, T, tile_start, desc, masks, bg_bits, out, smem_raw);
 }
 
 }  // namespace rz
