@@ -74,6 +74,131 @@ struct DevBuf {
     template <typename T> T* as() { return reinterpret_cast<T*>(p); }
 };
 
+// ------------------------------------------------------------------------------------------------
+// page-locked host blocks
+// ------------------------------------------------------------------------------------------------
+// Host memory for sparse results and for the vertex pools of geometry sets.  Handing out gigabytes of FRESH
+// memory per call costs far more than the whole device pipeline (measured for 125 M triplets = 2.5 GB: 3.8 ms of
+// kernels against 700 ms to fault the pages in and page-lock them for the copy).  Blocks are therefore huge-page
+// backed, faulted in by several threads, page-locked once (portable: every device's copy engine may use them),
+// and recycled through a pool when their owner is freed: steady-state calls copy straight into / out of
+// resident, pinned memory at the PCIe rate.  RZ_HOST_POOL_BYTES caps what the pool keeps (default 8 GiB).
+struct HostBlock {
+    void* p = nullptr;
+    size_t cap = 0;
+    bool pinned = false;
+};
+class HostPool {
+  public:
+    HostBlock get(size_t bytes) {
+        if (bytes == 0) return HostBlock{};
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            size_t best = free_.size();
+            for (size_t i = 0; i < free_.size(); i++)
+                if (free_[i].cap >= bytes && free_[i].cap <= 2 * bytes + (1u << 20) &&
+                    (best == free_.size() || free_[i].cap < free_[best].cap))
+                    best = i;
+            if (best != free_.size()) {
+                HostBlock b = free_[best];
+                free_.erase(free_.begin() + best);
+                pooled_ -= b.cap;
+                return b;
+            }
+        }
+        HostBlock b;
+        const size_t huge = (size_t)2 << 20;
+        b.cap = bytes >= huge ? (bytes + huge - 1) & ~(huge - 1) : bytes;
+        if (bytes >= huge) {
+            if (posix_memalign(&b.p, huge, b.cap) != 0) throw std::bad_alloc();
+            madvise(b.p, b.cap, MADV_HUGEPAGE);
+            // first touch in parallel: the kernel clears the pages on the faulting thread
+            const unsigned nt = std::min<unsigned>({std::max(1u, std::thread::hardware_concurrency()), 16u,
+                                                   (unsigned)(b.cap >> 26) + 1u});
+            std::vector<std::thread> th;
+            for (unsigned t = 0; t < nt; t++)
+                th.emplace_back([&, t]() {
+                    char* q = (char*)b.p;
+                    const size_t lo = b.cap / nt * t, hi = t + 1 == nt ? b.cap : b.cap / nt * (t + 1);
+                    for (size_t o = lo; o < hi; o += 4096) q[o] = 0;
+                });
+            for (auto& x : th) x.join();
+            if (cudaHostRegister(b.p, b.cap, cudaHostRegisterPortable) == cudaSuccess) b.pinned = true;
+            else (void)cudaGetLastError();
+        } else {
+            b.p = std::malloc(b.cap);
+            if (!b.p) throw std::bad_alloc();
+        }
+        return b;
+    }
+    void put(HostBlock b) {
+        if (!b.p) return;
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            if (b.cap >= ((size_t)2 << 20) && pooled_ + b.cap <= limit()) {
+                free_.push_back(b);
+                pooled_ += b.cap;
+                return;
+            }
+        }
+        release(b);
+    }
+    // blocks lent to a container that only knows the pointer (the vertex pools' allocator)
+    void* lease(size_t bytes) {
+        HostBlock b = get(bytes);
+        std::lock_guard<std::mutex> lk(mu_);
+        leased_[b.p] = b;
+        return b.p;
+    }
+    bool unlease(void* p) {
+        HostBlock b;
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            auto it = leased_.find(p);
+            if (it == leased_.end()) return false;
+            b = it->second;
+            leased_.erase(it);
+        }
+        put(b);
+        return true;
+    }
+    bool leased(const void* p, HostBlock* out) {
+        std::lock_guard<std::mutex> lk(mu_);
+        auto it = leased_.find(const_cast<void*>(p));
+        if (it == leased_.end()) return false;
+        if (out) *out = it->second;
+        return true;
+    }
+
+  private:
+    static void release(HostBlock& b) {
+        if (b.pinned && cudaHostUnregister(b.p) != cudaSuccess) (void)cudaGetLastError();
+        std::free(b.p);
+        b.p = nullptr;
+    }
+    static size_t limit() {
+        if (const char* e = std::getenv("RZ_HOST_POOL_BYTES")) return (size_t)std::strtoull(e, nullptr, 10);
+        return (size_t)8 << 30;
+    }
+    std::mutex mu_;
+    std::vector<HostBlock> free_;
+    std::map<void*, HostBlock> leased_;
+    size_t pooled_ = 0;
+};
+// never destroyed: geometry sets and sparse results may be freed while the process shuts down
+static HostPool& g_host_pool = *new HostPool();
+static const bool g_pinned_hooks_set = []() {
+    g_pinned_hooks.alloc = [](size_t bytes) -> void* {
+        try {
+            return g_host_pool.lease(bytes);
+        } catch (const std::bad_alloc&) {
+            return nullptr;
+        }
+    };
+    g_pinned_hooks.release = [](void* p) -> bool { return g_host_pool.unlease(p); };
+    return true;
+}();
+
 struct DeviceGeoms {
     int dev = 0;
     double* x[3] = {nullptr, nullptr, nullptr};
@@ -211,6 +336,11 @@ template <typename T, typename A>
 static bool pin_vec(rz_geoms* g, std::vector<T, A>& v, bool verbose) {  // true: fully page-locked
     const size_t bytes = v.size() * sizeof(T);
     if (bytes < (1u << 16)) return false;
+    HostBlock blk;
+    if (g_host_pool.leased(v.data(), &blk) && blk.pinned) {  // built into a recycled page-locked block
+        g->pinned_ranges.emplace_back(blk.p, blk.cap);
+        return true;
+    }
     auto try_reg = [&](void* p, size_t n) {
         const cudaError_t e = cudaHostRegister(p, n, cudaHostRegisterMapped | cudaHostRegisterPortable);
         if (e == cudaSuccess) {
@@ -267,8 +397,8 @@ static void pin_host(rz_geoms* g) {
 
 static void unpin_host(rz_geoms* g) {
     if (!g->pinned) return;
-    for (auto& r : g->pinned_ranges)
-        if (cudaHostUnregister(r.first) != cudaSuccess) (void)cudaGetLastError();
+    for (auto& r : g->pinned_ranges)  // (pool blocks stay page-locked: they are recycled)
+        if (!g_host_pool.leased(r.first, nullptr) && cudaHostUnregister(r.first) != cudaSuccess) (void)cudaGetLastError();
     g->pinned_ranges.clear();
     g->pinned = false;
     g->pool0_mapped = false;
@@ -452,7 +582,13 @@ static void validate_lengths(const rz_geoms* g, const rz_context* ctx) {
     }
 }
 
-static void rasterize_dense(rz_geoms* g, const rz_context* ctx, void* out, rz_stats* st) {
+// Where a row shard lands inside a larger host array (multi-device calls): band b of the shard starts at row
+// `row_off` of band b of an array holding `band_rows` rows per band.
+struct DenseExtra {
+    uint64_t band_rows, row_off;
+};
+
+static void rasterize_dense(rz_geoms* g, const rz_context* ctx, void* out, rz_stats* st, const DenseExtra* ex = nullptr) {
     const rz_raster_info& ri = ctx->raster_info;
     validate_lengths(g, ctx);
     const size_t isz = dtype_size(ctx->dtype);
@@ -629,7 +765,8 @@ static void rasterize_dense(rz_geoms* g, const rz_context* ctx, void* out, rz_st
         const size_t half = split ? (size_t)(rows / 2) * ri.ncols * isz : chunk;
         if (split) CUDA_TRY(cudaStreamWaitEvent(c.copy_stream2, c.ev_filled[k], 0));
         for (uint32_t b = 0; b < n_bands; b++) {
-            char* dst = (char*)out + ((size_t)b * shard_rows + (w.r0 - shard_r0)) * ri.ncols * isz;
+            char* dst = (char*)out + ((size_t)b * (ex ? ex->band_rows : shard_rows) + (ex ? ex->row_off : 0) +
+                                      (w.r0 - shard_r0)) * ri.ncols * isz;
             const char* src = (const char*)d_out + (size_t)b * chunk;
             CUDA_TRY(cudaMemcpyAsync(dst, src, half, cudaMemcpyDeviceToHost, c.copy_stream));
             if (split) CUDA_TRY(cudaMemcpyAsync(dst + half, src + half, chunk - half, cudaMemcpyDeviceToHost, c.copy_stream2));
@@ -1100,93 +1237,6 @@ static void rasterize_dense(rz_geoms* g, const rz_context* ctx, void* out, rz_st
 // ------------------------------------------------------------------------------------------------
 // the sparse pipeline
 // ------------------------------------------------------------------------------------------------
-}  // namespace rz
-
-// Host memory for sparse results.  Handing out gigabytes of FRESH memory per call costs far more than the whole
-// device pipeline (measured for 125 M triplets = 2.5 GB: 3.8 ms of kernels against 700 ms to fault the pages in
-// and page-lock them for the copy).  Blocks are therefore huge-page backed, faulted in by several threads,
-// page-locked once, and recycled through a pool when an rz_sparse is freed: steady-state calls copy straight
-// into resident, pinned memory at the PCIe rate.  RZ_HOST_POOL_BYTES caps what the pool keeps (default 8 GiB).
-namespace rz {
-struct HostBlock {
-    void* p = nullptr;
-    size_t cap = 0;
-    bool pinned = false;
-};
-class HostPool {
-  public:
-    HostBlock get(size_t bytes) {
-        if (bytes == 0) return HostBlock{};
-        {
-            std::lock_guard<std::mutex> lk(mu_);
-            size_t best = free_.size();
-            for (size_t i = 0; i < free_.size(); i++)
-                if (free_[i].cap >= bytes && free_[i].cap <= 2 * bytes + (1u << 20) &&
-                    (best == free_.size() || free_[i].cap < free_[best].cap))
-                    best = i;
-            if (best != free_.size()) {
-                HostBlock b = free_[best];
-                free_.erase(free_.begin() + best);
-                pooled_ -= b.cap;
-                return b;
-            }
-        }
-        HostBlock b;
-        const size_t huge = (size_t)2 << 20;
-        b.cap = bytes >= huge ? (bytes + huge - 1) & ~(huge - 1) : bytes;
-        if (bytes >= huge) {
-            if (posix_memalign(&b.p, huge, b.cap) != 0) throw std::bad_alloc();
-            madvise(b.p, b.cap, MADV_HUGEPAGE);
-            // first touch in parallel: the kernel clears the pages on the faulting thread
-            const unsigned nt = std::min<unsigned>({std::max(1u, std::thread::hardware_concurrency()), 8u,
-                                                   (unsigned)(b.cap >> 26) + 1u});
-            std::vector<std::thread> th;
-            for (unsigned t = 0; t < nt; t++)
-                th.emplace_back([&, t]() {
-                    char* q = (char*)b.p;
-                    const size_t lo = b.cap / nt * t, hi = t + 1 == nt ? b.cap : b.cap / nt * (t + 1);
-                    for (size_t o = lo; o < hi; o += 4096) q[o] = 0;
-                });
-            for (auto& x : th) x.join();
-            if (cudaHostRegister(b.p, b.cap, cudaHostRegisterDefault) == cudaSuccess) b.pinned = true;
-            else (void)cudaGetLastError();
-        } else {
-            b.p = std::malloc(b.cap);
-            if (!b.p) throw std::bad_alloc();
-        }
-        return b;
-    }
-    void put(HostBlock b) {
-        if (!b.p) return;
-        {
-            std::lock_guard<std::mutex> lk(mu_);
-            if (b.cap >= ((size_t)2 << 20) && pooled_ + b.cap <= limit()) {
-                free_.push_back(b);
-                pooled_ += b.cap;
-                return;
-            }
-        }
-        release(b);
-    }
-    ~HostPool() {
-        for (auto& b : free_) release(b);
-    }
-
-  private:
-    static void release(HostBlock& b) {
-        if (b.pinned && cudaHostUnregister(b.p) != cudaSuccess) (void)cudaGetLastError();
-        std::free(b.p);
-        b.p = nullptr;
-    }
-    static size_t limit() {
-        if (const char* e = std::getenv("RZ_HOST_POOL_BYTES")) return (size_t)std::strtoull(e, nullptr, 10);
-        return (size_t)8 << 30;
-    }
-    std::mutex mu_;
-    std::vector<HostBlock> free_;
-    size_t pooled_ = 0;
-};
-static HostPool g_host_pool;
 }  // namespace rz
 
 struct rz_sparse {
@@ -1877,33 +1927,13 @@ rz_geoms* rz_geoms_from_wkt(const char* const* strs, uint64_t n, char* err, size
 rz_geoms* rz_geoms_from_soa(const rz_geom_soa* soa, char* err, size_t errlen) {
     std::unique_ptr<rz_geoms> g(new rz_geoms());
     int rc = guarded(err, errlen, [&]() {
-        rz::Flattener f(g.get());
-        for (int k = 0; k < 3; k++) {  // a good guess: most inputs are single-kind
-            g->pool[k].x.reserve(k == 0 ? soa->n_coords + soa->n_seqs : 0);
-            g->pool[k].y.reserve(k == 0 ? soa->n_coords + soa->n_seqs : 0);
-            g->pool[k].tag.reserve(k == 0 ? soa->n_coords + soa->n_seqs : 0);
-        }
-        for (uint64_t gi = 0; gi < soa->n_geoms; gi++) {
-            f.begin_geometry();
-            for (uint64_t p = soa->geom_part_off[gi]; p < soa->geom_part_off[gi + 1]; p++) {
-                int kind = soa->part_kind[p];
-                if (kind < 0 || kind > 2) throw Error{RZ_VALUE_ERROR, "Invalid part kind"};
-                f.begin_part(kind);
-                uint64_t s0 = soa->part_seq_off[p], s1 = soa->part_seq_off[p + 1];
-                for (uint64_t s = s0; s < s1; s++) {
-                    // geo::BoundingRect looks at exterior rings only; the SoA form has no polygon
-                    // boundaries, so every ring counts (callers needing exactness pass an extent).
-                    f.begin_seq(true);
-                    const uint64_t k0 = soa->seq_coord_off[s], k1 = soa->seq_coord_off[s + 1];
-                    if (k1 > k0) f.coords(soa->x + k0, soa->y + k0, (size_t)(k1 - k0));
-                    f.end_seq();
-                }
-                f.end_part();
-            }
-            f.end_geometry(true);
-            if (!f.ok()) throw Error{RZ_RUNTIME_ERROR, f.error()};
-        }
-        rz::finish_geoms(g.get());
+        // every size is known from the offsets: a counting pass gives each thread its exact place in the final
+        // (page-locked, recycled) pools, then copy + extents run in one sweep - memcpy speed, no intermediate copy
+        unsigned threads = std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
+        if (const char* e = std::getenv("RZ_PARSE_THREADS")) threads = std::max(1, std::atoi(e));
+        std::string msg;
+        const int code = rz::flatten_soa(soa, g.get(), threads, msg);
+        if (code != RZ_OK) throw Error{code, msg};
     });
     return rc == RZ_OK ? g.release() : nullptr;
 }
@@ -1961,7 +1991,10 @@ const uint64_t* rz_geoms_part_geom(const rz_geoms* g) { return g->part_geom.data
 uint64_t rz_geoms_pool_len(const rz_geoms* g, int kind) { return kind >= 0 && kind < 3 ? g->pool[kind].size() : 0; }
 const double* rz_geoms_pool_x(const rz_geoms* g, int kind) { return g->pool[kind].x.data(); }
 const double* rz_geoms_pool_y(const rz_geoms* g, int kind) { return g->pool[kind].y.data(); }
-const uint32_t* rz_geoms_pool_tag(const rz_geoms* g, int kind) { return g->pool[kind].tag.data(); }
+const uint32_t* rz_geoms_pool_tag(const rz_geoms* g, int kind) {
+    rz::ensure_tags(const_cast<rz_geoms*>(g), kind);  // not kept by every flattening path: the device never needs them
+    return g->pool[kind].tag.data();
+}
 
 int rz_raster_info_build(const rz_raw_raster_info* raw, const rz_geoms* g, rz_raster_info* out, char* err,
                          size_t errlen) {

@@ -8,12 +8,18 @@
 //   rust/src/rasterize.rs:199-205                    band order for `by`
 #include "rz_host.hpp"
 
+#include <algorithm>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
 #include <limits>
+#include <memory>
+#include <thread>
 
 namespace rz {
+
+PinnedHooks g_pinned_hooks;
+thread_local bool t_alloc_pinned = false;
 
 // ------------------------------------------------------------------------------------------------
 // Flattener
@@ -591,6 +597,409 @@ void finish_geoms(rz_geoms* g) {
         fit(g->pool[k].y);
         fit(g->pool[k].tag);
     }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Parallel SoA ingestion
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+// dst[i] = src[i] for one coordinate array, folding the run's minimum / maximum (strict compares seeded with
+// +-inf: NaN operands are ignored, like Flattener::extents) and whether any value is NaN or infinite.  Four
+// independent accumulators keep the min / max dependency chains off the critical path.
+inline void copy_fold(const double* src, double* dst, size_t n, double& lo, double& hi, uint64_t& bad) {
+    const double inf = std::numeric_limits<double>::infinity();
+    double l0 = inf, l1 = inf, l2 = inf, l3 = inf, h0 = -inf, h1 = -inf, h2 = -inf, h3 = -inf;
+    uint64_t b = 0;
+    const uint64_t EXP = 0x7ff0000000000000ull;
+    auto bits = [](double d) {
+        uint64_t u;
+        std::memcpy(&u, &d, 8);
+        return u;
+    };
+    size_t i = 0;
+    for (; i + 4 <= n; i += 4) {
+        const double a0 = src[i], a1 = src[i + 1], a2 = src[i + 2], a3 = src[i + 3];
+        dst[i] = a0;
+        dst[i + 1] = a1;
+        dst[i + 2] = a2;
+        dst[i + 3] = a3;
+        l0 = a0 < l0 ? a0 : l0;
+        l1 = a1 < l1 ? a1 : l1;
+        l2 = a2 < l2 ? a2 : l2;
+        l3 = a3 < l3 ? a3 : l3;
+        h0 = a0 > h0 ? a0 : h0;
+        h1 = a1 > h1 ? a1 : h1;
+        h2 = a2 > h2 ? a2 : h2;
+        h3 = a3 > h3 ? a3 : h3;
+        b |= (uint64_t)((bits(a0) & EXP) == EXP) | (uint64_t)((bits(a1) & EXP) == EXP) |
+             (uint64_t)((bits(a2) & EXP) == EXP) | (uint64_t)((bits(a3) & EXP) == EXP);
+    }
+    for (; i < n; i++) {
+        const double a = src[i];
+        dst[i] = a;
+        l0 = a < l0 ? a : l0;
+        h0 = a > h0 ? a : h0;
+        b |= (uint64_t)((bits(a) & EXP) == EXP);
+    }
+    l0 = l1 < l0 ? l1 : l0;
+    l2 = l3 < l2 ? l3 : l2;
+    l0 = l2 < l0 ? l2 : l0;
+    h0 = h1 > h0 ? h1 : h0;
+    h2 = h3 > h2 ? h3 : h2;
+    h0 = h2 > h0 ? h2 : h0;
+    lo = l0;
+    hi = h0;
+    bad |= b;
+}
+
+struct SoaChunk {
+    uint64_t g0 = 0, g1 = 0;               // geometry range
+    uint64_t pool_cnt[3] = {0, 0, 0};      // vertices written per pool (closing vertices included)
+    uint64_t seq_cnt[2] = {0, 0};          // non-empty sequences of the polygon / line pools
+    uint64_t pool_off[3] = {0, 0, 0}, seq_off[2] = {0, 0};
+    bool has_bounds = false, nonfinite = false;
+    double bounds[4] = {0, 0, 0, 0};
+    const char* error = nullptr;
+};
+
+}  // namespace
+
+int flatten_soa(const rz_geom_soa* soa, rz_geoms* g, unsigned threads, std::string& err) {
+    const uint64_t G = soa->n_geoms, NP = soa->n_parts, NS = soa->n_seqs, NC = soa->n_coords;
+    if (G == 0) return RZ_OK;
+    if (soa->geom_part_off[G] > NP || soa->part_seq_off[NP] > NS || soa->seq_coord_off[NS] > NC) {
+        err = "Inconsistent SoA offsets";
+        return RZ_VALUE_ERROR;
+    }
+    if (NP >= TAG_PART_MASK) {
+        err = "Too many geometry parts (limit 2^30 - 1).";
+        return RZ_RUNTIME_ERROR;
+    }
+    // first coordinate of geometry gi (non-decreasing in gi): where the chunk cuts are searched
+    auto first_coord = [&](uint64_t gi) -> uint64_t {
+        if (gi >= G) return NC;
+        const uint64_t p = soa->geom_part_off[gi];
+        if (p >= NP) return NC;
+        const uint64_t s = soa->part_seq_off[p];
+        return s >= NS ? NC : soa->seq_coord_off[s];
+    };
+    const unsigned T = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>({(uint64_t)std::max(1u, threads), G, NC / 65536 + 1}));
+    std::vector<SoaChunk> ch(T);
+    for (unsigned t = 0; t < T; t++) {
+        auto cut = [&](unsigned k) -> uint64_t {
+            if (k == 0) return 0;
+            if (k >= T) return G;
+            const uint64_t target = NC / T * k;
+            uint64_t lo = 0, hi = G;  // first geometry whose first coordinate is >= target
+            while (lo < hi) {
+                const uint64_t mid = (lo + hi) / 2;
+                if (first_coord(mid) < target) lo = mid + 1;
+                else hi = mid;
+            }
+            return lo;
+        };
+        ch[t].g0 = cut(t);
+        ch[t].g1 = cut(t + 1);
+    }
+    auto run = [&](auto&& body) {
+        if (T == 1) {
+            body(0u);
+            return;
+        }
+        std::vector<std::thread> th;
+        for (unsigned t = 0; t < T; t++) th.emplace_back([&, t]() { body(t); });
+        for (auto& x : th) x.join();
+    };
+    // ---- pass A: exact output sizes ---------------------------------------------------------------
+    run([&](unsigned t) {
+        SoaChunk& c = ch[t];
+        for (uint64_t p = soa->geom_part_off[c.g0]; p < soa->geom_part_off[c.g1]; p++) {
+            const unsigned kind = soa->part_kind[p];
+            if (kind > 2) {
+                c.error = "Invalid part kind";
+                return;
+            }
+            for (uint64_t s = soa->part_seq_off[p]; s < soa->part_seq_off[p + 1]; s++) {
+                const uint64_t k0 = soa->seq_coord_off[s], k1 = soa->seq_coord_off[s + 1];
+                if (k1 < k0 || k1 > NC) {
+                    c.error = "Inconsistent SoA offsets";
+                    return;
+                }
+                if (k1 == k0) continue;
+                uint64_t n = k1 - k0;
+                if (kind == RZ_PART_POLYGON) {  // geo_types::Polygon::new closes every ring
+                    const bool closed = soa->x[k0] == soa->x[k1 - 1] && soa->y[k0] == soa->y[k1 - 1];
+                    n += closed ? 0 : 1;
+                }
+                c.pool_cnt[kind] += n;
+                if (kind != RZ_PART_POINT) c.seq_cnt[kind]++;
+            }
+        }
+    });
+    for (auto& c : ch)
+        if (c.error) {
+            err = c.error;
+            return RZ_VALUE_ERROR;
+        }
+    uint64_t pool_tot[3] = {0, 0, 0}, seq_tot[2] = {0, 0};
+    for (auto& c : ch) {
+        for (int k = 0; k < 3; k++) {
+            c.pool_off[k] = pool_tot[k];
+            pool_tot[k] += c.pool_cnt[k];
+        }
+        for (int k = 0; k < 2; k++) {
+            c.seq_off[k] = seq_tot[k];
+            seq_tot[k] += c.seq_cnt[k];
+        }
+    }
+    for (int k = 0; k < 3; k++)
+        if (pool_tot[k] >= 0xfffffff0ull) {
+            err = "Too many vertices (limit 2^32 per pool).";
+            return RZ_RUNTIME_ERROR;
+        }
+    {
+        PinnedScope pinned;  // the pools go straight into recycled page-locked blocks
+        for (int k = 0; k < 3; k++) {
+            g->pool[k].x.resize(pool_tot[k]);
+            g->pool[k].y.resize(pool_tot[k]);
+        }
+    }
+    for (int k = 0; k < 2; k++) {
+        g->pool[k].seq_end.resize(seq_tot[k]);
+        g->pool[k].seq_closed.resize(seq_tot[k]);
+    }
+    g->part_kind.resize(NP);
+    g->part_geom.resize(NP);
+    g->part_xlo.resize(NP);
+    g->part_xhi.resize(NP);
+    g->part_ylo.resize(NP);
+    g->part_yhi.resize(NP);
+    g->part_vbeg.resize(NP);
+    g->part_vend.resize(NP);
+    // ---- pass B: copy + extents ---------------------------------------------------------------------
+    const double inf = std::numeric_limits<double>::infinity();
+    run([&](unsigned t) {
+        SoaChunk& c = ch[t];
+        uint64_t at[3] = {c.pool_off[0], c.pool_off[1], c.pool_off[2]};
+        uint64_t sq[2] = {c.seq_off[0], c.seq_off[1]};
+        uint64_t bad = 0;
+        for (uint64_t gi = c.g0; gi < c.g1; gi++) {
+            bool gb_has = false;
+            double gb[4] = {0, 0, 0, 0};
+            for (uint64_t p = soa->geom_part_off[gi]; p < soa->geom_part_off[gi + 1]; p++) {
+                const int kind = soa->part_kind[p];
+                Pool& pool = g->pool[kind];
+                double pxlo = inf, pxhi = -inf, pylo = inf, pyhi = -inf;
+                g->part_kind[p] = (uint8_t)kind;
+                g->part_geom[p] = gi;
+                g->part_vbeg[p] = (uint32_t)at[kind];
+                for (uint64_t s = soa->part_seq_off[p]; s < soa->part_seq_off[p + 1]; s++) {
+                    const uint64_t k0 = soa->seq_coord_off[s], n = soa->seq_coord_off[s + 1] - k0;
+                    if (n == 0) continue;
+                    double* xd = pool.x.data() + at[kind];
+                    double* yd = pool.y.data() + at[kind];
+                    double xlo, xhi, ylo, yhi;
+                    copy_fold(soa->x + k0, xd, n, xlo, xhi, bad);
+                    copy_fold(soa->y + k0, yd, n, ylo, yhi, bad);
+                    if (!gb_has) {  // geo's fold is seeded by the first coordinate (Flattener::bound)
+                        gb[0] = gb[2] = xd[0];
+                        gb[1] = gb[3] = yd[0];
+                        gb_has = true;
+                    }
+                    if (xlo < gb[0]) gb[0] = xlo;
+                    if (xhi > gb[2]) gb[2] = xhi;
+                    if (ylo < gb[1]) gb[1] = ylo;
+                    if (yhi > gb[3]) gb[3] = yhi;
+                    pxlo = std::fmin(pxlo, xlo);
+                    pxhi = std::fmax(pxhi, xhi);
+                    pylo = std::fmin(pylo, ylo);
+                    pyhi = std::fmax(pyhi, yhi);
+                    uint64_t m = n;
+                    if (kind == RZ_PART_POINT) {
+                        at[kind] += m;
+                        continue;
+                    }
+                    bool closed = xd[0] == xd[n - 1] && yd[0] == yd[n - 1];
+                    if (kind == RZ_PART_POLYGON && !closed) {
+                        xd[n] = xd[0];
+                        yd[n] = yd[0];
+                        m = n + 1;
+                        closed = true;
+                    }
+                    at[kind] += m;
+                    pool.seq_end[sq[kind]] = (uint32_t)(at[kind] - 1);
+                    pool.seq_closed[sq[kind]] = (kind == RZ_PART_LINE && closed) ? 1 : 0;
+                    sq[kind]++;
+                }
+                g->part_vend[p] = (uint32_t)at[kind];
+                const bool poly = kind == RZ_PART_POLYGON;
+                g->part_xlo[p] = poly ? pxlo : inf;
+                g->part_xhi[p] = poly ? pxhi : -inf;
+                g->part_ylo[p] = poly ? pylo : inf;
+                g->part_yhi[p] = poly ? pyhi : -inf;
+            }
+            if (gb_has) {  // Flattener::end_geometry (rust/src/geo/raster.rs:81-84)
+                if (!c.has_bounds) {
+                    std::memcpy(c.bounds, gb, sizeof gb);
+                    c.has_bounds = true;
+                } else {
+                    c.bounds[0] = std::fmin(c.bounds[0], gb[0]);
+                    c.bounds[1] = std::fmin(c.bounds[1], gb[1]);
+                    c.bounds[2] = std::fmax(c.bounds[2], gb[2]);
+                    c.bounds[3] = std::fmax(c.bounds[3], gb[3]);
+                }
+            }
+        }
+        c.nonfinite = bad != 0;
+    });
+    for (auto& c : ch) {
+        if (c.nonfinite) g->nonfinite = true;
+        if (!c.has_bounds) continue;
+        if (!g->has_bounds) {
+            std::memcpy(g->bounds, c.bounds, sizeof g->bounds);
+            g->has_bounds = true;
+        } else {
+            g->bounds[0] = std::fmin(g->bounds[0], c.bounds[0]);
+            g->bounds[1] = std::fmin(g->bounds[1], c.bounds[1]);
+            g->bounds[2] = std::fmax(g->bounds[2], c.bounds[2]);
+            g->bounds[3] = std::fmax(g->bounds[3], c.bounds[3]);
+        }
+    }
+    g->n_geoms = G;
+    return RZ_OK;
+}
+
+void ensure_tags(rz_geoms* g, int kind) {
+    std::lock_guard<std::mutex> lk(g->mu);
+    Pool& pool = g->pool[kind];
+    if (pool.tag.size() == pool.x.size()) return;
+    pool.tag.resize(pool.x.size());
+    for (size_t p = 0; p < g->part_kind.size(); p++)
+        if (g->part_kind[p] == kind)
+            for (uint32_t v = g->part_vbeg[p]; v < g->part_vend[p]; v++) pool.tag[v] = (uint32_t)p;
+    size_t start = 0;
+    for (size_t i = 0; i < pool.seq_end.size(); i++) {
+        const size_t end = pool.seq_end[i];
+        if (pool.seq_closed[i])
+            for (size_t v = start; v <= end; v++) pool.tag[v] |= TAG_CLOSED;
+        pool.tag[end] |= TAG_SEQ_END;
+        start = end + 1;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Part subsets (multi-device sharding)
+// ------------------------------------------------------------------------------------------------
+// A new geometry set holding the parts keep[0] < keep[1] < ... of `src`, in the same order: vertex ranges,
+// sequence lists and the parts table are copied (by `threads` threads, exact offsets from a counting pass);
+// geometry indices are unchanged (n_geoms stays src's), so field / by arrays of the original call still apply.
+rz_geoms* subset_parts(const rz_geoms* src, const uint32_t* keep, size_t n_keep, unsigned threads) {
+    std::unique_ptr<rz_geoms> g(new rz_geoms());
+    g->n_geoms = src->n_geoms;
+    g->has_bounds = src->has_bounds;
+    std::memcpy(g->bounds, src->bounds, sizeof g->bounds);
+    g->nonfinite = src->nonfinite;
+    if (n_keep == 0) return g.release();
+    const unsigned T = (unsigned)std::max<size_t>(1, std::min<size_t>({(size_t)std::max(1u, threads), n_keep / 4096 + 1}));
+    struct Chunk {
+        size_t j0, j1;
+        uint64_t pool_cnt[3] = {0, 0, 0}, seq_cnt[2] = {0, 0}, pool_off[3], seq_off[2];
+    };
+    std::vector<Chunk> ch(T);
+    for (unsigned t = 0; t < T; t++) {
+        ch[t].j0 = n_keep * t / T;
+        ch[t].j1 = n_keep * (t + 1) / T;
+    }
+    auto run = [&](auto&& body) {
+        if (T == 1) {
+            body(0u);
+            return;
+        }
+        std::vector<std::thread> th;
+        for (unsigned t = 0; t < T; t++) th.emplace_back([&, t]() { body(t); });
+        for (auto& x : th) x.join();
+    };
+    // sequences of part p inside its pool: those whose last vertex lies in [vbeg, vend)
+    auto seq_range = [&](uint32_t p, size_t& lo, size_t& hi) {
+        const int k = src->part_kind[p];
+        const auto& se = src->pool[k].seq_end;
+        lo = std::lower_bound(se.begin(), se.end(), src->part_vbeg[p]) - se.begin();
+        hi = std::lower_bound(se.begin() + lo, se.end(), src->part_vend[p]) - se.begin();
+    };
+    run([&](unsigned t) {
+        Chunk& c = ch[t];
+        for (size_t j = c.j0; j < c.j1; j++) {
+            const uint32_t p = keep[j];
+            const int k = src->part_kind[p];
+            c.pool_cnt[k] += src->part_vend[p] - src->part_vbeg[p];
+            if (k != RZ_PART_POINT) {
+                size_t lo, hi;
+                seq_range(p, lo, hi);
+                c.seq_cnt[k] += hi - lo;
+            }
+        }
+    });
+    uint64_t pool_tot[3] = {0, 0, 0}, seq_tot[2] = {0, 0};
+    for (auto& c : ch) {
+        for (int k = 0; k < 3; k++) {
+            c.pool_off[k] = pool_tot[k];
+            pool_tot[k] += c.pool_cnt[k];
+        }
+        for (int k = 0; k < 2; k++) {
+            c.seq_off[k] = seq_tot[k];
+            seq_tot[k] += c.seq_cnt[k];
+        }
+    }
+    {
+        PinnedScope pinned;
+        for (int k = 0; k < 3; k++) {
+            g->pool[k].x.resize(pool_tot[k]);
+            g->pool[k].y.resize(pool_tot[k]);
+        }
+    }
+    for (int k = 0; k < 2; k++) {
+        g->pool[k].seq_end.resize(seq_tot[k]);
+        g->pool[k].seq_closed.resize(seq_tot[k]);
+    }
+    g->part_kind.resize(n_keep);
+    g->part_geom.resize(n_keep);
+    g->part_xlo.resize(n_keep);
+    g->part_xhi.resize(n_keep);
+    g->part_ylo.resize(n_keep);
+    g->part_yhi.resize(n_keep);
+    g->part_vbeg.resize(n_keep);
+    g->part_vend.resize(n_keep);
+    run([&](unsigned t) {
+        Chunk& c = ch[t];
+        uint64_t at[3] = {c.pool_off[0], c.pool_off[1], c.pool_off[2]}, sq[2] = {c.seq_off[0], c.seq_off[1]};
+        for (size_t j = c.j0; j < c.j1; j++) {
+            const uint32_t p = keep[j];
+            const int k = src->part_kind[p];
+            const uint32_t vb = src->part_vbeg[p], n = src->part_vend[p] - vb;
+            std::memcpy(g->pool[k].x.data() + at[k], src->pool[k].x.data() + vb, (size_t)n * 8);
+            std::memcpy(g->pool[k].y.data() + at[k], src->pool[k].y.data() + vb, (size_t)n * 8);
+            g->part_kind[j] = (uint8_t)k;
+            g->part_geom[j] = src->part_geom[p];
+            g->part_xlo[j] = src->part_xlo[p];
+            g->part_xhi[j] = src->part_xhi[p];
+            g->part_ylo[j] = src->part_ylo[p];
+            g->part_yhi[j] = src->part_yhi[p];
+            g->part_vbeg[j] = (uint32_t)at[k];
+            g->part_vend[j] = (uint32_t)(at[k] + n);
+            if (k != RZ_PART_POINT) {
+                size_t lo, hi;
+                seq_range(p, lo, hi);
+                for (size_t q = lo; q < hi; q++) {
+                    g->pool[k].seq_end[sq[k]] = (uint32_t)(src->pool[k].seq_end[q] - vb + at[k]);
+                    g->pool[k].seq_closed[sq[k]] = src->pool[k].seq_closed[q];
+                    sq[k]++;
+                }
+            }
+            at[k] += n;
+        }
+    });
+    return g.release();
 }
 
 // ------------------------------------------------------------------------------------------------

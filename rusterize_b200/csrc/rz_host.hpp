@@ -4,6 +4,7 @@
 
 #include <cstdint>
 #include <map>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <cstdlib>
@@ -29,6 +30,23 @@ constexpr uint32_t TAG_SEQ_END = 0x80000000u;
 // Allocator of the vertex pools: large blocks are 2 MiB-aligned and advised to use transparent huge pages.
 // Filling a fresh 4 GB pool through 4 KiB pages spends most of its time in page faults (measured: 0.79 s
 // against 0.23 s for 20M vertices); with huge pages the faults are 512 times fewer.
+//
+// Page-locked blocks: while a PinnedScope is alive on the calling thread, large allocations are served by the
+// recycled, page-locked host blocks of rz_engine.cu (HostPool) through the hooks below - the final vertex pools
+// of a geometry set are built straight into memory the copy engine can read at PCIe speed, and a freed
+// geometry set hands its blocks to the next one (page-locking gigabytes per call costs more than the upload).
+struct PinnedHooks {
+    void* (*alloc)(size_t bytes) = nullptr;   // nullptr result: fall back to ordinary memory
+    bool (*release)(void* p) = nullptr;       // false: `p` is not a pool block
+};
+extern PinnedHooks g_pinned_hooks;
+extern thread_local bool t_alloc_pinned;
+struct PinnedScope {
+    bool prev;
+    PinnedScope() : prev(t_alloc_pinned) { t_alloc_pinned = true; }
+    ~PinnedScope() { t_alloc_pinned = prev; }
+};
+
 template <typename T> struct HugeAlloc {
     using value_type = T;
     HugeAlloc() = default;
@@ -36,6 +54,10 @@ template <typename T> struct HugeAlloc {
     T* allocate(size_t n) {
         const size_t bytes = n * sizeof(T);
         void* p = nullptr;
+        if (t_alloc_pinned && g_pinned_hooks.alloc && bytes >= ((size_t)4 << 20)) {
+            p = g_pinned_hooks.alloc(bytes);
+            if (p) return static_cast<T*>(p);
+        }
         if (bytes >= ((size_t)4 << 20)) {
             const size_t huge = (size_t)2 << 20, rounded = (bytes + huge - 1) & ~(huge - 1);
             if (posix_memalign(&p, huge, rounded) != 0) throw std::bad_alloc();
@@ -46,7 +68,10 @@ template <typename T> struct HugeAlloc {
         }
         return static_cast<T*>(p);
     }
-    void deallocate(T* p, size_t) { std::free(p); }
+    void deallocate(T* p, size_t n) {
+        if (n * sizeof(T) >= ((size_t)4 << 20) && g_pinned_hooks.release && g_pinned_hooks.release(p)) return;
+        std::free(p);
+    }
     // resize() default-initialises (no zero fill): the pools are always written right after they grow, and a
     // serial zero fill of gigabytes is exactly the first-touch cost the parallel ingestion avoids
     template <class U> void construct(U* p) noexcept { ::new (static_cast<void*>(p)) U; }
@@ -101,11 +126,11 @@ struct TilePlan {
 struct rz_geoms {
     uint64_t n_geoms = 0;
     rz::Pool pool[3];                  // indexed by RZ_PART_*
-    std::vector<uint8_t> part_kind;    // [n_parts]
-    std::vector<uint64_t> part_geom;   // [n_parts] owning geometry (index among kept geometries)
-    std::vector<double> part_xlo, part_xhi;  // [n_parts] world-x extent of polygon parts (column-tile range)
-    std::vector<double> part_ylo, part_yhi;  // [n_parts] world-y extent of polygon parts (row-tile range)
-    std::vector<uint32_t> part_vbeg, part_vend;  // [n_parts] vertex range of the part inside its pool
+    rz::HVec<uint8_t> part_kind;    // [n_parts]
+    rz::HVec<uint64_t> part_geom;   // [n_parts] owning geometry (index among kept geometries)
+    rz::HVec<double> part_xlo, part_xhi;  // [n_parts] world-x extent of polygon parts (column-tile range)
+    rz::HVec<double> part_ylo, part_yhi;  // [n_parts] world-y extent of polygon parts (row-tile range)
+    rz::HVec<uint32_t> part_vbeg, part_vend;  // [n_parts] vertex range of the part inside its pool
     bool has_bounds = false;
     double bounds[4] = {0, 0, 0, 0};   // union of geo::BoundingRect, xmin ymin xmax ymax
     bool pinned = false;
@@ -117,6 +142,9 @@ struct rz_geoms {
     std::mutex mu;
     std::map<int, rz::DeviceGeoms*> dev;  // cached device copies, by ordinal
     std::map<rz::TilePlanKey, rz::TilePlan> tile_plans;  // guarded by mu
+    // multi-device calls: the part subsets of this set's shards (row bands of a grid / geometry ranges), built
+    // once per (grid rows, band) and reused by later calls; guarded by mu
+    std::map<std::vector<uint64_t>, std::shared_ptr<rz_geoms>> shards;
 
     ~rz_geoms();
 };
@@ -171,6 +199,17 @@ bool read_wkb(const uint8_t* buf, size_t len, Flattener& f, bool* keep);
 bool read_wkt(const char* s, Flattener& f, bool* keep);
 
 void finish_geoms(rz_geoms* g);
+
+// rz_geoms_from_soa: the caller's SoA form -> pools + parts table, written by `threads` threads straight into
+// their final (page-locked) place: contiguous geometry ranges of equal coordinate counts, exact offsets from a
+// counting pass, copy + extents in one sweep.  Same result as feeding the Flattener one geometry at a time
+// (tests/test_host.py).  Returns RZ_OK or an error code with `err` set.
+int flatten_soa(const rz_geom_soa* soa, rz_geoms* g, unsigned threads, std::string& err);
+// tag[] of a pool (part id | TAG_CLOSED | TAG_SEQ_END), rebuilt from the parts table and the sequence lists
+// when a flattening path did not write it (the device never needs the host copy)
+void ensure_tags(rz_geoms* g, int kind);
+// the parts keep[0] < keep[1] < ... of `src` as a geometry set of their own (multi-device shards)
+rz_geoms* subset_parts(const rz_geoms* src, const uint32_t* keep, size_t n_keep, unsigned threads);
 
 int build_raster_info(const rz_raw_raster_info* raw, const rz_geoms* g, rz_raster_info* out, std::string& err);
 int64_t group_keys(const char* const* keys, uint64_t n, int32_t* band_of_geom, uint64_t* band_first);

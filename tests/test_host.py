@@ -160,3 +160,43 @@ def test_threaded_wkb_ingestion_equals_serial(monkeypatch):
     monkeypatch.setenv("RZ_PARSE_THREADS", "3")
     with pytest.raises(RuntimeError, match="Cannot parse geometry"):
         core.Geoms.from_wkb(geoms[:600] + [b"\x01\x03\x00\x00\x00\x01"] + geoms[600:])
+
+
+def test_parallel_soa_ingestion_equals_wkb_flattening(monkeypatch):
+    """rz_geoms_from_soa writes the pools with several threads at exact offsets (counting pass + copy/extents
+    sweep): pools, lazily rebuilt tags, parts table and bounds must equal what the streaming Flattener makes of
+    the same geometries (WKB route), for any thread count - unclosed rings, closed line strings, collections, empty
+    sequences and non-finite coordinates included."""
+    import synth
+    from oracle import wkt2wkb as W
+
+    geoms = synth.mixed_geometries(23, 700, 512, 512)
+    geoms[3] = W.wkt_to_wkb("POLYGON ((0 0, 4 0, 4 4))")  # unclosed ring: closed by the flattener
+    geoms[4] = W.wkt_to_wkb("POLYGON ((0 0, 4 0, 4 4, 0 0), (1 1, 2 1, 2 2))")
+    geoms[5] = W.wkt_to_wkb("LINESTRING (0 0, 1 1, 0 0)")
+    geoms[600] = W.wkt_to_wkb("GEOMETRYCOLLECTION (POINT (1 2), LINESTRING (0 0, 3 3), POLYGON ((0 0, 4 0, 4 4, 0 0)))")
+    ref = core.Geoms.from_wkb(geoms)
+    soa = synth.wkb_to_soa(geoms)
+    rk, rg = ref.parts()
+    for threads in ("1", "2", "5", "16"):
+        monkeypatch.setenv("RZ_PARSE_THREADS", threads)
+        g = core.Geoms.from_soa(*soa)
+        k, pg = g.parts()
+        assert len(g) == len(ref) and g.bounds() == ref.bounds()
+        assert np.array_equal(k, rk) and np.array_equal(pg, rg)
+        for kind in range(3):
+            for a, b in zip(g.pool(kind), ref.pool(kind)):
+                assert np.array_equal(a, b, equal_nan=True)
+    # an empty sequence, an empty part and a NaN coordinate
+    gpo = np.array([0, 1, 2, 3], np.uint64)
+    kinds = np.array([0, 1, 0], np.uint8)
+    pso = np.array([0, 2, 2, 3], np.uint64)
+    sco = np.array([0, 0, 4, 7], np.uint64)
+    x = np.array([0, 4, 4, 0, 1, np.nan, 3.0])
+    y = np.array([0, 0, 4, 0, 1, 2, 3.0])
+    g = core.Geoms.from_soa(gpo, kinds, pso, sco, x, y)
+    px, py, pt = g.pool(0)
+    assert len(g) == 3 and g.n_parts == 3 and len(px) == 4 + 4  # second ring gets its closing vertex (NaN != NaN)
+    assert [i for i in range(8) if pt[i] & 0x80000000] == [3, 7] and (pt & 0x3FFFFFFF).tolist() == [0] * 4 + [2] * 4
+    with pytest.raises(RuntimeError, match="Invalid part kind"):
+        core.Geoms.from_soa(gpo, np.array([0, 9, 0], np.uint8), pso, sco, x, y)
