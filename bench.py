@@ -1,16 +1,24 @@
 #!/usr/bin/env python
-"""bench.py — headline benchmark of the B200 burn path.
+"""bench.py — benchmark of the B200 burn path on every BASELINE.json config.
 
     python bench.py --gpus N --steps K --warmup W            # our arm (one rank per GPU under torchrun)
     python bench.py --impl reference --steps K --warmup W    # CPU restatement of the reference (oracle)
 
-Workload (BASELINE.json configs[3], the one `north_star`'s target is quoted on): 1M synthetic star
-polygons (100..300 vertices, seed 4) -> 65536 x 65536 float32 grid, fun=sum, background=NaN.  With
-N GPUs the raster is split into N row bands (no collective; strong scaling: total work is fixed).
+Headline workload (BASELINE.json configs[3], the one `north_star`'s target is quoted on): 1M synthetic star
+polygons (100..300 vertices, seed 4) -> 65536 x 65536 float32 grid, fun=sum, background=NaN.  The other configs
+(c1 10k polygons -> 4096^2 f64 sum; c2 100k mixed geometries -> 16384^2 count/any; c3 100k polygons, by = 32
+layers, first/last/min/max int32 on 8192^2; c5 10M parcels -> sparse triplets over 131072^2) ride along in the same
+JSON line under "other_configs", each with its own ms, roofline, cpu_baseline, e2e and parity_vs_oracle.
 
-One "step" = one full rasterisation.  `value` is device-resident throughput (geometry already in
-HBM, raster left in HBM); `e2e` goes through the public call with pinned HOST buffers: geometry
-host->device and raster device->host inside the timed region.
+With N GPUs a dense raster is split into N row bands (no collective; strong scaling: total work is fixed), each rank
+burning the parts the library cuts out for its band (rz_geoms_row_shard); the sparse config is split into N
+contiguous geometry ranges inside ONE library call (rz_rasterize_sparse_multi).
+
+One "step" = one full rasterisation.  `value` is device-resident throughput (geometry already in HBM, raster left
+in HBM).  `e2e` is the whole call a user makes, from host coordinate arrays to a host raster: flattening
+(rz_geoms_from_soa), the upload, the burn and the copy back into ONE pinned host array, through the library's
+multi-device entry point driven by rank 0 over all N GPUs.  Every rank checks rows of its own band (or a sampled
+geometry range of the sparse stream) against the CPU oracle, bit for bit, at every N.
 """
 from __future__ import annotations
 
@@ -30,50 +38,118 @@ sys.path.insert(0, str(ROOT))
 sys.path.insert(0, str(ROOT / "tests"))
 
 WORKLOADS = {
-    # name: (n_polys, vmin, vmax, rho, rows, cols, dtype, fun, seed)
-    "c4": dict(n=1_000_000, vmin=100, vmax=300, rho=48.0, rows=65536, cols=65536, dtype="float32", fun="sum", seed=4,
+    "c4": dict(kind="stars", n=1_000_000, vmin=100, vmax=300, rho=48.0, rows=65536, cols=65536, seed=4,
+               funs=[("sum", "float32", "nan")], cpu_rows=4096, cpu_threads=1,
                desc="1M star polygons (100-300 vertices) -> 65536x65536 f32, fun=sum, bg=NaN"),
-    "c1": dict(n=10_000, vmin=64, vmax=64, rho=82.0, rows=4096, cols=4096, dtype="float64", fun="sum", seed=1,
+    "c1": dict(kind="stars", n=10_000, vmin=64, vmax=64, rho=82.0, rows=4096, cols=4096, seed=1,
+               funs=[("sum", "float64", "nan")], cpu_rows=4096, cpu_threads=1,
                desc="10k 64-vertex star polygons -> 4096x4096 f64, fun=sum, bg=NaN"),
-    "tiny": dict(n=2_000, vmin=16, vmax=48, rho=24.0, rows=1024, cols=1024, dtype="float32", fun="sum", seed=7,
+    "c2": dict(kind="mixed", n=100_000, rows=16384, cols=16384, seed=2,
+               funs=[("count", "uint32", 0), ("any", "uint8", 0)], cpu_rows=2048, cpu_threads=1,
+               desc="100k mixed geometries (60% polygons, 25% lines, 15% points) -> 16384x16384, fun=count u32 / any u8"),
+    "c3": dict(kind="layers", n=100_000, vmin=64, vmax=64, rho=256.0, rows=8192, cols=8192, seed=3,
+               funs=[("first", "int32", 0), ("last", "int32", 0), ("min", "int32", 0), ("max", "int32", 0)], cpu_rows=512,
+               cpu_threads=32,
+               desc="100k star polygons (rho 256), by = 32 layers -> 32x8192x8192 i32, fun=first/last/min/max"),
+    "c5": dict(kind="parcels", n=10_000_000, rows=131072, cols=131072, seed=5, funs=[("sum", "float32", "nan")],
+               cpu_geoms=200_000, cpu_threads=1,
+               desc="10M parcels (jittered quads, side 6-14 px) over 131072x131072, sparse triplets, f32 sum"),
+    "tiny": dict(kind="stars", n=2_000, vmin=16, vmax=48, rho=24.0, rows=1024, cols=1024, seed=7,
+                 funs=[("sum", "float32", "nan")], cpu_rows=1024, cpu_threads=1,
                  desc="2k star polygons -> 1024x1024 f32 (CI smoke size)"),
 }
 
 
+def bg_of(v):
+    return np.nan if v == "nan" else v
+
+
 def make_workload(name: str, scale: float = 1.0):
+    """-> dict with the rz_geom_soa arrays (one part and one sequence per geometry), field values, `by` keys."""
     import synth
 
     w = dict(WORKLOADS[name])
-    if scale != 1.0:  # shrink polygons and grid together (keeps density)
+    if scale != 1.0:  # shrink geometry count and grid together (keeps density)
         w["n"] = max(1, int(w["n"] * scale))
         side = max(64, int(w["rows"] * scale ** 0.5) // 64 * 64)
         w["rows"] = w["cols"] = side
-    x, y, off = synth.star_polygons(w["seed"], w["n"], w["vmin"], w["vmax"], w["rho"], w["cols"], w["rows"])
-    vals = synth.splitmix_u(w["seed"], w["n"], 9).astype(w["dtype"])
-    return w, x, y, off, vals
+        if "cpu_geoms" in w:
+            w["cpu_geoms"] = max(1, int(w["cpu_geoms"] * scale))
+    n, rows, cols, seed = w["n"], w["rows"], w["cols"], w["seed"]
+    w["by"] = None
+    if w["kind"] in ("stars", "layers"):
+        x, y, off = synth.star_polygons(seed, n, w["vmin"], w["vmax"], w["rho"], cols, rows)
+        ar = np.arange(n + 1, dtype=np.uint64)
+        w["soa"] = (ar, np.zeros(n, np.uint8), ar, off, x, y)
+        if w["kind"] == "layers":
+            idx = np.arange(n, dtype=np.int64)
+            w["field"] = (1 + (idx * 2654435761 % 10**6)).astype(np.int32)
+            w["by"] = [str(i % 32) for i in range(n)]
+        else:
+            u = synth.splitmix_u(seed, n, 9)
+            w["field"] = (100.0 * u if name == "c1" else u).astype(w["funs"][0][1])
+    elif w["kind"] == "mixed":
+        w["soa"] = synth.config2_soa(seed, n, rows)
+        w["field"] = 1
+    elif w["kind"] == "parcels":
+        x, y, off = synth.parcels(seed, n, cols, rows)
+        ar = np.arange(n + 1, dtype=np.uint64)
+        w["soa"] = (ar, np.zeros(n, np.uint8), ar, off, x, y)
+        w["field"] = synth.splitmix_u(seed, n, 20).astype(np.float32)
+    w["n_vertices"] = int(len(w["soa"][4]))
+    return w
 
 
 def band_of(rank: int, world: int, rows: int):
-    r0 = rows * rank // world
-    r1 = rows * (rank + 1) // world
-    return r0, r1
+    return rows * rank // world, rows * (rank + 1) // world
 
 
-def select_band_polygons(x, y, off, vals, rows_total, r0, r1):
-    """Polygons whose y-extent can touch raster rows [r0, r1) (world y = rows_total - pixel y; res 1).
-    Order is preserved, so results equal the unsharded run."""
-    o = off.astype(np.int64)
-    ymin = np.minimum.reduceat(y, o[:-1])
-    ymax = np.maximum.reduceat(y, o[:-1])
-    # pixel rows covered: [rows_total - ymax, rows_total - ymin]; keep a 1-row margin
-    keep = (rows_total - ymax <= r1 + 1) & (rows_total - ymin >= r0 - 1)
-    if keep.all():
-        return x, y, off, vals
-    cnt = (o[1:] - o[:-1])[keep]
-    idx = np.repeat(o[:-1][keep], cnt) + (np.arange(int(cnt.sum())) - np.repeat(np.cumsum(cnt) - cnt, cnt))
-    noff = np.zeros(len(cnt) + 1, np.uint64)
-    noff[1:] = np.cumsum(cnt)
-    return x[idx], y[idx], noff, vals[keep]
+def geoms_touching_rows(w, r0, r1, margin=3):
+    """Mask of the geometries whose y-extent can touch raster rows [r0, r1) (extent (0,0,cols,rows), res 1: world
+    y = rows - pixel y).  Used only to cut the ORACLE's input down to a row slice."""
+    sco, y = w["soa"][3].astype(np.int64), w["soa"][5]
+    ymin = np.minimum.reduceat(y, sco[:-1])
+    ymax = np.maximum.reduceat(y, sco[:-1])
+    return (w["rows"] - ymax <= r1 + margin) & (w["rows"] - ymin >= r0 - margin)
+
+
+def oracle_geoms(w, keep):
+    """oracle.Geoms of the kept geometries + their field values and `by` keys (order preserved)."""
+    import oracle
+    import synth
+
+    sel = synth.soa_select(w["soa"], keep)
+    if w["kind"] == "mixed":
+        g = oracle.Geoms.from_wkb(synth.soa_to_wkb(sel))
+    else:
+        g = oracle.Geoms.from_rings(sel[4], sel[5], sel[3])
+    field = w["field"][keep] if np.ndim(w["field"]) else w["field"]
+    by = None if w["by"] is None else [b for b, k in zip(w["by"], keep) if k]
+    return g, field, by, int(keep.sum())
+
+
+def oracle_rows(w, fun, dtype, bg, r0, r1, threads=1, repeat=1):
+    """The oracle's raster rows [r0, r1) of the workload (all bands) -> (array [B][r1-r0][cols], seconds, #geometries)."""
+    import oracle
+
+    keep = geoms_touching_rows(w, r0, r1)
+    g, field, by, n_s = oracle_geoms(w, keep)
+    ri = oracle.raster_info(None, shape=(r1 - r0, w["cols"]), extent=(0.0, float(w["rows"] - r1), float(w["cols"]), float(w["rows"] - r0)))
+    if by is not None:  # every band must exist even if the slice misses one: keep the full key set's order
+        full = sorted(set(w["by"]))
+        have = sorted(set(by))
+    best = None
+    for _ in range(repeat):
+        t = time.perf_counter()
+        out, names = oracle.rasterize_dense(g, ri, fun, dtype, field, None, by, bg, False, threads)
+        sec = time.perf_counter() - t
+        best = sec if best is None else min(best, sec)
+    if by is not None and have != full:  # bands without a geometry in the slice stay background
+        big = np.full((len(full),) + out.shape[1:], bg, out.dtype)
+        for i, nm in enumerate(names):
+            big[full.index(nm)] = out[i]
+        out = big
+    return out, best, n_s
 
 
 class ClockSampler:
@@ -177,8 +253,7 @@ class ClockSampler:
 def bind_to_gpu_numa_node(gpu_index: int):
     """Pin this rank to the CPUs NVML reports as local to its GPU, so that the pinned host buffers of the
     end-to-end path (geometry pools, output raster) are first-touched on the NUMA node the GPU's PCIe link
-    hangs off.  With 8 ranks streaming 17 GB of raster to the host at once, cross-socket traffic is what
-    limits the copies.  Best effort: returns the CPU list or None."""
+    hangs off.  Best effort: returns the CPU list or None."""
     try:
         import pynvml
 
@@ -210,55 +285,84 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def config_of(name, w, scale, world, engine):
+    """The `config` object of a JSON line (the reference arm prints the same keys)."""
+    return {"workload": f"{name}: {w['desc']}", "scale": scale,
+            "parallelism": (f"geometry-ranges x{world}" if w["kind"] == "parcels" else f"row-bands x{world}"),
+            "l2": "inputs (vertex pools + record buffers + raster) are far larger than the 126 MB L2" if name in ("c4", "c5", "c3")
+                  else "every step rewrites the whole raster (larger than L2) from cold record buffers",
+            "engine": engine}
+
+
 # ------------------------------------------------------------------------------------------------
 # CPU arm: the oracle (C++ restatement of the reference's CPU algorithm) on a bounded sample
 # ------------------------------------------------------------------------------------------------
-def cpu_sample(w, x, y, off, vals, sample_rows: int):
-    """Rows [0, sample_rows) of the workload's raster with every polygon that can touch them; the
-    oracle burns them onto a sample_rows x cols grid aligned with the full grid."""
+def cpu_threads_for(w):
+    # the reference parallelises over `by` bands only (rust/src/rasterize.rs:89-101)
+    return 1 if w["by"] is None else max(1, min(w["cpu_threads"], os.cpu_count() or 1, len(set(w["by"]))))
+
+
+def cpu_dense_sample(w, fun, dtype, bg, repeat=1):
+    rows = min(w["rows"], w["cpu_rows"])
+    threads = cpu_threads_for(w)
+    out, sec, n_s = oracle_rows(w, fun, dtype, bg, 0, rows, threads, repeat)
+    n_b = 1 if w["by"] is None else len(set(w["by"]))
+    mpx = n_b * rows * w["cols"] / sec / 1e6
+    sample = (f"rows [0,{rows}) of the {n_b}x{w['rows']}x{w['cols']} grid with the {n_s} geometries touching them; C++ "
+              f"restatement of the rusterize CPU algorithm (oracle/rz_oracle.cpp), {threads} thread(s): the reference "
+              "parallelises over `by` bands only")
+    return out, {"value": mpx, "unit": "Mpixel/s", "cores": threads, "kind": "port", "sample": sample, "seconds": sec,
+                 "host_cores_available": os.cpu_count()}, rows
+
+
+def cpu_sparse_sample(w, dtype, bg):
     import oracle
 
-    sx, sy, soff, svals = select_band_polygons(x, y, off, vals, w["rows"], 0, sample_rows)
-    g = oracle.Geoms.from_rings(sx, sy, soff)
-    ri = oracle.raster_info(None, shape=(sample_rows, w["cols"]),
-                            extent=(0.0, float(w["rows"] - sample_rows), float(w["cols"]), float(w["rows"])))
-    return g, ri, svals, len(soff) - 1
-
-
-def time_oracle(w, g, ri, svals, steps: int, warmup: int):
-    import oracle
-
-    bg = np.nan if w["dtype"].startswith("float") else 0
-    ts = []
-    out = None
-    for i in range(warmup + steps):
-        t = time.perf_counter()
-        out, _ = oracle.rasterize_dense(g, ri, w["fun"], w["dtype"], svals, None, None, bg, threads=1)
-        if i >= warmup:
-            ts.append(time.perf_counter() - t)
-    return float(np.mean(ts)), out
+    m = min(w["n"], w["cpu_geoms"])
+    keep = np.zeros(w["n"], bool)
+    keep[:m] = True
+    g, field, by, _ = oracle_geoms(w, keep)
+    ri = oracle.raster_info(None, shape=(w["rows"], w["cols"]), extent=(0.0, 0.0, float(w["cols"]), float(w["rows"])))
+    t = time.perf_counter()
+    sp = oracle.rasterize_sparse(g, ri, "sum", dtype, field, None, None, bg)
+    sec = time.perf_counter() - t
+    # rate-normalised to the whole extent: the sample's geometries are 1/k of the job
+    mpx = w["rows"] * w["cols"] * (m / w["n"]) / sec / 1e6
+    return sp, {"value": mpx, "unit": "Mpixel/s", "cores": 1, "kind": "port", "seconds": sec,
+                "sample": f"the first {m} of {w['n']} parcels on the full extent (sparse stream), rate-normalised by geometry "
+                          "count; oracle/rz_oracle.cpp, 1 thread", "polygons_per_s": m / sec,
+                "triplets_per_s": len(sp["rows"]) / sec, "host_cores_available": os.cpu_count()}, m
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    w, x, y, off, vals = make_workload(args.workload, args.scale)
-    sample_rows = min(w["rows"], args.cpu_sample_rows)
-    g, ri, svals, n_s = cpu_sample(w, x, y, off, vals, sample_rows)
-    sec, _ = time_oracle(w, g, ri, svals, args.steps, args.warmup)
-    mpx = sample_rows * w["cols"] / sec / 1e6
-    sample = (f"rows [0,{sample_rows}) of the {w['rows']}x{w['cols']} grid with the {n_s} polygons touching them; "
-              "C++ restatement of the rusterize CPU algorithm (oracle/rz_oracle.cpp), 1 thread because the "
-              "reference parallelises over `by` bands only and this workload has one band")
+    name = args.workload
+    w = make_workload(name, args.scale)
+    fun, dtype, bgv = w["funs"][0]
+    bg = bg_of(bgv)
+    secs = []
+    if w["kind"] == "parcels":
+        for i in range(args.warmup + args.steps):
+            _, cpu, _ = cpu_sparse_sample(w, dtype, bg)
+            if i >= args.warmup:
+                secs.append(cpu["seconds"])
+    else:
+        for i in range(args.warmup + args.steps):
+            _, cpu, _ = cpu_dense_sample(w, fun, dtype, bg)
+            if i >= args.warmup:
+                secs.append(cpu["seconds"])
+    sec = float(np.mean(secs))
+    mpx = cpu["value"] * cpu["seconds"] / sec
+    cpu = dict(cpu, value=mpx, seconds=sec)
     line = {
         "impl": "reference", "metric": "output_Mpixels_per_s", "value": mpx, "unit": "Mpixel/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
-        "scaling": "strong", "vs_baseline": None, "dtype": "f64 geometry / %s values" % w["dtype"],
-        "data": "synthetic", "config": {"workload": f"{args.workload}: {w['desc']}", "scale": args.scale},
-        "polygons_per_s": n_s / sec,
-        "cpu_baseline": {"value": mpx, "unit": "Mpixel/s", "cores": 1, "kind": "port", "sample": sample,
-                         "host_cores_available": os.cpu_count()},
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64 geometry / %s values" % dtype,
+        "data": "synthetic", "config": config_of(name, w, args.scale, args.gpus, "tile-binned" if w["kind"] != "mixed" else "crossing-records"),
+        "polygons_per_s": w["n"] * (mpx * 1e6 / (w["rows"] * w["cols"] * (1 if w["by"] is None else len(set(w["by"]))))),
+        "cpu_baseline": cpu,
         "e2e": {"value": mpx, "unit": "Mpixel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
@@ -268,203 +372,449 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
-def run_b200(args):
-    import torch
-    import torch.distributed as dist
+class Env:
+    """Per-process state of the GPU arm: ranks, streams, barriers."""
 
-    from rusterize_b200 import _lib, core
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device; the burn path has no CPU fallback (use --impl reference)")
-    torch.cuda.set_device(local)
-    numa = bind_to_gpu_numa_node(local)  # before any large host allocation: first touch decides the NUMA node
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        self.torch, self.dist, self.args = torch, dist, args
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device; the burn path has no CPU fallback (use --impl reference)")
+        torch.cuda.set_device(self.local)
+        self.numa = bind_to_gpu_numa_node(self.local)  # before any large host allocation
+        self.cpu_group = None
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
+            self.cpu_group = dist.new_group(backend="gloo")  # host-side waits and object gathers
+        # A dedicated (non-default) stream: the library launches on the stream handle it is given and the timing
+        # events are recorded on the same stream.
+        self.tstream = torch.cuda.Stream()
+        torch.cuda.set_stream(self.tstream)
+        self.stream = self.tstream.cuda_stream
+        assert self.stream != 0
+        self.peak, self.peak_src = peaks()
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
 
-    w, x, y, off, vals = make_workload(args.workload, args.scale)
-    rows, cols = w["rows"], w["cols"]
-    r0, r1 = band_of(rank, world, rows)
-    bx, by, boff, bvals = select_band_polygons(x, y, off, vals, rows, r0, r1)
-    if world > 1:
-        del x, y, off, vals  # only rank 0 at N=1 needs the full set again (CPU baseline sample)
-    geoms = core.Geoms.from_polygons(bx, by, boff)
-    del bx, by
-    ri = core.raster_info(None, shape=(rows, cols), extent=(0.0, 0.0, float(cols), float(rows)))
-    dt = np.dtype(w["dtype"])
-    bg = np.nan if dt.kind == "f" else 0
-    tdt = {"float32": torch.float32, "float64": torch.float64}[w["dtype"]]
-    d_out = torch.empty((1, r1 - r0, cols), dtype=tdt, device="cuda")
-    # A dedicated (non-default) stream: the library launches on the stream handle it is given - handle 0
-    # would mean "use the library's own stream" - and the timing events below are recorded on the same stream.
-    tstream = torch.cuda.Stream()
-    torch.cuda.set_stream(tstream)
-    stream = tstream.cuda_stream
-    assert stream != 0
-    geoms.upload(local)
+    def host_barrier(self):  # ranks wait on the CPU (an NCCL barrier would spin on the GPUs rank 0 is about to use)
+        if self.world > 1:
+            self.dist.barrier(group=self.cpu_group)
 
-    eng_flag = {"auto": 0, "records": _lib.FLAG_NO_TILE_ENGINE, "tiles": _lib.FLAG_FORCE_TILE_ENGINE}[args.engine]
+    def max_over_ranks(self, v):
+        t = self.torch.tensor([float(x) for x in np.atleast_1d(v)], device="cuda", dtype=self.torch.float64)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return [float(x) for x in t.tolist()]
 
-    def step(flags=0, out=None):
-        return core.rasterize_dense(geoms, ri, w["fun"], w["dtype"], bvals, background=bg, device=local,
-                                    rows=(r0, r1), out=d_out.data_ptr() if out is None else out, stream=stream,
-                                    flags=flags | eng_flag, tile_bytes=args.tile_bytes)[1]
+    def sum_over_ranks(self, v):
+        t = self.torch.tensor([float(x) for x in np.atleast_1d(v)], device="cuda", dtype=self.torch.float64)
+        if self.world > 1:
+            self.dist.all_reduce(t)
+        return [float(x) for x in t.tolist()]
 
-    # ---- device-resident throughput --------------------------------------------------------------
-    for _ in range(args.warmup):
-        step()
-    sampler = ClockSampler(local)
-    barrier()
-    if rank == 0:
-        sampler.start()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t_wall = time.perf_counter()
-    ev0.record()
-    marks = []
-    for _ in range(args.steps):
-        step()
-        marks.append(torch.cuda.Event(enable_timing=True))
-        marks[-1].record()
-    ev1.record()
-    barrier()
-    wall_ms = (time.perf_counter() - t_wall) * 1e3 / args.steps  # cross-check of the CUDA-event time
-    each_ms = [a.elapsed_time(b) for a, b in zip([ev0] + marks[:-1], marks)]
-    clocks = sampler.stop() if rank == 0 else None
-    ms = ev0.elapsed_time(ev1) / args.steps
-    # per-stage CUDA-event timings come from a separate pass: the event synchronisations they need would
-    # otherwise sit inside the timed region
-    stats = [step(flags=_lib.FLAG_SYNC_STAGES) for _ in range(min(args.steps, 3))]
-    t = torch.tensor([ms], device="cuda", dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t.item())
+    def gather_objects(self, obj):
+        if self.world == 1:
+            return [obj]
+        out = [None] * self.world
+        self.dist.all_gather_object(out, obj, group=self.cpu_group)
+        return out
 
-    # ---- end to end through the public call with pinned host buffers -------------------------
-    e2e = None
-    if not args.no_e2e:
-        h_out = torch.empty((1, r1 - r0, cols), dtype=tdt).pin_memory()
-        h_np = h_out.numpy()
-        n_e2e = max(1, min(args.steps, args.e2e_steps))
-        step(flags=_lib.FLAG_FORCE_H2D | _lib.FLAG_SYNC_STAGES, out=h_np)  # warm
-        barrier()
-        t0 = time.perf_counter()
-        est, e_each = [], []
-        for _ in range(n_e2e):
-            t_s = time.perf_counter()
-            est.append(step(flags=_lib.FLAG_FORCE_H2D | _lib.FLAG_SYNC_STAGES, out=h_np))
-            e_each.append((time.perf_counter() - t_s) * 1e3)
-        barrier()
-        e_ms = (time.perf_counter() - t0) * 1e3 / n_e2e
-        t = torch.tensor([e_ms], device="cuda", dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e_ms = float(t.item())
-        hb = torch.tensor([est[-1]["h2d_bytes"], est[-1]["d2h_bytes"]], device="cuda", dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(hb)
-        # the host raster must equal the device-resident one (same rows sampled on both sides)
-        stride = max(1, (r1 - r0) // 64)
-        same = bool(np.array_equal(h_np[0, ::stride], d_out[0, ::stride].cpu().numpy(), equal_nan=True))
-        e2e = {"value": rows * cols / (e_ms / 1e3) / 1e6, "unit": "Mpixel/s", "ms_per_step": e_ms,
-               "h2d_bytes_per_step": int(hb[0].item()), "d2h_bytes_per_step": int(hb[1].item()), "steps": n_e2e,
-               "rank0_h2d_ms": est[-1]["h2d_ms"], "rank0_d2h_ms": est[-1]["d2h_ms"],
-               "rank0_ms_each_step": [round(v, 1) for v in e_each],
-               "rank0_lib_ms_each_step": [[round(s_["h2d_ms"], 1), round(s_["d2h_ms"], 1), round(s_["total_ms"], 1)] for s_ in est],
-               "host_equals_device_raster": same,
-               "checksum": float(np.nansum(h_np[0, ::stride], dtype=np.float64))}
 
-    # ---- gather per-rank stage stats -----------------------------------------------------------
-    keys = ["n_records", "n_crossings", "out_bytes", "kernel_launches"]
-    agg = torch.tensor([float(np.mean([s[k] for s in stats])) for k in keys], device="cuda", dtype=torch.float64)
-    stage = torch.tensor([float(np.mean([s[k] for s in stats])) for k in
-                          ["count_ms", "emit_ms", "sort_ms", "index_ms", "fill_ms"]], device="cuda", dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(agg)
-        dist.all_reduce(stage, op=dist.ReduceOp.MAX)
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return 0
-
-    peak, peak_src = peaks()
-    s0 = stats[-1]
-    fill_ms = float(np.mean([s["fill_ms"] for s in stats]))
-    other = None
+def roofline_of(env, w, fun, dtype, s0, fill_ms, mask_ms):
+    dt = np.dtype(dtype)
     if s0["engine"] == 1:
         # tile engine, span-fill kernel = tile_apply: compact inside-mask blocks (4 B / word) + one 16-byte block
         # descriptor per (part,tile) pair read once, raster written once
         tile_r = 64 if dt.itemsize <= 4 else 32
-        kernel = "tile_apply_kernel<%s, %s, %d>" % (w["dtype"], w["fun"], tile_r)
+        kernel = "tile_apply_kernel<%s, %s, %d>" % (dtype, fun, tile_r)
         fill_bytes = s0["n_mask_words"] * 4.0 + s0["n_records"] * 16.0 + s0["out_bytes"]
-        mask_ms = float(np.mean([s["count_ms"] for s in stats]))
         # tile_mask: world vertices (16 B) + tags (4 B) read once per mask unit, compact mask blocks written once
         mask_bytes = 20.0 * s0["n_poly_vertices"] + s0["n_mask_words"] * 4.0
-        other = {"kernel": "tile_mask_kernel<%d>" % tile_r, "ms_per_launch": mask_ms,
-                 "bytes_per_launch": mask_bytes, "achieved": mask_bytes / (mask_ms / 1e3) / 1e9,
-                 "frac": mask_bytes / (mask_ms / 1e3) / 1e9 / peak, "note": "instruction-issue bound (f64 edge math, one crossing per lane)"}
+        other = {"kernel": "tile_mask_kernel<%d>" % tile_r, "ms_per_launch": mask_ms, "bytes_per_launch": mask_bytes,
+                 "achieved": mask_bytes / (mask_ms / 1e3) / 1e9 if mask_ms else None,
+                 "frac": mask_bytes / (mask_ms / 1e3) / 1e9 / env.peak if mask_ms else None,
+                 "note": "instruction-issue bound (f64 edge math, one crossing per lane)"}
     else:
-        # record pipeline: crossing records read once + raster written once
-        kernel = "fill_kernel<%s, %s>" % (w["dtype"], w["fun"])
+        # record pipeline: crossing / pixel records (8 B) read once + raster written once
+        kernel = "fill_kernel<%s, %s>" % (dtype, fun)
         fill_bytes = 8.0 * s0["n_records"] + s0["out_bytes"]
-    achieved = fill_bytes / (fill_ms / 1e3) / 1e9
-    traffic = None  # measured DRAM bytes of one launch (ncu): captured for the 1-GPU launch only
-    tp = ROOT / "profiles" / "fill_traffic.json"
-    if tp.exists() and world == 1 and args.scale == 1.0:
-        try:
-            traffic = json.loads(tp.read_text()).get(args.workload)
-        except Exception:
-            pass
+        other = None
+    achieved = fill_bytes / (fill_ms / 1e3) / 1e9 if fill_ms else None
+    return {"bound": "hbm", "kernel": kernel, "achieved": achieved, "peak": env.peak, "unit": "GB/s",
+            "frac": achieved / env.peak if achieved else None, "traffic": None, "peak_source": env.peak_src,
+            "bytes_per_launch": fill_bytes, "ms_per_launch": fill_ms, "second_kernel": other}
 
-    # ---- CPU baseline on a bounded sample (rank 0, N=1 only) ---------------------------------
+
+def run_dense(env, name, w, headline):
+    """One dense config on this rank's row band.  Returns (on rank 0) the result dict."""
+    torch = env.torch
+    from rusterize_b200 import _lib, core
+
+    args, rank, world, local = env.args, env.rank, env.world, env.local
+    rows, cols = w["rows"], w["cols"]
+    n_b = 1 if w["by"] is None else len(set(w["by"]))
+    r0, r1 = band_of(rank, world, rows)
+    band, names = (None, None) if w["by"] is None else core.group_keys(w["by"])
+    t_f = time.perf_counter()
+    full = core.Geoms.from_soa(*w["soa"])
+    flatten_ms = (time.perf_counter() - t_f) * 1e3
+    ri = core.raster_info(None, shape=(rows, cols), extent=(0.0, 0.0, float(cols), float(rows)))
+    t_s = time.perf_counter()
+    geoms = full.row_shard(ri, r0, r1) if world > 1 else full
+    shard_ms = (time.perf_counter() - t_s) * 1e3
+    geoms.upload(local)
+    eng_flag = {"auto": 0, "records": _lib.FLAG_NO_TILE_ENGINE, "tiles": _lib.FLAG_FORCE_TILE_ENGINE}[args.engine]
+    steps, warmup = (args.steps, args.warmup) if headline else (max(3, min(args.steps, 5)), max(3, args.warmup))
+    per_fun, clocks, each_ms_head, wall_ms_head = {}, None, None, None
+    parity = {}
     cpu = None
-    if world == 1 and not args.no_cpu:
-        sample_rows = min(rows, args.cpu_sample_rows)
-        og, ori, svals, n_s = cpu_sample(w, x, y, off, vals, sample_rows)
-        sec, o_out = time_oracle(w, og, ori, svals, 1, 0)
-        # the sample doubles as a full-size parity check of the band's first rows
-        got = d_out[0, :sample_rows].cpu().numpy() if r0 == 0 else None
-        parity = None
-        if got is not None:
-            a, b = o_out[0], got
-            both_nan = np.isnan(a) & np.isnan(b)
-            parity = {"bit_exact": bool(np.array_equal(a, b, equal_nan=True)),
-                      "max_rel_err": float(np.max(np.where(both_nan, 0.0, np.abs(a - b) / np.maximum(np.abs(a), 1e-30))))}
-        cpu = {"value": sample_rows * cols / sec / 1e6, "unit": "Mpixel/s", "cores": 1, "kind": "port",
-               "sample": f"rows [0,{sample_rows}) of the grid with the {n_s} polygons touching them, oracle/rz_oracle.cpp, "
-                         "1 thread (the reference parallelises over `by` bands only)",
-               "seconds": sec, "parity_vs_gpu": parity, "host_cores_available": os.cpu_count()}
+    s_rows = min(512, r1 - r0)
+    for fi, (fun, dtype, bgv) in enumerate(w["funs"]):
+        bg = bg_of(bgv)
+        dt = np.dtype(dtype)
+        tdt = getattr(torch, dt.name)
+        d_out = torch.empty((n_b, r1 - r0, cols), dtype=tdt, device="cuda")
 
-    line = {
-        "metric": "output_Mpixels_per_s", "value": rows * cols / (ms_max / 1e3) / 1e6, "unit": "Mpixel/s",
-        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max,
-        "wall_ms_per_step_rank0": wall_ms, "ms_each_step_rank0": [round(v, 3) for v in each_ms],
-        "lib_total_ms_staged_pass": float(np.mean([s["total_ms"] for s in stats])),
-        "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-        "dtype": "f64 geometry / %s values" % w["dtype"], "data": "synthetic",
-        "config": {"workload": f"{args.workload}: {w['desc']}", "scale": args.scale, "parallelism": f"row-bands x{world}",
-                   "l2": "inputs (vertex pools + record buffers + raster) are far larger than the 126 MB L2",
-                   "engine": "tile-binned" if s0["engine"] == 1 else "crossing-records"},
-        "polygons_per_s": w["n"] / (ms_max / 1e3),
-        "stage_ms_max_over_ranks": dict(zip(["mask_build" if s0["engine"] == 1 else "count", "emit", "sort", "index", "fill"],
-                                            [float(v) for v in stage])),
-        "records": int(agg[0].item()), "crossings": int(agg[1].item()),
-        "gpu_launches": int(round(agg[3].item())) * args.steps,
-        "roofline": {"bound": "hbm", "kernel": kernel, "achieved": achieved, "peak": peak,
-                     "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                     "bytes_per_launch": fill_bytes, "ms_per_launch": fill_ms, "second_kernel": other},
-        "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
-        "rank0_cpu_affinity": (f"{len(numa)} CPUs local to the GPU (NVML)" if numa else "unchanged"),
-    }
+        def step(flags=0):
+            return core.rasterize_dense(geoms, ri, fun, dtype, w["field"], None, band, n_b, bg, device=local,
+                                        rows=(r0, r1), out=d_out.data_ptr(), stream=env.stream, flags=flags | eng_flag,
+                                        tile_bytes=args.tile_bytes)[1]
+
+        for _ in range(warmup):
+            step()
+        sampler = ClockSampler(local) if (headline and fi == 0 and rank == 0) else None
+        env.barrier()
+        if sampler:
+            sampler.start()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t_wall = time.perf_counter()
+        ev0.record()
+        marks = []
+        for _ in range(steps):
+            step()
+            marks.append(torch.cuda.Event(enable_timing=True))
+            marks[-1].record()
+        ev1.record()
+        env.barrier()
+        wall_ms = (time.perf_counter() - t_wall) * 1e3 / steps  # cross-check of the CUDA-event time
+        each_ms = [a.elapsed_time(b) for a, b in zip([ev0] + marks[:-1], marks)]
+        if sampler:
+            clocks = sampler.stop()
+            each_ms_head, wall_ms_head = each_ms, wall_ms
+        ms = ev0.elapsed_time(ev1) / steps
+        # per-stage CUDA-event timings come from a separate pass: the event synchronisations they need would
+        # otherwise sit inside the timed region
+        stats = [step(flags=_lib.FLAG_SYNC_STAGES) for _ in range(min(steps, 3))]
+        ms_max = env.max_over_ranks(ms)[0]
+        keys = ["n_records", "n_crossings", "out_bytes", "kernel_launches", "n_mask_words", "n_poly_vertices"]
+        agg = env.sum_over_ranks([float(np.mean([s[k] for s in stats])) for k in keys])
+        stage = env.max_over_ranks([float(np.mean([s[k] for s in stats])) for k in
+                                    ["count_ms", "emit_ms", "sort_ms", "index_ms", "fill_ms", "total_ms"]])
+        # ---- parity: the last rows of this rank's band against the oracle (every rank, every N) ----------
+        a0, a1 = r1 - s_rows, r1
+        exp, _, n_s = oracle_rows(w, fun, dtype, bg, a0, a1, cpu_threads_for(w))
+        got = d_out[:, a0 - r0:a1 - r0].cpu().numpy()
+        ok = bool(np.array_equal(exp, got, equal_nan=True))
+        par = {"rank": rank, "rows": [int(a0), int(a1)], "geometries": n_s, "bit_exact": ok}
+        # ---- CPU baseline (rank 0, N=1): the sample doubles as a parity check of the raster's first rows -------
+        if world == 1 and not args.no_cpu and fi == 0:
+            o_out, cpu, c_rows = cpu_dense_sample(w, fun, dtype, bg)
+            gtop = d_out[:, :c_rows].cpu().numpy()
+            cpu["parity_vs_gpu"] = {"bit_exact": bool(np.array_equal(o_out, gtop, equal_nan=True)), "rows": [0, int(c_rows)]}
+            par["bit_exact"] = par["bit_exact"] and cpu["parity_vs_gpu"]["bit_exact"]
+        parity[fun] = env.gather_objects(par)
+        s0 = dict(stats[-1])
+        for k, v in zip(keys, agg):
+            s0[k] = v
+        per_fun[fun] = {"dtype": dtype, "ms": ms_max, "Mpixel_per_s": n_b * rows * cols / (ms_max / 1e3) / 1e6,
+                        "polygons_per_s": w["n"] / (ms_max / 1e3),
+                        "engine": "tile-binned" if s0["engine"] == 1 else "crossing-records",
+                        "stage_ms_max_over_ranks": dict(zip(["mask_build" if s0["engine"] == 1 else "count", "emit", "sort",
+                                                             "index", "fill", "lib_total_staged_pass"], stage)),
+                        "records": int(agg[0]), "crossings": int(agg[1]), "launches_per_step": int(round(agg[3])),
+                        "host_syncs_per_step": int(stats[-1]["host_syncs"]),
+                        "roofline": roofline_of(env, w, fun, dtype, s0, stage[4], stage[0]),
+                        "whole_step_frac_of_hbm": (20.0 * agg[5] + agg[2]) / (ms_max / 1e3) / 1e9 / env.peak,
+                        "_steps": steps, "_warmup": warmup}
+        del d_out
+        torch.cuda.empty_cache()
+    res = {"per_fun": per_fun, "parity": parity, "cpu": cpu, "clocks": clocks, "each_ms": each_ms_head,
+           "wall_ms": wall_ms_head, "flatten_ms_rank0": flatten_ms, "row_shard_ms_rank0": shard_ms,
+           "n_vertices": w["n_vertices"]}
+    del geoms, full
+    return res
+
+
+def run_dense_e2e(env, name, w):
+    """Rank 0 only: the whole call from host coordinate arrays to ONE pinned host raster over all N GPUs."""
+    torch = env.torch
+    from rusterize_b200 import _lib, core
+
+    args, world = env.args, env.world
+    fun, dtype, bgv = w["funs"][0]
+    bg = bg_of(bgv)
+    rows, cols = w["rows"], w["cols"]
+    n_b = 1 if w["by"] is None else len(set(w["by"]))
+    band, names = (None, None) if w["by"] is None else core.group_keys(w["by"])
+    ri = core.raster_info(None, shape=(rows, cols), extent=(0.0, 0.0, float(cols), float(rows)))
+    h_out = torch.empty((n_b, rows, cols), dtype=getattr(torch, np.dtype(dtype).name)).pin_memory()
+    h_np = h_out.numpy()
+    devices = list(range(world))
+    eng_flag = {"auto": 0, "records": _lib.FLAG_NO_TILE_ENGINE, "tiles": _lib.FLAG_FORCE_TILE_ENGINE}[args.engine]
+
+    def call(g, flags):
+        return core.rasterize_dense(g, ri, fun, dtype, w["field"], None, band, n_b, bg, out=h_np, devices=devices,
+                                    flags=flags | eng_flag)[1]
+
+    n_e2e = max(1, args.e2e_steps)
+    # warm: page-locked pools / staging buffers exist, kernels are loaded
+    g = core.Geoms.from_soa(*w["soa"])
+    call(g, _lib.FLAG_SYNC_STAGES)
+    del g
+    whole, flat, st_last = [], [], None
+    for _ in range(n_e2e):
+        t0 = time.perf_counter()
+        g = core.Geoms.from_soa(*w["soa"])
+        t1 = time.perf_counter()
+        st_last = call(g, _lib.FLAG_SYNC_STAGES)
+        t2 = time.perf_counter()
+        whole.append((t2 - t0) * 1e3)
+        flat.append((t1 - t0) * 1e3)
+        g_keep = g
+        del g
+    # the same call on an already flattened handle (what a caller who keeps the handle pays): upload forced
+    cached = []
+    for _ in range(n_e2e):
+        t0 = time.perf_counter()
+        call(g_keep, _lib.FLAG_SYNC_STAGES | _lib.FLAG_FORCE_H2D)
+        cached.append((time.perf_counter() - t0) * 1e3)
+    e_ms = float(np.mean(whole))
+    per = st_last["per_device"]
+    stride = max(1, rows // 64)
+    return {"value": n_b * rows * cols / (e_ms / 1e3) / 1e6, "unit": "Mpixel/s", "ms_per_step": e_ms,
+            "h2d_bytes_per_step": int(st_last["h2d_bytes"]), "d2h_bytes_per_step": int(st_last["d2h_bytes"]), "steps": n_e2e,
+            "includes": "rz_geoms_from_soa (flatten into page-locked pools) + per-device part subsets + H2D + burn + D2H into one pinned host array",
+            "flatten_ms": float(np.mean(flat)), "flatten_Gvert_per_s": w["n_vertices"] / (float(np.mean(flat)) / 1e3) / 1e9,
+            "ms_each_step": [round(v, 1) for v in whole],
+            "e2e_handle_cached": {"ms_per_step": float(np.mean(cached)), "value": n_b * rows * cols / (float(np.mean(cached)) / 1e3) / 1e6,
+                                  "note": "geometry handle kept between calls (no flattening, part subsets cached), upload forced"},
+            "per_device": [{"device": d, "h2d_ms": round(p["h2d_ms"], 2), "d2h_ms": round(p["d2h_ms"], 2),
+                            "total_ms": round(p["total_ms"], 2), "h2d_MB": round(p["h2d_bytes"] / 1e6, 1),
+                            "d2h_MB": round(p["d2h_bytes"] / 1e6, 1)} for d, p in enumerate(per)],
+            "checksum": float(np.nansum(h_np[0, ::stride].astype(np.float64))), "_host": h_np}
+
+
+def run_sparse(env, name, w):
+    """Config 5: rank 0 drives all N GPUs through rz_rasterize_sparse_multi (contiguous geometry ranges balanced by
+    estimated work, streams concatenated by offset in one set of host arrays)."""
+    from rusterize_b200 import core
+
+    args, world = env.args, env.world
+    fun, dtype, bgv = w["funs"][0]
+    bg = bg_of(bgv)
+    rows, cols = w["rows"], w["cols"]
+    isz = np.dtype(dtype).itemsize
+    ri = core.raster_info(None, shape=(rows, cols), extent=(0.0, 0.0, float(cols), float(rows)))
+    devices = list(range(world))
+    steps = max(2, min(args.steps, 3))
+    g = core.Geoms.from_soa(*w["soa"])
+    sp = core.rasterize_sparse(g, ri, fun, dtype, w["field"], background=bg, devices=devices)  # warm (pools, uploads)
+    ms, sts = [], []
+    for _ in range(steps):
+        del sp
+        t0 = time.perf_counter()
+        sp = core.rasterize_sparse(g, ri, fun, dtype, w["field"], background=bg, devices=devices)
+        ms.append((time.perf_counter() - t0) * 1e3)
+        sts.append(sp["stats"])
+    # the whole call incl. flattening and upload
+    whole = []
+    for _ in range(max(1, args.e2e_steps)):
+        del sp
+        t0 = time.perf_counter()
+        g2 = core.Geoms.from_soa(*w["soa"])
+        sp = core.rasterize_sparse(g2, ri, fun, dtype, w["field"], background=bg, devices=devices)
+        whole.append((time.perf_counter() - t0) * 1e3)
+        st_e2e = sp["stats"]
+        del g2
+    st = sts[-1]
+    P = int(len(sp["rows"]))
+    X = int(st["n_crossings"])
+    t_ms = float(np.mean(ms))
+    fill_ms = float(np.mean([s["fill_ms"] for s in sts]))
+    a_fill = 8.0 * X + P * (16.0 + isz)
+    # ---- parity: sampled geometry ranges of the stream against the oracle --------------------------------
+    import oracle
+
+    n = w["n"]
+    m = min(n, 20_000)
+    checks = []
+    starts = sorted(set([0] + [n * i // world for i in range(1, world)] + [n - m]))
+    if len(starts) > 5:
+        starts = starts[:2] + starts[len(starts) // 2:len(starts) // 2 + 1] + starts[-2:]
+    ori = oracle.raster_info(None, shape=(rows, cols), extent=(0.0, 0.0, float(cols), float(rows)))
+    import synth
+
+    for a in starts:
+        a = max(0, min(a, n - m))
+        # offset of geometry a's first triplet = number of triplets of geometries [0, a): counted by a GPU call
+        if a == 0:
+            off = 0
+        elif a == n - m:
+            off = None  # the tail: aligned at the end of the stream
+        else:
+            keep = np.zeros(n, bool)
+            keep[:a] = True
+            sel = synth.soa_select(w["soa"], keep)
+            gh = core.Geoms.from_soa(*sel)
+            off = int(core.rasterize_sparse(gh, ri, fun, dtype, w["field"][:a], background=bg, devices=devices)["counts"][0])
+            del gh
+        keep = np.zeros(n, bool)
+        keep[a:a + m] = True
+        og, field, _, _ = oracle_geoms(w, keep)
+        osp = oracle.rasterize_sparse(og, ori, fun, dtype, field, None, None, bg)
+        k = len(osp["rows"])
+        lo = P - k if off is None else off
+        ok = all(np.array_equal(np.asarray(osp[key]), np.asarray(sp[key][lo:lo + k])) for key in ("rows", "cols", "data"))
+        checks.append({"geometries": [int(a), int(a + m)], "triplets": int(k), "stream_offset": int(lo), "bit_exact": bool(ok)})
+    cpu = None
+    if not args.no_cpu:
+        osp, cpu, m_c = cpu_sparse_sample(w, dtype, bg)
+        k = len(osp["rows"])
+        cpu["parity_vs_gpu"] = {"bit_exact": all(np.array_equal(np.asarray(osp[key]), np.asarray(sp[key][:k])) for key in ("rows", "cols", "data")),
+                                "geometries": [0, int(m_c)], "triplets": int(k)}
+    per = st["per_device"]
+    e_ms = float(np.mean(whole))
+    res = {"ms": t_ms, "Mpixel_per_s": rows * cols / (t_ms / 1e3) / 1e6, "polygons_per_s": n / (t_ms / 1e3),
+           "triplets": P, "triplets_per_s": P / (t_ms / 1e3), "crossings": X,
+           "note": "sparse output always lands in host memory: `ms` is the call on an uploaded handle (scans, sort, expand, D2H)",
+           "stage_ms_max_over_devices": {"crossings+sort": st["sort_ms"], "scans": st["index_ms"], "expand": st["fill_ms"], "d2h": st["d2h_ms"]},
+           "d2h_share": st["d2h_ms"] / max(st["total_ms"], 1e-9),
+           "roofline": {"bound": "hbm", "kernel": "poly_expand_kernel<f32> (triplet expand)", "achieved": a_fill / world / (fill_ms / 1e3) / 1e9,
+                        "peak": env.peak, "unit": "GB/s", "frac": a_fill / world / (fill_ms / 1e3) / 1e9 / env.peak, "traffic": None,
+                        "peak_source": env.peak_src, "bytes_per_launch": a_fill / world, "ms_per_launch": fill_ms,
+                        "formula": "A_fill(sparse) = 8*X + P*(16+s), per device"},
+           "cpu_baseline": cpu,
+           "e2e": {"value": rows * cols / (e_ms / 1e3) / 1e6, "unit": "Mpixel/s", "ms_per_step": e_ms,
+                   "h2d_bytes_per_step": int(st_e2e["h2d_bytes"]), "d2h_bytes_per_step": int(st_e2e["d2h_bytes"]),
+                   "includes": "rz_geoms_from_soa + geometry-range subsets + H2D + scans/sort/expand + D2H into one triplet stream",
+                   "ms_each_step": [round(v, 1) for v in whole]},
+           "per_device": [{"device": d, "total_ms": round(p["total_ms"], 2), "d2h_ms": round(p["d2h_ms"], 2),
+                           "expand_ms": round(p["fill_ms"], 2), "triplet_MB": round(p["out_bytes"] / 1e6, 1)} for d, p in enumerate(per)],
+           "parity_vs_oracle": {"bit_exact": all(c["bit_exact"] for c in checks), "checks": checks},
+           "config": config_of(name, w, args.scale, world, "sparse: scans + radix sort + expand"), "n_gpus": world}
+    del sp, g
+    return res
+
+
+def summarize_dense(env, name, w, res, e2e):
+    """Rank 0: the per-config object of the JSON line."""
+    first = w["funs"][0][0]
+    pf = res["per_fun"]
+    head = pf[first]
+    par = {f: {"bit_exact": all(p["bit_exact"] for p in ranks), "per_rank": ranks} for f, ranks in res["parity"].items()}
+    out = {"ms": head["ms"], "Mpixel_per_s": head["Mpixel_per_s"], "polygons_per_s": head["polygons_per_s"],
+           "fun": first, "roofline": head["roofline"], "cpu_baseline": res["cpu"], "e2e": e2e,
+           "parity_vs_oracle": {"bit_exact": all(v["bit_exact"] for v in par.values()), "per_fun": par},
+           "per_fun": {f: {k: v for k, v in d.items() if not k.startswith("_")} for f, d in pf.items()},
+           "config": config_of(name, w, env.args.scale, env.world, head["engine"]), "n_gpus": env.world,
+           "steps": head["_steps"], "warmup": head["_warmup"]}
+    return out
+
+
+def run_b200(args):
+    env = Env(args)
+    torch = env.torch
+    names = [args.workload] + [c for c in args.others.split(",") if c and c != "none" and c != args.workload]
+    results = {}
+    for name in names:
+        w = make_workload(name, args.scale)
+        headline = name == args.workload
+        if w["kind"] == "parcels":
+            env.barrier()
+            env.host_barrier()
+            if env.rank == 0:
+                results[name] = run_sparse(env, name, w)
+            env.host_barrier()
+            del w
+            continue
+        res = run_dense(env, name, w, headline)
+        torch.cuda.empty_cache()
+        env.barrier()
+        env.host_barrier()
+        e2e = None
+        if env.rank == 0 and not args.no_e2e:
+            e2e = run_dense_e2e(env, name, w)
+            # the host raster must equal the oracle rows checked above (rank 0's last band rows) - via the device copy
+            h_np = e2e.pop("_host")
+            fun, dtype, bgv = w["funs"][0]
+            a0, a1 = w["rows"] - min(512, w["rows"]), w["rows"]
+            exp, _, _ = oracle_rows(w, fun, dtype, bg_of(bgv), a0, a1, cpu_threads_for(w))
+            e2e["host_raster_vs_oracle"] = {"rows": [int(a0), int(a1)], "bit_exact": bool(np.array_equal(exp, h_np[:, a0:a1], equal_nan=True))}
+            del h_np
+        env.host_barrier()
+        if env.rank == 0:
+            results[name] = (summarize_dense(env, name, w, res, e2e), res)
+        del w
+
+    if env.rank != 0:
+        if env.world > 1:
+            env.dist.destroy_process_group()
+        return 0
+
+    hname = args.workload
+    hw = WORKLOADS[hname]
+    if hw["kind"] == "parcels":
+        body = results[hname]
+        line = {"metric": "output_Mpixels_per_s", "value": body["Mpixel_per_s"], "unit": "Mpixel/s", "n_gpus": env.world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": body["ms"], "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f64 geometry / float32 values", "data": "synthetic",
+                "gpu_launches": None}
+        line.update(body)
+    else:
+        summ, res = results[hname]
+        head = res["per_fun"][hw["funs"][0][0]]
+        tp = ROOT / "profiles" / "fill_traffic.json"
+        if tp.exists() and env.world == 1 and args.scale == 1.0:
+            try:
+                summ["roofline"]["traffic"] = json.loads(tp.read_text()).get(hname)
+            except Exception:
+                pass
+        line = {
+            "metric": "output_Mpixels_per_s", "value": head["Mpixel_per_s"], "unit": "Mpixel/s",
+            "n_gpus": env.world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": head["ms"],
+            "wall_ms_per_step_rank0": res["wall_ms"], "ms_each_step_rank0": [round(v, 3) for v in (res["each_ms"] or [])],
+            "lib_total_ms_staged_pass": head["stage_ms_max_over_ranks"]["lib_total_staged_pass"],
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64 geometry / %s values" % hw["funs"][0][1], "data": "synthetic",
+            "config": summ["config"], "polygons_per_s": head["polygons_per_s"],
+            "stage_ms_max_over_ranks": head["stage_ms_max_over_ranks"],
+            "records": head["records"], "crossings": head["crossings"],
+            "gpu_launches": head["launches_per_step"] * args.steps,
+            "host_syncs_per_step": head["host_syncs_per_step"],
+            "whole_step_frac_of_hbm": head["whole_step_frac_of_hbm"],
+            "flatten_ms_rank0": res["flatten_ms_rank0"], "row_shard_ms_rank0": res["row_shard_ms_rank0"],
+            "roofline": summ["roofline"], "cpu_baseline": summ["cpu_baseline"], "e2e": summ["e2e"],
+            "parity_vs_oracle": summ["parity_vs_oracle"], "clocks": res["clocks"],
+            "rank0_cpu_affinity": (f"{len(env.numa)} CPUs local to the GPU (NVML)" if env.numa else "unchanged"),
+        }
+    others = {}
+    for name in names:
+        if name == hname:
+            continue
+        r = results[name]
+        others[name] = r if isinstance(r, dict) else r[0]
+    line["other_configs"] = others
     print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    if env.world > 1:
+        env.dist.destroy_process_group()
     return 0
 
 
@@ -475,8 +825,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS))
-    ap.add_argument("--scale", type=float, default=1.0, help="shrink polygons and grid area by this factor")
-    ap.add_argument("--cpu-sample-rows", type=int, default=4096)
+    ap.add_argument("--others", default="c1,c2,c3,c5", help="configs reported under other_configs (comma list, or none)")
+    ap.add_argument("--scale", type=float, default=1.0, help="shrink geometry count and grid area by this factor")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--tile-bytes", type=int, default=0)
     ap.add_argument("--engine", default="auto", choices=["auto", "records", "tiles"])

@@ -102,6 +102,14 @@ int rz_geoms_upload(rz_geoms* g, int device, char* err, size_t errlen);
 /* Drop cached device copies so the next call pays the host->device transfer again. */
 void rz_geoms_evict(rz_geoms* g);
 void rz_geoms_free(rz_geoms* g);
+/* The parts of `g` that can write raster rows [row_begin, row_end) of the grid `ri`, as a geometry set of their
+ * own: same order, same geometry indices (field / by arrays of the full set still apply), so burning the shard
+ * with ctx->row_begin/row_end gives exactly those rows of the full result ("each GPU rasterises only
+ * the edges intersecting its band"; the cull is the y-extent test of rust/src/geo/edges.rs:105 with band-local
+ * bounds and a few rows of slack).  One process per GPU uses this to cut its share out of the full set;
+ * rz_rasterize_dense_multi does the same internally.  Free with rz_geoms_free. */
+rz_geoms* rz_geoms_row_shard(const rz_geoms* g, const rz_raster_info* ri, uint64_t row_begin, uint64_t row_end,
+                             int all_touched, char* err, size_t errlen);
 
 /* Introspection of the flattened form (tests, FFI debugging). Returned pointers live as long as g. */
 const uint8_t* rz_geoms_part_kind(const rz_geoms* g);
@@ -192,6 +200,22 @@ void rz_sparse_free(rz_sparse* s);
 int rz_sparse_build_array(const rz_context* ctx, uint64_t n_bands, const uint64_t* counts, const uint64_t* rows,
                           const uint64_t* cols, const void* data, void* out, rz_stats* stats, char* err,
                           size_t errlen);
+
+/* Multi-device variants (the reference's only parallel section is rayon over `by` bands,
+ * rust/src/rasterize.rs:89-101).  ONE call drives `n_devices` CUDA devices, one host thread per device, no
+ * collective on the data path; ctx->device and ctx->stream are ignored.
+ *   dense : device d owns the d-th of n_devices row bands of [row_begin,row_end); it uploads only the parts that
+ *           can write those rows and copies its rows straight into the caller's host array `out`
+ *           ([n_bands][rows][ncols], as rz_rasterize_dense; RZ_FLAG_OUT_ON_DEVICE is rejected).
+ *   sparse: the triplet stream is ordered band -> geometry -> burn order (rust/src/encoding/writers.rs:101-131), so
+ *           device d takes the d-th contiguous geometry range (ranges balanced by estimated work) and the streams
+ *           are concatenated by offset into one rz_sparse.
+ * Results are bit-identical to the single-device calls.  `stats` aggregates (sums of counts and bytes, maximum of
+ * the stage times); `per_device` (nullable) receives n_devices entries. */
+int rz_rasterize_dense_multi(rz_geoms* g, const rz_context* ctx, const int32_t* devices, int32_t n_devices, void* out,
+                             rz_stats* stats, rz_stats* per_device, char* err, size_t errlen);
+int rz_rasterize_sparse_multi(rz_geoms* g, const rz_context* ctx, const int32_t* devices, int32_t n_devices,
+                              rz_sparse** out, rz_stats* stats, rz_stats* per_device, char* err, size_t errlen);
 
 /* Device plumbing */
 int rz_device_count(void);

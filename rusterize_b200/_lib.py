@@ -92,6 +92,7 @@ SYMBOLS = {
     "rz_geoms_upload": (C.c_int, [C.c_void_p, C.c_int] + _ERR),
     "rz_geoms_evict": (None, [C.c_void_p]),
     "rz_geoms_free": (None, [C.c_void_p]),
+    "rz_geoms_row_shard": (C.c_void_p, [C.c_void_p, C.POINTER(RasterInfo), C.c_uint64, C.c_uint64, C.c_int] + _ERR),
     "rz_geoms_part_kind": (C.c_void_p, [C.c_void_p]),
     "rz_geoms_part_geom": (C.c_void_p, [C.c_void_p]),
     "rz_geoms_pool_len": (C.c_uint64, [C.c_void_p, C.c_int]),
@@ -102,6 +103,10 @@ SYMBOLS = {
     "rz_group_keys": (C.c_int64, [C.POINTER(C.c_char_p), C.c_uint64, C.c_void_p, C.c_void_p]),
     "rz_rasterize_dense": (C.c_int, [C.c_void_p, C.POINTER(Context), C.c_void_p, C.POINTER(Stats)] + _ERR),
     "rz_rasterize_sparse": (C.c_int, [C.c_void_p, C.POINTER(Context), C.POINTER(C.c_void_p), C.POINTER(Stats)] + _ERR),
+    "rz_rasterize_dense_multi": (C.c_int, [C.c_void_p, C.POINTER(Context), C.POINTER(C.c_int32), C.c_int32, C.c_void_p,
+                                           C.POINTER(Stats), C.POINTER(Stats)] + _ERR),
+    "rz_rasterize_sparse_multi": (C.c_int, [C.c_void_p, C.POINTER(Context), C.POINTER(C.c_int32), C.c_int32,
+                                            C.POINTER(C.c_void_p), C.POINTER(Stats), C.POINTER(Stats)] + _ERR),
     "rz_sparse_len": (C.c_uint64, [C.c_void_p]),
     "rz_sparse_n_bands": (C.c_uint64, [C.c_void_p]),
     "rz_sparse_rows": (C.c_void_p, [C.c_void_p]),

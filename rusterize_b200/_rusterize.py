@@ -257,8 +257,9 @@ def _rusterize(geometry, raw_raster_info, pypixel_fn, pydf=None, pyfield=None, p
     band, names = (None, ["band_1"])
     if by is not None:
         band, names = core.group_keys(by)
+    # every visible GPU takes a share of the job (row bands / geometry ranges); RZ_DEVICES narrows the list
     kw = dict(field=field, field_valid=field_valid, band_of_geom=band, n_bands=len(names), background=background,
-              all_touched=bool(pytouched))
+              all_touched=bool(pytouched), devices=core.default_devices())
     try:  # python/src/rusterize.rs:121-123
         if pyencoding == "sparse":
             sp = core.rasterize_sparse(geoms, ri, pypixel_fn, pydtype, **kw)

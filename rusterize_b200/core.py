@@ -105,6 +105,15 @@ class Geoms:
     def evict(self) -> None:
         lib().rz_geoms_evict(self._h)
 
+    def row_shard(self, ri, row_begin: int, row_end: int, all_touched: bool = False) -> "Geoms":
+        """The parts that can write raster rows [row_begin, row_end) of grid `ri`, as their own geometry set (same
+        order and geometry indices): what one GPU of a row-band sharded job is given."""
+        err = errbuf()
+        h = lib().rz_geoms_row_shard(self._h, C.byref(ri), int(row_begin), int(row_end), int(bool(all_touched)), err, len(err))
+        if not h:
+            raise ValueError(err.value.decode())
+        return Geoms(h)
+
     def parts(self):
         """(part_kind[u8], part_geom[u64]) of the flattened form."""
         L, n = lib(), self.n_parts
@@ -201,13 +210,31 @@ def _context(geoms, ri, fun, dtype, field, field_valid, band_of_geom, n_bands, b
     return ctx, dt, (f, bg, fv, band)
 
 
+def default_devices():
+    """Devices a call uses when none are named: every visible CUDA device, or the ordinals listed in RZ_DEVICES
+    (comma separated; e.g. RZ_DEVICES=0 keeps calls on one GPU)."""
+    import os
+
+    env = os.environ.get("RZ_DEVICES")
+    if env:
+        return [int(v) for v in env.split(",") if v.strip() != ""]
+    return list(range(max(1, lib().rz_device_count())))
+
+
+def _device_array(devices):
+    devs = [int(d) for d in devices]
+    return (C.c_int32 * len(devs))(*devs), len(devs)
+
+
 def rasterize_dense(geoms: Geoms, ri: RasterInfo, fun="last", dtype="float64", field=1, field_valid=None,
                     band_of_geom=None, n_bands=1, background=0, all_touched=False, out=None, device=0, rows=None,
-                    stream=None, flags=0, tile_bytes=0):
+                    stream=None, flags=0, tile_bytes=0, devices=None):
     """DenseArray::build (rust/src/rasterize.rs:71-116) on the GPU.
 
     `out`: None (a new numpy array is returned), a C-contiguous numpy array to fill, or an int
     device pointer (then RZ_FLAG_OUT_ON_DEVICE is implied and nothing is copied back).
+    `devices`: a list of CUDA ordinals -> one call over several GPUs (row bands, rz_rasterize_dense_multi); the
+    stats dict then aggregates and carries the per-device stats under "per_device".
     Returns (array_or_None, stats dict).  Shape [n_bands, rows, ncols]."""
     ctx, dt, keep = _context(geoms, ri, fun, dtype, field, field_valid, band_of_geom, n_bands, background,
                              all_touched, device, rows, stream, flags, tile_bytes)
@@ -224,21 +251,38 @@ def rasterize_dense(geoms: Geoms, ri: RasterInfo, fun="last", dtype="float64", f
         out_ptr = arr.ctypes.data
     st = Stats()
     err = errbuf()
+    if devices is not None and len(devices) > 0:
+        darr, nd = _device_array(devices)
+        per = (Stats * nd)()
+        rc = lib().rz_rasterize_dense_multi(geoms._h, C.byref(ctx), darr, nd, out_ptr, C.byref(st), per, err, len(err))
+        raise_for(rc, err)
+        d = st.as_dict()
+        d["per_device"] = [p.as_dict() for p in per]
+        return arr, d
     rc = lib().rz_rasterize_dense(geoms._h, C.byref(ctx), out_ptr, C.byref(st), err, len(err))
     raise_for(rc, err)
     return arr, st.as_dict()
 
 
 def rasterize_sparse(geoms: Geoms, ri: RasterInfo, fun="last", dtype="float64", field=1, field_valid=None,
-                     band_of_geom=None, n_bands=1, background=0, all_touched=False, device=0, stream=None, flags=0):
-    """SparseArray::build (rust/src/rasterize.rs:118-157) on the GPU -> dict(rows, cols, data, counts, stats)."""
+                     band_of_geom=None, n_bands=1, background=0, all_touched=False, device=0, stream=None, flags=0,
+                     devices=None):
+    """SparseArray::build (rust/src/rasterize.rs:118-157) on the GPU -> dict(rows, cols, data, counts, stats).
+    `devices`: a list of CUDA ordinals -> contiguous geometry ranges per GPU, streams concatenated by offset
+    (rz_rasterize_sparse_multi)."""
     ctx, dt, keep = _context(geoms, ri, fun, dtype, field, field_valid, band_of_geom, n_bands, background,
                              all_touched, device, None, stream, flags, 0)
     L = lib()
     h = C.c_void_p()
     st = Stats()
     err = errbuf()
-    rc = L.rz_rasterize_sparse(geoms._h, C.byref(ctx), C.byref(h), C.byref(st), err, len(err))
+    per = None
+    if devices is not None and len(devices) > 0:
+        darr, nd = _device_array(devices)
+        per = (Stats * nd)()
+        rc = L.rz_rasterize_sparse_multi(geoms._h, C.byref(ctx), darr, nd, C.byref(h), C.byref(st), per, err, len(err))
+    else:
+        rc = L.rz_rasterize_sparse(geoms._h, C.byref(ctx), C.byref(h), C.byref(st), err, len(err))
     raise_for(rc, err)
     owner = _SparseOwner(h)  # the arrays below are views of the library's buffers: freed with the last of them
     n, nb = L.rz_sparse_len(h), L.rz_sparse_n_bands(h)
@@ -250,9 +294,12 @@ def rasterize_sparse(geoms: Geoms, ri: RasterInfo, fun="last", dtype="float64", 
         buf._owner = owner
         return np.frombuffer(buf, dtype=t)
 
+    stats = st.as_dict()
+    if per is not None:
+        stats["per_device"] = [p.as_dict() for p in per]
     return dict(rows=view(L.rz_sparse_rows(h), n, np.uint64), cols=view(L.rz_sparse_cols(h), n, np.uint64),
                 data=view(L.rz_sparse_data(h), n, dt),
-                counts=view(L.rz_sparse_counts(h), nb, np.uint64).copy(), stats=st.as_dict())
+                counts=view(L.rz_sparse_counts(h), nb, np.uint64).copy(), stats=stats)
 
 
 class _SparseOwner:

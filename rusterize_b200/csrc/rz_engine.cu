@@ -9,6 +9,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <condition_variable>
+#include <functional>
+#include <limits>
 #include <memory>
 #include <string>
 #include <sys/mman.h>
@@ -1302,7 +1305,18 @@ static void sparse_expand(cudaStream_t s, const KParams& P, SparseLayout L, Devi
     }
 }
 
-static void rasterize_sparse(rz_geoms* g, const rz_context* ctx, rz_sparse* out, rz_stats* st) {
+// Multi-device calls: where a device's share of the triplet stream lands.  Once a device knows its per-band counts
+// it asks the sink for the element offset of each of its bands inside the final host arrays (the sink waits for
+// the counts of all devices, sizes the arrays once, and hands every device disjoint slices), then copies its
+// bands there straight from device memory.
+struct SparseSink {
+    virtual ~SparseSink() {}
+    // counts[b]: this device's triplets of band b -> elem_off[b]; the final arrays are then allocated
+    virtual void place(const std::vector<uint64_t>& counts, std::vector<uint64_t>& elem_off, char*& rows, char*& cols,
+                       char*& data) = 0;
+};
+
+static void rasterize_sparse(rz_geoms* g, const rz_context* ctx, rz_sparse* out, rz_stats* st, SparseSink* sink = nullptr) {
     const rz_raster_info& ri = ctx->raster_info;
     validate_lengths(g, ctx);
     const size_t isz = dtype_size(ctx->dtype);
@@ -1310,7 +1324,14 @@ static void rasterize_sparse(rz_geoms* g, const rz_context* ctx, rz_sparse* out,
     if (ctx->pixel_fn < 0 || ctx->pixel_fn > RZ_ANY) throw Error{RZ_VALUE_ERROR, "Unknown pixel function"};
     const uint32_t n_bands = ctx->band_of_geom ? (uint32_t)std::max(ctx->n_bands, 0) : 1u;
     out->counts.assign(n_bands, 0);
-    if (ri.nrows == 0 || ri.ncols == 0 || n_bands == 0) return;
+    // (a device of a multi-device call always reports its counts: the others wait for them)
+    auto place_nothing = [&]() {
+        if (!sink) return;
+        std::vector<uint64_t> off;
+        char *r = nullptr, *cc = nullptr, *d = nullptr;
+        sink->place(out->counts, off, r, cc, d);
+    };
+    if (ri.nrows == 0 || ri.ncols == 0 || n_bands == 0) return place_nothing();
     if (ri.nrows >= (1ull << 31) || ri.ncols >= (1ull << 31))
         throw Error{RZ_RUNTIME_ERROR, "Raster dimensions above 2^31 are not supported."};
     const uint32_t nv_poly = (uint32_t)g->pool[0].size(), nv_line = (uint32_t)g->pool[1].size(),
@@ -1383,7 +1404,7 @@ static void rasterize_sparse(rz_geoms* g, const rz_context* ctx, rz_sparse* out,
     S.n_line_vertices = nv_line;
     S.n_points = nv_pt;
     uint32_t launches = 0;
-    if (n_parts == 0) return;
+    if (n_parts == 0) return place_nothing();
 
     c.part_info.ensure((size_t)n_parts * sizeof(PartInfo));
     c.last_kept.ensure((size_t)n_parts * 4);
@@ -1570,9 +1591,18 @@ static void rasterize_sparse(rz_geoms* g, const rz_context* ctx, rz_sparse* out,
     CUDA_TRY(cudaEventRecord(c.ev[EV_COUNTED], s));
     // ---- expand ------------------------------------------------------------------------------------
     out->len = total;
-    out->rows = g_host_pool.get(total * 8);
-    out->cols = g_host_pool.get(total * 8);
-    out->data = g_host_pool.get(total * isz);
+    std::vector<uint64_t> sink_off;
+    char *h_rows = nullptr, *h_cols = nullptr, *h_data = nullptr;
+    if (sink) {
+        sink->place(out->counts, sink_off, h_rows, h_cols, h_data);
+    } else {
+        out->rows = g_host_pool.get(total * 8);
+        out->cols = g_host_pool.get(total * 8);
+        out->data = g_host_pool.get(total * isz);
+        h_rows = (char*)out->rows.p;
+        h_cols = (char*)out->cols.p;
+        h_data = (char*)out->data.p;
+    }
     if (total) {
         c.sp_rows.ensure(total * 8);
         c.sp_cols.ensure(total * 8);
@@ -1595,9 +1625,22 @@ static void rasterize_sparse(rz_geoms* g, const rz_context* ctx, rz_sparse* out,
         }
         CUDA_TRY(cudaGetLastError());
         CUDA_TRY(cudaEventRecord(c.ev[EV_EXPANDED], s));
-        CUDA_TRY(cudaMemcpyAsync(out->rows.p, c.sp_rows.p, total * 8, cudaMemcpyDeviceToHost, s));
-        CUDA_TRY(cudaMemcpyAsync(out->cols.p, c.sp_cols.p, total * 8, cudaMemcpyDeviceToHost, s));
-        CUDA_TRY(cudaMemcpyAsync(out->data.p, c.sp_data.p, total * isz, cudaMemcpyDeviceToHost, s));
+        if (!sink) {
+            CUDA_TRY(cudaMemcpyAsync(h_rows, c.sp_rows.p, total * 8, cudaMemcpyDeviceToHost, s));
+            CUDA_TRY(cudaMemcpyAsync(h_cols, c.sp_cols.p, total * 8, cudaMemcpyDeviceToHost, s));
+            CUDA_TRY(cudaMemcpyAsync(h_data, c.sp_data.p, total * isz, cudaMemcpyDeviceToHost, s));
+        } else {  // this device's stream is band-major; band b goes to its slice of band b of the final arrays
+            uint64_t at = 0;
+            for (uint32_t b = 0; b < n_bands; b++) {
+                const uint64_t n = out->counts[b], o = sink_off[b];
+                if (n) {
+                    CUDA_TRY(cudaMemcpyAsync(h_rows + o * 8, (char*)c.sp_rows.p + at * 8, n * 8, cudaMemcpyDeviceToHost, s));
+                    CUDA_TRY(cudaMemcpyAsync(h_cols + o * 8, (char*)c.sp_cols.p + at * 8, n * 8, cudaMemcpyDeviceToHost, s));
+                    CUDA_TRY(cudaMemcpyAsync(h_data + o * isz, (char*)c.sp_data.p + at * isz, n * isz, cudaMemcpyDeviceToHost, s));
+                }
+                at += n;
+            }
+        }
         S.d2h_bytes = total * (16 + isz);
     }
     CUDA_TRY(cudaEventRecord(c.ev[EV_END], s));
@@ -1719,6 +1762,334 @@ static void sparse_build_array(const rz_context* ctx, uint64_t n_bands, const ui
         st->h2d_bytes = (uint64_t)n * (16 + isz);
         st->d2h_bytes = out_dev ? 0 : out_bytes;
     }
+}
+
+// ------------------------------------------------------------------------------------------------
+// multi-device calls (one host thread per device, no data-path collective)
+// ------------------------------------------------------------------------------------------------
+// Dense: device d of D owns a band of raster rows of every band of the output; it is given the parts
+// that can write those rows - a part subset of the geometry set, in the same order, so every pixel sees its parts
+// in burn order and the result is bit-identical to the single-device one - uploads only those, and copies its rows
+// straight into the caller's [B][R][C] array.  Sparse: the stream is ordered band -> geometry -> burn order, so
+// devices take contiguous geometry ranges (balanced by a work estimate) and their streams are concatenated by
+// offset inside one set of host arrays (SparseSink).  Subsets are cached in the geometry handle.
+static void accumulate_stats(rz_stats& a, const rz_stats& b) {
+    a.n_parts += b.n_parts;
+    a.n_poly_vertices += b.n_poly_vertices;
+    a.n_line_vertices += b.n_line_vertices;
+    a.n_points += b.n_points;
+    a.n_records += b.n_records;
+    a.n_crossings += b.n_crossings;
+    a.n_tasks += b.n_tasks;
+    a.n_mask_words += b.n_mask_words;
+    a.h2d_bytes += b.h2d_bytes;
+    a.d2h_bytes += b.d2h_bytes;
+    a.out_bytes += b.out_bytes;
+    a.kernel_launches += b.kernel_launches;
+    a.host_syncs += b.host_syncs;
+    a.n_windows += b.n_windows;
+    a.key_bits = std::max(a.key_bits, b.key_bits);
+    a.sort_passes = std::max(a.sort_passes, b.sort_passes);
+    a.tile_width = std::max(a.tile_width, b.tile_width);
+    a.engine = std::max(a.engine, b.engine);
+    a.plan_cached = std::min(a.plan_cached, b.plan_cached);
+    // stage times: the slowest device (devices run concurrently)
+    a.h2d_ms = std::max(a.h2d_ms, b.h2d_ms);
+    a.count_ms = std::max(a.count_ms, b.count_ms);
+    a.emit_ms = std::max(a.emit_ms, b.emit_ms);
+    a.sort_ms = std::max(a.sort_ms, b.sort_ms);
+    a.index_ms = std::max(a.index_ms, b.index_ms);
+    a.fill_ms = std::max(a.fill_ms, b.fill_ms);
+    a.d2h_ms = std::max(a.d2h_ms, b.d2h_ms);
+    a.total_ms = std::max(a.total_ms, b.total_ms);
+}
+
+static uint64_t f64_bits(double v) {
+    uint64_t u;
+    std::memcpy(&u, &v, 8);
+    return u;
+}
+
+static std::shared_ptr<rz_geoms> cached_subset(rz_geoms* g, const std::vector<uint64_t>& key,
+                                               const std::function<void(std::vector<uint32_t>&)>& select) {
+    {
+        std::lock_guard<std::mutex> lk(g->mu);
+        auto it = g->shards.find(key);
+        if (it != g->shards.end()) return it->second;
+    }
+    std::vector<uint32_t> keep;
+    select(keep);
+    std::shared_ptr<rz_geoms> sub(subset_parts(g, keep.data(), keep.size(), 2));
+    std::lock_guard<std::mutex> lk(g->mu);
+    if (g->shards.size() >= 64) g->shards.clear();
+    g->shards[key] = sub;
+    return sub;
+}
+
+// world-y extent of a part: the parts table holds it for polygon parts, other kinds are scanned
+static void part_y_extent(const rz_geoms* g, uint32_t p, double& ylo, double& yhi) {
+    const int k = g->part_kind[p];
+    if (k == RZ_PART_POLYGON) {
+        ylo = g->part_ylo[p];
+        yhi = g->part_yhi[p];
+        return;
+    }
+    const double inf = std::numeric_limits<double>::infinity();
+    ylo = inf;
+    yhi = -inf;
+    const double* y = g->pool[k].y.data();
+    bool odd = false;
+    for (uint32_t v = g->part_vbeg[p]; v < g->part_vend[p]; v++) {
+        const double a = y[v];
+        if (a < ylo) ylo = a;
+        if (a > yhi) yhi = a;
+        odd |= !(a == a);
+    }
+    if (odd) {  // NaN ordinates: keep the part everywhere
+        ylo = -inf;
+        yhi = inf;
+    }
+}
+
+template <typename F> static void run_per_device(int n, F&& body, Error& first_error) {
+    std::vector<Error> errors((size_t)n, Error{RZ_OK, ""});
+    std::vector<std::thread> th;
+    for (int d = 0; d < n; d++)
+        th.emplace_back([&, d]() {
+            try {
+                body(d);
+            } catch (const Error& e) {
+                errors[d] = e;
+            } catch (const std::bad_alloc&) {
+                errors[d] = Error{RZ_RUNTIME_ERROR, "Out of host memory."};
+            } catch (const std::exception& e) {
+                errors[d] = Error{RZ_RUNTIME_ERROR, e.what()};
+            }
+        });
+    for (auto& t : th) t.join();
+    first_error = Error{RZ_OK, ""};
+    for (auto& e : errors)
+        if (e.code != RZ_OK) {
+            first_error = e;
+            break;
+        }
+}
+
+static void check_devices(const int32_t* devices, int32_t n_devices, bool allow_repeats = false) {
+    if (!devices || n_devices <= 0) throw Error{RZ_VALUE_ERROR, "Empty device list"};
+    if (allow_repeats) return;
+    for (int32_t i = 0; i < n_devices; i++)
+        for (int32_t j = 0; j < i; j++)
+            if (devices[i] == devices[j]) throw Error{RZ_VALUE_ERROR, "A device appears twice in the device list"};
+}
+
+// parts of g that can write raster rows [b0, b1) of the grid `ri` (margin: pixel rows of slack around a part's extent)
+static void select_row_parts(const rz_geoms* g, const rz_raster_info& ri, uint64_t b0, uint64_t b1, double margin,
+                             std::vector<uint32_t>& keep) {
+    const size_t np = g->part_kind.size();
+    keep.reserve(np / 4 + 16);
+    for (size_t p = 0; p < np; p++) {
+        double ylo, yhi;
+        part_y_extent(g, (uint32_t)p, ylo, yhi);
+        const double top = (ri.ymax - yhi) / ri.yres, bot = (ri.ymax - ylo) / ri.yres;
+        // kept unless certainly outside (comparisons with NaN are false: kept)
+        if (bot < (double)b0 - margin || top > (double)b1 + margin) continue;
+        keep.push_back((uint32_t)p);
+    }
+}
+
+static void rasterize_dense_multi(rz_geoms* g, const rz_context* ctx, const int32_t* devices, int32_t n_devices, void* out,
+                                  rz_stats* st, rz_stats* per_device) {
+    // (a repeated device only serialises its shards: single-GPU machines can exercise the sharding that way)
+    check_devices(devices, n_devices, std::getenv("RZ_ALLOW_REPEATED_DEVICES") != nullptr);
+    if (ctx->flags & RZ_FLAG_OUT_ON_DEVICE)
+        throw Error{RZ_VALUE_ERROR, "Multi-device calls write host memory; use rz_rasterize_dense per device for device output"};
+    const rz_raster_info& ri = ctx->raster_info;
+    validate_lengths(g, ctx);
+    uint64_t r0 = ctx->row_begin, r1 = ctx->row_end;
+    if (r0 == 0 && r1 == 0) r1 = ri.nrows;
+    if (r1 > ri.nrows || (r0 >= r1 && ri.nrows)) throw Error{RZ_VALUE_ERROR, "Invalid row shard"};
+    const uint64_t rows = r1 - r0;
+    const int D = (int)std::min<uint64_t>((uint64_t)n_devices, std::max<uint64_t>(rows, 1));
+    std::vector<rz_stats> S((size_t)D);
+    for (auto& x : S) std::memset(&x, 0, sizeof x);
+    const double margin = ctx->all_touched ? 3.0 : 2.0;  // pixel rows of slack around a part's extent
+    Error err;
+    run_per_device(D, [&](int d) {
+        const uint64_t b0 = r0 + rows * (uint64_t)d / (uint64_t)D, b1 = r0 + rows * (uint64_t)(d + 1) / (uint64_t)D;
+        rz_context c = *ctx;
+        c.device = devices[d];
+        c.stream = nullptr;  // the caller's stream belongs to one device
+        c.row_begin = b0;
+        c.row_end = b1;
+        if (b1 <= b0) return;
+        rz_geoms* use = g;
+        std::shared_ptr<rz_geoms> sub;
+        if (D > 1) {
+            const std::vector<uint64_t> key{0, f64_bits(ri.ymax), f64_bits(ri.yres), b0, b1, (uint64_t)margin};
+            sub = cached_subset(g, key, [&](std::vector<uint32_t>& keep) { select_row_parts(g, ri, b0, b1, margin, keep); });
+            use = sub.get();
+        }
+        const DenseExtra ex{rows, b0 - r0};
+        rasterize_dense(use, &c, out, &S[d], &ex);
+    }, err);
+    if (err.code != RZ_OK) throw err;
+    rz_stats A = S[0];
+    for (int d = 1; d < D; d++) accumulate_stats(A, S[d]);
+    if (st) *st = A;
+    if (per_device)
+        for (int d = 0; d < n_devices; d++) {
+            if (d < D) per_device[d] = S[d];
+            else std::memset(&per_device[d], 0, sizeof(rz_stats));
+        }
+}
+
+struct SparseGather : SparseSink {
+    std::mutex mu;
+    std::condition_variable cv;
+    int n_dev = 0, arrived = 0;
+    bool failed = false, ready = false;
+    size_t isz = 0;
+    std::vector<std::vector<uint64_t>> counts;  // [device][band]
+    std::vector<uint64_t> band_base;
+    rz_sparse* out = nullptr;
+    struct View : SparseSink {
+        SparseGather* g;
+        int d;
+        void place(const std::vector<uint64_t>& c, std::vector<uint64_t>& off, char*& r, char*& cc, char*& da) override {
+            g->place_from(d, c, off, r, cc, da);
+        }
+    };
+    void place(const std::vector<uint64_t>&, std::vector<uint64_t>&, char*&, char*&, char*&) override {}
+    void place_from(int d, const std::vector<uint64_t>& c, std::vector<uint64_t>& off, char*& r, char*& cc, char*& da) {
+        std::unique_lock<std::mutex> lk(mu);
+        counts[d] = c;
+        arrived++;
+        if (arrived == n_dev && !failed) {
+            const size_t nb = c.size();
+            band_base.assign(nb + 1, 0);
+            for (size_t b = 0; b < nb; b++) {
+                uint64_t t = 0;
+                for (int e = 0; e < n_dev; e++) t += b < counts[e].size() ? counts[e][b] : 0;
+                out->counts[b] = t;
+                band_base[b + 1] = band_base[b] + t;
+            }
+            const uint64_t total = band_base[nb];
+            try {
+                out->len = total;
+                out->rows = g_host_pool.get(total * 8);
+                out->cols = g_host_pool.get(total * 8);
+                out->data = g_host_pool.get(total * isz);
+                ready = true;
+            } catch (const std::bad_alloc&) {
+                failed = true;
+            }
+            cv.notify_all();
+        } else {
+            cv.wait(lk, [&]() { return ready || failed; });
+        }
+        if (failed) throw Error{RZ_RUNTIME_ERROR, "Multi-device sparse call aborted: a device failed or host memory ran out."};
+        off.assign(c.size(), 0);
+        for (size_t b = 0; b < c.size(); b++) {
+            uint64_t o = band_base[b];
+            for (int e = 0; e < d; e++) o += counts[e][b];
+            off[b] = o;
+        }
+        r = (char*)out->rows.p;
+        cc = (char*)out->cols.p;
+        da = (char*)out->data.p;
+    }
+    void fail() {
+        std::lock_guard<std::mutex> lk(mu);
+        failed = true;
+        cv.notify_all();
+    }
+};
+
+static void rasterize_sparse_multi(rz_geoms* g, const rz_context* ctx, const int32_t* devices, int32_t n_devices,
+                                   rz_sparse* out, rz_stats* st, rz_stats* per_device) {
+    check_devices(devices, n_devices);
+    validate_lengths(g, ctx);
+    const rz_raster_info& ri = ctx->raster_info;
+    const size_t isz = dtype_size(ctx->dtype);
+    if (!isz) throw Error{RZ_VALUE_ERROR, "Unsupported dtype"};
+    const uint32_t n_bands = ctx->band_of_geom ? (uint32_t)std::max(ctx->n_bands, 0) : 1u;
+    const size_t np = g->part_kind.size();
+    const int D = (int)std::max<size_t>(1, std::min<size_t>((size_t)n_devices, g->n_geoms));
+    // ---- contiguous geometry ranges of equal estimated work (a prefix sum of per-geometry cost) ----
+    // cost of a part: its vertices (setup) + for polygons the pixels of its box (fill, ~half of them burned) and two
+    // crossings per row; for lines the longer side of each part's box is unknown without a scan: vertices x 16
+    std::vector<double> cost(np);
+    for (size_t p = 0; p < np; p++) {
+        const double nv = (double)(g->part_vend[p] - g->part_vbeg[p]);
+        double c = 4.0 * nv + 8.0;
+        if (g->part_kind[p] == RZ_PART_POLYGON) {
+            double w = (g->part_xhi[p] - g->part_xlo[p]) / ri.xres, h = (g->part_yhi[p] - g->part_ylo[p]) / ri.yres;
+            w = std::min(std::max(w, 0.0), (double)ri.ncols);
+            h = std::min(std::max(h, 0.0), (double)ri.nrows);
+            if (w == w && h == h) c += 0.5 * w * h + 4.0 * h;
+        } else if (g->part_kind[p] == RZ_PART_LINE) {
+            c += 16.0 * nv;
+        }
+        cost[p] = c;
+    }
+    double total_cost = 0;
+    for (double c : cost) total_cost += c;
+    // cut at geometry borders: part p starts a geometry when part_geom changes
+    std::vector<size_t> cut((size_t)D + 1, np);
+    cut[0] = 0;
+    {
+        double acc = 0;
+        int k = 1;
+        for (size_t p = 0; p < np && k < D; p++) {
+            acc += cost[p];
+            const bool geom_end = p + 1 == np || g->part_geom[p + 1] != g->part_geom[p];
+            if (geom_end && acc >= total_cost * (double)k / (double)D) cut[(size_t)k++] = p + 1;
+        }
+    }
+    out->counts.assign(n_bands, 0);
+    SparseGather gather;
+    gather.n_dev = D;
+    gather.isz = isz;
+    gather.counts.assign((size_t)D, std::vector<uint64_t>(n_bands, 0));
+    gather.out = out;
+    std::vector<rz_stats> S((size_t)D);
+    for (auto& x : S) std::memset(&x, 0, sizeof x);
+    Error err;
+    run_per_device(D, [&](int d) {
+        SparseGather::View view;
+        view.g = &gather;
+        view.d = d;
+        try {
+            rz_context c = *ctx;
+            c.device = devices[d];
+            c.stream = nullptr;
+            rz_geoms* use = g;
+            std::shared_ptr<rz_geoms> sub;
+            if (D > 1) {
+                const std::vector<uint64_t> key{1, (uint64_t)cut[(size_t)d], (uint64_t)cut[(size_t)d + 1]};
+                sub = cached_subset(g, key, [&](std::vector<uint32_t>& keep) {
+                    keep.resize(cut[(size_t)d + 1] - cut[(size_t)d]);
+                    for (size_t i = 0; i < keep.size(); i++) keep[i] = (uint32_t)(cut[(size_t)d] + i);
+                });
+                use = sub.get();
+            }
+            rz_sparse local;  // counts only: the triplets go to the gathered arrays
+            rasterize_sparse(use, &c, &local, &S[d], &view);
+        } catch (...) {
+            gather.fail();
+            throw;
+        }
+    }, err);
+    if (err.code != RZ_OK) throw err;
+    rz_stats A = S[0];
+    for (int d = 1; d < D; d++) accumulate_stats(A, S[d]);
+    if (st) *st = A;
+    if (per_device)
+        for (int d = 0; d < n_devices; d++) {
+            if (d < D) per_device[d] = S[d];
+            else std::memset(&per_device[d], 0, sizeof(rz_stats));
+        }
 }
 
 }  // namespace rz
@@ -1986,6 +2357,20 @@ void rz_geoms_evict(rz_geoms* g) {
 
 void rz_geoms_free(rz_geoms* g) { delete g; }
 
+rz_geoms* rz_geoms_row_shard(const rz_geoms* g, const rz_raster_info* ri, uint64_t row_begin, uint64_t row_end,
+                             int all_touched, char* err, size_t errlen) {
+    rz_geoms* out = nullptr;
+    int rc = guarded(err, errlen, [&]() {
+        if (row_end > ri->nrows || row_begin >= row_end) throw Error{RZ_VALUE_ERROR, "Invalid row shard"};
+        std::vector<uint32_t> keep;
+        rz::select_row_parts(g, *ri, row_begin, row_end, all_touched ? 3.0 : 2.0, keep);
+        unsigned threads = std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
+        if (const char* e = std::getenv("RZ_PARSE_THREADS")) threads = std::max(1, std::atoi(e));
+        out = rz::subset_parts(g, keep.data(), keep.size(), threads);
+    });
+    return rc == RZ_OK ? out : nullptr;
+}
+
 const uint8_t* rz_geoms_part_kind(const rz_geoms* g) { return g->part_kind.data(); }
 const uint64_t* rz_geoms_part_geom(const rz_geoms* g) { return g->part_geom.data(); }
 uint64_t rz_geoms_pool_len(const rz_geoms* g, int kind) { return kind >= 0 && kind < 3 ? g->pool[kind].size() : 0; }
@@ -2016,6 +2401,18 @@ int rz_rasterize_sparse(rz_geoms* g, const rz_context* ctx, rz_sparse** out, rz_
                         size_t errlen) {
     std::unique_ptr<rz_sparse> sp(new rz_sparse());
     int rc = guarded(err, errlen, [&]() { rz::rasterize_sparse(g, ctx, sp.get(), stats); });
+    if (rc == RZ_OK) *out = sp.release();
+    return rc;
+}
+int rz_rasterize_dense_multi(rz_geoms* g, const rz_context* ctx, const int32_t* devices, int32_t n_devices, void* out,
+                             rz_stats* stats, rz_stats* per_device, char* err, size_t errlen) {
+    return guarded(err, errlen, [&]() { rz::rasterize_dense_multi(g, ctx, devices, n_devices, out, stats, per_device); });
+}
+int rz_rasterize_sparse_multi(rz_geoms* g, const rz_context* ctx, const int32_t* devices, int32_t n_devices,
+                              rz_sparse** out, rz_stats* stats, rz_stats* per_device, char* err, size_t errlen) {
+    std::unique_ptr<rz_sparse> sp(new rz_sparse());
+    int rc = guarded(err, errlen,
+                     [&]() { rz::rasterize_sparse_multi(g, ctx, devices, n_devices, sp.get(), stats, per_device); });
     if (rc == RZ_OK) *out = sp.release();
     return rc;
 }

@@ -200,3 +200,47 @@ def test_parallel_soa_ingestion_equals_wkb_flattening(monkeypatch):
     assert [i for i in range(8) if pt[i] & 0x80000000] == [3, 7] and (pt & 0x3FFFFFFF).tolist() == [0] * 4 + [2] * 4
     with pytest.raises(RuntimeError, match="Invalid part kind"):
         core.Geoms.from_soa(gpo, np.array([0, 9, 0], np.uint8), pso, sco, x, y)
+
+
+def test_row_shard_keeps_order_indices_and_vertices():
+    """rz_geoms_row_shard (the library-side cull of a row-band sharded job): the shard holds exactly the parts whose
+    y-extent comes within a few rows of the band, in the original order, with their original geometry indices and
+    vertices; parts of every kind are tested by their own extent."""
+    import synth
+
+    W, H = 400, 1000
+    geoms = synth.mixed_geometries(29, 500, W, H, rho=20.0)
+    g = core.Geoms.from_wkb(geoms)
+    ri = core.raster_info(None, shape=(H, W), extent=(0, 0, W, H))
+    kind, geom = g.parts()
+    pools = [g.pool(k) for k in range(3)]
+    # vertex range of every part inside its pool, from the tags (part id in the low 30 bits)
+    ymin, ymax = np.full(len(kind), np.inf), np.full(len(kind), -np.inf)
+    for k in range(3):
+        _, py, pt = pools[k]
+        ids = (pt & 0x3FFFFFFF).astype(np.int64)
+        np.minimum.at(ymin, ids, py)
+        np.maximum.at(ymax, ids, py)
+    for r0, r1 in [(0, 250), (250, 500), (777, 1000), (0, 1000)]:
+        sh = g.row_shard(ri, r0, r1)
+        sk, sg = sh.parts()
+        top, bot = H - ymax, H - ymin  # pixel rows of each part's extent (res 1)
+        must = (bot >= r0) & (top <= r1)          # certainly needed
+        may = (bot >= r0 - 3) & (top <= r1 + 3)   # allowed slack
+        assert len(sh) == len(g)  # geometry indices are unchanged
+        # the kept parts form a subsequence of the original parts table
+        j = 0
+        kept = np.zeros(len(kind), bool)
+        for i in range(len(kind)):
+            if j < len(sk) and sk[j] == kind[i] and sg[j] == geom[i] and may[i]:
+                kept[i] = True
+                j += 1
+        assert j == len(sk)
+        assert (kept | ~must).all()
+        for k in range(3):
+            px, py, pt = pools[k]
+            sel = kept[(pt & 0x3FFFFFFF).astype(np.int64)]
+            sx, sy, _ = sh.pool(k)
+            assert np.array_equal(sx, px[sel]) and np.array_equal(sy, py[sel])
+    with pytest.raises(ValueError, match="Invalid row shard"):
+        g.row_shard(ri, 10, 10)
