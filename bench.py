@@ -499,7 +499,7 @@ def run_dense(env, name, w, headline):
         ev0.record()
         marks = []
         for _ in range(steps):
-            step()
+            st_timed = step()
             marks.append(torch.cuda.Event(enable_timing=True))
             marks[-1].record()
         ev1.record()
@@ -540,7 +540,7 @@ def run_dense(env, name, w, headline):
                         "stage_ms_max_over_ranks": dict(zip(["mask_build" if s0["engine"] == 1 else "count", "emit", "sort",
                                                              "index", "fill", "lib_total_staged_pass"], stage)),
                         "records": int(agg[0]), "crossings": int(agg[1]), "launches_per_step": int(round(agg[3])),
-                        "host_syncs_per_step": int(stats[-1]["host_syncs"]),
+                        "host_syncs_per_step": int(st_timed["host_syncs"]),
                         "roofline": roofline_of(env, w, fun, dtype, s0, stage[4], stage[0]),
                         "whole_step_frac_of_hbm": (20.0 * agg[5] + agg[2]) / (ms_max / 1e3) / 1e9 / env.peak,
                         "_steps": steps, "_warmup": warmup}
@@ -579,8 +579,9 @@ def run_dense_e2e(env, name, w):
     g = core.Geoms.from_soa(*w["soa"])
     call(g, _lib.FLAG_SYNC_STAGES)
     del g
-    whole, flat, st_last = [], [], None
+    whole, flat, st_last, g = [], [], None, None
     for _ in range(n_e2e):
+        del g  # (a caller's previous geometry set is gone: its page-locked pools are recycled by the next one)
         t0 = time.perf_counter()
         g = core.Geoms.from_soa(*w["soa"])
         t1 = time.perf_counter()
@@ -588,14 +589,14 @@ def run_dense_e2e(env, name, w):
         t2 = time.perf_counter()
         whole.append((t2 - t0) * 1e3)
         flat.append((t1 - t0) * 1e3)
-        g_keep = g
-        del g
     # the same call on an already flattened handle (what a caller who keeps the handle pays): upload forced
-    cached = []
+    cached, cached_lib = [], []
     for _ in range(n_e2e):
         t0 = time.perf_counter()
-        call(g_keep, _lib.FLAG_SYNC_STAGES | _lib.FLAG_FORCE_H2D)
+        st_c = call(g, _lib.FLAG_SYNC_STAGES | _lib.FLAG_FORCE_H2D)
         cached.append((time.perf_counter() - t0) * 1e3)
+        cached_lib.append([round(st_c["h2d_ms"], 1), round(st_c["d2h_ms"], 1), round(st_c["total_ms"], 1), round(st_c["wall_ms"], 1)])
+    del g
     e_ms = float(np.mean(whole))
     per = st_last["per_device"]
     stride = max(1, rows // 64)
@@ -605,9 +606,11 @@ def run_dense_e2e(env, name, w):
             "flatten_ms": float(np.mean(flat)), "flatten_Gvert_per_s": w["n_vertices"] / (float(np.mean(flat)) / 1e3) / 1e9,
             "ms_each_step": [round(v, 1) for v in whole],
             "e2e_handle_cached": {"ms_per_step": float(np.mean(cached)), "value": n_b * rows * cols / (float(np.mean(cached)) / 1e3) / 1e6,
+                                  "ms_each_step": [round(v, 1) for v in cached], "lib_h2d_d2h_total_wall_ms_each_step": cached_lib,
                                   "note": "geometry handle kept between calls (no flattening, part subsets cached), upload forced"},
             "per_device": [{"device": d, "h2d_ms": round(p["h2d_ms"], 2), "d2h_ms": round(p["d2h_ms"], 2),
-                            "total_ms": round(p["total_ms"], 2), "h2d_MB": round(p["h2d_bytes"] / 1e6, 1),
+                            "total_ms": round(p["total_ms"], 2), "wall_ms": round(p["wall_ms"], 2),
+                            "shard_ms": round(p["shard_ms"], 2), "h2d_MB": round(p["h2d_bytes"] / 1e6, 1),
                             "d2h_MB": round(p["d2h_bytes"] / 1e6, 1)} for d, p in enumerate(per)],
             "checksum": float(np.nansum(h_np[0, ::stride].astype(np.float64))), "_host": h_np}
 
@@ -706,7 +709,8 @@ def run_sparse(env, name, w):
                    "h2d_bytes_per_step": int(st_e2e["h2d_bytes"]), "d2h_bytes_per_step": int(st_e2e["d2h_bytes"]),
                    "includes": "rz_geoms_from_soa + geometry-range subsets + H2D + scans/sort/expand + D2H into one triplet stream",
                    "ms_each_step": [round(v, 1) for v in whole]},
-           "per_device": [{"device": d, "total_ms": round(p["total_ms"], 2), "d2h_ms": round(p["d2h_ms"], 2),
+           "per_device": [{"device": d, "total_ms": round(p["total_ms"], 2), "wall_ms": round(p["wall_ms"], 2),
+                           "shard_ms": round(p["shard_ms"], 2), "d2h_ms": round(p["d2h_ms"], 2),
                            "expand_ms": round(p["fill_ms"], 2), "triplet_MB": round(p["out_bytes"] / 1e6, 1)} for d, p in enumerate(per)],
            "parity_vs_oracle": {"bit_exact": all(c["bit_exact"] for c in checks), "checks": checks},
            "config": config_of(name, w, args.scale, world, "sparse: scans + radix sort + expand"), "n_gpus": world}

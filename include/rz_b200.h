@@ -177,6 +177,8 @@ typedef struct rz_stats {
     uint32_t host_syncs;       /* times the host waited for the device inside the call (0 for a steady-state
                                   tile-engine call with device output) */
     uint32_t plan_cached;      /* tile engine: buffer bounds came from the geometry handle's cache */
+    float wall_ms;             /* host wall-clock time of the entry point (per device: its thread, shard_ms included) */
+    float shard_ms;            /* multi-device calls: cutting this device's part subset out of the geometry set */
 } rz_stats;
 
 /* DenseArray::build (rust/src/rasterize.rs:71-116): out is [n_bands][rows][ncols] of ctx->dtype,

@@ -73,6 +73,7 @@ class Stats(C.Structure):
         ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("out_bytes", C.c_uint64),
         ("kernel_launches", C.c_uint32), ("engine", C.c_uint32),
         ("n_mask_words", C.c_uint64), ("host_syncs", C.c_uint32), ("plan_cached", C.c_uint32),
+        ("wall_ms", C.c_float), ("shard_ms", C.c_float),
     ]
 
     def as_dict(self):

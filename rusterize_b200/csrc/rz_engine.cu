@@ -15,6 +15,8 @@
 #include <memory>
 #include <string>
 #include <sys/mman.h>
+#include <unistd.h>
+#include <chrono>
 #include <thread>
 #include <type_traits>
 #include <vector>
@@ -85,7 +87,8 @@ struct DevBuf {
 // kernels against 700 ms to fault the pages in and page-lock them for the copy).  Blocks are therefore huge-page
 // backed, faulted in by several threads, page-locked once (portable: every device's copy engine may use them),
 // and recycled through a pool when their owner is freed: steady-state calls copy straight into / out of
-// resident, pinned memory at the PCIe rate.  RZ_HOST_POOL_BYTES caps what the pool keeps (default 8 GiB).
+// resident, pinned memory at the PCIe rate.  RZ_HOST_POOL_BYTES caps what the pool keeps (default: a quarter of
+// the machine's memory, between 8 and 64 GiB).
 struct HostBlock {
     void* p = nullptr;
     size_t cap = 0;
@@ -181,7 +184,14 @@ class HostPool {
     }
     static size_t limit() {
         if (const char* e = std::getenv("RZ_HOST_POOL_BYTES")) return (size_t)std::strtoull(e, nullptr, 10);
-        return (size_t)8 << 30;
+        // a quarter of the machine's memory, between 8 and 64 GiB: the triplet stream of BASELINE config 5 is 20 GB,
+        // and re-faulting + re-locking it on every call costs three times the whole device pipeline
+        static const size_t def = []() {
+            const long pages = sysconf(_SC_PHYS_PAGES), psz = sysconf(_SC_PAGE_SIZE);
+            size_t quarter = pages > 0 && psz > 0 ? (size_t)pages / 4 * (size_t)psz : (size_t)8 << 30;
+            return std::min<size_t>(std::max<size_t>(quarter, (size_t)8 << 30), (size_t)64 << 30);
+        }();
+        return def;
     }
     std::mutex mu_;
     std::vector<HostBlock> free_;
@@ -591,7 +601,13 @@ struct DenseExtra {
     uint64_t band_rows, row_off;
 };
 
+struct WallClock {
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    float ms() const { return std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count(); }
+};
+
 static void rasterize_dense(rz_geoms* g, const rz_context* ctx, void* out, rz_stats* st, const DenseExtra* ex = nullptr) {
+    const WallClock wall;
     const rz_raster_info& ri = ctx->raster_info;
     validate_lengths(g, ctx);
     const size_t isz = dtype_size(ctx->dtype);
@@ -1231,6 +1247,7 @@ static void rasterize_dense(rz_geoms* g, const rz_context* ctx, void* out, rz_st
     S.fill_ms = fill_ms;
     S.d2h_ms = d2h_ms;
     S.kernel_launches = launches;
+    S.wall_ms = wall.ms();
     if (st) *st = S;
 #undef EV_A
 #undef EV_B
@@ -1317,6 +1334,7 @@ struct SparseSink {
 };
 
 static void rasterize_sparse(rz_geoms* g, const rz_context* ctx, rz_sparse* out, rz_stats* st, SparseSink* sink = nullptr) {
+    const WallClock wall;
     const rz_raster_info& ri = ctx->raster_info;
     validate_lengths(g, ctx);
     const size_t isz = dtype_size(ctx->dtype);
@@ -1351,7 +1369,7 @@ static void rasterize_sparse(rz_geoms* g, const rz_context* ctx, rz_sparse* out,
     order_after_previous_call(c, s);
     rz_stats S;
     std::memset(&S, 0, sizeof S);
-    enum { EV_START, EV_END, EV_SORTED, EV_COUNTED, EV_EXPANDED };  // stage marks (rz_stats: emit+sort, index, fill, d2h)
+    enum { EV_START, EV_END, EV_SORTED, EV_COUNTED, EV_EXPANDED, EV_EXPAND };  // stage marks (rz_stats: emit+sort, index, fill, d2h)
     CUDA_TRY(cudaEventRecord(c.ev[EV_START], s));
     size_t h2d = 0;
     DeviceGeoms* dg = geoms_on_device(g, c, s, (ctx->flags & RZ_FLAG_FORCE_H2D) != 0, &h2d);
@@ -1607,6 +1625,7 @@ static void rasterize_sparse(rz_geoms* g, const rz_context* ctx, rz_sparse* out,
         c.sp_rows.ensure(total * 8);
         c.sp_cols.ensure(total * 8);
         c.sp_data.ensure(total * isz);
+        CUDA_TRY(cudaEventRecord(c.ev[EV_EXPAND], s));  // (host blocks and device arrays exist: the kernels start now)
         SparseJob J;
         J.n_rec = n_rec;
         J.nv_poly = nv_poly;
@@ -1650,11 +1669,12 @@ static void rasterize_sparse(rz_geoms* g, const rz_context* ctx, rz_sparse* out,
     CUDA_TRY(cudaEventElapsedTime(&S.sort_ms, c.ev[EV_START], c.ev[EV_SORTED]));    // upload + crossings + sort
     CUDA_TRY(cudaEventElapsedTime(&S.index_ms, c.ev[EV_SORTED], c.ev[EV_COUNTED])); // unit scans, bases
     if (total) {
-        CUDA_TRY(cudaEventElapsedTime(&S.fill_ms, c.ev[EV_COUNTED], c.ev[EV_EXPANDED]));  // expand kernels
+        CUDA_TRY(cudaEventElapsedTime(&S.fill_ms, c.ev[EV_EXPAND], c.ev[EV_EXPANDED]));  // expand kernels
         CUDA_TRY(cudaEventElapsedTime(&S.d2h_ms, c.ev[EV_EXPANDED], c.ev[EV_END]));       // pin + copy back
     }
     S.out_bytes = total * (16 + isz);
     S.kernel_launches = launches;
+    S.wall_ms = wall.ms();
     if (st) *st = S;
 }
 
@@ -1802,6 +1822,8 @@ static void accumulate_stats(rz_stats& a, const rz_stats& b) {
     a.fill_ms = std::max(a.fill_ms, b.fill_ms);
     a.d2h_ms = std::max(a.d2h_ms, b.d2h_ms);
     a.total_ms = std::max(a.total_ms, b.total_ms);
+    a.wall_ms = std::max(a.wall_ms, b.wall_ms);
+    a.shard_ms = std::max(a.shard_ms, b.shard_ms);
 }
 
 static uint64_t f64_bits(double v) {
@@ -1900,6 +1922,7 @@ static void select_row_parts(const rz_geoms* g, const rz_raster_info& ri, uint64
 
 static void rasterize_dense_multi(rz_geoms* g, const rz_context* ctx, const int32_t* devices, int32_t n_devices, void* out,
                                   rz_stats* st, rz_stats* per_device) {
+    const WallClock call_clock;
     // (a repeated device only serialises its shards: single-GPU machines can exercise the sharding that way)
     check_devices(devices, n_devices, std::getenv("RZ_ALLOW_REPEATED_DEVICES") != nullptr);
     if (ctx->flags & RZ_FLAG_OUT_ON_DEVICE)
@@ -1925,17 +1948,22 @@ static void rasterize_dense_multi(rz_geoms* g, const rz_context* ctx, const int3
         if (b1 <= b0) return;
         rz_geoms* use = g;
         std::shared_ptr<rz_geoms> sub;
+        const WallClock shard_clock;
         if (D > 1) {
             const std::vector<uint64_t> key{0, f64_bits(ri.ymax), f64_bits(ri.yres), b0, b1, (uint64_t)margin};
             sub = cached_subset(g, key, [&](std::vector<uint32_t>& keep) { select_row_parts(g, ri, b0, b1, margin, keep); });
             use = sub.get();
         }
+        const float shard_ms = shard_clock.ms();
         const DenseExtra ex{rows, b0 - r0};
         rasterize_dense(use, &c, out, &S[d], &ex);
+        S[d].shard_ms = shard_ms;
+        S[d].wall_ms += shard_ms;
     }, err);
     if (err.code != RZ_OK) throw err;
     rz_stats A = S[0];
     for (int d = 1; d < D; d++) accumulate_stats(A, S[d]);
+    A.wall_ms = call_clock.ms();
     if (st) *st = A;
     if (per_device)
         for (int d = 0; d < n_devices; d++) {
@@ -2008,6 +2036,7 @@ struct SparseGather : SparseSink {
 
 static void rasterize_sparse_multi(rz_geoms* g, const rz_context* ctx, const int32_t* devices, int32_t n_devices,
                                    rz_sparse* out, rz_stats* st, rz_stats* per_device) {
+    const WallClock call_clock;
     check_devices(devices, n_devices);
     validate_lengths(g, ctx);
     const rz_raster_info& ri = ctx->raster_info;
@@ -2066,6 +2095,7 @@ static void rasterize_sparse_multi(rz_geoms* g, const rz_context* ctx, const int
             c.stream = nullptr;
             rz_geoms* use = g;
             std::shared_ptr<rz_geoms> sub;
+            const WallClock shard_clock;
             if (D > 1) {
                 const std::vector<uint64_t> key{1, (uint64_t)cut[(size_t)d], (uint64_t)cut[(size_t)d + 1]};
                 sub = cached_subset(g, key, [&](std::vector<uint32_t>& keep) {
@@ -2074,8 +2104,11 @@ static void rasterize_sparse_multi(rz_geoms* g, const rz_context* ctx, const int
                 });
                 use = sub.get();
             }
+            const float shard_ms = shard_clock.ms();
             rz_sparse local;  // counts only: the triplets go to the gathered arrays
             rasterize_sparse(use, &c, &local, &S[d], &view);
+            S[d].shard_ms = shard_ms;
+            S[d].wall_ms += shard_ms;
         } catch (...) {
             gather.fail();
             throw;
@@ -2084,6 +2117,7 @@ static void rasterize_sparse_multi(rz_geoms* g, const rz_context* ctx, const int
     if (err.code != RZ_OK) throw err;
     rz_stats A = S[0];
     for (int d = 1; d < D; d++) accumulate_stats(A, S[d]);
+    A.wall_ms = call_clock.ms();
     if (st) *st = A;
     if (per_device)
         for (int d = 0; d < n_devices; d++) {

@@ -8,6 +8,8 @@
 //   rust/src/rasterize.rs:199-205                    band order for `by`
 #include "rz_host.hpp"
 
+#include <emmintrin.h>
+
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
@@ -618,12 +620,20 @@ inline void copy_fold(const double* src, double* dst, size_t n, double& lo, doub
         return u;
     };
     size_t i = 0;
+    // The pools are written once and next read by the copy engine: streaming (non-temporal) stores keep them out of
+    // the cache and save the read-for-ownership of every destination line - a third of the sweep's memory traffic.
+    if (n && ((uintptr_t)dst & 15u)) {  // align the destination to 16 bytes
+        const double a = src[0];
+        dst[0] = a;
+        l0 = a < l0 ? a : l0;
+        h0 = a > h0 ? a : h0;
+        b |= (uint64_t)((bits(a) & EXP) == EXP);
+        i = 1;
+    }
     for (; i + 4 <= n; i += 4) {
         const double a0 = src[i], a1 = src[i + 1], a2 = src[i + 2], a3 = src[i + 3];
-        dst[i] = a0;
-        dst[i + 1] = a1;
-        dst[i + 2] = a2;
-        dst[i + 3] = a3;
+        _mm_stream_pd(dst + i, _mm_set_pd(a1, a0));
+        _mm_stream_pd(dst + i + 2, _mm_set_pd(a3, a2));
         l0 = a0 < l0 ? a0 : l0;
         l1 = a1 < l1 ? a1 : l1;
         l2 = a2 < l2 ? a2 : l2;
@@ -802,9 +812,10 @@ int flatten_soa(const rz_geom_soa* soa, rz_geoms* g, unsigned threads, std::stri
                     double xlo, xhi, ylo, yhi;
                     copy_fold(soa->x + k0, xd, n, xlo, xhi, bad);
                     copy_fold(soa->y + k0, yd, n, ylo, yhi, bad);
+                    const double *xs = soa->x + k0, *ys = soa->y + k0;  // (read the source: xd / yd were streamed out)
                     if (!gb_has) {  // geo's fold is seeded by the first coordinate (Flattener::bound)
-                        gb[0] = gb[2] = xd[0];
-                        gb[1] = gb[3] = yd[0];
+                        gb[0] = gb[2] = xs[0];
+                        gb[1] = gb[3] = ys[0];
                         gb_has = true;
                     }
                     if (xlo < gb[0]) gb[0] = xlo;
@@ -820,10 +831,10 @@ int flatten_soa(const rz_geom_soa* soa, rz_geoms* g, unsigned threads, std::stri
                         at[kind] += m;
                         continue;
                     }
-                    bool closed = xd[0] == xd[n - 1] && yd[0] == yd[n - 1];
+                    bool closed = xs[0] == xs[n - 1] && ys[0] == ys[n - 1];
                     if (kind == RZ_PART_POLYGON && !closed) {
-                        xd[n] = xd[0];
-                        yd[n] = yd[0];
+                        xd[n] = xs[0];
+                        yd[n] = ys[0];
                         m = n + 1;
                         closed = true;
                     }
@@ -852,6 +863,7 @@ int flatten_soa(const rz_geom_soa* soa, rz_geoms* g, unsigned threads, std::stri
             }
         }
         c.nonfinite = bad != 0;
+        _mm_sfence();  // streaming stores are visible before the thread is joined
     });
     for (auto& c : ch) {
         if (c.nonfinite) g->nonfinite = true;

@@ -23,6 +23,13 @@ template <> struct NanBackground<double> {
 // Which evaluation of the pixel-function rule a job gets (rz_tiles.cuh, MODE).  What depends on the burn VALUES
 // (all finite / none equal to the background) is decided on the device: modes 1 and 3 fall back to the generic
 // body inside the kernel.
+// (the opt-in to more than 48 KB of dynamic shared memory is per device: set on every launch, it costs nothing)
+template <typename K, typename... A>
+static void launch_apply(K kfn, dim3 grid, int threads, size_t smem, cudaStream_t s, A... a) {
+    if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return;  // surfaces through cudaGetLastError
+    kfn<<<grid, threads, smem, s>>>(a...);
+}
+
 template <typename N, int FN>
 static void tile_launch(cudaStream_t s, KParams P, TileParams T, const uint32_t* tile_start, const BlockDesc* desc,
                         const uint32_t* masks, const TileCounters* tcnt, uint64_t bg, void* out) {
@@ -36,24 +43,22 @@ static void tile_launch(cudaStream_t s, KParams P, TileParams T, const uint32_t*
     const uint32_t groups = (T.n_tc + APPLY_TILES - 1) / APPLY_TILES;
     static const bool force_1d = std::getenv("RZ_APPLY_1D") != nullptr;  // tests: exercise the flattened grid
     const dim3 grid = (gy <= 65535 && !force_1d) ? dim3(groups, (unsigned)gy) : dim3((unsigned)(groups * gy));
-    const size_t smem = (size_t)(TR / 8) * 8 * 4 * (32 * sizeof(N) + 16);  // flush staging: 8 padded rows per warp
+    // flush staging (8 padded rows per consumer warp) + the staged mask blocks and their mbarriers
+    const size_t smem = apply_smem_bytes<N, TR>();
+    constexpr int THREADS = TR * 4 + 32;  // consumer warps + the producer warp
     N bgv;
     std::memcpy(&bgv, &bg, sizeof(N));
     const bool bg_nan = NanBackground<N>::is(bgv);
     if (additive && is_float && bg_nan)  // MODE 1 (when every value is finite): masked add + touched mask
-        tile_apply_kernel<N, additive ? FN : RZ_SUM, TR, is_float ? 1 : 0, true><<<grid, TR * 4, smem, s>>>(
-            P, T, tile_start, desc, masks, tcnt, bg, (N*)out);
+        launch_apply(tile_apply_kernel<N, additive ? FN : RZ_SUM, TR, is_float ? 1 : 0, true>, grid, THREADS, smem, s, P, T, tile_start, desc, masks, tcnt, bg, (N*)out);
     else if (additive && !is_float && bg == 0)  // MODE 2: plain masked add
-        tile_apply_kernel<N, additive ? FN : RZ_SUM, TR, is_float ? 0 : 2, false><<<grid, TR * 4, smem, s>>>(
-            P, T, tile_start, desc, masks, tcnt, bg, (N*)out);
+        launch_apply(tile_apply_kernel<N, additive ? FN : RZ_SUM, TR, is_float ? 0 : 2, false>, grid, THREADS, smem, s, P, T, tile_start, desc, masks, tcnt, bg, (N*)out);
     else if (ordered && (is_float ? bg_nan : true))  // MODE 3 (when no value can look like the background)
-        tile_apply_kernel<N, ordered ? FN : RZ_FIRST, TR, 3, NanBackground<N>::possible><<<grid, TR * 4, smem, s>>>(
-            P, T, tile_start, desc, masks, tcnt, bg, (N*)out);
+        launch_apply(tile_apply_kernel<N, ordered ? FN : RZ_FIRST, TR, 3, NanBackground<N>::possible>, grid, THREADS, smem, s, P, T, tile_start, desc, masks, tcnt, bg, (N*)out);
     else if (bg_nan)  // float dtypes with a NaN background: one comparison less per pixel
-        tile_apply_kernel<N, FN, TR, 0, NanBackground<N>::possible><<<grid, TR * 4, smem, s>>>(P, T, tile_start, desc, masks,
-                                                                                            tcnt, bg, (N*)out);
+        launch_apply(tile_apply_kernel<N, FN, TR, 0, NanBackground<N>::possible>, grid, THREADS, smem, s, P, T, tile_start, desc, masks, tcnt, bg, (N*)out);
     else
-        tile_apply_kernel<N, FN, TR, 0, false><<<grid, TR * 4, smem, s>>>(P, T, tile_start, desc, masks, tcnt, bg, (N*)out);
+        launch_apply(tile_apply_kernel<N, FN, TR, 0, false>, grid, THREADS, smem, s, P, T, tile_start, desc, masks, tcnt, bg, (N*)out);
 }
 template <typename N> static TileLaunch tile_for_fn(int fn) {
     switch (fn) {

@@ -668,14 +668,73 @@ __device__ __forceinline__ void apply_part_word(N (&px)[32], uint32_t mw, N v, N
 }
 
 constexpr int APPLY_TILES = 8;  // consecutive tiles of one tile row handled by one CTA
-constexpr int APPLY_DEPTH = 4;  // blocks in flight per warp (power of two)
+constexpr int AP_STAGES = 3;               // batches of mask blocks in flight per CTA
+constexpr uint32_t AP_STAGE_WORDS = 2048;  // mask words of one batch (a block holds at most 64 x 4 = 256)
+constexpr uint32_t AP_STAGE_BLOCKS = 32;   // blocks of one batch (one producer lane each)
 
+// A block as the consumer warps see it: its value, where its words start inside the batch's stage, its geometry.
+struct alignas(16) StagedDesc {
+    unsigned long long value_bits;
+    uint32_t soff;
+    uint32_t geom;
+};
+
+// ---- mbarrier / bulk-copy (TMA) primitives -------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}" ::"r"(smem_addr(bar)), "r"(parity)
+        : "memory");
+}
+// global -> shared bulk copy (the TMA engine moves `bytes`, a multiple of 16, and signals `bar` with them)
+__device__ __forceinline__ void bulk_copy_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_addr(bar))
+                 : "memory");
+}
+
+// Shared memory of one tile_apply CTA, after the flush staging rows of its consumer warps.
+struct ApplyShared {
+    uint32_t words[AP_STAGES][AP_STAGE_WORDS];
+    StagedDesc desc[AP_STAGES][AP_STAGE_BLOCKS];
+    uint64_t full[AP_STAGES], empty[AP_STAGES];
+    uint32_t count[AP_STAGES];
+};
+template <typename N, int TILE_R> __host__ __device__ constexpr size_t apply_flush_bytes() { return (size_t)(TILE_R / 8) * 8 * 4 * (32 * sizeof(N) + 16); }
+template <typename N, int TILE_R> __host__ __device__ constexpr size_t apply_smem_bytes() { return apply_flush_bytes<N, TILE_R>() + sizeof(ApplyShared); }
+
+// One CTA = TILE_R / 8 consumer warps + ONE producer warp.  The descriptors of a CTA's tiles are consecutive in
+// memory, tile after tile, parts in burn order inside a tile.  The producer walks them in batches of up to 32 blocks
+// / 2048 mask words: lane i reads descriptor i of the batch (coalesced), a warp scan places the blocks' compact mask
+// words back to back in a shared-memory stage, and every lane issues ONE bulk copy (cp.async.bulk, the TMA engine)
+// for its block; the copies signal the stage's `full` mbarrier with their byte counts.  Three stages are in flight,
+// recycled through `empty` mbarriers the consumer warps arrive on.  The consumers never touch global memory for
+// masks: every block costs them a broadcast descriptor read, a row test and - if the block reaches their 8 rows -
+// one shared-memory word per lane.
 template <typename N, int FN, int TILE_R, int MODE, bool BGNAN>
 __device__ __forceinline__ void tile_apply_body(const KParams& P, const TileParams& T, const uint32_t* __restrict__ tile_start,
                                                 const BlockDesc* __restrict__ desc, const uint32_t* __restrict__ masks,
                                                 uint64_t bg_bits, N* __restrict__ out, unsigned char* smem_raw) {
+    constexpr uint32_t NW = TILE_R / 8;  // consumer warps
     const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
     const N bg = value_from_bits<N>(bg_bits);
+    ApplyShared& sh = *reinterpret_cast<ApplyShared*>(smem_raw + apply_flush_bytes<N, TILE_R>());
 
     // grid = (groups of APPLY_TILES tile columns, tile rows x bands), or 1-D when that does not fit the grid limits
     const uint32_t groups = (T.n_tc + APPLY_TILES - 1) / APPLY_TILES;
@@ -696,8 +755,59 @@ __device__ __forceinline__ void tile_apply_body(const KParams& P, const TilePara
     }
     const uint32_t tcol0 = tgrp * APPLY_TILES, n_here = min((uint32_t)APPLY_TILES, T.n_tc - tcol0);
     const uint32_t t0 = (band * T.n_tr + trow) * T.n_tc + tcol0;
+    const uint32_t tile_row0 = P.win_r0 + trow * TILE_R;
+    const uint32_t n_active = min(NW, (P.win_r1 - tile_row0 + 7u) / 8u);  // consumer warps that own raster rows
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int k = 0; k < AP_STAGES; k++) {
+            mbar_init(&sh.full[k], 1);
+            mbar_init(&sh.empty[k], n_active);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+    const uint32_t cta_beg = tile_start[t0], cta_end = tile_start[t0 + n_here];  // blocks of this CTA's tiles
+
+    if (warp == NW) {
+        // ---- producer --------------------------------------------------------------------------------------
+        uint32_t jb = cta_beg;
+        for (uint32_t k = 0; jb < cta_end; k++) {
+            const uint32_t st = k % AP_STAGES;
+            if (k >= (uint32_t)AP_STAGES) mbar_wait(&sh.empty[st], ((k / AP_STAGES) - 1u) & 1u);
+            const uint32_t j = jb + lane;
+            uint4 d = make_uint4(0, 0, 0, 0);
+            if (j < cta_end) d = __ldg(reinterpret_cast<const uint4*>(desc + j));  // value lo, value hi, woff, geom
+            const uint32_t size = j < cta_end ? ((((d.w >> 8) & 0xffu) * (d.w >> 20) + 7u) & ~7u) : 0u;
+            uint32_t inc = size;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t up = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= (uint32_t)o) inc += up;
+            }
+            const uint32_t fits = __ballot_sync(0xffffffffu, j < cta_end && inc <= AP_STAGE_WORDS);  // a prefix of the lanes
+            const uint32_t cnt = __popc(fits);                                                        // >= 8
+            const uint32_t total = __shfl_sync(0xffffffffu, inc, cnt - 1);
+            if (lane < cnt) {
+                StagedDesc sd;
+                sd.value_bits = (unsigned long long)d.x | ((unsigned long long)d.y << 32);
+                sd.soff = inc - size;
+                sd.geom = d.w;
+                sh.desc[st][lane] = sd;
+            }
+            if (lane == 0) sh.count[st] = cnt;
+            __syncwarp();
+            if (lane == 0) mbar_arrive_expect_tx(&sh.full[st], total * 4u);
+            __syncwarp();
+            if (lane < cnt) bulk_copy_g2s(&sh.words[st][inc - size], masks + d.z, size * 4u, &sh.full[st]);
+            jb += cnt;
+        }
+        return;
+    }
+
+    // ---- consumers ---------------------------------------------------------------------------------------------
     const uint32_t wr0 = warp * 8;  // first of this warp's rows inside the tile
-    const uint32_t r0 = P.win_r0 + trow * TILE_R + wr0;
+    const uint32_t r0 = tile_row0 + wr0;
     if (r0 >= P.win_r1) return;
 
     N ident;
@@ -711,75 +821,36 @@ __device__ __forceinline__ void tile_apply_body(const KParams& P, const TilePara
     } else {
         ident = bg;  // MODE 0: the background; MODE 2: bg == 0; MODE 3 first: never read before written
     }
-
-    // The descriptors of a CTA's tiles are consecutive in memory, tile after tile, parts in burn order inside a
-    // tile.  Two rings indexed by (block index mod APPLY_DEPTH) run over all of them without restarting at tile
-    // borders: slot u holds this lane's mask word and the value of the next block j = u (mod DEPTH) to consume,
-    // and the descriptor (where / which rows and words) of block j + DEPTH; consuming block j loads block
-    // j + DEPTH's word and block j + 2 DEPTH's descriptor.  Only the first tile of a CTA waits for its loads.
     const uint32_t my_r = wr0 + (lane >> 2), my_w = lane & 3u;
-    auto fetch_word = [&](uint32_t woff, uint32_t geom) -> uint32_t {  // this lane's word of a block, 0 if not covered
-        const uint32_t rr = my_r - (geom & 0xffu), ww = my_w - ((geom >> 16) & 0xfu), nw = geom >> 20;
-        const bool in = rr < ((geom >> 8) & 0xffu) && ww < nw;
-        return in ? __ldg(masks + woff + rr * nw + ww) : 0u;
-    };
-    auto reaches = [&](uint32_t geom) -> bool {  // does the block hold any of this warp's 8 rows?  (warp-uniform)
-        const uint32_t b_row = geom & 0xffu, b_nr = (geom >> 8) & 0xffu;
-        return b_row < wr0 + 8u && b_row + b_nr > wr0;
-    };
-    uint32_t m[APPLY_DEPTH], g_woff[APPLY_DEPTH], g_geom[APPLY_DEPTH];
-    N val[APPLY_DEPTH];  // the value occupies the low bytes of its 8-byte slot
-    bool hit[APPLY_DEPTH];
-    const uint32_t cta_end = tile_start[t0 + n_here];  // one past the last block of this CTA's tiles
-    uint32_t beg = tile_start[t0], end = tile_start[t0 + 1];
-#pragma unroll
-    for (int u = 0; u < APPLY_DEPTH; u++) {
-        uint32_t j = (beg & ~(uint32_t)(APPLY_DEPTH - 1)) + u;
-        if (j < beg) j += APPLY_DEPTH;
-        uint32_t woff = 0, geom = 0;
-        if (j < cta_end) {
-            const uint2 wg = *reinterpret_cast<const uint2*>(&desc[j].woff);
-            woff = wg.x;
-            geom = wg.y;
-        }
-        hit[u] = j < cta_end && reaches(geom);
-        m[u] = hit[u] ? fetch_word(woff, geom) : 0u;
-        val[u] = hit[u] ? *reinterpret_cast<const N*>(&desc[j].value_bits) : bg;
-        g_woff[u] = 0;
-        g_geom[u] = 0;
-        if (j + APPLY_DEPTH < cta_end) {
-            const uint2 wg = *reinterpret_cast<const uint2*>(&desc[j + APPLY_DEPTH].woff);
-            g_woff[u] = wg.x;
-            g_geom[u] = wg.y;
-        }
-    }
+    uint32_t j = cta_beg, batch_beg = cta_beg, batch_end = cta_beg, n_batches = 0, st = 0;
     for (uint32_t ti = 0; ti < n_here; ti++) {
-    const uint32_t end_next = ti + 1 < n_here ? tile_start[t0 + ti + 2] : end;  // needed after this tile's blocks
+    const uint32_t end = tile_start[t0 + ti + 1];
     const uint32_t c0 = (tcol0 + ti) * TILE_C;
     N px[32];  // pixel b = (row r0 + (lane >> 2), column c0 + 32 * (lane & 3) + b)
     uint32_t touched = 0;
 #pragma unroll
     for (int b = 0; b < 32; b++) px[b] = ident;
 
-    for (uint32_t j0 = beg & ~(uint32_t)(APPLY_DEPTH - 1); j0 < end; j0 += APPLY_DEPTH) {
-#pragma unroll
-        for (int u = 0; u < APPLY_DEPTH; u++) {
-            const uint32_t j = j0 + u;
-            if (j < beg || j >= end) continue;  // another tile's block: its slot stays as it is
-            const uint32_t mu = m[u];
-            const N v = val[u];
-            const bool was_hit = hit[u];
-            // refill the slot: word and value of block j + DEPTH (descriptor at hand), descriptor of j + 2 DEPTH
-            const uint32_t nxt = j + APPLY_DEPTH;
-            hit[u] = nxt < cta_end && reaches(g_geom[u]);
-            m[u] = hit[u] ? fetch_word(g_woff[u], g_geom[u]) : 0u;
-            val[u] = hit[u] ? *reinterpret_cast<const N*>(&desc[nxt].value_bits) : bg;
-            if (nxt + APPLY_DEPTH < cta_end) {
-                const uint2 wg = *reinterpret_cast<const uint2*>(&desc[nxt + APPLY_DEPTH].woff);
-                g_woff[u] = wg.x;
-                g_geom[u] = wg.y;
+    while (j < end) {
+        if (j >= batch_end) {  // next batch: hand the finished stage back, wait for the next one to land
+            if (n_batches) {
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&sh.empty[(n_batches - 1u) % AP_STAGES]);
             }
-            if (!was_hit) continue;  // the block does not reach these 8 rows
+            st = n_batches % AP_STAGES;
+            mbar_wait(&sh.full[st], (n_batches / AP_STAGES) & 1u);
+            batch_beg = batch_end;
+            batch_end += sh.count[st];
+            n_batches++;
+        }
+        const uint32_t lim = min(end, batch_end);
+        for (; j < lim; j++) {
+            const StagedDesc d = sh.desc[st][j - batch_beg];
+            const uint32_t b_row = d.geom & 0xffu, b_nr = (d.geom >> 8) & 0xffu;
+            if (!(b_row < wr0 + 8u && b_row + b_nr > wr0)) continue;  // the block does not reach these 8 rows
+            const uint32_t rr = my_r - b_row, ww = my_w - ((d.geom >> 16) & 0xfu), nw = d.geom >> 20;
+            const uint32_t mu = (rr < b_nr && ww < nw) ? sh.words[st][d.soff + rr * nw + ww] : 0u;
+            const N v = value_from_bits<N>(d.value_bits);
             if (MODE == 3) {
                 apply_part_word<N, FN, 3, BGNAN>(px, FN == RZ_FIRST ? (mu & ~touched) : mu, v, bg);
                 touched |= mu;
@@ -840,14 +911,12 @@ __device__ __forceinline__ void tile_apply_body(const KParams& P, const TilePara
         }
     }
     __syncwarp();  // the staging rows are reused by the next tile
-    beg = end;
-    end = end_next;
     }  // tiles of this CTA
 }
 
 // FAST_MODE runs when the burn values allow it (see MODE above), else the generic MODE 0 body.
 template <typename N, int FN, int TILE_R, int FAST_MODE, bool BGNAN>
-static __global__ void __launch_bounds__(TILE_R * 4, 4)
+static __global__ void __launch_bounds__(TILE_R * 4 + 32, TILE_R == 64 ? 3 : 4)
 tile_apply_kernel(KParams P, TileParams T, const uint32_t* __restrict__ tile_start, const BlockDesc* __restrict__ desc,
                   const uint32_t* __restrict__ masks, const TileCounters* __restrict__ tcnt, uint64_t bg_bits,
                   N* __restrict__ out) {

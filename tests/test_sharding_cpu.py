@@ -1,6 +1,7 @@
-"""Host-side logic of the multi-GPU path on CPU: row-band planning, per-band geometry selection and
-assembly, run as a world-size-2 gloo job.  The compute stand-in is the oracle (this is tests/): the
-CUDA path itself needs a GPU and is covered by test_gpu_parity.py::test_row_band_shards_equal_full_raster."""
+"""Host-side logic of the multi-GPU path on CPU: row-band planning, the library's per-band part selection
+(rz_geoms_row_shard) and assembly, run as a world-size-2 gloo job.  The compute stand-in is the oracle (this is
+tests/): the CUDA path itself needs a GPU and is covered by test_gpu_parity.py::test_row_band_shards_equal_full_raster
+and tests/test_gpu_multi.py."""
 import os
 import subprocess
 import sys
@@ -23,18 +24,38 @@ def test_band_plan_covers_rows_exactly():
             assert all(a[1] == b[0] for a, b in zip(bands, bands[1:]))
 
 
+def _shard_rings(w, r0, r1):
+    """This rank's share of a row-band sharded job, as the LIBRARY cuts it (rz_geoms_row_shard, host code): the
+    shard's polygon rings and the field value of each (by its unchanged geometry index)."""
+    from rusterize_b200 import core
+
+    full = core.Geoms.from_soa(*w["soa"])
+    ri = core.raster_info(None, shape=(w["rows"], w["cols"]), extent=(0, 0, w["cols"], w["rows"]))
+    sh = full.row_shard(ri, r0, r1)
+    x, y, tag = sh.pool(0)
+    ends = np.flatnonzero(tag & 0x80000000)
+    off = np.concatenate([[0], ends + 1]).astype(np.uint64)
+    _, geom = sh.parts()
+    part_of_ring = (tag[ends] & 0x3FFFFFFF).astype(np.int64)
+    return x, y, off, w["field"][geom[part_of_ring].astype(np.int64)], sh.n_parts
+
+
 def test_band_selection_keeps_every_touching_polygon_in_order():
-    w, x, y, off, vals = bench.make_workload("tiny")
+    w = bench.make_workload("tiny")
+    _, _, _, off, x, y = w["soa"]
     full = oracle.rasterize_dense(oracle.Geoms.from_rings(x, y, off), oracle.raster_info(
-        None, shape=(w["rows"], w["cols"]), extent=(0, 0, w["cols"], w["rows"])), "sum", "float32", vals,
+        None, shape=(w["rows"], w["cols"]), extent=(0, 0, w["cols"], w["rows"])), "sum", "float32", w["field"],
         background=np.nan)[0]
     for r0, r1 in [(0, 100), (100, 612), (612, 1024)]:
-        bx, by, boff, bvals = bench.select_band_polygons(x, y, off, vals, w["rows"], r0, r1)
-        assert len(boff) - 1 < w["n"]
+        bx, by, boff, bvals, n_parts = _shard_rings(w, r0, r1)
+        assert n_parts < w["n"]
         ri = oracle.raster_info(None, shape=(r1 - r0, w["cols"]), extent=(0, w["rows"] - r1, w["cols"], w["rows"] - r0))
         band = oracle.rasterize_dense(oracle.Geoms.from_rings(bx, by, boff), ri, "sum", "float32", bvals,
                                       background=np.nan)[0]
         assert np.array_equal(band[0], full[0, r0:r1], equal_nan=True)
+    # the oracle-side cut bench.py uses for its parity slices keeps at least what the library keeps
+    keep = bench.geoms_touching_rows(w, 100, 612)
+    assert keep.sum() >= _shard_rings(w, 100, 612)[4]
 
 
 WORKER = textwrap.dedent("""
@@ -42,18 +63,20 @@ WORKER = textwrap.dedent("""
     sys.path.insert(0, {root!r}); sys.path.insert(0, os.path.join({root!r}, "tests"))
     import numpy as np, torch, torch.distributed as dist
     import bench, oracle
+    from test_sharding_cpu import _shard_rings
     dist.init_process_group("gloo")
     rank, world = dist.get_rank(), dist.get_world_size()
-    w, x, y, off, vals = bench.make_workload("tiny")
+    w = bench.make_workload("tiny")
     r0, r1 = bench.band_of(rank, world, w["rows"])
-    bx, by, boff, bvals = bench.select_band_polygons(x, y, off, vals, w["rows"], r0, r1)
+    bx, by, boff, bvals, _ = _shard_rings(w, r0, r1)
     ri = oracle.raster_info(None, shape=(r1 - r0, w["cols"]), extent=(0, w["rows"] - r1, w["cols"], w["rows"] - r0))
     band = oracle.rasterize_dense(oracle.Geoms.from_rings(bx, by, boff), ri, "sum", "float32", bvals, background=np.nan)[0]
     parts = [torch.empty((1, b[1] - b[0], w["cols"])) for b in (bench.band_of(r, world, w["rows"]) for r in range(world))]
     dist.all_gather(parts, torch.from_numpy(band))
     if rank == 0:
+        _, _, _, off, x, y = w["soa"]
         full = oracle.rasterize_dense(oracle.Geoms.from_rings(x, y, off), oracle.raster_info(
-            None, shape=(w["rows"], w["cols"]), extent=(0, 0, w["cols"], w["rows"])), "sum", "float32", vals,
+            None, shape=(w["rows"], w["cols"]), extent=(0, 0, w["cols"], w["rows"])), "sum", "float32", w["field"],
             background=np.nan)[0]
         got = torch.cat(parts, 1).numpy()
         assert np.array_equal(got, full, equal_nan=True)
