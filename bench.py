@@ -533,7 +533,7 @@ def run_dense(env, name, w, headline):
         parity[fun] = env.gather_objects(par)
         s0 = dict(stats[-1])
         for k, v in zip(keys, agg):
-            s0[k] = v
+            s0[k] = v / world  # per GPU: a launch's bytes over that launch's duration (the slowest rank's)
         per_fun[fun] = {"dtype": dtype, "ms": ms_max, "Mpixel_per_s": n_b * rows * cols / (ms_max / 1e3) / 1e6,
                         "polygons_per_s": w["n"] / (ms_max / 1e3),
                         "engine": "tile-binned" if s0["engine"] == 1 else "crossing-records",
@@ -569,6 +569,11 @@ def run_dense_e2e(env, name, w):
     h_np = h_out.numpy()
     devices = list(range(world))
     eng_flag = {"auto": 0, "records": _lib.FLAG_NO_TILE_ENGINE, "tiles": _lib.FLAG_FORCE_TILE_ENGINE}[args.engine]
+    if world > 1:  # this process now drives every GPU: it may run on every core again
+        try:
+            os.sched_setaffinity(0, range(os.cpu_count()))
+        except OSError:
+            pass
 
     def call(g, flags):
         return core.rasterize_dense(g, ri, fun, dtype, w["field"], None, band, n_b, bg, out=h_np, devices=devices,
@@ -628,6 +633,11 @@ def run_sparse(env, name, w):
     ri = core.raster_info(None, shape=(rows, cols), extent=(0.0, 0.0, float(cols), float(rows)))
     devices = list(range(world))
     steps = max(2, min(args.steps, 3))
+    if world > 1:
+        try:
+            os.sched_setaffinity(0, range(os.cpu_count()))
+        except OSError:
+            pass
     g = core.Geoms.from_soa(*w["soa"])
     sp = core.rasterize_sparse(g, ri, fun, dtype, w["field"], background=bg, devices=devices)  # warm (pools, uploads)
     ms, sts = [], []
@@ -637,16 +647,22 @@ def run_sparse(env, name, w):
         sp = core.rasterize_sparse(g, ri, fun, dtype, w["field"], background=bg, devices=devices)
         ms.append((time.perf_counter() - t0) * 1e3)
         sts.append(sp["stats"])
-    # the whole call incl. flattening and upload
-    whole = []
-    for _ in range(max(1, args.e2e_steps)):
+    # the whole call incl. flattening and upload (a caller's previous geometry set is gone: its page-locked pools are
+    # recycled by the next one)
+    whole, flat = [], []
+    del g
+    for i in range(max(1, args.e2e_steps) + 1):
         del sp
         t0 = time.perf_counter()
-        g2 = core.Geoms.from_soa(*w["soa"])
-        sp = core.rasterize_sparse(g2, ri, fun, dtype, w["field"], background=bg, devices=devices)
-        whole.append((time.perf_counter() - t0) * 1e3)
+        g = core.Geoms.from_soa(*w["soa"])
+        t1 = time.perf_counter()
+        sp = core.rasterize_sparse(g, ri, fun, dtype, w["field"], background=bg, devices=devices)
+        if i:  # (the first pass re-creates the pools the warm handle above held differently sized)
+            whole.append((time.perf_counter() - t0) * 1e3)
+            flat.append((t1 - t0) * 1e3)
         st_e2e = sp["stats"]
-        del g2
+        if i < max(1, args.e2e_steps):
+            del g
     st = sts[-1]
     P = int(len(sp["rows"]))
     X = int(st["n_crossings"])
@@ -708,7 +724,8 @@ def run_sparse(env, name, w):
            "e2e": {"value": rows * cols / (e_ms / 1e3) / 1e6, "unit": "Mpixel/s", "ms_per_step": e_ms,
                    "h2d_bytes_per_step": int(st_e2e["h2d_bytes"]), "d2h_bytes_per_step": int(st_e2e["d2h_bytes"]),
                    "includes": "rz_geoms_from_soa + geometry-range subsets + H2D + scans/sort/expand + D2H into one triplet stream",
-                   "ms_each_step": [round(v, 1) for v in whole]},
+                   "ms_each_step": [round(v, 1) for v in whole], "flatten_ms": float(np.mean(flat)),
+                   "per_device_wall_shard_ms": [[round(p["wall_ms"], 1), round(p["shard_ms"], 1)] for p in st_e2e["per_device"]]},
            "per_device": [{"device": d, "total_ms": round(p["total_ms"], 2), "wall_ms": round(p["wall_ms"], 2),
                            "shard_ms": round(p["shard_ms"], 2), "d2h_ms": round(p["d2h_ms"], 2),
                            "expand_ms": round(p["fill_ms"], 2), "triplet_MB": round(p["out_bytes"] / 1e6, 1)} for d, p in enumerate(per)],

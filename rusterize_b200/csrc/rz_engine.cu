@@ -14,7 +14,10 @@
 #include <limits>
 #include <memory>
 #include <string>
+#include <pthread.h>
+#include <sched.h>
 #include <sys/mman.h>
+#include <cctype>
 #include <unistd.h>
 #include <chrono>
 #include <thread>
@@ -862,6 +865,12 @@ static void rasterize_dense(rz_geoms* g, const rz_context* ctx, void* out, rz_st
             T.n_tc = (uint32_t)((ri.ncols + TILE_C - 1) / TILE_C);
             T.n_tr = (rows + T.tile_r - 1) / T.tile_r;
             const uint64_t n_tiles64 = (uint64_t)n_bands * T.n_tr * T.n_tc;
+            // tile_apply: 8 consecutive tiles per CTA amortise the pipeline start-up; small rasters take fewer so that
+            // the grid still covers the machine several times over
+            T.apply_tiles = APPLY_TILES;
+            while (T.apply_tiles > 1 &&
+                   (uint64_t)n_bands * T.n_tr * ((T.n_tc + T.apply_tiles - 1) / T.apply_tiles) < (uint64_t)c.sm_count * 12)
+                T.apply_tiles /= 2;
             if (n_tiles64 < (1ull << 31)) {  // record = [tile | block], both below 2^31
                 T.n_tiles = (uint32_t)n_tiles64;
                 c.tile_cnt.ensure((size_t)n_parts * 12);
@@ -1832,7 +1841,7 @@ static uint64_t f64_bits(double v) {
     return u;
 }
 
-static std::shared_ptr<rz_geoms> cached_subset(rz_geoms* g, const std::vector<uint64_t>& key,
+static std::shared_ptr<rz_geoms> cached_subset(rz_geoms* g, const std::vector<uint64_t>& key, unsigned threads,
                                                const std::function<void(std::vector<uint32_t>&)>& select) {
     {
         std::lock_guard<std::mutex> lk(g->mu);
@@ -1841,7 +1850,7 @@ static std::shared_ptr<rz_geoms> cached_subset(rz_geoms* g, const std::vector<ui
     }
     std::vector<uint32_t> keep;
     select(keep);
-    std::shared_ptr<rz_geoms> sub(subset_parts(g, keep.data(), keep.size(), 2));
+    std::shared_ptr<rz_geoms> sub(subset_parts(g, keep.data(), keep.size(), threads));
     std::lock_guard<std::mutex> lk(g->mu);
     if (g->shards.size() >= 64) g->shards.clear();
     g->shards[key] = sub;
@@ -1871,6 +1880,46 @@ static void part_y_extent(const rz_geoms* g, uint32_t p, double& ylo, double& yh
         ylo = -inf;
         yhi = inf;
     }
+}
+
+// Run the calling thread (and the threads it starts) on the CPUs next to a device: its part subset is then first
+// touched, and its copies are staged, on the NUMA node the device's PCIe link hangs off.  The CPU list comes from
+// sysfs (/sys/bus/pci/devices/<bus id>/local_cpulist); best effort, RZ_NO_AFFINITY=1 turns it off.
+static void bind_thread_near_device(int dev) {
+    if (std::getenv("RZ_NO_AFFINITY")) return;
+    char bus[32] = {0};
+    if (cudaDeviceGetPCIBusId(bus, (int)sizeof bus, dev) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return;
+    }
+    for (char* q = bus; *q; q++) *q = (char)std::tolower((unsigned char)*q);
+    const std::string path = std::string("/sys/bus/pci/devices/") + bus + "/local_cpulist";
+    std::FILE* f = std::fopen(path.c_str(), "r");
+    if (!f) return;
+    char line[4096] = {0};
+    const bool ok = std::fgets(line, (int)sizeof line, f) != nullptr;
+    std::fclose(f);
+    if (!ok) return;
+    cpu_set_t set;
+    CPU_ZERO(&set);
+    int n_set = 0;
+    for (char* q = line; *q && *q != '\n';) {  // "0-15,64-79"
+        char* e = nullptr;
+        const long a = std::strtol(q, &e, 10);
+        if (e == q) break;
+        long b = a;
+        q = e;
+        if (*q == '-') {
+            b = std::strtol(q + 1, &e, 10);
+            q = e;
+        }
+        for (long c = a; c <= b && c < CPU_SETSIZE; c++) {
+            CPU_SET((int)c, &set);
+            n_set++;
+        }
+        if (*q == ',') q++;
+    }
+    if (n_set) (void)pthread_setaffinity_np(pthread_self(), sizeof set, &set);
 }
 
 template <typename F> static void run_per_device(int n, F&& body, Error& first_error) {
@@ -1934,6 +1983,8 @@ static void rasterize_dense_multi(rz_geoms* g, const rz_context* ctx, const int3
     if (r1 > ri.nrows || (r0 >= r1 && ri.nrows)) throw Error{RZ_VALUE_ERROR, "Invalid row shard"};
     const uint64_t rows = r1 - r0;
     const int D = (int)std::min<uint64_t>((uint64_t)n_devices, std::max<uint64_t>(rows, 1));
+    // the devices' host threads cut their subsets at the same time: they share the machine's cores
+    const unsigned sub_threads = std::max(2u, std::min(16u, std::max(1u, std::thread::hardware_concurrency()) / (unsigned)D));
     std::vector<rz_stats> S((size_t)D);
     for (auto& x : S) std::memset(&x, 0, sizeof x);
     const double margin = ctx->all_touched ? 3.0 : 2.0;  // pixel rows of slack around a part's extent
@@ -1946,12 +1997,13 @@ static void rasterize_dense_multi(rz_geoms* g, const rz_context* ctx, const int3
         c.row_begin = b0;
         c.row_end = b1;
         if (b1 <= b0) return;
+        if (D > 1) bind_thread_near_device(devices[d]);
         rz_geoms* use = g;
         std::shared_ptr<rz_geoms> sub;
         const WallClock shard_clock;
         if (D > 1) {
             const std::vector<uint64_t> key{0, f64_bits(ri.ymax), f64_bits(ri.yres), b0, b1, (uint64_t)margin};
-            sub = cached_subset(g, key, [&](std::vector<uint32_t>& keep) { select_row_parts(g, ri, b0, b1, margin, keep); });
+            sub = cached_subset(g, key, sub_threads, [&](std::vector<uint32_t>& keep) { select_row_parts(g, ri, b0, b1, margin, keep); });
             use = sub.get();
         }
         const float shard_ms = shard_clock.ms();
@@ -2045,6 +2097,7 @@ static void rasterize_sparse_multi(rz_geoms* g, const rz_context* ctx, const int
     const uint32_t n_bands = ctx->band_of_geom ? (uint32_t)std::max(ctx->n_bands, 0) : 1u;
     const size_t np = g->part_kind.size();
     const int D = (int)std::max<size_t>(1, std::min<size_t>((size_t)n_devices, g->n_geoms));
+    const unsigned sub_threads = std::max(2u, std::min(16u, std::max(1u, std::thread::hardware_concurrency()) / (unsigned)D));
     // ---- contiguous geometry ranges of equal estimated work (a prefix sum of per-geometry cost) ----
     // cost of a part: its vertices (setup) + for polygons the pixels of its box (fill, ~half of them burned) and two
     // crossings per row; for lines the longer side of each part's box is unknown without a scan: vertices x 16
@@ -2093,12 +2146,13 @@ static void rasterize_sparse_multi(rz_geoms* g, const rz_context* ctx, const int
             rz_context c = *ctx;
             c.device = devices[d];
             c.stream = nullptr;
+            if (D > 1) bind_thread_near_device(devices[d]);
             rz_geoms* use = g;
             std::shared_ptr<rz_geoms> sub;
             const WallClock shard_clock;
             if (D > 1) {
                 const std::vector<uint64_t> key{1, (uint64_t)cut[(size_t)d], (uint64_t)cut[(size_t)d + 1]};
-                sub = cached_subset(g, key, [&](std::vector<uint32_t>& keep) {
+                sub = cached_subset(g, key, sub_threads, [&](std::vector<uint32_t>& keep) {
                     keep.resize(cut[(size_t)d + 1] - cut[(size_t)d]);
                     for (size_t i = 0; i < keep.size(); i++) keep[i] = (uint32_t)(cut[(size_t)d] + i);
                 });

@@ -932,22 +932,40 @@ rz_geoms* subset_parts(const rz_geoms* src, const uint32_t* keep, size_t n_keep,
         for (unsigned t = 0; t < T; t++) th.emplace_back([&, t]() { body(t); });
         for (auto& x : th) x.join();
     };
-    // sequences of part p inside its pool: those whose last vertex lies in [vbeg, vend)
-    auto seq_range = [&](uint32_t p, size_t& lo, size_t& hi) {
+    // sequences of part p inside its pool: those whose last vertex lies in [vbeg, vend).  Kept parts ascend, so do
+    // their sequences: a cursor per kind (placed by one binary search, then advanced linearly) finds them.
+    struct SeqCursor {
+        size_t at[2] = {0, 0};
+        bool placed[2] = {false, false};
+    };
+    auto seq_range = [&](SeqCursor& cur, uint32_t p, size_t& lo, size_t& hi) {
         const int k = src->part_kind[p];
         const auto& se = src->pool[k].seq_end;
-        lo = std::lower_bound(se.begin(), se.end(), src->part_vbeg[p]) - se.begin();
-        hi = std::lower_bound(se.begin() + lo, se.end(), src->part_vend[p]) - se.begin();
+        const uint32_t vb = src->part_vbeg[p], ve = src->part_vend[p];
+        if (!cur.placed[k]) {
+            cur.at[k] = std::lower_bound(se.begin(), se.end(), vb) - se.begin();
+            cur.placed[k] = true;
+        }
+        size_t a = cur.at[k];
+        if (a < se.size() && se[a] < vb && a + 64 < se.size() && se[a + 64] < vb)  // a long jump between kept parts
+            a = std::lower_bound(se.begin() + a, se.end(), vb) - se.begin();
+        while (a < se.size() && se[a] < vb) a++;
+        size_t b = a;
+        while (b < se.size() && se[b] < ve) b++;
+        lo = a;
+        hi = b;
+        cur.at[k] = b;
     };
     run([&](unsigned t) {
         Chunk& c = ch[t];
+        SeqCursor cur;
         for (size_t j = c.j0; j < c.j1; j++) {
             const uint32_t p = keep[j];
             const int k = src->part_kind[p];
             c.pool_cnt[k] += src->part_vend[p] - src->part_vbeg[p];
             if (k != RZ_PART_POINT) {
                 size_t lo, hi;
-                seq_range(p, lo, hi);
+                seq_range(cur, p, lo, hi);
                 c.seq_cnt[k] += hi - lo;
             }
         }
@@ -985,6 +1003,7 @@ rz_geoms* subset_parts(const rz_geoms* src, const uint32_t* keep, size_t n_keep,
     run([&](unsigned t) {
         Chunk& c = ch[t];
         uint64_t at[3] = {c.pool_off[0], c.pool_off[1], c.pool_off[2]}, sq[2] = {c.seq_off[0], c.seq_off[1]};
+        SeqCursor cur;
         for (size_t j = c.j0; j < c.j1; j++) {
             const uint32_t p = keep[j];
             const int k = src->part_kind[p];
@@ -1001,7 +1020,7 @@ rz_geoms* subset_parts(const rz_geoms* src, const uint32_t* keep, size_t n_keep,
             g->part_vend[j] = (uint32_t)(at[k] + n);
             if (k != RZ_PART_POINT) {
                 size_t lo, hi;
-                seq_range(p, lo, hi);
+                seq_range(cur, p, lo, hi);
                 for (size_t q = lo; q < hi; q++) {
                     g->pool[k].seq_end[sq[k]] = (uint32_t)(src->pool[k].seq_end[q] - vb + at[k]);
                     g->pool[k].seq_closed[sq[k]] = src->pool[k].seq_closed[q];

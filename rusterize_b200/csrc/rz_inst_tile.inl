@@ -37,10 +37,10 @@ static void tile_launch(cudaStream_t s, KParams P, TileParams T, const uint32_t*
     constexpr bool is_float = std::is_floating_point<N>::value;
     constexpr bool additive = FN == RZ_SUM || FN == RZ_COUNT;
     constexpr bool ordered = FN == RZ_FIRST || FN == RZ_MIN || FN == RZ_MAX;
-    // one CTA per APPLY_TILES tiles of a tile row: (column groups, tile rows x bands) when that fits the grid
+    // one CTA per T.apply_tiles tiles of a tile row: (column groups, tile rows x bands) when that fits the grid
     // limits, else flattened
     const uint64_t gy = (uint64_t)T.n_tr * P.n_bands;
-    const uint32_t groups = (T.n_tc + APPLY_TILES - 1) / APPLY_TILES;
+    const uint32_t groups = (T.n_tc + T.apply_tiles - 1) / T.apply_tiles;
     static const bool force_1d = std::getenv("RZ_APPLY_1D") != nullptr;  // tests: exercise the flattened grid
     const dim3 grid = (gy <= 65535 && !force_1d) ? dim3(groups, (unsigned)gy) : dim3((unsigned)(groups * gy));
     // flush staging (8 padded rows per consumer warp) + the staged mask blocks and their mbarriers

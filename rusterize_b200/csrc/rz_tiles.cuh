@@ -55,6 +55,7 @@ struct TileParams {
     uint32_t win_row_off, out_rows;
     uint32_t vec_ok;
     uint32_t cap_pairs, cap_units;  // capacity of the record / unit arrays (upper bounds cached on the host)
+    uint32_t apply_tiles;           // consecutive tiles of a tile row per tile_apply CTA (1 .. APPLY_TILES)
 };
 
 struct TileCounters {
@@ -667,7 +668,7 @@ __device__ __forceinline__ void apply_part_word(N (&px)[32], uint32_t mw, N v, N
     }
 }
 
-constexpr int APPLY_TILES = 8;  // consecutive tiles of one tile row handled by one CTA
+constexpr int APPLY_TILES = 8;  // most consecutive tiles of one tile row handled by one CTA (TileParams::apply_tiles)
 constexpr int AP_STAGES = 3;               // batches of mask blocks in flight per CTA
 constexpr uint32_t AP_STAGE_WORDS = 2048;  // mask words of one batch (a block holds at most 64 x 4 = 256)
 constexpr uint32_t AP_STAGE_BLOCKS = 32;   // blocks of one batch (one producer lane each)
@@ -736,8 +737,8 @@ __device__ __forceinline__ void tile_apply_body(const KParams& P, const TilePara
     const N bg = value_from_bits<N>(bg_bits);
     ApplyShared& sh = *reinterpret_cast<ApplyShared*>(smem_raw + apply_flush_bytes<N, TILE_R>());
 
-    // grid = (groups of APPLY_TILES tile columns, tile rows x bands), or 1-D when that does not fit the grid limits
-    const uint32_t groups = (T.n_tc + APPLY_TILES - 1) / APPLY_TILES;
+    // grid = (groups of apply_tiles tile columns, tile rows x bands), or 1-D when that does not fit the grid limits
+    const uint32_t groups = (T.n_tc + T.apply_tiles - 1) / T.apply_tiles;
     uint32_t tgrp, trow, band;
     if (gridDim.y > 1 || T.n_tr * P.n_bands == 1) {
         tgrp = blockIdx.x;
@@ -753,7 +754,7 @@ __device__ __forceinline__ void tile_apply_body(const KParams& P, const TilePara
         trow = (tt / groups) % T.n_tr;
         band = tt / (groups * T.n_tr);
     }
-    const uint32_t tcol0 = tgrp * APPLY_TILES, n_here = min((uint32_t)APPLY_TILES, T.n_tc - tcol0);
+    const uint32_t tcol0 = tgrp * T.apply_tiles, n_here = min(T.apply_tiles, T.n_tc - tcol0);
     const uint32_t t0 = (band * T.n_tr + trow) * T.n_tc + tcol0;
     const uint32_t tile_row0 = P.win_r0 + trow * TILE_R;
     const uint32_t n_active = min(NW, (P.win_r1 - tile_row0 + 7u) / 8u);  // consumer warps that own raster rows
