@@ -222,6 +222,11 @@ int rz_rasterize_sparse_multi(rz_geoms* g, const rz_context* ctx, const int32_t*
 /* Device plumbing */
 int rz_device_count(void);
 const char* rz_version(void);
+/* ABI self-description for bindings that mirror the structs by hand (ctypes, Rust #[repr(C)]): writes up to n of
+ * 16 entries - sizeof rz_raster_info, rz_raw_raster_info, rz_geom_soa, rz_context, rz_stats; offsetof rz_context
+ * .field .band_of_geom .background .row_begin .stream .flags; offsetof rz_stats .h2d_ms .h2d_bytes .kernel_launches
+ * .n_mask_words .wall_ms - and returns 16. */
+int rz_abi_layout(uint64_t* out, int n);
 
 #ifdef __cplusplus
 }

@@ -119,9 +119,18 @@ SYMBOLS = {
                                         C.c_void_p, C.c_void_p, C.POINTER(Stats)] + _ERR),
     "rz_device_count": (C.c_int, []),
     "rz_version": (C.c_char_p, []),
+    "rz_abi_layout": (C.c_int, [C.POINTER(C.c_uint64), C.c_int]),
 }
 
 _lib = None
+
+
+def abi_layout_of_bindings():
+    """The 16 numbers rz_abi_layout() reports, computed from the ctypes mirrors above."""
+    return [C.sizeof(RasterInfo), C.sizeof(RawRasterInfo), C.sizeof(GeomSoA), C.sizeof(Context), C.sizeof(Stats),
+            Context.field.offset, Context.band_of_geom.offset, Context.background.offset, Context.row_begin.offset,
+            Context.stream.offset, Context.flags.offset, Stats.h2d_ms.offset, Stats.h2d_bytes.offset,
+            Stats.kernel_launches.offset, Stats.n_mask_words.offset, Stats.wall_ms.offset]
 
 
 def lib() -> C.CDLL:
@@ -137,6 +146,10 @@ def lib() -> C.CDLL:
             fn = getattr(L, name)  # AttributeError if the library does not export it
             fn.restype = res
             fn.argtypes = args
+        theirs = (C.c_uint64 * 16)()
+        if L.rz_abi_layout(theirs, 16) != 16 or list(theirs) != abi_layout_of_bindings():
+            raise ImportError(f"{SO_PATH}: struct layouts differ from rusterize_b200/_lib.py "
+                              f"(library {list(theirs)}, bindings {abi_layout_of_bindings()}); rebuild the library")
         _lib = L
     return _lib
 

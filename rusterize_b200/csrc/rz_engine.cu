@@ -8,6 +8,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <cstddef>
 #include <cstring>
 #include <condition_variable>
 #include <functional>
@@ -2525,6 +2526,18 @@ int rz_device_count(void) {
     return n;
 }
 
-const char* rz_version(void) { return "rz_b200 0.1.0 (sm_100a)"; }
+const char* rz_version(void) { return "rz_b200 0.2.0 (sm_100a)"; }
+
+// sizes and selected field offsets of the header's structs, for bindings that mirror them by hand
+int rz_abi_layout(uint64_t* out, int n) {
+    const uint64_t v[16] = {
+        sizeof(rz_raster_info), sizeof(rz_raw_raster_info), sizeof(rz_geom_soa), sizeof(rz_context), sizeof(rz_stats),
+        offsetof(rz_context, field), offsetof(rz_context, band_of_geom), offsetof(rz_context, background),
+        offsetof(rz_context, row_begin), offsetof(rz_context, stream), offsetof(rz_context, flags),
+        offsetof(rz_stats, h2d_ms), offsetof(rz_stats, h2d_bytes), offsetof(rz_stats, kernel_launches),
+        offsetof(rz_stats, n_mask_words), offsetof(rz_stats, wall_ms)};
+    for (int i = 0; i < n && i < 16; i++) out[i] = v[i];
+    return 16;
+}
 
 }  // extern "C"
