@@ -482,11 +482,18 @@ def run_dense(env, name, w, headline):
         dt = np.dtype(dtype)
         tdt = getattr(torch, dt.name)
         d_out = torch.empty((n_b, r1 - r0, cols), dtype=tdt, device="cuda")
+        # device-resident arm: every input of the call already lives in HBM - geometry (uploaded above), field values
+        # and band ids (RZ_FLAG_INPUTS_ON_DEVICE) - and the raster stays there
+        f_np = np.ascontiguousarray(np.asarray(w["field"]).astype(dt)) if np.ndim(w["field"]) else np.array([w["field"]], dt)
+        d_field = torch.from_numpy(f_np.view(np.uint8)).cuda()
+        d_band = None if band is None else torch.from_numpy(np.ascontiguousarray(band, np.int32)).cuda()
+        torch.cuda.synchronize()
+        inputs_dev = dict(field=d_field.data_ptr(), scalar=np.ndim(w["field"]) == 0, band=None if d_band is None else d_band.data_ptr())
 
         def step(flags=0):
-            return core.rasterize_dense(geoms, ri, fun, dtype, w["field"], None, band, n_b, bg, device=local,
+            return core.rasterize_dense(geoms, ri, fun, dtype, 0, None, None, n_b, bg, device=local,
                                         rows=(r0, r1), out=d_out.data_ptr(), stream=env.stream, flags=flags | eng_flag,
-                                        tile_bytes=args.tile_bytes)[1]
+                                        tile_bytes=args.tile_bytes, inputs_dev=inputs_dev)[1]
 
         for _ in range(warmup):
             step()

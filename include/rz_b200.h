@@ -159,6 +159,9 @@ typedef struct rz_context {
 #define RZ_FLAG_SYNC_STAGES 4u     /* record per-stage CUDA-event timings into rz_stats */
 #define RZ_FLAG_NO_TILE_ENGINE 8u      /* always use the crossing-record pipeline */
 #define RZ_FLAG_FORCE_TILE_ENGINE 16u  /* use the tile-binned engine whenever the job is polygon-only */
+#define RZ_FLAG_INPUTS_ON_DEVICE 128u   /* field, field_valid and band_of_geom are DEVICE pointers (same lengths and meaning):
+                                          nothing is copied per call; band values are then not range-checked. Single-device
+                                          calls only */
 #define RZ_FLAG_STREAMED_H2D 64u        /* accepted and ignored (round 1 experiment: pulling the polygon pool from mapped
                                           host memory under the raster's D2H did not pay) */
 

@@ -226,9 +226,22 @@ def _device_array(devices):
     return (C.c_int32 * len(devs))(*devs), len(devs)
 
 
+def _use_device_inputs(ctx, inputs_dev, n_geoms):
+    """RZ_FLAG_INPUTS_ON_DEVICE: `inputs_dev` = dict(field=<device pointer to n_geoms values of the dtype, or to one
+    value with scalar=True>, valid=<device pointer or None>, band=<device pointer or None>)."""
+    ctx.field = int(inputs_dev["field"])
+    ctx.field_is_scalar = int(bool(inputs_dev.get("scalar", False)))
+    ctx.field_len = 0 if ctx.field_is_scalar else n_geoms
+    ctx.field_valid = inputs_dev.get("valid") or None
+    band = inputs_dev.get("band") or None
+    ctx.band_of_geom = band
+    ctx.by_len = n_geoms if band else 0
+    ctx.flags |= _lib.FLAG_INPUTS_ON_DEVICE
+
+
 def rasterize_dense(geoms: Geoms, ri: RasterInfo, fun="last", dtype="float64", field=1, field_valid=None,
                     band_of_geom=None, n_bands=1, background=0, all_touched=False, out=None, device=0, rows=None,
-                    stream=None, flags=0, tile_bytes=0, devices=None):
+                    stream=None, flags=0, tile_bytes=0, devices=None, inputs_dev=None):
     """DenseArray::build (rust/src/rasterize.rs:71-116) on the GPU.
 
     `out`: None (a new numpy array is returned), a C-contiguous numpy array to fill, or an int
@@ -238,7 +251,9 @@ def rasterize_dense(geoms: Geoms, ri: RasterInfo, fun="last", dtype="float64", f
     Returns (array_or_None, stats dict).  Shape [n_bands, rows, ncols]."""
     ctx, dt, keep = _context(geoms, ri, fun, dtype, field, field_valid, band_of_geom, n_bands, background,
                              all_touched, device, rows, stream, flags, tile_bytes)
-    nb = n_bands if band_of_geom is not None else 1
+    nb = n_bands if (band_of_geom is not None or (inputs_dev and inputs_dev.get("band"))) else 1
+    if inputs_dev:
+        _use_device_inputs(ctx, inputs_dev, len(geoms))
     nrows = ri.nrows if rows is None else rows[1] - rows[0]
     arr = None
     if isinstance(out, (int, np.integer)):

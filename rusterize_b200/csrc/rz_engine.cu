@@ -28,6 +28,7 @@
 #include "rz_host.hpp"
 #include "rz_kernels.cuh"
 #include "rz_sparse.cuh"
+#include "rz_burn.cuh"
 #include "rz_tiles.cuh"
 #include "rz_dispatch.hpp"
 
@@ -218,9 +219,14 @@ static const bool g_pinned_hooks_set = []() {
 
 struct DeviceGeoms {
     int dev = 0;
+    // every array below lives in ONE device allocation (a cudaMalloc per array made a fresh geometry set pay ~20
+    // driver calls, which serialise across the host threads of a multi-device call)
+    void* block = nullptr;
     double* x[3] = {nullptr, nullptr, nullptr};
     double* y[3] = {nullptr, nullptr, nullptr};
     uint32_t* tag[3] = {nullptr, nullptr, nullptr};
+    uint32_t* seq_end[3] = {nullptr, nullptr, nullptr};
+    uint8_t* seq_closed[3] = {nullptr, nullptr, nullptr};
     uint8_t* part_kind = nullptr;
     uint32_t* part_geom = nullptr;
     double* part_xlo = nullptr;
@@ -234,19 +240,7 @@ struct DeviceGeoms {
         int prev = -1;
         if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
         cudaSetDevice(dev);
-        for (int k = 0; k < 3; k++) {
-            cudaFree(x[k]);
-            cudaFree(y[k]);
-            cudaFree(tag[k]);
-        }
-        cudaFree(part_kind);
-        cudaFree(part_geom);
-        cudaFree(part_xlo);
-        cudaFree(part_xhi);
-        cudaFree(part_ylo);
-        cudaFree(part_yhi);
-        cudaFree(part_vbeg);
-        cudaFree(part_vend);
+        cudaFree(block);
         if (prev >= 0) cudaSetDevice(prev);
         (void)cudaGetLastError();
     }
@@ -332,15 +326,13 @@ static void copy_h2d_split(void* dst, const void* src, size_t bytes, const std::
     }
 }
 
-// (re)upload a host vector; the device buffer is allocated on first use and reused afterwards (a
-// geometry set is immutable, so a forced re-upload only pays the copy)
+// (re)upload a host vector into its place inside the geometry set's device block (a geometry set is immutable, so a
+// forced re-upload only pays the copy)
 template <typename T, typename A>
-static void upload_vec(T** dst, const std::vector<T, A>& v, cudaStream_t s, size_t& bytes,
+static void upload_vec(T* dst, const std::vector<T, A>& v, cudaStream_t s, size_t& bytes,
                        const std::vector<std::pair<void*, size_t>>& pinned) {
     if (v.empty()) return;
-    // one spare element so kernels may read index i+1 of the last vertex unconditionally
-    if (*dst == nullptr) CUDA_TRY(cudaMalloc((void**)dst, (v.size() + 1) * sizeof(T)));
-    copy_h2d_split(*dst, v.data(), v.size() * sizeof(T), pinned, s);
+    copy_h2d_split(dst, v.data(), v.size() * sizeof(T), pinned, s);
     bytes += v.size() * sizeof(T);
 }
 
@@ -352,7 +344,9 @@ static void upload_vec(T** dst, const std::vector<T, A>& v, cudaStream_t s, size
 template <typename T, typename A>
 static bool pin_vec(rz_geoms* g, std::vector<T, A>& v, bool verbose) {  // true: fully page-locked
     const size_t bytes = v.size() * sizeof(T);
-    if (bytes < (1u << 16)) return false;
+    // small arrays go as pageable copies: a cudaHostRegister call costs more than staging a few megabytes, and the
+    // calls of the host threads of a multi-device job serialise inside the driver
+    if (bytes < ((size_t)4 << 20)) return false;
     HostBlock blk;
     if (g_host_pool.leased(v.data(), &blk) && blk.pinned) {  // built into a recycled page-locked block
         g->pinned_ranges.emplace_back(blk.p, blk.cap);
@@ -435,45 +429,73 @@ static DeviceGeoms* geoms_on_device(rz_geoms* g, DeviceCtx& c, cudaStream_t s, b
         d = fresh.get();
     }
     d->dev = c.dev;
+    const uint32_t n_parts = (uint32_t)g->part_kind.size();
+    if (!d->block) {  // carve every array out of one allocation (256-byte aligned; one spare element per array so
+                      // that kernels may read index i+1 of the last vertex unconditionally)
+        size_t total = 0;
+        auto reserve = [&](size_t count, size_t elem) {
+            const size_t at = total;
+            total += ((count + 1) * elem + 255) & ~(size_t)255;
+            return at;
+        };
+        size_t o_x[3], o_y[3], o_tag[3], o_se[3], o_sc[3];
+        for (int k = 0; k < 3; k++) {
+            o_x[k] = reserve(g->pool[k].size(), 8);
+            o_y[k] = reserve(g->pool[k].size(), 8);
+            o_tag[k] = reserve(g->pool[k].size(), 4);
+            o_se[k] = reserve(g->pool[k].seq_end.size(), 4);
+            o_sc[k] = reserve(g->pool[k].seq_closed.size(), 1);
+        }
+        const size_t o_kind = reserve(n_parts, 1), o_geom = reserve(n_parts, 4), o_xlo = reserve(n_parts, 8),
+                     o_xhi = reserve(n_parts, 8), o_ylo = reserve(n_parts, 8), o_yhi = reserve(n_parts, 8),
+                     o_vb = reserve(n_parts, 4), o_ve = reserve(n_parts, 4);
+        CUDA_TRY(cudaMalloc(&d->block, total));
+        char* base = (char*)d->block;
+        for (int k = 0; k < 3; k++) {
+            d->x[k] = (double*)(base + o_x[k]);
+            d->y[k] = (double*)(base + o_y[k]);
+            d->tag[k] = (uint32_t*)(base + o_tag[k]);
+            d->seq_end[k] = (uint32_t*)(base + o_se[k]);
+            d->seq_closed[k] = (uint8_t*)(base + o_sc[k]);
+        }
+        d->part_kind = (uint8_t*)(base + o_kind);
+        d->part_geom = (uint32_t*)(base + o_geom);
+        d->part_xlo = (double*)(base + o_xlo);
+        d->part_xhi = (double*)(base + o_xhi);
+        d->part_ylo = (double*)(base + o_ylo);
+        d->part_yhi = (double*)(base + o_yhi);
+        d->part_vbeg = (uint32_t*)(base + o_vb);
+        d->part_vend = (uint32_t*)(base + o_ve);
+    }
     size_t bytes = 0;
     for (int k = 0; k < 3; k++) {
-        upload_vec(&d->x[k], g->pool[k].x, s, bytes, g->pinned_ranges);
-        upload_vec(&d->y[k], g->pool[k].y, s, bytes, g->pinned_ranges);
-        if (g->pool[k].size() && !d->tag[k]) CUDA_TRY(cudaMalloc((void**)&d->tag[k], (g->pool[k].size() + 1) * 4));
+        upload_vec(d->x[k], g->pool[k].x, s, bytes, g->pinned_ranges);
+        upload_vec(d->y[k], g->pool[k].y, s, bytes, g->pinned_ranges);
     }
-    upload_vec(&d->part_kind, g->part_kind, s, bytes, g->pinned_ranges);
+    upload_vec(d->part_kind, g->part_kind, s, bytes, g->pinned_ranges);
     std::vector<uint32_t> pg(g->part_geom.begin(), g->part_geom.end());
-    upload_vec(&d->part_geom, pg, s, bytes, g->pinned_ranges);
-    upload_vec(&d->part_xlo, g->part_xlo, s, bytes, g->pinned_ranges);
-    upload_vec(&d->part_xhi, g->part_xhi, s, bytes, g->pinned_ranges);
-    upload_vec(&d->part_ylo, g->part_ylo, s, bytes, g->pinned_ranges);
-    upload_vec(&d->part_yhi, g->part_yhi, s, bytes, g->pinned_ranges);
-    upload_vec(&d->part_vbeg, g->part_vbeg, s, bytes, g->pinned_ranges);
-    upload_vec(&d->part_vend, g->part_vend, s, bytes, g->pinned_ranges);
+    upload_vec(d->part_geom, pg, s, bytes, g->pinned_ranges);
+    upload_vec(d->part_xlo, g->part_xlo, s, bytes, g->pinned_ranges);
+    upload_vec(d->part_xhi, g->part_xhi, s, bytes, g->pinned_ranges);
+    upload_vec(d->part_ylo, g->part_ylo, s, bytes, g->pinned_ranges);
+    upload_vec(d->part_yhi, g->part_yhi, s, bytes, g->pinned_ranges);
+    upload_vec(d->part_vbeg, g->part_vbeg, s, bytes, g->pinned_ranges);
+    upload_vec(d->part_vend, g->part_vend, s, bytes, g->pinned_ranges);
     // tag[] is not sent (4 bytes per vertex, a fifth of the upload): it is rebuilt from the parts table and the
     // sequence lists - tag = part id | TAG_SEQ_END on a sequence's last vertex | TAG_CLOSED on closed line strings
-    std::vector<void*> scratch;
-    if (const uint32_t n_parts = (uint32_t)g->part_kind.size()) {
+    if (n_parts) {
         for (int k = 0; k < 3; k++) {
             if (!g->pool[k].size()) continue;
             tag_parts_kernel<<<(n_parts + 7) / 8, 256, 0, s>>>(n_parts, (uint8_t)k, d->part_kind, d->part_vbeg, d->part_vend,
                                                              d->tag[k]);
             const uint32_t n_seq = (uint32_t)g->pool[k].seq_end.size();
             if (!n_seq) continue;
-            uint32_t* d_end = nullptr;
-            uint8_t* d_closed = nullptr;
-            CUDA_TRY(cudaMalloc((void**)&d_end, (size_t)n_seq * 4));
-            scratch.push_back(d_end);
-            CUDA_TRY(cudaMalloc((void**)&d_closed, n_seq));
-            scratch.push_back(d_closed);
-            CUDA_TRY(cudaMemcpyAsync(d_end, g->pool[k].seq_end.data(), (size_t)n_seq * 4, cudaMemcpyHostToDevice, s));
-            CUDA_TRY(cudaMemcpyAsync(d_closed, g->pool[k].seq_closed.data(), n_seq, cudaMemcpyHostToDevice, s));
-            bytes += (size_t)n_seq * 5;
-            tag_seqs_kernel<<<(n_seq + 255) / 256, 256, 0, s>>>(n_seq, d_end, d_closed, d->tag[k]);
+            upload_vec(d->seq_end[k], g->pool[k].seq_end, s, bytes, g->pinned_ranges);
+            upload_vec(d->seq_closed[k], g->pool[k].seq_closed, s, bytes, g->pinned_ranges);
+            tag_seqs_kernel<<<(n_seq + 255) / 256, 256, 0, s>>>(n_seq, d->seq_end[k], d->seq_closed[k], d->tag[k]);
         }
     }
-    CUDA_TRY(cudaStreamSynchronize(s));  // `pg`, the sequence lists on the device are temporaries
-    for (void* q : scratch) cudaFree(q);
+    CUDA_TRY(cudaStreamSynchronize(s));  // `pg` is a temporary
     d->bytes = bytes;
     if (h2d_bytes) *h2d_bytes += bytes;
     if (fresh) g->dev[c.dev] = fresh.release();
@@ -591,12 +613,50 @@ static void validate_lengths(const rz_geoms* g, const rz_context* ctx) {
         throw Error{RZ_VALUE_ERROR, "Geometry and field lengths must match"};
     if (ctx->band_of_geom && ctx->by_len != g->n_geoms)
         throw Error{RZ_VALUE_ERROR, "Geometry and by lengths must match"};
-    if (ctx->band_of_geom) {  // negative = skipped; anything else must name a band
+    if (ctx->band_of_geom && !(ctx->flags & RZ_FLAG_INPUTS_ON_DEVICE)) {  // negative = skipped; anything else must name a band
         const int32_t nb = std::max(ctx->n_bands, 0);
         bool bad = false;
         for (uint64_t i = 0; i < g->n_geoms; i++) bad |= ctx->band_of_geom[i] >= nb;
         if (bad) throw Error{RZ_VALUE_ERROR, "band_of_geom holds a band index >= n_bands"};
     }
+}
+
+// field / field_valid / band_of_geom of a call on the device: copied from the caller's host arrays, or used where they
+// lie with RZ_FLAG_INPUTS_ON_DEVICE (a steady-state call then moves nothing over PCIe: at 8 GPUs the 4 MB field array
+// of a 1M-geometry job, staged through pageable memory on every call, cost a quarter of the whole step)
+struct CallInputs {
+    const uint8_t* field = nullptr;
+    const uint8_t* valid = nullptr;
+    const int32_t* band = nullptr;
+    size_t h2d = 0;
+};
+static CallInputs inputs_on_device(DeviceCtx& c, cudaStream_t s, const rz_geoms* g, const rz_context* ctx, size_t isz) {
+    CallInputs in;
+    const size_t n_field = ctx->field_is_scalar ? 1 : (size_t)g->n_geoms;
+    if (ctx->flags & RZ_FLAG_INPUTS_ON_DEVICE) {
+        in.field = (const uint8_t*)ctx->field;
+        in.valid = g->n_geoms ? ctx->field_valid : nullptr;
+        in.band = g->n_geoms ? ctx->band_of_geom : nullptr;
+        if (!in.field) throw Error{RZ_VALUE_ERROR, "RZ_FLAG_INPUTS_ON_DEVICE needs a device `field` pointer"};
+        return in;
+    }
+    c.field.ensure(std::max<size_t>(n_field * isz, 8));
+    if (n_field) CUDA_TRY(cudaMemcpyAsync(c.field.p, ctx->field, n_field * isz, cudaMemcpyHostToDevice, s));
+    in.field = c.field.as<uint8_t>();
+    in.h2d += n_field * isz;
+    if (ctx->field_valid && g->n_geoms) {
+        c.valid.ensure(g->n_geoms);
+        CUDA_TRY(cudaMemcpyAsync(c.valid.p, ctx->field_valid, g->n_geoms, cudaMemcpyHostToDevice, s));
+        in.valid = c.valid.as<uint8_t>();
+        in.h2d += g->n_geoms;
+    }
+    if (ctx->band_of_geom && g->n_geoms) {
+        c.band.ensure(g->n_geoms * 4);
+        CUDA_TRY(cudaMemcpyAsync(c.band.p, ctx->band_of_geom, g->n_geoms * 4, cudaMemcpyHostToDevice, s));
+        in.band = c.band.as<int32_t>();
+        in.h2d += g->n_geoms * 4;
+    }
+    return in;
 }
 
 // Where a row shard lands inside a larger host array (multi-device calls): band b of the shard starts at row
@@ -644,24 +704,10 @@ static void rasterize_dense(rz_geoms* g, const rz_context* ctx, void* out, rz_st
     const uint64_t MAX_WINDOW_OUT_BYTES = max_window_out_bytes();
     DeviceGeoms* dg = geoms_on_device(g, c, s, (ctx->flags & RZ_FLAG_FORCE_H2D) != 0, &h2d);
     const uint32_t n_parts = (uint32_t)g->part_kind.size();
-    const size_t n_field = ctx->field_is_scalar ? 1 : (size_t)g->n_geoms;
-    c.field.ensure(std::max<size_t>(n_field * isz, 8));
-    if (n_field) CUDA_TRY(cudaMemcpyAsync(c.field.p, ctx->field, n_field * isz, cudaMemcpyHostToDevice, s));
-    h2d += n_field * isz;
-    const uint8_t* d_valid = nullptr;
-    if (ctx->field_valid && g->n_geoms) {
-        c.valid.ensure(g->n_geoms);
-        CUDA_TRY(cudaMemcpyAsync(c.valid.p, ctx->field_valid, g->n_geoms, cudaMemcpyHostToDevice, s));
-        d_valid = c.valid.as<uint8_t>();
-        h2d += g->n_geoms;
-    }
-    const int32_t* d_band = nullptr;
-    if (ctx->band_of_geom && g->n_geoms) {
-        c.band.ensure(g->n_geoms * 4);
-        CUDA_TRY(cudaMemcpyAsync(c.band.p, ctx->band_of_geom, g->n_geoms * 4, cudaMemcpyHostToDevice, s));
-        d_band = c.band.as<int32_t>();
-        h2d += g->n_geoms * 4;
-    }
+    const CallInputs in = inputs_on_device(c, s, g, ctx, isz);
+    h2d += in.h2d;
+    const uint8_t* d_valid = in.valid;
+    const int32_t* d_band = in.band;
     CUDA_TRY(cudaEventRecord(c.ev[EV_H2D], s));
 
     // ---- tiling and key layout -----------------------------------------------------------------
@@ -719,7 +765,7 @@ static void rasterize_dense(rz_geoms* g, const rz_context* ctx, void* out, rz_st
     c.counters.ensure(sizeof(Counters));
     if (n_parts)
         part_prepare_kernel<<<(n_parts + 255) / 256, 256, 0, s>>>(
-            P, dg->part_kind, dg->part_geom, dg->part_xlo, dg->part_xhi, c.field.as<uint8_t>(), (uint32_t)isz,
+            P, dg->part_kind, dg->part_geom, dg->part_xlo, dg->part_xhi, in.field, (uint32_t)isz,
             ctx->field_is_scalar, d_valid, d_band, c.part_info.as<PartInfo>());
     const PartInfo* d_info = c.part_info.as<PartInfo>();
     Counters* d_ctr = c.counters.as<Counters>();
@@ -847,7 +893,13 @@ static void rasterize_dense(rz_geoms* g, const rz_context* ctx, void* out, rz_st
 
     // The tile-binned engine takes polygon-only jobs without all_touched whose coordinates are all finite (its
     // odd-crossing rule relies on that; see tile_mask_kernel).
-    const bool tile_candidate = nv_line == 0 && nv_pt == 0 && !touched && n_parts && !g->nonfinite &&
+    // Lines and points ride along when the pixel function is order-free (rz_burn.cuh): `any`, or `count` / `sum` on
+    // an integer dtype with background 0, square pixels: they are applied to the finished tiles by atomics.
+    const bool int_dtype = ctx->dtype != RZ_F32 && ctx->dtype != RZ_F64;
+    const bool order_free = !touched && ri.xres == ri.yres &&
+                            (ctx->pixel_fn == RZ_ANY ||
+                             ((ctx->pixel_fn == RZ_COUNT || ctx->pixel_fn == RZ_SUM) && int_dtype && bg_bits == 0));
+    const bool tile_candidate = (order_free || (nv_line == 0 && nv_pt == 0)) && !touched && n_parts && !g->nonfinite &&
                                 !(ctx->flags & RZ_FLAG_NO_TILE_ENGINE);
     bool tile_stats_pending = false;
 
@@ -1030,6 +1082,61 @@ static void rasterize_dense(rz_geoms* g, const rz_context* ctx, void* out, rz_st
                     CUDA_TRY(cudaGetLastError());
                     if (timed) CUDA_TRY(cudaEventRecord(c.ev[EV_B], s));
                     lap(fill_ms, EV_A, EV_B);
+                    if (nv_line || nv_pt) {  // order-free job: line / point pixels onto the finished tiles
+                        if (timed) CUDA_TRY(cudaEventRecord(c.ev[EV_A], s));
+                        BurnTarget B;
+                        B.out = d_out;
+                        B.out_rows = T.out_rows;
+                        B.win_row_off = T.win_row_off;
+                        B.use_part_value = ctx->pixel_fn == RZ_SUM;
+                        B.one = 1ull;
+                        if (ctx->dtype == RZ_F32) B.one = 0x3f800000ull;
+                        if (ctx->dtype == RZ_F64) B.one = 0x3ff0000000000000ull;
+                        const bool add = ctx->pixel_fn != RZ_ANY;
+                        CUDA_TRY(cudaMemsetAsync(d_ctr, 0, sizeof(Counters), s));
+                        auto burn = [&](auto sz, auto adding) {
+                            constexpr int SZ = decltype(sz)::value;
+                            constexpr bool ADD = decltype(adding)::value;
+                            if (nv_line) {
+                                CUDA_TRY(cudaMemsetAsync(c.last_kept.p, 0, (size_t)n_parts * 4, s));
+                                line_last_kept_kernel<<<(nv_line + 255) / 256, 256, 0, s>>>(
+                                    P, dg->x[1], dg->y[1], dg->tag[1], nv_line, d_info, c.last_kept.as<uint32_t>(), d_ctr);
+                                line_burn_kernel<SZ, ADD><<<(nv_line + 255) / 256, 256, 0, s>>>(P, dg->x[1], dg->y[1], dg->tag[1],
+                                                                                              nv_line, d_info, d_ctr, B);
+                                line_final_burn_kernel<SZ, ADD><<<(n_parts + 255) / 256, 256, 0, s>>>(
+                                    P, dg->x[1], dg->y[1], dg->tag[1], dg->part_kind, d_info, c.last_kept.as<uint32_t>(), B);
+                                launches += 3;
+                            }
+                            if (nv_pt) {
+                                point_burn_kernel<SZ, ADD><<<(nv_pt + 255) / 256, 256, 0, s>>>(P, dg->x[2], dg->y[2], dg->tag[2],
+                                                                                             nv_pt, d_info, B);
+                                launches++;
+                            }
+                        };
+                        auto by_size = [&](auto adding) {
+                            switch (isz) {
+                                case 1: burn(std::integral_constant<int, 1>{}, adding); break;
+                                case 2: burn(std::integral_constant<int, 2>{}, adding); break;
+                                case 4: burn(std::integral_constant<int, 4>{}, adding); break;
+                                default: burn(std::integral_constant<int, 8>{}, adding); break;
+                            }
+                        };
+                        if (add) by_size(std::true_type{});
+                        else by_size(std::false_type{});
+                        CUDA_TRY(cudaGetLastError());
+                        if (timed) CUDA_TRY(cudaEventRecord(c.ev[EV_B], s));
+                        lap(index_ms, EV_A, EV_B);  // reported in the "index" stage slot: line / point burn
+                        if (nv_line) {  // a segment beyond the supported domain was skipped: report it like the record path
+                            readback_kernel<<<1, 32, 0, s>>>((const unsigned long long*)d_ctr,
+                                                             (volatile unsigned long long*)c.h_counters,
+                                                             (uint32_t)(sizeof(Counters) / 8));
+                            CUDA_TRY(cudaStreamSynchronize(s));
+                            S.host_syncs++;
+                            if (c.h_counters->bad_line)
+                                throw Error{RZ_RUNTIME_ERROR,
+                                            "A line segment extends more than 2^29 pixels from the raster origin; unsupported."};
+                        }
+                    }
                     S.engine = 1;
                     S.n_records += plan.pairs;
                     S.n_mask_words += plan.words;
@@ -1384,22 +1491,10 @@ static void rasterize_sparse(rz_geoms* g, const rz_context* ctx, rz_sparse* out,
     size_t h2d = 0;
     DeviceGeoms* dg = geoms_on_device(g, c, s, (ctx->flags & RZ_FLAG_FORCE_H2D) != 0, &h2d);
     const uint32_t n_parts = (uint32_t)g->part_kind.size();
-    const size_t n_field = ctx->field_is_scalar ? 1 : (size_t)g->n_geoms;
-    c.field.ensure(std::max<size_t>(n_field * isz, 8));
-    if (n_field) CUDA_TRY(cudaMemcpyAsync(c.field.p, ctx->field, n_field * isz, cudaMemcpyHostToDevice, s));
-    const uint8_t* d_valid = nullptr;
-    if (ctx->field_valid && g->n_geoms) {
-        c.valid.ensure(g->n_geoms);
-        CUDA_TRY(cudaMemcpyAsync(c.valid.p, ctx->field_valid, g->n_geoms, cudaMemcpyHostToDevice, s));
-        d_valid = c.valid.as<uint8_t>();
-    }
-    const int32_t* d_band = nullptr;
-    if (ctx->band_of_geom && g->n_geoms) {
-        c.band.ensure(g->n_geoms * 4);
-        CUDA_TRY(cudaMemcpyAsync(c.band.p, ctx->band_of_geom, g->n_geoms * 4, cudaMemcpyHostToDevice, s));
-        d_band = c.band.as<int32_t>();
-    }
-    S.h2d_bytes = h2d + n_field * isz;
+    const CallInputs in = inputs_on_device(c, s, g, ctx, isz);
+    const uint8_t* d_valid = in.valid;
+    const int32_t* d_band = in.band;
+    S.h2d_bytes = h2d + in.h2d;
 
     KParams P;
     std::memset(&P, 0, sizeof P);
@@ -1438,7 +1533,7 @@ static void rasterize_sparse(rz_geoms* g, const rz_context* ctx, rz_sparse* out,
     c.last_kept.ensure((size_t)n_parts * 4);
     c.counters.ensure(sizeof(Counters));
     part_prepare_kernel<<<(n_parts + 255) / 256, 256, 0, s>>>(P, dg->part_kind, dg->part_geom, dg->part_xlo,
-                                                              dg->part_xhi, c.field.as<uint8_t>(), (uint32_t)isz,
+                                                              dg->part_xhi, in.field, (uint32_t)isz,
                                                               ctx->field_is_scalar, d_valid, d_band,
                                                               c.part_info.as<PartInfo>());
     launches++;
@@ -1975,8 +2070,8 @@ static void rasterize_dense_multi(rz_geoms* g, const rz_context* ctx, const int3
     const WallClock call_clock;
     // (a repeated device only serialises its shards: single-GPU machines can exercise the sharding that way)
     check_devices(devices, n_devices, std::getenv("RZ_ALLOW_REPEATED_DEVICES") != nullptr);
-    if (ctx->flags & RZ_FLAG_OUT_ON_DEVICE)
-        throw Error{RZ_VALUE_ERROR, "Multi-device calls write host memory; use rz_rasterize_dense per device for device output"};
+    if (ctx->flags & (RZ_FLAG_OUT_ON_DEVICE | RZ_FLAG_INPUTS_ON_DEVICE))
+        throw Error{RZ_VALUE_ERROR, "Multi-device calls take host inputs and write host memory; use rz_rasterize_dense per device for device buffers"};
     const rz_raster_info& ri = ctx->raster_info;
     validate_lengths(g, ctx);
     uint64_t r0 = ctx->row_begin, r1 = ctx->row_end;
@@ -2091,6 +2186,8 @@ static void rasterize_sparse_multi(rz_geoms* g, const rz_context* ctx, const int
                                    rz_sparse* out, rz_stats* st, rz_stats* per_device) {
     const WallClock call_clock;
     check_devices(devices, n_devices);
+    if (ctx->flags & RZ_FLAG_INPUTS_ON_DEVICE)
+        throw Error{RZ_VALUE_ERROR, "Multi-device calls take host inputs; use rz_rasterize_sparse per device for device buffers"};
     validate_lengths(g, ctx);
     const rz_raster_info& ri = ctx->raster_info;
     const size_t isz = dtype_size(ctx->dtype);

@@ -783,24 +783,24 @@ int flatten_soa(const rz_geom_soa* soa, rz_geoms* g, unsigned threads, std::stri
             return RZ_RUNTIME_ERROR;
         }
     {
-        PinnedScope pinned;  // the pools go straight into recycled page-locked blocks
+        PinnedScope pinned;  // the pools and the parts table go straight into recycled page-locked blocks
         for (int k = 0; k < 3; k++) {
             g->pool[k].x.resize(pool_tot[k]);
             g->pool[k].y.resize(pool_tot[k]);
         }
+        g->part_kind.resize(NP);
+        g->part_geom.resize(NP);
+        g->part_xlo.resize(NP);
+        g->part_xhi.resize(NP);
+        g->part_ylo.resize(NP);
+        g->part_yhi.resize(NP);
+        g->part_vbeg.resize(NP);
+        g->part_vend.resize(NP);
     }
     for (int k = 0; k < 2; k++) {
         g->pool[k].seq_end.resize(seq_tot[k]);
         g->pool[k].seq_closed.resize(seq_tot[k]);
     }
-    g->part_kind.resize(NP);
-    g->part_geom.resize(NP);
-    g->part_xlo.resize(NP);
-    g->part_xhi.resize(NP);
-    g->part_ylo.resize(NP);
-    g->part_yhi.resize(NP);
-    g->part_vbeg.resize(NP);
-    g->part_vend.resize(NP);
     // ---- pass B: copy + extents ---------------------------------------------------------------------
     const double inf = std::numeric_limits<double>::infinity();
     run([&](unsigned t) {
@@ -1007,19 +1007,19 @@ rz_geoms* subset_parts(const rz_geoms* src, const uint32_t* keep, size_t n_keep,
             g->pool[k].x.resize(pool_tot[k]);
             g->pool[k].y.resize(pool_tot[k]);
         }
+        g->part_kind.resize(n_keep);
+        g->part_geom.resize(n_keep);
+        g->part_xlo.resize(n_keep);
+        g->part_xhi.resize(n_keep);
+        g->part_ylo.resize(n_keep);
+        g->part_yhi.resize(n_keep);
+        g->part_vbeg.resize(n_keep);
+        g->part_vend.resize(n_keep);
     }
     for (int k = 0; k < 2; k++) {
         g->pool[k].seq_end.resize(seq_tot[k]);
         g->pool[k].seq_closed.resize(seq_tot[k]);
     }
-    g->part_kind.resize(n_keep);
-    g->part_geom.resize(n_keep);
-    g->part_xlo.resize(n_keep);
-    g->part_xhi.resize(n_keep);
-    g->part_ylo.resize(n_keep);
-    g->part_yhi.resize(n_keep);
-    g->part_vbeg.resize(n_keep);
-    g->part_vend.resize(n_keep);
     run([&](unsigned t) {
         Chunk& c = ch[t];
         uint64_t at[3] = {c.pool_off[0], c.pool_off[1], c.pool_off[2]}, sq[2] = {c.seq_off[0], c.seq_off[1]};

@@ -90,3 +90,35 @@ def test_replay_duplicate_pixels_in_order():
         got = core.sparse_build_array(ri, fun, 2, counts, rows, cols, data)
         exp = oracle.sparse_replay(ori, dict(counts=counts, rows=rows, cols=cols, data=data), fun, 2)
         assert np.array_equal(exp, got), fun
+
+
+def test_inputs_on_device_flag_equals_host_inputs():
+    """RZ_FLAG_INPUTS_ON_DEVICE: field values, validity bytes and band ids read from device memory give the same
+    raster as the host arrays (nothing is copied per call), dense through both engines."""
+    import torch
+
+    import synth
+
+    n = 1500
+    x, y, off = synth.star_polygons(51, n, 6, 30, 30.0, 640, 480)
+    g = core.Geoms.from_polygons(x, y, off)
+    ri = core.raster_info(None, shape=(480, 640), extent=(0, 0, 640, 480))
+    rng = np.random.default_rng(51)
+    vals = rng.integers(1, 99, n).astype(np.int32)
+    valid = (rng.random(n) < 0.9).astype(np.uint8)
+    band, names = core.group_keys([str(i % 4) for i in range(n)])
+    d_vals, d_valid, d_band = (torch.from_numpy(a).cuda() for a in (vals, valid, band))
+    torch.cuda.synchronize()
+    dev = dict(field=d_vals.data_ptr(), valid=d_valid.data_ptr(), band=d_band.data_ptr())
+    for flags in (0, _lib.FLAG_NO_TILE_ENGINE):
+        exp, _ = core.rasterize_dense(g, ri, "max", "int32", vals, valid, band, 4, 0, flags=flags)
+        got, st = core.rasterize_dense(g, ri, "max", "int32", 0, None, None, 4, 0, flags=flags, inputs_dev=dev)
+        assert np.array_equal(exp, got) and exp.shape == (4, 480, 640)
+        assert st["h2d_bytes"] == 0  # geometry cached, inputs resident
+    one = torch.tensor([2.5], dtype=torch.float32, device="cuda")
+    exp, _ = core.rasterize_dense(g, ri, "sum", "float32", 2.5, background=np.nan)
+    got, _ = core.rasterize_dense(g, ri, "sum", "float32", 0, background=np.nan, inputs_dev=dict(field=one.data_ptr(), scalar=True))
+    assert np.array_equal(exp, got, equal_nan=True)
+    with pytest.raises(ValueError, match="host inputs"):
+        core.rasterize_dense(g, ri, "sum", "float32", 0, background=np.nan, inputs_dev=dict(field=one.data_ptr(), scalar=True),
+                             devices=[0])
