@@ -8,7 +8,7 @@ import oracle
 import synth
 from cases import GEOMS, VALUES
 from oracle.wkt2wkb import wkt_to_wkb
-from rusterize_b200 import SparseArray, core, rusterize
+from rusterize_b200 import SparseArray, _lib, core, rusterize
 
 pytestmark = pytest.mark.gpu
 GOLDEN = __import__("os").path.join(__import__("os").path.dirname(__file__), "golden")
