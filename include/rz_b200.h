@@ -162,6 +162,9 @@ typedef struct rz_context {
 #define RZ_FLAG_INPUTS_ON_DEVICE 128u   /* field, field_valid and band_of_geom are DEVICE pointers (same lengths and meaning):
                                           nothing is copied per call; band values are then not range-checked. Single-device
                                           calls only */
+#define RZ_FLAG_OUT_ROW_COL_BAND 256u   /* dense `out` in R's array layout, (row, col, band) column-major = C-order
+                                          [band][col][row] (R/rusterize/src/rust/src/encoding/rarrays.rs:9-17), instead of
+                                          [band][row][col]: the R binding's permute done on the device */
 #define RZ_FLAG_STREAMED_H2D 64u        /* accepted and ignored (round 1 experiment: pulling the polygon pool from mapped
                                           host memory under the raster's D2H did not pay) */
 

@@ -25,6 +25,8 @@ pub const RZ_FLAG_FORCE_H2D: u32 = 2;
 pub const RZ_FLAG_SYNC_STAGES: u32 = 4;
 pub const RZ_FLAG_NO_TILE_ENGINE: u32 = 8;
 pub const RZ_FLAG_FORCE_TILE_ENGINE: u32 = 16;
+pub const RZ_FLAG_INPUTS_ON_DEVICE: u32 = 128;
+pub const RZ_FLAG_OUT_ROW_COL_BAND: u32 = 256; // R's (row, col, band) column-major layout
 
 /// `rz_dtype`, in the order of python/src/rusterize.rs:171-182.
 pub trait RzDtype: Copy {

@@ -16,6 +16,7 @@ FUNS = ["sum", "first", "last", "min", "max", "count", "any"]
 RZ_OK, RZ_VALUE_ERROR, RZ_RUNTIME_ERROR = 0, 1, 2
 FLAG_OUT_ON_DEVICE, FLAG_FORCE_H2D, FLAG_SYNC_STAGES = 1, 2, 4
 FLAG_NO_TILE_ENGINE, FLAG_FORCE_TILE_ENGINE, FLAG_STREAMED_H2D, FLAG_INPUTS_ON_DEVICE = 8, 16, 64, 128
+FLAG_OUT_ROW_COL_BAND = 256
 
 
 class RasterInfo(C.Structure):

@@ -260,7 +260,9 @@ def rasterize_dense(geoms: Geoms, ri: RasterInfo, fun="last", dtype="float64", f
         ctx.flags |= _lib.FLAG_OUT_ON_DEVICE
         out_ptr = int(out)
     else:
-        arr = np.empty((nb, nrows, ri.ncols), dt) if out is None else out
+        # RZ_FLAG_OUT_ROW_COL_BAND: C-order [band][col][row] == R's (row, col, band) column-major array
+        shape = (nb, ri.ncols, nrows) if (int(flags) & _lib.FLAG_OUT_ROW_COL_BAND) else (nb, nrows, ri.ncols)
+        arr = np.empty(shape, dt) if out is None else out
         if arr.dtype != dt or not arr.flags.c_contiguous or arr.size != nb * nrows * ri.ncols:
             raise ValueError("`out` must be a C-contiguous array of the output dtype and shape")
         out_ptr = arr.ctypes.data

@@ -265,7 +265,7 @@ struct DeviceCtx {
     bool ev_last_valid = false;
     cudaStream_t last_stream = nullptr;
     cudaEvent_t ev_filled[2], ev_copied[2], ev_d2h[2];
-    DevBuf win_out2;
+    DevBuf win_out2, win_t;
 };
 
 static std::mutex g_ctx_mu;
@@ -665,6 +665,35 @@ struct DenseExtra {
     uint64_t band_rows, row_off;
 };
 
+// R's array layout (R/rusterize/src/rust/src/encoding/rarrays.rs:9-17: `permuted_axes([0, 2, 1])` made contiguous,
+// i.e. (row, col, band) column-major): element (band, r, col) of a rendered window goes to
+// dst[(band * ncols + col) * band_rows + row_off + r].  32 x 32 tiles through shared memory, both sides coalesced.
+template <typename T>
+static __global__ void __launch_bounds__(256)
+window_to_rcb_kernel(const T* __restrict__ src, T* __restrict__ dst, uint32_t rows, uint32_t ncols, uint64_t band_rows,
+                     uint64_t row_off, uint64_t dst_band_cols /* columns per band in dst */) {
+    __shared__ T tile[32][33];
+    const uint32_t b = blockIdx.z, c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+    const uint32_t tx = threadIdx.x & 31u, ty = threadIdx.x >> 5;  // 32 x 8
+    const T* in = src + (size_t)b * rows * ncols;
+    for (uint32_t j = ty; j < 32; j += 8)
+        if (r0 + j < rows && c0 + tx < ncols) tile[j][tx] = in[(size_t)(r0 + j) * ncols + c0 + tx];
+    __syncthreads();
+    for (uint32_t j = ty; j < 32; j += 8)
+        if (c0 + j < ncols && r0 + tx < rows)
+            dst[((size_t)b * dst_band_cols + c0 + j) * band_rows + row_off + r0 + tx] = tile[tx][j];
+}
+static void launch_window_to_rcb(cudaStream_t s, size_t isz, const void* src, void* dst, uint32_t n_bands, uint32_t rows,
+                                 uint32_t ncols, uint64_t band_rows, uint64_t row_off) {
+    const dim3 grid((ncols + 31) / 32, (rows + 31) / 32, n_bands);
+    switch (isz) {
+        case 1: window_to_rcb_kernel<uint8_t><<<grid, 256, 0, s>>>((const uint8_t*)src, (uint8_t*)dst, rows, ncols, band_rows, row_off, ncols); break;
+        case 2: window_to_rcb_kernel<uint16_t><<<grid, 256, 0, s>>>((const uint16_t*)src, (uint16_t*)dst, rows, ncols, band_rows, row_off, ncols); break;
+        case 4: window_to_rcb_kernel<uint32_t><<<grid, 256, 0, s>>>((const uint32_t*)src, (uint32_t*)dst, rows, ncols, band_rows, row_off, ncols); break;
+        default: window_to_rcb_kernel<uint64_t><<<grid, 256, 0, s>>>((const uint64_t*)src, (uint64_t*)dst, rows, ncols, band_rows, row_off, ncols); break;
+    }
+}
+
 struct WallClock {
     std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
     float ms() const { return std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count(); }
@@ -687,6 +716,9 @@ static void rasterize_dense(rz_geoms* g, const rz_context* ctx, void* out, rz_st
     if (shard_r1 > ri.nrows || shard_r0 >= shard_r1) throw Error{RZ_VALUE_ERROR, "Invalid row shard"};
     const uint32_t shard_rows = shard_r1 - shard_r0;
     const bool out_dev = (ctx->flags & RZ_FLAG_OUT_ON_DEVICE) != 0;
+    // R's (row, col, band) layout: windows are always rendered into the staging buffers and transposed out of them
+    const bool rcb = (ctx->flags & RZ_FLAG_OUT_ROW_COL_BAND) != 0;
+    const bool direct = out_dev && !rcb;  // the kernels write the caller's device array themselves
 
     DeviceGuard guard;
     DeviceCtx& c = device_ctx(ctx->device);
@@ -777,7 +809,7 @@ static void rasterize_dense(rz_geoms* g, const rz_context* ctx, void* out, rz_st
         uint64_t tasks = (uint64_t)n_bands * rows * n_tiles;
         if (tasks >= (1ull << 31)) return false;
         if (bits_for(tasks) + P.task_shift > 64) return false;
-        if (!out_dev && (uint64_t)n_bands * rows * ri.ncols * isz > MAX_WINDOW_OUT_BYTES && rows > 1) return false;
+        if (!direct && (uint64_t)n_bands * rows * ri.ncols * isz > MAX_WINDOW_OUT_BYTES && rows > 1) return false;
         return true;
     };
     uint32_t win_rows = shard_rows;
@@ -824,6 +856,31 @@ static void rasterize_dense(rz_geoms* g, const rz_context* ctx, void* out, rz_st
     };
     auto stage_copy = [&](const Window& w, void* d_out) {  // window finished on `s`: copy it back asynchronously
         const uint32_t k = n_staged & 1, rows = w.r1 - w.r0;
+        if (rcb) {
+            const uint64_t band_rows = ex ? ex->band_rows : shard_rows, row_off = (ex ? ex->row_off : 0) + (w.r0 - shard_r0);
+            if (out_dev) {  // transposed straight into the caller's device array
+                launch_window_to_rcb(s, isz, d_out, out, n_bands, rows, (uint32_t)ri.ncols, band_rows, row_off);
+                CUDA_TRY(cudaEventRecord(c.ev_copied[k], s));
+                n_staged++;
+                return;
+            }
+            // host: transpose into a compact [band][col][rows] slab, then one strided copy per band
+            if (n_staged) CUDA_TRY(cudaStreamWaitEvent(s, c.ev_copied[(n_staged - 1) & 1], 0));  // the slab is reused
+            c.win_t.ensure((size_t)n_bands * rows * ri.ncols * isz);
+            launch_window_to_rcb(s, isz, d_out, c.win_t.p, n_bands, rows, (uint32_t)ri.ncols, rows, 0);
+            if (n_staged == 0) CUDA_TRY(cudaEventRecord(c.ev_first_fill, s));
+            CUDA_TRY(cudaEventRecord(c.ev_filled[k], s));
+            CUDA_TRY(cudaStreamWaitEvent(c.copy_stream, c.ev_filled[k], 0));
+            if (n_staged == 0) CUDA_TRY(cudaEventRecord(c.ev_d2h[0], c.copy_stream));
+            for (uint32_t b = 0; b < n_bands; b++)
+                CUDA_TRY(cudaMemcpy2DAsync((char*)out + ((size_t)b * ri.ncols * band_rows + row_off) * isz, band_rows * isz,
+                                           (const char*)c.win_t.p + (size_t)b * ri.ncols * rows * isz, (size_t)rows * isz,
+                                           (size_t)rows * isz, ri.ncols, cudaMemcpyDeviceToHost, c.copy_stream));
+            CUDA_TRY(cudaEventRecord(c.ev_copied[k], c.copy_stream));
+            S.d2h_bytes += (size_t)rows * ri.ncols * isz * n_bands;
+            n_staged++;
+            return;
+        }
         if (n_staged == 0) CUDA_TRY(cudaEventRecord(c.ev_first_fill, s));
         CUDA_TRY(cudaEventRecord(c.ev_filled[k], s));
         CUDA_TRY(cudaStreamWaitEvent(c.copy_stream, c.ev_filled[k], 0));
@@ -918,12 +975,13 @@ static void rasterize_dense(rz_geoms* g, const rz_context* ctx, void* out, rz_st
             T.n_tc = (uint32_t)((ri.ncols + TILE_C - 1) / TILE_C);
             T.n_tr = (rows + T.tile_r - 1) / T.tile_r;
             const uint64_t n_tiles64 = (uint64_t)n_bands * T.n_tr * T.n_tc;
-            // tile_apply: 8 consecutive tiles per CTA amortise the pipeline start-up; small rasters take fewer so that
-            // the grid still covers the machine several times over
+            // tile_apply: up to 32 consecutive tiles per CTA amortise the pipeline start-up; small rasters take fewer so
+            // that the grid still covers the machine several times over
             T.apply_tiles = APPLY_TILES;
             while (T.apply_tiles > 1 &&
                    (uint64_t)n_bands * T.n_tr * ((T.n_tc + T.apply_tiles - 1) / T.apply_tiles) < (uint64_t)c.sm_count * 12)
                 T.apply_tiles /= 2;
+            if (const char* e = std::getenv("RZ_APPLY_TILES")) T.apply_tiles = (uint32_t)std::max(1, std::atoi(e));  // experiments
             if (n_tiles64 < (1ull << 31)) {  // record = [tile | block], both below 2^31
                 T.n_tiles = (uint32_t)n_tiles64;
                 c.tile_cnt.ensure((size_t)n_parts * 12);
@@ -1066,7 +1124,7 @@ static void rasterize_dense(rz_geoms* g, const rz_context* ctx, void* out, rz_st
                     // ---- apply ------------------------------------------------------------------------
                     if (timed) CUDA_TRY(cudaEventRecord(c.ev[EV_A], s));
                     void* d_out;
-                    if (out_dev) {
+                    if (direct) {
                         d_out = out;
                         T.out_rows = shard_rows;
                         T.win_row_off = w.r0 - shard_r0;
@@ -1145,7 +1203,7 @@ static void rasterize_dense(rz_geoms* g, const rz_context* ctx, void* out, rz_st
                     S.key_bits = std::max(S.key_bits, tkey_bits);
                     S.tile_width = TILE_C;
                     tile_stats_pending = true;
-                    if (!out_dev) stage_copy(w, d_out);
+                    if (!direct) stage_copy(w, d_out);
                     flush_laps();
                     continue;
                 }
@@ -1298,7 +1356,7 @@ static void rasterize_dense(rz_geoms* g, const rz_context* ctx, void* out, rz_st
         F.nrows = (uint32_t)ri.nrows;
         F.win_r0 = w.r0;
         void* d_out;
-        if (out_dev) {
+        if (direct) {
             d_out = out;
             F.out_rows = shard_rows;
             F.win_row_off = w.r0 - shard_r0;
@@ -1317,7 +1375,7 @@ static void rasterize_dense(rz_geoms* g, const rz_context* ctx, void* out, rz_st
         lap(fill_ms, EV_A, EV_B);
 
         // ---- copy back ----------------------------------------------------------------------
-        if (!out_dev) stage_copy(w, d_out);
+        if (!direct) stage_copy(w, d_out);
         flush_laps();
     }
     if (!out_dev && n_staged) {  // the call returns when the last window has landed in host memory

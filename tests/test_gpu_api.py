@@ -122,3 +122,38 @@ def test_inputs_on_device_flag_equals_host_inputs():
     with pytest.raises(ValueError, match="host inputs"):
         core.rasterize_dense(g, ri, "sum", "float32", 0, background=np.nan, inputs_dev=dict(field=one.data_ptr(), scalar=True),
                              devices=[0])
+
+
+def test_r_array_layout_flag(monkeypatch):
+    """RZ_FLAG_OUT_ROW_COL_BAND: the raster in R's (row, col, band) column-major layout, i.e. C-order [band][col][row]
+    (R/rusterize/src/rust/src/encoding/rarrays.rs:9-17 permutes [band][row][col] with axes [0, 2, 1]) - host output in
+    several row windows, device output, row shards, several devices writing one array; i32 and f64 are the R dtypes."""
+    import torch
+
+    W, H = 333, 257
+    geoms = synth.mixed_geometries(52, 300, W, H, rho=30.0)
+    n = len(geoms)
+    by = [str(i % 3) for i in range(n)]
+    band, names = core.group_keys(by)
+    g = core.Geoms.from_wkb(geoms)
+    ri = core.raster_info(g, shape=(H, W), extent=(0, 0, W, H))
+    og = oracle.Geoms.from_wkb(geoms)
+    ori = oracle.raster_info(og, shape=(H, W), extent=(0, 0, W, H))
+    RCB = _lib.FLAG_OUT_ROW_COL_BAND
+    monkeypatch.setenv("RZ_WINDOW_BYTES", str(40 * W * 3))  # 40 rows of the 1-byte dtype, 5 of the 8-byte one
+    monkeypatch.setenv("RZ_ALLOW_REPEATED_DEVICES", "1")
+    for dtype, bg, fun in (("int32", -2147483648, "sum"), ("float64", np.nan, "max"), ("uint8", 0, "count")):
+        vals = (np.arange(n) % 9 + 1).astype(dtype)
+        exp, _ = oracle.rasterize_dense(og, ori, fun, dtype, vals, None, by, bg)
+        want = np.ascontiguousarray(exp.transpose(0, 2, 1))
+        got, st = core.rasterize_dense(g, ri, fun, dtype, vals, None, band, 3, bg, flags=RCB)
+        assert got.shape == (3, W, H) and st["n_windows"] > 2
+        assert np.array_equal(want, got, equal_nan=True), dtype
+        d_out = torch.zeros((3, W, H), dtype=getattr(torch, dtype), device="cuda")
+        core.rasterize_dense(g, ri, fun, dtype, vals, None, band, 3, bg, flags=RCB, out=d_out.data_ptr())
+        torch.cuda.synchronize()
+        assert np.array_equal(want, d_out.cpu().numpy(), equal_nan=True), dtype
+        shard, _ = core.rasterize_dense(g, ri, fun, dtype, vals, None, band, 3, bg, flags=RCB, rows=(31, 200))
+        assert np.array_equal(want[:, :, 31:200], shard, equal_nan=True), dtype
+        multi, _ = core.rasterize_dense(g, ri, fun, dtype, vals, None, band, 3, bg, flags=RCB, devices=[0, 0, 0])
+        assert np.array_equal(want, multi, equal_nan=True), dtype
