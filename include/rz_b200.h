@@ -92,6 +92,10 @@ rz_geoms* rz_geoms_from_wkb(const uint8_t* const* bufs, const uint64_t* lens, ui
 /* python/src/geo/parse_geometry.rs:123-134 (parse_sequence_wkt) */
 rz_geoms* rz_geoms_from_wkt(const char* const* strs, uint64_t n, char* err, size_t errlen);
 rz_geoms* rz_geoms_from_soa(const rz_geom_soa* soa, char* err, size_t errlen);
+/* The same, and the set is resident on `device` when the call returns: the pools are copied to the device WHILE they
+ * are being flattened (the transfer hides behind the host sweep), so the first rasterize call on that device pays no
+ * upload. */
+rz_geoms* rz_geoms_from_soa_to(const rz_geom_soa* soa, int device, char* err, size_t errlen);
 uint64_t rz_geoms_len(const rz_geoms* g);     /* geometries kept */
 uint64_t rz_geoms_n_parts(const rz_geoms* g);
 uint64_t rz_geoms_n_coords(const rz_geoms* g);

@@ -158,6 +158,7 @@ unsafe extern "C" {
     pub fn rz_geoms_from_wkb(bufs: *const *const u8, lens: *const u64, n: u64, err: *mut c_char, errlen: usize) -> *mut rz_geoms;
     pub fn rz_geoms_from_wkt(strs: *const *const c_char, n: u64, err: *mut c_char, errlen: usize) -> *mut rz_geoms;
     pub fn rz_geoms_from_soa(soa: *const RzGeomSoa, err: *mut c_char, errlen: usize) -> *mut rz_geoms;
+    pub fn rz_geoms_from_soa_to(soa: *const RzGeomSoa, device: c_int, err: *mut c_char, errlen: usize) -> *mut rz_geoms;
     pub fn rz_geoms_len(g: *const rz_geoms) -> u64;
     pub fn rz_geoms_n_parts(g: *const rz_geoms) -> u64;
     pub fn rz_geoms_n_coords(g: *const rz_geoms) -> u64;

@@ -87,6 +87,7 @@ SYMBOLS = {
     "rz_geoms_from_wkb": (C.c_void_p, [C.POINTER(C.c_char_p), C.POINTER(C.c_uint64), C.c_uint64] + _ERR),
     "rz_geoms_from_wkt": (C.c_void_p, [C.POINTER(C.c_char_p), C.c_uint64] + _ERR),
     "rz_geoms_from_soa": (C.c_void_p, [C.POINTER(GeomSoA)] + _ERR),
+    "rz_geoms_from_soa_to": (C.c_void_p, [C.POINTER(GeomSoA), C.c_int] + _ERR),
     "rz_geoms_len": (C.c_uint64, [C.c_void_p]),
     "rz_geoms_n_parts": (C.c_uint64, [C.c_void_p]),
     "rz_geoms_n_coords": (C.c_uint64, [C.c_void_p]),

@@ -61,13 +61,16 @@ class Geoms:
         raise ValueError("Sequence must contain geometries as shapely Geometry, bytes (WKB), or string (WKT).")
 
     @classmethod
-    def from_soa(cls, geom_part_off, part_kind, part_seq_off, seq_coord_off, x, y) -> "Geoms":
+    def from_soa(cls, geom_part_off, part_kind, part_seq_off, seq_coord_off, x, y, device=None) -> "Geoms":
         a = [np.ascontiguousarray(geom_part_off, np.uint64), np.ascontiguousarray(part_kind, np.uint8),
              np.ascontiguousarray(part_seq_off, np.uint64), np.ascontiguousarray(seq_coord_off, np.uint64),
              np.ascontiguousarray(x, np.float64), np.ascontiguousarray(y, np.float64)]
         soa = GeomSoA(len(a[0]) - 1, len(a[1]), len(a[3]) - 1, len(a[4]), *[v.ctypes.data for v in a])
         err = errbuf()
-        h = lib().rz_geoms_from_soa(C.byref(soa), err, len(err))
+        if device is None:
+            h = lib().rz_geoms_from_soa(C.byref(soa), err, len(err))
+        else:  # flatten and upload at the same time: the set is resident on `device` when this returns
+            h = lib().rz_geoms_from_soa_to(C.byref(soa), int(device), err, len(err))
         if not h:
             raise RuntimeError(err.value.decode())
         return cls(h)

@@ -5,6 +5,7 @@
 // of the reference with:  host flattening (rz_host.cpp) -> CUDA kernels (rz_kernels.cuh) -> copy-back.
 // There is no CPU fallback: without a usable CUDA device every compute entry point fails.
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -415,23 +416,11 @@ static void unpin_host(rz_geoms* g) {
     g->pool0_mapped = false;
 }
 
-static DeviceGeoms* geoms_on_device(rz_geoms* g, DeviceCtx& c, cudaStream_t s, bool force, size_t* h2d_bytes) {
-    std::lock_guard<std::mutex> lk(g->mu);
-    auto it = g->dev.find(c.dev);
-    if (it != g->dev.end() && !force) return it->second;
-    for (int k = 0; k < 3; k++)
-        if (g->pool[k].size() >= 0xfffffff0ull) throw Error{RZ_RUNTIME_ERROR, "Too many vertices (limit 2^32 per pool)."};
-    pin_host(g);
-    std::unique_ptr<DeviceGeoms> fresh;
-    DeviceGeoms* d = it != g->dev.end() ? it->second : nullptr;
-    if (!d) {
-        fresh.reset(new DeviceGeoms());
-        d = fresh.get();
-    }
-    d->dev = c.dev;
+// carve every device array of a geometry set out of one allocation (256-byte aligned; one spare element per array
+// so that kernels may read index i+1 of the last vertex unconditionally)
+static void alloc_device_geoms(const rz_geoms* g, DeviceGeoms* d) {
     const uint32_t n_parts = (uint32_t)g->part_kind.size();
-    if (!d->block) {  // carve every array out of one allocation (256-byte aligned; one spare element per array so
-                      // that kernels may read index i+1 of the last vertex unconditionally)
+    if (!d->block) {
         size_t total = 0;
         auto reserve = [&](size_t count, size_t elem) {
             const size_t at = total;
@@ -467,8 +456,33 @@ static DeviceGeoms* geoms_on_device(rz_geoms* g, DeviceCtx& c, cudaStream_t s, b
         d->part_vbeg = (uint32_t*)(base + o_vb);
         d->part_vend = (uint32_t*)(base + o_ve);
     }
+}
+
+// pools_done: the vertex pools were already copied while the set was being flattened (rz_geoms_from_soa_to)
+static DeviceGeoms* geoms_on_device(rz_geoms* g, DeviceCtx& c, cudaStream_t s, bool force, size_t* h2d_bytes,
+                                    DeviceGeoms* prefilled = nullptr) {
+    std::lock_guard<std::mutex> lk(g->mu);
+    auto it = g->dev.find(c.dev);
+    if (it != g->dev.end() && !force && !prefilled) return it->second;
+    for (int k = 0; k < 3; k++)
+        if (g->pool[k].size() >= 0xfffffff0ull) throw Error{RZ_RUNTIME_ERROR, "Too many vertices (limit 2^32 per pool)."};
+    pin_host(g);
+    std::unique_ptr<DeviceGeoms> fresh;
+    DeviceGeoms* d = prefilled ? prefilled : (it != g->dev.end() ? it->second : nullptr);
+    if (prefilled) fresh.reset(prefilled);
+    if (!d) {
+        fresh.reset(new DeviceGeoms());
+        d = fresh.get();
+    }
+    d->dev = c.dev;
+    const uint32_t n_parts = (uint32_t)g->part_kind.size();
+    alloc_device_geoms(g, d);
     size_t bytes = 0;
     for (int k = 0; k < 3; k++) {
+        if (prefilled) {
+            bytes += g->pool[k].size() * 16;
+            continue;
+        }
         upload_vec(d->x[k], g->pool[k].x, s, bytes, g->pinned_ranges);
         upload_vec(d->y[k], g->pool[k].y, s, bytes, g->pinned_ranges);
     }
@@ -1098,9 +1112,7 @@ static void rasterize_dense(rz_geoms* g, const rz_context* ctx, void* out, rz_st
                     c.task_start.ensure(((size_t)T.n_tiles + 1) * 4);
                     task_index_kernel<<<(T.n_tiles + 1 + 255) / 256, 256, 0, s>>>(ka, n_rec, T.block_bits, T.n_tiles,
                                                                                 c.task_start.as<uint32_t>());
-                    block_pos_kernel<<<(n_rec + 255) / 256, 256, 0, s>>>(ka, d_tc, T.block_bits, c.tile_desc.as<BlockDesc>(),
-                                                                        c.tile_desc2.as<BlockDesc>());
-                    launches += 2;
+                    launches++;
                     if (timed) CUDA_TRY(cudaEventRecord(c.ev[EV_B], s));
                     lap(sort_ms, EV_A, EV_B);
                     // ---- inside masks of every (part, tile) block ---------------------------------
@@ -1119,6 +1131,10 @@ static void rasterize_dense(rz_geoms* g, const rz_context* ctx, void* out, rz_st
                                 c.tile_masks.as<uint32_t>());
                         launches++;
                     }
+                    // the descriptors in tile order (after tile_mask: it flags the blocks that turned out solid)
+                    block_pos_kernel<<<(n_rec + 255) / 256, 256, 0, s>>>(ka, d_tc, T.block_bits, c.tile_desc.as<BlockDesc>(),
+                                                                        c.tile_desc2.as<BlockDesc>());
+                    launches++;
                     if (timed) CUDA_TRY(cudaEventRecord(c.ev[EV_B], s));
                     lap(count_ms, EV_A, EV_B);  // reported as the "count" stage slot: mask build
                     // ---- apply ------------------------------------------------------------------------
@@ -2549,6 +2565,77 @@ rz_geoms* rz_geoms_from_soa(const rz_geom_soa* soa, char* err, size_t errlen) {
         std::string msg;
         const int code = rz::flatten_soa(soa, g.get(), threads, msg);
         if (code != RZ_OK) throw Error{code, msg};
+    });
+    return rc == RZ_OK ? g.release() : nullptr;
+}
+
+// Flatten and upload at the same time: the worker threads hand every few megabytes of finished pool to the copy engine
+// (the pools are page-locked blocks), so the H2D transfer of a 3.3 GB geometry set (60 ms) hides behind its flattening
+// (75 ms) instead of following it.
+namespace {
+struct UploadWhileFlattening {
+    rz::DeviceCtx* c = nullptr;
+    rz::DeviceGeoms* d = nullptr;
+    rz_geoms* g = nullptr;
+    std::atomic<int> failed{0};
+    static void on_sized(void* p, rz_geoms* g) {
+        auto* u = static_cast<UploadWhileFlattening*>(p);
+        u->g = g;
+        for (int k = 0; k < 3; k++)
+            if (g->pool[k].size() >= 0xfffffff0ull) return;  // reported by the normal path
+        u->d = new rz::DeviceGeoms();
+        u->d->dev = u->c->dev;
+        try {
+            rz::alloc_device_geoms(g, u->d);
+        } catch (const Error&) {
+            delete u->d;
+            u->d = nullptr;  // the first rasterize call uploads (and reports the problem)
+        }
+    }
+    static void on_range(void* p, int kind, uint64_t v0, uint64_t v1) {
+        auto* u = static_cast<UploadWhileFlattening*>(p);
+        if (!u->d || u->failed.load(std::memory_order_relaxed)) return;
+        const size_t n = (size_t)(v1 - v0) * 8;
+        if (cudaSetDevice(u->c->dev) != cudaSuccess ||
+            cudaMemcpyAsync(u->d->x[kind] + v0, u->g->pool[kind].x.data() + v0, n, cudaMemcpyHostToDevice, u->c->copy_stream) != cudaSuccess ||
+            cudaMemcpyAsync(u->d->y[kind] + v0, u->g->pool[kind].y.data() + v0, n, cudaMemcpyHostToDevice, u->c->copy_stream) != cudaSuccess) {
+            (void)cudaGetLastError();
+            u->failed.store(1);
+        }
+    }
+};
+}  // namespace
+
+rz_geoms* rz_geoms_from_soa_to(const rz_geom_soa* soa, int device, char* err, size_t errlen) {
+    std::unique_ptr<rz_geoms> g(new rz_geoms());
+    int rc = guarded(err, errlen, [&]() {
+        rz::DeviceGuard guard;
+        rz::DeviceCtx& c = rz::device_ctx(device);
+        std::lock_guard<std::mutex> lk(c.mu);
+        CUDA_TRY(cudaSetDevice(c.dev));
+        unsigned threads = std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
+        if (const char* e = std::getenv("RZ_PARSE_THREADS")) threads = std::max(1, std::atoi(e));
+        UploadWhileFlattening up;
+        up.c = &c;
+        rz::FlattenHooks hooks;
+        hooks.ctx = &up;
+        hooks.on_sized = UploadWhileFlattening::on_sized;
+        hooks.on_range = UploadWhileFlattening::on_range;
+        std::string msg;
+        const int code = rz::flatten_soa(soa, g.get(), threads, msg, &hooks);
+        if (code != RZ_OK) {
+            if (up.d) {
+                cudaStreamSynchronize(c.copy_stream);
+                delete up.d;
+            }
+            throw Error{code, msg};
+        }
+        if (up.d && !up.failed.load()) {  // parts table, sequence lists, vertex tags; then the set is resident
+            rz::geoms_on_device(g.get(), c, c.copy_stream, false, nullptr, up.d);
+        } else if (up.d) {
+            cudaStreamSynchronize(c.copy_stream);
+            delete up.d;
+        }
     });
     return rc == RZ_OK ? g.release() : nullptr;
 }

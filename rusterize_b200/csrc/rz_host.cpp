@@ -689,7 +689,7 @@ struct SoaChunk {
 
 }  // namespace
 
-int flatten_soa(const rz_geom_soa* soa, rz_geoms* g, unsigned threads, std::string& err) {
+int flatten_soa(const rz_geom_soa* soa, rz_geoms* g, unsigned threads, std::string& err, const FlattenHooks* hooks) {
     const uint64_t G = soa->n_geoms, NP = soa->n_parts, NS = soa->n_seqs, NC = soa->n_coords;
     if (G == 0) return RZ_OK;
     if (soa->geom_part_off[G] > NP || soa->part_seq_off[NP] > NS || soa->seq_coord_off[NS] > NC) {
@@ -801,13 +801,23 @@ int flatten_soa(const rz_geom_soa* soa, rz_geoms* g, unsigned threads, std::stri
         g->pool[k].seq_end.resize(seq_tot[k]);
         g->pool[k].seq_closed.resize(seq_tot[k]);
     }
+    if (hooks && hooks->on_sized) hooks->on_sized(hooks->ctx, g);
     // ---- pass B: copy + extents ---------------------------------------------------------------------
     const double inf = std::numeric_limits<double>::infinity();
+    const uint64_t NOTIFY = (uint64_t)1 << 19;  // vertices per on_range call (4 MB of x + 4 MB of y)
     run([&](unsigned t) {
         SoaChunk& c = ch[t];
         uint64_t at[3] = {c.pool_off[0], c.pool_off[1], c.pool_off[2]};
+        uint64_t sent[3] = {c.pool_off[0], c.pool_off[1], c.pool_off[2]};
         uint64_t sq[2] = {c.seq_off[0], c.seq_off[1]};
         uint64_t bad = 0;
+        auto notify = [&](int kind, bool flush) {
+            if (!hooks || !hooks->on_range || at[kind] == sent[kind]) return;
+            if (!flush && at[kind] - sent[kind] < NOTIFY) return;
+            _mm_sfence();  // the streaming stores of this range are visible to the copy engine
+            hooks->on_range(hooks->ctx, kind, sent[kind], at[kind]);
+            sent[kind] = at[kind];
+        };
         for (uint64_t gi = c.g0; gi < c.g1; gi++) {
             bool gb_has = false;
             double gb[4] = {0, 0, 0, 0};
@@ -843,6 +853,7 @@ int flatten_soa(const rz_geom_soa* soa, rz_geoms* g, unsigned threads, std::stri
                     uint64_t m = n;
                     if (kind == RZ_PART_POINT) {
                         at[kind] += m;
+                        notify(kind, false);
                         continue;
                     }
                     bool closed = xs[0] == xs[n - 1] && ys[0] == ys[n - 1];
@@ -856,6 +867,7 @@ int flatten_soa(const rz_geom_soa* soa, rz_geoms* g, unsigned threads, std::stri
                     pool.seq_end[sq[kind]] = (uint32_t)(at[kind] - 1);
                     pool.seq_closed[sq[kind]] = (kind == RZ_PART_LINE && closed) ? 1 : 0;
                     sq[kind]++;
+                    notify(kind, false);
                 }
                 g->part_vend[p] = (uint32_t)at[kind];
                 const bool poly = kind == RZ_PART_POLYGON;
@@ -884,6 +896,7 @@ int flatten_soa(const rz_geom_soa* soa, rz_geoms* g, unsigned threads, std::stri
         }
         c.nonfinite = bad != 0;
         _mm_sfence();  // streaming stores are visible before the thread is joined
+        for (int k = 0; k < 3; k++) notify(k, true);
     });
     for (auto& c : ch) {
         if (c.nonfinite) g->nonfinite = true;

@@ -204,7 +204,15 @@ void finish_geoms(rz_geoms* g);
 // their final (page-locked) place: contiguous geometry ranges of equal coordinate counts, exact offsets from a
 // counting pass, copy + extents in one sweep.  Same result as feeding the Flattener one geometry at a time
 // (tests/test_host.py).  Returns RZ_OK or an error code with `err` set.
-int flatten_soa(const rz_geom_soa* soa, rz_geoms* g, unsigned threads, std::string& err);
+// Hooks let the caller start copying the pools to a device while they are still being written (rz_geoms_from_soa_to):
+// on_sized runs once all sizes are known and the pools are allocated, on_range (from the worker threads) every time
+// a few megabytes of a pool - vertices [v0, v1) of kind `kind`, x and y - have reached their final state.
+struct FlattenHooks {
+    void* ctx = nullptr;
+    void (*on_sized)(void* ctx, rz_geoms* g) = nullptr;
+    void (*on_range)(void* ctx, int kind, uint64_t v0, uint64_t v1) = nullptr;
+};
+int flatten_soa(const rz_geom_soa* soa, rz_geoms* g, unsigned threads, std::string& err, const FlattenHooks* hooks = nullptr);
 // tag[] of a pool (part id | TAG_CLOSED | TAG_SEQ_END), rebuilt from the parts table and the sequence lists
 // when a flattening path did not write it (the device never needs the host copy)
 void ensure_tags(rz_geoms* g, int kind);

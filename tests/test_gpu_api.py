@@ -157,3 +157,26 @@ def test_r_array_layout_flag(monkeypatch):
         assert np.array_equal(want[:, :, 31:200], shard, equal_nan=True), dtype
         multi, _ = core.rasterize_dense(g, ri, fun, dtype, vals, None, band, 3, bg, flags=RCB, devices=[0, 0, 0])
         assert np.array_equal(want, multi, equal_nan=True), dtype
+
+
+def test_flatten_and_upload_at_once_equals_the_two_step_route():
+    """rz_geoms_from_soa_to: pools copied to the device while they are flattened; the first call pays no upload and
+    the raster equals the two-step route's (several threads, closing vertices, all three pools)."""
+    geoms = synth.mixed_geometries(53, 3000, 900, 700, rho=35.0)
+    soa = synth.wkb_to_soa(geoms)
+    ri = core.raster_info(None, shape=(700, 900), extent=(0, 0, 900, 700))
+    vals = (np.arange(len(geoms)) % 11 + 1).astype(np.float32)
+    a = core.Geoms.from_soa(*soa)
+    b = core.Geoms.from_soa(*soa, device=0)
+    exp, st_a = core.rasterize_dense(a, ri, "sum", "float32", vals, background=np.nan)
+    got, st_b = core.rasterize_dense(b, ri, "sum", "float32", vals, background=np.nan)
+    assert np.array_equal(exp, got, equal_nan=True)
+    assert st_a["h2d_bytes"] > 16 * a.n_coords and st_b["h2d_bytes"] == vals.nbytes  # b was already resident
+    x, y, off = synth.star_polygons(53, 200000, 10, 40, 8.0, 3000, 3000)  # > 4 MB per pool: page-locked blocks, many ranges
+    big = core.Geoms.from_polygons(x, y, off)
+    idx = np.arange(len(off), dtype=np.uint64)
+    big_dev = core.Geoms.from_soa(idx, np.zeros(len(off) - 1, np.uint8), idx, off, x, y, device=0)
+    ri2 = core.raster_info(None, shape=(3000, 3000), extent=(0, 0, 3000, 3000))
+    e2, _ = core.rasterize_dense(big, ri2, "count", "uint16", 1, background=0)
+    g2, s2 = core.rasterize_dense(big_dev, ri2, "count", "uint16", 1, background=0)
+    assert np.array_equal(e2, g2) and s2["h2d_bytes"] <= 8
