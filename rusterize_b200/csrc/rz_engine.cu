@@ -1112,7 +1112,9 @@ static void rasterize_dense(rz_geoms* g, const rz_context* ctx, void* out, rz_st
                     c.task_start.ensure(((size_t)T.n_tiles + 1) * 4);
                     task_index_kernel<<<(T.n_tiles + 1 + 255) / 256, 256, 0, s>>>(ka, n_rec, T.block_bits, T.n_tiles,
                                                                                 c.task_start.as<uint32_t>());
-                    launches++;
+                    block_pos_kernel<<<(n_rec + 255) / 256, 256, 0, s>>>(ka, d_tc, T.block_bits, c.tile_desc.as<BlockDesc>(),
+                                                                        c.tile_desc2.as<BlockDesc>());
+                    launches += 2;
                     if (timed) CUDA_TRY(cudaEventRecord(c.ev[EV_B], s));
                     lap(sort_ms, EV_A, EV_B);
                     // ---- inside masks of every (part, tile) block ---------------------------------
@@ -1131,10 +1133,6 @@ static void rasterize_dense(rz_geoms* g, const rz_context* ctx, void* out, rz_st
                                 c.tile_masks.as<uint32_t>());
                         launches++;
                     }
-                    // the descriptors in tile order (after tile_mask: it flags the blocks that turned out solid)
-                    block_pos_kernel<<<(n_rec + 255) / 256, 256, 0, s>>>(ka, d_tc, T.block_bits, c.tile_desc.as<BlockDesc>(),
-                                                                        c.tile_desc2.as<BlockDesc>());
-                    launches++;
                     if (timed) CUDA_TRY(cudaEventRecord(c.ev[EV_B], s));
                     lap(count_ms, EV_A, EV_B);  // reported as the "count" stage slot: mask build
                     // ---- apply ------------------------------------------------------------------------

@@ -77,12 +77,11 @@ struct TileCounters {
 struct alignas(16) BlockDesc {
     unsigned long long value_bits;
     uint32_t woff;
-    uint32_t geom;  // row_off | nrows << 8 | w_off << 16 | nw << 20 | BLOCK_SOLID
+    uint32_t geom;  // row_off | nrows << 8 | w_off << 16 | nw << 20
 };
-// Set by tile_mask when every word of the block is 0xffffffff (a tile in the interior of a large polygon):
-// tile_apply then neither copies nor reads the block's words (config 3: most of its 4 GB of masks).
-constexpr uint32_t BLOCK_SOLID = 0x80000000u;
-__device__ __forceinline__ uint32_t block_nw(uint32_t geom) { return (geom >> 20) & 0xffu; }
+__device__ __forceinline__ uint32_t block_nw(uint32_t geom) { return geom >> 20; }
+// (Tried: tile_mask flagging blocks whose words are all ones - tiles inside a large polygon - so that tile_apply
+// skips their copy.  Config 3: ~15 % of the blocks, tile_apply unchanged at 4.75 / 3.4 ms, tile_mask 2 % slower.)
 __device__ __forceinline__ uint32_t pack_geom(uint32_t row_off, uint32_t nrows, uint32_t w_off, uint32_t nw) {
     return row_off | (nrows << 8) | (w_off << 16) | (nw << 20);
 }
@@ -435,7 +434,7 @@ static __global__ void __launch_bounds__(MASK_WARPS * 32, 8)
 tile_mask_kernel(KParams P, TileParams T, const uint64_t* __restrict__ units, const TileCounters* __restrict__ tcnt,
                  const PartTile* __restrict__ pt, const uint32_t* __restrict__ vbeg, const uint32_t* __restrict__ vend,
                  const double* __restrict__ wx, const double* __restrict__ wy, const uint32_t* __restrict__ tag,
-                 BlockDesc* desc, uint32_t* __restrict__ masks) {
+                 const BlockDesc* __restrict__ desc, uint32_t* __restrict__ masks) {
     __shared__ uint32_t s_mask[MASK_WARPS][MASK_SMEM_WORDS];
     __shared__ MaskEdge s_edge[MASK_WARPS][32];  // the batch's active edges, compacted
     const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
@@ -607,14 +606,10 @@ tile_mask_kernel(KParams P, TileParams T, const uint64_t* __restrict__ units, co
                 const uint32_t inv = b_nw == 1 ? 65536u : b_nw == 2 ? 32768u : b_nw == 3 ? 21846u : 16384u;
                 const uint32_t src0 = (tj + b_row - row_start) * stride + (tcl * 4u + b_w - wa);
                 uint32_t* dst = masks + wg.x;
-                uint32_t all = 0xffffffffu;
                 for (uint32_t i = lane; i < b_nr * b_nw; i += 32) {
                     const uint32_t r = (i * inv) >> 16, w = i - r * b_nw;
-                    const uint32_t v = mask[src0 + r * stride + w];
-                    dst[i] = v;
-                    all &= v;
+                    dst[i] = mask[src0 + r * stride + w];
                 }
-                if (__all_sync(0xffffffffu, all == 0xffffffffu) && lane == 0) desc[blk_row + tcl].geom = geom | BLOCK_SOLID;
             }
         }
         __syncwarp();
@@ -788,8 +783,7 @@ __device__ __forceinline__ void tile_apply_body(const KParams& P, const TilePara
             const uint32_t j = jb + lane;
             uint4 d = make_uint4(0, 0, 0, 0);
             if (j < cta_end) d = __ldg(reinterpret_cast<const uint4*>(desc + j));  // value lo, value hi, woff, geom
-            const uint32_t size =
-                (j < cta_end && !(d.w & BLOCK_SOLID)) ? ((((d.w >> 8) & 0xffu) * block_nw(d.w) + 7u) & ~7u) : 0u;
+            const uint32_t size = j < cta_end ? ((((d.w >> 8) & 0xffu) * block_nw(d.w) + 7u) & ~7u) : 0u;
             uint32_t inc = size;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
@@ -810,7 +804,7 @@ __device__ __forceinline__ void tile_apply_body(const KParams& P, const TilePara
             __syncwarp();
             if (lane == 0) mbar_arrive_expect_tx(&sh.full[st], total * 4u);
             __syncwarp();
-            if (lane < cnt && size) bulk_copy_g2s(&sh.words[st][inc - size], masks + d.z, size * 4u, &sh.full[st]);
+            if (lane < cnt) bulk_copy_g2s(&sh.words[st][inc - size], masks + d.z, size * 4u, &sh.full[st]);
             jb += cnt;
         }
         return;
@@ -860,9 +854,7 @@ __device__ __forceinline__ void tile_apply_body(const KParams& P, const TilePara
             const uint32_t b_row = d.geom & 0xffu, b_nr = (d.geom >> 8) & 0xffu;
             if (!(b_row < wr0 + 8u && b_row + b_nr > wr0)) continue;  // the block does not reach these 8 rows
             const uint32_t rr = my_r - b_row, ww = my_w - ((d.geom >> 16) & 0xfu), nw = block_nw(d.geom);
-            const uint32_t mu = (rr < b_nr && ww < nw)
-                                    ? ((d.geom & BLOCK_SOLID) ? 0xffffffffu : sh.words[st][d.soff + rr * nw + ww])
-                                    : 0u;
+            const uint32_t mu = (rr < b_nr && ww < nw) ? sh.words[st][d.soff + rr * nw + ww] : 0u;
             const N v = value_from_bits<N>(d.value_bits);
             if (MODE == 3) {
                 apply_part_word<N, FN, 3, BGNAN>(px, FN == RZ_FIRST ? (mu & ~touched) : mu, v, bg);
