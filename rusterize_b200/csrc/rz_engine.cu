@@ -1091,7 +1091,11 @@ static void rasterize_dense(rz_geoms* g, const rz_context* ctx, void* out, rz_st
                     lap(emit_ms, EV_A, EV_B);
                     // ---- records are in part order: a stable sort on the tile bits keeps burn order ----------
                     if (timed) CUDA_TRY(cudaEventRecord(c.ev[EV_A], s));
-                    const uint32_t tkey_bits = T.block_bits + bits_for(n_tiles64 + 1);
+                    // Only the tile bits are sorted.  The 0xff.. fillers behind the actual records need no extra bit: their
+                    // tile field is all ones, they come last in the input, and the sort is stable - they stay behind the
+                    // records of the last tile (task_index compares the whole upper key, where a filler is huge).
+                    // (65536 tiles per rank at 8 GPUs: 16 bits = two passes instead of three.)
+                    const uint32_t tkey_bits = T.block_bits + std::max(1u, bits_for(n_tiles64));
                     if (n_rec > 1) {
                         const uint32_t n_blocks = (n_rec + RS_TILE - 1) / RS_TILE;
                         c.hist.ensure((size_t)n_blocks * RS_RADIX * 4);

@@ -6,57 +6,38 @@ import pytest
 
 import oracle
 import synth
-from oracle import wkt2wkb as W
-from rusterize_b200 import core
+from rusterize_b200 import _lib, core
 
 pytestmark = pytest.mark.gpu
 
 
-def _config2(seed=2, n=100_000, size=16384):
-    """100k mixed geometries: 60% star polygons (16..64 vertices, rho 64), 25% line strings (2..32
-    vertices, random walk, step <= 64 px), 15% points / multipoints."""
-    rng = np.random.default_rng(seed)
-    kinds = rng.random(n)
-    out = []
-    for i in range(n):
-        cx, cy = rng.random(2) * size
-        if kinds[i] < 0.60:
-            nv = int(rng.integers(16, 65))
-            th = 2 * np.pi * (np.arange(nv) + 0.8 * rng.random(nv)) / nv
-            r = 64.0 * (0.5 + 0.5 * rng.random(nv))
-            p = np.stack([cx + r * np.cos(th), cy + r * np.sin(th)], 1)
-            out.append(W.polygon_wkb([np.vstack([p, p[:1]])]))
-        elif kinds[i] < 0.85:
-            nv = int(rng.integers(2, 33))
-            p = np.cumsum(rng.uniform(-64, 64, (nv, 2)), 0) + [cx, cy]
-            out.append(W.linestring_wkb(p))
-        else:
-            k = int(rng.integers(1, 9))
-            p = rng.random((k, 2)) * size
-            out.append(W.point_wkb(*p[0]) if k == 1 else W.multipoint_wkb(p))
-    return out
-
-
 def test_config2_mixed_count_and_any():
+    """BASELINE config 2 exactly as bench.py runs it (SplitMix64 seed 2, synth.config2_soa): 100k mixed
+    geometries - 60 % star polygons, 25 % line strings, 15 % points / multipoints - on 16384 x 16384."""
     size = 16384
-    geoms = _config2()
-    g = core.Geoms.from_wkb(geoms)
+    soa = synth.config2_soa(2, 100_000, size)
+    g = core.Geoms.from_soa(*soa)
     ri = core.raster_info(None, shape=(size, size), extent=(0, 0, size, size))
     cnt, st = core.rasterize_dense(g, ri, "count", "uint32", 1, background=0)
     anyv, _ = core.rasterize_dense(g, ri, "any", "uint8", 1, background=0)
     assert st["engine"] == 1  # count / any are order-free: polygons through the tile engine, lines and points by atomics
     assert np.array_equal(anyv[0] == 1, cnt[0] > 0)
     assert cnt.sum() > 0
-    # oracle on a row band of the same grid (bit-exact path)
+    # oracle on a row band of the same grid (bit-exact path): the geometries that can touch it, in input order
     r0, r1 = 4096, 4096 + 1024
-    og = oracle.Geoms.from_wkb(geoms)
+    sco, y = soa[3].astype(np.int64), soa[5]
+    ymin, ymax = np.minimum.reduceat(y, sco[:-1]), np.maximum.reduceat(y, sco[:-1])
+    keep = (size - ymax <= r1 + 3) & (size - ymin >= r0 - 3)
+    og = oracle.Geoms.from_wkb(synth.soa_to_wkb(synth.soa_select(soa, keep)))
     ori = oracle.raster_info(None, shape=(r1 - r0, size), extent=(0, size - r1, size, size - r0))
     exp_c, _ = oracle.rasterize_dense(og, ori, "count", "uint32", 1, background=0)
     exp_a, _ = oracle.rasterize_dense(og, ori, "any", "uint8", 1, background=0)
     assert np.array_equal(exp_c[0], cnt[0, r0:r1]) and np.array_equal(exp_a[0], anyv[0, r0:r1])
-    # a shard computed on its own equals the same rows of the full raster
+    # a shard computed on its own equals the same rows of the full raster; so does the forced record pipeline
     shard, _ = core.rasterize_dense(g, ri, "count", "uint32", 1, background=0, rows=(r0, r1))
     assert np.array_equal(shard[0], cnt[0, r0:r1])
+    rec, st_r = core.rasterize_dense(g, ri, "count", "uint32", 1, background=0, rows=(r0, r1), flags=_lib.FLAG_NO_TILE_ENGINE)
+    assert st_r["engine"] == 0 and np.array_equal(rec[0], cnt[0, r0:r1])
 
 
 def test_config3_32_layers_first_last_min_max():

@@ -173,3 +173,26 @@ def test_two_streams_share_the_device_scratch_safely():
         torch.cuda.synchronize()
         assert np.array_equal(ea[0], oa[0].cpu().numpy(), equal_nan=True)
         assert np.array_equal(eb[0], ob[0].cpu().numpy(), equal_nan=True)
+
+
+@pytest.mark.parametrize("shape", [(256, 512), (64, 128), (192, 384)])
+def test_filler_records_behind_the_last_tile(shape):
+    """The tile sort covers exactly the tile bits: filler records (parts skipped by a null field leave the record
+    array short of its cached bound) carry an all-ones tile field, equal to the last tile's id when the tile count is
+    a power of two.  They must stay behind that tile's real records (stable sort, fillers last in the input)."""
+    H, W = shape
+    n = 600
+    x, y, off = synth.star_polygons(61, n, 5, 12, 40.0, W, H)
+    # make sure the last tile (bottom-right) is busy
+    x[: int(off[60])] = x[: int(off[60])] * 0.1 + (W - 60)
+    y[: int(off[60])] = y[: int(off[60])] * 0.1 + 5
+    kw = dict(shape=(H, W), extent=(0, 0, W, H))
+    g = core.Geoms.from_polygons(x, y, off)
+    ri = core.raster_info(None, **kw)
+    rng = np.random.default_rng(61)
+    vals = rng.integers(1, 50, n).astype(np.float32)
+    for keep in (1.0, 0.5, 0.05):
+        valid = (rng.random(n) < keep).astype(np.uint8)
+        exp = _oracle(x, y, off, "sum", "float32", vals, np.nan, valid=valid, **kw)
+        got, st = core.rasterize_dense(g, ri, "sum", "float32", vals, valid, background=np.nan, flags=TILES)
+        assert st["engine"] == 1 and np.array_equal(exp, got, equal_nan=True), (shape, keep)
