@@ -266,12 +266,22 @@ static __global__ void tile_bin_kernel(KParams P, TileParams T, const PartInfo* 
             visits += __shfl_down_sync(0xffffffffu, visits, o);
             cross += __shfl_down_sync(0xffffffffu, cross, o);
         }
+        // one set of atomics per CTA, not per warp: all of them hit the same five words (C4: 31 k warps)
+        __shared__ unsigned long long s_tot[5];
+        if (threadIdx.x < 5) s_tot[threadIdx.x] = 0;
+        __syncthreads();
         if (lane_id() == 0 && pairs) {
-            atomicAdd(&tc->pairs, pairs);
-            atomicAdd(&tc->units, un);
-            atomicAdd(&tc->words, words);
-            atomicAdd(&tc->edge_visits, visits);
-            atomicAdd(&tc->cross_lb, cross);
+            atomicAdd(&s_tot[0], pairs);
+            atomicAdd(&s_tot[1], un);
+            atomicAdd(&s_tot[2], words);
+            atomicAdd(&s_tot[3], visits);
+            atomicAdd(&s_tot[4], cross);
+        }
+        __syncthreads();
+        if (threadIdx.x < 5 && s_tot[threadIdx.x]) {
+            unsigned long long* dst = threadIdx.x == 0 ? &tc->pairs : threadIdx.x == 1 ? &tc->units : threadIdx.x == 2 ? &tc->words
+                                      : threadIdx.x == 3 ? &tc->edge_visits : &tc->cross_lb;
+            atomicAdd(dst, s_tot[threadIdx.x]);
         }
     }
 }
