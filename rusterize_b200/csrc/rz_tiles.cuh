@@ -867,7 +867,16 @@ __device__ __forceinline__ void tile_apply_body(const KParams& P, const TilePara
             const uint32_t mu = (rr < b_nr && ww < nw) ? sh.words[st][d.soff + rr * nw + ww] : 0u;
             const N v = value_from_bits<N>(d.value_bits);
             if (MODE == 3) {
-                apply_part_word<N, FN, 3, BGNAN>(px, FN == RZ_FIRST ? (mu & ~touched) : mu, v, bg);
+                // `first` = `last` under the mask of the pixels nobody has written yet
+                if (FN == RZ_FIRST) {
+                    // The mask goes through a (no-op) shuffle so that ptxas keeps it in ONE register and expands it with
+                    // R2P: it otherwise folds `mu & ~touched & bit` into a 3-input LOP3 per pixel - 64 instead of 36
+                    // instructions per word (config 3 `first`: 4.75 ms against 3.4 ms for `last`).
+                    const uint32_t fresh = __shfl_sync(0xffffffffu, mu & ~touched, lane);
+                    apply_part_word<N, RZ_LAST, 0, BGNAN>(px, fresh, v, bg);
+                } else {
+                    apply_part_word<N, FN, 3, BGNAN>(px, mu, v, bg);
+                }
                 touched |= mu;
             } else if (MODE != 0) {
                 apply_part_word<N, FN, MODE, BGNAN>(px, mu, v, bg);
