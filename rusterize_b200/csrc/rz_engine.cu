@@ -1124,7 +1124,9 @@ static void rasterize_dense(rz_geoms* g, const rz_context* ctx, void* out, rz_st
                     // ---- inside masks of every (part, tile) block ---------------------------------
                     if (timed) CUDA_TRY(cudaEventRecord(c.ev[EV_A], s));
                     {
-                        const uint32_t grid = (T.cap_units + MASK_WARPS * MASK_UNITS - 1) / (MASK_WARPS * MASK_UNITS);
+                        // persistent grid: 8 CTAs per SM (the kernel's launch bounds), fewer when there is less work
+                        const uint32_t grid = std::min<uint32_t>((T.cap_units + MASK_WARPS * MASK_UNITS - 1) / (MASK_WARPS * MASK_UNITS),
+                                                                 (uint32_t)c.sm_count * 8u);
                         if (T.tile_r == 64)
                             tile_mask_kernel<64><<<grid, MASK_WARPS * 32, 0, s>>>(
                                 P, T, c.tile_units.as<uint64_t>(), d_tc, c.tile_pt.as<PartTile>(), dg->part_vbeg,

@@ -70,6 +70,8 @@ struct TileCounters {
     unsigned int overflow;           // a count exceeded its cached upper bound (never expected; checked by the host
                                      // whenever it synchronises anyway)
     unsigned int scan_ticket;        // block ticket of the look-back scan
+    unsigned int mask_ticket;        // next unassigned mask unit (tile_mask's warps take MASK_UNITS at a time)
+    unsigned int pad_;
 };
 
 // One (part, tile) block of the inside mask: rows [row_off, row_off + nrows) x words [w_off, w_off + nw) of the
@@ -441,7 +443,7 @@ static __global__ void block_pos_kernel(const uint64_t* __restrict__ recs, const
 // geometry sets holding any are never given to this engine.)
 template <int TILE_R>
 static __global__ void __launch_bounds__(MASK_WARPS * 32, 8)
-tile_mask_kernel(KParams P, TileParams T, const uint64_t* __restrict__ units, const TileCounters* __restrict__ tcnt,
+tile_mask_kernel(KParams P, TileParams T, const uint64_t* __restrict__ units, TileCounters* tcnt,
                  const PartTile* __restrict__ pt, const uint32_t* __restrict__ vbeg, const uint32_t* __restrict__ vend,
                  const double* __restrict__ wx, const double* __restrict__ wy, const uint32_t* __restrict__ tag,
                  const BlockDesc* __restrict__ desc, uint32_t* __restrict__ masks) {
@@ -452,7 +454,13 @@ tile_mask_kernel(KParams P, TileParams T, const uint64_t* __restrict__ units, co
     // A warp builds MASK_UNITS consecutive units (units are in part order, so are their vertices).  While it works
     // on one it asks the L2 for the next one's part record and vertex range: a unit lives for ~20 us and would
     // otherwise start with three dependent global loads.
-    const uint32_t unit0 = (blockIdx.x * MASK_WARPS + warp) * MASK_UNITS;
+    // The grid is persistent (one CTA per resident slot) and the warps draw their units from a ticket counter: no
+    // partial last wave, and long parts do not hold up a fixed share of the work (8 GPUs: 0.55 -> see DESIGN.md).
+    for (;;) {
+    uint32_t unit0 = 0;
+    if (lane == 0) unit0 = atomicAdd(&tcnt->mask_ticket, MASK_UNITS);
+    unit0 = __shfl_sync(0xffffffffu, unit0, 0);
+    if (unit0 >= n_units) break;
     for (uint32_t unit = unit0; unit < min(unit0 + MASK_UNITS, n_units); unit++) {
     const uint64_t un = units[unit];
     const uint32_t part = (uint32_t)un, k_tr = (uint32_t)(un >> 32) & 63u, tr = (uint32_t)(un >> 38);
@@ -624,7 +632,8 @@ tile_mask_kernel(KParams P, TileParams T, const uint64_t* __restrict__ units, co
         }
         __syncwarp();
     }
-    }  // units of this warp
+    }  // units of this draw
+    }  // draws
 }
 
 // ---------------------------------------------------------------------------------------------
