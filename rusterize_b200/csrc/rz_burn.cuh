@@ -73,12 +73,29 @@ line_burn_kernel(KParams P, const double* __restrict__ x, const double* __restri
     line_setup(P, x, y, tag, info, i, n, l, &kept, ctr);
     const unsigned long long v = (l.n && B.use_part_value) ? info[l.part].value_bits : B.one;
     const bool is_long = l.n > LONG_EDGE;
-    if (!is_long)
+    if (!is_long && l.n) {
+        // sequential walk: the minor coordinate q(k) = floor((2 dmin k + dmaj) / (2 dmaj)) of line_pixel() is carried
+        // along with its remainder instead of being divided out per pixel (a 64-bit division costs more than the
+        // atomic it feeds)
+        long long num = 2 * l.dmin * (long long)l.k_lo + l.dmaj;
+        const long long den = 2 * l.dmaj;
+        long long q = den > 0 ? num / den : 0;
+        long long rem = den > 0 ? num - q * den : 0;
+        const long long step = 2 * l.dmin;  // step <= den, so q advances by at most one per pixel
+        long long maj = (l.xmajor ? l.ix0 : l.iy0) + (l.xmajor ? l.sx : l.sy) * (long long)l.k_lo;
+        const long long min0 = l.xmajor ? l.iy0 : l.ix0;
+        const int smaj = l.xmajor ? l.sx : l.sy, smin = l.xmajor ? l.sy : l.sx;
         for (uint32_t k = 0; k < l.n; k++) {
-            long long px, py;
-            line_pixel(l, (long long)(l.k_lo + k), px, py);
-            burn_pixel<SZ, ADD>(P, B, l.band, py, px, v);
+            const long long mn = min0 + smin * q;
+            burn_pixel<SZ, ADD>(P, B, l.band, l.xmajor ? mn : maj, l.xmajor ? maj : mn, v);
+            maj += smaj;
+            rem += step;
+            if (rem >= den) {
+                rem -= den;
+                q++;
+            }
         }
+    }
     uint32_t m = __ballot_sync(0xffffffffu, is_long);
     const uint32_t lane = lane_id();
     while (m) {
