@@ -15,9 +15,9 @@ burning the parts the library cuts out for its band (rz_geoms_row_shard); the sp
 contiguous geometry ranges inside ONE library call (rz_rasterize_sparse_multi).
 
 One "step" = one full rasterisation.  `value` is device-resident throughput (geometry already in HBM, raster left
-in HBM).  `e2e` is the whole call a user makes, from host coordinate arrays to a host raster: flattening
-(rz_geoms_from_soa), the upload, the burn and the copy back into ONE pinned host array, through the library's
-multi-device entry point driven by rank 0 over all N GPUs.  Every rank checks rows of its own band (or a sampled
+in HBM).  `e2e` is the whole call a user makes, from host coordinate arrays to a host raster: flattening, the
+upload, the burn and the copy back into ONE pinned host array, all inside one library call
+(rz_rasterize_dense_soa) driven by rank 0 over all N GPUs.  Every rank checks rows of its own band (or a sampled
 geometry range of the sparse stream) against the CPU oracle, bit for bit, at every N.
 """
 from __future__ import annotations
@@ -587,24 +587,21 @@ def run_dense_e2e(env, name, w):
                                     flags=flags | eng_flag)[1]
 
     n_e2e = max(1, args.e2e_steps)
-    # one GPU: the pools are copied to the device while they are being flattened (rz_geoms_from_soa_to); several
-    # GPUs: every device uploads its own part subset inside the call
-    to_dev = 0 if world == 1 else None
-    # warm: page-locked pools / staging buffers exist, kernels are loaded
-    g = core.Geoms.from_soa(*w["soa"], device=to_dev)
-    call(g, _lib.FLAG_SYNC_STAGES)
-    del g
-    whole, flat, st_last, g = [], [], None, None
+
+    def one_shot(flags):  # rz_rasterize_dense_soa: flatten (each device only its band's parts) + H2D + burn + D2H
+        return core.rasterize_dense_soa(w["soa"], ri, fun, dtype, w["field"], None, band, n_b, bg, out=h_np,
+                                        devices=devices, flags=flags | eng_flag)[1]
+
+    one_shot(_lib.FLAG_SYNC_STAGES)  # warm: page-locked pools / staging buffers exist, kernels are loaded
+    whole, flat, st_last = [], [], None
     for _ in range(n_e2e):
-        del g  # (a caller's previous geometry set is gone: its page-locked pools are recycled by the next one)
         t0 = time.perf_counter()
-        g = core.Geoms.from_soa(*w["soa"], device=to_dev)
-        t1 = time.perf_counter()
-        st_last = call(g, _lib.FLAG_SYNC_STAGES)
-        t2 = time.perf_counter()
-        whole.append((t2 - t0) * 1e3)
-        flat.append((t1 - t0) * 1e3)
-    # the same call on an already flattened handle (what a caller who keeps the handle pays): upload forced
+        st_last = one_shot(_lib.FLAG_SYNC_STAGES)
+        whole.append((time.perf_counter() - t0) * 1e3)
+        flat.append(max(p["shard_ms"] for p in st_last["per_device"]))
+    # the same job on an already flattened handle (what a caller who keeps the handle pays): upload forced
+    g = core.Geoms.from_soa(*w["soa"])
+    call(g, _lib.FLAG_SYNC_STAGES)
     cached, cached_lib = [], []
     for _ in range(n_e2e):
         t0 = time.perf_counter()
@@ -646,12 +643,12 @@ def run_dense_e2e(env, name, w):
         except Exception as e:  # the probe must never take the bench down
             ceiling = {"error": str(e)[:200]}
     return {"value": n_b * rows * cols / (e_ms / 1e3) / 1e6, "unit": "Mpixel/s", "ms_per_step": e_ms, "host_d2h_ceiling": ceiling,
-            "h2d_bytes_per_step": int(max(st_last["h2d_bytes"], st_c["h2d_bytes"])), "d2h_bytes_per_step": int(st_last["d2h_bytes"]), "steps": n_e2e,
-            "includes": ("rz_geoms_from_soa_to (flatten into page-locked pools, H2D of the pools overlapped with it) + burn + D2H into one pinned host array"
-                         if world == 1 else
-                         "rz_geoms_from_soa (flatten into page-locked pools) + per-device part subsets + H2D + burn + D2H into one pinned host array"),
+            "h2d_bytes_per_step": int(st_c["h2d_bytes"]), "d2h_bytes_per_step": int(st_last["d2h_bytes"]), "steps": n_e2e,
+            "includes": "ONE library call from host coordinate arrays to the pinned host raster (rz_rasterize_dense_soa): every "
+                        "device flattens the parts of its row band into page-locked pools with the H2D overlapped, burns, "
+                        "copies its rows back",
             "flatten_ms": float(np.mean(flat)), "flatten_Gvert_per_s": w["n_vertices"] / (float(np.mean(flat)) / 1e3) / 1e9,
-            "flatten_note": "at one GPU this time includes the overlapped upload of the pools" if world == 1 else "host only",
+            "flatten_note": "slowest device: y-extent pass + flattening of its band's parts, upload overlapped",
             "ms_each_step": [round(v, 1) for v in whole],
             "e2e_handle_cached": {"ms_per_step": float(np.mean(cached)), "value": n_b * rows * cols / (float(np.mean(cached)) / 1e3) / 1e6,
                                   "ms_each_step": [round(v, 1) for v in cached], "lib_h2d_d2h_total_wall_ms_each_step": cached_lib,

@@ -114,6 +114,10 @@ void rz_geoms_free(rz_geoms* g);
  * rz_rasterize_dense_multi does the same internally.  Free with rz_geoms_free. */
 rz_geoms* rz_geoms_row_shard(const rz_geoms* g, const rz_raster_info* ri, uint64_t row_begin, uint64_t row_end,
                              int all_touched, char* err, size_t errlen);
+/* The same shard straight from the caller's arrays: only the band's parts are ever flattened (one parallel read of
+ * the y ordinates decides which). */
+rz_geoms* rz_geoms_from_soa_rows(const rz_geom_soa* soa, const rz_raster_info* ri, uint64_t row_begin, uint64_t row_end,
+                                 int all_touched, char* err, size_t errlen);
 
 /* Introspection of the flattened form (tests, FFI debugging). Returned pointers live as long as g. */
 const uint8_t* rz_geoms_part_kind(const rz_geoms* g);
@@ -228,6 +232,14 @@ int rz_rasterize_dense_multi(rz_geoms* g, const rz_context* ctx, const int32_t* 
                              rz_stats* stats, rz_stats* per_device, char* err, size_t errlen);
 int rz_rasterize_sparse_multi(rz_geoms* g, const rz_context* ctx, const int32_t* devices, int32_t n_devices,
                               rz_sparse** out, rz_stats* stats, rz_stats* per_device, char* err, size_t errlen);
+
+/* DenseArray::build (rust/src/rasterize.rs:77-115) in ONE call, for callers that hold the geometries and the context
+ * at the same time (the FFI shim): flatten + upload + burn + copy back.  With several devices every device's host
+ * thread flattens only the parts of its row band straight out of the caller's arrays (their extents come from one
+ * parallel read of the y ordinates), so no full flattened copy is made first.  Same result as
+ * rz_geoms_from_soa + rz_rasterize_dense_multi. */
+int rz_rasterize_dense_soa(const rz_geom_soa* soa, const rz_context* ctx, const int32_t* devices, int32_t n_devices,
+                           void* out, rz_stats* stats, rz_stats* per_device, char* err, size_t errlen);
 
 /* Device plumbing */
 int rz_device_count(void);

@@ -168,6 +168,8 @@ unsafe extern "C" {
     pub fn rz_geoms_free(g: *mut rz_geoms);
     pub fn rz_geoms_row_shard(g: *const rz_geoms, ri: *const RzRasterInfo, row_begin: u64, row_end: u64, all_touched: c_int,
                               err: *mut c_char, errlen: usize) -> *mut rz_geoms;
+    pub fn rz_geoms_from_soa_rows(soa: *const RzGeomSoa, ri: *const RzRasterInfo, row_begin: u64, row_end: u64,
+                                  all_touched: c_int, err: *mut c_char, errlen: usize) -> *mut rz_geoms;
     pub fn rz_geoms_part_kind(g: *const rz_geoms) -> *const u8;
     pub fn rz_geoms_part_geom(g: *const rz_geoms) -> *const u64;
     pub fn rz_geoms_pool_len(g: *const rz_geoms, kind: c_int) -> u64;
@@ -187,6 +189,9 @@ unsafe extern "C" {
     pub fn rz_rasterize_sparse_multi(g: *mut rz_geoms, ctx: *const RzContext, devices: *const i32, n_devices: i32,
                                      out: *mut *mut rz_sparse, stats: *mut RzStats, per_device: *mut RzStats,
                                      err: *mut c_char, errlen: usize) -> c_int;
+    pub fn rz_rasterize_dense_soa(soa: *const RzGeomSoa, ctx: *const RzContext, devices: *const i32, n_devices: i32,
+                                  out: *mut c_void, stats: *mut RzStats, per_device: *mut RzStats, err: *mut c_char,
+                                  errlen: usize) -> c_int;
     pub fn rz_sparse_len(s: *const rz_sparse) -> u64;
     pub fn rz_sparse_n_bands(s: *const rz_sparse) -> u64;
     pub fn rz_sparse_rows(s: *const rz_sparse) -> *const u64;

@@ -96,6 +96,7 @@ SYMBOLS = {
     "rz_geoms_evict": (None, [C.c_void_p]),
     "rz_geoms_free": (None, [C.c_void_p]),
     "rz_geoms_row_shard": (C.c_void_p, [C.c_void_p, C.POINTER(RasterInfo), C.c_uint64, C.c_uint64, C.c_int] + _ERR),
+    "rz_geoms_from_soa_rows": (C.c_void_p, [C.POINTER(GeomSoA), C.POINTER(RasterInfo), C.c_uint64, C.c_uint64, C.c_int] + _ERR),
     "rz_geoms_part_kind": (C.c_void_p, [C.c_void_p]),
     "rz_geoms_part_geom": (C.c_void_p, [C.c_void_p]),
     "rz_geoms_pool_len": (C.c_uint64, [C.c_void_p, C.c_int]),
@@ -110,6 +111,8 @@ SYMBOLS = {
                                            C.POINTER(Stats), C.POINTER(Stats)] + _ERR),
     "rz_rasterize_sparse_multi": (C.c_int, [C.c_void_p, C.POINTER(Context), C.POINTER(C.c_int32), C.c_int32,
                                             C.POINTER(C.c_void_p), C.POINTER(Stats), C.POINTER(Stats)] + _ERR),
+    "rz_rasterize_dense_soa": (C.c_int, [C.POINTER(GeomSoA), C.POINTER(Context), C.POINTER(C.c_int32), C.c_int32, C.c_void_p,
+                                         C.POINTER(Stats), C.POINTER(Stats)] + _ERR),
     "rz_sparse_len": (C.c_uint64, [C.c_void_p]),
     "rz_sparse_n_bands": (C.c_uint64, [C.c_void_p]),
     "rz_sparse_rows": (C.c_void_p, [C.c_void_p]),

@@ -76,6 +76,19 @@ class Geoms:
         return cls(h)
 
     @classmethod
+    def from_soa_rows(cls, soa, ri, row_begin: int, row_end: int, all_touched: bool = False) -> "Geoms":
+        """The row-band shard of `from_soa(*soa).row_shard(...)` without flattening the whole set first."""
+        a = [np.ascontiguousarray(soa[0], np.uint64), np.ascontiguousarray(soa[1], np.uint8),
+             np.ascontiguousarray(soa[2], np.uint64), np.ascontiguousarray(soa[3], np.uint64),
+             np.ascontiguousarray(soa[4], np.float64), np.ascontiguousarray(soa[5], np.float64)]
+        s = GeomSoA(len(a[0]) - 1, len(a[1]), len(a[3]) - 1, len(a[4]), *[v.ctypes.data for v in a])
+        err = errbuf()
+        h = lib().rz_geoms_from_soa_rows(C.byref(s), C.byref(ri), int(row_begin), int(row_end), int(bool(all_touched)), err, len(err))
+        if not h:
+            raise ValueError(err.value.decode())
+        return cls(h)
+
+    @classmethod
     def from_polygons(cls, x, y, ring_off) -> "Geoms":
         """G single-ring polygons: polygon i = coords[ring_off[i]:ring_off[i+1]] (closed if needed)."""
         ring_off = np.ascontiguousarray(ring_off, np.uint64)
@@ -282,6 +295,34 @@ def rasterize_dense(geoms: Geoms, ri: RasterInfo, fun="last", dtype="float64", f
     rc = lib().rz_rasterize_dense(geoms._h, C.byref(ctx), out_ptr, C.byref(st), err, len(err))
     raise_for(rc, err)
     return arr, st.as_dict()
+
+
+def rasterize_dense_soa(soa, ri: RasterInfo, fun="last", dtype="float64", field=1, field_valid=None, band_of_geom=None,
+                        n_bands=1, background=0, all_touched=False, out=None, devices=None, rows=None, flags=0):
+    """DenseArray::build in ONE library call (rz_rasterize_dense_soa): the six rz_geom_soa arrays, the context, the
+    devices, the host array.  Flattening, upload, burn and copy-back all happen inside; with several devices each one
+    flattens only its row band's parts straight out of `soa`.  Returns (array, stats dict)."""
+    a = [np.ascontiguousarray(soa[0], np.uint64), np.ascontiguousarray(soa[1], np.uint8),
+         np.ascontiguousarray(soa[2], np.uint64), np.ascontiguousarray(soa[3], np.uint64),
+         np.ascontiguousarray(soa[4], np.float64), np.ascontiguousarray(soa[5], np.float64)]
+    s = GeomSoA(len(a[0]) - 1, len(a[1]), len(a[3]) - 1, len(a[4]), *[v.ctypes.data for v in a])
+    ctx, dt, keep = _context(None, ri, fun, dtype, field, field_valid, band_of_geom, n_bands, background, all_touched,
+                             0, rows, None, flags, 0)
+    nb = n_bands if band_of_geom is not None else 1
+    nrows = ri.nrows if rows is None else rows[1] - rows[0]
+    shape = (nb, ri.ncols, nrows) if (int(flags) & _lib.FLAG_OUT_ROW_COL_BAND) else (nb, nrows, ri.ncols)
+    arr = np.empty(shape, dt) if out is None else out
+    if arr.dtype != dt or not arr.flags.c_contiguous or arr.size != nb * nrows * ri.ncols:
+        raise ValueError("`out` must be a C-contiguous array of the output dtype and shape")
+    darr, nd = _device_array(default_devices() if devices is None else devices)
+    per = (Stats * nd)()
+    st = Stats()
+    err = errbuf()
+    rc = lib().rz_rasterize_dense_soa(C.byref(s), C.byref(ctx), darr, nd, arr.ctypes.data, C.byref(st), per, err, len(err))
+    raise_for(rc, err)
+    d = st.as_dict()
+    d["per_device"] = [p.as_dict() for p in per]
+    return arr, d
 
 
 def rasterize_sparse(geoms: Geoms, ri: RasterInfo, fun="last", dtype="float64", field=1, field_valid=None,

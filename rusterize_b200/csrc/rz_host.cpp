@@ -681,6 +681,7 @@ struct SoaChunk {
     uint64_t g0 = 0, g1 = 0;               // geometry range
     uint64_t pool_cnt[3] = {0, 0, 0};      // vertices written per pool (closing vertices included)
     uint64_t seq_cnt[2] = {0, 0};          // non-empty sequences of the polygon / line pools
+    uint64_t part_cnt = 0, part_off = 0;   // parts written (all of the range's parts unless a keep mask is given)
     uint64_t pool_off[3] = {0, 0, 0}, seq_off[2] = {0, 0};
     bool has_bounds = false, nonfinite = false;
     double bounds[4] = {0, 0, 0, 0};
@@ -689,7 +690,8 @@ struct SoaChunk {
 
 }  // namespace
 
-int flatten_soa(const rz_geom_soa* soa, rz_geoms* g, unsigned threads, std::string& err, const FlattenHooks* hooks) {
+int flatten_soa(const rz_geom_soa* soa, rz_geoms* g, unsigned threads, std::string& err, const FlattenHooks* hooks,
+                const uint8_t* keep_part) {
     const uint64_t G = soa->n_geoms, NP = soa->n_parts, NS = soa->n_seqs, NC = soa->n_coords;
     if (G == 0) return RZ_OK;
     if (soa->geom_part_off[G] > NP || soa->part_seq_off[NP] > NS || soa->seq_coord_off[NS] > NC) {
@@ -744,6 +746,8 @@ int flatten_soa(const rz_geom_soa* soa, rz_geoms* g, unsigned threads, std::stri
                 c.error = "Invalid part kind";
                 return;
             }
+            if (keep_part && !keep_part[p]) continue;
+            c.part_cnt++;
             for (uint64_t s = soa->part_seq_off[p]; s < soa->part_seq_off[p + 1]; s++) {
                 const uint64_t k0 = soa->seq_coord_off[s], k1 = soa->seq_coord_off[s + 1];
                 if (k1 < k0 || k1 > NC) {
@@ -766,7 +770,7 @@ int flatten_soa(const rz_geom_soa* soa, rz_geoms* g, unsigned threads, std::stri
             err = c.error;
             return RZ_VALUE_ERROR;
         }
-    uint64_t pool_tot[3] = {0, 0, 0}, seq_tot[2] = {0, 0};
+    uint64_t pool_tot[3] = {0, 0, 0}, seq_tot[2] = {0, 0}, part_tot = 0;
     for (auto& c : ch) {
         for (int k = 0; k < 3; k++) {
             c.pool_off[k] = pool_tot[k];
@@ -776,6 +780,8 @@ int flatten_soa(const rz_geom_soa* soa, rz_geoms* g, unsigned threads, std::stri
             c.seq_off[k] = seq_tot[k];
             seq_tot[k] += c.seq_cnt[k];
         }
+        c.part_off = part_tot;
+        part_tot += c.part_cnt;
     }
     for (int k = 0; k < 3; k++)
         if (pool_tot[k] >= 0xfffffff0ull) {
@@ -788,14 +794,14 @@ int flatten_soa(const rz_geom_soa* soa, rz_geoms* g, unsigned threads, std::stri
             g->pool[k].x.resize(pool_tot[k]);
             g->pool[k].y.resize(pool_tot[k]);
         }
-        g->part_kind.resize(NP);
-        g->part_geom.resize(NP);
-        g->part_xlo.resize(NP);
-        g->part_xhi.resize(NP);
-        g->part_ylo.resize(NP);
-        g->part_yhi.resize(NP);
-        g->part_vbeg.resize(NP);
-        g->part_vend.resize(NP);
+        g->part_kind.resize(part_tot);
+        g->part_geom.resize(part_tot);
+        g->part_xlo.resize(part_tot);
+        g->part_xhi.resize(part_tot);
+        g->part_ylo.resize(part_tot);
+        g->part_yhi.resize(part_tot);
+        g->part_vbeg.resize(part_tot);
+        g->part_vend.resize(part_tot);
     }
     for (int k = 0; k < 2; k++) {
         g->pool[k].seq_end.resize(seq_tot[k]);
@@ -811,6 +817,7 @@ int flatten_soa(const rz_geom_soa* soa, rz_geoms* g, unsigned threads, std::stri
         uint64_t sent[3] = {c.pool_off[0], c.pool_off[1], c.pool_off[2]};
         uint64_t sq[2] = {c.seq_off[0], c.seq_off[1]};
         uint64_t bad = 0;
+        uint64_t pi = c.part_off;  // index of the next part written (== p without a keep mask)
         auto notify = [&](int kind, bool flush) {
             if (!hooks || !hooks->on_range || at[kind] == sent[kind]) return;
             if (!flush && at[kind] - sent[kind] < NOTIFY) return;
@@ -821,14 +828,16 @@ int flatten_soa(const rz_geom_soa* soa, rz_geoms* g, unsigned threads, std::stri
         for (uint64_t gi = c.g0; gi < c.g1; gi++) {
             bool gb_has = false;
             double gb[4] = {0, 0, 0, 0};
-            for (uint64_t p = soa->geom_part_off[gi]; p < soa->geom_part_off[gi + 1]; p++) {
-                const int kind = soa->part_kind[p];
+            for (uint64_t p0 = soa->geom_part_off[gi]; p0 < soa->geom_part_off[gi + 1]; p0++) {
+                if (keep_part && !keep_part[p0]) continue;
+                const uint64_t p = pi++;
+                const int kind = soa->part_kind[p0];
                 Pool& pool = g->pool[kind];
                 double pxlo = inf, pxhi = -inf, pylo = inf, pyhi = -inf;
                 g->part_kind[p] = (uint8_t)kind;
                 g->part_geom[p] = gi;
                 g->part_vbeg[p] = (uint32_t)at[kind];
-                for (uint64_t s = soa->part_seq_off[p]; s < soa->part_seq_off[p + 1]; s++) {
+                for (uint64_t s = soa->part_seq_off[p0]; s < soa->part_seq_off[p0 + 1]; s++) {
                     const uint64_t k0 = soa->seq_coord_off[s], n = soa->seq_coord_off[s + 1] - k0;
                     if (n == 0) continue;
                     double* xd = pool.x.data() + at[kind];
@@ -912,6 +921,44 @@ int flatten_soa(const rz_geom_soa* soa, rz_geoms* g, unsigned threads, std::stri
         }
     }
     g->n_geoms = G;
+    return RZ_OK;
+}
+
+// world-y extent of every part of a caller's SoA (one parallel read of the y array): what a one-shot multi-device
+// call needs to decide which device gets which part before anything is copied.  A part holding a NaN ordinate gets
+// (-inf, +inf): kept everywhere.
+int soa_part_y_extents(const rz_geom_soa* soa, unsigned threads, double* ylo, double* yhi, std::string& err) {
+    const uint64_t NP = soa->n_parts, NS = soa->n_seqs, NC = soa->n_coords;
+    if (soa->part_seq_off[NP] > NS || soa->seq_coord_off[NS] > NC) {
+        err = "Inconsistent SoA offsets";
+        return RZ_VALUE_ERROR;
+    }
+    const unsigned T = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>({(uint64_t)std::max(1u, threads), NP, NC / 65536 + 1}));
+    const double inf = std::numeric_limits<double>::infinity();
+    std::vector<std::thread> th;
+    auto body = [&](unsigned t) {
+        for (uint64_t p = NP * t / T; p < NP * (t + 1) / T; p++) {
+            double lo = inf, hi = -inf;
+            bool odd = false;
+            const uint64_t s0 = soa->part_seq_off[p], s1 = soa->part_seq_off[p + 1];
+            if (s1 > s0) {
+                const double* y = soa->y;
+                for (uint64_t k = soa->seq_coord_off[s0]; k < soa->seq_coord_off[s1]; k++) {
+                    const double a = y[k];
+                    lo = a < lo ? a : lo;
+                    hi = a > hi ? a : hi;
+                    odd |= !(a == a);
+                }
+            }
+            ylo[p] = odd ? -inf : lo;
+            yhi[p] = odd ? inf : hi;
+        }
+    };
+    if (T == 1) body(0);
+    else {
+        for (unsigned t = 0; t < T; t++) th.emplace_back([&, t]() { body(t); });
+        for (auto& x : th) x.join();
+    }
     return RZ_OK;
 }
 

@@ -212,7 +212,11 @@ struct FlattenHooks {
     void (*on_sized)(void* ctx, rz_geoms* g) = nullptr;
     void (*on_range)(void* ctx, int kind, uint64_t v0, uint64_t v1) = nullptr;
 };
-int flatten_soa(const rz_geom_soa* soa, rz_geoms* g, unsigned threads, std::string& err, const FlattenHooks* hooks = nullptr);
+// keep_part (nullable, [n_parts]): only the parts flagged non-zero are flattened - the geometry count and indices stay
+// the caller's - which gives the part subset of a row band (subset_parts) without flattening the whole set first.
+int flatten_soa(const rz_geom_soa* soa, rz_geoms* g, unsigned threads, std::string& err, const FlattenHooks* hooks = nullptr,
+                const uint8_t* keep_part = nullptr);
+int soa_part_y_extents(const rz_geom_soa* soa, unsigned threads, double* ylo, double* yhi, std::string& err);
 // tag[] of a pool (part id | TAG_CLOSED | TAG_SEQ_END), rebuilt from the parts table and the sequence lists
 // when a flattening path did not write it (the device never needs the host copy)
 void ensure_tags(rz_geoms* g, int kind);

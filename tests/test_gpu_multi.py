@@ -153,3 +153,36 @@ def test_two_devices_dense_and_sparse_equal_the_oracle():
         assert np.array_equal(one[k], many[k]), k
     trip = [p["out_bytes"] for p in many["stats"]["per_device"]]
     assert max(trip) < 1.25 * (sum(trip) / nd)  # balanced split
+
+
+def test_one_shot_dense_soa_equals_the_oracle(repeated):
+    """rz_rasterize_dense_soa: flatten + upload + burn + copy-back in ONE call; with several devices each flattens only
+    the parts of its row band straight out of the caller's arrays.  Mixed geometries with `by` bands, a row window,
+    all_touched, one device and four shards."""
+    W, H = 517, 389
+    geoms = synth.mixed_geometries(38, 500, W, H, rho=40.0)
+    n = len(geoms)
+    soa = synth.wkb_to_soa(geoms)
+    kw = dict(shape=(H, W), extent=(0, 0, W, H))
+    by = [str(i % 3) for i in range(n)]
+    band, names = core.group_keys(by)
+    og = oracle.Geoms.from_wkb(geoms)
+    ri, ori = core.raster_info(None, **kw), oracle.raster_info(None, **kw)
+    vals = (np.arange(n) % 13 + 1).astype(np.float32)
+    for touched in (False, True):
+        exp, _ = oracle.rasterize_dense(og, ori, "sum", "float32", vals, None, by, np.nan, all_touched=touched)
+        for devs in ([0], [0, 0, 0, 0]):
+            got, st = core.rasterize_dense_soa(soa, ri, "sum", "float32", vals, None, band, len(names), np.nan,
+                                               all_touched=touched, devices=devs)
+            assert np.array_equal(exp, got, equal_nan=True), (touched, devs)
+            assert len(st["per_device"]) == len(devs)
+        win, _ = core.rasterize_dense_soa(soa, ri, "sum", "float32", vals, None, band, len(names), np.nan,
+                                          all_touched=touched, devices=[0, 0, 0], rows=(100, 333))
+        assert np.array_equal(exp[:, 100:333], win, equal_nan=True)
+    if _n_dev() >= 2:
+        devs = list(range(min(_n_dev(), 4)))
+        exp, _ = oracle.rasterize_dense(og, ori, "count", "uint16", 1, None, by, 0)
+        got, st = core.rasterize_dense_soa(soa, ri, "count", "uint16", 1, None, band, len(names), 0, devices=devs)
+        assert np.array_equal(exp, got)
+    with pytest.raises(ValueError, match="Geometry and field lengths must match"):
+        core.rasterize_dense_soa(soa, ri, "sum", "float32", vals[:-1], None, band, len(names), np.nan, devices=[0])

@@ -4,6 +4,8 @@ points fail loudly (no CPU fallback) without a GPU."""
 import re
 from pathlib import Path
 
+import os
+
 import numpy as np
 import pytest
 
@@ -244,3 +246,30 @@ def test_row_shard_keeps_order_indices_and_vertices():
             assert np.array_equal(sx, px[sel]) and np.array_equal(sy, py[sel])
     with pytest.raises(ValueError, match="Invalid row shard"):
         g.row_shard(ri, 10, 10)
+
+
+def test_band_shard_straight_from_soa_equals_shard_of_the_flattened_set():
+    """rz_geoms_from_soa_rows (extents pass + flatten with a keep mask: what every device of a one-shot multi-GPU call
+    does) gives exactly the geometry set rz_geoms_from_soa + rz_geoms_row_shard gives: same parts in the same order,
+    same geometry indices, same pools - for any thread count."""
+    import synth
+
+    W, H = 400, 1000
+    geoms = synth.mixed_geometries(33, 600, W, H, rho=20.0)
+    soa = synth.wkb_to_soa(geoms)
+    full = core.Geoms.from_soa(*soa)
+    ri = core.raster_info(None, shape=(H, W), extent=(0, 0, W, H))
+    for threads in ("1", "3", "16"):
+        os.environ["RZ_PARSE_THREADS"] = threads
+        try:
+            for r0, r1, touched in [(0, 250, False), (250, 500, True), (777, 1000, False), (0, 1000, False), (499, 500, False)]:
+                a = full.row_shard(ri, r0, r1, touched)
+                b = core.Geoms.from_soa_rows(soa, ri, r0, r1, touched)
+                assert len(a) == len(b) == len(full) and a.n_parts == b.n_parts
+                for u, v in zip(a.parts(), b.parts()):
+                    assert np.array_equal(u, v)
+                for kind in range(3):
+                    for u, v in zip(a.pool(kind), b.pool(kind)):
+                        assert np.array_equal(u, v, equal_nan=True)
+        finally:
+            del os.environ["RZ_PARSE_THREADS"]
