@@ -236,8 +236,11 @@ int rz_rasterize_sparse_multi(rz_geoms* g, const rz_context* ctx, const int32_t*
 /* DenseArray::build (rust/src/rasterize.rs:77-115) in ONE call, for callers that hold the geometries and the context
  * at the same time (the FFI shim): flatten + upload + burn + copy back.  With several devices every device's host
  * thread flattens only the parts of its row band straight out of the caller's arrays (their extents come from one
- * parallel read of the y ordinates), so no full flattened copy is made first.  Same result as
- * rz_geoms_from_soa + rz_rasterize_dense_multi. */
+ * parallel read of the y ordinates), so no full flattened copy is made first.  With env RZ_ONE_SHOT_RUNS=k a
+ * device goes through its rows in k runs, flattening and uploading run i+1 while run i burns and copies back (off
+ * by default: on the boxes measured the two compete for the host's memory system and nothing is gained).
+ * `stats->shard_ms` = flattening time of the slowest device.  Same result as rz_geoms_from_soa +
+ * rz_rasterize_dense_multi. */
 int rz_rasterize_dense_soa(const rz_geom_soa* soa, const rz_context* ctx, const int32_t* devices, int32_t n_devices,
                            void* out, rz_stats* stats, rz_stats* per_device, char* err, size_t errlen);
 

@@ -66,7 +66,7 @@ fn bands(by: &[String]) -> (Vec<i32>, Vec<String>) {
 
 /// Everything a call borrows: the context points into these.
 struct Call<N> {
-    geoms: sys::Geoms,
+    soa: sys::GeomSoa, // coordinate arrays in the library's input layout (pooling rules applied, not yet flattened)
     scalar: [N; 1],
     background: [N; 1],
     band: Option<Vec<i32>>,
@@ -77,7 +77,7 @@ struct Call<N> {
 
 fn prepare<N: RasterDtype + sys::RzDtype>(geoms: &[Geometry<f64>], ctx: &RasterizeContext<N>) -> RusterizeResult<(Call<N>, sys::RzContext)> {
     sys::check_abi().map_err(|m| RusterizeError::RuntimeError(Box::leak(m.into_boxed_str())))?;
-    let handle = sys::Geoms::from_geometries(geoms).map_err(to_error)?;
+    let soa = sys::flatten(geoms);
     let (band, band_names) = match ctx.by {
         Some(by) => {
             let (b, n) = bands(by);
@@ -86,7 +86,7 @@ fn prepare<N: RasterDtype + sys::RzDtype>(geoms: &[Geometry<f64>], ctx: &Rasteri
         None => (None, vec![String::from("band_1")]),
     };
     let mut call = Call {
-        geoms: handle,
+        soa,
         scalar: [N::one()],
         background: [ctx.background],
         band,
@@ -185,10 +185,12 @@ pub(crate) fn build_dense<N: RasterDtype + sys::RzDtype>(geoms: &[Geometry<f64>]
     let devices = sys::default_devices();
     let mut err = sys::ErrBuf::new();
     let mut stats = sys::RzStats::default();
+    // one call: every device flattens the parts of its rows straight out of `soa`, uploads, burns, copies back
+    let raw_soa = call.soa.as_raw();
     let rc = unsafe {
-        sys::rz_rasterize_dense_multi(call.geoms.as_ptr(), &c, devices.as_ptr(), devices.len() as i32,
-                                      raster.as_mut_ptr() as *mut c_void, &mut stats, std::ptr::null_mut(), err.ptr(),
-                                      sys::ErrBuf::LEN)
+        sys::rz_rasterize_dense_soa(&raw_soa, &c, devices.as_ptr(), devices.len() as i32,
+                                    raster.as_mut_ptr() as *mut c_void, &mut stats, std::ptr::null_mut(), err.ptr(),
+                                    sys::ErrBuf::LEN)
     };
     if rc != sys::RZ_OK {
         return Err(to_error(err.to_error(rc)));
@@ -203,11 +205,12 @@ pub(crate) fn build_sparse<N: RasterDtype + sys::RzDtype>(geoms: &[Geometry<f64>
     let (call, mut c) = prepare(geoms, &ctx)?;
     bind(&call, &mut c);
     let devices = sys::default_devices();
+    let handle = sys::Geoms::from_soa(&call.soa).map_err(to_error)?;
     let mut err = sys::ErrBuf::new();
     let mut stats = sys::RzStats::default();
     let mut raw: *mut sys::rz_sparse = std::ptr::null_mut();
     let rc = unsafe {
-        sys::rz_rasterize_sparse_multi(call.geoms.as_ptr(), &c, devices.as_ptr(), devices.len() as i32, &mut raw, &mut stats,
+        sys::rz_rasterize_sparse_multi(handle.as_ptr(), &c, devices.as_ptr(), devices.len() as i32, &mut raw, &mut stats,
                                        std::ptr::null_mut(), err.ptr(), sys::ErrBuf::LEN)
     };
     if rc != sys::RZ_OK {

@@ -271,7 +271,10 @@ unsafe impl Send for Geoms {}
 impl Geoms {
     /// `&[geo::Geometry<f64>]` -> SoA (pooling rules of burn_geometry.rs:24-210) -> library handle.
     pub fn from_geometries(geoms: &[geo_types::Geometry<f64>]) -> Result<Self, RzError> {
-        let soa = flatten(geoms);
+        Self::from_soa(&flatten(geoms))
+    }
+    /// Coordinate arrays -> library handle (`rz_geoms_from_soa`: parallel flattening into page-locked pools).
+    pub fn from_soa(soa: &GeomSoa) -> Result<Self, RzError> {
         let raw = soa.as_raw();
         let mut err = ErrBuf::new();
         let h = unsafe { rz_geoms_from_soa(&raw, err.ptr(), ErrBuf::LEN) };

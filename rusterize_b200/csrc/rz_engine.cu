@@ -22,6 +22,7 @@
 #include <cctype>
 #include <unistd.h>
 #include <chrono>
+#include <future>
 #include <thread>
 #include <type_traits>
 #include <vector>
@@ -261,6 +262,8 @@ struct DeviceCtx {
     cudaEvent_t ev[16];
     cudaStream_t copy_stream = nullptr;  // device->host copies of finished row windows overlap the next window
     cudaStream_t copy_stream2 = nullptr; // second half of every window copy (two copy engines in flight)
+    cudaStream_t upload_stream = nullptr; // geometry pools copied while they are flattened; independent of the calls
+                                          // in flight on this device (one-shot calls flatten the next rows meanwhile)
     cudaEvent_t ev_half = nullptr, ev_first_fill = nullptr;
     cudaEvent_t ev_last = nullptr;  // end of the previous call on this device (scratch buffers are shared by all streams)
     bool ev_last_valid = false;
@@ -296,6 +299,7 @@ static DeviceCtx& device_ctx(int dev) {
     for (auto& e : c->ev) CUDA_TRY(cudaEventCreate(&e));
     CUDA_TRY(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaStreamCreateWithFlags(&c->copy_stream2, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&c->upload_stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaEventCreateWithFlags(&c->ev_half, cudaEventDisableTiming));
     CUDA_TRY(cudaEventCreate(&c->ev_first_fill));
     CUDA_TRY(cudaEventCreateWithFlags(&c->ev_last, cudaEventDisableTiming));
@@ -2009,6 +2013,23 @@ static void accumulate_stats(rz_stats& a, const rz_stats& b) {
     a.shard_ms = std::max(a.shard_ms, b.shard_ms);
 }
 
+// b ran after a on the same device (the row runs of a one-shot call): counts and times add
+static void append_stats(rz_stats& a, const rz_stats& b) {
+    const rz_stats first = a;
+    a.h2d_ms = a.count_ms = a.emit_ms = a.sort_ms = a.index_ms = a.fill_ms = a.d2h_ms = a.total_ms = a.wall_ms = a.shard_ms = 0.f;
+    accumulate_stats(a, b);  // counts add, flags combine
+    a.h2d_ms = first.h2d_ms + b.h2d_ms;
+    a.count_ms = first.count_ms + b.count_ms;
+    a.emit_ms = first.emit_ms + b.emit_ms;
+    a.sort_ms = first.sort_ms + b.sort_ms;
+    a.index_ms = first.index_ms + b.index_ms;
+    a.fill_ms = first.fill_ms + b.fill_ms;
+    a.d2h_ms = first.d2h_ms + b.d2h_ms;
+    a.total_ms = first.total_ms + b.total_ms;
+    a.wall_ms = first.wall_ms + b.wall_ms;
+    a.shard_ms = first.shard_ms + b.shard_ms;
+}
+
 static uint64_t f64_bits(double v) {
     uint64_t u;
     std::memcpy(&u, &v, 8);
@@ -2601,8 +2622,8 @@ struct UploadWhileFlattening {
         if (!u->d || u->failed.load(std::memory_order_relaxed)) return;
         const size_t n = (size_t)(v1 - v0) * 8;
         if (cudaSetDevice(u->c->dev) != cudaSuccess ||
-            cudaMemcpyAsync(u->d->x[kind] + v0, u->g->pool[kind].x.data() + v0, n, cudaMemcpyHostToDevice, u->c->copy_stream) != cudaSuccess ||
-            cudaMemcpyAsync(u->d->y[kind] + v0, u->g->pool[kind].y.data() + v0, n, cudaMemcpyHostToDevice, u->c->copy_stream) != cudaSuccess) {
+            cudaMemcpyAsync(u->d->x[kind] + v0, u->g->pool[kind].x.data() + v0, n, cudaMemcpyHostToDevice, u->c->upload_stream) != cudaSuccess ||
+            cudaMemcpyAsync(u->d->y[kind] + v0, u->g->pool[kind].y.data() + v0, n, cudaMemcpyHostToDevice, u->c->upload_stream) != cudaSuccess) {
             (void)cudaGetLastError();
             u->failed.store(1);
         }
@@ -2616,7 +2637,8 @@ static std::unique_ptr<rz_geoms> flatten_to_device(const rz_geom_soa* soa, const
     std::unique_ptr<rz_geoms> g(new rz_geoms());
     rz::DeviceGuard guard;
     rz::DeviceCtx& c = rz::device_ctx(device);
-    std::lock_guard<std::mutex> lk(c.mu);
+    // no context mutex: nothing of the context's scratch is touched, the copies go to their own stream - a call in
+    // flight on this device (the previous rows of a one-shot call) keeps running
     CUDA_TRY(cudaSetDevice(c.dev));
     UploadWhileFlattening up;
     up.c = &c;
@@ -2628,15 +2650,15 @@ static std::unique_ptr<rz_geoms> flatten_to_device(const rz_geom_soa* soa, const
     const int code = rz::flatten_soa(soa, g.get(), threads, msg, &hooks, keep_part);
     if (code != RZ_OK) {
         if (up.d) {
-            cudaStreamSynchronize(c.copy_stream);
+            cudaStreamSynchronize(c.upload_stream);
             delete up.d;
         }
         throw Error{code, msg};
     }
     if (up.d && !up.failed.load()) {  // parts table, sequence lists, vertex tags; then the set is resident
-        rz::geoms_on_device(g.get(), c, c.copy_stream, false, nullptr, up.d);
+        rz::geoms_on_device(g.get(), c, c.upload_stream, false, nullptr, up.d);
     } else if (up.d) {
-        cudaStreamSynchronize(c.copy_stream);
+        cudaStreamSynchronize(c.upload_stream);
         delete up.d;
     }
     return g;
@@ -2681,11 +2703,75 @@ rz_geoms* rz_geoms_from_soa_rows(const rz_geom_soa* soa, const rz_raster_info* r
     return rc == RZ_OK ? g.release() : nullptr;
 }
 
+// Rows [b0, b1) of a one-shot call on one device, as a two-stage pipeline over runs of rows: while run k burns and
+// copies back (PCIe device -> host, the long stage), the calling thread flattens and uploads the parts of run k+1
+// (host -> device: the other direction of the link).  The first copy-back starts after 1/n_runs of the flattening.
+static void one_shot_rows(const rz_geom_soa* soa, const rz_context* ctx, int device, uint64_t b0, uint64_t b1, uint64_t r0,
+                          uint64_t rows, const double* ylo, const double* yhi, int n_runs, unsigned threads, void* out,
+                          rz_stats& S) {
+    const rz_raster_info& ri = ctx->raster_info;
+    const uint64_t NP = soa->n_parts;
+    const double margin = ctx->all_touched ? 3.0 : 2.0;
+    std::vector<uint8_t> keep;
+    std::future<rz_stats> burn;
+    bool have = false;
+    float flatten_ms = 0.f;
+    auto collect = [&]() {
+        const rz_stats st = burn.get();  // rethrows what the burn threw
+        if (have) rz::append_stats(S, st);
+        else S = st;
+        have = true;
+    };
+    try {
+        for (int k = 0; k < n_runs; k++) {
+            const uint64_t a0 = b0 + (b1 - b0) * (uint64_t)k / (uint64_t)n_runs, a1 = b0 + (b1 - b0) * (uint64_t)(k + 1) / (uint64_t)n_runs;
+            if (a1 <= a0) continue;
+            const rz::WallClock clock;
+            const uint8_t* keep_ptr = nullptr;
+            if (ylo) {  // (no extents: one run over every row of the call - every part is kept)
+                keep.resize(NP);
+                keep_row_parts(ri, ylo, yhi, NP, a0, a1, margin, keep.data());
+                keep_ptr = keep.data();
+            }
+            std::shared_ptr<rz_geoms> g(flatten_to_device(soa, keep_ptr, device, threads).release());
+            flatten_ms += clock.ms();
+            if (burn.valid()) collect();
+            rz_context c = *ctx;
+            c.device = device;
+            c.stream = nullptr;
+            c.row_begin = a0;
+            c.row_end = a1;
+            const rz::DenseExtra ex{rows, a0 - r0};
+            burn = std::async(std::launch::async, [g, c, ex, out, device]() {
+                rz::bind_thread_near_device(device);
+                rz_stats st;
+                std::memset(&st, 0, sizeof st);
+                rz::rasterize_dense(g.get(), &c, out, &st, &ex);
+                return st;
+            });
+        }
+        if (burn.valid()) collect();
+    } catch (...) {
+        if (burn.valid()) burn.wait();  // the burn in flight reads the caller's arrays: let it finish
+        throw;
+    }
+    S.shard_ms = flatten_ms;
+}
+
+// how many runs of rows a device's share of a one-shot call is cut into.  ONE unless RZ_ONE_SHOT_RUNS says otherwise:
+// measured on config 4 / 1 B200 (profiles/r2_one_shot_runs.txt) the flattening of run k+1 next to the copy-back of
+// run k takes 2.3x as long and slows the copy by 6 % (both are bound by the host's memory system), so 4 runs end at
+// 398 ms against 403 ms for one - within run-to-run noise - and 8 runs are slower.
+static int one_shot_runs(const rz_geom_soa*, const rz_context*, uint64_t) {
+    if (const char* e = std::getenv("RZ_ONE_SHOT_RUNS")) return std::max(1, std::min(64, std::atoi(e)));
+    return 1;
+}
+
 // DenseArray::build in one call (rust/src/rasterize.rs:77-115): the caller's geometries (SoA), the context, the
-// devices, the caller's array.  One device: flatten + upload overlapped, then the burn.  Several devices: one
-// parallel read of the y ordinates gives every part's extent, every device's host thread flattens ONLY the parts of
-// its row band straight out of the caller's arrays (no full flattened copy, no second subset copy: 8.2 GB of host
-// traffic instead of 13 GB for config 4) with its upload overlapped, burns its band and copies it into `out`.
+// devices, the caller's array.  One parallel read of the y ordinates gives every part's extent; every device's host
+// thread then flattens ONLY the parts of its rows straight out of the caller's arrays (no full flattened copy, no
+// second subset copy: 8.2 GB of host traffic instead of 13 GB for config 4 on several devices) with the upload
+// overlapped, burns them and copies them into `out` (one_shot_rows; optionally a run of rows at a time).
 int rz_rasterize_dense_soa(const rz_geom_soa* soa, const rz_context* ctx, const int32_t* devices, int32_t n_devices,
                            void* out, rz_stats* stats, rz_stats* per_device, char* err, size_t errlen) {
     return guarded(err, errlen, [&]() {
@@ -2702,23 +2788,24 @@ int rz_rasterize_dense_soa(const rz_geom_soa* soa, const rz_context* ctx, const 
         const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
         std::vector<rz_stats> S((size_t)D);
         for (auto& x : S) std::memset(&x, 0, sizeof x);
-        if (D == 1) {
-            std::unique_ptr<rz_geoms> g = flatten_to_device(soa, nullptr, devices[0], host_threads());
-            rz_context c = *ctx;
-            c.device = devices[0];
-            c.stream = nullptr;
-            S[0].shard_ms = call_clock.ms();
-            const float flat = S[0].shard_ms;
-            rz::rasterize_dense(g.get(), &c, out, &S[0]);
-            S[0].shard_ms = flat;
-        } else {
-            const uint64_t NP = soa->n_parts;
-            std::vector<double> ylo(NP), yhi(NP);
+        const int n_runs = one_shot_runs(soa, ctx, (rows + (uint64_t)D - 1) / (uint64_t)D);
+        const uint64_t NP = soa->n_parts;
+        std::vector<double> ylo, yhi;
+        float extents_ms = 0.f;
+        if (D > 1 || n_runs > 1) {
+            ylo.resize(NP);
+            yhi.resize(NP);
             std::string msg;
             const int code = rz::soa_part_y_extents(soa, std::min(32u, hw), ylo.data(), yhi.data(), msg);
             if (code != RZ_OK) throw Error{code, msg};
-            const float extents_ms = call_clock.ms();
-            const double margin = ctx->all_touched ? 3.0 : 2.0;
+            extents_ms = call_clock.ms();
+        }
+        const double* pylo = ylo.empty() ? nullptr : ylo.data();
+        const double* pyhi = yhi.empty() ? nullptr : yhi.data();
+        if (D == 1) {
+            one_shot_rows(soa, ctx, devices[0], r0, r1, r0, rows, (n_runs > 1 ? pylo : nullptr), pyhi, n_runs, host_threads(), out, S[0]);
+            S[0].shard_ms += extents_ms;
+        } else {
             const unsigned sub_threads = std::max(2u, std::min(16u, hw / (unsigned)D));
             Error first;
             rz::run_per_device(D, [&](int d) {
@@ -2726,19 +2813,9 @@ int rz_rasterize_dense_soa(const rz_geom_soa* soa, const rz_context* ctx, const 
                 if (b1 <= b0) return;
                 rz::bind_thread_near_device(devices[d]);
                 const rz::WallClock shard_clock;
-                std::vector<uint8_t> keep(NP);
-                keep_row_parts(ri, ylo.data(), yhi.data(), NP, b0, b1, margin, keep.data());
-                std::unique_ptr<rz_geoms> g = flatten_to_device(soa, keep.data(), devices[d], sub_threads);
-                const float shard_ms = shard_clock.ms();
-                rz_context c = *ctx;
-                c.device = devices[d];
-                c.stream = nullptr;
-                c.row_begin = b0;
-                c.row_end = b1;
-                const rz::DenseExtra ex{rows, b0 - r0};
-                rz::rasterize_dense(g.get(), &c, out, &S[d], &ex);
-                S[d].shard_ms = shard_ms + extents_ms;
-                S[d].wall_ms += shard_ms;
+                one_shot_rows(soa, ctx, devices[d], b0, b1, r0, rows, pylo, pyhi, n_runs, sub_threads, out, S[d]);
+                S[d].shard_ms += extents_ms;
+                S[d].wall_ms = shard_clock.ms();
             }, first);
             if (first.code != RZ_OK) throw first;
         }

@@ -155,10 +155,14 @@ def test_two_devices_dense_and_sparse_equal_the_oracle():
     assert max(trip) < 1.25 * (sum(trip) / nd)  # balanced split
 
 
-def test_one_shot_dense_soa_equals_the_oracle(repeated):
+@pytest.mark.parametrize("runs", [None, "3"])
+def test_one_shot_dense_soa_equals_the_oracle(repeated, monkeypatch, runs):
     """rz_rasterize_dense_soa: flatten + upload + burn + copy-back in ONE call; with several devices each flattens only
-    the parts of its row band straight out of the caller's arrays.  Mixed geometries with `by` bands, a row window,
-    all_touched, one device and four shards."""
+    the parts of its row band straight out of the caller's arrays, and a device's rows go through in runs (the next
+    run is flattened while the previous one burns and copies back; forced to 3 runs here, large rasters choose it
+    themselves).  Mixed geometries with `by` bands, a row window, all_touched, one device and four shards."""
+    if runs:
+        monkeypatch.setenv("RZ_ONE_SHOT_RUNS", runs)
     W, H = 517, 389
     geoms = synth.mixed_geometries(38, 500, W, H, rho=40.0)
     n = len(geoms)
