@@ -572,8 +572,10 @@ def run_dense_e2e(env, name, w):
     n_b = 1 if w["by"] is None else len(set(w["by"]))
     band, names = (None, None) if w["by"] is None else core.group_keys(w["by"])
     ri = core.raster_info(None, shape=(rows, cols), extent=(0.0, 0.0, float(cols), float(rows)))
-    h_out = torch.empty((n_b, rows, cols), dtype=getattr(torch, np.dtype(dtype).name)).pin_memory()
-    h_np = h_out.numpy()
+    # the caller-owned host raster: page-locked memory from the library's allocator (rz_host_alloc: recycled huge pages,
+    # interleaved over the host's memory nodes so that GPUs on either socket copy into it at the same rate)
+    h_np = core.host_empty((n_b, rows, cols), dtype)
+    h_out = torch.from_numpy(h_np)
     devices = list(range(world))
     eng_flag = {"auto": 0, "records": _lib.FLAG_NO_TILE_ENGINE, "tiles": _lib.FLAG_FORCE_TILE_ENGINE}[args.engine]
     if world > 1:  # this process now drives every GPU: it may run on every core again

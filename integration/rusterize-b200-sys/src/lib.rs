@@ -202,6 +202,8 @@ unsafe extern "C" {
     pub fn rz_sparse_build_array(ctx: *const RzContext, n_bands: u64, counts: *const u64, rows: *const u64, cols: *const u64,
                                  data: *const c_void, out: *mut c_void, stats: *mut RzStats, err: *mut c_char,
                                  errlen: usize) -> c_int;
+    pub fn rz_host_alloc(bytes: usize, err: *mut c_char, errlen: usize) -> *mut c_void;
+    pub fn rz_host_free(p: *mut c_void);
     pub fn rz_device_count() -> c_int;
     pub fn rz_version() -> *const c_char;
     pub fn rz_abi_layout(out: *mut u64, n: c_int) -> c_int;

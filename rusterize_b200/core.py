@@ -237,6 +237,46 @@ def default_devices():
     return list(range(max(1, lib().rz_device_count())))
 
 
+class _HostBlock:
+    """Owner of one rz_host_alloc block: handed back to the library's pool when the last array over it goes away."""
+
+    def __init__(self, p):
+        self.p = p
+
+    def __del__(self):
+        try:
+            lib().rz_host_free(self.p)
+        except Exception:  # interpreter shutdown
+            pass
+
+
+def host_empty(shape, dtype):
+    """np.empty in the library's page-locked host memory (rz_host_alloc): huge pages already faulted in, recycled
+    between calls, registered with CUDA (device -> host copies land at the PCIe rate without staging) and interleaved
+    over the machine's memory nodes so that GPUs on either socket write it equally fast."""
+    dt = np.dtype(dtype)
+    shape = tuple(int(v) for v in (shape if isinstance(shape, (tuple, list)) else (shape,)))
+    n = int(np.prod(shape, dtype=np.int64)) * dt.itemsize
+    if n == 0:
+        return np.empty(shape, dt)
+    err = errbuf()
+    p = lib().rz_host_alloc(n, err, len(err))
+    if not p:
+        raise RuntimeError(err.value.decode(errors="replace"))
+    buf = (C.c_uint8 * n).from_address(p)
+    buf._rz_owner = _HostBlock(p)  # the array's base chain (memoryview -> buf) keeps the block alive
+    return np.frombuffer(buf, dtype=dt).reshape(shape)
+
+
+_HOST_EMPTY_MIN = 64 << 20  # outputs from this size on are allocated page-locked (smaller ones: plain numpy)
+
+
+def _new_output(shape, dt):
+    if int(np.prod(shape, dtype=np.int64)) * np.dtype(dt).itemsize >= _HOST_EMPTY_MIN:
+        return host_empty(shape, dt)
+    return np.empty(shape, dt)
+
+
 def _device_array(devices):
     devs = [int(d) for d in devices]
     return (C.c_int32 * len(devs))(*devs), len(devs)
@@ -278,7 +318,7 @@ def rasterize_dense(geoms: Geoms, ri: RasterInfo, fun="last", dtype="float64", f
     else:
         # RZ_FLAG_OUT_ROW_COL_BAND: C-order [band][col][row] == R's (row, col, band) column-major array
         shape = (nb, ri.ncols, nrows) if (int(flags) & _lib.FLAG_OUT_ROW_COL_BAND) else (nb, nrows, ri.ncols)
-        arr = np.empty(shape, dt) if out is None else out
+        arr = _new_output(shape, dt) if out is None else out
         if arr.dtype != dt or not arr.flags.c_contiguous or arr.size != nb * nrows * ri.ncols:
             raise ValueError("`out` must be a C-contiguous array of the output dtype and shape")
         out_ptr = arr.ctypes.data
@@ -311,7 +351,7 @@ def rasterize_dense_soa(soa, ri: RasterInfo, fun="last", dtype="float64", field=
     nb = n_bands if band_of_geom is not None else 1
     nrows = ri.nrows if rows is None else rows[1] - rows[0]
     shape = (nb, ri.ncols, nrows) if (int(flags) & _lib.FLAG_OUT_ROW_COL_BAND) else (nb, nrows, ri.ncols)
-    arr = np.empty(shape, dt) if out is None else out
+    arr = _new_output(shape, dt) if out is None else out
     if arr.dtype != dt or not arr.flags.c_contiguous or arr.size != nb * nrows * ri.ncols:
         raise ValueError("`out` must be a C-contiguous array of the output dtype and shape")
     darr, nd = _device_array(default_devices() if devices is None else devices)

@@ -19,6 +19,7 @@
 #include <pthread.h>
 #include <sched.h>
 #include <sys/mman.h>
+#include <sys/syscall.h>
 #include <cctype>
 #include <unistd.h>
 #include <chrono>
@@ -100,16 +101,79 @@ struct HostBlock {
     void* p = nullptr;
     size_t cap = 0;
     bool pinned = false;
+    bool interleaved = false;  // pages placed on the memory nodes of the GPUs (rz_host_alloc, sparse results)
 };
+
+// Memory nodes the CUDA devices in use (RZ_DEVICES, else every visible one) hang off
+// (/sys/bus/pci/devices/<bus id>/numa_node), distinct, ascending.
+static const std::vector<int>& device_memory_nodes() {
+    static const std::vector<int> nodes = []() {
+        std::vector<int> v;
+        int n = 0;
+        if (cudaGetDeviceCount(&n) != cudaSuccess) {
+            (void)cudaGetLastError();
+            return v;
+        }
+        std::vector<int> devs;
+        if (const char* e = std::getenv("RZ_DEVICES")) {  // the devices calls use by default (same rule as the bindings)
+            for (const char* q = e; *q;) {
+                char* end = nullptr;
+                const long d = std::strtol(q, &end, 10);
+                if (end == q) break;
+                if (d >= 0 && d < n) devs.push_back((int)d);
+                q = *end == ',' ? end + 1 : end;
+            }
+        }
+        if (devs.empty())
+            for (int d = 0; d < n; d++) devs.push_back(d);
+        for (int d : devs) {
+            char bus[32] = {0};
+            if (cudaDeviceGetPCIBusId(bus, (int)sizeof bus, d) != cudaSuccess) {
+                (void)cudaGetLastError();
+                continue;
+            }
+            for (char* q = bus; *q; q++) *q = (char)std::tolower((unsigned char)*q);
+            const std::string path = std::string("/sys/bus/pci/devices/") + bus + "/numa_node";
+            std::FILE* f = std::fopen(path.c_str(), "r");
+            if (!f) continue;
+            int node = -1;
+            if (std::fscanf(f, "%d", &node) != 1) node = -1;
+            std::fclose(f);
+            if (node >= 0 && node < 1024 && std::find(v.begin(), v.end(), node) == v.end()) v.push_back(node);
+        }
+        std::sort(v.begin(), v.end());
+        return v;
+    }();
+    return nodes;
+}
+
+// Place the pages of [p, p+bytes) - before they are touched - on the memory nodes the visible GPUs are attached to:
+// round-robin over them (mbind, MPOL_INTERLEAVE) when they hang off several nodes, on the one node otherwise
+// (MPOL_PREFERRED).  A raster written by the copy engines of GPUs on BOTH sockets otherwise lives on the socket of
+// the thread that first touched it, and the devices of the other socket copy into it at 60 % of the rate (measured
+// at 8 GPUs: 170 ms against 105 ms for the same 2.1 GB; at 4 GPUs 161 against 94).  Returns false when the nodes
+// are unknown or the kernel refuses (containers without CAP_SYS_NICE): the pages then follow first touch.
+static bool place_pages_near_devices(void* p, size_t bytes) {
+    if (const char* e = std::getenv("RZ_HOST_INTERLEAVE"))
+        if (std::atoi(e) == 0) return false;
+    const std::vector<int>& nodes = device_memory_nodes();
+    if (nodes.empty()) return false;
+    const unsigned long bits = 8 * sizeof(unsigned long);
+    const unsigned long max_node = (unsigned long)nodes.back();
+    std::vector<unsigned long> mask(max_node / bits + 2, 0ul);
+    for (int k : nodes) mask[(unsigned long)k / bits] |= 1ul << ((unsigned long)k % bits);
+    const int MPOL_PREFERRED_ = 1, MPOL_INTERLEAVE_ = 3;
+    return syscall(SYS_mbind, p, bytes, nodes.size() > 1 ? MPOL_INTERLEAVE_ : MPOL_PREFERRED_, mask.data(), max_node + 2, 0u) == 0;
+}
 class HostPool {
   public:
-    HostBlock get(size_t bytes) {
+    HostBlock get(size_t bytes, bool interleave = false) {
         if (bytes == 0) return HostBlock{};
         {
             std::lock_guard<std::mutex> lk(mu_);
             size_t best = free_.size();
             for (size_t i = 0; i < free_.size(); i++)
-                if (free_[i].cap >= bytes && free_[i].cap <= 2 * bytes + (1u << 20) &&
+                if (free_[i].cap >= bytes && free_[i].cap <= 2 * bytes + (1u << 20) && free_[i].interleaved == interleave &&
                     (best == free_.size() || free_[i].cap < free_[best].cap))
                     best = i;
             if (best != free_.size()) {
@@ -125,6 +189,8 @@ class HostPool {
         if (bytes >= huge) {
             if (posix_memalign(&b.p, huge, b.cap) != 0) throw std::bad_alloc();
             madvise(b.p, b.cap, MADV_HUGEPAGE);
+            if (interleave) place_pages_near_devices(b.p, b.cap);  // (the flag is kept either way: it is the pool's key)
+            b.interleaved = interleave;
             // first touch in parallel: the kernel clears the pages on the faulting thread
             const unsigned nt = std::min<unsigned>({std::max(1u, std::thread::hardware_concurrency()), 16u,
                                                    (unsigned)(b.cap >> 26) + 1u});
@@ -157,8 +223,8 @@ class HostPool {
         release(b);
     }
     // blocks lent to a container that only knows the pointer (the vertex pools' allocator)
-    void* lease(size_t bytes) {
-        HostBlock b = get(bytes);
+    void* lease(size_t bytes, bool interleave = false) {
+        HostBlock b = get(bytes, interleave);
         std::lock_guard<std::mutex> lk(mu_);
         leased_[b.p] = b;
         return b.p;
@@ -2252,9 +2318,10 @@ struct SparseGather : SparseSink {
             const uint64_t total = band_base[nb];
             try {
                 out->len = total;
-                out->rows = g_host_pool.get(total * 8);
-                out->cols = g_host_pool.get(total * 8);
-                out->data = g_host_pool.get(total * isz);
+                // (written by every device of the call: pages on the memory nodes the devices hang off)
+                out->rows = g_host_pool.get(total * 8, true);
+                out->cols = g_host_pool.get(total * 8, true);
+                out->data = g_host_pool.get(total * isz, true);
                 ready = true;
             } catch (const std::bad_alloc&) {
                 failed = true;
@@ -2948,6 +3015,24 @@ void rz_sparse_free(rz_sparse* s) { delete s; }
 int rz_sparse_build_array(const rz_context* ctx, uint64_t n_bands, const uint64_t* counts, const uint64_t* rows,
                           const uint64_t* cols, const void* data, void* out, rz_stats* stats, char* err, size_t errlen) {
     return guarded(err, errlen, [&]() { rz::sparse_build_array(ctx, n_bands, counts, rows, cols, data, out, stats); });
+}
+
+void* rz_host_alloc(size_t bytes, char* err, size_t errlen) {
+    void* p = nullptr;
+    const int rc = guarded(err, errlen, [&]() {
+        if (bytes == 0) throw Error{RZ_VALUE_ERROR, "rz_host_alloc: zero bytes"};
+        int n = 0;
+        if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+            (void)cudaGetLastError();
+            throw Error{RZ_RUNTIME_ERROR, "No CUDA device available: librz_b200 has no CPU fallback."};
+        }
+        p = rz::g_host_pool.lease(std::max<size_t>(bytes, (size_t)2 << 20), true);
+    });
+    return rc == RZ_OK ? p : nullptr;
+}
+
+void rz_host_free(void* p) {
+    if (p) rz::g_host_pool.unlease(p);
 }
 
 int rz_device_count(void) {

@@ -82,6 +82,18 @@ int main(int argc, char** argv) {
         fprintf(stderr, "rz_rasterize_dense: %d %s\n", rc, err);
         return 17;
     }
+    /* the same burn into the library's page-locked host memory (rz_host_alloc) gives the same bytes */
+    uint8_t* pinned = (uint8_t*)rz_host_alloc(ri.nrows * ri.ncols, err, sizeof err);
+    if (!pinned) {
+        fprintf(stderr, "rz_host_alloc: %s\n", err);
+        return 18;
+    }
+    rc = rz_rasterize_dense(g, &ctx, pinned, &st, err, sizeof err);
+    if (rc != RZ_OK || memcmp(pinned, out, ri.nrows * ri.ncols) != 0) {
+        fprintf(stderr, "burn into rz_host_alloc memory: %d %s\n", rc, err);
+        return 19;
+    }
+    rz_host_free(pinned);
     unsigned long long hist[256] = {0}, sum = 0;
     for (uint64_t i = 0; i < ri.nrows * ri.ncols; i++) {
         hist[out[i]]++;

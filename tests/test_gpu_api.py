@@ -180,3 +180,38 @@ def test_flatten_and_upload_at_once_equals_the_two_step_route():
     e2, _ = core.rasterize_dense(big, ri2, "count", "uint16", 1, background=0)
     g2, s2 = core.rasterize_dense(big_dev, ri2, "count", "uint16", 1, background=0)
     assert np.array_equal(e2, g2) and s2["h2d_bytes"] <= 8
+
+
+def test_host_empty_outputs_are_recycled_page_locked_blocks(monkeypatch):
+    """rz_host_alloc / rz_host_free through core.host_empty: an array over library memory is filled by a call exactly
+    like a numpy array, large outputs are allocated there by default, and a freed block is handed out again."""
+    W, H = 700, 500
+    x, y, off = synth.star_polygons(41, 300, 8, 30, 40.0, W, H)
+    vals = (synth.splitmix_u(41, 300, 9) * 100).astype(np.int32)
+    g = core.Geoms.from_polygons(x, y, off)
+    ri = core.raster_info(None, shape=(H, W), extent=(0, 0, W, H))
+    ref, _ = core.rasterize_dense(g, ri, "max", "int32", vals, background=-1, out=np.empty((1, H, W), np.int32))
+    a = core.host_empty((1, H, W), "int32")
+    assert a.flags.writeable and a.flags.c_contiguous and a.shape == (1, H, W)
+    got, _ = core.rasterize_dense(g, ri, "max", "int32", vals, background=-1, out=a)
+    assert got is a and np.array_equal(ref, a)
+    addr = a.ctypes.data
+    del a, got
+    import gc
+
+    gc.collect()
+    b = core.host_empty((1, H, W), "int32")
+    assert b.ctypes.data == addr  # the block went back to the pool and came out again
+    del b
+    monkeypatch.setattr(core, "_HOST_EMPTY_MIN", 0)
+    auto, _ = core.rasterize_dense(g, ri, "max", "int32", vals, background=-1)
+    assert np.array_equal(ref, auto)
+    keep = auto[0, 10:20].copy()
+    view = auto[0, 10:20]
+    del auto
+    gc.collect()
+    assert np.array_equal(view, keep)  # a view keeps the block alive
+    soa = (np.arange(301, dtype=np.uint64), np.zeros(300, np.uint8), np.arange(301, dtype=np.uint64), off, x, y)
+    one, _ = core.rasterize_dense_soa(soa, ri, "max", "int32", vals, background=-1, devices=[0])
+    assert np.array_equal(ref, one)
+    assert core.host_empty((0, 5), "float32").shape == (0, 5)
