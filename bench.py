@@ -572,10 +572,14 @@ def run_dense_e2e(env, name, w):
     n_b = 1 if w["by"] is None else len(set(w["by"]))
     band, names = (None, None) if w["by"] is None else core.group_keys(w["by"])
     ri = core.raster_info(None, shape=(rows, cols), extent=(0.0, 0.0, float(cols), float(rows)))
-    # the caller-owned host raster: page-locked memory from the library's allocator (rz_host_alloc: recycled huge pages,
-    # interleaved over the host's memory nodes so that GPUs on either socket copy into it at the same rate)
-    h_np = core.host_empty((n_b, rows, cols), dtype)
-    h_out = torch.from_numpy(h_np)
+    # the caller-owned host raster: one page-locked array (cudaHostAlloc through torch; `--host-alloc rz` takes it from
+    # the library's own allocator, rz_host_alloc, instead)
+    if args.host_alloc == "rz":
+        h_np = core.host_empty((n_b, rows, cols), dtype)
+        h_out = torch.from_numpy(h_np)
+    else:
+        h_out = torch.empty((n_b, rows, cols), dtype=getattr(torch, np.dtype(dtype).name)).pin_memory()
+        h_np = h_out.numpy()
     devices = list(range(world))
     eng_flag = {"auto": 0, "records": _lib.FLAG_NO_TILE_ENGINE, "tiles": _lib.FLAG_FORCE_TILE_ENGINE}[args.engine]
     if world > 1:  # this process now drives every GPU: it may run on every core again
@@ -805,6 +809,17 @@ def run_b200(args):
     names = [args.workload] + [c for c in args.others.split(",") if c and c != "none" and c != args.workload]
     results = {}
     for name in names:
+        # every workload starts with an empty host pool: the page-locked blocks the previous one left behind (its 17 GB
+        # raster, its vertex pools) go back to the system here, outside every timed region
+        import gc
+
+        from rusterize_b200 import core as _core
+
+        gc.collect()
+        pooled = _core.host_trim(1 << 62)
+        _core.host_trim(0)
+        if env.rank == 0:
+            print(f"[bench] {name}: host pool held {pooled / 1e9:.2f} GB of free page-locked blocks, trimmed", file=sys.stderr)
         w = make_workload(name, args.scale)
         headline = name == args.workload
         if w["kind"] == "parcels":
@@ -903,6 +918,7 @@ def main():
     ap.add_argument("--tile-bytes", type=int, default=0)
     ap.add_argument("--engine", default="auto", choices=["auto", "records", "tiles"])
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--host-alloc", default="torch", choices=["torch", "rz"], help="who allocates the pinned host raster of the e2e arm")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -254,6 +254,12 @@ int rz_rasterize_dense_soa(const rz_geom_soa* soa, const rz_context* ctx, const 
  * hands them back, it does not unmap them.  Returns NULL with the reason in `err`. */
 void* rz_host_alloc(size_t bytes, char* err, size_t errlen);
 void rz_host_free(void* p);
+/* The library keeps freed page-locked blocks (vertex pools of freed geometry sets, freed sparse results, blocks given
+ * back with rz_host_free) for the next call, up to RZ_HOST_POOL_BYTES (default: a quarter of the machine's memory,
+ * 8 - 64 GiB; the oldest blocks go first when it is full).  rz_host_trim returns free blocks to the system until at
+ * most `keep_bytes` stay pooled - between jobs of different shapes, or before handing memory to another consumer -
+ * and returns the bytes still pooled. */
+uint64_t rz_host_trim(uint64_t keep_bytes);
 
 int rz_device_count(void);
 const char* rz_version(void);

@@ -204,6 +204,7 @@ unsafe extern "C" {
                                  errlen: usize) -> c_int;
     pub fn rz_host_alloc(bytes: usize, err: *mut c_char, errlen: usize) -> *mut c_void;
     pub fn rz_host_free(p: *mut c_void);
+    pub fn rz_host_trim(keep_bytes: u64) -> u64;
     pub fn rz_device_count() -> c_int;
     pub fn rz_version() -> *const c_char;
     pub fn rz_abi_layout(out: *mut u64, n: c_int) -> c_int;

@@ -124,6 +124,7 @@ SYMBOLS = {
                                         C.c_void_p, C.c_void_p, C.POINTER(Stats)] + _ERR),
     "rz_host_alloc": (C.c_void_p, [C.c_size_t, C.c_char_p, C.c_size_t]),
     "rz_host_free": (None, [C.c_void_p]),
+    "rz_host_trim": (C.c_uint64, [C.c_uint64]),
     "rz_device_count": (C.c_int, []),
     "rz_version": (C.c_char_p, []),
     "rz_abi_layout": (C.c_int, [C.POINTER(C.c_uint64), C.c_int]),

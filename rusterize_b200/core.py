@@ -268,6 +268,11 @@ def host_empty(shape, dtype):
     return np.frombuffer(buf, dtype=dt).reshape(shape)
 
 
+def host_trim(keep_bytes=0):
+    """Return the library's free page-locked blocks to the system until at most keep_bytes stay pooled."""
+    return int(lib().rz_host_trim(int(keep_bytes)))
+
+
 _HOST_EMPTY_MIN = 64 << 20  # outputs from this size on are allocated page-locked (smaller ones: plain numpy)
 
 

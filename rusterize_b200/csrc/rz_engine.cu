@@ -63,6 +63,8 @@ static void set_err(char* err, size_t n, const std::string& m) {
 // ------------------------------------------------------------------------------------------------
 // device memory
 // ------------------------------------------------------------------------------------------------
+static bool trim_device_pool_current();  // frees the pooled geometry blocks of the current device (defined below)
+
 struct DevBuf {
     void* p = nullptr;
     size_t cap = 0;
@@ -75,7 +77,12 @@ struct DevBuf {
         if (cudaMalloc(&p, want) != cudaSuccess) {
             (void)cudaGetLastError();
             want = bytes;
-            CUDA_TRY(cudaMalloc(&p, want));
+            if (cudaMalloc(&p, want) != cudaSuccess) {
+                (void)cudaGetLastError();
+                p = nullptr;
+                trim_device_pool_current();
+                CUDA_TRY(cudaMalloc(&p, want));
+            }
         }
         cap = want;
     }
@@ -212,15 +219,42 @@ class HostPool {
     }
     void put(HostBlock b) {
         if (!b.p) return;
+        std::vector<HostBlock> evicted;
+        bool kept = false;
         {
             std::lock_guard<std::mutex> lk(mu_);
-            if (b.cap >= ((size_t)2 << 20) && pooled_ + b.cap <= limit()) {
+            if (b.cap >= ((size_t)2 << 20) && b.cap <= limit()) {
+                // a full pool gives up its oldest blocks (free_ is in order of return): the block handed back last is
+                // the one the next call of the same shape asks for
+                while (pooled_ + b.cap > limit() && !free_.empty()) {
+                    evicted.push_back(free_.front());
+                    pooled_ -= free_.front().cap;
+                    free_.erase(free_.begin());
+                }
                 free_.push_back(b);
                 pooled_ += b.cap;
-                return;
+                kept = true;
             }
         }
-        release(b);
+        for (auto& e : evicted) release(e);
+        if (!kept) release(b);
+    }
+    // give the free blocks back to the system until at most keep_bytes stay pooled (oldest first)
+    void trim(size_t keep_bytes) {
+        std::vector<HostBlock> evicted;
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            while (pooled_ > keep_bytes && !free_.empty()) {
+                evicted.push_back(free_.front());
+                pooled_ -= free_.front().cap;
+                free_.erase(free_.begin());
+            }
+        }
+        for (auto& e : evicted) release(e);
+    }
+    size_t pooled() {
+        std::lock_guard<std::mutex> lk(mu_);
+        return pooled_;
     }
     // blocks lent to a container that only knows the pointer (the vertex pools' allocator)
     void* lease(size_t bytes, bool interleave = false) {
@@ -285,6 +319,88 @@ static const bool g_pinned_hooks_set = []() {
     return true;
 }();
 
+// Device blocks of freed geometry sets, kept per device for the next set of about the same size: a one-shot call
+// (flatten -> upload -> burn -> free) otherwise pays a cudaMalloc and a cudaFree every time, and both go through the
+// driver's global lock - measured on shared boxes as stalls of tens to hundreds of milliseconds around a 3 ms call,
+// and serialising the host threads of a multi-device call.  RZ_DEVICE_POOL_BYTES caps what is kept per device
+// (default 8 GiB, oldest blocks go first); DevBuf::ensure and alloc_device_geoms empty the pool and retry when a
+// cudaMalloc fails.
+class DeviceBlockPool {
+  public:
+    void* get(int dev, size_t bytes, size_t* cap) {
+        std::lock_guard<std::mutex> lk(mu_);
+        auto& v = free_[dev];
+        size_t best = v.size();
+        for (size_t i = 0; i < v.size(); i++)
+            if (v[i].cap >= bytes && v[i].cap <= 2 * bytes + (1u << 20) && (best == v.size() || v[i].cap < v[best].cap)) best = i;
+        if (best == v.size()) return nullptr;
+        void* p = v[best].p;
+        *cap = v[best].cap;
+        pooled_[dev] -= v[best].cap;
+        v.erase(v.begin() + best);
+        return p;
+    }
+    // the caller has made sure that no work still uses the block (cudaDeviceSynchronize, as cudaFree would)
+    void put(int dev, void* p, size_t cap) {
+        std::vector<Blk> evicted;
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            auto& v = free_[dev];
+            size_t& pooled = pooled_[dev];
+            if (cap <= limit()) {
+                while (pooled + cap > limit() && !v.empty()) {
+                    evicted.push_back(v.front());
+                    pooled -= v.front().cap;
+                    v.erase(v.begin());
+                }
+                v.push_back(Blk{p, cap});
+                pooled += cap;
+                p = nullptr;
+            }
+        }
+        for (auto& e : evicted) cudaFree(e.p);
+        if (p) cudaFree(p);
+        (void)cudaGetLastError();
+    }
+    // cudaFree every pooled block of the CURRENT device `dev`; returns whether anything was freed
+    bool trim(int dev) {
+        std::vector<Blk> evicted;
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            evicted.swap(free_[dev]);
+            pooled_[dev] = 0;
+        }
+        for (auto& e : evicted) cudaFree(e.p);
+        (void)cudaGetLastError();
+        return !evicted.empty();
+    }
+
+  private:
+    struct Blk {
+        void* p;
+        size_t cap;
+    };
+    static size_t limit() {
+        static const size_t v = []() -> size_t {
+            if (const char* e = std::getenv("RZ_DEVICE_POOL_BYTES")) return (size_t)std::strtoull(e, nullptr, 10);
+            return (size_t)8 << 30;
+        }();
+        return v;
+    }
+    std::mutex mu_;
+    std::map<int, std::vector<Blk>> free_;
+    std::map<int, size_t> pooled_;
+};
+static DeviceBlockPool& g_device_pool = *new DeviceBlockPool();
+static bool trim_device_pool_current() {
+    int dev = -1;
+    if (cudaGetDevice(&dev) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return false;
+    }
+    return g_device_pool.trim(dev);
+}
+
 struct DeviceGeoms {
     int dev = 0;
     // every array below lives in ONE device allocation (a cudaMalloc per array made a fresh geometry set pay ~20
@@ -304,11 +420,14 @@ struct DeviceGeoms {
     uint32_t* part_vbeg = nullptr;
     uint32_t* part_vend = nullptr;
     size_t bytes = 0;
+    size_t block_cap = 0;
     ~DeviceGeoms() {
+        if (!block) return;
         int prev = -1;
         if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
         cudaSetDevice(dev);
-        cudaFree(block);
+        cudaDeviceSynchronize();  // (what cudaFree implies: no kernel of any stream still reads the block)
+        g_device_pool.put(dev, block, block_cap);
         if (prev >= 0) cudaSetDevice(prev);
         (void)cudaGetLastError();
     }
@@ -508,7 +627,16 @@ static void alloc_device_geoms(const rz_geoms* g, DeviceGeoms* d) {
         const size_t o_kind = reserve(n_parts, 1), o_geom = reserve(n_parts, 4), o_xlo = reserve(n_parts, 8),
                      o_xhi = reserve(n_parts, 8), o_ylo = reserve(n_parts, 8), o_yhi = reserve(n_parts, 8),
                      o_vb = reserve(n_parts, 4), o_ve = reserve(n_parts, 4);
-        CUDA_TRY(cudaMalloc(&d->block, total));
+        d->block = g_device_pool.get(d->dev, total, &d->block_cap);
+        if (!d->block) {
+            if (cudaMalloc(&d->block, total) != cudaSuccess) {
+                (void)cudaGetLastError();
+                d->block = nullptr;
+                g_device_pool.trim(d->dev);
+                CUDA_TRY(cudaMalloc(&d->block, total));
+            }
+            d->block_cap = total;
+        }
         char* base = (char*)d->block;
         for (int k = 0; k < 3; k++) {
             d->x[k] = (double*)(base + o_x[k]);
@@ -2809,6 +2937,11 @@ static void one_shot_rows(const rz_geom_soa* soa, const rz_context* ctx, int dev
             c.row_begin = a0;
             c.row_end = a1;
             const rz::DenseExtra ex{rows, a0 - r0};
+            if (n_runs == 1) {  // nothing to overlap with: burn on the calling thread
+                rz::rasterize_dense(g.get(), &c, out, &S, &ex);
+                have = true;
+                break;
+            }
             burn = std::async(std::launch::async, [g, c, ex, out, device]() {
                 rz::bind_thread_near_device(device);
                 rz_stats st;
@@ -3033,6 +3166,12 @@ void* rz_host_alloc(size_t bytes, char* err, size_t errlen) {
 
 void rz_host_free(void* p) {
     if (p) rz::g_host_pool.unlease(p);
+}
+
+uint64_t rz_host_trim(uint64_t keep_bytes) {
+    rz::DeviceGuard guard;
+    rz::g_host_pool.trim((size_t)keep_bytes);
+    return (uint64_t)rz::g_host_pool.pooled();
 }
 
 int rz_device_count(void) {
