@@ -37,6 +37,16 @@ def test_no_cpu_fallback():
     ri = core.raster_info(g, shape=(4, 4))
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         core.rasterize_dense(g, ri)
+    # the one-shot call, the sparse call and the page-locked allocator fail the same way
+    soa = (np.arange(2, dtype=np.uint64), np.zeros(1, np.uint8), np.arange(2, dtype=np.uint64),
+           np.array([0, 5], np.uint64), np.array([0.0, 4, 4, 0, 0]), np.array([0.0, 0, 4, 4, 0]))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        core.rasterize_dense_soa(soa, ri, devices=[0])
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        core.rasterize_sparse(g, ri)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        core.host_empty((1 << 20,), "float32")
+    assert core.host_trim(0) == 0  # (nothing pooled, nothing to give back: works without a device)
 
 
 def test_flatten_parts_and_pooling():
