@@ -283,3 +283,18 @@ def test_band_shard_straight_from_soa_equals_shard_of_the_flattened_set():
                         assert np.array_equal(u, v, equal_nan=True)
         finally:
             del os.environ["RZ_PARSE_THREADS"]
+
+
+def test_band_shard_from_soa_keeps_parts_with_non_finite_ordinates_everywhere():
+    """A part with a NaN ordinate has no usable y-extent: the straight-from-arrays shard keeps it in every band (a
+    superset never changes a band's pixels - the part burns only where its finite edges are), the two-step shard cuts
+    it by the extent of its finite vertices.  Both keep every finite part a band needs, in order."""
+    x = np.array([1, 3, 3, 1, 1, 5, 7, 7, 5, 5.0])
+    y = np.array([1, 1, 3, 3, 1, 90, 90, np.nan, 95, 90.0])
+    soa = (np.arange(3, dtype=np.uint64), np.zeros(2, np.uint8), np.arange(3, dtype=np.uint64),
+           np.array([0, 5, 10], np.uint64), x, y)
+    ri = core.raster_info(None, shape=(100, 10), extent=(0, 0, 10, 100))
+    full = core.Geoms.from_soa(*soa)
+    for r0, r1, two_step, straight in [(0, 10, [1], [1]), (50, 60, [], [1]), (90, 100, [0], [0, 1])]:
+        assert list(full.row_shard(ri, r0, r1).parts()[1]) == two_step
+        assert list(core.Geoms.from_soa_rows(soa, ri, r0, r1).parts()[1]) == straight
