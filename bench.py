@@ -655,7 +655,29 @@ def run_dense_e2e(env, name, w):
             del bufs
         except Exception as e:  # the probe must never take the bench down
             ceiling = {"error": str(e)[:200]}
+    # the same call into a PAGEABLE destination, freshly allocated each time - what a binding that allocates its own
+    # array (ndarray's Array3 in the Rust shim) hands over: the library drains the device through two page-locked
+    # bounce blocks with host copy threads instead of letting the driver stage the copy
+    pageable = None
+    if name == args.workload and not args.no_pageable:
+        flat_out = None
+        del h_out, h_np
+        try:
+            each, same = [], True
+            for _ in range(2):
+                dst = np.empty((n_b, rows, cols), dtype)
+                t0 = time.perf_counter()
+                core.rasterize_dense_soa(w["soa"], ri, fun, dtype, w["field"], None, band, n_b, bg, out=dst, devices=devices,
+                                         flags=eng_flag)
+                each.append(round((time.perf_counter() - t0) * 1e3, 1))
+                same = same and bool(np.array_equal(dst[:, a0:rows], tail_one_shot, equal_nan=True))
+                del dst
+            pageable = {"ms_each_call": each, "last_rows_equal_the_pinned_run": same,
+                        "note": "destination = np.empty (fresh pageable pages) per call; page faults of the destination included"}
+        except Exception as e:  # never take the bench down
+            pageable = {"error": str(e)[:200]}
     return {"value": n_b * rows * cols / (e_ms / 1e3) / 1e6, "unit": "Mpixel/s", "ms_per_step": e_ms, "host_d2h_ceiling": ceiling,
+            "pageable_destination": pageable,
             "h2d_bytes_per_step": int(st_c["h2d_bytes"]), "d2h_bytes_per_step": int(st_last["d2h_bytes"]), "steps": n_e2e,
             "includes": "ONE library call from host coordinate arrays to the pinned host raster (rz_rasterize_dense_soa): every "
                         "device flattens the parts of its row band into page-locked pools with the H2D overlapped, burns, "
@@ -918,6 +940,7 @@ def main():
     ap.add_argument("--tile-bytes", type=int, default=0)
     ap.add_argument("--engine", default="auto", choices=["auto", "records", "tiles"])
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-pageable", action="store_true", help="skip the e2e variant that writes a pageable destination")
     ap.add_argument("--host-alloc", default="torch", choices=["torch", "rz"], help="who allocates the pinned host raster of the e2e arm")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

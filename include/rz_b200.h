@@ -245,7 +245,10 @@ int rz_rasterize_dense_soa(const rz_geom_soa* soa, const rz_context* ctx, const 
                            void* out, rz_stats* stats, rz_stats* per_device, char* err, size_t errlen);
 
 /* Device plumbing */
-/* Page-locked host memory for caller-owned outputs (and anything else handed to the library): huge-page backed,
+/* Where the reference allocates its output with Array3::from_elem (RasterInfo::build_raster,
+ * rust/src/geo/raster.rs:23-28), a caller of this library can take the array from here instead (the background fill
+ * is fused into the burn, so the memory needs no initialisation).
+ * Page-locked host memory for caller-owned outputs (and anything else handed to the library): huge-page backed,
  * faulted in by several threads, registered with CUDA as portable pinned memory, and placed on the memory nodes the
  * GPUs in use hang off (env RZ_DEVICES, else every visible device): interleaved over them when there are several,
  * so that devices attached to either socket copy into it at the same rate (a raster living on one socket is written

@@ -453,7 +453,7 @@ struct DeviceCtx {
     cudaEvent_t ev_last = nullptr;  // end of the previous call on this device (scratch buffers are shared by all streams)
     bool ev_last_valid = false;
     cudaStream_t last_stream = nullptr;
-    cudaEvent_t ev_filled[2], ev_copied[2], ev_d2h[2];
+    cudaEvent_t ev_filled[2], ev_copied[2], ev_d2h[2], ev_bounce[2];
     DevBuf win_out2, win_t;
 };
 
@@ -492,6 +492,7 @@ static DeviceCtx& device_ctx(int dev) {
         CUDA_TRY(cudaEventCreateWithFlags(&c->ev_filled[k], cudaEventDisableTiming));
         CUDA_TRY(cudaEventCreateWithFlags(&c->ev_copied[k], cudaEventDisableTiming));
         CUDA_TRY(cudaEventCreate(&c->ev_d2h[k]));
+        CUDA_TRY(cudaEventCreateWithFlags(&c->ev_bounce[k], cudaEventDisableTiming));
     }
     DeviceCtx& ref = *c;
     g_ctx[dev] = std::move(c);
@@ -911,6 +912,35 @@ struct WallClock {
     float ms() const { return std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count(); }
 };
 
+// Copy out of a page-locked bounce block into the caller's pageable array with several threads: the destination's
+// pages are usually untouched (a fresh Vec / numpy array), so the copy is bound by page faults, which scale with
+// threads; one thread reaches 3-5 GB/s, the link delivers 55.
+static void parallel_copy(char* dst, const char* src, size_t bytes, unsigned threads) {
+    const size_t grain = (size_t)4 << 20;
+    const unsigned nt = (unsigned)std::max<size_t>(1, std::min<size_t>(threads, (bytes + grain - 1) / grain));
+    if (nt == 1) {
+        std::memcpy(dst, src, bytes);
+        return;
+    }
+    std::vector<std::thread> th;
+    for (unsigned t = 1; t < nt; t++) {
+        const size_t lo = bytes / nt * t & ~(size_t)4095, hi = t + 1 == nt ? bytes : bytes / nt * (t + 1) & ~(size_t)4095;
+        th.emplace_back([=]() { std::memcpy(dst + lo, src + lo, hi - lo); });
+    }
+    std::memcpy(dst, src, nt > 1 ? (bytes / nt & ~(size_t)4095) : bytes);
+    for (auto& x : th) x.join();
+}
+
+// is `p` ordinary (pageable) host memory, i.e. neither page-locked / registered nor managed?
+static bool is_pageable_host(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return true;
+    }
+    return a.type == cudaMemoryTypeUnregistered;
+}
+
 static void rasterize_dense(rz_geoms* g, const rz_context* ctx, void* out, rz_stats* st, const DenseExtra* ex = nullptr) {
     const WallClock wall;
     const rz_raster_info& ri = ctx->raster_info;
@@ -1059,6 +1089,41 @@ static void rasterize_dense(rz_geoms* g, const rz_context* ctx, void* out, rz_st
     // Host output: windows are rendered into two staging buffers in turn; the copy of a finished window runs
     // on the copy stream while the next window is computed (PCIe D2H is the longest phase of an end-to-end call).
     uint32_t n_staged = 0;
+    // A pageable destination (the Array3 / numpy array a binding allocated itself): cudaMemcpyAsync into it is a
+    // synchronous, driver-staged copy at a fraction of the link rate.  Large rasters therefore go through two
+    // page-locked bounce blocks - the DMA of piece i+1 runs while host threads copy piece i into the caller's array
+    // (RZ_BOUNCE=0 turns it off, RZ_BOUNCE_MIN_BYTES moves the 64 MB threshold).
+    const size_t bounce_min = std::getenv("RZ_BOUNCE_MIN_BYTES") ? (size_t)std::strtoull(std::getenv("RZ_BOUNCE_MIN_BYTES"), nullptr, 10) : ((size_t)64 << 20);
+    const bool bounce = !out_dev && !rcb && !(std::getenv("RZ_BOUNCE") && std::atoi(std::getenv("RZ_BOUNCE")) == 0) &&
+                        (uint64_t)n_bands * shard_rows * ri.ncols * isz >= bounce_min && is_pageable_host(out);
+    const size_t BOUNCE_BYTES = std::getenv("RZ_BOUNCE_BYTES") ? std::max<size_t>(4096, (size_t)std::strtoull(std::getenv("RZ_BOUNCE_BYTES"), nullptr, 10)) : ((size_t)128 << 20);
+    HostBlock bounce_blk[2];
+    struct BounceGuard {
+        HostBlock* b;
+        ~BounceGuard() {
+            for (int i = 0; i < 2; i++) g_host_pool.put(b[i]);
+        }
+    } bounce_guard{bounce_blk};
+    unsigned bounce_threads = 8;
+    if (bounce) {
+        for (auto& b : bounce_blk) {
+            b = g_host_pool.get(BOUNCE_BYTES);
+            if (!b.pinned && cudaHostRegister(b.p, b.cap, cudaHostRegisterPortable) == cudaSuccess) b.pinned = true;
+            else (void)cudaGetLastError();
+        }
+        const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+        // the copy out is bound by page faults on the fresh destination, which scale with threads (config 4, 16
+        // cores: 8 threads 730 ms, 16 threads 625 ms for the raster's 17.2 GB); shards of a multi-device call share
+        bounce_threads = ex ? std::max(2u, std::min(16u, hw / 4)) : std::min(16u, hw);
+        if (const char* e = std::getenv("RZ_BOUNCE_THREADS")) bounce_threads = (unsigned)std::max(1, std::atoi(e));
+        // the destination is about to be written from end to end: ask for huge pages where it is not touched yet
+        const uintptr_t huge = (uintptr_t)2 << 20;
+        const size_t band_rows_all = ex ? ex->band_rows : shard_rows;
+        const uintptr_t a = ((uintptr_t)out + huge - 1) & ~(huge - 1),
+                        e = ((uintptr_t)out + (size_t)n_bands * band_rows_all * ri.ncols * isz) & ~(huge - 1);
+        const bool want_huge = !(std::getenv("RZ_BOUNCE_HUGEPAGE") && std::atoi(std::getenv("RZ_BOUNCE_HUGEPAGE")) == 0);
+        if (want_huge && e > a && (!ex || ex->row_off == 0)) (void)madvise((void*)a, e - a, MADV_HUGEPAGE);
+    }
     const int copy_streams = std::getenv("RZ_COPY_STREAMS") ? std::atoi(std::getenv("RZ_COPY_STREAMS")) : 1;  // 2: ~2 % faster when it works, but the NEXT call's upload then often runs at half speed (measured)
     auto stage_begin = [&](uint32_t rows) -> void* {  // staging buffer the window's kernels may write now
         DevBuf& b = (n_staged & 1) ? c.win_out2 : c.win_out;
@@ -1098,6 +1163,35 @@ static void rasterize_dense(rz_geoms* g, const rz_context* ctx, void* out, rz_st
         CUDA_TRY(cudaStreamWaitEvent(c.copy_stream, c.ev_filled[k], 0));
         if (n_staged == 0) CUDA_TRY(cudaEventRecord(c.ev_d2h[0], c.copy_stream));
         const size_t chunk = (size_t)rows * ri.ncols * isz;
+        if (bounce) {  // drain the window now: DMA piece i+1 into one bounce block while piece i leaves the other
+            struct Piece {
+                char* dst;
+                const char* src;
+                size_t n;
+            };
+            std::vector<Piece> pieces;
+            for (uint32_t b = 0; b < n_bands; b++) {
+                char* dst = (char*)out + ((size_t)b * (ex ? ex->band_rows : shard_rows) + (ex ? ex->row_off : 0) +
+                                          (w.r0 - shard_r0)) * ri.ncols * isz;
+                const char* src = (const char*)d_out + (size_t)b * chunk;
+                for (size_t o = 0; o < chunk; o += BOUNCE_BYTES) pieces.push_back(Piece{dst + o, src + o, std::min(BOUNCE_BYTES, chunk - o)});
+            }
+            auto issue = [&](size_t i) {
+                CUDA_TRY(cudaMemcpyAsync(bounce_blk[i & 1].p, pieces[i].src, pieces[i].n, cudaMemcpyDeviceToHost, c.copy_stream));
+                CUDA_TRY(cudaEventRecord(c.ev_bounce[i & 1], c.copy_stream));
+            };
+            if (!pieces.empty()) issue(0);
+            for (size_t i = 0; i < pieces.size(); i++) {
+                if (i + 1 < pieces.size()) issue(i + 1);  // (block (i+1)&1 was emptied by the host copy of piece i-1)
+                CUDA_TRY(cudaEventSynchronize(c.ev_bounce[i & 1]));
+                parallel_copy(pieces[i].dst, (const char*)bounce_blk[i & 1].p, pieces[i].n, bounce_threads);
+            }
+            CUDA_TRY(cudaEventRecord(c.ev_copied[k], c.copy_stream));
+            S.d2h_bytes += chunk * n_bands;
+            S.host_syncs += (uint32_t)pieces.size();
+            n_staged++;
+            return;
+        }
         // large slabs go out as two halves on two streams: two copy engines in flight fill the link more evenly
         const bool split = copy_streams >= 2 && chunk >= ((size_t)64 << 20);
         const size_t half = split ? (size_t)(rows / 2) * ri.ncols * isz : chunk;

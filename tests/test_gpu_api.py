@@ -215,3 +215,38 @@ def test_host_empty_outputs_are_recycled_page_locked_blocks(monkeypatch):
     one, _ = core.rasterize_dense_soa(soa, ri, "max", "int32", vals, background=-1, devices=[0])
     assert np.array_equal(ref, one)
     assert core.host_empty((0, 5), "float32").shape == (0, 5)
+
+
+@pytest.mark.parametrize("piece", ["4096", "100000", str(128 << 20)])
+def test_pageable_outputs_through_bounce_blocks(monkeypatch, piece):
+    """A pageable destination (what a binding's own Array3 / numpy array is) is filled through two page-locked bounce
+    blocks and host copy threads once it is large; forced here for small rasters, with pieces smaller than a row, a
+    few rows and the whole window: bands, a row window, row-band shards and the one-shot call all land bit-exact."""
+    monkeypatch.setenv("RZ_BOUNCE_MIN_BYTES", "0")
+    monkeypatch.setenv("RZ_BOUNCE_BYTES", piece)
+    monkeypatch.setenv("RZ_ALLOW_REPEATED_DEVICES", "1")
+    W, H = 517, 389
+    geoms = synth.mixed_geometries(43, 300, W, H, rho=40.0)
+    n = len(geoms)
+    by = [str(i % 3) for i in range(n)]
+    band, names = core.group_keys(by)
+    g = core.Geoms.from_wkb(geoms)
+    og = oracle.Geoms.from_wkb(geoms)
+    kw = dict(shape=(H, W), extent=(0, 0, W, H))
+    ri, ori = core.raster_info(g, **kw), oracle.raster_info(og, **kw)
+    vals = (np.arange(n) % 11 + 1).astype(np.float64)
+    exp, _ = oracle.rasterize_dense(og, ori, "sum", "float64", vals, None, by, np.nan)
+    out = np.full((3, H, W), 7.0)  # pageable
+    got, st = core.rasterize_dense(g, ri, "sum", "float64", vals, None, band, 3, np.nan, out=out)
+    assert np.array_equal(exp, got, equal_nan=True)
+    assert st["host_syncs"] > 1  # one wait per piece
+    win, _ = core.rasterize_dense(g, ri, "sum", "float64", vals, None, band, 3, np.nan, rows=(100, 333))
+    assert np.array_equal(exp[:, 100:333], win, equal_nan=True)
+    many, _ = core.rasterize_dense(g, ri, "sum", "float64", vals, None, band, 3, np.nan, devices=[0, 0, 0])
+    assert np.array_equal(exp, many, equal_nan=True)
+    one, _ = core.rasterize_dense_soa(synth.wkb_to_soa(geoms), ri, "sum", "float64", vals, None, band, 3, np.nan,
+                                      devices=[0, 0], out=np.empty((3, H, W)))
+    assert np.array_equal(exp, one, equal_nan=True)
+    monkeypatch.setenv("RZ_BOUNCE", "0")
+    plain, st0 = core.rasterize_dense(g, ri, "sum", "float64", vals, None, band, 3, np.nan, out=np.empty((3, H, W)))
+    assert np.array_equal(exp, plain, equal_nan=True)
