@@ -659,7 +659,7 @@ def run_dense_e2e(env, name, w):
     # array (ndarray's Array3 in the Rust shim) hands over: the library drains the device through two page-locked
     # bounce blocks with host copy threads instead of letting the driver stage the copy
     pageable = None
-    if name == args.workload and not args.no_pageable:
+    if name == args.workload and not args.no_pageable and world == 1:  # (measured on one GPU only)
         flat_out = None
         del h_out, h_np
         try:
