@@ -196,7 +196,11 @@ typedef struct rz_stats {
 } rz_stats;
 
 /* DenseArray::build (rust/src/rasterize.rs:71-116): out is [n_bands][rows][ncols] of ctx->dtype,
- * C-contiguous, host memory unless RZ_FLAG_OUT_ON_DEVICE. */
+ * C-contiguous, host memory unless RZ_FLAG_OUT_ON_DEVICE.  Host memory may be page-locked (rz_host_alloc,
+ * cudaHostAlloc, cudaHostRegister: row windows are copied straight into it at the link rate) or pageable (an array the
+ * binding allocated itself): rasters of 64 MB and more then leave the device through two page-locked bounce blocks
+ * and host copy threads instead of a driver-staged copy (env RZ_BOUNCE=0 restores the plain copy, RZ_BOUNCE_THREADS /
+ * RZ_BOUNCE_BYTES / RZ_BOUNCE_MIN_BYTES tune it). */
 int rz_rasterize_dense(rz_geoms* g, const rz_context* ctx, void* out, rz_stats* stats, char* err, size_t errlen);
 
 /* SparseArray::build (rust/src/rasterize.rs:118-157): every (row, col, value) write, per band, in
